@@ -1,0 +1,167 @@
+/*
+ * permutect_b200 C-ABI: the ArtifactModel hot path on NVIDIA B200 (sm_100a).
+ *
+ * The reference (broadinstitute/permutect) is pure Python/PyTorch and has no FFI; the boundary it
+ * exposes for this path is the Python surface of permutect/architecture/artifact_model.py
+ * (ArtifactModel.compute_batch_output :281, compute_batch_losses :299, calculate_features :239).
+ * Underneath that surface this library is what a maintainer would bind (ctypes stub in
+ * INTEGRATION.md).  Each entry point names the reference code it replaces.
+ *
+ * Conventions: plain pointers and sizes only.  Every pointer is a DEVICE pointer unless its name
+ * starts with h_.  The caller owns every buffer; the library allocates nothing and keeps no mutable
+ * global state.  All calls are stream-ordered on the cudaStream_t passed as `void* stream`
+ * (NULL = default stream), re-entrant across streams.  Return 0 on success, non-zero on error;
+ * pmt_last_error() returns a thread-local message.
+ *
+ * Weights: one flat fp32 buffer holding the MATERIALISED (constraint-applied) parameters in
+ * ArtifactModel.named_parameters() order; PmtModelDesc carries the offsets.
+ * Gradients come back in a flat buffer of the same layout.
+ */
+#ifndef PERMUTECT_B200_H
+#define PERMUTECT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PMT_ABI_VERSION 1
+#define PMT_MAX_MLP_OPS 16
+#define PMT_MAX_BLOCKS 12
+#define PMT_MAX_CNN_OPS 16
+#define PMT_MAX_DIM 64      /* widest per-read activation / layer width */
+#define PMT_MAX_INFO_DIM 128 /* widest info-feature input */
+#define PMT_MAX_FEAT 32     /* final feature dimension E */
+#define PMT_MAX_CLUSTERS 14 /* K; K+2 log-likelihood columns <= 16 */
+#define PMT_TILE_ROWS 128   /* reads per CTA tile */
+
+/* PmtLinearOp.flags */
+#define PMT_OP_POST_SELU 1   /* SELU applied to the output                      (mlp.py:61-62) */
+#define PMT_OP_SKIP_BEGIN 2  /* first layer of a DenseSkipBlock: input is SELU(x) (mlp.py:8-22) */
+#define PMT_OP_SKIP_END 4    /* last layer of a DenseSkipBlock: x <- x + alpha * y             */
+
+/* One nn.Linear of an MLP program (reference: permutect/architecture/mlp.py:25-76). */
+typedef struct PmtLinearOp {
+  int32_t in_dim, out_dim;
+  int32_t w_off, b_off;   /* offsets (floats) into the flat weight buffer; weight is [out][in] */
+  int32_t alpha_off;      /* DenseSkipBlock.alpha (valid when PMT_OP_SKIP_END) */
+  int32_t flags;
+} PmtLinearOp;
+
+/* PmtCnnOp.kind */
+#define PMT_CNN_CONV 1
+#define PMT_CNN_POOL 2
+#define PMT_CNN_LINEAR 3   /* after flatten; in_ch = channels*length, out_ch = out_features */
+/* PmtCnnOp.act */
+#define PMT_ACT_NONE 0
+#define PMT_ACT_SELU 1
+#define PMT_ACT_LEAKY_RELU 2
+
+/* One layer of DNASequenceConvolution (reference: dna_sequence_convolution.py:57-111).
+ * An activation that follows a conv (possibly after max-pools, with which any monotone activation
+ * commutes exactly) is folded into that conv's `act`. */
+typedef struct PmtCnnOp {
+  int32_t kind, in_ch, out_ch, ksize, stride, in_len, out_len, act;
+  int32_t w_off, b_off;   /* conv weight [out][in][k]; linear weight [out][in_ch] */
+} PmtCnnOp;
+
+/* Parameter offsets of one GatedRefAltMLPBlock (reference: gated_mlp.py:148-251). */
+typedef struct PmtBlockOffsets {
+  int32_t ln_w, ln_b;               /* norm (shared by ref and alt, quirk Q4) */
+  int32_t p1_ref_w, p1_ref_b, p1_alt_w, p1_alt_b;
+  int32_t alpha_ref, alpha_alt, beta_ref, beta_alt, gamma;
+  int32_t regularizer;              /* sgu.ref_regularizer [d_ffn/2] */
+  int32_t ln2_w, ln2_b;             /* sgu.norm */
+  int32_t reg_weight;               /* materialised exp(reg_weight.original); kernel adds 0.25 (gated_mlp.py:237) */
+  int32_t p2_ref_w, p2_ref_b, p2_alt_w, p2_alt_b;
+} PmtBlockOffsets;
+
+typedef struct PmtModelDesc {
+  int32_t abi_version;
+  int32_t n_read_features;   /* decoded width F = 8*7 + (read_row_bytes - 7) */
+  int32_t read_row_bytes;    /* bytes per compressed read (12) */
+  int32_t n_info_features, hap_len; /* hap_len = L, each variant has 2L haplotype codes */
+  int32_t d_read, d_info, d_seq, d_model, d_ffn, n_blocks, d_feat, n_clusters;
+  int32_t n_read_ops, n_info_ops, n_red_ops, n_cnn_ops;
+  PmtLinearOp read_ops[PMT_MAX_MLP_OPS];   /* read_embedding   (artifact_model.py:142) */
+  PmtLinearOp info_ops[PMT_MAX_MLP_OPS];   /* info_embedding   (artifact_model.py:147) */
+  PmtLinearOp red_ops[PMT_MAX_MLP_OPS];    /* reducer          (artifact_model.py:164) */
+  PmtCnnOp cnn_ops[PMT_MAX_CNN_OPS];       /* haplotypes_cnn   (artifact_model.py:152) */
+  PmtBlockOffsets blocks[PMT_MAX_BLOCKS];  /* ref_alt_reads_encoder (artifact_model.py:161) */
+  int32_t translation, rotation;           /* pre_clustering_transform: t[E], Q[E][E] (f = Q (y + t)) */
+  int32_t sigma_e, unit_ke, tau_k, logw_k, mu_k, emg_sigma_k, lambda_k; /* feature_clustering, materialised */
+  int32_t n_params;                        /* length of the flat buffer */
+} PmtModelDesc;
+
+/* PmtBatch.reads_kind / info_kind / hap_kind */
+#define PMT_READS_U8 0    /* compressed rows [R][read_row_bytes] (datum.py:27, batch.py:51-56) */
+#define PMT_READS_F32 1   /* decoded rows [R][F] float32 */
+#define PMT_READS_F16 2   /* decoded rows [R][F] float16 */
+#define PMT_F32 0
+#define PMT_F16 1
+#define PMT_I16 0
+#define PMT_I64 1
+
+/* One batch of ragged read sets, laid out as the reference's Batch (batch.py:41-62):
+ * all ref reads of all variants, then all alt reads.  Row n of the batch is source row
+ * read_indices[n] when read_indices != NULL (DownsampledBatch.get_reads_re, batch.py:458-459;
+ * indices are consumed verbatim, quirk Q1), else row n. */
+typedef struct PmtBatch {
+  int32_t n_variants;
+  int32_t reads_kind, info_kind, hap_kind;
+  int64_t n_rows;              /* total_ref + total_alt */
+  int64_t total_ref;
+  int64_t max_rows_per_variant;/* >= max_b(ref_count+alt_count); sizes the long-set workspace */
+  const void* reads;
+  const int64_t* read_indices; /* NULL or [n_rows] */
+  const int64_t* ref_off;      /* [B+1] exclusive prefix sums of ref counts */
+  const int64_t* alt_off;      /* [B+1] exclusive prefix sums of alt counts */
+  const void* info;            /* [B][info_stride], first n_info_features used */
+  int64_t info_stride;
+  const void* haplotypes;      /* [B][hap_stride], first 2*hap_len used; codes 0..4 */
+  int64_t hap_stride;
+} PmtBatch;
+
+/* Replaces BatchOutput (artifact_model.py:38-73) minus the balancer weights. Any pointer may be NULL. */
+typedef struct PmtOutputs {
+  float* logits_bk;       /* [B][K+2]  feature_clustering.py:82-119 */
+  float* logits_b;        /* [B]       20*tanh(raw/20), feature_clustering.py:121-135 */
+  float* outlier_logits_b;/* [B]       artifact_model.py:62-73 */
+  float* alt_means_be;    /* [B][E]    features_be, artifact_model.py:291 */
+  float* ref_means_be;    /* [B][E]    ref_features_be, artifact_model.py:292 */
+  float* info_seq_be;     /* [B][d_info+d_seq]  artifact_model.py:244-246 (ref_seq embedding = last d_seq columns) */
+  float* final_re;        /* [n_rows][E] per-read final features (calculate_features, artifact_model.py:261-265) */
+} PmtOutputs;
+
+/* Upstream gradients for pmt_backward (dL/d of the PmtOutputs fields that carry gradient). NULL = zero. */
+typedef struct PmtOutGrads {
+  const float* d_logits_bk;   /* [B][K+2] */
+  const float* d_alt_means_be;/* [B][E] */
+  const float* d_ref_means_be;/* [B][E] */
+} PmtOutGrads;
+
+const char* pmt_last_error(void);
+int pmt_abi_version(void);
+
+/* Bytes of device workspace pmt_forward / pmt_backward need for this model and batch shape. */
+size_t pmt_workspace_size(const PmtModelDesc* desc, const PmtBatch* batch, int for_backward);
+
+/* Forward: ArtifactModel.calculate_features + FeatureClustering.calculate_logits + set means
+ * (artifact_model.py:239-297). */
+int pmt_forward(const PmtModelDesc* desc, const float* weights, const PmtBatch* batch, const PmtOutputs* out,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward of pmt_forward (autograd of artifact_model.py:239-297): accumulates nothing, WRITES
+ * d_weights[n_params] (gradient w.r.t. the materialised flat weights). */
+int pmt_backward(const PmtModelDesc* desc, const float* weights, const PmtBatch* batch, const PmtOutGrads* grads,
+                 float* d_weights, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Batch.__init__ decode (batch.py:51-56, plain_text_data.py:510-511): compressed rows -> [R][F] float32. */
+int pmt_decode_reads(const uint8_t* reads_u8, int64_t n_rows, int32_t row_bytes, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PERMUTECT_B200_H */

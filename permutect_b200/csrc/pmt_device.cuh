@@ -1,0 +1,244 @@
+// Device-side building blocks shared by the forward and backward kernels (sm_100a).
+//
+// Data layout inside a CTA: a tile of up to TILE reads (rows) is held FEATURE-MAJOR in shared memory,
+// buf[f * LD + r], so that (a) per-row work (LayerNorm, gating, decode) has lane == row and is
+// bank-conflict free, and (b) the register-tiled FP32 GEMM reads 4 consecutive rows of one feature
+// as a single 16-byte LDS.  Weights of the GEMM being executed are staged in shared memory with
+// cp.async, double-buffered, from a packed image built once per call by pack_weights_kernel.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/permutect_b200.h"
+
+namespace pmt {
+
+constexpr int TILE = PMT_TILE_ROWS;  // rows (reads, or variants in the per-variant kernels) per CTA tile
+constexpr int LD = TILE + 4;         // row stride of the feature-major activation buffers (floats)
+constexpr int NTHREADS = 256;
+constexpr int NWARPS = NTHREADS / 32;
+constexpr int MAX_GEMM = 96;
+constexpr int GROUP_STRIDE = 8;      // floats per column group in a packed weight image row
+
+constexpr float SELU_ALPHA = 1.6732632423543772848170429916717f;
+constexpr float SELU_SCALE = 1.0507009873554804934193349852946f;
+constexpr float LN_EPS = 1e-5f;
+constexpr float LOG_2PI = 1.8378770664093453f;
+
+// One staged GEMM: Y[n][r] = sum_k W[n][k] X[k][r] + b[n].  The packed image is [K][G][8] floats
+// (column n lives at group n / NT, slot n % NT; unused slots are zero).  `dual` ops carry a second
+// image/bias for alt rows (proj1/proj2 of the gated block, gated_mlp.py:165-171).
+struct GemmOp {
+  int K, N, G, NT;
+  int img_off;     // float offset of the (ref) image inside the packed buffer; alt image follows it
+  int img_floats;  // floats staged for this op (both images when dual)
+  int w_off, b_off, w_alt_off, b_alt_off;  // flat-weight offsets; *_alt_off < 0 when not dual
+};
+
+struct Plan {
+  PmtModelDesc d;
+  int n_gemm;
+  int read_g0, info_g0, red_g0, blk_g0;  // first GemmOp of each program; block b uses blk_g0 + 2b (+1)
+  int img_total;                         // floats in the packed image buffer
+  int stage_floats;                      // largest img_floats of the read-path ops (sizes the stage buffers)
+  int info_stage_floats;
+  int sum_w;                             // width of the per-variant sum scratch: max(d_ffn/2, d_feat)
+  int claim_variants;                    // variants claimed per scheduling step
+  GemmOp gemm[MAX_GEMM];
+};
+
+struct CnnGeom {
+  int vt;                        // variants per CTA pass
+  int lp[PMT_MAX_CNN_OPS + 1];   // padded per-variant length of the activation entering op i (lp[n] = after last)
+  int img_off[PMT_MAX_CNN_OPS];  // conv image offsets (floats) inside the conv image buffer
+  int img_total;
+  int buf_floats;                // floats per ping-pong activation buffer
+  int n_spatial;                 // ops before the first PMT_CNN_LINEAR
+};
+
+__device__ __forceinline__ float selu(float x) {
+  return SELU_SCALE * (x > 0.f ? x : SELU_ALPHA * (expf(x) - 1.f));
+}
+// d selu / dx expressed through the OUTPUT y = selu(x): y > 0 -> scale, else y + scale*alpha
+__device__ __forceinline__ float selu_grad_from_out(float y) {
+  return y > 0.f ? SELU_SCALE : y + SELU_SCALE * SELU_ALPHA;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// Double-buffered weight stage.  All control flow is CTA-uniform.
+struct Stage {
+  float* buf[2];
+  int resident[2];  // GemmOp index held (or in flight) in each buffer, -1 = none
+  int last;         // buffer most recently acquired
+  bool pending;     // a prefetch into buf[last ^ 1] has been issued and not yet acquired
+  const float* image;
+  const Plan* plan;
+
+  __device__ __forceinline__ void init(float* b0, float* b1, const float* img, const Plan* p) {
+    buf[0] = b0; buf[1] = b1; resident[0] = resident[1] = -1; last = 1; pending = false; image = img; plan = p;
+  }
+  __device__ __forceinline__ void issue(int slot, int g) {
+    const GemmOp& op = plan->gemm[g];
+    const float4* src = reinterpret_cast<const float4*>(image + op.img_off);
+    float4* dst = reinterpret_cast<float4*>(buf[slot]);
+    for (int i = threadIdx.x; i < op.img_floats / 4; i += NTHREADS) cp_async16(dst + i, src + i);
+    cp_async_commit();
+    resident[slot] = g;
+  }
+  // Start loading op g (if it is not already resident) into the buffer that is NOT in use.
+  __device__ __forceinline__ void prefetch(int g) {
+    if (g < 0 || pending || resident[0] == g || resident[1] == g) return;
+    issue(last ^ 1, g);
+    pending = true;
+  }
+  // Make op g available; contains a __syncthreads() (which also orders the preceding activation writes).
+  __device__ __forceinline__ const float* acquire(int g) {
+    int slot = resident[0] == g ? 0 : (resident[1] == g ? 1 : -1);
+    if (slot < 0) {
+      slot = last ^ 1;
+      cp_async_wait_all();
+      __syncthreads();  // nobody still reads buf[slot], no copy into it is in flight
+      issue(slot, g);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    last = slot;
+    pending = false;
+    return buf[slot];
+  }
+};
+
+enum Epilogue { EPI_STORE = 0, EPI_SELU = 1, EPI_RESIDUAL = 2 };
+
+template <int NT>
+__device__ __forceinline__ void gemm_tile_nt(const float* __restrict__ X, const GemmOp& op, const float* __restrict__ img,
+                                             const float* __restrict__ wflat, int ref_rows_padded, float* __restrict__ Y,
+                                             int epilogue, float alpha, int rows_used) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r0 = lane * 4;
+  if (r0 >= rows_used) return;
+  const bool is_alt = (op.w_alt_off >= 0) && (r0 >= ref_rows_padded);
+  const int wstride = op.G * GROUP_STRIDE;
+  const float* wimg = img + (is_alt ? op.K * wstride : 0);
+  const int boff = is_alt ? op.b_alt_off : op.b_off;
+  for (int g = warp; g < op.G; g += NWARPS) {
+    float acc[4][NT];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const int n = g * NT + j;
+      const float b = (boff >= 0 && n < op.N) ? __ldg(wflat + boff + n) : 0.f;
+      acc[0][j] = b; acc[1][j] = b; acc[2][j] = b; acc[3][j] = b;
+    }
+    const float* xp = X + r0;
+    const float* wp = wimg + g * GROUP_STRIDE;
+#pragma unroll 4
+    for (int k = 0; k < op.K; ++k) {
+      const float4 x = *reinterpret_cast<const float4*>(xp + k * LD);
+      float w[8];
+      const float4 w0 = *reinterpret_cast<const float4*>(wp + k * wstride);
+      w[0] = w0.x; w[1] = w0.y; w[2] = w0.z; w[3] = w0.w;
+      if (NT > 4) {
+        const float4 w1 = *reinterpret_cast<const float4*>(wp + k * wstride + 4);
+        w[4] = w1.x; w[5] = w1.y; w[6] = w1.z; w[7] = w1.w;
+      }
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        acc[0][j] = fmaf(x.x, w[j], acc[0][j]);
+        acc[1][j] = fmaf(x.y, w[j], acc[1][j]);
+        acc[2][j] = fmaf(x.z, w[j], acc[2][j]);
+        acc[3][j] = fmaf(x.w, w[j], acc[3][j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const int n = g * NT + j;
+      if (n < op.N) {
+        float4* yp = reinterpret_cast<float4*>(Y + n * LD + r0);
+        float4 v = make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]);
+        if (epilogue == EPI_SELU) {
+          v.x = selu(v.x); v.y = selu(v.y); v.z = selu(v.z); v.w = selu(v.w);
+        } else if (epilogue == EPI_RESIDUAL) {
+          const float4 o = *yp;
+          v.x = fmaf(alpha, v.x, o.x); v.y = fmaf(alpha, v.y, o.y); v.z = fmaf(alpha, v.z, o.z); v.w = fmaf(alpha, v.w, o.w);
+        }
+        *yp = v;
+      }
+    }
+  }
+}
+
+// Y <- epilogue(W X + b) over the tile.  X and Y must be different buffers unless epilogue is
+// EPI_RESIDUAL with Y disjoint from X.  Caller synchronises before consumers read Y.
+__device__ __forceinline__ void gemm_tile(const float* X, const GemmOp& op, const float* img, const float* wflat,
+                                          int ref_rows_padded, float* Y, int epilogue, float alpha, int rows_used) {
+  switch (op.NT) {
+    case 1: gemm_tile_nt<1>(X, op, img, wflat, ref_rows_padded, Y, epilogue, alpha, rows_used); break;
+    case 2: gemm_tile_nt<2>(X, op, img, wflat, ref_rows_padded, Y, epilogue, alpha, rows_used); break;
+    case 3: gemm_tile_nt<3>(X, op, img, wflat, ref_rows_padded, Y, epilogue, alpha, rows_used); break;
+    case 4: gemm_tile_nt<4>(X, op, img, wflat, ref_rows_padded, Y, epilogue, alpha, rows_used); break;
+    case 5: gemm_tile_nt<5>(X, op, img, wflat, ref_rows_padded, Y, epilogue, alpha, rows_used); break;
+    case 6: gemm_tile_nt<6>(X, op, img, wflat, ref_rows_padded, Y, epilogue, alpha, rows_used); break;
+    case 7: gemm_tile_nt<7>(X, op, img, wflat, ref_rows_padded, Y, epilogue, alpha, rows_used); break;
+    default: gemm_tile_nt<8>(X, op, img, wflat, ref_rows_padded, Y, epilogue, alpha, rows_used); break;
+  }
+}
+
+// dst[f][r] = selu(src[f][r]) for f < nf (all TILE rows; padding rows hold finite garbage)
+__device__ __forceinline__ void selu_copy(const float* src, float* dst, int nf) {
+  for (int i = threadIdx.x; i < nf * (TILE / 4); i += NTHREADS) {
+    const int f = i / (TILE / 4), q = i % (TILE / 4);
+    float4 v = *reinterpret_cast<const float4*>(src + f * LD + q * 4);
+    v.x = selu(v.x); v.y = selu(v.y); v.z = selu(v.z); v.w = selu(v.w);
+    *reinterpret_cast<float4*>(dst + f * LD + q * 4) = v;
+  }
+}
+__device__ __forceinline__ void copy_features(const float* src, float* dst, int nf) {
+  for (int i = threadIdx.x; i < nf * (TILE / 4); i += NTHREADS) {
+    const int f = i / (TILE / 4), q = i % (TILE / 4);
+    *reinterpret_cast<float4*>(dst + f * LD + q * 4) = *reinterpret_cast<const float4*>(src + f * LD + q * 4);
+  }
+}
+
+// Runs an MLP program (mlp.py:25-76) over the tile.  `cur` holds the input; b0/b1/b2 are the three
+// activation buffers (cur is one of them).  Returns the buffer holding the output.
+// next_after: GemmOp to prefetch while the last layer runs (-1 = none).
+__device__ __forceinline__ float* run_mlp(const Plan& P, const PmtLinearOp* ops, int n_ops, int g0, float* cur,
+                                          float* b0, float* b1, float* b2, Stage& stage, const float* wflat,
+                                          int rows_used, int next_after) {
+  float* res = nullptr;
+  for (int i = 0; i < n_ops; ++i) {
+    const PmtLinearOp& lop = ops[i];
+    const GemmOp& gop = P.gemm[g0 + i];
+    float* src = cur;
+    if (lop.flags & PMT_OP_SKIP_BEGIN) {
+      res = cur;
+      float* tmp = (b0 != cur) ? b0 : b1;
+      __syncthreads();  // producers of `cur` are done
+      selu_copy(cur, tmp, lop.in_dim);
+      src = tmp;
+    }
+    const float* img = stage.acquire(g0 + i);
+    stage.prefetch(i + 1 < n_ops ? g0 + i + 1 : next_after);
+    if (lop.flags & PMT_OP_SKIP_END) {
+      gemm_tile(src, gop, img, wflat, 0, res, EPI_RESIDUAL, __ldg(wflat + lop.alpha_off), rows_used);
+      cur = res;
+      res = nullptr;
+    } else {
+      float* dst = b0;
+      if (dst == src || dst == res) dst = b1;
+      if (dst == src || dst == res) dst = b2;
+      gemm_tile(src, gop, img, wflat, 0, dst, (lop.flags & PMT_OP_POST_SELU) ? EPI_SELU : EPI_STORE, 0.f, rows_used);
+      cur = dst;
+    }
+  }
+  return cur;
+}
+
+}  // namespace pmt

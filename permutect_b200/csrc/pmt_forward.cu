@@ -1,0 +1,848 @@
+// Forward kernels of the ArtifactModel hot path (sm_100a) and the forward half of the C-ABI.
+//
+//   pack_weights_kernel   flat materialised weights -> GEMM-ready packed images        (once per call)
+//   info_mlp_kernel       info_embedding MLP, one variant per row        (artifact_model.py:244)
+//   hap_cnn_kernel        one-hot haplotypes + DNASequenceConvolution    (artifact_model.py:245, batch.py:115-130)
+//   reads_forward_kernel  decode -> read_embedding -> concat -> gated ref/alt blocks -> reducer ->
+//                         rotation -> clustering head -> per-variant sums (artifact_model.py:243-297)
+#include <cstdio>
+#include <cstring>
+
+#include "pmt_device.cuh"
+#include "pmt_host.h"
+
+namespace pmt {
+
+// ------------------------------------------------------------------------------------------------
+// weight packing
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_weights_kernel(const __grid_constant__ Plan P, const float* __restrict__ w, float* __restrict__ image) {
+  const GemmOp& op = P.gemm[blockIdx.x];
+  const int per_image = op.K * op.G * GROUP_STRIDE;
+  const int n_images = op.w_alt_off >= 0 ? 2 : 1;
+  for (int idx = threadIdx.x; idx < per_image * n_images; idx += blockDim.x) {
+    const int which = idx / per_image, rem = idx % per_image;
+    const int k = rem / (op.G * GROUP_STRIDE), slot = rem % (op.G * GROUP_STRIDE);
+    const int grp = slot / GROUP_STRIDE, j = slot % GROUP_STRIDE;
+    const int n = grp * op.NT + j;
+    const int woff = which ? op.w_alt_off : op.w_off;
+    image[op.img_off + idx] = (j < op.NT && n < op.N) ? w[woff + n * op.K + k] : 0.f;
+  }
+}
+
+// conv weights [out][in][ks] -> image [(ci*ks + t)][G][8] with NT = 8
+__global__ void pack_conv_kernel(const __grid_constant__ Plan P, const __grid_constant__ CnnGeom Gm,
+                                 const float* __restrict__ w, float* __restrict__ image) {
+  const PmtCnnOp& op = P.d.cnn_ops[blockIdx.x];
+  if (op.kind != PMT_CNN_CONV) return;
+  const int G = (op.out_ch + 7) / 8;
+  const int total = op.in_ch * op.ksize * G * GROUP_STRIDE;
+  float* img = image + Gm.img_off[blockIdx.x];
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int kk = idx / (G * GROUP_STRIDE), slot = idx % (G * GROUP_STRIDE);
+    const int ci = kk / op.ksize, t = kk % op.ksize;
+    const int co = (slot / GROUP_STRIDE) * 8 + slot % GROUP_STRIDE;
+    img[idx] = co < op.out_ch ? w[op.w_off + (co * op.in_ch + ci) * op.ksize + t] : 0.f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// info MLP: rows of the tile are variants
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NTHREADS, 1)
+info_mlp_kernel(const __grid_constant__ Plan P, const float* __restrict__ wflat, const float* __restrict__ image,
+                const void* __restrict__ info, int info_kind, long long info_stride, int n_variants,
+                float* __restrict__ info_seq) {
+  extern __shared__ __align__(16) float smem[];
+  const int in_rows = P.d.n_info_features > PMT_MAX_DIM ? PMT_MAX_INFO_DIM : PMT_MAX_DIM;
+  float* b0 = smem;                       // input buffer (up to 128 features)
+  float* b1 = b0 + in_rows * LD;
+  float* b2 = b1 + PMT_MAX_DIM * LD;
+  float* st0 = b2 + PMT_MAX_DIM * LD;
+  float* st1 = st0 + P.info_stage_floats;
+  Stage stage;
+  stage.init(st0, st1, image, &P);
+  const int v0 = blockIdx.x * TILE;
+  const int nv = min(TILE, n_variants - v0);
+  const int I = P.d.n_info_features;
+  stage.prefetch(P.info_g0);
+  for (int idx = threadIdx.x; idx < TILE * I; idx += NTHREADS) {
+    const int r = idx / I, f = idx % I;
+    float v = 0.f;
+    if (r < nv) {
+      const long long off = (long long)(v0 + r) * info_stride + f;
+      v = info_kind == PMT_F16 ? __half2float(reinterpret_cast<const __half*>(info)[off])
+                               : reinterpret_cast<const float*>(info)[off];
+    }
+    b0[f * LD + r] = v;
+  }
+  float* out = run_mlp(P, P.d.info_ops, P.d.n_info_ops, P.info_g0, b0, b1, b2, b0, stage, wflat, TILE, -1);
+  __syncthreads();
+  const int w = P.d.d_info + P.d.d_seq;
+  for (int idx = threadIdx.x; idx < nv * P.d.d_info; idx += NTHREADS) {
+    const int r = idx / P.d.d_info, j = idx % P.d.d_info;
+    info_seq[(long long)(v0 + r) * w + j] = out[j * LD + r];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// haplotype CNN
+// ------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == PMT_ACT_SELU) return selu(x);
+  if (act == PMT_ACT_LEAKY_RELU) return x > 0.f ? x : 0.01f * x;
+  return x;
+}
+
+template <int KS>
+__device__ __forceinline__ void conv_units(const PmtCnnOp& op, const float* __restrict__ in, int in_ld, int lp_in,
+                                           float* __restrict__ out, int out_ld, int lp_out, const float* __restrict__ img,
+                                           const float* __restrict__ wflat, int vt) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = (op.out_ch + 7) / 8;
+  const int q_per_var = lp_out / 4;
+  const int n_q = vt * q_per_var;  // 4-row groups
+  const int q_blocks = (n_q + 31) / 32;
+  for (int unit = warp; unit < q_blocks * G; unit += NWARPS) {
+    const int g = unit % G, q = (unit / G) * 32 + lane;
+    if (q >= n_q) continue;
+    const int v = q / q_per_var, p0 = (q % q_per_var) * 4;
+    float acc[4][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int co = g * 8 + j;
+      const float b = co < op.out_ch ? __ldg(wflat + op.b_off + co) : 0.f;
+      acc[0][j] = b; acc[1][j] = b; acc[2][j] = b; acc[3][j] = b;
+    }
+    const float* xp = in + v * lp_in + p0;
+    const float* wp = img + g * GROUP_STRIDE;
+    const int wstride = G * GROUP_STRIDE;
+    for (int ci = 0; ci < op.in_ch; ++ci) {
+      float xw[12];
+      const float4 a = *reinterpret_cast<const float4*>(xp + ci * in_ld);
+      xw[0] = a.x; xw[1] = a.y; xw[2] = a.z; xw[3] = a.w;
+      if (KS > 1) {
+        const float4 b = *reinterpret_cast<const float4*>(xp + ci * in_ld + 4);
+        xw[4] = b.x; xw[5] = b.y; xw[6] = b.z; xw[7] = b.w;
+      }
+      if (KS > 5) {
+        const float4 c = *reinterpret_cast<const float4*>(xp + ci * in_ld + 8);
+        xw[8] = c.x; xw[9] = c.y; xw[10] = c.z; xw[11] = c.w;
+      }
+#pragma unroll
+      for (int t = 0; t < KS; ++t) {
+        const float* wr = wp + (ci * KS + t) * wstride;
+        const float4 w0 = *reinterpret_cast<const float4*>(wr);
+        const float4 w1 = *reinterpret_cast<const float4*>(wr + 4);
+        const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[0][j] = fmaf(xw[t], w[j], acc[0][j]);
+          acc[1][j] = fmaf(xw[t + 1], w[j], acc[1][j]);
+          acc[2][j] = fmaf(xw[t + 2], w[j], acc[2][j]);
+          acc[3][j] = fmaf(xw[t + 3], w[j], acc[3][j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int co = g * 8 + j;
+      if (co < op.out_ch) {
+        float4 o = make_float4(apply_act(acc[0][j], op.act), apply_act(acc[1][j], op.act),
+                               apply_act(acc[2][j], op.act), apply_act(acc[3][j], op.act));
+        *reinterpret_cast<float4*>(out + co * out_ld + v * lp_out + p0) = o;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+hap_cnn_kernel(const __grid_constant__ Plan P, const __grid_constant__ CnnGeom Gm, const float* __restrict__ wflat,
+               const float* __restrict__ conv_image, const void* __restrict__ haps, int hap_kind, long long hap_stride,
+               int n_variants, float* __restrict__ info_seq) {
+  extern __shared__ __align__(16) float smem[];
+  float* bufA = smem;
+  float* bufB = bufA + Gm.buf_floats;
+  float* wimg = bufB + Gm.buf_floats;
+  float* vec0 = wimg + Gm.img_total;  // [vt][256] linear-stack scratch
+  float* vec1 = vec0 + Gm.vt * 256;
+  for (int i = threadIdx.x; i < Gm.img_total / 4; i += NTHREADS)
+    reinterpret_cast<float4*>(wimg)[i] = __ldg(reinterpret_cast<const float4*>(conv_image) + i);
+  for (int i = threadIdx.x; i < 2 * Gm.buf_floats; i += NTHREADS) bufA[i] = 0.f;
+  __syncthreads();
+  const int L = P.d.hap_len;
+  const int vt = Gm.vt;
+  const int out_w = P.d.d_info + P.d.d_seq;
+  for (int v0 = blockIdx.x * vt; v0 < n_variants; v0 += gridDim.x * vt) {
+    const int nv = min(vt, n_variants - v0);
+    // one-hot input, batch.py:115-130: channel 2c + h is "haplotype h (0 ref, 1 alt) has code c at position p"
+    const int ld0 = vt * Gm.lp[0] + 8;
+    for (int idx = threadIdx.x; idx < nv * 2 * L; idx += NTHREADS) {
+      const int v = idx / (2 * L), hp = idx % (2 * L);
+      const long long off = (long long)(v0 + v) * hap_stride + hp;
+      const int code = hap_kind == PMT_I64 ? (int)reinterpret_cast<const long long*>(haps)[off]
+                                           : (int)reinterpret_cast<const short*>(haps)[off];
+      const int h = hp / L, p = hp % L;
+#pragma unroll
+      for (int c = 0; c < 5; ++c) bufA[(2 * c + h) * ld0 + v * Gm.lp[0] + p] = (code == c) ? 1.f : 0.f;
+    }
+    __syncthreads();
+    float* in = bufA;
+    float* out = bufB;
+    int i = 0;
+    for (; i < Gm.n_spatial; ++i) {
+      const PmtCnnOp& op = P.d.cnn_ops[i];
+      const int in_ld = vt * Gm.lp[i] + 8, out_ld = vt * Gm.lp[i + 1] + 8;
+      if (op.kind == PMT_CNN_CONV) {
+        const float* img = wimg + Gm.img_off[i];
+        switch (op.ksize) {
+          case 1: conv_units<1>(op, in, in_ld, Gm.lp[i], out, out_ld, Gm.lp[i + 1], img, wflat, vt); break;
+          case 2: conv_units<2>(op, in, in_ld, Gm.lp[i], out, out_ld, Gm.lp[i + 1], img, wflat, vt); break;
+          case 3: conv_units<3>(op, in, in_ld, Gm.lp[i], out, out_ld, Gm.lp[i + 1], img, wflat, vt); break;
+          case 4: conv_units<4>(op, in, in_ld, Gm.lp[i], out, out_ld, Gm.lp[i + 1], img, wflat, vt); break;
+          case 5: conv_units<5>(op, in, in_ld, Gm.lp[i], out, out_ld, Gm.lp[i + 1], img, wflat, vt); break;
+          case 6: conv_units<6>(op, in, in_ld, Gm.lp[i], out, out_ld, Gm.lp[i + 1], img, wflat, vt); break;
+          case 7: conv_units<7>(op, in, in_ld, Gm.lp[i], out, out_ld, Gm.lp[i + 1], img, wflat, vt); break;
+          case 8: conv_units<8>(op, in, in_ld, Gm.lp[i], out, out_ld, Gm.lp[i + 1], img, wflat, vt); break;
+          default: conv_units<9>(op, in, in_ld, Gm.lp[i], out, out_ld, Gm.lp[i + 1], img, wflat, vt); break;
+        }
+      } else {  // max pool, dna_sequence_convolution.py:75-77
+        const int total = op.in_ch * vt * op.out_len;
+        for (int idx = threadIdx.x; idx < total; idx += NTHREADS) {
+          const int c = idx / (vt * op.out_len), rem = idx % (vt * op.out_len);
+          const int v = rem / op.out_len, p = rem % op.out_len;
+          const float* src = in + c * in_ld + v * Gm.lp[i] + p * op.stride;
+          float m = src[0];
+          for (int t = 1; t < op.ksize; ++t) m = fmaxf(m, src[t]);
+          out[c * out_ld + v * Gm.lp[i + 1] + p] = m;
+        }
+      }
+      __syncthreads();
+      float* tmp = in; in = out; out = tmp;
+    }
+    // flatten (channel-major, dna_sequence_convolution.py:84-89) + linear stack
+    {
+      const PmtCnnOp& last = P.d.cnn_ops[Gm.n_spatial - 1];
+      const int C = Gm.n_spatial > 0 ? (last.kind == PMT_CNN_CONV ? last.out_ch : last.in_ch) : 10;
+      const int len = Gm.n_spatial > 0 ? last.out_len : L;
+      const int in_ld = vt * Gm.lp[Gm.n_spatial] + 8;
+      const float* vin = nullptr;
+      float* vout = vec0;
+      for (; i < P.d.n_cnn_ops; ++i) {
+        const PmtCnnOp& op = P.d.cnn_ops[i];
+        const bool is_last = (i + 1 == P.d.n_cnn_ops);
+        for (int idx = threadIdx.x; idx < nv * op.out_ch; idx += NTHREADS) {
+          const int v = idx / op.out_ch, n = idx % op.out_ch;
+          float acc = __ldg(wflat + op.b_off + n);
+          const float* wr = wflat + op.w_off + (long long)n * op.in_ch;
+          if (vin == nullptr) {
+            for (int c = 0; c < C; ++c)
+              for (int p = 0; p < len; ++p) acc = fmaf(__ldg(wr + c * len + p), in[c * in_ld + v * Gm.lp[Gm.n_spatial] + p], acc);
+          } else {
+            for (int k = 0; k < op.in_ch; ++k) acc = fmaf(__ldg(wr + k), vin[v * 256 + k], acc);
+          }
+          acc = apply_act(acc, op.act);
+          if (is_last) info_seq[(long long)(v0 + v) * out_w + P.d.d_info + n] = acc;
+          else vout[v * 256 + n] = acc;
+        }
+        __syncthreads();
+        vin = vout;
+        vout = (vout == vec0) ? vec1 : vec0;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// read path
+// ------------------------------------------------------------------------------------------------
+struct HeadConst {   // per-CTA constants of the clustering head (feature_clustering.py:82-119)
+  float sigma[PMT_MAX_FEAT];
+  float c_non, c_out;
+  float c_orth[PMT_MAX_CLUSTERS], inv_two_tau2[PMT_MAX_CLUSTERS];
+  float log_half_lambda[PMT_MAX_CLUSTERS], shift[PMT_MAX_CLUSTERS], inv_sqrt2_sigma[PMT_MAX_CLUSTERS],
+      half_lambda[PMT_MAX_CLUSTERS], two_mu_plus[PMT_MAX_CLUSTERS], logw[PMT_MAX_CLUSTERS];
+};
+
+struct TileMeta {
+  int nv;             // variants in the tile
+  int v0;             // first variant (global index)
+  int ref_pad;        // ref rows, padded to a multiple of 4; alt rows start here
+  int rows;           // ref_pad + alt rows
+  int next_v;
+  int rowvar[TILE];         // local variant of each row, -1 for padding
+  long long rowidx[TILE];   // batch row index of each row (position in [0, n_rows)), -1 for padding
+  int ref_start[TILE], ref_cnt[TILE], alt_start[TILE], alt_cnt[TILE];  // per local variant, tile row units
+};
+
+// exponentially_modified_gaussian.py:30-55
+__device__ __forceinline__ float logerfc(float z) {
+  if (z > 5.f) {
+    const float z2 = z * z, z4 = z2 * z2, z6 = z2 * z4;
+    return -z2 - logf(z * 1.7724538509055160273f) + log1pf(-1.f / (2.f * z2) + 3.f / (4.f * z4) - 15.f / (8.f * z6));
+  }
+  return logf(fmaxf(erfcf(z), 1.0e-12f));
+}
+
+__device__ __forceinline__ float logsumexp2(float a, float b) {
+  const float m = fmaxf(a, b);
+  return m + logf(expf(a - m) + expf(b - m));
+}
+
+struct ReadKernelArgs {
+  const float* wflat;
+  const float* image;
+  PmtBatch batch;
+  PmtOutputs out;
+  int* claim_counter;
+};
+
+// Per-variant sums of feature rows [f0, f0+nf) of `buf` over the ref rows and the alt rows
+// (ragged_sets.py:157-158).  out is [nv][2][sw].
+__device__ __forceinline__ void segment_sums(const TileMeta& M, const float* buf, int f0, int nf, float* out, int sw,
+                                             bool alt_only) {
+  const int sides = alt_only ? 1 : 2;
+  for (int idx = threadIdx.x; idx < M.nv * sides * nf; idx += NTHREADS) {
+    const int j = idx / (sides * nf), rem = idx % (sides * nf);
+    const int s = alt_only ? 1 : rem / nf, f = rem % nf;
+    const int start = s ? M.alt_start[j] : M.ref_start[j], cnt = s ? M.alt_cnt[j] : M.ref_cnt[j];
+    const float* p = buf + (f0 + f) * LD + start;
+    float sum = 0.f;
+    for (int i = 0; i < cnt; ++i) sum += p[i];
+    out[(j * 2 + s) * sw + f] = sum;
+  }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+reads_forward_kernel(const __grid_constant__ Plan P, const __grid_constant__ ReadKernelArgs A) {
+  extern __shared__ __align__(16) float smem[];
+  const PmtModelDesc& D = P.d;
+  float* X = smem;
+  float* T1 = X + PMT_MAX_DIM * LD;
+  float* T2 = T1 + PMT_MAX_DIM * LD;
+  float* st0 = T2 + PMT_MAX_DIM * LD;
+  float* st1 = st0 + P.stage_floats;
+  float* sums = st1 + P.stage_floats;            // [TILE][2][sum_w]
+  float* llsum = sums + TILE * 2 * P.sum_w;      // [TILE][2][16] (alt side used)
+  HeadConst* HC = reinterpret_cast<HeadConst*>(llsum + TILE * 2 * 16);
+  TileMeta* Mp = reinterpret_cast<TileMeta*>((reinterpret_cast<uintptr_t>(HC + 1) + 15) & ~uintptr_t(15));
+  TileMeta& M = *Mp;
+  __shared__ int s_claim;
+
+  const float* W = A.wflat;
+  const int tid = threadIdx.x;
+  const int row = tid & (TILE - 1), half = tid >> 7;
+  const int E = D.d_feat, K = D.n_clusters, Dm = D.d_model, H = D.d_ffn / 2;
+  const int B = A.batch.n_variants;
+
+  Stage stage;
+  stage.init(st0, st1, A.image, &P);
+
+  // head constants
+  if (tid == 0) {
+    float sum_log_sigma = 0.f;
+    for (int e = 0; e < E; ++e) { HC->sigma[e] = W[D.sigma_e + e]; sum_log_sigma += logf(W[D.sigma_e + e]); }
+    HC->c_non = -(E * 0.5f) * LOG_2PI - sum_log_sigma;
+    float sum_log_2sigma = 0.f;
+    for (int e = 0; e < E; ++e) sum_log_2sigma += logf(2.f * W[D.sigma_e + e]);
+    HC->c_out = -(E * 0.5f) * LOG_2PI - sum_log_2sigma;
+    for (int k = 0; k < K; ++k) {
+      const float tau = W[D.tau_k + k], lam = W[D.lambda_k + k], sg = W[D.emg_sigma_k + k], mu = W[D.mu_k + k];
+      HC->c_orth[k] = -((E - 1) * 0.5f) * LOG_2PI - (E - 1) * logf(tau);
+      HC->inv_two_tau2[k] = 2.f * tau * tau;  // divisor, kept as the reference writes it
+      HC->log_half_lambda[k] = logf(lam / 2.f);
+      HC->shift[k] = mu + lam * sg * sg;
+      HC->inv_sqrt2_sigma[k] = 1.41421356237309504880f * sg;  // divisor
+      HC->half_lambda[k] = lam / 2.f;
+      HC->two_mu_plus[k] = 2.f * mu + lam * sg * sg;
+      HC->logw[k] = W[D.logw_k + k];
+    }
+  }
+  for (int i = tid; i < 3 * PMT_MAX_DIM * LD; i += NTHREADS) X[i] = 0.f;
+  __syncthreads();
+
+  const long long total_ref = __ldg(A.batch.ref_off + B);  // == sum of ref counts
+  const int claim = P.claim_variants;
+
+  for (;;) {
+    if (tid == 0) s_claim = atomicAdd(A.claim_counter, 1);
+    __syncthreads();
+    const long long cv0 = (long long)s_claim * claim;
+    __syncthreads();
+    if (cv0 >= B) break;
+    const int cv1 = (int)min((long long)B, cv0 + claim);
+    int v_cur = (int)cv0;
+
+    while (v_cur < cv1) {
+      // ---------------- build the tile: greedily take whole variants while they fit ----------------
+      {
+        const long long r_base = __ldg(A.batch.ref_off + v_cur), a_base = __ldg(A.batch.alt_off + v_cur);
+        int fits = 0;
+        if (tid < TILE && v_cur + tid + 1 <= cv1) {
+          const long long nr = __ldg(A.batch.ref_off + v_cur + tid + 1) - r_base;
+          const long long na = __ldg(A.batch.alt_off + v_cur + tid + 1) - a_base;
+          fits = (((nr + 3) & ~3LL) + na <= TILE) ? 1 : 0;
+        }
+        const int nv = __syncthreads_count(fits);
+        if (nv == 0) {  // a single variant longer than the tile: not handled by this kernel
+          v_cur += 1;
+          continue;
+        }
+        if (tid < TILE) { M.rowvar[tid] = -1; M.rowidx[tid] = -1; }
+        __syncthreads();
+        const long long nr_tot = __ldg(A.batch.ref_off + v_cur + nv) - r_base;
+        const long long na_tot = __ldg(A.batch.alt_off + v_cur + nv) - a_base;
+        const int ref_pad = (int)((nr_tot + 3) & ~3LL);
+        if (tid < nv) {
+          const long long r0 = __ldg(A.batch.ref_off + v_cur + tid), r1 = __ldg(A.batch.ref_off + v_cur + tid + 1);
+          const long long a0 = __ldg(A.batch.alt_off + v_cur + tid), a1 = __ldg(A.batch.alt_off + v_cur + tid + 1);
+          M.ref_start[tid] = (int)(r0 - r_base); M.ref_cnt[tid] = (int)(r1 - r0);
+          M.alt_start[tid] = ref_pad + (int)(a0 - a_base); M.alt_cnt[tid] = (int)(a1 - a0);
+          for (int i = 0; i < (int)(r1 - r0); ++i) { M.rowvar[(int)(r0 - r_base) + i] = tid; M.rowidx[(int)(r0 - r_base) + i] = r0 + i; }
+          for (int i = 0; i < (int)(a1 - a0); ++i) {
+            M.rowvar[ref_pad + (int)(a0 - a_base) + i] = tid;
+            M.rowidx[ref_pad + (int)(a0 - a_base) + i] = total_ref + a0 + i;
+          }
+        }
+        if (tid == 0) { M.nv = nv; M.v0 = v_cur; M.ref_pad = ref_pad; M.rows = ref_pad + (int)na_tot; }
+        v_cur += nv;
+        __syncthreads();
+      }
+      const int rows_used = (M.rows + 3) & ~3;
+      const int ref_pad = M.ref_pad;
+      const long long my_idx = M.rowidx[row];
+      const int my_var = M.rowvar[row];
+      stage.prefetch(P.read_g0);
+
+      // ---------------- decode reads into T1 (batch.py:51-56; plain_text_data.py:510-511) ----------------
+      {
+        const int F = D.n_read_features;
+        long long src = -1;
+        if (my_idx >= 0) src = A.batch.read_indices ? __ldg(A.batch.read_indices + my_idx) : my_idx;
+        if (A.batch.reads_kind == PMT_READS_U8) {
+          const int rb = D.read_row_bytes;
+          const uint8_t* rp = reinterpret_cast<const uint8_t*>(A.batch.reads) + src * rb;
+          // half 0 expands packed bytes 0..3, half 1 bytes 4..6 and the quantised floats
+          const int b_lo = half ? 4 : 0, b_hi = half ? 7 : 4;
+          for (int b = b_lo; b < b_hi; ++b) {
+            const unsigned byte = src >= 0 ? __ldg(rp + b) : 0u;
+#pragma unroll
+            for (int bit = 0; bit < 8; ++bit) T1[(b * 8 + bit) * LD + row] = (float)((byte >> (7 - bit)) & 1u);
+          }
+          if (half) {
+            for (int b = 7; b < rb; ++b) {
+              const unsigned byte = src >= 0 ? __ldg(rp + b) : 128u;
+              T1[(56 + b - 7) * LD + row] = (float)((byte + 128u) & 255u) * 0.03125f;
+            }
+          }
+        } else {
+          for (int f = half; f < F; f += 2) {
+            float v = 0.f;
+            if (src >= 0) {
+              v = A.batch.reads_kind == PMT_READS_F16
+                      ? __half2float(reinterpret_cast<const __half*>(A.batch.reads)[src * F + f])
+                      : reinterpret_cast<const float*>(A.batch.reads)[src * F + f];
+            }
+            T1[f * LD + row] = v;
+          }
+        }
+      }
+      // ---------------- read embedding MLP (artifact_model.py:243) ----------------
+      float* emb = run_mlp(P, D.read_ops, D.n_read_ops, P.read_g0, T1, X, T1, T2, stage, W, rows_used, P.blk_g0);
+      __syncthreads();
+      if (emb != X) { copy_features(emb, X, D.d_read); }
+      // ---------------- concat info/seq embedding of the row's variant (artifact_model.py:246-251) ----------------
+      {
+        const int w = D.d_info + D.d_seq;
+        const float* src = my_var >= 0 ? A.out.info_seq_be + (long long)(M.v0 + my_var) * w : nullptr;
+        for (int j = half; j < w; j += 2) X[(D.d_read + j) * LD + row] = src ? __ldg(src + j) : 0.f;
+      }
+      __syncthreads();
+
+      // ---------------- gated ref/alt MLP blocks (gated_mlp.py:177-251) ----------------
+      for (int blk = 0; blk < D.n_blocks; ++blk) {
+        const PmtBlockOffsets& BO = D.blocks[blk];
+        const int g1 = P.blk_g0 + 2 * blk, g2 = g1 + 1;
+        {  // LayerNorm over d_model (shared by ref and alt): T1 = LN(X)
+          float mean = 0.f;
+          for (int f = 0; f < Dm; ++f) mean += X[f * LD + row];
+          mean /= Dm;
+          float var = 0.f;
+          for (int f = 0; f < Dm; ++f) { const float d = X[f * LD + row] - mean; var = fmaf(d, d, var); }
+          const float rstd = rsqrtf(var / Dm + LN_EPS);
+          const int f_lo = half ? Dm / 2 : 0, f_hi = half ? Dm : Dm / 2;
+          for (int f = f_lo; f < f_hi; ++f)
+            T1[f * LD + row] = (X[f * LD + row] - mean) * rstd * __ldg(W + BO.ln_w + f) + __ldg(W + BO.ln_b + f);
+        }
+        const float* img1 = stage.acquire(g1);
+        stage.prefetch(g2);
+        gemm_tile(T1, P.gemm[g1], img1, W, ref_pad, T2, EPI_SELU, 0.f, rows_used);
+        __syncthreads();
+        {  // SGU LayerNorm on z2 = T2[H..2H) in place (gated_mlp.py:230-233)
+          float mean = 0.f;
+          for (int f = 0; f < H; ++f) mean += T2[(H + f) * LD + row];
+          mean /= H;
+          float var = 0.f;
+          for (int f = 0; f < H; ++f) { const float d = T2[(H + f) * LD + row] - mean; var = fmaf(d, d, var); }
+          const float rstd = rsqrtf(var / H + LN_EPS);
+          __syncthreads();  // both halves have read the raw z2 of this row
+          const int f_lo = half ? H / 2 : 0, f_hi = half ? H : H / 2;
+          for (int f = f_lo; f < f_hi; ++f)
+            T2[(H + f) * LD + row] = (T2[(H + f) * LD + row] - mean) * rstd * __ldg(W + BO.ln2_w + f) + __ldg(W + BO.ln2_b + f);
+        }
+        __syncthreads();
+        segment_sums(M, T2, H, H, sums, P.sum_w, false);
+        __syncthreads();
+        {  // mean fields (gated_mlp.py:236-239; ragged_sets.py:144-155)
+          const float regw = __ldg(W + BO.reg_weight) + 0.25f;
+          for (int idx = tid; idx < M.nv * 2 * H; idx += NTHREADS) {
+            const int j = idx / (2 * H), s = (idx / H) & 1, f = idx % H;
+            float* p = sums + (j * 2 + s) * P.sum_w + f;
+            if (s == 0) *p = (*p + regw * __ldg(W + BO.regularizer + f)) / ((float)M.ref_cnt[j] + regw);
+            else *p = *p / ((float)M.alt_cnt[j] + 1e-4f);
+          }
+        }
+        __syncthreads();
+        {  // gate: T1[0..H) = z1 * (alpha z2 + 1 + beta m_own (+ gamma m_ref))   (gated_mlp.py:243-251)
+          const bool is_alt = row >= ref_pad;
+          const float alpha = __ldg(W + (is_alt ? BO.alpha_alt : BO.alpha_ref));
+          const float beta = __ldg(W + (is_alt ? BO.beta_alt : BO.beta_ref));
+          const float gamma = __ldg(W + BO.gamma);
+          const int f_lo = half ? H / 2 : 0, f_hi = half ? H : H / 2;
+          for (int f = f_lo; f < f_hi; ++f) {
+            float gate = T2[(H + f) * LD + row] * alpha + 1.f;
+            if (my_var >= 0) {
+              const float m_ref = sums[(my_var * 2 + 0) * P.sum_w + f];
+              if (is_alt) gate = gate + beta * sums[(my_var * 2 + 1) * P.sum_w + f] + gamma * m_ref;
+              else gate = gate + beta * m_ref;
+            }
+            T1[f * LD + row] = T2[f * LD + row] * gate;
+          }
+        }
+        const float* img2 = stage.acquire(g2);
+        stage.prefetch(blk + 1 < D.n_blocks ? g2 + 1 : P.red_g0);
+        gemm_tile(T1, P.gemm[g2], img2, W, ref_pad, X, EPI_RESIDUAL, 1.f, rows_used);
+        __syncthreads();
+      }
+
+      // ---------------- reducer MLP (artifact_model.py:258-259) ----------------
+      float* red = run_mlp(P, D.red_ops, D.n_red_ops, P.red_g0, X, X, T1, T2, stage, W, rows_used, -1);
+      __syncthreads();
+      float* Fb = (red == T1) ? T2 : T1;                       // final features
+      float* Lb = (red != X && Fb != X) ? X : ((red != T2 && Fb != T2) ? T2 : T1);  // per-read log-likelihoods
+      {  // pre_clustering_transform (euclidean_transformation.py:19-20): f = Q (y + t)
+        const int e_lo = half ? E / 2 : 0, e_hi = half ? E : E / 2;
+        for (int i = e_lo; i < e_hi; ++i) {
+          float acc = 0.f;
+          for (int j = 0; j < E; ++j) acc = fmaf(__ldg(W + D.rotation + i * E + j), red[j * LD + row] + __ldg(W + D.translation + j), acc);
+          Fb[i * LD + row] = acc;
+        }
+      }
+      __syncthreads();
+      if (row >= ref_pad && my_var >= 0) {  // clustering head on alt rows (feature_clustering.py:82-119)
+        if (half == 0) {
+          float q = 0.f, q2 = 0.f;
+          for (int e = 0; e < E; ++e) {
+            const float x = Fb[e * LD + row];
+            const float a = x / HC->sigma[e], b = x / (2.f * HC->sigma[e]);
+            q = fmaf(a, a, q); q2 = fmaf(b, b, q2);
+          }
+          Lb[0 * LD + row] = HC->c_non - q / 2.f;
+          Lb[1 * LD + row] = HC->c_out - q2 / 2.f;
+        }
+        for (int k = half; k < K; k += 2) {
+          const float* u = W + D.unit_ke + k * E;
+          float p = 0.f;
+          for (int e = 0; e < E; ++e) p = fmaf(Fb[e * LD + row], __ldg(u + e), p);
+          float o2 = 0.f;
+          for (int e = 0; e < E; ++e) { const float d = Fb[e * LD + row] - p * __ldg(u + e); o2 = fmaf(d, d, o2); }
+          const float dist = sqrtf(o2);
+          const float ll_orth = HC->c_orth[k] - (dist * dist) / HC->inv_two_tau2[k];
+          const float ll_par = HC->log_half_lambda[k] + logerfc((HC->shift[k] - p) / HC->inv_sqrt2_sigma[k]) +
+                               HC->half_lambda[k] * (HC->two_mu_plus[k] - 2.f * p);
+          Lb[(2 + k) * LD + row] = ll_orth + ll_par;
+        }
+      }
+      __syncthreads();
+      segment_sums(M, Fb, 0, E, sums, P.sum_w, false);
+      segment_sums(M, Lb, 0, K + 2, llsum, 16, true);
+      __syncthreads();
+      // ---------------- per-variant outputs ----------------
+      for (int idx = tid; idx < M.nv * E; idx += NTHREADS) {
+        const int j = idx / E, e = idx % E;
+        const long long v = M.v0 + j;
+        if (A.out.alt_means_be) A.out.alt_means_be[v * E + e] = sums[(j * 2 + 1) * P.sum_w + e] / ((float)M.alt_cnt[j] + 1e-4f);
+        if (A.out.ref_means_be) A.out.ref_means_be[v * E + e] = sums[(j * 2 + 0) * P.sum_w + e] / ((float)M.ref_cnt[j] + 1e-4f);
+      }
+      if (tid < M.nv) {
+        const long long v = M.v0 + tid;
+        const float* ll = llsum + (tid * 2 + 1) * 16;
+        const float non = ll[0], outl = ll[1];
+        float art_max = -INFINITY;
+        for (int k = 0; k < K; ++k) art_max = fmaxf(art_max, ll[2 + k] + HC->logw[k]);
+        float s = 0.f;
+        for (int k = 0; k < K; ++k) s += expf(ll[2 + k] + HC->logw[k] - art_max);
+        const float art = art_max + logf(s);
+        if (A.out.logits_bk) {
+          A.out.logits_bk[v * (K + 2) + 0] = non;
+          A.out.logits_bk[v * (K + 2) + 1] = outl;
+          for (int k = 0; k < K; ++k) A.out.logits_bk[v * (K + 2) + 2 + k] = ll[2 + k] + HC->logw[k];
+        }
+        if (A.out.logits_b) A.out.logits_b[v] = 20.f * tanhf((art - non) / 20.f);
+        if (A.out.outlier_logits_b) A.out.outlier_logits_b[v] = outl - logsumexp2(non, art);
+      }
+      if (A.out.final_re) {
+        for (int idx = tid; idx < TILE * E; idx += NTHREADS) {
+          const int r = idx / E, e = idx % E;
+          const long long n = M.rowidx[r];
+          if (n >= 0) A.out.final_re[n * E + e] = Fb[e * LD + r];
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// stand-alone decode (Batch.__init__, batch.py:51-56)
+// ------------------------------------------------------------------------------------------------
+__global__ void decode_reads_kernel(const uint8_t* __restrict__ reads, long long n_rows, int row_bytes, float* __restrict__ out) {
+  const int F = 56 + row_bytes - 7;
+  const long long total = n_rows * F;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long r = idx / F;
+    const int f = (int)(idx % F);
+    const uint8_t* rp = reads + r * row_bytes;
+    float v;
+    if (f < 56) v = (float)((rp[f >> 3] >> (7 - (f & 7))) & 1u);
+    else v = (float)((rp[7 + f - 56] + 128u) & 255u) * 0.03125f;
+    out[idx] = v;
+  }
+}
+
+}  // namespace pmt
+
+// ================================================================================================
+// host side
+// ================================================================================================
+using namespace pmt;
+
+static thread_local char g_err[512] = "";
+void pmt_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* pmt_last_error(void) { return g_err; }
+extern "C" int pmt_abi_version(void) { return PMT_ABI_VERSION; }
+
+static void choose_groups(int N, int* G, int* NT) {
+  int g = N > 32 ? 8 : 4;
+  int nt = (N + g - 1) / g;
+  if (nt < 1) nt = 1;
+  g = (N + nt - 1) / nt;
+  *G = g; *NT = nt;
+}
+
+static int add_gemm(Plan& P, int K, int N, int w, int b, int w_alt, int b_alt) {
+  if (P.n_gemm >= MAX_GEMM) return -1;
+  GemmOp& op = P.gemm[P.n_gemm];
+  op.K = K; op.N = N;
+  choose_groups(N, &op.G, &op.NT);
+  op.w_off = w; op.b_off = b; op.w_alt_off = w_alt; op.b_alt_off = b_alt;
+  op.img_off = P.img_total;
+  op.img_floats = K * op.G * GROUP_STRIDE * (w_alt >= 0 ? 2 : 1);
+  op.img_floats = (op.img_floats + 3) & ~3;
+  P.img_total += op.img_floats;
+  return P.n_gemm++;
+}
+
+int pmt_build_plan(const PmtModelDesc* d, Plan* out) {
+  Plan& P = *out;
+  memset(&P, 0, sizeof(P));
+  if (d->abi_version != PMT_ABI_VERSION) { pmt_set_error("PmtModelDesc.abi_version %d != %d", d->abi_version, PMT_ABI_VERSION); return 1; }
+  P.d = *d;
+  PMT_CHECK(d->n_read_features <= PMT_MAX_DIM && d->n_read_features == 56 + d->read_row_bytes - 7,
+            "n_read_features %d unsupported (max %d, must equal 8*7 + row_bytes - 7)", d->n_read_features, PMT_MAX_DIM);
+  PMT_CHECK(d->n_info_features <= PMT_MAX_INFO_DIM, "n_info_features %d > %d", d->n_info_features, PMT_MAX_INFO_DIM);
+  PMT_CHECK(d->d_model <= PMT_MAX_DIM && d->d_model == d->d_read + d->d_info + d->d_seq, "d_model %d unsupported", d->d_model);
+  PMT_CHECK(d->d_ffn <= PMT_MAX_DIM && d->d_ffn % 2 == 0, "d_ffn %d unsupported", d->d_ffn);
+  PMT_CHECK(d->d_feat <= PMT_MAX_FEAT && d->n_clusters <= PMT_MAX_CLUSTERS && d->n_clusters >= 1, "d_feat/n_clusters unsupported");
+  PMT_CHECK(d->n_blocks <= PMT_MAX_BLOCKS, "too many gated blocks");
+  PMT_CHECK(d->n_read_ops <= PMT_MAX_MLP_OPS && d->n_info_ops <= PMT_MAX_MLP_OPS && d->n_red_ops <= PMT_MAX_MLP_OPS &&
+            d->n_cnn_ops <= PMT_MAX_CNN_OPS, "too many layers");
+  auto add_program = [&](const PmtLinearOp* ops, int n, int max_in, int* g0) -> int {
+    *g0 = P.n_gemm;
+    for (int i = 0; i < n; ++i) {
+      if (ops[i].in_dim > (i == 0 ? max_in : PMT_MAX_DIM) || ops[i].out_dim > PMT_MAX_DIM) { pmt_set_error("layer width > %d", PMT_MAX_DIM); return 1; }
+      if (add_gemm(P, ops[i].in_dim, ops[i].out_dim, ops[i].w_off, ops[i].b_off, -1, -1) < 0) { pmt_set_error("too many GEMMs"); return 1; }
+    }
+    return 0;
+  };
+  if (add_program(d->read_ops, d->n_read_ops, PMT_MAX_DIM, &P.read_g0)) return 1;
+  P.blk_g0 = P.n_gemm;
+  for (int b = 0; b < d->n_blocks; ++b) {
+    const PmtBlockOffsets& o = d->blocks[b];
+    add_gemm(P, d->d_model, d->d_ffn, o.p1_ref_w, o.p1_ref_b, o.p1_alt_w, o.p1_alt_b);
+    add_gemm(P, d->d_ffn / 2, d->d_model, o.p2_ref_w, o.p2_ref_b, o.p2_alt_w, o.p2_alt_b);
+  }
+  if (add_program(d->red_ops, d->n_red_ops, PMT_MAX_DIM, &P.red_g0)) return 1;
+  int read_path_end = P.n_gemm;
+  if (add_program(d->info_ops, d->n_info_ops, PMT_MAX_INFO_DIM, &P.info_g0)) return 1;
+  for (int g = 0; g < P.n_gemm; ++g) {
+    int& tgt = g < read_path_end ? P.stage_floats : P.info_stage_floats;
+    if (P.gemm[g].img_floats > tgt) tgt = P.gemm[g].img_floats;
+  }
+  P.sum_w = d->d_ffn / 2 > d->d_feat ? d->d_ffn / 2 : d->d_feat;
+  P.claim_variants = 64;
+  return 0;
+}
+
+int pmt_cnn_geometry(const Plan& P, CnnGeom* out) {
+  CnnGeom& G = *out;
+  memset(&G, 0, sizeof(G));
+  const PmtModelDesc& d = P.d;
+  int n_sp = 0;
+  while (n_sp < d.n_cnn_ops && d.cnn_ops[n_sp].kind != PMT_CNN_LINEAR) ++n_sp;
+  PMT_CHECK(n_sp < d.n_cnn_ops, "haplotype CNN must end with flatten + linear");
+  for (int i = n_sp; i < d.n_cnn_ops; ++i) {
+    PMT_CHECK(d.cnn_ops[i].kind == PMT_CNN_LINEAR, "spatial layer after flatten");
+    PMT_CHECK(d.cnn_ops[i].out_ch <= 256 && (i == n_sp || d.cnn_ops[i].in_ch <= 256), "CNN linear layer too wide");
+  }
+  G.n_spatial = n_sp;
+  int max_per_var = 10 * ((d.hap_len + 3) & ~3);
+  G.lp[0] = (d.hap_len + 3) & ~3;
+  int img = 0;
+  for (int i = 0; i < n_sp; ++i) {
+    const PmtCnnOp& op = d.cnn_ops[i];
+    PMT_CHECK(op.ksize >= 1 && op.ksize <= 9, "conv/pool kernel_size %d unsupported (1..9)", op.ksize);
+    G.lp[i + 1] = (op.out_len + 3) & ~3;
+    const int ch = op.kind == PMT_CNN_CONV ? op.out_ch : op.in_ch;
+    PMT_CHECK(ch <= 64 && op.in_ch <= 64, "CNN channels > 64 unsupported");
+    if (ch * G.lp[i + 1] > max_per_var) max_per_var = ch * G.lp[i + 1];
+    if (op.kind == PMT_CNN_CONV) {
+      PMT_CHECK(op.stride == 1, "conv stride != 1 unsupported");
+      G.img_off[i] = img;
+      img += op.in_ch * op.ksize * ((op.out_ch + 7) / 8) * GROUP_STRIDE;
+    }
+  }
+  G.img_total = (img + 3) & ~3;
+  // shared memory budget: 2 activation buffers + conv images + linear scratch
+  const int budget_floats = (200 * 1024) / 4 - G.img_total;
+  int vt = 32;
+  for (; vt >= 1; --vt) {
+    const int buf = 64 * 8 + vt * max_per_var + 64;  // + per-channel slack of 8 floats
+    if (2 * buf + 2 * vt * 256 <= budget_floats) break;
+  }
+  PMT_CHECK(vt >= 1, "haplotype CNN does not fit in shared memory");
+  G.vt = vt;
+  G.buf_floats = ((64 * 8 + vt * max_per_var + 64) + 3) & ~3;
+  return 0;
+}
+
+size_t pmt_image_bytes(const Plan& P, const CnnGeom& G) { return (size_t)(P.img_total + G.img_total + 64) * sizeof(float); }
+
+extern "C" size_t pmt_workspace_size(const PmtModelDesc* desc, const PmtBatch* batch, int for_backward) {
+  Plan P;
+  CnnGeom G;
+  if (pmt_build_plan(desc, &P) || pmt_cnn_geometry(P, &G)) return 0;
+  size_t bytes = 256;                       // claim counter + flags
+  bytes += pmt_image_bytes(P, G);
+  if (batch) bytes += (size_t)batch->n_variants * (desc->d_info + desc->d_seq) * sizeof(float) + 256;  // info_seq when caller passes none
+  if (for_backward) bytes += pmt_backward_workspace_bytes(P, batch);
+  return bytes;
+}
+
+static size_t reads_kernel_smem(const Plan& P) {
+  return (size_t)(3 * PMT_MAX_DIM * LD + 2 * P.stage_floats + TILE * 2 * P.sum_w + TILE * 2 * 16) * sizeof(float) +
+         sizeof(HeadConst) + sizeof(TileMeta) + 16;
+}
+
+int pmt_launch_prepare(const Plan& P, const CnnGeom& G, const float* weights, float* image, cudaStream_t st) {
+  pack_weights_kernel<<<P.n_gemm, 256, 0, st>>>(P, weights, image);
+  if (G.n_spatial > 0) pack_conv_kernel<<<G.n_spatial, 256, 0, st>>>(P, G, weights, image + P.img_total);
+  return 0;
+}
+
+int pmt_launch_variant_kernels(const Plan& P, const CnnGeom& G, const float* weights, const float* image,
+                               const PmtBatch* batch, float* info_seq, cudaStream_t st) {
+  const int B = batch->n_variants;
+  {
+    const int in_rows = P.d.n_info_features > PMT_MAX_DIM ? PMT_MAX_INFO_DIM : PMT_MAX_DIM;
+    const size_t smem = (size_t)((in_rows + 2 * PMT_MAX_DIM) * LD + 2 * P.info_stage_floats) * sizeof(float);
+    cudaFuncSetAttribute(info_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    info_mlp_kernel<<<(B + TILE - 1) / TILE, NTHREADS, smem, st>>>(P, weights, image, batch->info, batch->info_kind,
+                                                                   batch->info_stride, B, info_seq);
+  }
+  {
+    const size_t smem = (size_t)(2 * G.buf_floats + G.img_total + 2 * G.vt * 256) * sizeof(float);
+    cudaFuncSetAttribute(hap_cnn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int grid = (B + G.vt - 1) / G.vt;
+    if (grid > 148 * 4) grid = 148 * 4;
+    hap_cnn_kernel<<<grid, NTHREADS, smem, st>>>(P, G, weights, image + P.img_total, batch->haplotypes, batch->hap_kind,
+                                                 batch->hap_stride, B, info_seq);
+  }
+  return 0;
+}
+
+static int choose_claim(const PmtBatch* batch, int n_sm) {
+  // aim for ~8 tiles per claim, but keep at least ~2 claims per SM when the batch is small
+  const double avg = batch->n_variants > 0 ? (double)batch->n_rows / batch->n_variants : 1.0;
+  int claim = (int)(8.0 * TILE / (avg + 1.0));
+  const int by_parallelism = batch->n_variants / (2 * n_sm);
+  if (claim > by_parallelism) claim = by_parallelism;
+  if (claim > 512) claim = 512;
+  if (claim < 1) claim = 1;
+  return claim;
+}
+
+extern "C" int pmt_forward(const PmtModelDesc* desc, const float* weights, const PmtBatch* batch, const PmtOutputs* out,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+  Plan P;
+  CnnGeom G;
+  if (pmt_build_plan(desc, &P) || pmt_cnn_geometry(P, &G)) return 1;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t need = pmt_workspace_size(desc, batch, 0);
+  PMT_CHECK(workspace && workspace_bytes >= need, "workspace too small: %zu < %zu", workspace_bytes, need);
+  PMT_CHECK(batch->n_variants > 0, "empty batch");
+  PMT_CHECK(batch->max_rows_per_variant <= TILE, "variant with %lld reads: sets longer than %d reads need the long-set path",
+            (long long)batch->max_rows_per_variant, TILE);
+  char* ws = reinterpret_cast<char*>(workspace);
+  int* counter = reinterpret_cast<int*>(ws);
+  float* image = reinterpret_cast<float*>(ws + 256);
+  float* info_seq = out->info_seq_be;
+  if (!info_seq) info_seq = reinterpret_cast<float*>(ws + 256 + pmt_image_bytes(P, G));
+  cudaMemsetAsync(counter, 0, 256, st);
+  pmt_launch_prepare(P, G, weights, image, st);
+  pmt_launch_variant_kernels(P, G, weights, image, batch, info_seq, st);
+
+  int dev = 0, n_sm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  P.claim_variants = choose_claim(batch, n_sm);
+  ReadKernelArgs A;
+  A.wflat = weights; A.image = image; A.batch = *batch; A.out = *out; A.out.info_seq_be = info_seq; A.claim_counter = counter;
+  const size_t smem = reads_kernel_smem(P);
+  cudaFuncSetAttribute(reads_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int n_claims = (batch->n_variants + P.claim_variants - 1) / P.claim_variants;
+  const int grid = n_claims < n_sm ? n_claims : n_sm;
+  reads_forward_kernel<<<grid, NTHREADS, smem, st>>>(P, A);
+  cudaError_t e = cudaGetLastError();
+  PMT_CHECK(e == cudaSuccess, "pmt_forward launch failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+extern "C" int pmt_decode_reads(const uint8_t* reads_u8, int64_t n_rows, int32_t row_bytes, float* out, void* stream) {
+  PMT_CHECK(row_bytes >= 7, "row_bytes %d < 7 packed bytes", row_bytes);
+  if (n_rows == 0) return 0;
+  const long long total = (long long)n_rows * (56 + row_bytes - 7);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  decode_reads_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reads_u8, n_rows, row_bytes, out);
+  cudaError_t e = cudaGetLastError();
+  PMT_CHECK(e == cudaSuccess, "pmt_decode_reads launch failed: %s", cudaGetErrorString(e));
+  return 0;
+}

@@ -1,0 +1,23 @@
+// Host-side helpers shared by the translation units of libpermutect_b200.so.
+#pragma once
+#include <cstdarg>
+#include <cstddef>
+
+#include "pmt_device.cuh"
+
+void pmt_set_error(const char* fmt, ...);
+#define PMT_CHECK(cond, ...)     \
+  do {                           \
+    if (!(cond)) {               \
+      pmt_set_error(__VA_ARGS__); \
+      return 1;                  \
+    }                            \
+  } while (0)
+
+int pmt_build_plan(const PmtModelDesc* d, pmt::Plan* out);
+int pmt_cnn_geometry(const pmt::Plan& P, pmt::CnnGeom* out);
+size_t pmt_image_bytes(const pmt::Plan& P, const pmt::CnnGeom& G);
+int pmt_launch_prepare(const pmt::Plan& P, const pmt::CnnGeom& G, const float* weights, float* image, cudaStream_t st);
+int pmt_launch_variant_kernels(const pmt::Plan& P, const pmt::CnnGeom& G, const float* weights, const float* image,
+                               const PmtBatch* batch, float* info_seq, cudaStream_t st);
+size_t pmt_backward_workspace_bytes(const pmt::Plan& P, const PmtBatch* batch);

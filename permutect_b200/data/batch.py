@@ -1,0 +1,198 @@
+"""Ragged batch of variants for the fused kernels (reference: permutect/data/batch.py:40-183, 383-459).
+
+Differences from the reference that matter for speed, none for results:
+  * reads stay COMPRESSED (uint8 [R, 12], 12 B/read) on the host, over PCIe and in HBM; the decode
+    of batch.py:51-56 (unpackbits + wrapped ``(u8-128)/32``) happens inside the read kernel.  The
+    reference ships the fp32 expansion (244 B/read).
+  * int / float side arrays keep their on-disk dtypes (int16 / fp16, datum.py:23-25).
+  * ragged structure is carried as exclusive prefix sums (``ref_off`` / ``alt_off``) computed on the
+    device, so no ``.item()`` synchronisation is needed anywhere on the hot path.
+Row order is the reference's: all ref reads of all variants, then all alt reads (batch.py:45-47).
+"""
+from __future__ import annotations
+
+import copy
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from permutect_b200.data.datum import (COMPRESSED_READS_ARRAY_DTYPE, HAPLOTYPES_START_IDX, INFO_START_IDX, Data, Datum)
+from permutect_b200.engine import library as L
+from permutect_b200.utils.enums import Label
+
+
+class Batch:
+    def __init__(self, data: List[Datum]):
+        """Collate (batch.py:41-62): vstack side arrays; all ref rows, then all alt rows."""
+        int_array = np.vstack([d.get_int_array() for d in data])
+        float_array = np.vstack([d.get_float_array() for d in data])
+        reads = np.vstack([d.get_ref_reads_re() for d in data] + [d.get_alt_reads_re() for d in data])
+        self._init_from_arrays(int_array, float_array, reads)
+
+    @classmethod
+    def from_arrays(cls, int_array: np.ndarray, float_array: np.ndarray, reads: np.ndarray) -> "Batch":
+        """Bulk constructor: ``reads`` already in batch order (all ref rows by variant, then all alt rows)."""
+        self = cls.__new__(cls)
+        self._init_from_arrays(int_array, float_array, reads)
+        return self
+
+    def _init_from_arrays(self, int_array, float_array, reads):
+        assert int_array.dtype == np.int16 and float_array.dtype == np.float16
+        self.int_tensor = torch.from_numpy(np.ascontiguousarray(int_array))
+        self.float_tensor = torch.from_numpy(np.ascontiguousarray(float_array))
+        self.reads_are_compressed = reads.dtype == COMPRESSED_READS_ARRAY_DTYPE
+        self.reads = torch.from_numpy(np.ascontiguousarray(reads))
+        counts = int_array[:, :2].astype(np.int64)
+        assert counts[:, 0].sum() + counts[:, 1].sum() == len(reads), "read rows do not match ref+alt counts"
+        self.max_rows_per_variant = int((counts[:, 0] + counts[:, 1]).max()) if len(counts) else 0
+        self.read_indices = None
+        self._finish_initialization_from_arrays()
+
+    def _finish_initialization_from_arrays(self):
+        self._size = len(self.int_tensor)
+        self._offsets = None
+        self._decoded = None
+        self._device_counts = None      # (ref_counts, alt_counts) int64 when they differ from the int array (downsampling)
+
+    # ---- reference accessors (batch.py:87-133,182) ------------------------------------------------
+    def get(self, data_field: Data) -> torch.Tensor:
+        if self._device_counts is not None and data_field in (Data.REF_COUNT, Data.ALT_COUNT):
+            return self._device_counts[0 if data_field == Data.REF_COUNT else 1]
+        if data_field.kind == "int":
+            return self.int_tensor[:, data_field.idx].long()
+        return self.float_tensor[:, data_field.idx].float()
+
+    def get_training_labels(self) -> torch.Tensor:
+        labels = self.int_tensor[:, Data.LABEL.idx]
+        return 1.0 * (labels == Label.ARTIFACT) + 0.5 * (labels == Label.UNLABELED)
+
+    def get_is_labeled_mask(self) -> torch.Tensor:
+        return (self.int_tensor[:, Data.LABEL.idx] != Label.UNLABELED).int()
+
+    def get_info_be(self) -> torch.Tensor:
+        return self.float_tensor[:, INFO_START_IDX:].float()
+
+    def get_haplotypes_bs(self) -> torch.Tensor:
+        return self.int_tensor[:, HAPLOTYPES_START_IDX:].long()
+
+    def get_one_hot_haplotypes_bcs(self) -> torch.Tensor:
+        """batch.py:115-130 (API parity only; the CNN kernel builds the one-hot image in shared memory)."""
+        haps = self.get_haplotypes_bs()
+        one_hot = torch.nn.functional.one_hot(haps, num_classes=5).permute(0, 2, 1)
+        return one_hot.reshape(len(haps), 10, haps.shape[1] // 2)
+
+    def get_reads_re(self) -> torch.Tensor:
+        """Decoded reads [N, F] float32 (batch.py:132-133), produced on demand by the decode kernel."""
+        if self._decoded is None:
+            self._decoded = self._decode()
+        return self._decoded if self.read_indices is None else self._decoded[self.read_indices]
+
+    def _decode(self) -> torch.Tensor:
+        if not self.reads_are_compressed:
+            return self.reads.float()
+        if self.reads.device.type != "cuda":
+            raise RuntimeError("read decode runs on the GPU; call batch.copy_to(cuda_device) first")
+        lib = L.load()
+        n, row_bytes = self.reads.shape
+        out = torch.empty((n, 56 + row_bytes - 7), dtype=torch.float32, device=self.reads.device)
+        L.check(lib.pmt_decode_reads(self.reads.data_ptr(), n, row_bytes, out.data_ptr(),
+                                     torch.cuda.current_stream(self.reads.device).cuda_stream))
+        return out
+
+    def size(self) -> int:
+        return self._size
+
+    # ---- host <-> device (batch.py:155-174) -------------------------------------------------------
+    def pin_memory(self):
+        self.int_tensor = self.int_tensor.pin_memory()
+        self.float_tensor = self.float_tensor.pin_memory()
+        self.reads = self.reads.pin_memory()
+        return self
+
+    def copy_to(self, device, dtype=None):
+        device = torch.device(device)
+        non_blocking = device.type == "cuda"
+        new_batch = copy.copy(self)
+        new_batch.reads = self.reads.to(device, non_blocking=non_blocking)
+        new_batch.int_tensor = self.int_tensor.to(device, non_blocking=non_blocking)
+        new_batch.float_tensor = self.float_tensor.to(device, non_blocking=non_blocking)
+        if self.read_indices is not None:
+            new_batch.read_indices = self.read_indices.to(device, non_blocking=non_blocking)
+        new_batch._offsets = None
+        new_batch._decoded = None
+        return new_batch
+
+    def h2d_bytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in (self.reads, self.int_tensor, self.float_tensor))
+
+    # ---- kernel-facing view -----------------------------------------------------------------------
+    def counts(self):
+        if self._device_counts is not None:
+            return self._device_counts
+        return self.int_tensor[:, Data.REF_COUNT.idx].long(), self.int_tensor[:, Data.ALT_COUNT.idx].long()
+
+    def offsets(self):
+        """Exclusive prefix sums [B+1] (int64) of the ref and alt counts, on the batch's device."""
+        if self._offsets is None:
+            ref_counts, alt_counts = self.counts()
+            both = torch.stack((ref_counts, alt_counts)).to(torch.int64)
+            off = torch.zeros((2, self._size + 1), dtype=torch.int64, device=both.device)
+            torch.cumsum(both, dim=1, out=off[:, 1:])
+            self._offsets = off
+        return self._offsets[0], self._offsets[1]
+
+    def pmt_batch(self) -> L.PmtBatch:
+        """Fill the C-ABI PmtBatch (include/permutect_b200.h).  Keeps no host copies of device data."""
+        if self.reads.device.type != "cuda":
+            raise RuntimeError("the ArtifactModel kernels need the batch on a CUDA device (Batch.copy_to)")
+        ref_off, alt_off = self.offsets()
+        b = L.PmtBatch()
+        b.n_variants = self._size
+        if self.reads_are_compressed:
+            b.reads_kind = L.READS_U8
+        else:
+            b.reads_kind = L.READS_F16 if self.reads.dtype == torch.float16 else L.READS_F32
+        b.info_kind, b.hap_kind = L.F16, L.I16
+        b.n_rows = -1          # the kernels take totals from ref_off[B] / alt_off[B]
+        b.total_ref = -1
+        b.max_rows_per_variant = self.max_rows_per_variant
+        b.reads = self.reads.data_ptr()
+        b.read_indices = self.read_indices.data_ptr() if self.read_indices is not None else None
+        b.ref_off, b.alt_off = ref_off.data_ptr(), alt_off.data_ptr()
+        b.info = self.float_tensor.data_ptr() + INFO_START_IDX * self.float_tensor.element_size()
+        b.info_stride = self.float_tensor.shape[1]
+        b.haplotypes = self.int_tensor.data_ptr() + HAPLOTYPES_START_IDX * self.int_tensor.element_size()
+        b.hap_stride = self.int_tensor.shape[1]
+        return b
+
+
+class DownsampledBatch(Batch):
+    """Read-downsampled view of a parent batch without copying reads (batch.py:383-459).
+
+    ``read_indices`` lists the kept rows: kept ref rows followed by kept alt rows.  As in the reference
+    the alt entries index the alt block WITHOUT the ref-block offset (quirk Q1, batch.py:436-439) unless
+    ``offset_alt_rows=True`` is requested explicitly.
+    """
+
+    def __init__(self, original_batch: Batch, ref_fracs_b: Optional[torch.Tensor] = None,
+                 alt_fracs_b: Optional[torch.Tensor] = None, *, read_indices: Optional[torch.Tensor] = None,
+                 ref_counts: Optional[torch.Tensor] = None, alt_counts: Optional[torch.Tensor] = None,
+                 offset_alt_rows: bool = False, seed: Optional[int] = None):
+        self.int_tensor = original_batch.int_tensor
+        self.float_tensor = original_batch.float_tensor
+        self.reads = original_batch.reads
+        self.reads_are_compressed = original_batch.reads_are_compressed
+        self.max_rows_per_variant = original_batch.max_rows_per_variant
+        self.device = self.int_tensor.device
+        self._finish_initialization_from_arrays()
+        self._decoded = original_batch._decoded
+        if read_indices is not None:       # pre-drawn masks (tests, reproducible benchmarks)
+            self.read_indices = read_indices.to(self.device, torch.int64)
+            self._device_counts = (ref_counts.to(self.device, torch.int64), alt_counts.to(self.device, torch.int64))
+        else:
+            from permutect_b200.data.downsample import downsample_on_device
+            self.read_indices, ref_c, alt_c = downsample_on_device(original_batch, ref_fracs_b, alt_fracs_b,
+                                                                   offset_alt_rows=offset_alt_rows, seed=seed)
+            self._device_counts = (ref_c, alt_c)
+        self.ref_counts, self.alt_counts = self._device_counts

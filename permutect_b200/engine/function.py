@@ -1,0 +1,107 @@
+"""Calls into libpermutect_b200 (C-ABI) with torch-owned device memory, and the autograd bridge.
+
+PyTorch is plumbing here: it owns the buffers, the stream and the autograd tape that chains the
+parameter-constraint Jacobians; every per-read / per-variant FLOP is executed by the library.
+"""
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from permutect_b200.engine import library as L
+
+_WORKSPACES: Dict[torch.device, torch.Tensor] = {}
+
+
+def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    ws = _WORKSPACES.get(device)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=device)
+        _WORKSPACES[device] = ws
+    return ws
+
+
+def _require_cuda(t: torch.Tensor):
+    if t.device.type != "cuda":
+        raise RuntimeError("permutect_b200 computes on CUDA devices only (no CPU fallback)")
+
+
+def forward_call(desc: L.PmtModelDesc, flat: torch.Tensor, batch, want_final: bool = False,
+                 n_rows: Optional[int] = None) -> Dict[str, torch.Tensor]:
+    """pmt_forward: one fused pass over a batch.  Returns logits_bk, logits_b, outlier_logits, alt/ref means,
+    info_seq (and per-read final features when asked)."""
+    lib = L.load()
+    _require_cuda(flat)
+    dev = flat.device
+    B, K, E = batch.size(), desc.n_clusters, desc.d_feat
+    pb = batch.pmt_batch()
+    f32 = dict(dtype=torch.float32, device=dev)
+    out = {
+        "logits_bk": torch.empty((B, K + 2), **f32), "logits_b": torch.empty(B, **f32),
+        "outlier_logits": torch.empty(B, **f32), "alt_means": torch.empty((B, E), **f32),
+        "ref_means": torch.empty((B, E), **f32), "info_seq": torch.empty((B, desc.d_info + desc.d_seq), **f32),
+    }
+    po = L.PmtOutputs(out["logits_bk"].data_ptr(), out["logits_b"].data_ptr(), out["outlier_logits"].data_ptr(),
+                      out["alt_means"].data_ptr(), out["ref_means"].data_ptr(), out["info_seq"].data_ptr(), None)
+    if want_final:
+        out["final_re"] = torch.empty((n_rows, E), **f32)
+        po.final_re = out["final_re"].data_ptr()
+    need = lib.pmt_workspace_size(C.byref(desc), C.byref(pb), 0)
+    if need == 0:
+        raise RuntimeError("libpermutect_b200: " + lib.pmt_last_error().decode())
+    ws = _workspace(dev, need)
+    flat = flat.contiguous()
+    L.check(lib.pmt_forward(C.byref(desc), flat.data_ptr(), C.byref(pb), C.byref(po), ws.data_ptr(), ws.numel(),
+                            torch.cuda.current_stream(dev).cuda_stream))
+    return out
+
+
+def backward_call(desc: L.PmtModelDesc, flat: torch.Tensor, batch, d_logits_bk: Optional[torch.Tensor],
+                  d_alt_means: Optional[torch.Tensor], d_ref_means: Optional[torch.Tensor]) -> torch.Tensor:
+    """pmt_backward: gradient of the fused pass w.r.t. the flat materialised weights."""
+    lib = L.load()
+    _require_cuda(flat)
+    dev = flat.device
+    pb = batch.pmt_batch()
+    ptr = lambda t: None if t is None else t.contiguous().data_ptr()
+    keep = [None if t is None else t.contiguous() for t in (d_logits_bk, d_alt_means, d_ref_means)]
+    pg = L.PmtOutGrads(*[None if t is None else t.data_ptr() for t in keep])
+    d_flat = torch.empty_like(flat)
+    need = lib.pmt_workspace_size(C.byref(desc), C.byref(pb), 1)
+    if need == 0:
+        raise RuntimeError("libpermutect_b200: " + lib.pmt_last_error().decode())
+    ws = _workspace(dev, need)
+    L.check(lib.pmt_backward(C.byref(desc), flat.contiguous().data_ptr(), C.byref(pb), C.byref(pg), d_flat.data_ptr(),
+                             ws.data_ptr(), ws.numel(), torch.cuda.current_stream(dev).cuda_stream))
+    return d_flat
+
+
+class FusedArtifactFunction(torch.autograd.Function):
+    """(flat weights, batch) -> (logits_bk, alt_means, ref_means, logits_b, outlier_logits)."""
+
+    @staticmethod
+    def forward(ctx, flat, desc, batch):
+        out = forward_call(desc, flat, batch)
+        ctx.desc, ctx.batch = desc, batch
+        ctx.save_for_backward(flat, out["logits_bk"], out["logits_b"])
+        ctx.info_seq = out["info_seq"]
+        return out["logits_bk"], out["alt_means"], out["ref_means"], out["logits_b"], out["outlier_logits"]
+
+    @staticmethod
+    def backward(ctx, g_bk, g_alt, g_ref, g_lb, g_out):
+        flat, ll, logits_b = ctx.saved_tensors
+        # fold the gradients of the two derived logits into d/d logits_bk
+        # (feature_clustering.py:121-135, artifact_model.py:62-73)
+        g = torch.zeros_like(ll) if g_bk is None else g_bk.clone()
+        if g_lb is not None:
+            d_raw = g_lb * (1.0 - torch.square(logits_b / 20.0))
+            g[:, 2:] += d_raw[:, None] * torch.softmax(ll[:, 2:], dim=-1)
+            g[:, 0] -= d_raw
+        if g_out is not None:
+            non_outlier = torch.cat((ll[:, :1], ll[:, 2:]), dim=-1)
+            sm = torch.softmax(non_outlier, dim=-1)
+            g[:, 1] += g_out
+            g[:, 0] -= g_out * sm[:, 0]
+            g[:, 2:] -= g_out[:, None] * sm[:, 1:]
+        d_flat = backward_call(ctx.desc, flat, ctx.batch, g, g_alt, g_ref)
+        return d_flat, None, None

@@ -1,0 +1,108 @@
+"""ctypes binding of libpermutect_b200.so (C-ABI declared in include/permutect_b200.h).
+
+The structures below mirror the header field for field.  The library is located in-tree
+(``permutect_b200/csrc/libpermutect_b200.so``, built by ``permutect_b200.csrc.build``); if it is
+missing the compute entry points raise -- there is no fallback implementation.
+"""
+import ctypes as C
+import os
+
+PMT_ABI_VERSION = 1
+MAX_MLP_OPS, MAX_BLOCKS, MAX_CNN_OPS = 16, 12, 16
+MAX_DIM, MAX_INFO_DIM, MAX_FEAT, MAX_CLUSTERS, TILE_ROWS = 64, 128, 32, 14, 128
+
+OP_POST_SELU, OP_SKIP_BEGIN, OP_SKIP_END = 1, 2, 4
+CNN_CONV, CNN_POOL, CNN_LINEAR = 1, 2, 3
+ACT_NONE, ACT_SELU, ACT_LEAKY_RELU = 0, 1, 2
+READS_U8, READS_F32, READS_F16 = 0, 1, 2
+F32, F16 = 0, 1
+I16, I64 = 0, 1
+
+_i32 = C.c_int32
+
+
+class PmtLinearOp(C.Structure):
+    _fields_ = [("in_dim", _i32), ("out_dim", _i32), ("w_off", _i32), ("b_off", _i32), ("alpha_off", _i32),
+                ("flags", _i32)]
+
+
+class PmtCnnOp(C.Structure):
+    _fields_ = [("kind", _i32), ("in_ch", _i32), ("out_ch", _i32), ("ksize", _i32), ("stride", _i32),
+                ("in_len", _i32), ("out_len", _i32), ("act", _i32), ("w_off", _i32), ("b_off", _i32)]
+
+
+class PmtBlockOffsets(C.Structure):
+    _fields_ = [(n, _i32) for n in (
+        "ln_w", "ln_b", "p1_ref_w", "p1_ref_b", "p1_alt_w", "p1_alt_b", "alpha_ref", "alpha_alt", "beta_ref",
+        "beta_alt", "gamma", "regularizer", "ln2_w", "ln2_b", "reg_weight", "p2_ref_w", "p2_ref_b", "p2_alt_w",
+        "p2_alt_b")]
+
+
+class PmtModelDesc(C.Structure):
+    _fields_ = ([(n, _i32) for n in (
+        "abi_version", "n_read_features", "read_row_bytes", "n_info_features", "hap_len", "d_read", "d_info", "d_seq",
+        "d_model", "d_ffn", "n_blocks", "d_feat", "n_clusters", "n_read_ops", "n_info_ops", "n_red_ops", "n_cnn_ops")]
+        + [("read_ops", PmtLinearOp * MAX_MLP_OPS), ("info_ops", PmtLinearOp * MAX_MLP_OPS),
+           ("red_ops", PmtLinearOp * MAX_MLP_OPS), ("cnn_ops", PmtCnnOp * MAX_CNN_OPS),
+           ("blocks", PmtBlockOffsets * MAX_BLOCKS)]
+        + [(n, _i32) for n in ("translation", "rotation", "sigma_e", "unit_ke", "tau_k", "logw_k", "mu_k",
+                               "emg_sigma_k", "lambda_k", "n_params")])
+
+
+class PmtBatch(C.Structure):
+    _fields_ = [("n_variants", _i32), ("reads_kind", _i32), ("info_kind", _i32), ("hap_kind", _i32),
+                ("n_rows", C.c_int64), ("total_ref", C.c_int64), ("max_rows_per_variant", C.c_int64),
+                ("reads", C.c_void_p), ("read_indices", C.c_void_p), ("ref_off", C.c_void_p), ("alt_off", C.c_void_p),
+                ("info", C.c_void_p), ("info_stride", C.c_int64), ("haplotypes", C.c_void_p), ("hap_stride", C.c_int64)]
+
+
+class PmtOutputs(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("logits_bk", "logits_b", "outlier_logits_b", "alt_means_be", "ref_means_be",
+                                          "info_seq_be", "final_re")]
+
+
+class PmtOutGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("d_logits_bk", "d_alt_means_be", "d_ref_means_be")]
+
+
+EXPORTED_SYMBOLS = ["pmt_last_error", "pmt_abi_version", "pmt_workspace_size", "pmt_forward", "pmt_backward",
+                    "pmt_decode_reads"]
+
+_LIB = None
+
+
+def library_path() -> str:
+    return os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc", "libpermutect_b200.so")
+
+
+def load():
+    """Load the shared library (once) and declare the prototypes of include/permutect_b200.h."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is not built; run `python -m permutect_b200.csrc.build` "
+                           "(there is no CPU fallback for the ArtifactModel hot path)")
+    lib = C.CDLL(path)
+    lib.pmt_last_error.restype = C.c_char_p
+    lib.pmt_abi_version.restype = C.c_int
+    lib.pmt_workspace_size.restype = C.c_size_t
+    lib.pmt_workspace_size.argtypes = [C.POINTER(PmtModelDesc), C.POINTER(PmtBatch), C.c_int]
+    lib.pmt_forward.restype = C.c_int
+    lib.pmt_forward.argtypes = [C.POINTER(PmtModelDesc), C.c_void_p, C.POINTER(PmtBatch), C.POINTER(PmtOutputs),
+                                C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.pmt_backward.restype = C.c_int
+    lib.pmt_backward.argtypes = [C.POINTER(PmtModelDesc), C.c_void_p, C.POINTER(PmtBatch), C.POINTER(PmtOutGrads),
+                                 C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.pmt_decode_reads.restype = C.c_int
+    lib.pmt_decode_reads.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
+    if lib.pmt_abi_version() != PMT_ABI_VERSION:
+        raise RuntimeError(f"libpermutect_b200 ABI {lib.pmt_abi_version()} != binding {PMT_ABI_VERSION}")
+    _LIB = lib
+    return lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise RuntimeError("libpermutect_b200: " + load().pmt_last_error().decode())

@@ -1,0 +1,161 @@
+"""Translates an ArtifactModel into the kernel-facing description: a PmtModelDesc (layer programs
+and offsets into a flat weight buffer) plus the list of materialised tensors that fills that buffer.
+
+Flat layout: one slot per entry of ``model.named_parameters()``, in that order and with that shape
+(SURVEY.md Appendix B).  A slot whose parameter is the ``original`` of a torch parametrisation holds
+the CONSTRAINED value the reference's forward would see (bounded stdev, unit directions, log-softmax
+weights, exp(reg_weight), the orthogonal rotation matrix), so autograd chains the constraint
+Jacobians when the flat buffer is assembled with ``torch.cat``.
+"""
+from typing import Dict, List, Tuple
+
+import torch
+
+from permutect_b200.engine import library as L
+
+_PARAM_TAG = ".parametrizations."
+
+
+def flat_layout(model) -> Tuple[Dict[str, int], int]:
+    offsets, off = {}, 0
+    for name, p in model.named_parameters():
+        offsets[name] = off
+        off += p.numel()
+    return offsets, off
+
+
+def _owner_and_attr(model, name: str):
+    """'a.b.parametrizations.x.original' -> (module a.b, 'x')."""
+    head, tail = name.split(_PARAM_TAG)
+    attr = tail.split(".")[0]
+    module = model.get_submodule(head) if head else model
+    return module, attr
+
+
+def materialized_tensors(model) -> List[torch.Tensor]:
+    """Tensors to concatenate into the flat weight buffer (autograd-connected to the raw parameters)."""
+    out = []
+    for name, p in model.named_parameters():
+        if _PARAM_TAG in name:
+            module, attr = _owner_and_attr(model, name)
+            t = getattr(module, attr)                       # evaluates the parametrisation
+            if attr == "artifact_directions_ke":
+                # the head normalises the (already unit) directions once more (feature_clustering.py:24, quirk Q5)
+                t = t / torch.norm(t, dim=-1, keepdim=True)
+            out.append(t)
+        else:
+            out.append(p)
+    return out
+
+
+def _mlp_ops(offsets: Dict[str, int], prefix: str, layer_sizes: List[int]):
+    """mlp.py:39-66 as a flat program of Linear ops."""
+    ops, idx, in_dim = [], 0, layer_sizes[0]
+    n_entries = len(layer_sizes) - 1
+    for k, width in enumerate(layer_sizes[1:]):
+        if width < 0:
+            depth = -width
+            for j in range(depth):
+                flags = (L.OP_SKIP_BEGIN if j == 0 else 0) | (L.OP_SKIP_END if j == depth - 1 else L.OP_POST_SELU)
+                base = f"{prefix}._model.{idx}.mlp._model.{2 * j + 1}"
+                ops.append(L.PmtLinearOp(in_dim, in_dim, offsets[base + ".weight"], offsets[base + ".bias"],
+                                         offsets[f"{prefix}._model.{idx}.alpha"], flags))
+            idx += 1
+            continue
+        post = k < n_entries - 1
+        base = f"{prefix}._model.{idx}"
+        ops.append(L.PmtLinearOp(in_dim, width, offsets[base + ".weight"], offsets[base + ".bias"], -1,
+                                 L.OP_POST_SELU if post else 0))
+        idx += 2 if post else 1
+        in_dim = width
+    if len(ops) > L.MAX_MLP_OPS:
+        raise NotImplementedError(f"{prefix}: more than {L.MAX_MLP_OPS} linear layers")
+    return ops
+
+
+def _cnn_ops(offsets: Dict[str, int], prefix: str, layers: List[dict]):
+    """dna_sequence_convolution.py:57-99 as conv / pool / linear ops with activations folded into the
+    preceding conv or linear (a monotone activation commutes exactly with the max-pools between)."""
+    ops = []
+    act_code = {"selu": L.ACT_SELU, "leaky_relu": L.ACT_LEAKY_RELU}
+    for i, rec in enumerate(layers):
+        kind = rec["kind"]
+        if kind == "convolution":
+            ops.append(L.PmtCnnOp(L.CNN_CONV, rec["in_ch"], rec["out_ch"], rec["kernel_size"], 1, rec["in_len"],
+                                  rec["out_len"], L.ACT_NONE, offsets[f"{prefix}._model.{i}.weight"],
+                                  offsets[f"{prefix}._model.{i}.bias"]))
+        elif kind == "pool":
+            ops.append(L.PmtCnnOp(L.CNN_POOL, rec["in_ch"], rec["in_ch"], rec["kernel_size"],
+                                  rec.get("stride", rec["kernel_size"]), rec["in_len"], rec["out_len"], L.ACT_NONE, -1, -1))
+        elif kind in act_code:
+            target = next((o for o in reversed(ops) if o.kind in (L.CNN_CONV, L.CNN_LINEAR)), None)
+            if target is None or target.act != L.ACT_NONE:
+                raise NotImplementedError("activation without a preceding conv/linear layer, or two in a row")
+            target.act = act_code[kind]
+        elif kind == "flatten":
+            continue
+        elif kind == "linear":
+            ops.append(L.PmtCnnOp(L.CNN_LINEAR, rec["in_ch"], rec["out_ch"], 1, 1, 1, 1, L.ACT_NONE,
+                                  offsets[f"{prefix}._model.{i}.weight"], offsets[f"{prefix}._model.{i}.bias"]))
+    if len(ops) > L.MAX_CNN_OPS:
+        raise NotImplementedError(f"haplotype CNN: more than {L.MAX_CNN_OPS} layers")
+    return ops
+
+
+def build_desc(model, read_row_bytes: int = 12) -> L.PmtModelDesc:
+    offsets, n_params = flat_layout(model)
+    hp = model._params
+    d = L.PmtModelDesc()
+    d.abi_version = L.PMT_ABI_VERSION
+    d.n_read_features = model.read_embedding.input_dimension()
+    d.read_row_bytes = d.n_read_features - 56 + 7
+    d.n_info_features = model.info_embedding.input_dimension()
+    d.hap_len = model.haplotypes_length() // 2
+    d.d_read = model.read_embedding.output_dimension()
+    d.d_info = model.info_embedding.output_dimension()
+    d.d_seq = model.haplotypes_cnn.output_dimension()
+    d.d_model = d.d_read + d.d_info + d.d_seq
+    d.d_ffn = hp.self_attention_hidden_dimension
+    d.n_blocks = hp.num_self_attention_layers
+    d.d_feat = model.reducer.output_dimension()
+    d.n_clusters = hp.num_artifact_clusters
+    if d.n_blocks > L.MAX_BLOCKS:
+        raise NotImplementedError(f"more than {L.MAX_BLOCKS} gated blocks")
+
+    for field, count, ops in (
+            ("read_ops", "n_read_ops", _mlp_ops(offsets, "read_embedding", [d.n_read_features] + list(hp.read_layers))),
+            ("info_ops", "n_info_ops", _mlp_ops(offsets, "info_embedding", [d.n_info_features] + list(hp.info_layers))),
+            ("red_ops", "n_red_ops", _mlp_ops(offsets, "reducer", [d.d_model] + list(hp.aggregation_layers))),
+            ("cnn_ops", "n_cnn_ops", _cnn_ops(offsets, "haplotypes_cnn", model.haplotypes_cnn.layers))):
+        setattr(d, count, len(ops))
+        arr = getattr(d, field)
+        for i, op in enumerate(ops):
+            arr[i] = op
+
+    for b in range(d.n_blocks):
+        p = f"ref_alt_reads_encoder.blocks.{b}"
+        o = d.blocks[b]
+        o.ln_w, o.ln_b = offsets[p + ".norm.weight"], offsets[p + ".norm.bias"]
+        o.p1_ref_w, o.p1_ref_b = offsets[p + ".proj1_ref.weight"], offsets[p + ".proj1_ref.bias"]
+        o.p1_alt_w, o.p1_alt_b = offsets[p + ".proj1_alt.weight"], offsets[p + ".proj1_alt.bias"]
+        o.alpha_ref, o.alpha_alt = offsets[p + ".sgu.alpha_ref"], offsets[p + ".sgu.alpha_alt"]
+        o.beta_ref, o.beta_alt = offsets[p + ".sgu.beta_ref"], offsets[p + ".sgu.beta_alt"]
+        o.gamma = offsets[p + ".sgu.gamma"]
+        o.regularizer = offsets[p + ".sgu.ref_regularizer"]
+        o.ln2_w, o.ln2_b = offsets[p + ".sgu.norm.weight"], offsets[p + ".sgu.norm.bias"]
+        o.reg_weight = offsets[p + ".sgu.parametrizations.reg_weight.original"]
+        o.p2_ref_w, o.p2_ref_b = offsets[p + ".proj2_ref.weight"], offsets[p + ".proj2_ref.bias"]
+        o.p2_alt_w, o.p2_alt_b = offsets[p + ".proj2_alt.weight"], offsets[p + ".proj2_alt.bias"]
+
+    d.translation = offsets["pre_clustering_transform.translation_e"]
+    d.rotation = offsets["pre_clustering_transform.rotation_ee.parametrizations.weight.original"]
+    fc = "feature_clustering"
+    d.sigma_e = offsets[fc + ".parametrizations.nonartifact_stdev_e.original"]
+    d.unit_ke = offsets[fc + ".parametrizations.artifact_directions_ke.original"]
+    d.tau_k = offsets[fc + ".parametrizations.artifact_stdev_k.original"]
+    d.logw_k = offsets[fc + ".parametrizations.log_cluster_weights_k.original"]
+    d.mu_k = offsets[fc + ".artifact_emg.mu_k"]
+    d.emg_sigma_k = offsets[fc + ".artifact_emg.parametrizations.sigma_k.original"]
+    d.lambda_k = offsets[fc + ".artifact_emg.parametrizations.lambda_k.original"]
+    d.n_params = n_params
+    return d
