@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""Benchmark of the ArtifactModel hot path (BASELINE.json metric: ArtifactModel variants/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--variants V] [--impl reference]
+
+A step is one pass of the fused forward (compute_batch_output: every BatchOutput field) over one
+shard of synthetic WGS-shaped variants (10M variants sharded by variant
+over 8 GPUs -> 1.25M variants per GPU; weak scaling, per-GPU shard fixed).  `value` is measured with
+the shard resident in HBM; `e2e` goes through the public API with pinned HOST buffers, H2D of the
+compressed shard and D2H of the logits inside the timed region.  `train` (when the backward kernels
+are built) is one forward + losses + backward + clip + AdamW step per batch.
+
+`--impl reference` times the CPU restatement of the reference (oracle/, kind "port": the Python
+reference cannot travel to the GPU box) on the host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, "tests"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+V040 = dict(read_layers=[30, -2, -2, -2], self_attention_hidden_dimension=20, num_self_attention_layers=6,
+            info_layers=[20, -2, -2, -2], aggregation_layers=[-2, -2, 10], num_artifact_clusters=4,
+            calibration_layers=[20, 20, 20, 20, 10],
+            ref_seq_layer_strings=['convolution/kernel_size=3/out_channels=32', 'selu', 'pool/kernel_size=2/stride=1',
+                                   'convolution/kernel_size=3/out_channels=32', 'selu', 'pool/kernel_size=1',
+                                   'convolution/kernel_size=5/out_channels=32', 'selu', 'pool/kernel_size=2',
+                                   'convolution/kernel_size=5/out_channels=32', 'selu', 'pool/kernel_size=2',
+                                   'flatten', 'linear/out_features=10'],
+            dropout_p=0.0, reweighting_range=0.0, batch_normalize=False, num_sources=1)
+
+# algorithmic work per unit, forward: MAC = 2 FLOP, unpadded dims
+FLOP_PER_READ = 66260
+FLOP_PER_ALT_READ = 500
+FLOP_PER_VARIANT = 286424
+FP32_FMA_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12      # nominal B200 FP32 pipe
+
+
+def load_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], bf16=p.get("bf16_tflops_sustained", p["bf16_tflops"]), source="measured")
+    return dict(hbm=6650.0, bf16=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu_index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 8 for i in range(4) if r[4 + i].lower() == "active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def make_model(device):
+    from helpers import params_from_hp
+    from permutect_b200.architecture.artifact_model import ArtifactModel
+    torch.manual_seed(0)
+    model = ArtifactModel(params_from_hp(V040), 61, 71, 42, device=device)
+    # move every scalar away from its init so no term is numerically hidden
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for _, p in model.named_parameters():
+            if p.dim() == 0:
+                p.copy_(0.05 + 0.1 * torch.rand((), generator=g))
+    return model
+
+
+def oracle_inputs(ia, fa, reads):
+    return dict(reads_u8=reads, read_indices=None, ref_counts=ia[:, 0], alt_counts=ia[:, 1],
+                info=fa[:, 6:].astype(np.float32), haplotypes=ia[:, 16:], labels=ia[:, 2], sources=ia[:, 4])
+
+
+def time_oracle(model_sd, n_variants, seed, budget_s=20.0, train=False):
+    """CPU restatement of the reference on all host cores, bounded sample.  Returns variants/s."""
+    from oracle import artifact_oracle as orc
+    from permutect_b200.synthetic import make_wgs_arrays
+    torch.set_num_threads(os.cpu_count())
+    ia, fa, reads = make_wgs_arrays(n_variants, seed=seed)
+    raw = oracle_inputs(ia, fa, reads)
+    sd = {k: v.detach().cpu() for k, v in model_sd.items()}
+    times = []
+    t_end = time.perf_counter() + budget_s
+    it = 0
+    while True:
+        t0 = time.perf_counter()
+        if train:
+            orc.loss_and_grads(sd, V040, raw, [k for k in sd if sd[k].dtype.is_floating_point and "base" not in k])
+        else:
+            with torch.no_grad():
+                orc.forward(sd, V040, raw)
+        dt = time.perf_counter() - t0
+        if it > 0:
+            times.append(dt)
+        it += 1
+        if (time.perf_counter() > t_end and len(times) >= 2) or len(times) >= 10:
+            break
+    return n_variants / float(np.median(times)), len(times)
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    model = make_model(torch.device("cpu"))
+    sample = 8192
+    steps, warm = max(args.steps, 1), args.warmup
+    from oracle import artifact_oracle as orc
+    from permutect_b200.synthetic import make_wgs_arrays
+    torch.set_num_threads(os.cpu_count())
+    ia, fa, reads = make_wgs_arrays(sample, seed=3000)
+    raw = oracle_inputs(ia, fa, reads)
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    ts = []
+    budget_end = time.perf_counter() + 150.0
+    for i in range(warm + steps):
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            orc.forward(sd, V040, raw)
+        if i >= warm:
+            ts.append(time.perf_counter() - t0)
+        if time.perf_counter() > budget_end and len(ts) >= 1:
+            break
+    ms = 1e3 * float(np.mean(ts))
+    v = sample / (ms / 1e3)
+    sample_txt = f"{sample} WGS-shaped variants per step (batch of the same synthetic distribution), {len(ts)} steps"
+    print(json.dumps({
+        "impl": "reference", "metric": "artifact_model_inference_variants_per_sec", "value": v, "unit": "variants/s",
+        "n_gpus": args.gpus, "steps": len(ts), "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "synthetic WGS-scale inference (SURVEY §8d config 3), CPU sample", "variants_per_step": sample},
+        "cpu_baseline": {"value": v, "unit": "variants/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample_txt},
+        "e2e": {"value": v, "unit": "variants/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--variants", type=int, default=1_250_000, help="variants per GPU shard")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch.distributed as dist
+    from permutect_b200.data.batch import Batch
+    from permutect_b200.engine import function as engine
+    from permutect_b200.synthetic import make_wgs_arrays
+    from permutect_b200.utils.enums import Epoch
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    model = make_model(dev)
+    model.set_epoch_type(Epoch.VALID)
+    ia, fa, reads = make_wgs_arrays(args.variants, seed=1000 * 3 + rank)
+    n_reads = len(reads)
+    n_alt = int(ia[:, 1].sum())
+    host_batch = Batch.from_arrays(ia, fa, reads).pin_memory()
+    dev_batch = host_batch.copy_to(dev)
+    dev_batch.offsets()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+
+    # ---- device-resident throughput -------------------------------------------------------------------
+    with torch.inference_mode():
+        for _ in range(args.warmup):
+            model.compute_batch_output(dev_batch)
+        barrier()
+        sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        prof = engine.ProfileEvents(dev)             # CUDA events around the dominant kernel, same stream
+        ev0.record()
+        for _ in range(args.steps):
+            prof.arm()
+            model.compute_batch_output(dev_batch)
+        ev1.record()
+        barrier()
+        clocks = sampler.stop()
+        step_ms = ev0.elapsed_time(ev1) / args.steps
+        read_kernel_ms = prof.mean_ms()
+    t = torch.tensor([step_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    step_ms_max = float(t.item())
+    value = args.variants * world / (step_ms_max / 1e3)
+
+    # ---- end to end through the public API: pinned host shard -> H2D -> forward -> D2H logits ----------
+    h2d = host_batch.h2d_bytes()
+    logits_host = torch.empty(args.variants, dtype=torch.float32).pin_memory()
+    with torch.inference_mode():
+        for _ in range(2):
+            out = model.compute_batch_output(host_batch.copy_to(dev))
+            logits_host.copy_(out.logits_b, non_blocking=True)
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            out = model.compute_batch_output(host_batch.copy_to(dev))
+            logits_host.copy_(out.logits_b, non_blocking=True)
+        ev1.record()
+        barrier()
+        e2e_ms = ev0.elapsed_time(ev1) / args.steps
+    t = torch.tensor([e2e_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = args.variants * world / (float(t.item()) / 1e3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = load_peaks()
+    flops = FLOP_PER_READ * n_reads + FLOP_PER_ALT_READ * n_alt        # the read kernel's algorithmic work
+    achieved = flops / (read_kernel_ms / 1e3) / 1e12 if read_kernel_ms else None
+    roofline = {"bound": "tensor", "kernel": "reads_forward_kernel (FP32 SIMT mode)", "achieved": achieved,
+                "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16"] if achieved else None,
+                "peak_source": peaks["source"] + " bf16 dense (sustained)", "traffic": None,
+                "kernel_ms": read_kernel_ms, "kernel_share_of_step": read_kernel_ms / step_ms if read_kernel_ms else None,
+                "fp32_fma_peak_tflops_nominal": FP32_FMA_PEAK_TFLOPS,
+                "frac_of_fp32_fma_peak": achieved / FP32_FMA_PEAK_TFLOPS if achieved else None,
+                "flop_per_launch": flops}
+    result = {
+        "metric": "artifact_model_inference_variants_per_sec", "value": value, "unit": "variants/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms_max, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "synthetic WGS-scale inference (SURVEY §8d config 3: 10M variants / 8 GPUs)",
+                   "variants_per_gpu": args.variants, "reads_per_gpu": n_reads, "mean_reads_per_variant": n_reads / args.variants,
+                   "hyperparameters": "artifact-model-v0.4.0", "timing": "inputs larger than L2 (compressed shard "
+                   f"{h2d / 2**20:.0f} MiB), CUDA events, max over ranks"},
+        "clocks": clocks, "gpu_launches": 5 * args.steps,
+        "e2e": {"value": e2e_value, "unit": "variants/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * args.variants},
+        "roofline": roofline,
+    }
+    if not args.no_cpu_baseline:
+        sample = 8192
+        v, n_it = time_oracle(model.state_dict(), sample, seed=3000, budget_s=15.0)
+        result["cpu_baseline"] = {"value": v, "unit": "variants/s", "cores": torch.get_num_threads(), "kind": "port",
+                                  "sample": f"oracle forward on {sample} WGS-shaped variants per batch, median of {n_it} batches"}
+    print(json.dumps(result))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

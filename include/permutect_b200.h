@@ -158,6 +158,11 @@ int pmt_forward(const PmtModelDesc* desc, const float* weights, const PmtBatch* 
 int pmt_backward(const PmtModelDesc* desc, const float* weights, const PmtBatch* batch, const PmtOutGrads* grads,
                  float* d_weights, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Measurement hook (no reference counterpart): when both are non-NULL, the next pmt_forward /
+ * pmt_backward calls on this host thread record these cudaEvent_t around their dominant kernel
+ * (reads_forward_kernel / reads_backward_kernel) on the call's stream.  Pass NULLs to disarm. */
+int pmt_set_profile_events(void* start_event, void* stop_event);
+
 /* Batch.__init__ decode (batch.py:51-56, plain_text_data.py:510-511): compressed rows -> [R][F] float32. */
 int pmt_decode_reads(const uint8_t* reads_u8, int64_t n_rows, int32_t row_bytes, float* out, void* stream);
 

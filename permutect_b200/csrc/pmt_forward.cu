@@ -637,6 +637,14 @@ void pmt_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 extern "C" const char* pmt_last_error(void) { return g_err; }
+static thread_local cudaEvent_t g_prof_start = nullptr, g_prof_stop = nullptr;
+extern "C" int pmt_set_profile_events(void* start_event, void* stop_event) {
+  g_prof_start = reinterpret_cast<cudaEvent_t>(start_event);
+  g_prof_stop = reinterpret_cast<cudaEvent_t>(stop_event);
+  return 0;
+}
+void pmt_profile_begin(cudaStream_t st) { if (g_prof_start && g_prof_stop) cudaEventRecord(g_prof_start, st); }
+void pmt_profile_end(cudaStream_t st) { if (g_prof_start && g_prof_stop) cudaEventRecord(g_prof_stop, st); }
 extern "C" int pmt_abi_version(void) { return PMT_ABI_VERSION; }
 
 static void choose_groups(int N, int* G, int* NT) {
@@ -829,7 +837,9 @@ extern "C" int pmt_forward(const PmtModelDesc* desc, const float* weights, const
   cudaFuncSetAttribute(reads_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int n_claims = (batch->n_variants + P.claim_variants - 1) / P.claim_variants;
   const int grid = n_claims < n_sm ? n_claims : n_sm;
+  pmt_profile_begin(st);
   reads_forward_kernel<<<grid, NTHREADS, smem, st>>>(P, A);
+  pmt_profile_end(st);
   cudaError_t e = cudaGetLastError();
   PMT_CHECK(e == cudaSuccess, "pmt_forward launch failed: %s", cudaGetErrorString(e));
   return 0;

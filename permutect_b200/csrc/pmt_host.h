@@ -21,3 +21,5 @@ int pmt_launch_prepare(const pmt::Plan& P, const pmt::CnnGeom& G, const float* w
 int pmt_launch_variant_kernels(const pmt::Plan& P, const pmt::CnnGeom& G, const float* weights, const float* image,
                                const PmtBatch* batch, float* info_seq, cudaStream_t st);
 size_t pmt_backward_workspace_bytes(const pmt::Plan& P, const PmtBatch* batch);
+void pmt_profile_begin(cudaStream_t st);
+void pmt_profile_end(cudaStream_t st);

@@ -105,3 +105,27 @@ class FusedArtifactFunction(torch.autograd.Function):
             g[:, 2:] -= g_out[:, None] * sm[:, 1:]
         d_flat = backward_call(ctx.desc, flat, ctx.batch, g, g_alt, g_ref)
         return d_flat, None, None
+
+
+class ProfileEvents:
+    """CUDA-event timing of the library's dominant kernel (pmt_set_profile_events).  ``arm()`` before a
+    call gives that call a fresh event pair; ``mean_ms()`` (after a synchronize) averages the pairs."""
+
+    def __init__(self, device):
+        self.device, self.pairs = device, []
+
+    def arm(self):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stream = torch.cuda.current_stream(self.device)
+        a.record(stream)      # instantiates the underlying cudaEvent_t
+        b.record(stream)
+        L.load().pmt_set_profile_events(a.cuda_event, b.cuda_event)
+        self.pairs.append((a, b))
+
+    def disarm(self):
+        L.load().pmt_set_profile_events(None, None)
+
+    def mean_ms(self) -> float:
+        self.disarm()
+        times = [a.elapsed_time(b) for a, b in self.pairs]
+        return sum(times) / len(times) if times else float("nan")
