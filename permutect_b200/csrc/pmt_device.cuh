@@ -45,6 +45,15 @@ struct Plan {
   int info_stage_floats;
   int sum_w;                             // width of the per-variant sum scratch: max(d_ffn/2, d_feat)
   int claim_variants;                    // variants claimed per scheduling step
+  // per-CTA activation scratch of the backward kernel: feature-major [nf][LD] images, float offsets
+  int scr_read[PMT_MAX_MLP_OPS + 1];     // input of read op i; [n_read_ops] unused
+  int scr_red[PMT_MAX_MLP_OPS + 1];      // input of reducer op i; [n_red_ops] = reducer output y
+  int scr_x[PMT_MAX_BLOCKS];             // x entering gated block b
+  int scr_z[PMT_MAX_BLOCKS];             // z = SELU(proj1(LN x)) of block b (before the SGU LayerNorm)
+  int scratch_floats;
+  // transposed images for the backward data-gradient GEMMs (same GemmOp index, K and N swapped)
+  int imgT_off[MAX_GEMM], imgT_floats[MAX_GEMM], GT[MAX_GEMM], NTT[MAX_GEMM];
+  int imgT_total, stageT_floats;
   GemmOp gemm[MAX_GEMM];
 };
 
@@ -57,8 +66,24 @@ struct CnnGeom {
   int n_spatial;                 // ops before the first PMT_CNN_LINEAR
 };
 
+// Branch-free: the exponential is evaluated for every lane (argument clamped to <= 0) and selected.
 __device__ __forceinline__ float selu(float x) {
-  return SELU_SCALE * (x > 0.f ? x : SELU_ALPHA * (expf(x) - 1.f));
+  const float neg = SELU_ALPHA * (expf(fminf(x, 0.f)) - 1.f);
+  return SELU_SCALE * (x > 0.f ? x : neg);
+}
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ float4 lds128(unsigned a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float lds32(unsigned a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts128(unsigned a, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 // d selu / dx expressed through the OUTPUT y = selu(x): y > 0 -> scale, else y + scale*alpha
 __device__ __forceinline__ float selu_grad_from_out(float y) {
@@ -74,33 +99,34 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 // Double-buffered weight stage.  All control flow is CTA-uniform.
 struct Stage {
-  float* buf[2];
-  int resident[2];  // GemmOp index held (or in flight) in each buffer, -1 = none
+  float* buf0;
+  float* buf1;
+  int res0, res1;   // GemmOp index held (or in flight) in each buffer, -1 = none
   int last;         // buffer most recently acquired
   bool pending;     // a prefetch into buf[last ^ 1] has been issued and not yet acquired
   const float* image;
   const Plan* plan;
 
   __device__ __forceinline__ void init(float* b0, float* b1, const float* img, const Plan* p) {
-    buf[0] = b0; buf[1] = b1; resident[0] = resident[1] = -1; last = 1; pending = false; image = img; plan = p;
+    buf0 = b0; buf1 = b1; res0 = res1 = -1; last = 1; pending = false; image = img; plan = p;
   }
   __device__ __forceinline__ void issue(int slot, int g) {
     const GemmOp& op = plan->gemm[g];
     const float4* src = reinterpret_cast<const float4*>(image + op.img_off);
-    float4* dst = reinterpret_cast<float4*>(buf[slot]);
+    float4* dst = reinterpret_cast<float4*>(slot ? buf1 : buf0);
     for (int i = threadIdx.x; i < op.img_floats / 4; i += NTHREADS) cp_async16(dst + i, src + i);
     cp_async_commit();
-    resident[slot] = g;
+    if (slot) res1 = g; else res0 = g;
   }
   // Start loading op g (if it is not already resident) into the buffer that is NOT in use.
   __device__ __forceinline__ void prefetch(int g) {
-    if (g < 0 || pending || resident[0] == g || resident[1] == g) return;
+    if (g < 0 || pending || res0 == g || res1 == g) return;
     issue(last ^ 1, g);
     pending = true;
   }
   // Make op g available; contains a __syncthreads() (which also orders the preceding activation writes).
   __device__ __forceinline__ const float* acquire(int g) {
-    int slot = resident[0] == g ? 0 : (resident[1] == g ? 1 : -1);
+    int slot = res0 == g ? 0 : (res1 == g ? 1 : -1);
     if (slot < 0) {
       slot = last ^ 1;
       cp_async_wait_all();
@@ -111,43 +137,45 @@ struct Stage {
     __syncthreads();
     last = slot;
     pending = false;
-    return buf[slot];
+    return slot ? buf1 : buf0;
   }
 };
 
 enum Epilogue { EPI_STORE = 0, EPI_SELU = 1, EPI_RESIDUAL = 2 };
 
 template <int NT>
-__device__ __forceinline__ void gemm_tile_nt(const float* __restrict__ X, const GemmOp& op, const float* __restrict__ img,
-                                             const float* __restrict__ wflat, int ref_rows_padded, float* __restrict__ Y,
-                                             int epilogue, float alpha, int rows_used) {
+__device__ __noinline__ void gemm_tile_nt(unsigned x_s, int K, int N, int G, bool dual, int b_off, int b_alt_off,
+                                          unsigned img_s, const float* __restrict__ wflat, int ref_rows_padded,
+                                          unsigned y_s, int epilogue, float alpha, int rows_used) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r0 = lane * 4;
   if (r0 >= rows_used) return;
-  const bool is_alt = (op.w_alt_off >= 0) && (r0 >= ref_rows_padded);
-  const int wstride = op.G * GROUP_STRIDE;
-  const float* wimg = img + (is_alt ? op.K * wstride : 0);
-  const int boff = is_alt ? op.b_alt_off : op.b_off;
-  for (int g = warp; g < op.G; g += NWARPS) {
+  const bool is_alt = dual && (r0 >= ref_rows_padded);
+  const int wstride = G * GROUP_STRIDE * 4;  // bytes
+  const unsigned wimg = img_s + (is_alt ? K * wstride : 0);
+  const int boff = is_alt ? b_alt_off : b_off;
+  for (int g = warp; g < G; g += NWARPS) {
     float acc[4][NT];
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
       const int n = g * NT + j;
-      const float b = (boff >= 0 && n < op.N) ? __ldg(wflat + boff + n) : 0.f;
+      const float b = (boff >= 0 && n < N) ? __ldg(wflat + boff + n) : 0.f;
       acc[0][j] = b; acc[1][j] = b; acc[2][j] = b; acc[3][j] = b;
     }
-    const float* xp = X + r0;
-    const float* wp = wimg + g * GROUP_STRIDE;
+    unsigned xp = x_s + r0 * 4;
+    unsigned wp = wimg + g * GROUP_STRIDE * 4;
 #pragma unroll 4
-    for (int k = 0; k < op.K; ++k) {
-      const float4 x = *reinterpret_cast<const float4*>(xp + k * LD);
+    for (int k = 0; k < K; ++k) {
+      const float4 x = lds128(xp);
       float w[8];
-      const float4 w0 = *reinterpret_cast<const float4*>(wp + k * wstride);
+      const float4 w0 = lds128(wp);
       w[0] = w0.x; w[1] = w0.y; w[2] = w0.z; w[3] = w0.w;
       if (NT > 4) {
-        const float4 w1 = *reinterpret_cast<const float4*>(wp + k * wstride + 4);
+        const float4 w1 = lds128(wp + 16);
         w[4] = w1.x; w[5] = w1.y; w[6] = w1.z; w[7] = w1.w;
       }
+      xp += LD * 4;
+      wp += wstride;
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
         acc[0][j] = fmaf(x.x, w[j], acc[0][j]);
@@ -159,16 +187,16 @@ __device__ __forceinline__ void gemm_tile_nt(const float* __restrict__ X, const 
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
       const int n = g * NT + j;
-      if (n < op.N) {
-        float4* yp = reinterpret_cast<float4*>(Y + n * LD + r0);
+      if (n < N) {
+        const unsigned yp = y_s + (n * LD + r0) * 4;
         float4 v = make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]);
         if (epilogue == EPI_SELU) {
           v.x = selu(v.x); v.y = selu(v.y); v.z = selu(v.z); v.w = selu(v.w);
         } else if (epilogue == EPI_RESIDUAL) {
-          const float4 o = *yp;
+          const float4 o = lds128(yp);
           v.x = fmaf(alpha, v.x, o.x); v.y = fmaf(alpha, v.y, o.y); v.z = fmaf(alpha, v.z, o.z); v.w = fmaf(alpha, v.w, o.w);
         }
-        *yp = v;
+        sts128(yp, v);
       }
     }
   }
@@ -178,16 +206,16 @@ __device__ __forceinline__ void gemm_tile_nt(const float* __restrict__ X, const 
 // EPI_RESIDUAL with Y disjoint from X.  Caller synchronises before consumers read Y.
 __device__ __forceinline__ void gemm_tile(const float* X, const GemmOp& op, const float* img, const float* wflat,
                                           int ref_rows_padded, float* Y, int epilogue, float alpha, int rows_used) {
+  const unsigned xs = smem_addr(X), is = smem_addr(img), ys = smem_addr(Y);
+  const int K = op.K, N = op.N, G = op.G, b = op.b_off, ba = op.b_alt_off;
+  const bool dual = op.w_alt_off >= 0;
+#define PMT_GEMM_CASE(NT_) case NT_: gemm_tile_nt<NT_>(xs, K, N, G, dual, b, ba, is, wflat, ref_rows_padded, ys, epilogue, alpha, rows_used); break;
   switch (op.NT) {
-    case 1: gemm_tile_nt<1>(X, op, img, wflat, ref_rows_padded, Y, epilogue, alpha, rows_used); break;
-    case 2: gemm_tile_nt<2>(X, op, img, wflat, ref_rows_padded, Y, epilogue, alpha, rows_used); break;
-    case 3: gemm_tile_nt<3>(X, op, img, wflat, ref_rows_padded, Y, epilogue, alpha, rows_used); break;
-    case 4: gemm_tile_nt<4>(X, op, img, wflat, ref_rows_padded, Y, epilogue, alpha, rows_used); break;
-    case 5: gemm_tile_nt<5>(X, op, img, wflat, ref_rows_padded, Y, epilogue, alpha, rows_used); break;
-    case 6: gemm_tile_nt<6>(X, op, img, wflat, ref_rows_padded, Y, epilogue, alpha, rows_used); break;
-    case 7: gemm_tile_nt<7>(X, op, img, wflat, ref_rows_padded, Y, epilogue, alpha, rows_used); break;
-    default: gemm_tile_nt<8>(X, op, img, wflat, ref_rows_padded, Y, epilogue, alpha, rows_used); break;
+    PMT_GEMM_CASE(1) PMT_GEMM_CASE(2) PMT_GEMM_CASE(3) PMT_GEMM_CASE(4)
+    PMT_GEMM_CASE(5) PMT_GEMM_CASE(6) PMT_GEMM_CASE(7)
+    default: gemm_tile_nt<8>(xs, K, N, G, dual, b, ba, is, wflat, ref_rows_padded, ys, epilogue, alpha, rows_used); break;
   }
+#undef PMT_GEMM_CASE
 }
 
 // dst[f][r] = selu(src[f][r]) for f < nf (all TILE rows; padding rows hold finite garbage)
@@ -206,12 +234,26 @@ __device__ __forceinline__ void copy_features(const float* src, float* dst, int 
   }
 }
 
+// feature-major image <-> global scratch (nf features, all LD columns; 16-byte vectors)
+__device__ __forceinline__ void save_rows(const float* buf, int nf, float* g) {
+  const float4* s4 = reinterpret_cast<const float4*>(buf);
+  float4* g4 = reinterpret_cast<float4*>(g);
+  for (int i = threadIdx.x; i < nf * (LD / 4); i += NTHREADS) g4[i] = s4[i];
+}
+__device__ __forceinline__ void load_rows(float* buf, int nf, const float* g) {
+  float4* s4 = reinterpret_cast<float4*>(buf);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  for (int i = threadIdx.x; i < nf * (LD / 4); i += NTHREADS) s4[i] = g4[i];
+}
+
 // Runs an MLP program (mlp.py:25-76) over the tile.  `cur` holds the input; b0/b1/b2 are the three
 // activation buffers (cur is one of them).  Returns the buffer holding the output.
 // next_after: GemmOp to prefetch while the last layer runs (-1 = none).
-__device__ __forceinline__ float* run_mlp(const Plan& P, const PmtLinearOp* ops, int n_ops, int g0, float* cur,
+static __device__ __noinline__ float* run_mlp(const Plan& P, const PmtLinearOp* ops, int n_ops, int g0, float* cur,
                                           float* b0, float* b1, float* b2, Stage& stage, const float* wflat,
-                                          int rows_used, int next_after) {
+                                          int rows_used, int next_after, float* scr = nullptr,
+                                          const int* scr_off = nullptr) {
+  // scr != nullptr: the activation entering every op is saved to scr + scr_off[i] (backward recompute pass)
   float* res = nullptr;
   for (int i = 0; i < n_ops; ++i) {
     const PmtLinearOp& lop = ops[i];
@@ -221,11 +263,13 @@ __device__ __forceinline__ float* run_mlp(const Plan& P, const PmtLinearOp* ops,
       res = cur;
       float* tmp = (b0 != cur) ? b0 : b1;
       __syncthreads();  // producers of `cur` are done
+      if (scr) save_rows(cur, lop.in_dim, scr + scr_off[i]);
       selu_copy(cur, tmp, lop.in_dim);
       src = tmp;
     }
     const float* img = stage.acquire(g0 + i);
     stage.prefetch(i + 1 < n_ops ? g0 + i + 1 : next_after);
+    if (scr && !(lop.flags & PMT_OP_SKIP_BEGIN)) save_rows(cur, lop.in_dim, scr + scr_off[i]);
     if (lop.flags & PMT_OP_SKIP_END) {
       gemm_tile(src, gop, img, wflat, 0, res, EPI_RESIDUAL, __ldg(wflat + lop.alpha_off), rows_used);
       cur = res;

@@ -8,8 +8,8 @@
 #include <cstdio>
 #include <cstring>
 
-#include "pmt_device.cuh"
 #include "pmt_host.h"
+#include "pmt_tile.cuh"
 
 namespace pmt {
 
@@ -258,111 +258,26 @@ hap_cnn_kernel(const __grid_constant__ Plan P, const __grid_constant__ CnnGeom G
 // ------------------------------------------------------------------------------------------------
 // read path
 // ------------------------------------------------------------------------------------------------
-struct HeadConst {   // per-CTA constants of the clustering head (feature_clustering.py:82-119)
-  float sigma[PMT_MAX_FEAT];
-  float c_non, c_out;
-  float c_orth[PMT_MAX_CLUSTERS], inv_two_tau2[PMT_MAX_CLUSTERS];
-  float log_half_lambda[PMT_MAX_CLUSTERS], shift[PMT_MAX_CLUSTERS], inv_sqrt2_sigma[PMT_MAX_CLUSTERS],
-      half_lambda[PMT_MAX_CLUSTERS], two_mu_plus[PMT_MAX_CLUSTERS], logw[PMT_MAX_CLUSTERS];
-};
-
-struct TileMeta {
-  int nv;             // variants in the tile
-  int v0;             // first variant (global index)
-  int ref_pad;        // ref rows, padded to a multiple of 4; alt rows start here
-  int rows;           // ref_pad + alt rows
-  int next_v;
-  int rowvar[TILE];         // local variant of each row, -1 for padding
-  long long rowidx[TILE];   // batch row index of each row (position in [0, n_rows)), -1 for padding
-  int ref_start[TILE], ref_cnt[TILE], alt_start[TILE], alt_cnt[TILE];  // per local variant, tile row units
-};
-
-// exponentially_modified_gaussian.py:30-55
-__device__ __forceinline__ float logerfc(float z) {
-  if (z > 5.f) {
-    const float z2 = z * z, z4 = z2 * z2, z6 = z2 * z4;
-    return -z2 - logf(z * 1.7724538509055160273f) + log1pf(-1.f / (2.f * z2) + 3.f / (4.f * z4) - 15.f / (8.f * z6));
-  }
-  return logf(fmaxf(erfcf(z), 1.0e-12f));
-}
-
-__device__ __forceinline__ float logsumexp2(float a, float b) {
-  const float m = fmaxf(a, b);
-  return m + logf(expf(a - m) + expf(b - m));
-}
-
-struct ReadKernelArgs {
-  const float* wflat;
-  const float* image;
-  PmtBatch batch;
-  PmtOutputs out;
-  int* claim_counter;
-};
-
-// Per-variant sums of feature rows [f0, f0+nf) of `buf` over the ref rows and the alt rows
-// (ragged_sets.py:157-158).  out is [nv][2][sw].
-__device__ __forceinline__ void segment_sums(const TileMeta& M, const float* buf, int f0, int nf, float* out, int sw,
-                                             bool alt_only) {
-  const int sides = alt_only ? 1 : 2;
-  for (int idx = threadIdx.x; idx < M.nv * sides * nf; idx += NTHREADS) {
-    const int j = idx / (sides * nf), rem = idx % (sides * nf);
-    const int s = alt_only ? 1 : rem / nf, f = rem % nf;
-    const int start = s ? M.alt_start[j] : M.ref_start[j], cnt = s ? M.alt_cnt[j] : M.ref_cnt[j];
-    const float* p = buf + (f0 + f) * LD + start;
-    float sum = 0.f;
-    for (int i = 0; i < cnt; ++i) sum += p[i];
-    out[(j * 2 + s) * sw + f] = sum;
-  }
-}
-
+// Variants whose reads fit one tile (the only case on real data: reads are capped at 10 ref + 15 alt at
+// ingest, plain_text_data.py:172-174).  Persistent CTAs claim runs of variants from an atomic counter and
+// pack them greedily into tiles; everything between the compressed reads and the per-variant outputs
+// stays in shared memory.
 __global__ void __launch_bounds__(NTHREADS, 1)
 reads_forward_kernel(const __grid_constant__ Plan P, const __grid_constant__ ReadKernelArgs A) {
   extern __shared__ __align__(16) float smem[];
   const PmtModelDesc& D = P.d;
-  float* X = smem;
-  float* T1 = X + PMT_MAX_DIM * LD;
-  float* T2 = T1 + PMT_MAX_DIM * LD;
-  float* st0 = T2 + PMT_MAX_DIM * LD;
-  float* st1 = st0 + P.stage_floats;
-  float* sums = st1 + P.stage_floats;            // [TILE][2][sum_w]
-  float* llsum = sums + TILE * 2 * P.sum_w;      // [TILE][2][16] (alt side used)
-  HeadConst* HC = reinterpret_cast<HeadConst*>(llsum + TILE * 2 * 16);
-  TileMeta* Mp = reinterpret_cast<TileMeta*>((reinterpret_cast<uintptr_t>(HC + 1) + 15) & ~uintptr_t(15));
-  TileMeta& M = *Mp;
+  TileCtx C;
+  float *st0, *st1;
+  carve_tile_ctx(P, smem, C, st0, st1, P.stage_floats);
+  C.W = A.wflat;
   __shared__ int s_claim;
-
-  const float* W = A.wflat;
   const int tid = threadIdx.x;
-  const int row = tid & (TILE - 1), half = tid >> 7;
-  const int E = D.d_feat, K = D.n_clusters, Dm = D.d_model, H = D.d_ffn / 2;
   const int B = A.batch.n_variants;
-
   Stage stage;
   stage.init(st0, st1, A.image, &P);
-
-  // head constants
-  if (tid == 0) {
-    float sum_log_sigma = 0.f;
-    for (int e = 0; e < E; ++e) { HC->sigma[e] = W[D.sigma_e + e]; sum_log_sigma += logf(W[D.sigma_e + e]); }
-    HC->c_non = -(E * 0.5f) * LOG_2PI - sum_log_sigma;
-    float sum_log_2sigma = 0.f;
-    for (int e = 0; e < E; ++e) sum_log_2sigma += logf(2.f * W[D.sigma_e + e]);
-    HC->c_out = -(E * 0.5f) * LOG_2PI - sum_log_2sigma;
-    for (int k = 0; k < K; ++k) {
-      const float tau = W[D.tau_k + k], lam = W[D.lambda_k + k], sg = W[D.emg_sigma_k + k], mu = W[D.mu_k + k];
-      HC->c_orth[k] = -((E - 1) * 0.5f) * LOG_2PI - (E - 1) * logf(tau);
-      HC->inv_two_tau2[k] = 2.f * tau * tau;  // divisor, kept as the reference writes it
-      HC->log_half_lambda[k] = logf(lam / 2.f);
-      HC->shift[k] = mu + lam * sg * sg;
-      HC->inv_sqrt2_sigma[k] = 1.41421356237309504880f * sg;  // divisor
-      HC->half_lambda[k] = lam / 2.f;
-      HC->two_mu_plus[k] = 2.f * mu + lam * sg * sg;
-      HC->logw[k] = W[D.logw_k + k];
-    }
-  }
-  for (int i = tid; i < 3 * PMT_MAX_DIM * LD; i += NTHREADS) X[i] = 0.f;
+  if (tid == 0) head_constants(D, C.W, C.HC);
+  for (int i = tid; i < 3 * PMT_MAX_DIM * LD; i += NTHREADS) C.X[i] = 0.f;
   __syncthreads();
-
   const long long total_ref = __ldg(A.batch.ref_off + B);  // == sum of ref counts
   const int claim = P.claim_variants;
 
@@ -374,234 +289,97 @@ reads_forward_kernel(const __grid_constant__ Plan P, const __grid_constant__ Rea
     if (cv0 >= B) break;
     const int cv1 = (int)min((long long)B, cv0 + claim);
     int v_cur = (int)cv0;
-
     while (v_cur < cv1) {
-      // ---------------- build the tile: greedily take whole variants while they fit ----------------
-      {
-        const long long r_base = __ldg(A.batch.ref_off + v_cur), a_base = __ldg(A.batch.alt_off + v_cur);
-        int fits = 0;
-        if (tid < TILE && v_cur + tid + 1 <= cv1) {
-          const long long nr = __ldg(A.batch.ref_off + v_cur + tid + 1) - r_base;
-          const long long na = __ldg(A.batch.alt_off + v_cur + tid + 1) - a_base;
-          fits = (((nr + 3) & ~3LL) + na <= TILE) ? 1 : 0;
-        }
-        const int nv = __syncthreads_count(fits);
-        if (nv == 0) {  // a single variant longer than the tile: not handled by this kernel
-          v_cur += 1;
-          continue;
-        }
-        if (tid < TILE) { M.rowvar[tid] = -1; M.rowidx[tid] = -1; }
-        __syncthreads();
-        const long long nr_tot = __ldg(A.batch.ref_off + v_cur + nv) - r_base;
-        const long long na_tot = __ldg(A.batch.alt_off + v_cur + nv) - a_base;
-        const int ref_pad = (int)((nr_tot + 3) & ~3LL);
-        if (tid < nv) {
-          const long long r0 = __ldg(A.batch.ref_off + v_cur + tid), r1 = __ldg(A.batch.ref_off + v_cur + tid + 1);
-          const long long a0 = __ldg(A.batch.alt_off + v_cur + tid), a1 = __ldg(A.batch.alt_off + v_cur + tid + 1);
-          M.ref_start[tid] = (int)(r0 - r_base); M.ref_cnt[tid] = (int)(r1 - r0);
-          M.alt_start[tid] = ref_pad + (int)(a0 - a_base); M.alt_cnt[tid] = (int)(a1 - a0);
-          for (int i = 0; i < (int)(r1 - r0); ++i) { M.rowvar[(int)(r0 - r_base) + i] = tid; M.rowidx[(int)(r0 - r_base) + i] = r0 + i; }
-          for (int i = 0; i < (int)(a1 - a0); ++i) {
-            M.rowvar[ref_pad + (int)(a0 - a_base) + i] = tid;
-            M.rowidx[ref_pad + (int)(a0 - a_base) + i] = total_ref + a0 + i;
-          }
-        }
-        if (tid == 0) { M.nv = nv; M.v0 = v_cur; M.ref_pad = ref_pad; M.rows = ref_pad + (int)na_tot; }
-        v_cur += nv;
-        __syncthreads();
-      }
-      const int rows_used = (M.rows + 3) & ~3;
-      const int ref_pad = M.ref_pad;
-      const long long my_idx = M.rowidx[row];
-      const int my_var = M.rowvar[row];
-      stage.prefetch(P.read_g0);
-
-      // ---------------- decode reads into T1 (batch.py:51-56; plain_text_data.py:510-511) ----------------
-      {
-        const int F = D.n_read_features;
-        long long src = -1;
-        if (my_idx >= 0) src = A.batch.read_indices ? __ldg(A.batch.read_indices + my_idx) : my_idx;
-        if (A.batch.reads_kind == PMT_READS_U8) {
-          const int rb = D.read_row_bytes;
-          const uint8_t* rp = reinterpret_cast<const uint8_t*>(A.batch.reads) + src * rb;
-          // half 0 expands packed bytes 0..3, half 1 bytes 4..6 and the quantised floats
-          const int b_lo = half ? 4 : 0, b_hi = half ? 7 : 4;
-          for (int b = b_lo; b < b_hi; ++b) {
-            const unsigned byte = src >= 0 ? __ldg(rp + b) : 0u;
-#pragma unroll
-            for (int bit = 0; bit < 8; ++bit) T1[(b * 8 + bit) * LD + row] = (float)((byte >> (7 - bit)) & 1u);
-          }
-          if (half) {
-            for (int b = 7; b < rb; ++b) {
-              const unsigned byte = src >= 0 ? __ldg(rp + b) : 128u;
-              T1[(56 + b - 7) * LD + row] = (float)((byte + 128u) & 255u) * 0.03125f;
-            }
-          }
-        } else {
-          for (int f = half; f < F; f += 2) {
-            float v = 0.f;
-            if (src >= 0) {
-              v = A.batch.reads_kind == PMT_READS_F16
-                      ? __half2float(reinterpret_cast<const __half*>(A.batch.reads)[src * F + f])
-                      : reinterpret_cast<const float*>(A.batch.reads)[src * F + f];
-            }
-            T1[f * LD + row] = v;
-          }
-        }
-      }
-      // ---------------- read embedding MLP (artifact_model.py:243) ----------------
-      float* emb = run_mlp(P, D.read_ops, D.n_read_ops, P.read_g0, T1, X, T1, T2, stage, W, rows_used, P.blk_g0);
-      __syncthreads();
-      if (emb != X) { copy_features(emb, X, D.d_read); }
-      // ---------------- concat info/seq embedding of the row's variant (artifact_model.py:246-251) ----------------
-      {
-        const int w = D.d_info + D.d_seq;
-        const float* src = my_var >= 0 ? A.out.info_seq_be + (long long)(M.v0 + my_var) * w : nullptr;
-        for (int j = half; j < w; j += 2) X[(D.d_read + j) * LD + row] = src ? __ldg(src + j) : 0.f;
-      }
-      __syncthreads();
-
-      // ---------------- gated ref/alt MLP blocks (gated_mlp.py:177-251) ----------------
+      const int nv = build_tile(A.batch, v_cur, cv1, total_ref, *C.M);
+      if (nv == 0) { v_cur += 1; continue; }   // longer than a tile: handled by reads_forward_long_kernel
+      v_cur += nv;
+      C.rows_used = (C.M->rows + 3) & ~3;
+      tile_embed(P, C, stage, A.batch, A.out.info_seq_be, nullptr);
       for (int blk = 0; blk < D.n_blocks; ++blk) {
-        const PmtBlockOffsets& BO = D.blocks[blk];
-        const int g1 = P.blk_g0 + 2 * blk, g2 = g1 + 1;
-        {  // LayerNorm over d_model (shared by ref and alt): T1 = LN(X)
-          float mean = 0.f;
-          for (int f = 0; f < Dm; ++f) mean += X[f * LD + row];
-          mean /= Dm;
-          float var = 0.f;
-          for (int f = 0; f < Dm; ++f) { const float d = X[f * LD + row] - mean; var = fmaf(d, d, var); }
-          const float rstd = rsqrtf(var / Dm + LN_EPS);
-          const int f_lo = half ? Dm / 2 : 0, f_hi = half ? Dm : Dm / 2;
-          for (int f = f_lo; f < f_hi; ++f)
-            T1[f * LD + row] = (X[f * LD + row] - mean) * rstd * __ldg(W + BO.ln_w + f) + __ldg(W + BO.ln_b + f);
-        }
-        const float* img1 = stage.acquire(g1);
-        stage.prefetch(g2);
-        gemm_tile(T1, P.gemm[g1], img1, W, ref_pad, T2, EPI_SELU, 0.f, rows_used);
+        block_phase_a(P, C, stage, blk, nullptr);
+        segment_sums(*C.M, C.T2, D.d_ffn / 2, D.d_ffn / 2, C.sums, P.sum_w, false, false);
         __syncthreads();
-        {  // SGU LayerNorm on z2 = T2[H..2H) in place (gated_mlp.py:230-233)
-          float mean = 0.f;
-          for (int f = 0; f < H; ++f) mean += T2[(H + f) * LD + row];
-          mean /= H;
-          float var = 0.f;
-          for (int f = 0; f < H; ++f) { const float d = T2[(H + f) * LD + row] - mean; var = fmaf(d, d, var); }
-          const float rstd = rsqrtf(var / H + LN_EPS);
-          __syncthreads();  // both halves have read the raw z2 of this row
-          const int f_lo = half ? H / 2 : 0, f_hi = half ? H : H / 2;
-          for (int f = f_lo; f < f_hi; ++f)
-            T2[(H + f) * LD + row] = (T2[(H + f) * LD + row] - mean) * rstd * __ldg(W + BO.ln2_w + f) + __ldg(W + BO.ln2_b + f);
-        }
-        __syncthreads();
-        segment_sums(M, T2, H, H, sums, P.sum_w, false);
-        __syncthreads();
-        {  // mean fields (gated_mlp.py:236-239; ragged_sets.py:144-155)
-          const float regw = __ldg(W + BO.reg_weight) + 0.25f;
-          for (int idx = tid; idx < M.nv * 2 * H; idx += NTHREADS) {
-            const int j = idx / (2 * H), s = (idx / H) & 1, f = idx % H;
-            float* p = sums + (j * 2 + s) * P.sum_w + f;
-            if (s == 0) *p = (*p + regw * __ldg(W + BO.regularizer + f)) / ((float)M.ref_cnt[j] + regw);
-            else *p = *p / ((float)M.alt_cnt[j] + 1e-4f);
-          }
-        }
-        __syncthreads();
-        {  // gate: T1[0..H) = z1 * (alpha z2 + 1 + beta m_own (+ gamma m_ref))   (gated_mlp.py:243-251)
-          const bool is_alt = row >= ref_pad;
-          const float alpha = __ldg(W + (is_alt ? BO.alpha_alt : BO.alpha_ref));
-          const float beta = __ldg(W + (is_alt ? BO.beta_alt : BO.beta_ref));
-          const float gamma = __ldg(W + BO.gamma);
-          const int f_lo = half ? H / 2 : 0, f_hi = half ? H : H / 2;
-          for (int f = f_lo; f < f_hi; ++f) {
-            float gate = T2[(H + f) * LD + row] * alpha + 1.f;
-            if (my_var >= 0) {
-              const float m_ref = sums[(my_var * 2 + 0) * P.sum_w + f];
-              if (is_alt) gate = gate + beta * sums[(my_var * 2 + 1) * P.sum_w + f] + gamma * m_ref;
-              else gate = gate + beta * m_ref;
-            }
-            T1[f * LD + row] = T2[f * LD + row] * gate;
-          }
-        }
-        const float* img2 = stage.acquire(g2);
-        stage.prefetch(blk + 1 < D.n_blocks ? g2 + 1 : P.red_g0);
-        gemm_tile(T1, P.gemm[g2], img2, W, ref_pad, X, EPI_RESIDUAL, 1.f, rows_used);
-        __syncthreads();
+        block_means(P, C, blk);
+        block_phase_b(P, C, stage, blk, blk + 1 < D.n_blocks ? P.blk_g0 + 2 * blk + 2 : P.red_g0);
       }
-
-      // ---------------- reducer MLP (artifact_model.py:258-259) ----------------
-      float* red = run_mlp(P, D.red_ops, D.n_red_ops, P.red_g0, X, X, T1, T2, stage, W, rows_used, -1);
-      __syncthreads();
-      float* Fb = (red == T1) ? T2 : T1;                       // final features
-      float* Lb = (red != X && Fb != X) ? X : ((red != T2 && Fb != T2) ? T2 : T1);  // per-read log-likelihoods
-      {  // pre_clustering_transform (euclidean_transformation.py:19-20): f = Q (y + t)
-        const int e_lo = half ? E / 2 : 0, e_hi = half ? E : E / 2;
-        for (int i = e_lo; i < e_hi; ++i) {
-          float acc = 0.f;
-          for (int j = 0; j < E; ++j) acc = fmaf(__ldg(W + D.rotation + i * E + j), red[j * LD + row] + __ldg(W + D.translation + j), acc);
-          Fb[i * LD + row] = acc;
-        }
-      }
-      __syncthreads();
-      if (row >= ref_pad && my_var >= 0) {  // clustering head on alt rows (feature_clustering.py:82-119)
-        if (half == 0) {
-          float q = 0.f, q2 = 0.f;
-          for (int e = 0; e < E; ++e) {
-            const float x = Fb[e * LD + row];
-            const float a = x / HC->sigma[e], b = x / (2.f * HC->sigma[e]);
-            q = fmaf(a, a, q); q2 = fmaf(b, b, q2);
-          }
-          Lb[0 * LD + row] = HC->c_non - q / 2.f;
-          Lb[1 * LD + row] = HC->c_out - q2 / 2.f;
-        }
-        for (int k = half; k < K; k += 2) {
-          const float* u = W + D.unit_ke + k * E;
-          float p = 0.f;
-          for (int e = 0; e < E; ++e) p = fmaf(Fb[e * LD + row], __ldg(u + e), p);
-          float o2 = 0.f;
-          for (int e = 0; e < E; ++e) { const float d = Fb[e * LD + row] - p * __ldg(u + e); o2 = fmaf(d, d, o2); }
-          const float dist = sqrtf(o2);
-          const float ll_orth = HC->c_orth[k] - (dist * dist) / HC->inv_two_tau2[k];
-          const float ll_par = HC->log_half_lambda[k] + logerfc((HC->shift[k] - p) / HC->inv_sqrt2_sigma[k]) +
-                               HC->half_lambda[k] * (HC->two_mu_plus[k] - 2.f * p);
-          Lb[(2 + k) * LD + row] = ll_orth + ll_par;
-        }
-      }
-      __syncthreads();
-      segment_sums(M, Fb, 0, E, sums, P.sum_w, false);
-      segment_sums(M, Lb, 0, K + 2, llsum, 16, true);
-      __syncthreads();
-      // ---------------- per-variant outputs ----------------
-      for (int idx = tid; idx < M.nv * E; idx += NTHREADS) {
-        const int j = idx / E, e = idx % E;
-        const long long v = M.v0 + j;
-        if (A.out.alt_means_be) A.out.alt_means_be[v * E + e] = sums[(j * 2 + 1) * P.sum_w + e] / ((float)M.alt_cnt[j] + 1e-4f);
-        if (A.out.ref_means_be) A.out.ref_means_be[v * E + e] = sums[(j * 2 + 0) * P.sum_w + e] / ((float)M.ref_cnt[j] + 1e-4f);
-      }
-      if (tid < M.nv) {
-        const long long v = M.v0 + tid;
-        const float* ll = llsum + (tid * 2 + 1) * 16;
-        const float non = ll[0], outl = ll[1];
-        float art_max = -INFINITY;
-        for (int k = 0; k < K; ++k) art_max = fmaxf(art_max, ll[2 + k] + HC->logw[k]);
-        float s = 0.f;
-        for (int k = 0; k < K; ++k) s += expf(ll[2 + k] + HC->logw[k] - art_max);
-        const float art = art_max + logf(s);
-        if (A.out.logits_bk) {
-          A.out.logits_bk[v * (K + 2) + 0] = non;
-          A.out.logits_bk[v * (K + 2) + 1] = outl;
-          for (int k = 0; k < K; ++k) A.out.logits_bk[v * (K + 2) + 2 + k] = ll[2 + k] + HC->logw[k];
-        }
-        if (A.out.logits_b) A.out.logits_b[v] = 20.f * tanhf((art - non) / 20.f);
-        if (A.out.outlier_logits_b) A.out.outlier_logits_b[v] = outl - logsumexp2(non, art);
-      }
-      if (A.out.final_re) {
-        for (int idx = tid; idx < TILE * E; idx += NTHREADS) {
-          const int r = idx / E, e = idx % E;
-          const long long n = M.rowidx[r];
-          if (n >= 0) A.out.final_re[n * E + e] = Fb[e * LD + r];
-        }
-      }
+      float *y, *Fb;
+      tile_tail(P, C, stage, A.out, false, nullptr, y, Fb);
+      tile_outputs(P, C, A.out);
       __syncthreads();
     }
+  }
+}
+
+// Variants with more reads than a tile (synthetic high-depth sets, BASELINE config 5).  One CTA walks the
+// variant in chunks of TILE rows; the residual stream x and the gated-block hidden z of every chunk live
+// in a per-CTA global scratch (L2 resident for moderately long sets); the per-block mean fields and the
+// final sums are accumulated across chunks, which is the only cross-read coupling (gated_mlp.py:236-248).
+__global__ void __launch_bounds__(NTHREADS, 1)
+reads_forward_long_kernel(const __grid_constant__ Plan P, const __grid_constant__ ReadKernelArgs A) {
+  extern __shared__ __align__(16) float smem[];
+  const PmtModelDesc& D = P.d;
+  TileCtx C;
+  float *st0, *st1;
+  carve_tile_ctx(P, smem, C, st0, st1, P.stage_floats);
+  C.W = A.wflat;
+  const int tid = threadIdx.x;
+  const int B = A.batch.n_variants;
+  Stage stage;
+  stage.init(st0, st1, A.image, &P);
+  if (tid == 0) head_constants(D, C.W, C.HC);
+  for (int i = tid; i < 3 * PMT_MAX_DIM * LD; i += NTHREADS) C.X[i] = 0.f;
+  __syncthreads();
+  const long long total_ref = __ldg(A.batch.ref_off + B);
+  float* scr = A.scratch + (long long)blockIdx.x * A.scratch_stride;
+  const int x_img = D.d_model * LD, z_img = D.d_ffn * LD, chunk_img = x_img + z_img;
+  const int H = D.d_ffn / 2;
+
+  for (int v = blockIdx.x; v < B; v += gridDim.x) {
+    const long long nref = __ldg(A.batch.ref_off + v + 1) - __ldg(A.batch.ref_off + v);
+    const long long nalt = __ldg(A.batch.alt_off + v + 1) - __ldg(A.batch.alt_off + v);
+    const long long total = ((nref + 3) & ~3LL) + nalt;
+    if (total <= TILE) continue;
+    const int n_chunks = (int)((total + TILE - 1) / TILE);
+    for (int c = 0; c < n_chunks; ++c) {
+      build_chunk(A.batch, v, c, total_ref, *C.M);
+      C.rows_used = (C.M->rows + 3) & ~3;
+      tile_embed(P, C, stage, A.batch, A.out.info_seq_be, nullptr);
+      save_rows(C.X, D.d_model, scr + (long long)c * chunk_img);
+      __syncthreads();
+    }
+    for (int blk = 0; blk < D.n_blocks; ++blk) {
+      for (int c = 0; c < n_chunks; ++c) {
+        build_chunk(A.batch, v, c, total_ref, *C.M);
+        C.rows_used = (C.M->rows + 3) & ~3;
+        load_rows(C.X, D.d_model, scr + (long long)c * chunk_img);
+        __syncthreads();
+        block_phase_a(P, C, stage, blk, nullptr);
+        save_rows(C.T2, D.d_ffn, scr + (long long)c * chunk_img + x_img);   // z1 and the normalised z2
+        segment_sums(*C.M, C.T2, H, H, C.sums, P.sum_w, false, c > 0);
+        __syncthreads();
+      }
+      block_means(P, C, blk);
+      for (int c = 0; c < n_chunks; ++c) {
+        build_chunk(A.batch, v, c, total_ref, *C.M);
+        C.rows_used = (C.M->rows + 3) & ~3;
+        load_rows(C.X, D.d_model, scr + (long long)c * chunk_img);
+        load_rows(C.T2, D.d_ffn, scr + (long long)c * chunk_img + x_img);
+        __syncthreads();
+        block_phase_b(P, C, stage, blk, -1);
+        save_rows(C.X, D.d_model, scr + (long long)c * chunk_img);
+        __syncthreads();
+      }
+    }
+    for (int c = 0; c < n_chunks; ++c) {
+      build_chunk(A.batch, v, c, total_ref, *C.M);
+      C.rows_used = (C.M->rows + 3) & ~3;
+      load_rows(C.X, D.d_model, scr + (long long)c * chunk_img);
+      __syncthreads();
+      float *y, *Fb;
+      tile_tail(P, C, stage, A.out, c > 0, nullptr, y, Fb);
+    }
+    tile_outputs(P, C, A.out);
+    __syncthreads();
   }
 }
 
@@ -753,6 +531,8 @@ int pmt_cnn_geometry(const Plan& P, CnnGeom* out) {
 
 size_t pmt_image_bytes(const Plan& P, const CnnGeom& G) { return (size_t)(P.img_total + G.img_total + 64) * sizeof(float); }
 
+static size_t long_scratch_floats_per_cta(const Plan& P, const PmtBatch* batch);
+
 extern "C" size_t pmt_workspace_size(const PmtModelDesc* desc, const PmtBatch* batch, int for_backward) {
   Plan P;
   CnnGeom G;
@@ -760,13 +540,19 @@ extern "C" size_t pmt_workspace_size(const PmtModelDesc* desc, const PmtBatch* b
   size_t bytes = 256;                       // claim counter + flags
   bytes += pmt_image_bytes(P, G);
   if (batch) bytes += (size_t)batch->n_variants * (desc->d_info + desc->d_seq) * sizeof(float) + 256;  // info_seq when caller passes none
+  bytes += long_scratch_floats_per_cta(P, batch) * sizeof(float) * 148 + 256;
   if (for_backward) bytes += pmt_backward_workspace_bytes(P, batch);
   return bytes;
 }
 
-static size_t reads_kernel_smem(const Plan& P) {
-  return (size_t)(3 * PMT_MAX_DIM * LD + 2 * P.stage_floats + TILE * 2 * P.sum_w + TILE * 2 * 16) * sizeof(float) +
-         sizeof(HeadConst) + sizeof(TileMeta) + 16;
+static size_t reads_kernel_smem(const Plan& P) { return tile_ctx_bytes(P, P.stage_floats); }
+
+// long-set scratch: per CTA, one (x, z) image pair per chunk of the longest variant
+static int long_grid(const PmtBatch* batch, int n_sm) { return batch->n_variants < n_sm ? batch->n_variants : n_sm; }
+static size_t long_scratch_floats_per_cta(const Plan& P, const PmtBatch* batch) {
+  if (!batch || batch->max_rows_per_variant <= TILE) return 0;
+  const size_t chunks = (size_t)((batch->max_rows_per_variant + 3 + TILE - 1) / TILE) + 1;
+  return chunks * (size_t)(P.d.d_model + P.d.d_ffn) * LD;
 }
 
 int pmt_launch_prepare(const Plan& P, const CnnGeom& G, const float* weights, float* image, cudaStream_t st) {
@@ -816,8 +602,6 @@ extern "C" int pmt_forward(const PmtModelDesc* desc, const float* weights, const
   const size_t need = pmt_workspace_size(desc, batch, 0);
   PMT_CHECK(workspace && workspace_bytes >= need, "workspace too small: %zu < %zu", workspace_bytes, need);
   PMT_CHECK(batch->n_variants > 0, "empty batch");
-  PMT_CHECK(batch->max_rows_per_variant <= TILE, "variant with %lld reads: sets longer than %d reads need the long-set path",
-            (long long)batch->max_rows_per_variant, TILE);
   char* ws = reinterpret_cast<char*>(workspace);
   int* counter = reinterpret_cast<int*>(ws);
   float* image = reinterpret_cast<float*>(ws + 256);
@@ -833,6 +617,7 @@ extern "C" int pmt_forward(const PmtModelDesc* desc, const float* weights, const
   P.claim_variants = choose_claim(batch, n_sm);
   ReadKernelArgs A;
   A.wflat = weights; A.image = image; A.batch = *batch; A.out = *out; A.out.info_seq_be = info_seq; A.claim_counter = counter;
+  A.scratch = nullptr; A.scratch_stride = 0;
   const size_t smem = reads_kernel_smem(P);
   cudaFuncSetAttribute(reads_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int n_claims = (batch->n_variants + P.claim_variants - 1) / P.claim_variants;
@@ -840,6 +625,15 @@ extern "C" int pmt_forward(const PmtModelDesc* desc, const float* weights, const
   pmt_profile_begin(st);
   reads_forward_kernel<<<grid, NTHREADS, smem, st>>>(P, A);
   pmt_profile_end(st);
+  if (batch->max_rows_per_variant > TILE) {
+    size_t off = 256 + pmt_image_bytes(P, G) + (size_t)batch->n_variants * (desc->d_info + desc->d_seq) * sizeof(float) + 256;
+    off = (off + 255) & ~(size_t)255;
+    A.scratch = reinterpret_cast<float*>(ws + off);
+    A.scratch_stride = (long long)long_scratch_floats_per_cta(P, batch);
+    const int lgrid = long_grid(batch, n_sm < 148 ? n_sm : 148);
+    cudaFuncSetAttribute(reads_forward_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    reads_forward_long_kernel<<<lgrid, NTHREADS, smem, st>>>(P, A);
+  }
   cudaError_t e = cudaGetLastError();
   PMT_CHECK(e == cudaSuccess, "pmt_forward launch failed: %s", cudaGetErrorString(e));
   return 0;
