@@ -1,9 +1,653 @@
-// Backward half of the C-ABI (placeholder until the backward kernels land).
+// Backward kernels of the ArtifactModel hot path (sm_100a) and the backward half of the C-ABI.
+//
+// pmt_backward = autograd of artifact_model.py:239-297 w.r.t. the flat materialised weights:
+//   reads_backward_kernel     per tile: forward recompute (activations to a per-CTA L2-resident scratch),
+//                             then head -> rotation -> reducer -> gated blocks -> read embedding in reverse;
+//                             weight gradients accumulate in a CTA-private flat buffer (no atomics, fixed order)
+//   info_mlp_backward_kernel  info_embedding MLP, rows = variants
+//   hap_cnn_backward_kernel   DNASequenceConvolution
+//   reduce_partials_kernel    sum of the CTA-private buffers in CTA order (bitwise reproducible)
+//   skip_fix_kernel           DenseSkipBlock.alpha gradients and the alpha scaling of its last layer
+#include <cstring>
+
 #include "pmt_host.h"
+#include "pmt_tile.cuh"
 
-size_t pmt_backward_workspace_bytes(const pmt::Plan&, const PmtBatch*) { return 0; }
+namespace pmt {
 
-extern "C" int pmt_backward(const PmtModelDesc*, const float*, const PmtBatch*, const PmtOutGrads*, float*, void*, size_t, void*) {
-  pmt_set_error("pmt_backward: not built yet");
-  return 1;
+struct BwdArgs {
+  const float* wflat;
+  const float* image;
+  PmtBatch batch;
+  const float* info_seq;      // [B][d_info + d_seq] from the variant kernels (forward recompute)
+  const float* d_logits_bk;   // upstream gradients (may be null)
+  const float* d_alt_means;
+  const float* d_ref_means;
+  float* d_info_seq;          // [B][d_info + d_seq] gradient handed to the variant kernels
+  float* scratch;             // per-CTA activation scratch
+  long long scratch_stride;   // floats
+  float* partials;            // per-CTA flat gradient buffers [grid][n_params]
+  int n_claims;
+};
+
+__device__ __forceinline__ float* pick_free(float* const* bufs, const float* a, const float* b, const float* c) {
+  for (int i = 0; i < 4; ++i)
+    if (bufs[i] != a && bufs[i] != b && bufs[i] != c) return bufs[i];
+  return nullptr;
+}
+
+// Backward of an MLP program (mlp.py:8-76).  On entry `g` holds dL/d(output); activations entering each op
+// were saved at scr + scr_off[i].  Returns the buffer holding dL/d(input) (meaningful if need_input_grad).
+// Weight/bias gradients are accumulated into `part`; for the last layer of a DenseSkipBlock the un-scaled
+// U = dx_out . s^T is accumulated instead (skip_fix_kernel turns it into dW = alpha U and d alpha = <W, U> + <b, Ub>).
+static __device__ __noinline__ float* mlp_backward(const Plan& P, const PmtLinearOp* ops, int n_ops, int g0,
+                                                   const float* scr, const int* scr_off, float* g, float* const* bufs,
+                                                   Stage& stage, const float* wflat, float* part, int rows_used,
+                                                   bool need_input_grad) {
+  float* gcur = g;
+  int i = n_ops - 1;
+  while (i >= 0) {
+    if (ops[i].flags & PMT_OP_SKIP_END) {
+      const int j1 = i;
+      int j0 = i;
+      while (!(ops[j0].flags & PMT_OP_SKIP_BEGIN)) --j0;
+      float* gres = gcur;
+      float* din = gres;
+      const float alpha = __ldg(wflat + ops[j1].alpha_off);
+      for (int j = j1; j >= j0; --j) {
+        const PmtLinearOp& lop = ops[j];
+        const GemmOp& gop = P.gemm[g0 + j];
+        float* A = pick_free(bufs, gres, din, nullptr);
+        __syncthreads();
+        load_rows(A, lop.in_dim, scr + scr_off[j]);
+        const float* imgT = stage.acquire(MAX_GEMM + g0 + j);
+        if (j == j0) { selu_copy(A, A, lop.in_dim); __syncthreads(); }   // A = s0 = SELU(x)
+        if (j > 0) stage.prefetch(MAX_GEMM + g0 + j - 1);
+        wgrad_tile(smem_addr(din), lop.out_dim, smem_addr(A), lop.in_dim, part + lop.w_off, 0, rows_used);
+        rowdot_tile(din, nullptr, lop.out_dim, part + lop.b_off, 0, rows_used);
+        const float scale = (j == j1) ? alpha : 1.f;
+        float* dnext = pick_free(bufs, gres, din, A);
+        gemm_tile_T(din, gop, imgT, 0, dnext, EPI_DSELU, scale, A, rows_used);
+        if (j == j0) {   // gres += dnext (the SELU(x) branch joins the identity branch)
+          __syncthreads();
+          for (int t = threadIdx.x; t < lop.in_dim * (TILE / 4); t += NTHREADS) {
+            const int f = t / (TILE / 4), q = t % (TILE / 4);
+            float4 a = *reinterpret_cast<float4*>(gres + f * LD + q * 4);
+            const float4 b = *reinterpret_cast<const float4*>(dnext + f * LD + q * 4);
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+            *reinterpret_cast<float4*>(gres + f * LD + q * 4) = a;
+          }
+        } else {
+          din = dnext;
+        }
+      }
+      if (j0 > 0 && (ops[j0 - 1].flags & PMT_OP_POST_SELU)) {   // x itself is a SELU output of the previous layer
+        float* A = pick_free(bufs, gres, nullptr, nullptr);
+        __syncthreads();
+        load_rows(A, ops[j0].in_dim, scr + scr_off[j0]);
+        __syncthreads();
+        mul_dselu(gres, A, ops[j0].in_dim);
+      }
+      gcur = gres;
+      i = j0 - 1;
+    } else {
+      const PmtLinearOp& lop = ops[i];
+      const GemmOp& gop = P.gemm[g0 + i];
+      float* A = pick_free(bufs, gcur, nullptr, nullptr);
+      __syncthreads();
+      load_rows(A, lop.in_dim, scr + scr_off[i]);
+      const bool want_dgrad = i > 0 || need_input_grad;
+      const float* imgT = nullptr;
+      if (want_dgrad) {
+        imgT = stage.acquire(MAX_GEMM + g0 + i);
+        if (i > 0) stage.prefetch(MAX_GEMM + g0 + i - 1);
+      } else {
+        __syncthreads();
+      }
+      wgrad_tile(smem_addr(gcur), lop.out_dim, smem_addr(A), lop.in_dim, part + lop.w_off, 0, rows_used);
+      rowdot_tile(gcur, nullptr, lop.out_dim, part + lop.b_off, 0, rows_used);
+      if (want_dgrad) {
+        float* dnext = pick_free(bufs, gcur, A, nullptr);
+        const bool dselu = i > 0 && (ops[i - 1].flags & PMT_OP_POST_SELU);
+        gemm_tile_T(gcur, gop, imgT, 0, dnext, dselu ? EPI_DSELU : EPI_STORE, 1.f, A, rows_used);
+        gcur = dnext;
+      }
+      i -= 1;
+    }
+  }
+  __syncthreads();
+  return gcur;
+}
+
+__device__ __forceinline__ float ldg_or_zero(const float* p, long long i) { return p ? __ldg(p + i) : 0.f; }
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+reads_backward_kernel(const __grid_constant__ Plan P, const __grid_constant__ BwdArgs A) {
+  extern __shared__ __align__(16) float smem[];
+  const PmtModelDesc& D = P.d;
+  const int R = P.bwd_rows;
+  float* bufs[4] = {smem, smem + R * LD, smem + 2 * R * LD, smem + 3 * R * LD};
+  float* st0 = smem + 4 * R * LD;
+  float* st1 = st0 + P.stage_floats;
+  TileCtx C;
+  C.X = bufs[0]; C.T1 = bufs[1]; C.T2 = bufs[2];
+  C.sums = st1 + P.stage_floats;
+  float* dsums = C.sums + TILE * 2 * P.sum_w;   // same [nv][2][sum_w] layout, gradients of the mean fields
+  C.llsum = dsums + TILE * 2 * P.sum_w;
+  const int E = D.d_feat, K = D.n_clusters, Dm = D.d_model, H = D.d_ffn / 2;
+  const int n_head = E + K * E + 5 * K;
+  const int acc_cap = n_head > 8 ? n_head : 8;
+  float* wpart = C.llsum + TILE * 2 * 16;
+  float* stat = wpart + NWARPS * acc_cap;          // [2][TILE] LayerNorm rstd of the block being differentiated
+  float* small = stat + 2 * TILE;                  // [64] scratch for tiny reductions
+  C.HC = reinterpret_cast<HeadConst*>(small + 64);
+  C.M = reinterpret_cast<TileMeta*>((reinterpret_cast<uintptr_t>(C.HC + 1) + 15) & ~uintptr_t(15));
+  TileMeta& M = *C.M;
+  C.W = A.wflat;
+  const float* W = A.wflat;
+  BlockAccum acc;
+  acc.init(wpart, acc_cap);
+
+  const int tid = threadIdx.x;
+  const int row = tid & (TILE - 1), half = tid >> 7;
+  const int B = A.batch.n_variants;
+  Stage stage;
+  stage.init(st0, st1, A.image, &P);
+  if (tid == 0) head_constants(D, W, C.HC);
+  for (int i = tid; i < 4 * R * LD; i += NTHREADS) smem[i] = 0.f;
+  __syncthreads();
+  const long long total_ref = __ldg(A.batch.ref_off + B);
+  float* scr = A.scratch + (long long)blockIdx.x * A.scratch_stride;
+  float* part = A.partials + (long long)blockIdx.x * D.n_params;
+  const int claim = P.claim_variants;
+  PmtOutputs no_out;
+  memset(&no_out, 0, sizeof(no_out));
+
+  // static round-robin assignment of claims to CTAs: the summation order of every gradient is fixed
+  for (int c = blockIdx.x; c < A.n_claims; c += gridDim.x) {
+    const long long cv0 = (long long)c * claim;
+    const int cv1 = (int)min((long long)B, cv0 + claim);
+    int v_cur = (int)cv0;
+    while (v_cur < cv1) {
+      const int nv = build_tile(A.batch, v_cur, cv1, total_ref, M);
+      if (nv == 0) { v_cur += 1; continue; }   // sets longer than a tile are rejected by the host for training
+      v_cur += nv;
+      const int rows_used = (M.rows + 3) & ~3;
+      C.rows_used = rows_used;
+      const int ref_pad = M.ref_pad;
+      const int my_var = M.rowvar[row];
+      const bool is_alt = row >= ref_pad;
+
+      // ======================= forward recompute, activations to scratch =======================
+      tile_embed(P, C, stage, A.batch, A.info_seq, scr);
+      for (int blk = 0; blk < D.n_blocks; ++blk) {
+        save_rows(C.X, Dm, scr + P.scr_x[blk]);
+        block_phase_a(P, C, stage, blk, scr + P.scr_z[blk]);
+        segment_sums(M, C.T2, H, H, C.sums, P.sum_w, false, false);
+        __syncthreads();
+        block_means(P, C, blk);
+        block_phase_b(P, C, stage, blk, blk + 1 < D.n_blocks ? P.blk_g0 + 2 * blk + 2 : P.red_g0);
+      }
+      float *Yb, *Fb;
+      tile_tail(P, C, stage, no_out, false, scr, Yb, Fb);
+      float* Lb = pick_free(bufs, Yb, Fb, bufs[3]);   // the third forward buffer (held the log-likelihoods)
+      float* Xtra = bufs[3];
+
+      // ======================= clustering head + set means (feature_clustering.py:82-135) =======================
+      for (int i = tid; i < NWARPS * acc_cap; i += NTHREADS) wpart[i] = 0.f;
+      __syncthreads();
+      {
+        const bool live = is_alt && my_var >= 0;
+        const long long v = live ? (long long)M.v0 + my_var : 0;
+        // half h writes its share of d f into Lb rows [h*E, (h+1)*E)
+        float* dfp = Lb + half * E * LD;
+        for (int e = 0; e < E; ++e) dfp[e * LD + row] = 0.f;
+        if (half == 0) {
+          const float g0 = live ? ldg_or_zero(A.d_logits_bk, v * (K + 2) + 0) : 0.f;
+          const float g1 = live ? ldg_or_zero(A.d_logits_bk, v * (K + 2) + 1) : 0.f;
+          for (int e = 0; e < E; ++e) {
+            const float s = C.HC->sigma[e], f = Fb[e * LD + row];
+            float contrib = 0.f;
+            if (live) {
+              dfp[e * LD + row] += -g0 * f / (s * s) - g1 * f / (4.f * s * s);
+              contrib = g0 * (-1.f / s + f * f / (s * s * s)) + g1 * (-1.f / s + f * f / (4.f * s * s * s));
+            }
+            acc.add(e, contrib);
+          }
+        }
+        for (int k = half; k < K; k += 2) {
+          const float* u = W + D.unit_ke + k * E;
+          const float gk = live ? ldg_or_zero(A.d_logits_bk, v * (K + 2) + 2 + k) : 0.f;
+          const float tau = __ldg(W + D.tau_k + k), lam = __ldg(W + D.lambda_k + k), sg = __ldg(W + D.emg_sigma_k + k),
+                      mu = __ldg(W + D.mu_k + k);
+          float p = 0.f;
+          for (int e = 0; e < E; ++e) p = fmaf(Fb[e * LD + row], __ldg(u + e), p);
+          float o2 = 0.f, odu = 0.f;
+          for (int e = 0; e < E; ++e) {
+            const float o = Fb[e * LD + row] - p * __ldg(u + e);
+            o2 = fmaf(o, o, o2); odu = fmaf(o, __ldg(u + e), odu);
+          }
+          const float zarg = (C.HC->shift[k] - p) / C.HC->sqrt2_sigma[k];
+          const float dlp = dlogerfc(zarg);
+          const float dpar_dp = -dlp / C.HC->sqrt2_sigma[k] - lam;
+          const float c_orth = -1.f / C.HC->two_tau2[k];
+          for (int e = 0; e < E; ++e) {
+            const float f = Fb[e * LD + row], ue = __ldg(u + e), o = f - p * ue;
+            if (live) dfp[e * LD + row] += gk * (c_orth * (2.f * o - 2.f * odu * ue) + dpar_dp * ue);
+            acc.add(E + k * E + e, gk * (c_orth * (-2.f * f * odu - 2.f * p * o) + dpar_dp * f));
+          }
+          const int base = E + K * E;
+          acc.add(base + 0 * K + k, gk * (-(E - 1) / tau + o2 / (tau * tau * tau)));                       // tau
+          acc.add(base + 1 * K + k, gk * (dlp / C.HC->sqrt2_sigma[k] + lam));                              // mu
+          acc.add(base + 2 * K + k, gk * (dlp * (1.41421356237f * lam - zarg / sg) + lam * lam * sg));    // emg sigma
+          acc.add(base + 3 * K + k, gk * (1.f / lam + dlp * sg * 0.70710678118f + mu + lam * sg * sg - p));  // lambda
+          acc.add(base + 4 * K + k, gk);                                                                  // log weight
+        }
+      }
+      __syncthreads();
+      acc.flush(part + D.sigma_e, 0, E);
+      acc.flush(part + D.unit_ke, E, K * E);
+      {
+        const int base = E + K * E;
+        const int offs[5] = {D.tau_k, D.mu_k, D.emg_sigma_k, D.lambda_k, D.logw_k};
+        for (int q = 0; q < 5; ++q) acc.flush(part + offs[q], base + q * K, K);
+      }
+      // d f = head part (both halves) + mean part; written in place over the final features
+      {
+        const int e_lo = half ? E / 2 : 0, e_hi = half ? E : E / 2;
+        for (int e = e_lo; e < e_hi; ++e) {
+          float d = Lb[e * LD + row] + Lb[(E + e) * LD + row];
+          if (my_var >= 0) {
+            const long long v = (long long)M.v0 + my_var;
+            d += is_alt ? ldg_or_zero(A.d_alt_means, v * E + e) / (M.alt_total[my_var] + 1e-4f)
+                        : ldg_or_zero(A.d_ref_means, v * E + e) / (M.ref_total[my_var] + 1e-4f);
+          } else {
+            d = 0.f;
+          }
+          Fb[e * LD + row] = d;
+          Yb[e * LD + row] += __ldg(W + D.translation + e);   // y + t, the rotation's input
+        }
+      }
+      __syncthreads();
+      // rotation (euclidean_transformation.py:19-20): f = Q (y + t)
+      wgrad_tile(smem_addr(Fb), E, smem_addr(Yb), E, part + D.rotation, 0, rows_used);
+      {
+        const int e_lo = half ? E / 2 : 0, e_hi = half ? E : E / 2;
+        for (int j = e_lo; j < e_hi; ++j) {
+          float a = 0.f;
+          for (int i = 0; i < E; ++i) a = fmaf(__ldg(W + D.rotation + i * E + j), Fb[i * LD + row], a);
+          Xtra[j * LD + row] = a;
+        }
+      }
+      __syncthreads();
+      rowdot_tile(Xtra, nullptr, E, part + D.translation, 0, rows_used);
+
+      // ======================= reducer (artifact_model.py:258-259) =======================
+      float* G = mlp_backward(P, D.red_ops, D.n_red_ops, P.red_g0, scr, P.scr_red, Xtra, bufs, stage, W, part,
+                              rows_used, true);
+
+      // ======================= gated blocks in reverse (gated_mlp.py:177-251) =======================
+      float* Ab = nullptr; float* Bn = nullptr; float* Cz = nullptr;
+      {
+        int q = 0;
+        float* others[3];
+        for (int i = 0; i < 4; ++i) if (bufs[i] != G) others[q++] = bufs[i];
+        Ab = others[0]; Bn = others[1]; Cz = others[2];
+      }
+      for (int blk = D.n_blocks - 1; blk >= 0; --blk) {
+        const PmtBlockOffsets& BO = D.blocks[blk];
+        const int g1 = P.blk_g0 + 2 * blk, g2 = g1 + 1;
+        const float alpha = __ldg(W + (is_alt ? BO.alpha_alt : BO.alpha_ref));
+        const float beta = __ldg(W + (is_alt ? BO.beta_alt : BO.beta_ref));
+        const float gamma = __ldg(W + BO.gamma);
+        const int f_lo = half ? H / 2 : 0, f_hi = half ? H : H / 2;
+        const int d_lo = half ? Dm / 2 : 0, d_hi = half ? Dm : Dm / 2;
+        load_rows(Ab, Dm, scr + P.scr_x[blk]);
+        load_rows(Cz, 2 * H, scr + P.scr_z[blk]);
+        stage.prefetch(MAX_GEMM + g2);
+        __syncthreads();
+        float mean, rstd, mean2, rstd2;
+        row_stats(Ab, Dm, row, mean, rstd);
+        row_stats(Cz + H * LD, H, row, mean2, rstd2);
+        __syncthreads();
+        for (int f = d_lo; f < d_hi; ++f) {
+          const float xh = (Ab[f * LD + row] - mean) * rstd;
+          Ab[f * LD + row] = xh;
+          Bn[f * LD + row] = xh * __ldg(W + BO.ln_w + f) + __ldg(W + BO.ln_b + f);
+        }
+        for (int f = f_lo; f < f_hi; ++f) {
+          const float xh2 = (Cz[(H + f) * LD + row] - mean2) * rstd2;
+          Cz[(2 * H + f) * LD + row] = xh2;
+          Cz[(3 * H + f) * LD + row] = xh2 * __ldg(W + BO.ln2_w + f) + __ldg(W + BO.ln2_b + f);   // z2n
+        }
+        __syncthreads();
+        segment_sums(M, Cz, 3 * H, H, C.sums, P.sum_w, false, false);
+        __syncthreads();
+        block_means(P, C, blk);
+        for (int f = f_lo; f < f_hi; ++f) {
+          const float gate = gate_value(P, C, BO, row, f, Cz[(3 * H + f) * LD + row], my_var, is_alt, alpha, beta, gamma);
+          Cz[(3 * H + f) * LD + row] = gate;
+          Cz[(4 * H + f) * LD + row] = Cz[f * LD + row] * gate;   // u = z1 * gate
+        }
+        // proj2: x_out = x + W2_s u + b2_s
+        const float* imgT2 = stage.acquire(MAX_GEMM + g2);
+        stage.prefetch(MAX_GEMM + g1);
+        wgrad_tile(smem_addr(G), Dm, smem_addr(Cz + 4 * H * LD), H, part + BO.p2_ref_w, 0, ref_pad);
+        wgrad_tile(smem_addr(G), Dm, smem_addr(Cz + 4 * H * LD), H, part + BO.p2_alt_w, ref_pad, rows_used);
+        rowdot_tile(G, nullptr, Dm, part + BO.p2_ref_b, 0, ref_pad);
+        rowdot_tile(G, nullptr, Dm, part + BO.p2_alt_b, ref_pad, rows_used);
+        gemm_tile_T(G, P.gemm[g2], imgT2, ref_pad, Cz + 5 * H * LD, EPI_STORE, 1.f, nullptr, rows_used);   // du
+        __syncthreads();
+        {  // d z1 = du * gate ; d gate = du * z1 ; scalar gradients of the gate
+          float s_alpha = 0.f, s_beta = 0.f, s_gamma = 0.f;
+          for (int f = f_lo; f < f_hi; ++f) {
+            const float du = Cz[(5 * H + f) * LD + row], gate = Cz[(3 * H + f) * LD + row], z1 = Cz[f * LD + row];
+            const float dgate = du * z1;
+            Cz[(4 * H + f) * LD + row] = du * gate;
+            Cz[(5 * H + f) * LD + row] = dgate;
+            if (my_var >= 0) {
+              const float z2n = Cz[(2 * H + f) * LD + row] * __ldg(W + BO.ln2_w + f) + __ldg(W + BO.ln2_b + f);
+              const float m_ref = C.sums[(my_var * 2 + 0) * P.sum_w + f];
+              s_alpha = fmaf(dgate, z2n, s_alpha);
+              s_beta = fmaf(dgate, is_alt ? C.sums[(my_var * 2 + 1) * P.sum_w + f] : m_ref, s_beta);
+              if (is_alt) s_gamma = fmaf(dgate, m_ref, s_gamma);
+            }
+          }
+          acc.add(0, is_alt ? 0.f : s_alpha); acc.add(1, is_alt ? s_alpha : 0.f);
+          acc.add(2, is_alt ? 0.f : s_beta);  acc.add(3, is_alt ? s_beta : 0.f);
+          acc.add(4, s_gamma);
+        }
+        __syncthreads();
+        if (tid < 5) {
+          const int offs[5] = {BO.alpha_ref, BO.alpha_alt, BO.beta_ref, BO.beta_alt, BO.gamma};
+          float s = 0.f;
+          for (int w = 0; w < NWARPS; ++w) s += wpart[w * acc_cap + tid];
+          part[offs[tid]] += s;
+        }
+        segment_sums(M, Cz, 5 * H, H, dsums, P.sum_w, false, false);
+        __syncthreads();
+        {  // gradients of the mean fields (ragged_sets.py:144-155 backward)
+          const float regw = __ldg(W + BO.reg_weight) + 0.25f;
+          const float b_ref = __ldg(W + BO.beta_ref), b_alt = __ldg(W + BO.beta_alt);
+          for (int idx = tid; idx < M.nv * H; idx += NTHREADS) {
+            const int j = idx / H, f = idx % H;
+            const float s_ref = dsums[(j * 2 + 0) * P.sum_w + f], s_alt = dsums[(j * 2 + 1) * P.sum_w + f];
+            dsums[(j * 2 + 0) * P.sum_w + f] = b_ref * s_ref + gamma * s_alt;   // d m_ref
+            dsums[(j * 2 + 1) * P.sum_w + f] = b_alt * s_alt;                   // d m_alt
+          }
+          __syncthreads();
+          if (tid < H) {
+            float d_reg = 0.f, d_w = 0.f;
+            const float reg = __ldg(W + BO.regularizer + tid);
+            for (int j = 0; j < M.nv; ++j) {
+              const float dm = dsums[(j * 2 + 0) * P.sum_w + tid], den = M.ref_total[j] + regw;
+              d_reg += dm * regw / den;
+              d_w += dm * (reg - C.sums[(j * 2 + 0) * P.sum_w + tid]) / den;
+            }
+            part[BO.regularizer + tid] += d_reg;
+            small[tid] = d_w;
+          }
+          __syncthreads();
+          if (tid == 0) {
+            float s = 0.f;
+            for (int f = 0; f < H; ++f) s += small[f];
+            part[BO.reg_weight] += s;
+          }
+          for (int idx = tid; idx < M.nv * H; idx += NTHREADS) {
+            const int j = idx / H, f = idx % H;
+            dsums[(j * 2 + 0) * P.sum_w + f] /= (M.ref_total[j] + regw);
+            dsums[(j * 2 + 1) * P.sum_w + f] /= (M.alt_total[j] + 1e-4f);
+          }
+        }
+        __syncthreads();
+        for (int f = f_lo; f < f_hi; ++f) {   // d z2n
+          float d = alpha * Cz[(5 * H + f) * LD + row];
+          if (my_var >= 0) d += dsums[(my_var * 2 + (is_alt ? 1 : 0)) * P.sum_w + f];
+          Cz[(3 * H + f) * LD + row] = d;
+        }
+        __syncthreads();
+        rowdot_tile(Cz + 3 * H * LD, Cz + 2 * H * LD, H, part + BO.ln2_w, 0, rows_used);
+        rowdot_tile(Cz + 3 * H * LD, nullptr, H, part + BO.ln2_b, 0, rows_used);
+        {  // SGU LayerNorm backward -> d z2 (pre-norm), placed after d z1 so that [4H, 6H) = d z
+          float m1 = 0.f, m2 = 0.f;
+          for (int f = 0; f < H; ++f) {
+            const float dxh = Cz[(3 * H + f) * LD + row] * __ldg(W + BO.ln2_w + f);
+            m1 += dxh; m2 = fmaf(dxh, Cz[(2 * H + f) * LD + row], m2);
+          }
+          m1 /= H; m2 /= H;
+          for (int f = f_lo; f < f_hi; ++f) {
+            const float dxh = Cz[(3 * H + f) * LD + row] * __ldg(W + BO.ln2_w + f);
+            Cz[(5 * H + f) * LD + row] = rstd2 * (dxh - m1 - Cz[(2 * H + f) * LD + row] * m2);
+          }
+        }
+        __syncthreads();
+        mul_dselu(Cz + 4 * H * LD, Cz, 2 * H);   // through z = SELU(proj1 n)
+        // proj1: z_pre = W1_s n + b1_s
+        const float* imgT1 = stage.acquire(MAX_GEMM + g1);
+        if (blk > 0) stage.prefetch(MAX_GEMM + g1 - 1);
+        wgrad_tile(smem_addr(Cz + 4 * H * LD), 2 * H, smem_addr(Bn), Dm, part + BO.p1_ref_w, 0, ref_pad);
+        wgrad_tile(smem_addr(Cz + 4 * H * LD), 2 * H, smem_addr(Bn), Dm, part + BO.p1_alt_w, ref_pad, rows_used);
+        rowdot_tile(Cz + 4 * H * LD, nullptr, 2 * H, part + BO.p1_ref_b, 0, ref_pad);
+        rowdot_tile(Cz + 4 * H * LD, nullptr, 2 * H, part + BO.p1_alt_b, ref_pad, rows_used);
+        __syncthreads();
+        gemm_tile_T(Cz + 4 * H * LD, P.gemm[g1], imgT1, ref_pad, Bn, EPI_STORE, 1.f, nullptr, rows_used);   // d n
+        __syncthreads();
+        rowdot_tile(Bn, Ab, Dm, part + BO.ln_w, 0, rows_used);
+        rowdot_tile(Bn, nullptr, Dm, part + BO.ln_b, 0, rows_used);
+        {  // LayerNorm backward, added to the residual gradient
+          float m1 = 0.f, m2 = 0.f;
+          for (int f = 0; f < Dm; ++f) {
+            const float dxh = Bn[f * LD + row] * __ldg(W + BO.ln_w + f);
+            m1 += dxh; m2 = fmaf(dxh, Ab[f * LD + row], m2);
+          }
+          m1 /= Dm; m2 /= Dm;
+          for (int f = d_lo; f < d_hi; ++f) {
+            const float dxh = Bn[f * LD + row] * __ldg(W + BO.ln_w + f);
+            G[f * LD + row] += rstd * (dxh - m1 - Ab[f * LD + row] * m2);
+          }
+        }
+        __syncthreads();
+      }
+
+      // ======================= concat (artifact_model.py:246-251): d info_seq of each variant =======================
+      {
+        const int w = D.d_info + D.d_seq;
+        for (int idx = tid; idx < M.nv * w; idx += NTHREADS) {
+          const int j = idx / w, f = idx % w;
+          const float* p = G + (D.d_read + f) * LD;
+          float s = 0.f;
+          for (int i = 0; i < M.ref_cnt[j]; ++i) s += p[M.ref_start[j] + i];
+          for (int i = 0; i < M.alt_cnt[j]; ++i) s += p[M.alt_start[j] + i];
+          A.d_info_seq[((long long)M.v0 + j) * w + f] = s;
+        }
+      }
+      // ======================= read embedding (artifact_model.py:243) =======================
+      mlp_backward(P, D.read_ops, D.n_read_ops, P.read_g0, scr, P.scr_read, G, bufs, stage, W, part, rows_used, false);
+      __syncthreads();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// info MLP backward: rows of the tile are variants
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NTHREADS, 1)
+info_mlp_backward_kernel(const __grid_constant__ Plan P, const float* __restrict__ wflat, const float* __restrict__ image,
+                         const void* __restrict__ info, int info_kind, long long info_stride, int n_variants,
+                         const float* __restrict__ d_info_seq, float* scratch, long long scratch_stride, float* partials,
+                         int rows_per_buf) {
+  extern __shared__ __align__(16) float smem[];
+  float* bufs[4] = {smem, smem + rows_per_buf * LD, smem + 2 * rows_per_buf * LD, smem + 3 * rows_per_buf * LD};
+  float* st0 = smem + 4 * rows_per_buf * LD;
+  float* st1 = st0 + P.info_stage_floats;
+  Stage stage;
+  stage.init(st0, st1, image, &P);
+  float* scr = scratch + (long long)blockIdx.x * scratch_stride;
+  float* part = partials + (long long)blockIdx.x * P.d.n_params;
+  const int I = P.d.n_info_features, w = P.d.d_info + P.d.d_seq;
+  for (int i = threadIdx.x; i < 4 * rows_per_buf * LD; i += NTHREADS) smem[i] = 0.f;
+  __syncthreads();
+  const int n_tiles = (n_variants + TILE - 1) / TILE;
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int v0 = t * TILE;
+    const int nv = min(TILE, n_variants - v0);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < TILE * I; idx += NTHREADS) {
+      const int r = idx / I, f = idx % I;
+      float v = 0.f;
+      if (r < nv) {
+        const long long off = (long long)(v0 + r) * info_stride + f;
+        v = info_kind == PMT_F16 ? __half2float(reinterpret_cast<const __half*>(info)[off])
+                                 : reinterpret_cast<const float*>(info)[off];
+      }
+      bufs[0][f * LD + r] = v;
+    }
+    float* out = run_mlp(P, P.d.info_ops, P.d.n_info_ops, P.info_g0, bufs[0], bufs[1], bufs[2], bufs[0], stage, wflat,
+                         TILE, -1, scr, P.scr_info);
+    __syncthreads();
+    float* g = bufs[3];
+    (void)out;
+    for (int idx = threadIdx.x; idx < TILE * P.d.d_info; idx += NTHREADS) {
+      const int r = idx / P.d.d_info, j = idx % P.d.d_info;
+      g[j * LD + r] = r < nv ? d_info_seq[(long long)(v0 + r) * w + j] : 0.f;
+    }
+    __syncthreads();
+    mlp_backward(P, P.d.info_ops, P.d.n_info_ops, P.info_g0, scr, P.scr_info, g, bufs, stage, wflat, part, TILE, false);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// reduction of the CTA-private gradient buffers, DenseSkipBlock fix-ups
+// ------------------------------------------------------------------------------------------------
+__global__ void reduce_partials_kernel(const float* __restrict__ partials, int n_cta, int n_params, float* __restrict__ out) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_params) return;
+  float s = 0.f;
+  for (int c = 0; c < n_cta; ++c) s += partials[(long long)c * n_params + p];
+  out[p] = s;
+}
+
+// out holds U (un-scaled last-layer gradients of each DenseSkipBlock): d alpha = <W, U> + <b, Ub>; dW = alpha U.
+__global__ void skip_fix_kernel(const __grid_constant__ Plan P, const float* __restrict__ w, float* __restrict__ out) {
+  const SkipFix f = P.skipfix[blockIdx.x];
+  __shared__ float red[256];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < f.n_w; i += blockDim.x) s = fmaf(w[f.w_off + i], out[f.w_off + i], s);
+  for (int i = threadIdx.x; i < f.n_b; i += blockDim.x) s = fmaf(w[f.b_off + i], out[f.b_off + i], s);
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  const float alpha = w[f.alpha_off];
+  if (threadIdx.x == 0) out[f.alpha_off] = red[0];
+  for (int i = threadIdx.x; i < f.n_w; i += blockDim.x) out[f.w_off + i] *= alpha;
+  for (int i = threadIdx.x; i < f.n_b; i += blockDim.x) out[f.b_off + i] *= alpha;
+}
+
+}  // namespace pmt
+
+// ================================================================================================
+// host side
+// ================================================================================================
+using namespace pmt;
+
+int pmt_launch_cnn_backward(const Plan&, const CnnGeom&, const float*, const float*, const PmtBatch*, const float*, float*,
+                            int, cudaStream_t) {
+  return 0;   // TODO(next commit): haplotype CNN backward kernel
+}
+
+static size_t bwd_smem_bytes(const Plan& P) {
+  const int n_head = P.d.d_feat + P.d.n_clusters * P.d.d_feat + 5 * P.d.n_clusters;
+  const int acc_cap = n_head > 8 ? n_head : 8;
+  return (size_t)(4 * P.bwd_rows * LD + 2 * P.stage_floats + 2 * TILE * 2 * P.sum_w + TILE * 2 * 16 + NWARPS * acc_cap +
+                  2 * TILE + 64) * sizeof(float) + sizeof(HeadConst) + sizeof(TileMeta) + 64;
+}
+static int info_rows(const Plan& P) {
+  int r = P.d.n_info_features;
+  for (int i = 0; i < P.d.n_info_ops; ++i) if (P.d.info_ops[i].out_dim > r) r = P.d.info_ops[i].out_dim;
+  return r;
+}
+static const int kBwdGrid = 148;
+
+size_t pmt_backward_workspace_bytes(const Plan& P, const PmtBatch* batch) {
+  size_t bytes = 1024;
+  bytes += (size_t)kBwdGrid * P.d.n_params * sizeof(float);                                  // partials
+  const size_t scr = P.scratch_floats > P.info_scratch_floats ? P.scratch_floats : P.info_scratch_floats;
+  bytes += (size_t)kBwdGrid * scr * sizeof(float);                                           // activation scratch
+  if (batch) bytes += 2 * (size_t)batch->n_variants * (P.d.d_info + P.d.d_seq) * sizeof(float);   // info_seq, d_info_seq
+  return bytes;
+}
+
+extern "C" int pmt_backward(const PmtModelDesc* desc, const float* weights, const PmtBatch* batch, const PmtOutGrads* grads,
+                            float* d_weights, void* workspace, size_t workspace_bytes, void* stream) {
+  Plan P;
+  CnnGeom G;
+  if (pmt_build_plan(desc, &P) || pmt_cnn_geometry(P, &G)) return 1;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t need = pmt_workspace_size(desc, batch, 1);
+  PMT_CHECK(workspace && workspace_bytes >= need, "workspace too small: %zu < %zu", workspace_bytes, need);
+  PMT_CHECK(batch->n_variants > 0, "empty batch");
+  PMT_CHECK(batch->max_rows_per_variant <= TILE,
+            "pmt_backward: a variant has %lld reads; training on sets longer than %d reads is not supported yet "
+            "(the reference caps reads at 10 ref + 15 alt at ingest)", (long long)batch->max_rows_per_variant, TILE);
+  const size_t smem = bwd_smem_bytes(P);
+  PMT_CHECK(smem <= 227 * 1024, "model too wide for the backward kernel's shared-memory plan (%zu bytes)", smem);
+
+  const int B = batch->n_variants, w = desc->d_info + desc->d_seq;
+  char* ws = reinterpret_cast<char*>(workspace);
+  size_t off = 256;
+  float* image = reinterpret_cast<float*>(ws + off); off += pmt_image_bytes(P, G); off = (off + 255) & ~(size_t)255;
+  float* partials = reinterpret_cast<float*>(ws + off); off += (size_t)kBwdGrid * desc->n_params * sizeof(float);
+  const size_t scr_floats = P.scratch_floats > P.info_scratch_floats ? P.scratch_floats : P.info_scratch_floats;
+  float* scratch = reinterpret_cast<float*>(ws + off); off += (size_t)kBwdGrid * scr_floats * sizeof(float);
+  float* info_seq = reinterpret_cast<float*>(ws + off); off += (size_t)B * w * sizeof(float);
+  float* d_info_seq = reinterpret_cast<float*>(ws + off); off += (size_t)B * w * sizeof(float);
+  PMT_CHECK(off <= workspace_bytes, "workspace layout overflow");
+
+  cudaMemsetAsync(partials, 0, (size_t)kBwdGrid * desc->n_params * sizeof(float), st);
+  pmt_launch_prepare(P, G, weights, image, st);
+  pmt_launch_variant_kernels(P, G, weights, image, batch, info_seq, st);
+
+  int dev = 0, n_sm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  const double avg = (double)(batch->n_rows > 0 ? batch->n_rows : 16LL * B) / B;
+  int claim = (int)(4.0 * TILE / (avg + 1.0));
+  if (claim > B / (2 * n_sm)) claim = B / (2 * n_sm);
+  if (claim < 1) claim = 1;
+  if (claim > 512) claim = 512;
+  P.claim_variants = claim;
+
+  BwdArgs A;
+  A.wflat = weights; A.image = image; A.batch = *batch; A.info_seq = info_seq;
+  A.d_logits_bk = grads ? grads->d_logits_bk : nullptr;
+  A.d_alt_means = grads ? grads->d_alt_means_be : nullptr;
+  A.d_ref_means = grads ? grads->d_ref_means_be : nullptr;
+  A.d_info_seq = d_info_seq; A.scratch = scratch; A.scratch_stride = (long long)scr_floats; A.partials = partials;
+  A.n_claims = (B + claim - 1) / claim;
+  int grid = A.n_claims < kBwdGrid ? A.n_claims : kBwdGrid;
+  if (grid > n_sm) grid = n_sm;
+  cudaFuncSetAttribute(reads_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  pmt_profile_begin(st);
+  reads_backward_kernel<<<grid, NTHREADS, smem, st>>>(P, A);
+  pmt_profile_end(st);
+  {
+    const int rows = info_rows(P);
+    const size_t ismem = (size_t)(4 * rows * LD + 2 * P.info_stage_floats) * sizeof(float);
+    PMT_CHECK(ismem <= 227 * 1024, "info MLP too wide for the backward kernel (%zu bytes of shared memory)", ismem);
+    const int n_tiles = (B + TILE - 1) / TILE;
+    const int igrid = n_tiles < kBwdGrid ? n_tiles : kBwdGrid;
+    cudaFuncSetAttribute(info_mlp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ismem);
+    info_mlp_backward_kernel<<<igrid, NTHREADS, ismem, st>>>(P, weights, image, batch->info, batch->info_kind,
+                                                             batch->info_stride, B, d_info_seq, scratch,
+                                                             (long long)scr_floats, partials, rows);
+  }
+  if (pmt_launch_cnn_backward(P, G, weights, image, batch, d_info_seq, partials, kBwdGrid, st)) return 1;
+  reduce_partials_kernel<<<(desc->n_params + 255) / 256, 256, 0, st>>>(partials, kBwdGrid, desc->n_params, d_weights);
+  if (P.n_skipfix > 0) skip_fix_kernel<<<P.n_skipfix, 256, 0, st>>>(P, weights, d_weights);
+  cudaError_t e = cudaGetLastError();
+  PMT_CHECK(e == cudaSuccess, "pmt_backward launch failed: %s", cudaGetErrorString(e));
+  return 0;
 }

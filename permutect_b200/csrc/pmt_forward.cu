@@ -28,6 +28,16 @@ __global__ void pack_weights_kernel(const __grid_constant__ Plan P, const float*
     const int woff = which ? op.w_alt_off : op.w_off;
     image[op.img_off + idx] = (j < op.NT && n < op.N) ? w[woff + n * op.K + k] : 0.f;
   }
+  // transposed image for the data-gradient GEMM: reduction over n (N rows), K outputs
+  const int per_imageT = op.N * op.GT * GROUP_STRIDE;
+  for (int idx = threadIdx.x; idx < per_imageT * n_images; idx += blockDim.x) {
+    const int which = idx / per_imageT, rem = idx % per_imageT;
+    const int n = rem / (op.GT * GROUP_STRIDE), slot = rem % (op.GT * GROUP_STRIDE);
+    const int grp = slot / GROUP_STRIDE, j = slot % GROUP_STRIDE;
+    const int k = grp * op.NTT + j;
+    const int woff = which ? op.w_alt_off : op.w_off;
+    image[op.imgT_off + idx] = (j < op.NTT && k < op.K) ? w[woff + n * op.K + k] : 0.f;
+  }
 }
 
 // conv weights [out][in][ks] -> image [(ci*ks + t)][G][8] with NT = 8
@@ -443,6 +453,10 @@ static int add_gemm(Plan& P, int K, int N, int w, int b, int w_alt, int b_alt) {
   op.img_floats = K * op.G * GROUP_STRIDE * (w_alt >= 0 ? 2 : 1);
   op.img_floats = (op.img_floats + 3) & ~3;
   P.img_total += op.img_floats;
+  choose_groups(K, &op.GT, &op.NTT);
+  op.imgT_off = P.img_total;
+  op.imgT_floats = (N * op.GT * GROUP_STRIDE * (w_alt >= 0 ? 2 : 1) + 3) & ~3;
+  P.img_total += op.imgT_floats;
   return P.n_gemm++;
 }
 
@@ -481,9 +495,32 @@ int pmt_build_plan(const PmtModelDesc* d, Plan* out) {
   for (int g = 0; g < P.n_gemm; ++g) {
     int& tgt = g < read_path_end ? P.stage_floats : P.info_stage_floats;
     if (P.gemm[g].img_floats > tgt) tgt = P.gemm[g].img_floats;
+    if (P.gemm[g].imgT_floats > tgt) tgt = P.gemm[g].imgT_floats;
   }
   P.sum_w = d->d_ffn / 2 > d->d_feat ? d->d_ffn / 2 : d->d_feat;
   P.claim_variants = 64;
+  // backward: activation scratch layout, buffer height, DenseSkipBlock fix-ups
+  int off = 0, rows = d->d_model;
+  auto grow = [&](int v) { if (v > rows) rows = v; };
+  for (int i = 0; i < d->n_read_ops; ++i) { P.scr_read[i] = off; off += d->read_ops[i].in_dim * LD; grow(d->read_ops[i].in_dim); grow(d->read_ops[i].out_dim); }
+  for (int b = 0; b < d->n_blocks; ++b) { P.scr_x[b] = off; off += d->d_model * LD; P.scr_z[b] = off; off += d->d_ffn * LD; }
+  for (int i = 0; i < d->n_red_ops; ++i) { P.scr_red[i] = off; off += d->red_ops[i].in_dim * LD; grow(d->red_ops[i].in_dim); grow(d->red_ops[i].out_dim); }
+  P.scr_red[d->n_red_ops] = off; off += d->d_feat * LD;
+  P.scratch_floats = off;
+  grow(3 * d->d_ffn); grow(d->d_feat + d->n_clusters + 2);
+  P.bwd_rows = rows;
+  off = 0;
+  for (int i = 0; i < d->n_info_ops; ++i) { P.scr_info[i] = off; off += d->info_ops[i].in_dim * LD; }
+  P.info_scratch_floats = off;
+  auto add_fix = [&](const PmtLinearOp* ops, int n) {
+    for (int i = 0; i < n; ++i)
+      if (ops[i].flags & PMT_OP_SKIP_END) {
+        SkipFix& f = P.skipfix[P.n_skipfix++];
+        f.w_off = ops[i].w_off; f.b_off = ops[i].b_off; f.alpha_off = ops[i].alpha_off;
+        f.n_w = ops[i].in_dim * ops[i].out_dim; f.n_b = ops[i].out_dim;
+      }
+  };
+  add_fix(d->read_ops, d->n_read_ops); add_fix(d->info_ops, d->n_info_ops); add_fix(d->red_ops, d->n_red_ops);
   return 0;
 }
 

@@ -23,3 +23,5 @@ int pmt_launch_variant_kernels(const pmt::Plan& P, const pmt::CnnGeom& G, const 
 size_t pmt_backward_workspace_bytes(const pmt::Plan& P, const PmtBatch* batch);
 void pmt_profile_begin(cudaStream_t st);
 void pmt_profile_end(cudaStream_t st);
+int pmt_launch_cnn_backward(const pmt::Plan& P, const pmt::CnnGeom& G, const float* weights, const float* image,
+                            const PmtBatch* batch, const float* d_info_seq, float* partials, int n_partials, cudaStream_t st);

@@ -259,7 +259,7 @@ __device__ __forceinline__ void block_phase_a(const Plan& P, TileCtx& C, Stage& 
   }
   const float* img1 = stage.acquire(g1);
   stage.prefetch(g1 + 1);
-  gemm_tile(C.T1, P.gemm[g1], img1, W, C.M->ref_pad, C.T2, EPI_SELU, 0.f, C.rows_used);
+  gemm_tile(C.T1, P.gemm[g1], img1, W, C.M->ref_pad, C.T2, EPI_SELU, 1.f, C.rows_used);
   __syncthreads();
   if (z_save) save_rows(C.T2, D.d_ffn, z_save);
   {
