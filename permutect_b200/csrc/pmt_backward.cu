@@ -241,7 +241,8 @@ reads_backward_kernel(const __grid_constant__ Plan P, const __grid_constant__ Bw
           acc.add(base + 1 * K + k, gk * (dlp / C.HC->sqrt2_sigma[k] + lam));                              // mu
           acc.add(base + 2 * K + k, gk * (dlp * (1.41421356237f * lam - zarg / sg) + lam * lam * sg));    // emg sigma
           acc.add(base + 3 * K + k, gk * (1.f / lam + dlp * sg * 0.70710678118f + mu + lam * sg * sg - p));  // lambda
-          acc.add(base + 4 * K + k, gk);                                                                  // log weight
+          // the log cluster weight is added once per variant, after the sum over its reads (feature_clustering.py:115-116)
+          acc.add(base + 4 * K + k, (live && row == M.alt_start[my_var]) ? gk : 0.f);
         }
       }
       __syncthreads();
@@ -546,6 +547,226 @@ __global__ void skip_fix_kernel(const __grid_constant__ Plan P, const float* __r
   for (int i = threadIdx.x; i < f.n_b; i += blockDim.x) out[f.b_off + i] *= alpha;
 }
 
+// ------------------------------------------------------------------------------------------------
+// haplotype CNN backward (dna_sequence_convolution.py:57-111).  VT variants per pass; every layer's
+// activation of the pass stays in shared memory as [C][VT][len]; gradients ping-pong between two buffers.
+// ------------------------------------------------------------------------------------------------
+struct CnnBwdGeom {
+  int vt;
+  int act_off[PMT_MAX_CNN_OPS + 1];   // float offset of the activation entering spatial op i ([n_spatial] = last output)
+  int ch[PMT_MAX_CNN_OPS + 1], len[PMT_MAX_CNN_OPS + 1];
+  int act_total, gmax, n_spatial, n_linear;
+  int vs;                             // row stride of the linear-stack vectors
+};
+
+__device__ __forceinline__ float act_grad_from_out(float y, int act) {
+  if (act == PMT_ACT_SELU) return selu_grad_from_out(y);
+  if (act == PMT_ACT_LEAKY_RELU) return y > 0.f ? 1.f : 0.01f;
+  return 1.f;
+}
+__device__ __forceinline__ float apply_act_b(float x, int act) {
+  if (act == PMT_ACT_SELU) return selu(x);
+  if (act == PMT_ACT_LEAKY_RELU) return x > 0.f ? x : 0.01f * x;
+  return x;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+hap_cnn_backward_kernel(const __grid_constant__ Plan P, const __grid_constant__ CnnBwdGeom Gb, const float* __restrict__ wflat,
+                        const void* __restrict__ haps, int hap_kind, long long hap_stride, int n_variants,
+                        const float* __restrict__ d_info_seq, float* partials) {
+  extern __shared__ __align__(16) float smem[];
+  float* acts = smem;
+  float* gA = acts + Gb.act_total;
+  float* gB = gA + Gb.gmax;
+  float* vec = gB + Gb.gmax;                 // [(n_linear + 1)][VT][vs] activations of the linear stack
+  float* dvec = vec + (Gb.n_linear + 1) * Gb.vt * Gb.vs;   // [2][VT][vs] gradients of the linear stack
+  const PmtModelDesc& D = P.d;
+  const int VT = Gb.vt, VS = Gb.vs, L = D.hap_len, ns = Gb.n_spatial, tid = threadIdx.x;
+  const int out_w = D.d_info + D.d_seq;
+  float* part = partials + (long long)blockIdx.x * D.n_params;
+
+  for (int v0 = blockIdx.x * VT; v0 < n_variants; v0 += gridDim.x * VT) {
+    const int nv = min(VT, n_variants - v0);
+    __syncthreads();
+    // ---- forward recompute ----
+    for (int idx = tid; idx < 10 * VT * L; idx += NTHREADS) {
+      const int c = idx / (VT * L), v = (idx / L) % VT, p = idx % L;
+      float x = 0.f;
+      if (v < nv) {
+        const int h = c & 1, code_want = c >> 1;
+        const long long off = (long long)(v0 + v) * hap_stride + h * L + p;
+        const int code = hap_kind == PMT_I64 ? (int)reinterpret_cast<const long long*>(haps)[off]
+                                             : (int)reinterpret_cast<const short*>(haps)[off];
+        x = code == code_want ? 1.f : 0.f;
+      }
+      acts[Gb.act_off[0] + idx] = x;
+    }
+    __syncthreads();
+    for (int i = 0; i < ns; ++i) {
+      const PmtCnnOp& op = D.cnn_ops[i];
+      const float* in = acts + Gb.act_off[i];
+      float* out = acts + Gb.act_off[i + 1];
+      const int li = Gb.len[i], lo = Gb.len[i + 1];
+      if (op.kind == PMT_CNN_CONV) {
+        for (int idx = tid; idx < op.out_ch * VT * lo; idx += NTHREADS) {
+          const int co = idx / (VT * lo), v = (idx / lo) % VT, p = idx % lo;
+          float a = __ldg(wflat + op.b_off + co);
+          const float* wr = wflat + op.w_off + (long long)co * op.in_ch * op.ksize;
+          for (int ci = 0; ci < op.in_ch; ++ci) {
+            const float* xr = in + (ci * VT + v) * li + p;
+            for (int t = 0; t < op.ksize; ++t) a = fmaf(__ldg(wr + ci * op.ksize + t), xr[t], a);
+          }
+          out[idx] = apply_act_b(a, op.act);
+        }
+      } else {
+        for (int idx = tid; idx < op.in_ch * VT * lo; idx += NTHREADS) {
+          const int cv = idx / lo, p = idx % lo;
+          const float* xr = in + cv * li + p * op.stride;
+          float m = xr[0];
+          for (int t = 1; t < op.ksize; ++t) m = fmaxf(m, xr[t]);
+          out[idx] = m;
+        }
+      }
+      __syncthreads();
+    }
+    // linear stack forward; vec level 0 = flattened spatial output (channel-major flatten)
+    {
+      const int C = Gb.ch[ns], len = Gb.len[ns];
+      for (int idx = tid; idx < VT * C * len; idx += NTHREADS) {
+        const int v = idx / (C * len), k = idx % (C * len), c = k / len, p = k % len;
+        vec[v * VS + k] = acts[Gb.act_off[ns] + (c * VT + v) * len + p];
+      }
+      __syncthreads();
+      for (int l = 0; l < Gb.n_linear; ++l) {
+        const PmtCnnOp& op = D.cnn_ops[ns + l];
+        const float* vin = vec + l * VT * VS;
+        float* vout = vec + (l + 1) * VT * VS;
+        for (int idx = tid; idx < VT * op.out_ch; idx += NTHREADS) {
+          const int v = idx / op.out_ch, n = idx % op.out_ch;
+          float a = __ldg(wflat + op.b_off + n);
+          const float* wr = wflat + op.w_off + (long long)n * op.in_ch;
+          for (int k = 0; k < op.in_ch; ++k) a = fmaf(__ldg(wr + k), vin[v * VS + k], a);
+          vout[v * VS + n] = apply_act_b(a, op.act);
+        }
+        __syncthreads();
+      }
+    }
+    // ---- backward: linear stack ----
+    float* dcur = dvec;
+    float* dnxt = dvec + VT * VS;
+    for (int idx = tid; idx < VT * D.d_seq; idx += NTHREADS) {
+      const int v = idx / D.d_seq, n = idx % D.d_seq;
+      dcur[v * VS + n] = v < nv ? d_info_seq[(long long)(v0 + v) * out_w + D.d_info + n] : 0.f;
+    }
+    __syncthreads();
+    for (int l = Gb.n_linear - 1; l >= 0; --l) {
+      const PmtCnnOp& op = D.cnn_ops[ns + l];
+      const float* vin = vec + l * VT * VS;
+      const float* vout = vec + (l + 1) * VT * VS;
+      for (int idx = tid; idx < VT * op.out_ch; idx += NTHREADS) {
+        const int v = idx / op.out_ch, n = idx % op.out_ch;
+        dcur[v * VS + n] *= act_grad_from_out(vout[v * VS + n], op.act);
+      }
+      __syncthreads();
+      for (int idx = tid; idx < op.out_ch * op.in_ch; idx += NTHREADS) {
+        const int n = idx / op.in_ch, k = idx % op.in_ch;
+        float a = 0.f;
+        for (int v = 0; v < nv; ++v) a = fmaf(dcur[v * VS + n], vin[v * VS + k], a);
+        part[op.w_off + idx] += a;
+      }
+      for (int n = tid; n < op.out_ch; n += NTHREADS) {
+        float a = 0.f;
+        for (int v = 0; v < nv; ++v) a += dcur[v * VS + n];
+        part[op.b_off + n] += a;
+      }
+      for (int idx = tid; idx < VT * op.in_ch; idx += NTHREADS) {
+        const int v = idx / op.in_ch, k = idx % op.in_ch;
+        float a = 0.f;
+        for (int n = 0; n < op.out_ch; ++n) a = fmaf(__ldg(wflat + op.w_off + (long long)n * op.in_ch + k), dcur[v * VS + n], a);
+        dnxt[v * VS + k] = a;
+      }
+      __syncthreads();
+      float* t = dcur; dcur = dnxt; dnxt = t;
+    }
+    // un-flatten into the gradient of the last spatial activation
+    float* gcur = gA;
+    float* gnxt = gB;
+    {
+      const int C = Gb.ch[ns], len = Gb.len[ns];
+      for (int idx = tid; idx < C * VT * len; idx += NTHREADS) {
+        const int c = idx / (VT * len), v = (idx / len) % VT, p = idx % len;
+        gcur[idx] = dcur[v * VS + c * len + p];
+      }
+      __syncthreads();
+    }
+    // ---- backward: spatial ops in reverse ----
+    for (int i = ns - 1; i >= 0; --i) {
+      const PmtCnnOp& op = D.cnn_ops[i];
+      const float* in = acts + Gb.act_off[i];
+      const float* out = acts + Gb.act_off[i + 1];
+      const int li = Gb.len[i], lo = Gb.len[i + 1];
+      if (op.kind == PMT_CNN_POOL) {
+        // gradient goes to the first maximum of each window (one thread per INPUT element: no atomics)
+        for (int idx = tid; idx < op.in_ch * VT * li; idx += NTHREADS) {
+          const int cv = idx / li, q = idx % li;
+          float a = 0.f;
+          int p_lo = q - op.ksize + 1;
+          p_lo = p_lo <= 0 ? 0 : (p_lo + op.stride - 1) / op.stride;
+          const int p_hi = min(lo - 1, q / op.stride);
+          for (int p = p_lo; p <= p_hi; ++p) {
+            const float* xr = in + cv * li + p * op.stride;
+            int arg = 0;
+            float m = xr[0];
+            for (int t = 1; t < op.ksize; ++t) if (xr[t] > m) { m = xr[t]; arg = t; }
+            if (p * op.stride + arg == q) a += gcur[cv * lo + p];
+          }
+          gnxt[idx] = a;
+        }
+        __syncthreads();
+      } else {
+        // through the activation folded into this conv
+        for (int idx = tid; idx < op.out_ch * VT * lo; idx += NTHREADS) gcur[idx] *= act_grad_from_out(out[idx], op.act);
+        __syncthreads();
+        // weight and bias gradients
+        for (int idx = tid; idx < op.out_ch * op.in_ch * op.ksize; idx += NTHREADS) {
+          const int co = idx / (op.in_ch * op.ksize), ci = (idx / op.ksize) % op.in_ch, t = idx % op.ksize;
+          float a = 0.f;
+          for (int v = 0; v < nv; ++v) {
+            const float* gr = gcur + (co * VT + v) * lo;
+            const float* xr = in + (ci * VT + v) * li + t;
+            for (int p = 0; p < lo; ++p) a = fmaf(gr[p], xr[p], a);
+          }
+          part[op.w_off + idx] += a;
+        }
+        for (int co = tid; co < op.out_ch; co += NTHREADS) {
+          float a = 0.f;
+          for (int v = 0; v < nv; ++v)
+            for (int p = 0; p < lo; ++p) a += gcur[(co * VT + v) * lo + p];
+          part[op.b_off + co] += a;
+        }
+        // data gradient (not needed for the one-hot input)
+        if (i > 0) {
+          for (int idx = tid; idx < op.in_ch * VT * li; idx += NTHREADS) {
+            const int ci = idx / (VT * li), v = (idx / li) % VT, q = idx % li;
+            float a = 0.f;
+            for (int co = 0; co < op.out_ch; ++co) {
+              const float* gr = gcur + (co * VT + v) * lo;
+              const float* wr = wflat + op.w_off + ((long long)co * op.in_ch + ci) * op.ksize;
+              for (int t = 0; t < op.ksize; ++t) {
+                const int p = q - t;
+                if (p >= 0 && p < lo) a = fmaf(__ldg(wr + t), gr[p], a);
+              }
+            }
+            gnxt[idx] = a;
+          }
+        }
+        __syncthreads();
+      }
+      float* t = gcur; gcur = gnxt; gnxt = t;
+    }
+  }
+}
+
 }  // namespace pmt
 
 // ================================================================================================
@@ -553,9 +774,49 @@ __global__ void skip_fix_kernel(const __grid_constant__ Plan P, const float* __r
 // ================================================================================================
 using namespace pmt;
 
-int pmt_launch_cnn_backward(const Plan&, const CnnGeom&, const float*, const float*, const PmtBatch*, const float*, float*,
-                            int, cudaStream_t) {
-  return 0;   // TODO(next commit): haplotype CNN backward kernel
+int pmt_launch_cnn_backward(const Plan& P, const CnnGeom& G, const float* weights, const float* image,
+                            const PmtBatch* batch, const float* d_info_seq, float* partials, int n_partials,
+                            cudaStream_t st) {
+  (void)image;
+  CnnBwdGeom Gb;
+  memset(&Gb, 0, sizeof(Gb));
+  const PmtModelDesc& d = P.d;
+  Gb.n_spatial = G.n_spatial;
+  Gb.n_linear = d.n_cnn_ops - G.n_spatial;
+  PMT_CHECK(Gb.n_linear >= 1 && Gb.n_linear <= 4, "haplotype CNN backward supports 1..4 linear layers after flatten");
+  Gb.ch[0] = 10; Gb.len[0] = d.hap_len;
+  for (int i = 0; i < G.n_spatial; ++i) {
+    const PmtCnnOp& op = d.cnn_ops[i];
+    Gb.ch[i + 1] = op.kind == PMT_CNN_CONV ? op.out_ch : op.in_ch;
+    Gb.len[i + 1] = op.out_len;
+  }
+  int vs = Gb.ch[G.n_spatial] * Gb.len[G.n_spatial];
+  for (int l = 0; l < Gb.n_linear; ++l) if (d.cnn_ops[G.n_spatial + l].out_ch > vs) vs = d.cnn_ops[G.n_spatial + l].out_ch;
+  vs = (vs + 3) & ~3;
+  Gb.vs = vs;
+  int per_var = 0, gmax = 0;
+  for (int i = 0; i <= G.n_spatial; ++i) {
+    per_var += Gb.ch[i] * Gb.len[i];
+    if (Gb.ch[i] * Gb.len[i] > gmax) gmax = Gb.ch[i] * Gb.len[i];
+  }
+  int vt = 16;
+  size_t smem = 0;
+  for (; vt >= 1; --vt) {
+    smem = (size_t)(vt * per_var + 2 * vt * gmax + (Gb.n_linear + 3) * vt * vs + 16) * sizeof(float);
+    if (smem <= 200 * 1024) break;
+  }
+  PMT_CHECK(vt >= 1, "haplotype CNN backward does not fit in shared memory");
+  Gb.vt = vt; Gb.gmax = vt * gmax;
+  int off = 0;
+  for (int i = 0; i <= G.n_spatial; ++i) { Gb.act_off[i] = off; off += vt * Gb.ch[i] * Gb.len[i]; }
+  Gb.act_total = off;
+  const int B = batch->n_variants;
+  int grid = (B + vt - 1) / vt;
+  if (grid > n_partials) grid = n_partials;
+  cudaFuncSetAttribute(hap_cnn_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  hap_cnn_backward_kernel<<<grid, NTHREADS, smem, st>>>(P, Gb, weights, batch->haplotypes, batch->hap_kind, batch->hap_stride,
+                                                        B, d_info_seq, partials);
+  return 0;
 }
 
 static size_t bwd_smem_bytes(const Plan& P) {

@@ -255,44 +255,46 @@ static __device__ __noinline__ void wgrad_tile(unsigned dy_s, int N, unsigned a_
   if (r_hi <= r_lo) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kl = lane & 15;
-  const int ka = (K + 15) >> 4;
-  for (int ng = warp * 2 + (lane >> 4); ng * 4 < N; ng += 2 * NWARPS) {
-    float acc[4][4];
-#pragma unroll
-    for (int b = 0; b < 4; ++b)
-#pragma unroll
-      for (int a = 0; a < 4; ++a) acc[b][a] = 0.f;
-    unsigned dyp[4], ap[4];
-#pragma unroll
-    for (int b = 0; b < 4; ++b) dyp[b] = dy_s + (min(ng * 4 + b, N - 1) * LD) * 4;
-#pragma unroll
-    for (int a = 0; a < 4; ++a) ap[a] = a_s + (min(kl + 16 * a, K - 1) * LD) * 4;
-    for (int r = r_lo; r < r_hi; r += 4) {
-      float4 dy[4], av[4];
-#pragma unroll
-      for (int b = 0; b < 4; ++b) dy[b] = lds128(dyp[b] + r * 4);
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-        if (a < ka) av[a] = lds128(ap[a] + r * 4);
+  for (int k0 = 0; k0 < K; k0 += 64) {
+    const int ka = min(4, (K - k0 + 15) >> 4);
+    for (int ng = warp * 2 + (lane >> 4); ng * 4 < N; ng += 2 * NWARPS) {
+      float acc[4][4];
 #pragma unroll
       for (int b = 0; b < 4; ++b)
 #pragma unroll
+        for (int a = 0; a < 4; ++a) acc[b][a] = 0.f;
+      unsigned dyp[4], ap[4];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) dyp[b] = dy_s + (min(ng * 4 + b, N - 1) * LD) * 4;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) ap[a] = a_s + (min(k0 + kl + 16 * a, K - 1) * LD) * 4;
+      for (int r = r_lo; r < r_hi; r += 4) {
+        float4 dy[4], av[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) dy[b] = lds128(dyp[b] + r * 4);
+#pragma unroll
         for (int a = 0; a < 4; ++a)
-          if (a < ka) {
-            acc[b][a] = fmaf(dy[b].x, av[a].x, acc[b][a]);
-            acc[b][a] = fmaf(dy[b].y, av[a].y, acc[b][a]);
-            acc[b][a] = fmaf(dy[b].z, av[a].z, acc[b][a]);
-            acc[b][a] = fmaf(dy[b].w, av[a].w, acc[b][a]);
+          if (a < ka) av[a] = lds128(ap[a] + r * 4);
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+            if (a < ka) {
+              acc[b][a] = fmaf(dy[b].x, av[a].x, acc[b][a]);
+              acc[b][a] = fmaf(dy[b].y, av[a].y, acc[b][a]);
+              acc[b][a] = fmaf(dy[b].z, av[a].z, acc[b][a]);
+              acc[b][a] = fmaf(dy[b].w, av[a].w, acc[b][a]);
+            }
+      }
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int n = ng * 4 + b;
+        if (n < N) {
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            const int k = k0 + kl + 16 * a;
+            if (a < ka && k < K) part[n * K + k] += acc[b][a];
           }
-    }
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const int n = ng * 4 + b;
-      if (n < N) {
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          const int k = kl + 16 * a;
-          if (k < K) part[n * K + k] += acc[b][a];
         }
       }
     }
