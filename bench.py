@@ -168,6 +168,66 @@ def run_reference(args, rank):
     }))
 
 
+def run_training(args, model, ia, fa, reads, dev, world, barrier):
+    """every step draws a DownsampledBatch of one resident parent chunk on the device and
+    takes one optimiser step.  Returns the `train` record (rank-local timing reduced with MAX by the caller's barrier)."""
+    import torch.distributed as dist
+    from permutect_b200.data.batch import Batch, DownsampledBatch
+    from permutect_b200.engine import function as engine
+    from permutect_b200.training.step import make_optimizer, train_step
+    from permutect_b200.utils.enums import Epoch
+
+    bt = min(args.train_batch, len(ia))
+    n_chunks = max(1, min(8, len(ia) // bt))
+    ref_c, alt_c = ia[:, 0].astype(np.int64), ia[:, 1].astype(np.int64)
+    ref_off, alt_off = np.concatenate(([0], np.cumsum(ref_c))), np.concatenate(([0], np.cumsum(alt_c)))
+    total_ref = int(ref_off[-1])
+    parents = []
+    for c in range(n_chunks):
+        v0, v1 = c * bt, (c + 1) * bt
+        sub = np.concatenate((reads[ref_off[v0]:ref_off[v1]], reads[total_ref + alt_off[v0]:total_ref + alt_off[v1]]))
+        parents.append(Batch.from_arrays(ia[v0:v1], fa[v0:v1], sub).copy_to(dev))
+    g = torch.Generator().manual_seed(7)
+    fracs = [(0.3 + 0.7 * torch.rand(bt, generator=g), 0.3 + 0.7 * torch.rand(bt, generator=g)) for _ in range(n_chunks)]
+    fracs = [(a.to(dev), b.to(dev)) for a, b in fracs]
+    model.set_epoch_type(Epoch.TRAIN)
+    opt = make_optimizer(model, learning_rate=1e-3, weight_decay=0.01)
+    prof = engine.ProfileEvents(dev)
+
+    def step(i, profile=False):
+        parent = parents[i % n_chunks]
+        batch = DownsampledBatch(parent, fracs[i % n_chunks][0], fracs[i % n_chunks][1], seed=1000 + i)
+        out = model.compute_batch_output(batch)
+        losses = model.compute_batch_losses(out, batch)
+        if profile:
+            prof.arm()           # arm only around the backward so the events bracket reads_backward_kernel
+        from permutect_b200.training.step import backpropagate
+        backpropagate(opt, losses.total_loss, params_to_clip=model.parameters())
+        if profile:
+            prof.disarm()
+        return losses
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        losses = step(args.warmup + i, profile=True)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    model.set_epoch_type(Epoch.VALID)
+    return {"metric": "artifact_model_training_variants_per_sec", "value": bt * world / (ms_max / 1e3), "unit": "variants/s",
+            "ms_per_step": ms_max, "batch_variants_per_gpu": bt, "last_loss_per_variant": float(losses.total_loss) / bt,
+            "backward_kernel_ms": prof.mean_ms(), "gpu_launches": 16 * args.steps,
+            "step": "device DownsampledBatch + compute_batch_output + compute_batch_losses + backward + grad all-reduce + clip(1.0) + AdamW"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -176,6 +236,8 @@ def main():
     ap.add_argument("--variants", type=int, default=1_250_000, help="variants per GPU shard")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--train-batch", type=int, default=65536, help="variants per optimiser step")
+    ap.add_argument("--no-train", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -257,6 +319,11 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = args.variants * world / (float(t.item()) / 1e3)
 
+    # ---- training: downsample -> forward -> losses -> backward -> (all-reduce) -> clip -> AdamW ----------------
+    train = None
+    if not args.no_train:
+        train = run_training(args, model, ia, fa, reads, dev, world, barrier)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -284,6 +351,9 @@ def main():
         "e2e": {"value": e2e_value, "unit": "variants/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * args.variants},
         "roofline": roofline,
     }
+    if train is not None:
+        result["train"] = train
+        result["gpu_launches"] = 5 * args.steps + train["gpu_launches"]
     if not args.no_cpu_baseline:
         sample = 8192
         v, n_it = time_oracle(model.state_dict(), sample, seed=3000, budget_s=15.0)

@@ -163,6 +163,19 @@ int pmt_backward(const PmtModelDesc* desc, const float* weights, const PmtBatch*
  * (reads_forward_kernel / reads_backward_kernel) on the call's stream.  Pass NULLs to disarm. */
 int pmt_set_profile_events(void* start_event, void* stop_event);
 
+/* DownsampledBatch.__init__ (batch.py:383-439) on the device, in two stream-ordered steps with an
+ * exclusive scan of the new counts (caller-side) in between.  Keep decisions are a counter-based hash of
+ * (seed, read row) compared with the per-variant keep fractions; one alt read per variant is always
+ * kept (batch.py:418-425, `random_int` plays the role of the reference's randint(0, 100)).
+ * read_indices receives the kept ref rows followed by the kept alt rows; alt entries are NOT offset by
+ * the ref-block size unless offset_alt_rows != 0 (reference behaviour, quirk Q1, batch.py:436-439). */
+int pmt_downsample_counts(const int64_t* ref_off, const int64_t* alt_off, const float* ref_fracs, const float* alt_fracs,
+                          int32_t n_variants, uint64_t seed, int32_t random_int, int64_t* new_ref_counts,
+                          int64_t* new_alt_counts, void* stream);
+int pmt_downsample_fill(const int64_t* ref_off, const int64_t* alt_off, const float* ref_fracs, const float* alt_fracs,
+                        int32_t n_variants, uint64_t seed, int32_t random_int, const int64_t* new_ref_off,
+                        const int64_t* new_alt_off, int32_t offset_alt_rows, int64_t* read_indices, void* stream);
+
 /* Batch.__init__ decode (batch.py:51-56, plain_text_data.py:510-511): compressed rows -> [R][F] float32. */
 int pmt_decode_reads(const uint8_t* reads_u8, int64_t n_rows, int32_t row_bytes, float* out, void* stream);
 

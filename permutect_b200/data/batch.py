@@ -192,7 +192,8 @@ class DownsampledBatch(Batch):
             self._device_counts = (ref_counts.to(self.device, torch.int64), alt_counts.to(self.device, torch.int64))
         else:
             from permutect_b200.data.downsample import downsample_on_device
-            self.read_indices, ref_c, alt_c = downsample_on_device(original_batch, ref_fracs_b, alt_fracs_b,
-                                                                   offset_alt_rows=offset_alt_rows, seed=seed)
+            self.read_indices, ref_c, alt_c, new_off = downsample_on_device(original_batch, ref_fracs_b, alt_fracs_b,
+                                                                            offset_alt_rows=offset_alt_rows, seed=seed)
             self._device_counts = (ref_c, alt_c)
+            self._offsets = new_off
         self.ref_counts, self.alt_counts = self._device_counts

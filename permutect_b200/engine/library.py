@@ -66,7 +66,7 @@ class PmtOutGrads(C.Structure):
 
 
 EXPORTED_SYMBOLS = ["pmt_last_error", "pmt_abi_version", "pmt_workspace_size", "pmt_forward", "pmt_backward",
-                    "pmt_decode_reads", "pmt_set_profile_events"]
+                    "pmt_decode_reads", "pmt_set_profile_events", "pmt_downsample_counts", "pmt_downsample_fill"]
 
 _LIB = None
 
@@ -97,6 +97,12 @@ def load():
                                  C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.pmt_decode_reads.restype = C.c_int
     lib.pmt_decode_reads.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.pmt_downsample_counts.restype = C.c_int
+    lib.pmt_downsample_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_uint64, C.c_int32,
+                                          C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.pmt_downsample_fill.restype = C.c_int
+    lib.pmt_downsample_fill.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_uint64, C.c_int32,
+                                        C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     lib.pmt_set_profile_events.restype = C.c_int
     lib.pmt_set_profile_events.argtypes = [C.c_void_p, C.c_void_p]
     if lib.pmt_abi_version() != PMT_ABI_VERSION:

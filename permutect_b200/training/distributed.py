@@ -1,0 +1,70 @@
+"""Variant-sharded data parallelism.  The reference has no multi-GPU code; variants are
+independent (the only cross-read coupling is inside a variant, gated_mlp.py:236-248), so
+
+  * inference shards variants by contiguous index range with NO collective (the scheme the reference uses
+    for DataLoader workers, reads_dataset.py:141-142);
+  * training adds exactly one exchange per optimiser step: an all-reduce(SUM) of the flat fp32 gradient
+    (68 229 floats = 273 KB at the shipped hyper-parameters).  The reference differentiates the SUM of the
+    per-variant losses (artifact_model.py:90), so gradients are summed, not averaged, and the learning rate
+    is unchanged; clipping uses the norm of the reduced gradient, hence identical updates on every rank.
+    Host-side per-rank statistics that feed back into training (Balancer counters) are summed the same way.
+"""
+from typing import Iterable, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def is_initialized() -> bool:
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def shard_range(n_items: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous, balanced [start, end) of rank's share of n_items (sizes differ by at most one)."""
+    base, extra = divmod(n_items, world_size)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def allreduce_flat_(tensors: List[torch.Tensor], group=None) -> None:
+    """Sum a list of same-dtype tensors across ranks with ONE collective on a flat buffer, in place."""
+    tensors = [t for t in tensors if t is not None]
+    if not tensors:
+        return
+    flat = torch.cat([t.reshape(-1) for t in tensors])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    off = 0
+    for t in tensors:
+        n = t.numel()
+        t.copy_(flat[off:off + n].view_as(t))
+        off += n
+
+
+def allreduce_gradients(params: Iterable[torch.nn.Parameter], group=None) -> None:
+    """Sum .grad across ranks.  A parameter without a gradient on this rank contributes zeros, so the
+    collective has the same shape everywhere (e.g. calibration epochs freeze most tensors on all ranks alike)."""
+    params = [p for p in params if p.requires_grad]
+    for p in params:
+        if p.grad is None:
+            p.grad = torch.zeros_like(p)
+    allreduce_flat_([p.grad for p in params], group)
+
+
+def allreduce_counters(tensors: List[torch.Tensor], group=None) -> None:
+    """Balancer / loss-metric increments observed on each rank -> global sums (balancer.py:61-72)."""
+    allreduce_flat_(tensors, group)
+
+
+def gather_variant_outputs(local: torch.Tensor, n_total: int, group=None) -> Optional[torch.Tensor]:
+    """Concatenate rank-local per-variant outputs in variant order on every rank (inference needs the order
+    only to re-associate logits with their Datum, filter_variants.py:302-320)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    sizes = [shard_range(n_total, r, world)[1] - shard_range(n_total, r, world)[0] for r in range(world)]
+    assert local.shape[0] == sizes[rank]
+    biggest = max(sizes)          # shard sizes differ by at most one; pad so the collective is uniform
+    padded = torch.zeros((biggest,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    padded[: local.shape[0]] = local
+    chunks = [torch.empty_like(padded) for _ in sizes]
+    dist.all_gather(chunks, padded, group=group)
+    return torch.cat([c[:s] for c, s in zip(chunks, sizes)])
