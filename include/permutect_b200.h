@@ -159,7 +159,7 @@ int pmt_backward(const PmtModelDesc* desc, const float* weights, const PmtBatch*
                  float* d_weights, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Measurement hook (no reference counterpart): when both are non-NULL, the next pmt_forward /
- * pmt_backward calls on this host thread record these cudaEvent_t around their dominant kernel
+ * pmt_backward calls of this process record these cudaEvent_t around their dominant kernel
  * (reads_forward_kernel / reads_backward_kernel) on the call's stream.  Pass NULLs to disarm. */
 int pmt_set_profile_events(void* start_event, void* stop_event);
 

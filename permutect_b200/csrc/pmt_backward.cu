@@ -10,6 +10,7 @@
 //   skip_fix_kernel           DenseSkipBlock.alpha gradients and the alpha scaling of its last layer
 #include <cstring>
 
+#include "pmt_cnn.cuh"
 #include "pmt_host.h"
 #include "pmt_tile.cuh"
 
@@ -549,14 +550,17 @@ __global__ void skip_fix_kernel(const __grid_constant__ Plan P, const float* __r
 
 // ------------------------------------------------------------------------------------------------
 // haplotype CNN backward (dna_sequence_convolution.py:57-111).  VT variants per pass; every layer's
-// activation of the pass stays in shared memory as [C][VT][len]; gradients ping-pong between two buffers.
+// activation of the pass stays in shared memory, channel-major with a per-variant stride lp[i] (multiple of 4)
+// and a channel stride ld[i] == 4 (mod 32) so that 16-byte loads by lanes on consecutive channels are
+// conflict-free.  conv data gradient = the forward conv routine on the zero-padded output gradient with the
+// flipped/transposed image; conv weight gradient = register-tiled reduction over (variant, position).
 // ------------------------------------------------------------------------------------------------
 struct CnnBwdGeom {
-  int vt;
-  int act_off[PMT_MAX_CNN_OPS + 1];   // float offset of the activation entering spatial op i ([n_spatial] = last output)
-  int ch[PMT_MAX_CNN_OPS + 1], len[PMT_MAX_CNN_OPS + 1];
-  int act_total, gmax, n_spatial, n_linear;
-  int vs;                             // row stride of the linear-stack vectors
+  int vt, n_spatial, n_linear, vs;
+  int ch[PMT_MAX_CNN_OPS + 1], len[PMT_MAX_CNN_OPS + 1], lp[PMT_MAX_CNN_OPS + 1], ld[PMT_MAX_CNN_OPS + 1];
+  int act_off[PMT_MAX_CNN_OPS + 1];   // activation entering spatial op i ([n_spatial] = last output)
+  int lpg[PMT_MAX_CNN_OPS], ldg[PMT_MAX_CNN_OPS];   // zero-padded layout of conv op i's output gradient
+  int act_total, gbuf_floats, stage_floats;
 };
 
 __device__ __forceinline__ float act_grad_from_out(float y, int act) {
@@ -564,67 +568,118 @@ __device__ __forceinline__ float act_grad_from_out(float y, int act) {
   if (act == PMT_ACT_LEAKY_RELU) return y > 0.f ? 1.f : 0.01f;
   return 1.f;
 }
-__device__ __forceinline__ float apply_act_b(float x, int act) {
-  if (act == PMT_ACT_SELU) return selu(x);
-  if (act == PMT_ACT_LEAKY_RELU) return x > 0.f ? x : 0.01f * x;
-  return x;
+
+__device__ __forceinline__ void stage_image(float* dst, const float* __restrict__ src, int n_floats) {
+  for (int i = threadIdx.x; i < n_floats / 4; i += NTHREADS)
+    reinterpret_cast<float4*>(dst)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+}
+
+// dW[co][ci][t] += sum_{v, p} g[co][v, p] * in[ci][v, p + t];  g must be zero at padding positions.
+// One (4 output channels, 1 input channel) unit per thread; lanes run over consecutive input channels.
+template <int KS>
+__device__ __forceinline__ void conv_wgrad(const PmtCnnOp& op, const float* __restrict__ in, int in_ld, int lp_in,
+                                           const float* __restrict__ g, int g_ld, int lp_out, int vt,
+                                           float* __restrict__ part) {
+  const int n_cg = (op.out_ch + 3) / 4;
+  for (int unit = threadIdx.x; unit < n_cg * op.in_ch; unit += NTHREADS) {
+    const int cg = unit / op.in_ch, ci = unit % op.in_ch;
+    float acc[4][KS];
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+      for (int t = 0; t < KS; ++t) acc[b][t] = 0.f;
+    const float* xr = in + ci * in_ld;
+    const float* gr[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) gr[b] = g + min(cg * 4 + b, op.out_ch - 1) * g_ld;
+    for (int v = 0; v < vt; ++v) {
+      for (int p0 = 0; p0 < lp_out; p0 += 4) {
+        float xw[12];
+        const float4 a = *reinterpret_cast<const float4*>(xr + v * lp_in + p0);
+        xw[0] = a.x; xw[1] = a.y; xw[2] = a.z; xw[3] = a.w;
+        if (KS > 1) {
+          const float4 c = *reinterpret_cast<const float4*>(xr + v * lp_in + p0 + 4);
+          xw[4] = c.x; xw[5] = c.y; xw[6] = c.z; xw[7] = c.w;
+        }
+        if (KS > 5) {
+          const float4 c = *reinterpret_cast<const float4*>(xr + v * lp_in + p0 + 8);
+          xw[8] = c.x; xw[9] = c.y; xw[10] = c.z; xw[11] = c.w;
+        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const float4 gv = *reinterpret_cast<const float4*>(gr[b] + v * lp_out + p0);
+#pragma unroll
+          for (int t = 0; t < KS; ++t) {
+            acc[b][t] = fmaf(gv.x, xw[t], acc[b][t]);
+            acc[b][t] = fmaf(gv.y, xw[t + 1], acc[b][t]);
+            acc[b][t] = fmaf(gv.z, xw[t + 2], acc[b][t]);
+            acc[b][t] = fmaf(gv.w, xw[t + 3], acc[b][t]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int co = cg * 4 + b;
+      if (co < op.out_ch) {
+#pragma unroll
+        for (int t = 0; t < KS; ++t) part[op.w_off + (co * op.in_ch + ci) * KS + t] += acc[b][t];
+      }
+    }
+  }
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
-hap_cnn_backward_kernel(const __grid_constant__ Plan P, const __grid_constant__ CnnBwdGeom Gb, const float* __restrict__ wflat,
-                        const void* __restrict__ haps, int hap_kind, long long hap_stride, int n_variants,
-                        const float* __restrict__ d_info_seq, float* partials) {
+hap_cnn_backward_kernel(const __grid_constant__ Plan P, const __grid_constant__ CnnGeom Gm,
+                        const __grid_constant__ CnnBwdGeom Gb, const float* __restrict__ wflat,
+                        const float* __restrict__ conv_image, const void* __restrict__ haps, int hap_kind,
+                        long long hap_stride, int n_variants, const float* __restrict__ d_info_seq, float* partials) {
   extern __shared__ __align__(16) float smem[];
   float* acts = smem;
   float* gA = acts + Gb.act_total;
-  float* gB = gA + Gb.gmax;
-  float* vec = gB + Gb.gmax;                 // [(n_linear + 1)][VT][vs] activations of the linear stack
+  float* gB = gA + Gb.gbuf_floats;
+  float* wst = gB + Gb.gbuf_floats;                        // staged conv image (forward or flipped)
+  float* vec = wst + Gb.stage_floats;                      // [(n_linear + 1)][VT][vs] activations of the linear stack
   float* dvec = vec + (Gb.n_linear + 1) * Gb.vt * Gb.vs;   // [2][VT][vs] gradients of the linear stack
   const PmtModelDesc& D = P.d;
   const int VT = Gb.vt, VS = Gb.vs, L = D.hap_len, ns = Gb.n_spatial, tid = threadIdx.x;
   const int out_w = D.d_info + D.d_seq;
   float* part = partials + (long long)blockIdx.x * D.n_params;
+  for (int i = tid; i < Gb.act_total + 2 * Gb.gbuf_floats; i += NTHREADS) smem[i] = 0.f;
 
   for (int v0 = blockIdx.x * VT; v0 < n_variants; v0 += gridDim.x * VT) {
     const int nv = min(VT, n_variants - v0);
     __syncthreads();
     // ---- forward recompute ----
-    for (int idx = tid; idx < 10 * VT * L; idx += NTHREADS) {
-      const int c = idx / (VT * L), v = (idx / L) % VT, p = idx % L;
-      float x = 0.f;
+    for (int idx = tid; idx < VT * 2 * L; idx += NTHREADS) {
+      const int v = idx / (2 * L), hp = idx % (2 * L);
+      int code = -1;
       if (v < nv) {
-        const int h = c & 1, code_want = c >> 1;
-        const long long off = (long long)(v0 + v) * hap_stride + h * L + p;
-        const int code = hap_kind == PMT_I64 ? (int)reinterpret_cast<const long long*>(haps)[off]
-                                             : (int)reinterpret_cast<const short*>(haps)[off];
-        x = code == code_want ? 1.f : 0.f;
+        const long long off = (long long)(v0 + v) * hap_stride + hp;
+        code = hap_kind == PMT_I64 ? (int)reinterpret_cast<const long long*>(haps)[off]
+                                   : (int)reinterpret_cast<const short*>(haps)[off];
       }
-      acts[Gb.act_off[0] + idx] = x;
+      const int h = hp / L, p = hp % L;
+#pragma unroll
+      for (int c = 0; c < 5; ++c) acts[Gb.act_off[0] + (2 * c + h) * Gb.ld[0] + v * Gb.lp[0] + p] = (code == c) ? 1.f : 0.f;
     }
     __syncthreads();
     for (int i = 0; i < ns; ++i) {
       const PmtCnnOp& op = D.cnn_ops[i];
       const float* in = acts + Gb.act_off[i];
       float* out = acts + Gb.act_off[i + 1];
-      const int li = Gb.len[i], lo = Gb.len[i + 1];
       if (op.kind == PMT_CNN_CONV) {
-        for (int idx = tid; idx < op.out_ch * VT * lo; idx += NTHREADS) {
-          const int co = idx / (VT * lo), v = (idx / lo) % VT, p = idx % lo;
-          float a = __ldg(wflat + op.b_off + co);
-          const float* wr = wflat + op.w_off + (long long)co * op.in_ch * op.ksize;
-          for (int ci = 0; ci < op.in_ch; ++ci) {
-            const float* xr = in + (ci * VT + v) * li + p;
-            for (int t = 0; t < op.ksize; ++t) a = fmaf(__ldg(wr + ci * op.ksize + t), xr[t], a);
-          }
-          out[idx] = apply_act_b(a, op.act);
-        }
+        stage_image(wst, conv_image + Gm.img_off[i], op.in_ch * op.ksize * ((op.out_ch + 7) / 8) * GROUP_STRIDE);
+        __syncthreads();
+        PMT_CONV_DISPATCH(op.ksize, op, in, Gb.ld[i], Gb.lp[i], out, Gb.ld[i + 1], Gb.lp[i + 1], wst, wflat, VT)
       } else {
+        const int lo = Gb.len[i + 1];
         for (int idx = tid; idx < op.in_ch * VT * lo; idx += NTHREADS) {
-          const int cv = idx / lo, p = idx % lo;
-          const float* xr = in + cv * li + p * op.stride;
+          const int c = idx / (VT * lo), v = (idx / lo) % VT, p = idx % lo;
+          const float* xr = in + c * Gb.ld[i] + v * Gb.lp[i] + p * op.stride;
           float m = xr[0];
           for (int t = 1; t < op.ksize; ++t) m = fmaxf(m, xr[t]);
-          out[idx] = m;
+          out[c * Gb.ld[i + 1] + v * Gb.lp[i + 1] + p] = m;
         }
       }
       __syncthreads();
@@ -634,7 +689,7 @@ hap_cnn_backward_kernel(const __grid_constant__ Plan P, const __grid_constant__ 
       const int C = Gb.ch[ns], len = Gb.len[ns];
       for (int idx = tid; idx < VT * C * len; idx += NTHREADS) {
         const int v = idx / (C * len), k = idx % (C * len), c = k / len, p = k % len;
-        vec[v * VS + k] = acts[Gb.act_off[ns] + (c * VT + v) * len + p];
+        vec[v * VS + k] = acts[Gb.act_off[ns] + c * Gb.ld[ns] + v * Gb.lp[ns] + p];
       }
       __syncthreads();
       for (int l = 0; l < Gb.n_linear; ++l) {
@@ -646,7 +701,7 @@ hap_cnn_backward_kernel(const __grid_constant__ Plan P, const __grid_constant__ 
           float a = __ldg(wflat + op.b_off + n);
           const float* wr = wflat + op.w_off + (long long)n * op.in_ch;
           for (int k = 0; k < op.in_ch; ++k) a = fmaf(__ldg(wr + k), vin[v * VS + k], a);
-          vout[v * VS + n] = apply_act_b(a, op.act);
+          vout[v * VS + n] = apply_act(a, op.act);
         }
         __syncthreads();
       }
@@ -688,14 +743,14 @@ hap_cnn_backward_kernel(const __grid_constant__ Plan P, const __grid_constant__ 
       __syncthreads();
       float* t = dcur; dcur = dnxt; dnxt = t;
     }
-    // un-flatten into the gradient of the last spatial activation
+    // un-flatten into the gradient of the last spatial activation (layout of act[ns])
     float* gcur = gA;
     float* gnxt = gB;
     {
       const int C = Gb.ch[ns], len = Gb.len[ns];
       for (int idx = tid; idx < C * VT * len; idx += NTHREADS) {
         const int c = idx / (VT * len), v = (idx / len) % VT, p = idx % len;
-        gcur[idx] = dcur[v * VS + c * len + p];
+        gcur[c * Gb.ld[ns] + v * Gb.lp[ns] + p] = dcur[v * VS + c * len + p];
       }
       __syncthreads();
     }
@@ -705,64 +760,66 @@ hap_cnn_backward_kernel(const __grid_constant__ Plan P, const __grid_constant__ 
       const float* in = acts + Gb.act_off[i];
       const float* out = acts + Gb.act_off[i + 1];
       const int li = Gb.len[i], lo = Gb.len[i + 1];
+      const int ld_i = Gb.ld[i], lp_i = Gb.lp[i], ld_o = Gb.ld[i + 1], lp_o = Gb.lp[i + 1];
       if (op.kind == PMT_CNN_POOL) {
         // gradient goes to the first maximum of each window (one thread per INPUT element: no atomics)
         for (int idx = tid; idx < op.in_ch * VT * li; idx += NTHREADS) {
-          const int cv = idx / li, q = idx % li;
+          const int c = idx / (VT * li), v = (idx / li) % VT, q = idx % li;
           float a = 0.f;
           int p_lo = q - op.ksize + 1;
           p_lo = p_lo <= 0 ? 0 : (p_lo + op.stride - 1) / op.stride;
           const int p_hi = min(lo - 1, q / op.stride);
           for (int p = p_lo; p <= p_hi; ++p) {
-            const float* xr = in + cv * li + p * op.stride;
+            const float* xr = in + c * ld_i + v * lp_i + p * op.stride;
             int arg = 0;
             float m = xr[0];
             for (int t = 1; t < op.ksize; ++t) if (xr[t] > m) { m = xr[t]; arg = t; }
-            if (p * op.stride + arg == q) a += gcur[cv * lo + p];
+            if (p * op.stride + arg == q) a += gcur[c * ld_o + v * lp_o + p];
           }
-          gnxt[idx] = a;
+          gnxt[c * ld_i + v * lp_i + q] = a;
         }
         __syncthreads();
+        float* t = gcur; gcur = gnxt; gnxt = t;
       } else {
-        // through the activation folded into this conv
-        for (int idx = tid; idx < op.out_ch * VT * lo; idx += NTHREADS) gcur[idx] *= act_grad_from_out(out[idx], op.act);
+        // through the activation folded into this conv; padding positions are forced to zero
+        for (int idx = tid; idx < op.out_ch * VT * lp_o; idx += NTHREADS) {
+          const int c = idx / (VT * lp_o), v = (idx / lp_o) % VT, p = idx % lp_o;
+          const int o = c * ld_o + v * lp_o + p;
+          gcur[o] = p < lo ? gcur[o] * act_grad_from_out(out[o], op.act) : 0.f;
+        }
         __syncthreads();
-        // weight and bias gradients
-        for (int idx = tid; idx < op.out_ch * op.in_ch * op.ksize; idx += NTHREADS) {
-          const int co = idx / (op.in_ch * op.ksize), ci = (idx / op.ksize) % op.in_ch, t = idx % op.ksize;
-          float a = 0.f;
-          for (int v = 0; v < nv; ++v) {
-            const float* gr = gcur + (co * VT + v) * lo;
-            const float* xr = in + (ci * VT + v) * li + t;
-            for (int p = 0; p < lo; ++p) a = fmaf(gr[p], xr[p], a);
-          }
-          part[op.w_off + idx] += a;
+        switch (op.ksize) {
+          case 1: conv_wgrad<1>(op, in, ld_i, lp_i, gcur, ld_o, lp_o, VT, part); break;
+          case 2: conv_wgrad<2>(op, in, ld_i, lp_i, gcur, ld_o, lp_o, VT, part); break;
+          case 3: conv_wgrad<3>(op, in, ld_i, lp_i, gcur, ld_o, lp_o, VT, part); break;
+          case 4: conv_wgrad<4>(op, in, ld_i, lp_i, gcur, ld_o, lp_o, VT, part); break;
+          case 5: conv_wgrad<5>(op, in, ld_i, lp_i, gcur, ld_o, lp_o, VT, part); break;
+          case 6: conv_wgrad<6>(op, in, ld_i, lp_i, gcur, ld_o, lp_o, VT, part); break;
+          case 7: conv_wgrad<7>(op, in, ld_i, lp_i, gcur, ld_o, lp_o, VT, part); break;
+          case 8: conv_wgrad<8>(op, in, ld_i, lp_i, gcur, ld_o, lp_o, VT, part); break;
+          default: conv_wgrad<9>(op, in, ld_i, lp_i, gcur, ld_o, lp_o, VT, part); break;
         }
         for (int co = tid; co < op.out_ch; co += NTHREADS) {
           float a = 0.f;
-          for (int v = 0; v < nv; ++v)
-            for (int p = 0; p < lo; ++p) a += gcur[(co * VT + v) * lo + p];
+          for (int v = 0; v < VT; ++v)
+            for (int p = 0; p < lo; ++p) a += gcur[co * ld_o + v * lp_o + p];
           part[op.b_off + co] += a;
         }
-        // data gradient (not needed for the one-hot input)
         if (i > 0) {
-          for (int idx = tid; idx < op.in_ch * VT * li; idx += NTHREADS) {
-            const int ci = idx / (VT * li), v = (idx / li) % VT, q = idx % li;
-            float a = 0.f;
-            for (int co = 0; co < op.out_ch; ++co) {
-              const float* gr = gcur + (co * VT + v) * lo;
-              const float* wr = wflat + op.w_off + ((long long)co * op.in_ch + ci) * op.ksize;
-              for (int t = 0; t < op.ksize; ++t) {
-                const int p = q - t;
-                if (p >= 0 && p < lo) a = fmaf(__ldg(wr + t), gr[p], a);
-              }
-            }
-            gnxt[idx] = a;
+          // zero-padded copy of the output gradient, then the forward conv routine with the flipped image
+          const int ldg = Gb.ldg[i], lpg = Gb.lpg[i], ks = op.ksize;
+          stage_image(wst, conv_image + Gm.img_total + Gm.imgT_off[i], op.out_ch * ks * ((op.in_ch + 7) / 8) * GROUP_STRIDE);
+          for (int idx = tid; idx < op.out_ch * VT * lpg; idx += NTHREADS) {
+            const int c = idx / (VT * lpg), v = (idx / lpg) % VT, pp = idx % lpg, p = pp - (ks - 1);
+            gnxt[c * ldg + v * lpg + pp] = (p >= 0 && p < lo) ? gcur[c * ld_o + v * lp_o + p] : 0.f;
           }
+          __syncthreads();
+          PmtCnnOp tr = op;
+          tr.in_ch = op.out_ch; tr.out_ch = op.in_ch; tr.b_off = -1; tr.act = PMT_ACT_NONE;
+          PMT_CONV_DISPATCH(ks, tr, gnxt, ldg, lpg, gcur, ld_i, lp_i, wst, wflat, VT)
+          __syncthreads();
         }
-        __syncthreads();
       }
-      float* t = gcur; gcur = gnxt; gnxt = t;
     }
   }
 }
@@ -774,48 +831,65 @@ hap_cnn_backward_kernel(const __grid_constant__ Plan P, const __grid_constant__ 
 // ================================================================================================
 using namespace pmt;
 
+static int pad_ld(int n) {   // smallest ld >= n + 12 with ld == 4 (mod 32)
+  int ld = n + 12;
+  while ((ld & 31) != 4) ++ld;
+  return ld;
+}
+
 int pmt_launch_cnn_backward(const Plan& P, const CnnGeom& G, const float* weights, const float* image,
                             const PmtBatch* batch, const float* d_info_seq, float* partials, int n_partials,
                             cudaStream_t st) {
-  (void)image;
   CnnBwdGeom Gb;
-  memset(&Gb, 0, sizeof(Gb));
   const PmtModelDesc& d = P.d;
-  Gb.n_spatial = G.n_spatial;
-  Gb.n_linear = d.n_cnn_ops - G.n_spatial;
-  PMT_CHECK(Gb.n_linear >= 1 && Gb.n_linear <= 4, "haplotype CNN backward supports 1..4 linear layers after flatten");
-  Gb.ch[0] = 10; Gb.len[0] = d.hap_len;
-  for (int i = 0; i < G.n_spatial; ++i) {
-    const PmtCnnOp& op = d.cnn_ops[i];
-    Gb.ch[i + 1] = op.kind == PMT_CNN_CONV ? op.out_ch : op.in_ch;
-    Gb.len[i + 1] = op.out_len;
-  }
-  int vs = Gb.ch[G.n_spatial] * Gb.len[G.n_spatial];
-  for (int l = 0; l < Gb.n_linear; ++l) if (d.cnn_ops[G.n_spatial + l].out_ch > vs) vs = d.cnn_ops[G.n_spatial + l].out_ch;
-  vs = (vs + 3) & ~3;
-  Gb.vs = vs;
-  int per_var = 0, gmax = 0;
-  for (int i = 0; i <= G.n_spatial; ++i) {
-    per_var += Gb.ch[i] * Gb.len[i];
-    if (Gb.ch[i] * Gb.len[i] > gmax) gmax = Gb.ch[i] * Gb.len[i];
-  }
-  int vt = 16;
+  const int ns = G.n_spatial;
   size_t smem = 0;
+  int vt = 16;
   for (; vt >= 1; --vt) {
-    smem = (size_t)(vt * per_var + 2 * vt * gmax + (Gb.n_linear + 3) * vt * vs + 16) * sizeof(float);
-    if (smem <= 200 * 1024) break;
+    memset(&Gb, 0, sizeof(Gb));
+    Gb.vt = vt; Gb.n_spatial = ns; Gb.n_linear = d.n_cnn_ops - ns;
+    PMT_CHECK(Gb.n_linear >= 1 && Gb.n_linear <= 4, "haplotype CNN backward supports 1..4 linear layers after flatten");
+    Gb.ch[0] = 10; Gb.len[0] = d.hap_len;
+    for (int i = 0; i < ns; ++i) {
+      const PmtCnnOp& op = d.cnn_ops[i];
+      Gb.ch[i + 1] = op.kind == PMT_CNN_CONV ? op.out_ch : op.in_ch;
+      Gb.len[i + 1] = op.out_len;
+    }
+    int off = 0, gmax = 0, stage = 4;
+    for (int i = 0; i <= ns; ++i) {
+      Gb.lp[i] = (Gb.len[i] + 3) & ~3;
+      Gb.ld[i] = pad_ld(vt * Gb.lp[i]);
+      Gb.act_off[i] = off;
+      off += Gb.ch[i] * Gb.ld[i];
+      if (Gb.ch[i] * Gb.ld[i] > gmax) gmax = Gb.ch[i] * Gb.ld[i];
+    }
+    for (int i = 0; i < ns; ++i) {
+      const PmtCnnOp& op = d.cnn_ops[i];
+      if (op.kind != PMT_CNN_CONV) continue;
+      Gb.lpg[i] = (Gb.lp[i] + op.ksize - 1 + 3) & ~3;
+      Gb.ldg[i] = pad_ld(vt * Gb.lpg[i]);
+      if (i > 0 && op.out_ch * Gb.ldg[i] > gmax) gmax = op.out_ch * Gb.ldg[i];
+      const int fwd = op.in_ch * op.ksize * ((op.out_ch + 7) / 8) * GROUP_STRIDE;
+      const int bwd = op.out_ch * op.ksize * ((op.in_ch + 7) / 8) * GROUP_STRIDE;
+      if (fwd > stage) stage = fwd;
+      if (bwd > stage) stage = bwd;
+    }
+    int vs = Gb.ch[ns] * Gb.len[ns];
+    for (int l = 0; l < Gb.n_linear; ++l) if (d.cnn_ops[ns + l].out_ch > vs) vs = d.cnn_ops[ns + l].out_ch;
+    Gb.vs = (vs + 3) & ~3;
+    Gb.act_total = (off + 3) & ~3;
+    Gb.gbuf_floats = (gmax + 3) & ~3;
+    Gb.stage_floats = (stage + 3) & ~3;
+    smem = (size_t)(Gb.act_total + 2 * Gb.gbuf_floats + Gb.stage_floats + (Gb.n_linear + 3) * vt * Gb.vs + 16) * sizeof(float);
+    if (smem <= 220 * 1024) break;
   }
   PMT_CHECK(vt >= 1, "haplotype CNN backward does not fit in shared memory");
-  Gb.vt = vt; Gb.gmax = vt * gmax;
-  int off = 0;
-  for (int i = 0; i <= G.n_spatial; ++i) { Gb.act_off[i] = off; off += vt * Gb.ch[i] * Gb.len[i]; }
-  Gb.act_total = off;
   const int B = batch->n_variants;
   int grid = (B + vt - 1) / vt;
   if (grid > n_partials) grid = n_partials;
   cudaFuncSetAttribute(hap_cnn_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  hap_cnn_backward_kernel<<<grid, NTHREADS, smem, st>>>(P, Gb, weights, batch->haplotypes, batch->hap_kind, batch->hap_stride,
-                                                        B, d_info_seq, partials);
+  hap_cnn_backward_kernel<<<grid, NTHREADS, smem, st>>>(P, G, Gb, weights, image + P.img_total, batch->haplotypes,
+                                                        batch->hap_kind, batch->hap_stride, B, d_info_seq, partials);
   return 0;
 }
 

@@ -70,6 +70,8 @@ struct CnnGeom {
   int lp[PMT_MAX_CNN_OPS + 1];   // padded per-variant length of the activation entering op i (lp[n] = after last)
   int img_off[PMT_MAX_CNN_OPS];  // conv image offsets (floats) inside the conv image buffer
   int img_total;
+  int imgT_off[PMT_MAX_CNN_OPS]; // flipped + transposed conv images (backward data gradient), after the forward ones
+  int imgT_total;
   int buf_floats;                // floats per ping-pong activation buffer
   int n_spatial;                 // ops before the first PMT_CNN_LINEAR
 };

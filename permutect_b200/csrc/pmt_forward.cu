@@ -10,6 +10,7 @@
 
 #include "pmt_host.h"
 #include "pmt_tile.cuh"
+#include "pmt_cnn.cuh"
 
 namespace pmt {
 
@@ -56,6 +57,23 @@ __global__ void pack_conv_kernel(const __grid_constant__ Plan P, const __grid_co
   }
 }
 
+// backward data gradient of a conv = convolution of dOut (zero-padded by ks-1) with the flipped kernel:
+// image [(co*ks + t')][G over ci][8] = W[co][ci][ks-1-t']
+__global__ void pack_convT_kernel(const __grid_constant__ Plan P, const __grid_constant__ CnnGeom Gm,
+                                  const float* __restrict__ w, float* __restrict__ image) {
+  const PmtCnnOp& op = P.d.cnn_ops[blockIdx.x];
+  if (op.kind != PMT_CNN_CONV) return;
+  const int G = (op.in_ch + 7) / 8;
+  const int total = op.out_ch * op.ksize * G * GROUP_STRIDE;
+  float* img = image + Gm.img_total + Gm.imgT_off[blockIdx.x];
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int kk = idx / (G * GROUP_STRIDE), slot = idx % (G * GROUP_STRIDE);
+    const int co = kk / op.ksize, t = kk % op.ksize;
+    const int ci = (slot / GROUP_STRIDE) * 8 + slot % GROUP_STRIDE;
+    img[idx] = ci < op.in_ch ? w[op.w_off + (co * op.in_ch + ci) * op.ksize + (op.ksize - 1 - t)] : 0.f;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // info MLP: rows of the tile are variants
 // ------------------------------------------------------------------------------------------------
@@ -99,74 +117,6 @@ info_mlp_kernel(const __grid_constant__ Plan P, const float* __restrict__ wflat,
 // haplotype CNN
 // ------------------------------------------------------------------------------------------------
 
-__device__ __forceinline__ float apply_act(float x, int act) {
-  if (act == PMT_ACT_SELU) return selu(x);
-  if (act == PMT_ACT_LEAKY_RELU) return x > 0.f ? x : 0.01f * x;
-  return x;
-}
-
-template <int KS>
-__device__ __forceinline__ void conv_units(const PmtCnnOp& op, const float* __restrict__ in, int in_ld, int lp_in,
-                                           float* __restrict__ out, int out_ld, int lp_out, const float* __restrict__ img,
-                                           const float* __restrict__ wflat, int vt) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int G = (op.out_ch + 7) / 8;
-  const int q_per_var = lp_out / 4;
-  const int n_q = vt * q_per_var;  // 4-row groups
-  const int q_blocks = (n_q + 31) / 32;
-  for (int unit = warp; unit < q_blocks * G; unit += NWARPS) {
-    const int g = unit % G, q = (unit / G) * 32 + lane;
-    if (q >= n_q) continue;
-    const int v = q / q_per_var, p0 = (q % q_per_var) * 4;
-    float acc[4][8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int co = g * 8 + j;
-      const float b = co < op.out_ch ? __ldg(wflat + op.b_off + co) : 0.f;
-      acc[0][j] = b; acc[1][j] = b; acc[2][j] = b; acc[3][j] = b;
-    }
-    const float* xp = in + v * lp_in + p0;
-    const float* wp = img + g * GROUP_STRIDE;
-    const int wstride = G * GROUP_STRIDE;
-    for (int ci = 0; ci < op.in_ch; ++ci) {
-      float xw[12];
-      const float4 a = *reinterpret_cast<const float4*>(xp + ci * in_ld);
-      xw[0] = a.x; xw[1] = a.y; xw[2] = a.z; xw[3] = a.w;
-      if (KS > 1) {
-        const float4 b = *reinterpret_cast<const float4*>(xp + ci * in_ld + 4);
-        xw[4] = b.x; xw[5] = b.y; xw[6] = b.z; xw[7] = b.w;
-      }
-      if (KS > 5) {
-        const float4 c = *reinterpret_cast<const float4*>(xp + ci * in_ld + 8);
-        xw[8] = c.x; xw[9] = c.y; xw[10] = c.z; xw[11] = c.w;
-      }
-#pragma unroll
-      for (int t = 0; t < KS; ++t) {
-        const float* wr = wp + (ci * KS + t) * wstride;
-        const float4 w0 = *reinterpret_cast<const float4*>(wr);
-        const float4 w1 = *reinterpret_cast<const float4*>(wr + 4);
-        const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          acc[0][j] = fmaf(xw[t], w[j], acc[0][j]);
-          acc[1][j] = fmaf(xw[t + 1], w[j], acc[1][j]);
-          acc[2][j] = fmaf(xw[t + 2], w[j], acc[2][j]);
-          acc[3][j] = fmaf(xw[t + 3], w[j], acc[3][j]);
-        }
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int co = g * 8 + j;
-      if (co < op.out_ch) {
-        float4 o = make_float4(apply_act(acc[0][j], op.act), apply_act(acc[1][j], op.act),
-                               apply_act(acc[2][j], op.act), apply_act(acc[3][j], op.act));
-        *reinterpret_cast<float4*>(out + co * out_ld + v * lp_out + p0) = o;
-      }
-    }
-  }
-}
-
 __global__ void __launch_bounds__(NTHREADS, 1)
 hap_cnn_kernel(const __grid_constant__ Plan P, const __grid_constant__ CnnGeom Gm, const float* __restrict__ wflat,
                const float* __restrict__ conv_image, const void* __restrict__ haps, int hap_kind, long long hap_stride,
@@ -206,17 +156,7 @@ hap_cnn_kernel(const __grid_constant__ Plan P, const __grid_constant__ CnnGeom G
       const int in_ld = vt * Gm.lp[i] + 8, out_ld = vt * Gm.lp[i + 1] + 8;
       if (op.kind == PMT_CNN_CONV) {
         const float* img = wimg + Gm.img_off[i];
-        switch (op.ksize) {
-          case 1: conv_units<1>(op, in, in_ld, Gm.lp[i], out, out_ld, Gm.lp[i + 1], img, wflat, vt); break;
-          case 2: conv_units<2>(op, in, in_ld, Gm.lp[i], out, out_ld, Gm.lp[i + 1], img, wflat, vt); break;
-          case 3: conv_units<3>(op, in, in_ld, Gm.lp[i], out, out_ld, Gm.lp[i + 1], img, wflat, vt); break;
-          case 4: conv_units<4>(op, in, in_ld, Gm.lp[i], out, out_ld, Gm.lp[i + 1], img, wflat, vt); break;
-          case 5: conv_units<5>(op, in, in_ld, Gm.lp[i], out, out_ld, Gm.lp[i + 1], img, wflat, vt); break;
-          case 6: conv_units<6>(op, in, in_ld, Gm.lp[i], out, out_ld, Gm.lp[i + 1], img, wflat, vt); break;
-          case 7: conv_units<7>(op, in, in_ld, Gm.lp[i], out, out_ld, Gm.lp[i + 1], img, wflat, vt); break;
-          case 8: conv_units<8>(op, in, in_ld, Gm.lp[i], out, out_ld, Gm.lp[i + 1], img, wflat, vt); break;
-          default: conv_units<9>(op, in, in_ld, Gm.lp[i], out, out_ld, Gm.lp[i + 1], img, wflat, vt); break;
-        }
+        PMT_CONV_DISPATCH(op.ksize, op, in, in_ld, Gm.lp[i], out, out_ld, Gm.lp[i + 1], img, wflat, vt)
       } else {  // max pool, dna_sequence_convolution.py:75-77
         const int total = op.in_ch * vt * op.out_len;
         for (int idx = threadIdx.x; idx < total; idx += NTHREADS) {
@@ -425,7 +365,8 @@ void pmt_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 extern "C" const char* pmt_last_error(void) { return g_err; }
-static thread_local cudaEvent_t g_prof_start = nullptr, g_prof_stop = nullptr;
+// process-wide on purpose: autograd runs pmt_backward on its own host thread
+static cudaEvent_t g_prof_start = nullptr, g_prof_stop = nullptr;
 extern "C" int pmt_set_profile_events(void* start_event, void* stop_event) {
   g_prof_start = reinterpret_cast<cudaEvent_t>(start_event);
   g_prof_stop = reinterpret_cast<cudaEvent_t>(stop_event);
@@ -553,6 +494,14 @@ int pmt_cnn_geometry(const Plan& P, CnnGeom* out) {
     }
   }
   G.img_total = (img + 3) & ~3;
+  int imgT = 0;
+  for (int i = 0; i < n_sp; ++i) {
+    const PmtCnnOp& op = d.cnn_ops[i];
+    if (op.kind != PMT_CNN_CONV) continue;
+    G.imgT_off[i] = imgT;
+    imgT += op.out_ch * op.ksize * ((op.in_ch + 7) / 8) * GROUP_STRIDE;
+  }
+  G.imgT_total = (imgT + 3) & ~3;
   // shared memory budget: 2 activation buffers + conv images + linear scratch
   const int budget_floats = (200 * 1024) / 4 - G.img_total;
   int vt = 32;
@@ -566,7 +515,9 @@ int pmt_cnn_geometry(const Plan& P, CnnGeom* out) {
   return 0;
 }
 
-size_t pmt_image_bytes(const Plan& P, const CnnGeom& G) { return (size_t)(P.img_total + G.img_total + 64) * sizeof(float); }
+size_t pmt_image_bytes(const Plan& P, const CnnGeom& G) {
+  return (size_t)(P.img_total + G.img_total + G.imgT_total + 64) * sizeof(float);
+}
 
 static size_t long_scratch_floats_per_cta(const Plan& P, const PmtBatch* batch);
 
@@ -595,6 +546,7 @@ static size_t long_scratch_floats_per_cta(const Plan& P, const PmtBatch* batch) 
 int pmt_launch_prepare(const Plan& P, const CnnGeom& G, const float* weights, float* image, cudaStream_t st) {
   pack_weights_kernel<<<P.n_gemm, 256, 0, st>>>(P, weights, image);
   if (G.n_spatial > 0) pack_conv_kernel<<<G.n_spatial, 256, 0, st>>>(P, G, weights, image + P.img_total);
+  if (G.n_spatial > 0) pack_convT_kernel<<<G.n_spatial, 256, 0, st>>>(P, G, weights, image + P.img_total);
   return 0;
 }
 
