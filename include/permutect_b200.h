@@ -158,6 +158,18 @@ int pmt_forward(const PmtModelDesc* desc, const float* weights, const PmtBatch* 
 int pmt_backward(const PmtModelDesc* desc, const float* weights, const PmtBatch* batch, const PmtOutGrads* grads,
                  float* d_weights, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Arithmetic mode of the dense layers of the read path (process-wide; default PMT_PRECISION_FP32).
+ *   FP32    FP32 FMA pipe (SIMT); forward and backward.
+ *   TF32X3  tcgen05 tensor cores, TF32 with a hi/lo split of both operands (3 MMAs, ~2^-21 relative error):
+ *           the fp32-parity mode on tensor cores.  Forward (inference) only; backward stays FP32.
+ *   TF32    tcgen05 tensor cores, plain TF32 (10-bit mantissa); logits are NOT within 1e-3 of the reference,
+ *           tolerance stated separately.  Forward only. */
+#define PMT_PRECISION_FP32 0
+#define PMT_PRECISION_TF32X3 1
+#define PMT_PRECISION_TF32 2
+int pmt_set_precision(int mode);
+int pmt_get_precision(void);
+
 /* Measurement hook (no reference counterpart): when both are non-NULL, the next pmt_forward /
  * pmt_backward calls of this process record these cudaEvent_t around their dominant kernel
  * (reads_forward_kernel / reads_backward_kernel) on the call's stream.  Pass NULLs to disarm. */

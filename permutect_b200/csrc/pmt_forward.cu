@@ -529,6 +529,7 @@ extern "C" size_t pmt_workspace_size(const PmtModelDesc* desc, const PmtBatch* b
   bytes += pmt_image_bytes(P, G);
   if (batch) bytes += (size_t)batch->n_variants * (desc->d_info + desc->d_seq) * sizeof(float) + 256;  // info_seq when caller passes none
   bytes += long_scratch_floats_per_cta(P, batch) * sizeof(float) * 148 + 256;
+  bytes += pmt_tc_image_bytes(P) + 1024;
   if (for_backward) bytes += pmt_backward_workspace_bytes(P, batch);
   return bytes;
 }
@@ -611,9 +612,18 @@ extern "C" int pmt_forward(const PmtModelDesc* desc, const float* weights, const
   cudaFuncSetAttribute(reads_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int n_claims = (batch->n_variants + P.claim_variants - 1) / P.claim_variants;
   const int grid = n_claims < n_sm ? n_claims : n_sm;
-  pmt_profile_begin(st);
-  reads_forward_kernel<<<grid, NTHREADS, smem, st>>>(P, A);
-  pmt_profile_end(st);
+  const int mode = pmt_precision_mode();
+  if (mode != PMT_PRECISION_FP32) {
+    PMT_CHECK(pmt_tc_supported(P), "this model shape is outside the tensor-core kernel's envelope; use PMT_PRECISION_FP32");
+    unsigned char* tc_image = reinterpret_cast<unsigned char*>(ws) + workspace_bytes - pmt_tc_image_bytes(P) - 512;
+    PmtOutputs o2 = *out;
+    o2.info_seq_be = info_seq;
+    if (pmt_launch_reads_tc(P, weights, batch, &o2, tc_image, n_sm, mode, st)) return 1;
+  } else {
+    pmt_profile_begin(st);
+    reads_forward_kernel<<<grid, NTHREADS, smem, st>>>(P, A);
+    pmt_profile_end(st);
+  }
   if (batch->max_rows_per_variant > TILE) {
     size_t off = 256 + pmt_image_bytes(P, G) + (size_t)batch->n_variants * (desc->d_info + desc->d_seq) * sizeof(float) + 256;
     off = (off + 255) & ~(size_t)255;

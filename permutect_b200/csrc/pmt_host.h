@@ -25,3 +25,8 @@ void pmt_profile_begin(cudaStream_t st);
 void pmt_profile_end(cudaStream_t st);
 int pmt_launch_cnn_backward(const pmt::Plan& P, const pmt::CnnGeom& G, const float* weights, const float* image,
                             const PmtBatch* batch, const float* d_info_seq, float* partials, int n_partials, cudaStream_t st);
+int pmt_precision_mode();
+bool pmt_tc_supported(const pmt::Plan& P);
+size_t pmt_tc_image_bytes(const pmt::Plan& P);
+int pmt_launch_reads_tc(const pmt::Plan& P, const float* weights, const PmtBatch* batch, const PmtOutputs* out,
+                        unsigned char* tc_image, int n_sm, int mode, cudaStream_t st);

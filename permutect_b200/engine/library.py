@@ -18,6 +18,8 @@ READS_U8, READS_F32, READS_F16 = 0, 1, 2
 F32, F16 = 0, 1
 I16, I64 = 0, 1
 
+PRECISION_MODES = {"fp32": 0, "tf32x3": 1, "tf32": 2}
+
 _i32 = C.c_int32
 
 
@@ -66,7 +68,7 @@ class PmtOutGrads(C.Structure):
 
 
 EXPORTED_SYMBOLS = ["pmt_last_error", "pmt_abi_version", "pmt_workspace_size", "pmt_forward", "pmt_backward",
-                    "pmt_decode_reads", "pmt_set_profile_events", "pmt_downsample_counts", "pmt_downsample_fill"]
+                    "pmt_decode_reads", "pmt_set_profile_events", "pmt_downsample_counts", "pmt_downsample_fill", "pmt_set_precision", "pmt_get_precision"]
 
 _LIB = None
 
@@ -103,6 +105,9 @@ def load():
     lib.pmt_downsample_fill.restype = C.c_int
     lib.pmt_downsample_fill.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_uint64, C.c_int32,
                                         C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.pmt_set_precision.restype = C.c_int
+    lib.pmt_set_precision.argtypes = [C.c_int]
+    lib.pmt_get_precision.restype = C.c_int
     lib.pmt_set_profile_events.restype = C.c_int
     lib.pmt_set_profile_events.argtypes = [C.c_void_p, C.c_void_p]
     if lib.pmt_abi_version() != PMT_ABI_VERSION:
@@ -114,3 +119,15 @@ def load():
 def check(rc: int):
     if rc != 0:
         raise RuntimeError("libpermutect_b200: " + load().pmt_last_error().decode())
+
+
+def set_precision(mode: str) -> None:
+    """Arithmetic of the read path's dense layers: "fp32" (FP32 FMA pipe, forward + backward), "tf32x3" (tcgen05
+    tensor cores with split-precision TF32: the fp32-parity mode on tensor cores, forward only) or "tf32"
+    (plain TF32 on tensor cores; tolerance stated separately, forward only)."""
+    check(load().pmt_set_precision(PRECISION_MODES[mode]))
+
+
+def get_precision() -> str:
+    code = load().pmt_get_precision()
+    return {v: k for k, v in PRECISION_MODES.items()}[code]

@@ -1,0 +1,73 @@
+"""The tcgen05 forward modes against the reference-generated fixtures and the oracle.
+tf32x3 (split-precision TF32 on the tensor cores) must meet the fp32 contract (logits within 1e-3);
+plain tf32 is a separately stated, looser mode."""
+import numpy as np
+import pytest
+import torch
+
+from golden_utils import load
+from helpers import golden_batch, model_from_golden
+from permutect_b200.engine import library as L
+from permutect_b200.utils.enums import Epoch
+
+pytestmark = pytest.mark.gpu
+CASES = ["v040_seed0_b64", "v040_seed0_downsampled", "v040_perturbed_edge", "v040_two_sources"]
+
+
+@pytest.fixture(autouse=True)
+def _restore_precision():
+    yield
+    L.set_precision("fp32")
+
+
+def _forward(case, mode):
+    g = load(case)
+    dev = torch.device("cuda:0")
+    model = model_from_golden(g, dev)
+    model.set_epoch_type(Epoch.VALID)
+    batch = golden_batch(g, dev)
+    L.set_precision(mode)
+    with torch.inference_mode():
+        out = model.compute_batch_output(batch)
+    torch.cuda.synchronize()
+    return g, out
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_tf32x3_meets_the_fp32_contract(case):
+    g, out = _forward(case, "tf32x3")
+    np.testing.assert_allclose(out.logits_b.cpu().numpy(), g.out["logits_b"], rtol=0, atol=1e-3)
+    np.testing.assert_allclose(out.logits_bk.cpu().numpy(), g.out["logits_bk"], rtol=5e-5, atol=2e-3)
+    np.testing.assert_allclose(out.features_be.cpu().numpy(), g.out["features_be"], rtol=1e-4, atol=2e-4)
+    np.testing.assert_allclose(out.ref_features_be.cpu().numpy(), g.out["ref_features_be"], rtol=1e-4, atol=2e-4)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_tf32_mode_stated_tolerance(case):
+    """Plain TF32 (10-bit mantissa) through ~45 layers: logits within 0.25 absolute, same sign away from zero."""
+    g, out = _forward(case, "tf32")
+    got, want = out.logits_b.cpu().numpy(), g.out["logits_b"]
+    np.testing.assert_allclose(got, want, rtol=0, atol=0.25)
+    far = np.abs(want) > 0.5
+    assert np.array_equal(np.sign(got[far]), np.sign(want[far]))
+
+
+def test_tensor_core_modes_on_a_large_ragged_batch():
+    from oracle import artifact_oracle as orc
+    from permutect_b200.data.batch import Batch
+    from permutect_b200.synthetic import make_wgs_arrays
+    g = load("v040_perturbed_edge")
+    dev = torch.device("cuda:0")
+    model = model_from_golden(g, dev)
+    model.set_epoch_type(Epoch.VALID)
+    ia, fa, reads = make_wgs_arrays(3000, seed=5)
+    batch = Batch.from_arrays(ia, fa, reads).copy_to(dev)
+    raw = dict(reads_u8=reads, read_indices=None, ref_counts=ia[:, 0], alt_counts=ia[:, 1], info=fa[:, 6:].astype(np.float32),
+               haplotypes=ia[:, 16:], labels=ia[:, 2], sources=ia[:, 4])
+    with torch.no_grad():
+        want = orc.forward(g.sd, g.hp, raw)
+    L.set_precision("tf32x3")
+    with torch.inference_mode():
+        out = model.compute_batch_output(batch)
+    torch.testing.assert_close(out.logits_b.cpu(), want["logits_b"], rtol=0, atol=1e-3)
+    torch.testing.assert_close(out.features_be.cpu(), want["features_be"], rtol=1e-4, atol=2e-4)
