@@ -238,6 +238,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--train-batch", type=int, default=65536, help="variants per optimiser step")
     ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "tf32"],
+                    help="arithmetic of the inference forward's dense layers (training always runs fp32)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -264,8 +266,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    from permutect_b200.engine import library as pmt_lib
     model = make_model(dev)
     model.set_epoch_type(Epoch.VALID)
+    pmt_lib.set_precision(args.precision)
     ia, fa, reads = make_wgs_arrays(args.variants, seed=1000 * 3 + rank)
     n_reads = len(reads)
     n_alt = int(ia[:, 1].sum())
@@ -321,6 +325,7 @@ def main():
 
     # ---- training: downsample -> forward -> losses -> backward -> (all-reduce) -> clip -> AdamW ----------------
     train = None
+    pmt_lib.set_precision("fp32")
     if not args.no_train:
         train = run_training(args, model, ia, fa, reads, dev, world, barrier)
 
@@ -332,7 +337,9 @@ def main():
     peaks = load_peaks()
     flops = FLOP_PER_READ * n_reads + FLOP_PER_ALT_READ * n_alt        # the read kernel's algorithmic work
     achieved = flops / (read_kernel_ms / 1e3) / 1e12 if read_kernel_ms else None
-    roofline = {"bound": "tensor", "kernel": "reads_forward_kernel (FP32 SIMT mode)", "achieved": achieved,
+    kernel_name = {"fp32": "reads_forward_kernel (FP32 SIMT)", "tf32x3": "reads_forward_tc_kernel<3> (tcgen05, split TF32x3)",
+                   "tf32": "reads_forward_tc_kernel<1> (tcgen05, TF32)"}[args.precision]
+    roofline = {"bound": "tensor", "kernel": kernel_name, "achieved": achieved,
                 "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16"] if achieved else None,
                 "peak_source": peaks["source"] + " bf16 dense (sustained)", "traffic": None,
                 "kernel_ms": read_kernel_ms, "kernel_share_of_step": read_kernel_ms / step_ms if read_kernel_ms else None,
@@ -342,8 +349,10 @@ def main():
     result = {
         "metric": "artifact_model_inference_variants_per_sec", "value": value, "unit": "variants/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms_max, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "tf32x3 (fp32-parity split TF32)", "tf32": "tf32"}[args.precision],
+        "data": "synthetic",
         "config": {"workload": "synthetic WGS-scale inference (SURVEY §8d config 3: 10M variants / 8 GPUs)",
+                   "precision": args.precision,
                    "variants_per_gpu": args.variants, "reads_per_gpu": n_reads, "mean_reads_per_variant": n_reads / args.variants,
                    "hyperparameters": "artifact-model-v0.4.0", "timing": "inputs larger than L2 (compressed shard "
                    f"{h2d / 2**20:.0f} MiB), CUDA events, max over ranks"},
