@@ -238,7 +238,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--train-batch", type=int, default=65536, help="variants per optimiser step")
     ap.add_argument("--no-train", action="store_true")
-    ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "tf32"],
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32x3", "tf32"],
                     help="arithmetic of the inference forward's dense layers (training always runs fp32)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -1,4 +1,4 @@
-"""Small forward-only driver for ncu captures: python profiles/prof_forward.py [n_variants] [iters]"""
+"""Small forward-only driver for ncu captures: python profiles/prof_forward.py [n_variants] [iters] [precision]"""
 import os
 import sys
 
@@ -8,11 +8,13 @@ import torch  # noqa: E402
 
 import bench  # noqa: E402
 from permutect_b200.data.batch import Batch  # noqa: E402
+from permutect_b200.engine import library as L  # noqa: E402
 from permutect_b200.synthetic import make_wgs_arrays  # noqa: E402
 from permutect_b200.utils.enums import Epoch  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 200_000
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+L.set_precision(sys.argv[3] if len(sys.argv) > 3 else "fp32")
 dev = torch.device("cuda:0")
 model = bench.make_model(dev)
 model.set_epoch_type(Epoch.VALID)
