@@ -529,7 +529,7 @@ extern "C" size_t pmt_workspace_size(const PmtModelDesc* desc, const PmtBatch* b
   bytes += pmt_image_bytes(P, G);
   if (batch) bytes += (size_t)batch->n_variants * (desc->d_info + desc->d_seq) * sizeof(float) + 256;  // info_seq when caller passes none
   bytes += long_scratch_floats_per_cta(P, batch) * sizeof(float) * 148 + 256;
-  bytes += pmt_tc_image_bytes(P) + 1024;
+  bytes += pmt_tc_workspace_bytes(P, batch) + 1024;
   if (for_backward) bytes += pmt_backward_workspace_bytes(P, batch);
   return bytes;
 }
@@ -615,7 +615,7 @@ extern "C" int pmt_forward(const PmtModelDesc* desc, const float* weights, const
   const int mode = pmt_precision_mode();
   if (mode != PMT_PRECISION_FP32) {
     PMT_CHECK(pmt_tc_supported(P), "this model shape is outside the tensor-core kernel's envelope; use PMT_PRECISION_FP32");
-    unsigned char* tc_image = reinterpret_cast<unsigned char*>(ws) + workspace_bytes - pmt_tc_image_bytes(P) - 512;
+    unsigned char* tc_image = reinterpret_cast<unsigned char*>(ws) + workspace_bytes - pmt_tc_workspace_bytes(P, batch) - 512;
     PmtOutputs o2 = *out;
     o2.info_seq_be = info_seq;
     if (pmt_launch_reads_tc(P, weights, batch, &o2, tc_image, n_sm, mode, st)) return 1;

@@ -28,5 +28,6 @@ int pmt_launch_cnn_backward(const pmt::Plan& P, const pmt::CnnGeom& G, const flo
 int pmt_precision_mode();
 bool pmt_tc_supported(const pmt::Plan& P);
 size_t pmt_tc_image_bytes(const pmt::Plan& P);
+size_t pmt_tc_workspace_bytes(const pmt::Plan& P, const PmtBatch* batch);
 int pmt_launch_reads_tc(const pmt::Plan& P, const float* weights, const PmtBatch* batch, const PmtOutputs* out,
                         unsigned char* tc_image, int n_sm, int mode, cudaStream_t st);

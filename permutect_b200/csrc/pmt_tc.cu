@@ -1,19 +1,28 @@
 // Tensor-core (tcgen05 / TMEM) forward of the read path for sm_100a.
 //
-// One CTA = one tile of 128 reads = the 128 lanes of TMEM.  Warps 0-3 are EPILOGUE warps: thread r owns
-// read r of the tile for the whole network -- it keeps the read's residual stream in registers, writes the
-// row of the next A operand (K-major, 128B-swizzled) to shared memory, and after the MMA reads its own
-// accumulator row back with tcgen05.ld, so bias / SELU / residual / LayerNorm / gating / clustering head are
-// all register-resident row-local work.  Warp 4 is the CONTROL warp: one lane streams each layer's
-// pre-swizzled weight image with cp.async.bulk (mbarrier complete_tx) and issues the tcgen05.mma chain
-// (M = 128, N = padded layer width, kind::tf32), committing to an mbarrier the epilogue waits on.
-// The only cross-read coupling -- the per-variant mean fields of the gated blocks and the final set sums --
-// goes through a small shared exchange buffer between the four epilogue warps.
+// One persistent CTA per SM keeps TWO tiles of 128 reads in flight (ping-pong): while the tensor core runs a
+// layer of tile A, the epilogue warps of tile B turn the previous accumulator into the next operand.
 //
-// Precision modes (pmt_set_precision): TF32 (one MMA per k-step) and TF32x3 (hi/lo split of both operands,
-// three MMAs: Ahi.Bhi + Alo.Bhi + Ahi.Blo, ~2^-21 relative error, the fp32-parity mode on tensor cores).
-// Layers with separate ref / alt weights (proj1 / proj2 of the gated block) are computed for both weight
-// sets side by side in N; each row keeps the half that matches its read type.
+//   warps 0-3   epilogue of slot 0: thread r owns read (row) r of the tile -- TMEM lane r
+//   warps 4-7   epilogue of slot 1
+//   warp  8     MMA issuer: warp-uniform loop, one elected lane issues the tcgen05.mma chains (kind::tf32,
+//               M = 128, A operand in TMEM, B = weights in shared memory) and commits to mbarriers
+//   warp  9     weight loader: streams every layer's pre-swizzled weight image through a ring of shared-memory
+//               stages with cp.async.bulk (mbarrier complete_tx); both slots consume a stage before it is refilled
+//
+// Tensor memory per slot (256 columns): X = residual stream (64), Z = layer output (64), A_hi / A_lo = next
+// operand (64 + 64).  Residual additions never touch registers: the last layer of a DenseSkipBlock and proj2 of a
+// gated block ACCUMULATE into X (alpha folded into the weights).  Biases ride in a constant-1 operand column;
+// LayerNorm affine, SELU scale and the final rotation are folded into the weight images by pack_tc_kernel.
+// Layers with separate ref / alt weights: proj1 computes both sets side by side in N and each row keeps its half;
+// proj2 stacks both sets along K and each row feeds only its own half of the operand.
+// The only cross-read coupling -- the per-variant mean fields of the gated blocks and the final set sums -- goes
+// through a small shared exchange buffer between the four epilogue warps of a slot.
+//
+// Precision modes (pmt_set_precision): TF32 (one MMA per k-step; the tensor core truncates fp32 inputs to TF32)
+// and TF32x3 (hi/lo split of both operands, Ahi.Bhi + Alo.Bhi + Ahi.Blo, ~2^-20 relative error: the fp32-parity
+// mode).  Tiles are planned by plan_tiles_kernel (greedy packing of whole variants, one warp per claim) so that
+// every role of every CTA knows its tile list up front.
 #include <cstring>
 
 #include "pmt_host.h"
@@ -22,30 +31,45 @@
 namespace pmt {
 namespace tc {
 
-constexpr int EPI_THREADS = 128;
-constexpr int THREADS = 160;
-constexpr int A_KB_BYTES = 128 * 128;   // one 32-element K block of the A operand: 128 rows x 128 B
-constexpr int TMEM_COLS = 128;
-constexpr int MAX_TC_OPS = 64;
+constexpr int THREADS = 320;
+constexpr int MAX_STEPS = 64;
+constexpr int COL_X = 0, COL_Z = 64, COL_AHI = 128, COL_ALO = 192, SLOT_COLS = 256;
+constexpr int MAXH = 11;    // d_ffn / 2: the proj2 operand [t_ref | t_alt | is_ref, is_alt] must fit 24 columns
+constexpr int NP1 = 24;     // padded width of one proj1 weight set (>= 2 * MAXH)
+constexpr int MAXE = 16;    // final feature dimension
+constexpr int MAXK = 6;     // artifact clusters
+constexpr int XCH_ROWS = MAXE + MAXK + 2;
+constexpr int NS_MAX = 8;
+constexpr int PLAN_CLAIM = 512;   // variants per planner claim
 
-struct TcOp {
-  int K, N;          // padded: K multiple of 8, N multiple of 16 (dual ops: N = 2 * Np)
-  int Np;            // padded width of one weight set
-  int n_out;         // real output width of one weight set
-  int dual;
-  int img_off;       // byte offset of the hi image in the TC image buffer (1024-aligned); lo image follows
-  int img_bytes;     // bytes of ONE image (hi); the staged size is img_bytes * (passes == 3 ? 2 : 1)
-  int b_off, b_alt_off;
-  int k_real;        // un-padded reduction length (row length of the weight matrix)
-  int w_off, w_alt_off;
-  int a_exact;       // the A operand is exactly representable in TF32 (decoded reads): skip the Alo.Bhi MMA
+enum EpiKind { EPI_DECODE = 0, EPI_FIRST32, EPI_ACT_Z32, EPI_ACT_X32, EPI_LN_FIRST, EPI_LN, EPI_GATE, EPI_ACT_X64,
+               EPI_ACT_Z64, EPI_COPY_X64 };
+enum PackKind { PK_LINEAR = 0, PK_PROJ1, PK_PROJ2, PK_FINAL };
+
+struct TcStep {
+  int epi;          // epilogue kind that PRODUCES this step's A operand
+  int N, KS;        // MMA shape: N columns (multiple of 8), KS k-steps of 8
+  int dst_x;        // 1: accumulate into X, 0: overwrite Z
+  int img_off;      // byte offset of the hi image (1024-aligned); the lo image follows at + img_bytes
+  int img_bytes;    // bytes of ONE image
+  int blk;          // gated block of EPI_LN* / EPI_GATE
+  // packing
+  int pk, k_real, n_real, w_off, b_off, alpha_off, k_perm, n_perm, k_selu_scale, bias_col;
 };
 
 struct TcPlan {
-  int n_ops, read0, blk0, red0;
-  int image_bytes;   // total bytes of the TC image buffer
-  int stage_bytes;   // largest staged op image (both parts)
-  TcOp op[MAX_TC_OPS];
+  int n_steps;
+  int image_bytes;   // total bytes of the image buffer
+  int slot_bytes;    // bytes of one ring stage for the x3 mode (largest hi + lo image)
+  TcStep step[MAX_STEPS];
+};
+
+struct TcArgs {
+  const float* wflat;
+  const unsigned char* image;
+  const int* tiles;       // [0] = number of tiles, then (v0, nv) pairs from entry 2
+  PmtBatch batch;
+  PmtOutputs out;
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -59,574 +83,677 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
-  unsigned done = 0;
-  while (!done) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  }
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(bar), "r"(parity)
+      : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
-__device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
-
+__device__ __forceinline__ void slot_barrier(int slot) { asm volatile("bar.sync %0, 128;" ::"r"(slot + 1) : "memory"); }
+__device__ __forceinline__ bool elect_one() {
+  unsigned pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ uint64_t smem_desc(unsigned addr) {
   // K-major, SWIZZLE_128B: 8-row groups 1024 B apart, descriptor version 1 (sm_100)
   return (uint64_t)((addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
-__device__ __forceinline__ void mma_tf32(unsigned tmem_d, uint64_t adesc, uint64_t bdesc, unsigned idesc, unsigned accumulate) {
+__device__ __forceinline__ void mma_ts(unsigned tmem_d, unsigned tmem_a, uint64_t bdesc, unsigned idesc, unsigned accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void mma_commit(unsigned bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(unsigned taddr, float* v) {
-  unsigned r[16];
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+#define PMT_R8(r, o) "=r"(r[o]), "=r"(r[o + 1]), "=r"(r[o + 2]), "=r"(r[o + 3]), "=r"(r[o + 4]), "=r"(r[o + 5]), "=r"(r[o + 6]), "=r"(r[o + 7])
+#define PMT_W8(r, o) "r"(r[o]), "r"(r[o + 1]), "r"(r[o + 2]), "r"(r[o + 3]), "r"(r[o + 4]), "r"(r[o + 5]), "r"(r[o + 6]), "r"(r[o + 7])
+
+// 32 lanes x 32 bit: thread t of the warp gets columns [col, col + n) of its TMEM lane
+__device__ __forceinline__ void tmem_ld8(unsigned taddr, unsigned* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : PMT_R8(r, 0) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16(unsigned taddr, unsigned* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : PMT_R8(r, 0), PMT_R8(r, 8)
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld32(unsigned taddr, unsigned* r) {
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,"
+      "%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : PMT_R8(r, 0), PMT_R8(r, 8), PMT_R8(r, 16), PMT_R8(r, 24)
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
-__device__ __forceinline__ float tf32_round(float x) {
-  unsigned r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+__device__ __forceinline__ void tmem_st8(unsigned taddr, const unsigned* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};" ::PMT_W8(r, 0), "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(unsigned taddr, const unsigned* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15};" ::PMT_W8(r, 0),
+               PMT_W8(r, 8), "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st32(unsigned taddr, const unsigned* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%32], {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,"
+      "%23,%24,%25,%26,%27,%28,%29,%30,%31};" ::PMT_W8(r, 0),
+      PMT_W8(r, 8), PMT_W8(r, 16), PMT_W8(r, 24), "r"(taddr)
+      : "memory");
 }
 
-// Shared state of one CTA
+// u(x) = x > 0 ? x : alpha (e^x - 1); selu(x) = scale * u(x).  The scale is folded into the consuming weights
+// wherever a SELU output feeds a Linear layer.
+__device__ __forceinline__ float selu_u(float x) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
+  const float neg = fmaf(SELU_ALPHA, e, -SELU_ALPHA);
+  return x > 0.f ? x : neg;
+}
+
+struct SlotMeta {
+  int nv, v0, ref_pad, pad_;
+  unsigned char rowvar[TILE];   // local variant of each row, 255 = padding
+  unsigned char ref_start[TILE], ref_cnt[TILE], alt_start[TILE], alt_cnt[TILE];
+};
+
 struct Shared {
-  unsigned long long bar_a, bar_w, bar_d;   // operand ready (128 arrivals) / weights landed (tx) / MMA done (commit)
+  unsigned long long bar_a[2], bar_d[2], wfull[NS_MAX], wfree[NS_MAX];
   unsigned tmem_base;
-  int req;                                  // op requested by the epilogue (-1 = finished)
-  int warp_cnt[4];
-  int nv, v0, ref_pad, rows;
-  int rowvar[TILE];
-  long long rowidx[TILE];
-  int ref_start[TILE], ref_cnt[TILE], alt_start[TILE], alt_cnt[TILE];
+  int pad_;
+  SlotMeta slot[2];
 };
 
-struct TcArgs {
-  const float* wflat;
-  const unsigned char* image;   // TC weight images (global)
-  PmtBatch batch;
-  PmtOutputs out;
-  int n_claims, claim;
-};
-
-// Writes this row's vector v[0..n) (zero beyond n, up to KP) as the A operand row: hi part to a0, lo part to a1.
-template <int KP, int PASSES>
-__device__ __forceinline__ void write_a_row(const float* v, int n, int kchunks, int row, unsigned a0, unsigned a1) {
+// Stores v[0..NC) as the operand columns [0, NC) of this thread's row: raw fp32 (the tensor core truncates to
+// TF32) into A_hi and, in the split mode, the truncation remainder into A_lo.
+template <int NC, int PASSES>
+__device__ __forceinline__ void store_operand(unsigned t_hi, unsigned t_lo, const float* v, bool lo_pass) {
+  unsigned r[NC];
 #pragma unroll
-  for (int c = 0; c < KP / 4; ++c) {
-    if (c < kchunks) {
-      float4 hi, lo;
-      float e[4];
+  for (int i = 0; i < NC; ++i) r[i] = __float_as_uint(v[i]);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) e[j] = (c * 4 + j < n) ? v[c * 4 + j] : 0.f;
-      if (PASSES == 3) {
-        hi.x = tf32_round(e[0]); hi.y = tf32_round(e[1]); hi.z = tf32_round(e[2]); hi.w = tf32_round(e[3]);
-        lo.x = e[0] - hi.x; lo.y = e[1] - hi.y; lo.z = e[2] - hi.z; lo.w = e[3] - hi.w;
-      } else {
-        hi = make_float4(e[0], e[1], e[2], e[3]);
-      }
-      const unsigned off = (c >> 3) * A_KB_BYTES + row * 128 + ((((unsigned)c & 7u) ^ ((unsigned)row & 7u)) << 4);
-      sts128(a0 + off, hi);
-      if (PASSES == 3) sts128(a1 + off, lo);
+  for (int c = 0; c < NC; c += 32) {
+    if (NC - c >= 32) tmem_st32(t_hi + c, r + c);
+    else if (NC - c >= 16) { tmem_st16(t_hi + c, r + c); if (NC - c == 24) tmem_st8(t_hi + c + 16, r + c + 16); }
+    else tmem_st8(t_hi + c, r + c);
+  }
+  if (PASSES == 3 && lo_pass) {
+#pragma unroll
+    for (int i = 0; i < NC; ++i) r[i] = __float_as_uint(v[i] - __uint_as_float(r[i] & 0xFFFFE000u));
+#pragma unroll
+    for (int c = 0; c < NC; c += 32) {
+      if (NC - c >= 32) tmem_st32(t_lo + c, r + c);
+      else if (NC - c >= 16) { tmem_st16(t_lo + c, r + c); if (NC - c == 24) tmem_st8(t_lo + c + 16, r + c + 16); }
+      else tmem_st8(t_lo + c, r + c);
     }
   }
 }
 
-template <int PASSES>
-struct Epi {   // per-thread state of an epilogue thread
-  Shared* S;
-  unsigned a0, a1, bar_a, bar_d, tmem_row;   // tmem_row: TMEM address of this thread's lane, column 0
-  unsigned phase_d;
-  int row;
-  const float* W;
-
-  // publish the A operand for `op`, let the control warp run the MMA, wait for the accumulator
-  __device__ __forceinline__ void run_mma(int op) {
-    fence_async_proxy();
-    tc_fence_before();
-    if (row == 0) S->req = op;
-    mbar_arrive(bar_a);
-    mbar_wait(bar_d, phase_d);
-    phase_d ^= 1;
-    tc_fence_after();
-  }
-  // out[0..n_out) = acc[col0 .. col0 + n_out) for up to 64 columns
-  __device__ __forceinline__ void load_cols(int col0, int n_pad, float* out) {
+template <int NC>
+__device__ __forceinline__ void load_cols(unsigned taddr, float* v) {
+  unsigned r[NC];
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
-      if (c * 16 < n_pad) tmem_ld16(tmem_row + col0 + c * 16, out + c * 16);
+  for (int c = 0; c < NC; c += 32) {
+    if (NC - c >= 32) tmem_ld32(taddr + c, r + c);
+    else if (NC - c >= 16) { tmem_ld16(taddr + c, r + c); if (NC - c == 24) tmem_ld8(taddr + c + 16, r + c + 16); }
+    else tmem_ld8(taddr + c, r + c);
   }
-};
-
-template <int PASSES>
-__device__ __forceinline__ void control_loop(const TcPlan& TP, Shared* S, const unsigned char* image, unsigned wbuf,
-                                             unsigned a0, unsigned a1) {
-  const unsigned bar_a = smem_addr(&S->bar_a), bar_w = smem_addr(&S->bar_w), bar_d = smem_addr(&S->bar_d);
-  unsigned phase_a = 0, phase_w = 0, phase_d = 0;
-  int inflight = 0;
-  {
-    const TcOp& o = TP.op[0];
-    const unsigned bytes = o.img_bytes * (PASSES == 3 ? 2 : 1);
-    mbar_expect_tx(bar_w, bytes);
-    bulk_g2s(wbuf, image + o.img_off, bytes, bar_w);
-  }
-  const unsigned tmem_d = S->tmem_base;
-  for (;;) {
-    mbar_wait(bar_a, phase_a);
-    phase_a ^= 1;
-    const int op = S->req;
-    if (op < 0) break;
-    if (inflight != op) {   // not the predicted op: drain the wrong prefetch, fetch the right one
-      mbar_wait(bar_w, phase_w);
-      phase_w ^= 1;
-      const TcOp& o = TP.op[op];
-      const unsigned bytes = o.img_bytes * (PASSES == 3 ? 2 : 1);
-      mbar_expect_tx(bar_w, bytes);
-      bulk_g2s(wbuf, image + o.img_off, bytes, bar_w);
-      inflight = op;
-    }
-    mbar_wait(bar_w, phase_w);
-    phase_w ^= 1;
-    tc_fence_after();
-    const TcOp& o = TP.op[op];
-    const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(o.N >> 3) << 17) | ((128u >> 4) << 24);
-    const int n_ks = o.K >> 3;
-    const unsigned b_kb_bytes = o.N * 128;
-    for (int ks = 0; ks < n_ks; ++ks) {
-      const unsigned aoff = (ks >> 2) * A_KB_BYTES + (ks & 3) * 32;
-      const unsigned boff = (ks >> 2) * b_kb_bytes + (ks & 3) * 32;
-      mma_tf32(tmem_d, smem_desc(a0 + aoff), smem_desc(wbuf + boff), idesc, ks > 0 ? 1u : 0u);
-      if (PASSES == 3) {
-        if (!o.a_exact) mma_tf32(tmem_d, smem_desc(a1 + aoff), smem_desc(wbuf + boff), idesc, 1u);
-        mma_tf32(tmem_d, smem_desc(a0 + aoff), smem_desc(wbuf + o.img_bytes + boff), idesc, 1u);
-      }
-    }
-    mma_commit(bar_d);
-    mbar_wait(bar_d, phase_d);   // the weight slot is free once the MMAs have completed
-    phase_d ^= 1;
-    const int next = (op + 1 == TP.n_ops) ? 0 : op + 1;
-    const TcOp& no = TP.op[next];
-    const unsigned nbytes = no.img_bytes * (PASSES == 3 ? 2 : 1);
-    mbar_expect_tx(bar_w, nbytes);
-    bulk_g2s(wbuf, image + no.img_off, nbytes, bar_w);
-    inflight = next;
-  }
-  mbar_wait(bar_w, phase_w);   // never leave with a bulk copy in flight
+  tmem_wait_ld();
+#pragma unroll
+  for (int i = 0; i < NC; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// Greedy tile construction by the 128 epilogue threads (same packing as build_tile in pmt_tile.cuh).
-__device__ __forceinline__ int build_tile_128(const PmtBatch& batch, int v_cur, int v_end, long long total_ref, Shared* S) {
-  const int tid = threadIdx.x;
-  const long long r_base = __ldg(batch.ref_off + v_cur), a_base = __ldg(batch.alt_off + v_cur);
-  int fits = 0;
-  if (v_cur + tid + 1 <= v_end) {
-    const long long nr = __ldg(batch.ref_off + v_cur + tid + 1) - r_base;
-    const long long na = __ldg(batch.alt_off + v_cur + tid + 1) - a_base;
-    fits = (((nr + 3) & ~3LL) + na <= TILE) ? 1 : 0;
+// One layer's MMA chain, fully unrolled over k-steps so that every descriptor is a constant offset (the chain then
+// runs at the tensor-core floor of N/2 cycles per instruction, profiles/r1/tc_probe_b200.log).
+template <int KS, int PASSES>
+__device__ __forceinline__ void issue_chain(unsigned d, unsigned a_hi, unsigned a_lo, uint64_t b_hi, uint64_t b_lo, unsigned kb_stride16,
+                                            unsigned idesc, unsigned first_acc, bool lo_pass) {
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+    const uint64_t off = (uint64_t)((ks >> 2) * kb_stride16 + (ks & 3) * 2);
+    mma_ts(d, a_hi + ks * 8, b_hi + off, idesc, ks > 0 ? 1u : first_acc);
+    if (PASSES == 3) {
+      if (lo_pass) mma_ts(d, a_lo + ks * 8, b_hi + off, idesc, 1u);
+      mma_ts(d, a_hi + ks * 8, b_lo + off, idesc, 1u);
+    }
   }
-  const unsigned ballot = __ballot_sync(0xffffffffu, fits);
-  epi_barrier();   // previous tile's readers of S are done
-  if ((tid & 31) == 0) S->warp_cnt[tid >> 5] = __popc(ballot);
-  S->rowvar[tid] = -1;
-  S->rowidx[tid] = -1;
-  epi_barrier();
-  const int nv = S->warp_cnt[0] + S->warp_cnt[1] + S->warp_cnt[2] + S->warp_cnt[3];
-  if (nv == 0) return 0;
-  const long long nr_tot = __ldg(batch.ref_off + v_cur + nv) - r_base;
-  const long long na_tot = __ldg(batch.alt_off + v_cur + nv) - a_base;
-  const int ref_pad = (int)((nr_tot + 3) & ~3LL);
-  if (tid < nv) {
-    const long long r0 = __ldg(batch.ref_off + v_cur + tid), r1 = __ldg(batch.ref_off + v_cur + tid + 1);
-    const long long a0 = __ldg(batch.alt_off + v_cur + tid), a1 = __ldg(batch.alt_off + v_cur + tid + 1);
-    const int rs = (int)(r0 - r_base), rc = (int)(r1 - r0), as = ref_pad + (int)(a0 - a_base), ac = (int)(a1 - a0);
-    S->ref_start[tid] = rs; S->ref_cnt[tid] = rc; S->alt_start[tid] = as; S->alt_cnt[tid] = ac;
-    for (int i = 0; i < rc; ++i) { S->rowvar[rs + i] = tid; S->rowidx[rs + i] = r0 + i; }
-    for (int i = 0; i < ac; ++i) { S->rowvar[as + i] = tid; S->rowidx[as + i] = total_ref + a0 + i; }
-  }
-  if (tid == 0) { S->nv = nv; S->v0 = v_cur; S->ref_pad = ref_pad; S->rows = ref_pad + (int)na_tot; }
-  epi_barrier();
-  return nv;
 }
-
-// Supported shape envelope of this kernel (register-resident rows): checked on the host.
-constexpr int MAXW = 64;    // widest layer / d_model
-constexpr int MAXH = 16;    // d_ffn / 2
-constexpr int MAXE = 16;    // final feature dimension
-constexpr int MAXK = 6;     // artifact clusters
 
 template <int PASSES>
 __global__ void __launch_bounds__(THREADS, 1)
-reads_forward_tc_kernel(const __grid_constant__ Plan P, const __grid_constant__ TcPlan TP, const __grid_constant__ TcArgs A) {
+reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_constant__ TcPlan TP, const __grid_constant__ TcArgs A,
+                        int n_stages, int stage_bytes) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  const PmtModelDesc& D = P.d;
-  // carve: [A hi 32 KB][A lo 32 KB (3-pass)][weights stage][exchange floats][sums][Shared]
+  // carve: [weight ring: n_stages x stage_bytes][xch 2 slots][sums 2 slots][HeadConst][Shared]
   unsigned char* p = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const unsigned a0 = smem_addr(p); p += 2 * A_KB_BYTES;
-  unsigned a1 = a0;
-  if (PASSES == 3) { a1 = smem_addr(p); p += 2 * A_KB_BYTES; }
-  const unsigned wbuf = smem_addr(p); p += (PASSES == 3 ? TP.stage_bytes : TP.stage_bytes / 2);
-  float* xch = reinterpret_cast<float*>(p); p += 32 * TILE * sizeof(float);    // [32][TILE] per-row values to be summed
-  float* sums = reinterpret_cast<float*>(p); p += TILE * 2 * MAXH * sizeof(float);  // [nv][2][MAXH] mean fields
+  const unsigned ring = smem_addr(p); p += (size_t)n_stages * stage_bytes;
+  float* xch_all = reinterpret_cast<float*>(p); p += 2 * XCH_ROWS * TILE * sizeof(float);
+  float* sums_all = reinterpret_cast<float*>(p); p += 2 * TILE * 2 * MAXH * sizeof(float);
   HeadConst* HC = reinterpret_cast<HeadConst*>(p); p += sizeof(HeadConst);
   Shared* S = reinterpret_cast<Shared*>((reinterpret_cast<uintptr_t>(p) + 15) & ~uintptr_t(15));
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const float* W = A.wflat;
   if (tid == 0) {
-    mbar_init(smem_addr(&S->bar_a), EPI_THREADS);
-    mbar_init(smem_addr(&S->bar_w), 1);
-    mbar_init(smem_addr(&S->bar_d), 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(smem_addr(&S->bar_a[s]), 4); mbar_init(smem_addr(&S->bar_d[s]), 1); }
+    for (int i = 0; i < n_stages; ++i) { mbar_init(smem_addr(&S->wfull[i]), 1); mbar_init(smem_addr(&S->wfree[i]), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     head_constants(D, W, HC);
   }
-  if (warp == 4) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&S->tmem_base)),
-                 "r"(TMEM_COLS));
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&S->tmem_base)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
 
-  if (warp == 4) {
-    if ((tid & 31) == 0) control_loop<PASSES>(TP, S, A.image, wbuf, a0, a1);
-    __syncwarp();
-  } else {
-    // ===================================== epilogue: thread = row =====================================
-    const int row = tid;
-    const int E = D.d_feat, K = D.n_clusters, Dm = D.d_model, H = D.d_ffn / 2, DR = D.d_read, F = D.n_read_features;
-    const int B = A.batch.n_variants;
-    Epi<PASSES> ep;
-    ep.S = S; ep.a0 = a0; ep.a1 = a1; ep.bar_a = smem_addr(&S->bar_a); ep.bar_d = smem_addr(&S->bar_d);
-    ep.tmem_row = S->tmem_base + ((unsigned)(warp * 32) << 16);
-    ep.phase_d = 0; ep.row = row; ep.W = W;
-    const long long total_ref = __ldg(A.batch.ref_off + B);
-    float x[MAXW];   // residual stream of this read
-    float t[MAXW];   // temporary
+  const int n_tiles = __ldg(A.tiles);
+  const int n_slots = 2 * gridDim.x;
+  // every slot of the CTA runs the same number of rounds (idle slots process an empty tile)
+  const int rounds = (n_tiles - 2 * (int)blockIdx.x + n_slots - 1) / n_slots;   // rounds of slot 0 >= rounds of slot 1
+  const int n_steps = TP.n_steps;
+  const unsigned tmem_base = __shfl_sync(0xffffffffu, S->tmem_base, 0);
+  const bool l0_lo = A.batch.reads_kind != PMT_READS_U8;   // decoded reads k/32 and bits are exact in TF32
 
-    for (int c = blockIdx.x; c < A.n_claims; c += gridDim.x) {
-      const long long cv0 = (long long)c * A.claim;
-      const int cv1 = (int)min((long long)B, cv0 + A.claim);
-      int v_cur = (int)cv0;
-      while (v_cur < cv1) {
-        const int nv = build_tile_128(A.batch, v_cur, cv1, total_ref, S);
-        if (nv == 0) { v_cur += 1; continue; }   // longer than a tile: reads_forward_long_kernel
-        v_cur += nv;
-        const int ref_pad = S->ref_pad;
-        const bool is_alt = row >= ref_pad;
-        const int my_var = S->rowvar[row];
-        const long long my_idx = S->rowidx[row];
-
-        // ---- decode (batch.py:51-56): bits and wrapped quantised floats are exact in TF32 ----
-        {
-#pragma unroll
-          for (int i = 0; i < MAXW; ++i) t[i] = 0.f;
-          if (my_idx >= 0) {
-            const long long src = A.batch.read_indices ? __ldg(A.batch.read_indices + my_idx) : my_idx;
-            if (A.batch.reads_kind == PMT_READS_U8) {
-              const int rb = D.read_row_bytes;
-              const unsigned char* rp = reinterpret_cast<const unsigned char*>(A.batch.reads) + src * rb;
-#pragma unroll
-              for (int b = 0; b < 7; ++b) {
-                const unsigned byte = __ldg(rp + b);
-#pragma unroll
-                for (int bit = 0; bit < 8; ++bit) t[b * 8 + bit] = (float)((byte >> (7 - bit)) & 1u);
-              }
-#pragma unroll
-              for (int b = 7; b < 15; ++b)
-                if (b < rb) t[56 + b - 7] = (float)((__ldg(rp + b) + 128u) & 255u) * 0.03125f;
-            } else {
-#pragma unroll
-              for (int f = 0; f < MAXW; ++f)
-                if (f < F)
-                  t[f] = A.batch.reads_kind == PMT_READS_F16
-                             ? __half2float(reinterpret_cast<const __half*>(A.batch.reads)[src * F + f])
-                             : reinterpret_cast<const float*>(A.batch.reads)[src * F + f];
-            }
-          }
-        }
-        // ---- MLP programs (mlp.py): a tiny interpreter over the op list; vectors stay in registers ----
-        auto run_program = [&](const PmtLinearOp* ops, int n_ops, int tc0, float* cur /* in/out */, float* tmp) {
-          // cur holds the program input; on return cur holds the output
-          for (int i = 0; i < n_ops; ++i) {
-            const PmtLinearOp& lop = ops[i];
-            const TcOp& o = TP.op[tc0 + i];
-            if (lop.flags & PMT_OP_SKIP_BEGIN) {
-              // residual block: cur + alpha * g(cur); layers i .. j1
-              int j1 = i;
-              while (!(ops[j1].flags & PMT_OP_SKIP_END)) ++j1;
-#pragma unroll
-              for (int k = 0; k < MAXW; ++k) tmp[k] = selu(cur[k]);
-              for (int j = i; j <= j1; ++j) {
-                const TcOp& oj = TP.op[tc0 + j];
-                write_a_row<MAXW, PASSES>(tmp, ops[j].in_dim, oj.K >> 2, row, a0, a1);
-                ep.run_mma(tc0 + j);
-                ep.load_cols(0, oj.N, tmp);
-                if (j < j1) {
-#pragma unroll
-                  for (int k = 0; k < MAXW; ++k)
-                    tmp[k] = k < ops[j].out_dim ? selu(tmp[k] + __ldg(W + ops[j].b_off + min(k, ops[j].out_dim - 1))) : 0.f;
-                }
-              }
-              const float alpha = __ldg(W + ops[j1].alpha_off);
-#pragma unroll
-              for (int k = 0; k < MAXW; ++k)
-                if (k < ops[j1].out_dim) cur[k] = fmaf(alpha, tmp[k] + __ldg(W + ops[j1].b_off + k), cur[k]);
-              i = j1;
-            } else {
-              write_a_row<MAXW, PASSES>(cur, lop.in_dim, o.K >> 2, row, a0, a1);
-              ep.run_mma(tc0 + i);
-              ep.load_cols(0, o.N, cur);
-#pragma unroll
-              for (int k = 0; k < MAXW; ++k) {
-                if (k < lop.out_dim) {
-                  const float v = cur[k] + __ldg(W + lop.b_off + k);
-                  cur[k] = (lop.flags & PMT_OP_POST_SELU) ? selu(v) : v;
-                } else {
-                  cur[k] = 0.f;
-                }
-              }
-            }
-          }
-        };
-        run_program(D.read_ops, D.n_read_ops, TP.read0, t, x);
-        // ---- concat (artifact_model.py:246-251) ----
-        {
-          const int w = D.d_info + D.d_seq;
-          const float* src = my_var >= 0 ? A.out.info_seq_be + (long long)(S->v0 + my_var) * w : nullptr;
-#pragma unroll
-          for (int k = 0; k < MAXW; ++k) {
-            if (k < DR) x[k] = t[k];
-            else if (k < Dm) x[k] = src ? __ldg(src + (k - DR)) : 0.f;
-            else x[k] = 0.f;
-          }
-        }
-        // ---- gated blocks (gated_mlp.py:177-251) ----
-        for (int blk = 0; blk < D.n_blocks; ++blk) {
-          const PmtBlockOffsets& BO = D.blocks[blk];
-          const int op1 = TP.blk0 + 2 * blk, op2 = op1 + 1;
-          {
-            float mean = 0.f;
-#pragma unroll
-            for (int k = 0; k < MAXW; ++k) if (k < Dm) mean += x[k];
-            mean /= Dm;
-            float var = 0.f;
-#pragma unroll
-            for (int k = 0; k < MAXW; ++k) if (k < Dm) { const float d = x[k] - mean; var = fmaf(d, d, var); }
-            const float rstd = rsqrtf(var / Dm + LN_EPS);
-#pragma unroll
-            for (int k = 0; k < MAXW; ++k) t[k] = k < Dm ? (x[k] - mean) * rstd * __ldg(W + BO.ln_w + k) + __ldg(W + BO.ln_b + k) : 0.f;
-          }
-          write_a_row<MAXW, PASSES>(t, Dm, TP.op[op1].K >> 2, row, a0, a1);
-          ep.run_mma(op1);
-          float z[2 * MAXH];
-          {
-            const TcOp& o = TP.op[op1];
-            float zr[2 * MAXH], za[2 * MAXH];
-            ep.load_cols(0, 2 * MAXH, zr);
-            ep.load_cols(o.Np, 2 * MAXH, za);
-#pragma unroll
-            for (int k = 0; k < 2 * MAXH; ++k) {
-              const float v = (is_alt ? za[k] : zr[k]) + (k < 2 * H ? __ldg(W + (is_alt ? BO.p1_alt_b : BO.p1_ref_b) + k) : 0.f);
-              z[k] = k < 2 * H ? selu(v) : 0.f;
-            }
-          }
-          float z2n[MAXH];
-          {
-            float mean = 0.f;
-#pragma unroll
-            for (int k = 0; k < MAXH; ++k) if (k < H) mean += z[H + k];
-            mean /= H;
-            float var = 0.f;
-#pragma unroll
-            for (int k = 0; k < MAXH; ++k) if (k < H) { const float d = z[H + k] - mean; var = fmaf(d, d, var); }
-            const float rstd = rsqrtf(var / H + LN_EPS);
-#pragma unroll
-            for (int k = 0; k < MAXH; ++k)
-              if (k < H) {
-                z2n[k] = (z[H + k] - mean) * rstd * __ldg(W + BO.ln2_w + k) + __ldg(W + BO.ln2_b + k);
-                xch[k * TILE + row] = z2n[k];
-              }
-          }
-          epi_barrier();
-          {  // per-variant mean fields (gated_mlp.py:236-239)
-            const float regw = __ldg(W + BO.reg_weight) + 0.25f;
-            for (int idx = tid; idx < S->nv * 2 * H; idx += EPI_THREADS) {
-              const int j = idx / (2 * H), s = (idx / H) & 1, f = idx % H;
-              const int start = s ? S->alt_start[j] : S->ref_start[j], cnt = s ? S->alt_cnt[j] : S->ref_cnt[j];
-              float sum = 0.f;
-              for (int i = 0; i < cnt; ++i) sum += xch[f * TILE + start + i];
-              sums[(j * 2 + s) * MAXH + f] = s == 0 ? (sum + regw * __ldg(W + BO.regularizer + f)) / ((float)cnt + regw)
-                                                  : sum / ((float)cnt + 1e-4f);
-            }
-          }
-          epi_barrier();
-          {
-            const float alpha = __ldg(W + (is_alt ? BO.alpha_alt : BO.alpha_ref));
-            const float beta = __ldg(W + (is_alt ? BO.beta_alt : BO.beta_ref));
-            const float gamma = __ldg(W + BO.gamma);
-#pragma unroll
-            for (int k = 0; k < MAXH; ++k) {
-              float gate = 0.f;
-              if (k < H) {
-                gate = z2n[k] * alpha + 1.f;
-                if (my_var >= 0) {
-                  const float m_ref = sums[(my_var * 2 + 0) * MAXH + k];
-                  gate = is_alt ? gate + beta * sums[(my_var * 2 + 1) * MAXH + k] + gamma * m_ref : gate + beta * m_ref;
-                }
-              }
-              t[k] = k < H ? z[k] * gate : 0.f;
-            }
-          }
-          write_a_row<MAXH, PASSES>(t, H, TP.op[op2].K >> 2, row, a0, a1);
-          ep.run_mma(op2);
-          {
-            const TcOp& o = TP.op[op2];
-            const int boff = is_alt ? BO.p2_alt_b : BO.p2_ref_b;
-#pragma unroll
-            for (int c = 0; c < MAXW / 16; ++c) {
-              if (c * 16 < Dm) {
-                float yr[16], ya[16];
-                tmem_ld16(ep.tmem_row + c * 16, yr);
-                tmem_ld16(ep.tmem_row + o.Np + c * 16, ya);
-#pragma unroll
-                for (int k = 0; k < 16; ++k)
-                  if (c * 16 + k < Dm) x[c * 16 + k] += (is_alt ? ya[k] : yr[k]) + __ldg(W + boff + c * 16 + k);
-              }
-            }
-          }
-        }
-        // ---- reducer (artifact_model.py:258-259) ----
-        run_program(D.red_ops, D.n_red_ops, TP.red0, x, t);
-        // ---- rotation + clustering head in registers (euclidean_transformation.py:19-20; feature_clustering.py:82-119) ----
-        float f[MAXE];
-#pragma unroll
-        for (int i = 0; i < MAXE; ++i) {
-          float a = 0.f;
-          if (i < E) {
-#pragma unroll
-            for (int j = 0; j < MAXE; ++j)
-              if (j < E) a = fmaf(__ldg(W + D.rotation + i * E + j), x[j] + __ldg(W + D.translation + j), a);
-          }
-          f[i] = a;
-        }
-        epi_barrier();   // mean-field readers of xch / sums are done
-#pragma unroll
-        for (int i = 0; i < MAXE; ++i) if (i < E) xch[i * TILE + row] = f[i];
-        if (is_alt && my_var >= 0) {
-          float q = 0.f, q2 = 0.f;
-#pragma unroll
-          for (int e = 0; e < MAXE; ++e)
-            if (e < E) {
-              const float a = f[e] / HC->sigma[e], b = f[e] / (2.f * HC->sigma[e]);
-              q = fmaf(a, a, q); q2 = fmaf(b, b, q2);
-            }
-          xch[(MAXE + 0) * TILE + row] = HC->c_non - q / 2.f;
-          xch[(MAXE + 1) * TILE + row] = HC->c_out - q2 / 2.f;
-          for (int k = 0; k < K; ++k) {
-            const float* u = W + D.unit_ke + k * E;
-            float pr = 0.f;
-#pragma unroll
-            for (int e = 0; e < MAXE; ++e) if (e < E) pr = fmaf(f[e], __ldg(u + e), pr);
-            float o2 = 0.f;
-#pragma unroll
-            for (int e = 0; e < MAXE; ++e) if (e < E) { const float d = f[e] - pr * __ldg(u + e); o2 = fmaf(d, d, o2); }
-            const float dist = sqrtf(o2);
-            const float ll_orth = HC->c_orth[k] - (dist * dist) / HC->two_tau2[k];
-            const float ll_par = HC->log_half_lambda[k] + logerfc((HC->shift[k] - pr) / HC->sqrt2_sigma[k]) +
-                                 HC->half_lambda[k] * (HC->two_mu_plus[k] - 2.f * pr);
-            xch[(MAXE + 2 + k) * TILE + row] = ll_orth + ll_par;
-          }
-        }
-        if (A.out.final_re && my_idx >= 0) {
-#pragma unroll
-          for (int e = 0; e < MAXE; ++e) if (e < E) A.out.final_re[my_idx * E + e] = f[e];
-        }
-        epi_barrier();
-        // ---- per-variant sums and outputs ----
-        for (int idx = tid; idx < S->nv * 2 * E; idx += EPI_THREADS) {
-          const int j = idx / (2 * E), s = (idx / E) & 1, e = idx % E;
-          const int start = s ? S->alt_start[j] : S->ref_start[j], cnt = s ? S->alt_cnt[j] : S->ref_cnt[j];
-          float sum = 0.f;
-          for (int i = 0; i < cnt; ++i) sum += xch[e * TILE + start + i];
-          const long long v = S->v0 + j;
-          float* dst = s ? A.out.alt_means_be : A.out.ref_means_be;
-          if (dst) dst[v * E + e] = sum / ((float)cnt + 1e-4f);
-        }
-        if (tid < S->nv) {
-          const int j = tid;
-          const long long v = S->v0 + j;
-          float ll[MAXK + 2];
-#pragma unroll
-          for (int k = 0; k < MAXK + 2; ++k) {
-            float sum = 0.f;
-            if (k < K + 2)
-              for (int i = 0; i < S->alt_cnt[j]; ++i) sum += xch[(MAXE + k) * TILE + S->alt_start[j] + i];
-            ll[k] = sum;
-          }
-          float art_max = -INFINITY;
-#pragma unroll
-          for (int k = 0; k < MAXK; ++k) if (k < K) { ll[2 + k] += HC->logw[k]; art_max = fmaxf(art_max, ll[2 + k]); }
-          float s = 0.f;
-#pragma unroll
-          for (int k = 0; k < MAXK; ++k) if (k < K) s += expf(ll[2 + k] - art_max);
-          const float art = art_max + logf(s);
-          if (A.out.logits_bk) {
-#pragma unroll
-            for (int k = 0; k < MAXK + 2; ++k) if (k < K + 2) A.out.logits_bk[v * (K + 2) + k] = ll[k];
-          }
-          if (A.out.logits_b) A.out.logits_b[v] = 20.f * tanhf((art - ll[0]) / 20.f);
-          if (A.out.outlier_logits_b) A.out.outlier_logits_b[v] = ll[1] - logsumexp2(ll[0], art);
-        }
+  if (warp == 9) {
+    // ===================================== weight loader =====================================
+    if (elect_one()) {
+      const long long total = (long long)rounds * n_steps;
+      int stage = 0, step = 0;
+      unsigned parity = 1;   // first pass through the ring: stages are free
+      for (long long g = 0; g < total; ++g) {
+        mbar_wait(smem_addr(&S->wfree[stage]), parity);
+        const TcStep& o = TP.step[step];
+        const unsigned bytes = o.img_bytes * (PASSES == 3 ? 2 : 1);
+        mbar_expect_tx(smem_addr(&S->wfull[stage]), bytes);
+        bulk_g2s(ring + stage * stage_bytes, A.image + o.img_off, bytes, smem_addr(&S->wfull[stage]));
+        if (++stage == n_stages) { stage = 0; parity ^= 1; }
+        if (++step == n_steps) step = 0;
       }
     }
-    // tell the control warp we are done
-    tc_fence_before();
-    if (row == 0) S->req = -1;
-    mbar_arrive(ep.bar_a);
+    __syncwarp();
+  } else if (warp == 8) {
+    // ===================================== MMA issuer =====================================
+    int stage = 0;
+    unsigned wparity = 0, aparity = 0;
+    for (int round = 0; round < rounds; ++round) {
+      for (int step = 0; step < n_steps; ++step) {
+        const TcStep& o = TP.step[step];
+        mbar_wait(smem_addr(&S->wfull[stage]), wparity);
+        const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(o.N >> 3) << 17) | ((128u >> 4) << 24);
+        const unsigned wb = ring + stage * stage_bytes;
+        const uint64_t b_hi = smem_desc(wb), b_lo = smem_desc(wb + o.img_bytes);
+        const unsigned kb_stride16 = (unsigned)(o.N * 128) >> 4;
+        const bool lo_pass = step > 0 || l0_lo;
+#pragma unroll 1
+        for (int s = 0; s < 2; ++s) {
+          mbar_wait(smem_addr(&S->bar_a[s]), aparity);
+          tc_fence_after();
+          const unsigned tb = tmem_base + s * SLOT_COLS;
+          const unsigned d = tb + (o.dst_x ? COL_X : COL_Z);
+          if (elect_one()) {
+            switch (o.KS) {
+              case 3: issue_chain<3, PASSES>(d, tb + COL_AHI, tb + COL_ALO, b_hi, b_lo, kb_stride16, idesc, o.dst_x, lo_pass); break;
+              case 4: issue_chain<4, PASSES>(d, tb + COL_AHI, tb + COL_ALO, b_hi, b_lo, kb_stride16, idesc, o.dst_x, lo_pass); break;
+              default: issue_chain<8, PASSES>(d, tb + COL_AHI, tb + COL_ALO, b_hi, b_lo, kb_stride16, idesc, o.dst_x, lo_pass); break;
+            }
+            mma_commit(smem_addr(&S->bar_d[s]));
+            if (s == 1) mma_commit(smem_addr(&S->wfree[stage]));
+          }
+          __syncwarp();
+        }
+        aparity ^= 1;
+        if (++stage == n_stages) { stage = 0; wparity ^= 1; }
+      }
+    }
+  } else {
+    // ===================================== epilogue: thread = row =====================================
+    const int slot = warp >> 2;
+    const int row = tid & 127;
+    const int lane = tid & 31;
+    SlotMeta* M = &S->slot[slot];
+    float* xch = xch_all + slot * XCH_ROWS * TILE;
+    float* sums = sums_all + slot * TILE * 2 * MAXH;
+    const unsigned bar_a = smem_addr(&S->bar_a[slot]), bar_d = smem_addr(&S->bar_d[slot]);
+    const unsigned trow = tmem_base + slot * SLOT_COLS + ((unsigned)((warp & 3) * 32) << 16);
+    const unsigned t_x = trow + COL_X, t_z = trow + COL_Z, t_hi = trow + COL_AHI, t_lo = trow + COL_ALO;
+    const int E = D.d_feat, K = D.n_clusters, Dm = D.d_model, H = D.d_ffn / 2, DR = D.d_read, F = D.n_read_features;
+    const int DIS = D.d_info + D.d_seq;
+    const int B = A.batch.n_variants;
+    const long long total_ref = __ldg(A.batch.ref_off + B);
+    unsigned dparity = 0;
+
+    for (int round = 0; round < rounds; ++round) {
+      const int t = 2 * (int)blockIdx.x + slot + round * n_slots;
+      // ---------------- tile meta ----------------
+      int v0 = 0, nv = 0;
+      if (t < n_tiles) { v0 = __ldg(A.tiles + 2 + 2 * t); nv = __ldg(A.tiles + 3 + 2 * t); }
+      long long r_base = 0, a_base = 0;
+      int ref_pad = 0;
+      M->rowvar[row] = 255;
+      slot_barrier(slot);   // previous tile's readers of the tables are done; rowvar cleared
+      if (nv > 0) {
+        r_base = __ldg(A.batch.ref_off + v0);
+        a_base = __ldg(A.batch.alt_off + v0);
+        const long long nr_tot = __ldg(A.batch.ref_off + v0 + nv) - r_base;
+        ref_pad = (int)((nr_tot + 3) & ~3LL);
+        if (row < nv) {
+          const long long r0 = __ldg(A.batch.ref_off + v0 + row), r1 = __ldg(A.batch.ref_off + v0 + row + 1);
+          const long long a0 = __ldg(A.batch.alt_off + v0 + row), a1 = __ldg(A.batch.alt_off + v0 + row + 1);
+          const int rs = (int)(r0 - r_base), rc = (int)(r1 - r0), as = ref_pad + (int)(a0 - a_base), ac = (int)(a1 - a0);
+          M->ref_start[row] = (unsigned char)rs; M->ref_cnt[row] = (unsigned char)rc;
+          M->alt_start[row] = (unsigned char)as; M->alt_cnt[row] = (unsigned char)ac;
+          for (int i = 0; i < rc; ++i) M->rowvar[rs + i] = (unsigned char)row;
+          for (int i = 0; i < ac; ++i) M->rowvar[as + i] = (unsigned char)row;
+        }
+      }
+      slot_barrier(slot);
+      const int my_var = M->rowvar[row] == 255 ? -1 : (int)M->rowvar[row];
+      const bool is_alt = row >= ref_pad;
+      long long my_idx = -1;
+      if (my_var >= 0) my_idx = is_alt ? total_ref + a_base + (row - ref_pad) : r_base + row;
+
+      for (int step = 0; step < n_steps; ++step) {
+        const TcStep& o = TP.step[step];
+        switch (o.epi) {
+          case EPI_DECODE: {   // batch.py:51-56, plain_text_data.py:510-511 (quirk Q2: the uint8 de-quantisation wraps)
+            float v[64];
+#pragma unroll
+            for (int i = 0; i < 64; ++i) v[i] = 0.f;
+            if (my_idx >= 0) {
+              const long long src = A.batch.read_indices ? __ldg(A.batch.read_indices + my_idx) : my_idx;
+              if (A.batch.reads_kind == PMT_READS_U8) {
+                const int rb = D.read_row_bytes;
+                const unsigned char* rp = reinterpret_cast<const unsigned char*>(A.batch.reads) + src * rb;
+                unsigned bytes[16];
+                if (rb == 12) {
+                  const unsigned* wp = reinterpret_cast<const unsigned*>(rp);
+                  const unsigned w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
+#pragma unroll
+                  for (int b = 0; b < 4; ++b) { bytes[b] = (w0 >> (8 * b)) & 255u; bytes[4 + b] = (w1 >> (8 * b)) & 255u; bytes[8 + b] = (w2 >> (8 * b)) & 255u; }
+                  bytes[12] = bytes[13] = bytes[14] = bytes[15] = 128u;
+                } else {
+#pragma unroll
+                  for (int b = 0; b < 15; ++b) bytes[b] = b < rb ? (unsigned)__ldg(rp + b) : 128u;
+                  bytes[15] = 128u;
+                }
+#pragma unroll
+                for (int b = 0; b < 7; ++b)
+#pragma unroll
+                  for (int bit = 0; bit < 8; ++bit) v[b * 8 + bit] = __uint_as_float((0u - ((bytes[b] >> (7 - bit)) & 1u)) & 0x3f800000u);
+#pragma unroll
+                for (int b = 7; b < 14; ++b)
+                  if (b < rb) v[56 + b - 7] = (float)((bytes[b] + 128u) & 255u) * 0.03125f;
+              } else {
+#pragma unroll
+                for (int f = 0; f < 63; ++f)
+                  if (f < F)
+                    v[f] = A.batch.reads_kind == PMT_READS_F16 ? __half2float(reinterpret_cast<const __half*>(A.batch.reads)[src * F + f])
+                                                               : reinterpret_cast<const float*>(A.batch.reads)[src * F + f];
+              }
+            }
+            v[63] = 1.f;
+            store_operand<64, PASSES>(t_hi, t_lo, v, l0_lo);
+          } break;
+          case EPI_FIRST32: {   // mlp.py:61-62 then the first DenseSkipBlock's leading SELU (mlp.py:8-22)
+            float v[32];
+            load_cols<32>(t_z, v);
+            unsigned r[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { v[i] = SELU_SCALE * selu_u(v[i]); r[i] = __float_as_uint(v[i]); }
+            tmem_st32(t_x, r);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = selu_u(v[i]);
+            v[31] = 1.f;
+            store_operand<32, PASSES>(t_hi, t_lo, v, true);
+          } break;
+          case EPI_ACT_Z32:
+          case EPI_ACT_X32: {
+            float v[32];
+            load_cols<32>(o.epi == EPI_ACT_Z32 ? t_z : t_x, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = selu_u(v[i]);
+            v[31] = 1.f;
+            store_operand<32, PASSES>(t_hi, t_lo, v, true);
+          } break;
+          case EPI_LN_FIRST:
+          case EPI_LN: {   // gated_mlp.py:185 (LayerNorm affine folded into proj1); artifact_model.py:246-251 concat
+            float v[64];
+            if (o.epi == EPI_LN_FIRST) {
+              load_cols<32>(t_x, v);
+              const float* src = my_var >= 0 ? A.out.info_seq_be + (long long)(v0 + my_var) * DIS : nullptr;
+              unsigned r[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) { v[32 + i] = (src && i < DIS) ? __ldg(src + i) : 0.f; r[i] = __float_as_uint(v[32 + i]); }
+              tmem_st32(t_x + 32, r);
+            } else {
+              load_cols<64>(t_x, v);
+            }
+            float sum = 0.f;
+#pragma unroll
+            for (int i = 0; i < 64; ++i) sum += v[i];
+            const float mean = sum / (float)Dm;
+            float sq = 0.f;
+#pragma unroll
+            for (int i = 0; i < 64; ++i) { v[i] -= mean; sq = fmaf(v[i], v[i], sq); }
+            const float var = (sq - (float)(64 - Dm) * mean * mean) / (float)Dm;   // padding columns hold -mean
+            const float rstd = rsqrtf(fmaxf(var, 0.f) + LN_EPS);
+#pragma unroll
+            for (int i = 0; i < 64; ++i) v[i] *= rstd;
+            v[31] = 1.f;
+            store_operand<64, PASSES>(t_hi, t_lo, v, true);
+          } break;
+          case EPI_GATE: {   // gated_mlp.py:186-190, 228-251
+            const PmtBlockOffsets& BO = D.blocks[o.blk];
+            float zz[2 * NP1];
+            load_cols<2 * NP1>(t_z, zz);
+            // one weight set = [z1 at columns 0..H) | z2 at columns 12..12+H)]
+            float z1[MAXH], z2[MAXH];
+#pragma unroll
+            for (int k = 0; k < MAXH; ++k) {
+              z1[k] = SELU_SCALE * selu_u(is_alt ? zz[NP1 + k] : zz[k]);
+              z2[k] = SELU_SCALE * selu_u(is_alt ? zz[NP1 + NP1 / 2 + k] : zz[NP1 / 2 + k]);
+            }
+            float z2n[MAXH];
+            {
+              float mean = 0.f;
+#pragma unroll
+              for (int k = 0; k < MAXH; ++k) if (k < H) mean += z2[k];
+              mean /= (float)H;
+              float var = 0.f;
+#pragma unroll
+              for (int k = 0; k < MAXH; ++k) if (k < H) { const float dd = z2[k] - mean; var = fmaf(dd, dd, var); }
+              const float rstd = rsqrtf(var / (float)H + LN_EPS);
+#pragma unroll
+              for (int k = 0; k < MAXH; ++k) {
+                z2n[k] = 0.f;
+                if (k < H) {
+                  z2n[k] = (z2[k] - mean) * rstd * __ldg(W + BO.ln2_w + k) + __ldg(W + BO.ln2_b + k);
+                  xch[k * TILE + row] = z2n[k];
+                }
+              }
+            }
+            slot_barrier(slot);
+            {   // per-variant mean fields (gated_mlp.py:236-239)
+              const float regw = __ldg(W + BO.reg_weight) + 0.25f;
+              const int n_seg = nv * 2 * H;
+              for (int idx = row; idx < n_seg; idx += 128) {
+                const int j = idx / (2 * H), rem = idx - j * 2 * H, s = rem >= H ? 1 : 0, f = rem - s * H;
+                const int start = s ? M->alt_start[j] : M->ref_start[j], cnt = s ? M->alt_cnt[j] : M->ref_cnt[j];
+                float acc = 0.f;
+                for (int i = 0; i < cnt; ++i) acc += xch[f * TILE + start + i];
+                sums[(j * 2 + s) * MAXH + f] = s == 0 ? (acc + regw * __ldg(W + BO.regularizer + f)) / ((float)cnt + regw)
+                                                     : acc / ((float)cnt + 1e-4f);
+              }
+            }
+            slot_barrier(slot);
+            // proj2 operand [t_ref at 0..MAXH) | t_alt at MAXH..2 MAXH) | is_ref, is_alt]: a row feeds only its own weight set
+            float v[24];
+            {
+              const float alpha = __ldg(W + (is_alt ? BO.alpha_alt : BO.alpha_ref));
+              const float beta = __ldg(W + (is_alt ? BO.beta_alt : BO.beta_ref));
+              const float gamma = is_alt ? __ldg(W + BO.gamma) : 0.f;
+              const int mv = my_var >= 0 ? my_var : 0;
+#pragma unroll
+              for (int k = 0; k < MAXH; ++k) {
+                float tk = 0.f;
+                if (k < H) {
+                  float gate = fmaf(z2n[k], alpha, 1.f);
+                  if (my_var >= 0) {
+                    const float m_ref = sums[(mv * 2 + 0) * MAXH + k];
+                    const float m_own = is_alt ? sums[(mv * 2 + 1) * MAXH + k] : m_ref;
+                    gate = fmaf(beta, m_own, fmaf(gamma, m_ref, gate));
+                  }
+                  tk = z1[k] * gate;
+                }
+                v[k] = is_alt ? 0.f : tk;
+                v[MAXH + k] = is_alt ? tk : 0.f;
+              }
+              v[2 * MAXH] = is_alt ? 0.f : 1.f;
+              v[2 * MAXH + 1] = is_alt ? 1.f : 0.f;
+            }
+            store_operand<24, PASSES>(t_hi, t_lo, v, true);
+          } break;
+          case EPI_ACT_X64:
+          case EPI_ACT_Z64:
+          case EPI_COPY_X64: {
+            float v[64];
+            load_cols<64>(o.epi == EPI_ACT_Z64 ? t_z : t_x, v);
+            if (o.epi != EPI_COPY_X64) {
+#pragma unroll
+              for (int i = 0; i < 64; ++i) v[i] = selu_u(v[i]);
+            }
+            v[31] = 1.f;
+            store_operand<64, PASSES>(t_hi, t_lo, v, true);
+          } break;
+        }
+        // ---- hand the operand to the MMA warp, wait for the accumulator ----
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_a);
+        mbar_wait(bar_d, dparity);
+        dparity ^= 1;
+        tc_fence_after();
+      }
+
+      // ---------------- clustering head (rotation folded into the last layer; feature_clustering.py:82-135) ----------------
+      float f[MAXE];
+      load_cols<MAXE>(t_z, f);
+#pragma unroll
+      for (int i = 0; i < MAXE; ++i) if (i < E) xch[i * TILE + row] = f[i];
+      if (is_alt && my_var >= 0) {
+        float q = 0.f, q2 = 0.f;
+#pragma unroll
+        for (int e = 0; e < MAXE; ++e)
+          if (e < E) {
+            const float a = f[e] / HC->sigma[e], b = f[e] / (2.f * HC->sigma[e]);
+            q = fmaf(a, a, q); q2 = fmaf(b, b, q2);
+          }
+        xch[(MAXE + 0) * TILE + row] = HC->c_non - q / 2.f;
+        xch[(MAXE + 1) * TILE + row] = HC->c_out - q2 / 2.f;
+        for (int k = 0; k < K; ++k) {
+          const float* u = W + D.unit_ke + k * E;
+          float pr = 0.f;
+#pragma unroll
+          for (int e = 0; e < MAXE; ++e) if (e < E) pr = fmaf(f[e], __ldg(u + e), pr);
+          float o2 = 0.f;
+#pragma unroll
+          for (int e = 0; e < MAXE; ++e) if (e < E) { const float dd = f[e] - pr * __ldg(u + e); o2 = fmaf(dd, dd, o2); }
+          const float dist = sqrtf(o2);
+          const float ll_orth = HC->c_orth[k] - (dist * dist) / HC->two_tau2[k];
+          const float ll_par = HC->log_half_lambda[k] + logerfc((HC->shift[k] - pr) / HC->sqrt2_sigma[k]) +
+                               HC->half_lambda[k] * (HC->two_mu_plus[k] - 2.f * pr);
+          xch[(MAXE + 2 + k) * TILE + row] = ll_orth + ll_par;
+        }
+      }
+      if (A.out.final_re && my_idx >= 0) {
+#pragma unroll
+        for (int e = 0; e < MAXE; ++e) if (e < E) A.out.final_re[my_idx * E + e] = f[e];
+      }
+      slot_barrier(slot);
+      // ---- per-variant sums and outputs (ragged_sets.py:144-158; artifact_model.py:291-292) ----
+      for (int idx = row; idx < nv * 2 * E; idx += 128) {
+        const int j = idx / (2 * E), rem = idx - j * 2 * E, s = rem >= E ? 1 : 0, e = rem - s * E;
+        const int start = s ? M->alt_start[j] : M->ref_start[j], cnt = s ? M->alt_cnt[j] : M->ref_cnt[j];
+        float acc = 0.f;
+        for (int i = 0; i < cnt; ++i) acc += xch[e * TILE + start + i];
+        float* dst = s ? A.out.alt_means_be : A.out.ref_means_be;
+        if (dst) dst[(long long)(v0 + j) * E + e] = acc / ((float)cnt + 1e-4f);
+      }
+      if (row < nv) {
+        const int j = row;
+        const long long v = v0 + j;
+        const int as = M->alt_start[j], ac = M->alt_cnt[j];
+        float ll[MAXK + 2];
+#pragma unroll
+        for (int k = 0; k < MAXK + 2; ++k) {
+          float acc = 0.f;
+          if (k < K + 2)
+            for (int i = 0; i < ac; ++i) acc += xch[(MAXE + k) * TILE + as + i];
+          ll[k] = acc;
+        }
+        float art_max = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < MAXK; ++k) if (k < K) { ll[2 + k] += HC->logw[k]; art_max = fmaxf(art_max, ll[2 + k]); }
+        float sacc = 0.f;
+#pragma unroll
+        for (int k = 0; k < MAXK; ++k) if (k < K) sacc += expf(ll[2 + k] - art_max);
+        const float art = art_max + logf(sacc);
+        if (A.out.logits_bk) {
+#pragma unroll
+          for (int k = 0; k < MAXK + 2; ++k) if (k < K + 2) A.out.logits_bk[v * (K + 2) + k] = ll[k];
+        }
+        if (A.out.logits_b) A.out.logits_b[v] = 20.f * tanhf((art - ll[0]) / 20.f);
+        if (A.out.outlier_logits_b) A.out.outlier_logits_b[v] = ll[1] - logsumexp2(ll[0], art);
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(S->tmem_base), "r"(TMEM_COLS));
+  if (warp == 8) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
 }
 
-// Packs one TC op: hi and lo images, K-major, 128B swizzle, K blocks of 32 elements, N rows per block.
-__global__ void pack_tc_kernel(const __grid_constant__ TcPlan TP, const float* __restrict__ w, unsigned char* __restrict__ image) {
-  const TcOp& o = TP.op[blockIdx.x];
-  const int n_kb = (o.K * 4 + 127) / 128;
+// ------------------------------------------------------------------------------------------------
+// Tile planner: greedy packing of whole variants into tiles of <= TILE rows (ref rows padded to 4, then alt rows;
+// same rule as build_tile in pmt_tile.cuh, so the set of "long" variants left to reads_forward_long_kernel is the
+// same).  One warp per claim of PLAN_CLAIM consecutive variants; tiles never span claims.  tiles[0] = tile count
+// (reserved with one atomicAdd per claim: tile ORDER is arbitrary, results do not depend on it).
+// ------------------------------------------------------------------------------------------------
+__global__ void plan_tiles_kernel(const long long* __restrict__ ref_off, const long long* __restrict__ alt_off, int B, int* __restrict__ tiles) {
+  __shared__ int buf[4][2 * PLAN_CLAIM];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int claim = blockIdx.x * 4 + w;
+  const long long c0 = (long long)claim * PLAN_CLAIM;
+  if (c0 >= B) return;
+  const int c1 = (int)min((long long)B, c0 + PLAN_CLAIM);
+  int v = (int)c0, n = 0;
+  while (v < c1) {
+    const long long r_base = __ldg(ref_off + v), a_base = __ldg(alt_off + v);
+    int nv = 0;
+    for (int base = 0; base < TILE; base += 32) {
+      const int cand = v + base + lane + 1;   // tile would cover [v, cand)
+      int fits = 0;
+      if (cand <= c1) {
+        const long long nr = __ldg(ref_off + cand) - r_base, na = __ldg(alt_off + cand) - a_base;
+        fits = (((nr + 3) & ~3LL) + na <= TILE) ? 1 : 0;
+      }
+      const unsigned ballot = __ballot_sync(0xffffffffu, fits);
+      nv += __popc(ballot);
+      if (ballot != 0xffffffffu) break;
+    }
+    if (nv == 0) { v += 1; continue; }   // longer than a tile: reads_forward_long_kernel
+    if (lane == 0) { buf[w][2 * n] = v; buf[w][2 * n + 1] = nv; }
+    ++n;
+    v += nv;
+  }
+  int base = 0;
+  if (lane == 0) base = atomicAdd(tiles, n);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  __syncwarp();
+  for (int i = lane; i < 2 * n; i += 32) tiles[2 + 2 * base + i] = buf[w][i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight images: for every step the logical B matrix [N][K] (N = output column of the MMA, K = operand column),
+// K-major with the 128-byte swizzle, K blocks of 32 elements; hi = TF32-rounded value, lo = remainder.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int perm64(int j, int d_read) { return j < d_read ? j : 32 + (j - d_read); }   // d_model vector -> X column
+__device__ __forceinline__ int unperm64(int c, int d_read, int d_model) {   // X column -> d_model index or -1
+  if (c < 32) return c < d_read ? c : -1;
+  const int j = d_read + (c - 32);
+  return j < d_model ? j : -1;
+}
+
+__device__ float tc_weight(const PmtModelDesc& D, const TcStep& o, const float* __restrict__ w, int n, int k) {
+  const int DR = D.d_read, Dm = D.d_model, H = D.d_ffn / 2;
+  switch (o.pk) {
+    case PK_LINEAR: {
+      const int nn = o.n_perm ? unperm64(n, DR, Dm) : (n < o.n_real ? n : -1);
+      if (nn < 0) return 0.f;
+      const float alpha = o.alpha_off >= 0 ? w[o.alpha_off] : 1.f;
+      if (k == o.bias_col) return alpha * w[o.b_off + nn];
+      const int kk = o.k_perm ? unperm64(k, DR, Dm) : (k < o.k_real ? k : -1);
+      if (kk < 0) return 0.f;
+      return alpha * (o.k_selu_scale ? SELU_SCALE : 1.f) * w[o.w_off + nn * o.k_real + kk];
+    }
+    case PK_PROJ1: {   // [ref set | alt set] side by side in N; LayerNorm affine folded (gated_mlp.py:185-187)
+      const PmtBlockOffsets& BO = D.blocks[o.blk];
+      const int set = n / NP1, c = n - set * NP1;
+      // set layout: z1 (outputs 0..H) at columns 0..H), z2 (outputs H..2H) at columns 12..12+H)
+      int nn = -1;
+      if (c < H) nn = c;
+      else if (c >= NP1 / 2 && c - NP1 / 2 < H) nn = H + (c - NP1 / 2);
+      if (set > 1 || nn < 0) return 0.f;
+      const int w_off = set ? BO.p1_alt_w : BO.p1_ref_w, b_off = set ? BO.p1_alt_b : BO.p1_ref_b;
+      if (k == o.bias_col) {
+        float acc = w[b_off + nn];
+        for (int j = 0; j < Dm; ++j) acc = fmaf(w[w_off + nn * Dm + j], w[BO.ln_b + j], acc);
+        return acc;
+      }
+      const int kk = unperm64(k, DR, Dm);
+      if (kk < 0) return 0.f;
+      return w[w_off + nn * Dm + kk] * w[BO.ln_w + kk];
+    }
+    case PK_PROJ2: {   // ref and alt sets stacked along K: [t_ref (MAXH) | t_alt (MAXH) | is_ref, is_alt] (gated_mlp.py:197-198)
+      const PmtBlockOffsets& BO = D.blocks[o.blk];
+      const int nn = unperm64(n, DR, Dm);
+      if (nn < 0) return 0.f;
+      if (k < MAXH) return k < H ? w[BO.p2_ref_w + nn * H + k] : 0.f;
+      if (k < 2 * MAXH) return k - MAXH < H ? w[BO.p2_alt_w + nn * H + (k - MAXH)] : 0.f;
+      if (k == 2 * MAXH) return w[BO.p2_ref_b + nn];
+      return w[BO.p2_alt_b + nn];
+    }
+    case PK_FINAL: {   // f = Q (W x + b + t): rotation and translation folded (euclidean_transformation.py:19-20)
+      const int E = D.d_feat;
+      if (n >= E) return 0.f;
+      float acc = 0.f;
+      if (k == o.bias_col) {
+        for (int j = 0; j < E; ++j) acc = fmaf(w[D.rotation + n * E + j], w[o.b_off + j] + w[D.translation + j], acc);
+        return acc;
+      }
+      const int kk = unperm64(k, DR, Dm);
+      if (kk < 0) return 0.f;
+      for (int j = 0; j < E; ++j) acc = fmaf(w[D.rotation + n * E + j], w[o.w_off + j * o.k_real + kk], acc);
+      return acc;
+    }
+  }
+  return 0.f;
+}
+
+__global__ void pack_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_constant__ TcPlan TP, const float* __restrict__ w,
+                               unsigned char* __restrict__ image) {
+  const TcStep& o = TP.step[blockIdx.x];
+  const int K = o.KS * 8;
+  const int n_kb = (K + 31) / 32;
   for (int idx = threadIdx.x; idx < n_kb * o.N * 32; idx += blockDim.x) {
     const int kb = idx / (o.N * 32), rem = idx % (o.N * 32), n = rem / 32, kk = rem % 32;
     const int k = kb * 32 + kk;
-    const int set = n / o.Np, nn = n % o.Np;
-    float v = 0.f;
-    if (nn < o.n_out && k < o.k_real && (set == 0 || o.dual)) v = w[(set ? o.w_alt_off : o.w_off) + nn * o.k_real + k];
-    const float hi = tf32_round(v);
-    const float lo = tf32_round(v - hi);
+    const float v = k < K ? tc_weight(D, o, w, n, k) : 0.f;
+    unsigned hb;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+    const float hi = __uint_as_float(hb);
+    const float lo = v - hi;
     const unsigned L = (unsigned)n * 128u + (unsigned)kk * 4u;
     const unsigned phys = L ^ (((L >> 7) & 7u) << 4);
     const size_t off = (size_t)o.img_off + (size_t)kb * o.N * 128 + phys;
@@ -656,87 +783,140 @@ int pmt_precision_mode() { return g_precision; }
 
 static int pad_to(int v, int m) { return (v + m - 1) / m * m; }
 
+// Shape envelope of the tensor-core kernel.  Read program: Linear+SELU then DenseSkipBlocks of width d_read <= 31;
+// reducer: DenseSkipBlocks of width d_model then one Linear to d_feat; d_model = d_read + d_info + d_seq with
+// d_info + d_seq <= 32 (column 31 of every 64-wide operand carries the bias).
 bool pmt_tc_supported(const Plan& P) {
   const PmtModelDesc& d = P.d;
-  if (d.d_model > MAXW || d.n_read_features > MAXW || d.d_ffn / 2 > MAXH || d.d_feat > MAXE || d.n_clusters > MAXK ||
-      d.read_row_bytes > 15)
+  if (d.n_read_features > 63 || d.read_row_bytes > 14 || d.d_read > 31 || d.d_info + d.d_seq > 32 ||
+      d.d_model != d.d_read + d.d_info + d.d_seq || d.d_ffn / 2 > MAXH || d.d_ffn % 2 || d.d_feat > MAXE || d.n_clusters > MAXK ||
+      d.n_blocks < 1)
     return false;
-  for (int i = 0; i < d.n_read_ops; ++i) if (d.read_ops[i].in_dim > MAXW || d.read_ops[i].out_dim > MAXW) return false;
-  for (int i = 0; i < d.n_red_ops; ++i) if (d.red_ops[i].in_dim > MAXW || d.red_ops[i].out_dim > MAXW) return false;
-  return 2 + d.n_read_ops + 2 * d.n_blocks + d.n_red_ops <= MAX_TC_OPS;
+  if (d.n_read_ops < 2 || !(d.read_ops[0].flags & PMT_OP_POST_SELU) || (d.read_ops[0].flags & (PMT_OP_SKIP_BEGIN | PMT_OP_SKIP_END)) ||
+      d.read_ops[0].in_dim != d.n_read_features || d.read_ops[0].out_dim != d.d_read)
+    return false;
+  bool inside = false;
+  for (int i = 1; i < d.n_read_ops; ++i) {
+    const PmtLinearOp& o = d.read_ops[i];
+    if (o.in_dim != d.d_read || o.out_dim != d.d_read) return false;
+    if (!inside && !(o.flags & PMT_OP_SKIP_BEGIN)) return false;
+    inside = !(o.flags & PMT_OP_SKIP_END);
+  }
+  if (inside) return false;
+  if (d.n_red_ops < 1) return false;
+  for (int i = 0; i + 1 < d.n_red_ops; ++i) {
+    const PmtLinearOp& o = d.red_ops[i];
+    if (o.in_dim != d.d_model || o.out_dim != d.d_model) return false;
+    if (!inside && !(o.flags & PMT_OP_SKIP_BEGIN)) return false;
+    inside = !(o.flags & PMT_OP_SKIP_END);
+  }
+  if (inside) return false;
+  const PmtLinearOp& last = d.red_ops[d.n_red_ops - 1];
+  if (last.flags != 0 || last.in_dim != d.d_model || last.out_dim != d.d_feat) return false;
+  return d.n_read_ops + 2 * d.n_blocks + d.n_red_ops <= MAX_STEPS;
 }
 
-static void add_tc_op(TcPlan& T, int k_real, int n_out, int w, int b, int w_alt, int b_alt) {
-  TcOp& o = T.op[T.n_ops++];
+static TcStep& add_step(TcPlan& T, int epi, int N, int K, int dst_x) {
+  TcStep& o = T.step[T.n_steps++];
   memset(&o, 0, sizeof(o));
-  o.k_real = k_real; o.n_out = n_out;
-  o.K = pad_to(k_real, 8);
-  o.Np = pad_to(n_out, 16);
-  o.dual = w_alt >= 0;
-  o.N = o.dual ? 2 * o.Np : o.Np;
-  o.w_off = w; o.b_off = b; o.w_alt_off = w_alt; o.b_alt_off = b_alt;
+  o.epi = epi; o.N = N; o.KS = K / 8; o.dst_x = dst_x;
+  o.alpha_off = -1; o.bias_col = -1;
   T.image_bytes = pad_to(T.image_bytes, 1024);
   o.img_off = T.image_bytes;
-  o.img_bytes = ((o.K * 4 + 127) / 128) * o.N * 128;
+  o.img_bytes = ((K + 31) / 32) * N * 128;
   T.image_bytes += 2 * o.img_bytes;
-  if (2 * o.img_bytes > T.stage_bytes) T.stage_bytes = 2 * o.img_bytes;
+  if (2 * o.img_bytes > T.slot_bytes) T.slot_bytes = 2 * o.img_bytes;
+  return o;
 }
 
-void pmt_tc_plan(const Plan& P, const PmtBatch* batch, TcPlan* out) {
+static void linear_step(TcStep& o, const PmtLinearOp& l, int k_perm, int n_perm, int k_selu_scale, int bias_col) {
+  o.pk = PK_LINEAR; o.k_real = l.in_dim; o.n_real = l.out_dim; o.w_off = l.w_off; o.b_off = l.b_off;
+  o.alpha_off = (l.flags & PMT_OP_SKIP_END) ? l.alpha_off : -1;
+  o.k_perm = k_perm; o.n_perm = n_perm; o.k_selu_scale = k_selu_scale; o.bias_col = bias_col;
+}
+
+void pmt_tc_plan(const Plan& P, TcPlan* out) {
   TcPlan& T = *out;
   memset(&T, 0, sizeof(T));
   const PmtModelDesc& d = P.d;
-  T.read0 = T.n_ops;
-  for (int i = 0; i < d.n_read_ops; ++i) add_tc_op(T, d.read_ops[i].in_dim, d.read_ops[i].out_dim, d.read_ops[i].w_off, d.read_ops[i].b_off, -1, -1);
-  T.op[T.read0].a_exact = batch && batch->reads_kind == PMT_READS_U8;
-  T.blk0 = T.n_ops;
-  for (int b = 0; b < d.n_blocks; ++b) {
-    const PmtBlockOffsets& o = d.blocks[b];
-    add_tc_op(T, d.d_model, d.d_ffn, o.p1_ref_w, o.p1_ref_b, o.p1_alt_w, o.p1_alt_b);
-    add_tc_op(T, d.d_ffn / 2, d.d_model, o.p2_ref_w, o.p2_ref_b, o.p2_alt_w, o.p2_alt_b);
+  const int H = d.d_ffn / 2;
+  // read embedding (mlp.py:25-76)
+  linear_step(add_step(T, EPI_DECODE, 32, 64, 0), d.read_ops[0], 0, 0, 0, 63);
+  for (int i = 1; i < d.n_read_ops; ++i) {
+    const PmtLinearOp& l = d.read_ops[i];
+    const int epi = (l.flags & PMT_OP_SKIP_BEGIN) ? (i == 1 ? EPI_FIRST32 : EPI_ACT_X32) : EPI_ACT_Z32;
+    linear_step(add_step(T, epi, 32, 32, (l.flags & PMT_OP_SKIP_END) ? 1 : 0), l, 0, 0, 1, 31);
   }
-  T.red0 = T.n_ops;
-  for (int i = 0; i < d.n_red_ops; ++i) add_tc_op(T, d.red_ops[i].in_dim, d.red_ops[i].out_dim, d.red_ops[i].w_off, d.red_ops[i].b_off, -1, -1);
+  // gated blocks (gated_mlp.py:177-251)
+  for (int b = 0; b < d.n_blocks; ++b) {
+    TcStep& p1 = add_step(T, b == 0 ? EPI_LN_FIRST : EPI_LN, 2 * NP1, 64, 0);
+    p1.pk = PK_PROJ1; p1.blk = b; p1.bias_col = 31;
+    TcStep& p2 = add_step(T, EPI_GATE, 64, 24, 1);
+    p2.pk = PK_PROJ2; p2.blk = b;
+    (void)H;
+  }
+  // reducer (artifact_model.py:258-259) + rotation (euclidean_transformation.py:19-20)
+  for (int i = 0; i + 1 < d.n_red_ops; ++i) {
+    const PmtLinearOp& l = d.red_ops[i];
+    const int epi = (l.flags & PMT_OP_SKIP_BEGIN) ? EPI_ACT_X64 : EPI_ACT_Z64;
+    linear_step(add_step(T, epi, 64, 64, (l.flags & PMT_OP_SKIP_END) ? 1 : 0), l, 1, 1, 1, 31);
+  }
+  {
+    const PmtLinearOp& l = d.red_ops[d.n_red_ops - 1];
+    TcStep& o = add_step(T, EPI_COPY_X64, 16, 64, 0);
+    o.pk = PK_FINAL; o.k_real = l.in_dim; o.n_real = l.out_dim; o.w_off = l.w_off; o.b_off = l.b_off; o.bias_col = 31;
+  }
   T.image_bytes = pad_to(T.image_bytes, 1024);
 }
 
+static size_t tiles_bytes(int n_variants) { return ((size_t)(2 + 2 * (size_t)n_variants) * sizeof(int) + 255) & ~(size_t)255; }
+
 size_t pmt_tc_image_bytes(const Plan& P) {
   TcPlan T;
-  pmt_tc_plan(P, nullptr, &T);
+  pmt_tc_plan(P, &T);
   return (size_t)T.image_bytes + 2048;
+}
+size_t pmt_tc_workspace_bytes(const Plan& P, const PmtBatch* batch) {
+  return pmt_tc_image_bytes(P) + tiles_bytes(batch ? batch->n_variants : 0) + 1024;
 }
 
 template <int PASSES>
-static int launch_tc(const Plan& P, const TcPlan& T, const TcArgs& A, int grid, cudaStream_t st) {
-  const size_t smem = (size_t)(PASSES == 3 ? 4 : 2) * A_KB_BYTES + (PASSES == 3 ? T.stage_bytes : T.stage_bytes / 2) +
-                      32 * TILE * sizeof(float) + TILE * 2 * MAXH * sizeof(float) + sizeof(HeadConst) + sizeof(Shared) + 1024 + 64;
-  PMT_CHECK(smem <= 227 * 1024, "tensor-core forward needs %zu bytes of shared memory", smem);
+static int launch_tc(const PmtModelDesc& D, const TcPlan& T, const TcArgs& A, int grid, cudaStream_t st) {
+  const int stage_bytes = PASSES == 3 ? T.slot_bytes : T.slot_bytes / 2;
+  const size_t fixed = 2 * XCH_ROWS * TILE * sizeof(float) + 2 * TILE * 2 * MAXH * sizeof(float) + sizeof(HeadConst) + sizeof(Shared) + 1024 + 64;
+  int n_stages = (int)((227 * 1024 - fixed) / stage_bytes);
+  if (n_stages > NS_MAX) n_stages = NS_MAX;
+  PMT_CHECK(n_stages >= 2, "tensor-core forward: weight ring does not fit in shared memory");
+  const size_t smem = fixed + (size_t)n_stages * stage_bytes;
   cudaFuncSetAttribute(reads_forward_tc_kernel<PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  reads_forward_tc_kernel<PASSES><<<grid, THREADS, smem, st>>>(P, T, A);
+  reads_forward_tc_kernel<PASSES><<<grid, THREADS, smem, st>>>(D, T, A, n_stages, stage_bytes);
   return 0;
 }
 
-// Launches the tensor-core read kernel.  `tc_image` is a device buffer of pmt_tc_image_bytes(P) bytes.
+// Launches the tile planner, the weight packer and the tensor-core read kernel.  `tc_ws` is a device buffer of
+// pmt_tc_workspace_bytes(P, batch) bytes.
 int pmt_launch_reads_tc(const Plan& P, const float* weights, const PmtBatch* batch, const PmtOutputs* out,
-                        unsigned char* tc_image, int n_sm, int mode, cudaStream_t st) {
+                        unsigned char* tc_ws, int n_sm, int mode, cudaStream_t st) {
   TcPlan T;
-  pmt_tc_plan(P, batch, &T);
-  unsigned char* image = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_image) + 1023) & ~uintptr_t(1023));
-  pack_tc_kernel<<<T.n_ops, 256, 0, st>>>(T, weights, image);
+  pmt_tc_plan(P, &T);
+  unsigned char* image = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_ws) + 1023) & ~uintptr_t(1023));
+  int* tiles = reinterpret_cast<int*>(image + T.image_bytes);
+  cudaMemsetAsync(tiles, 0, 2 * sizeof(int), st);
+  const int n_claims = (batch->n_variants + PLAN_CLAIM - 1) / PLAN_CLAIM;
+  plan_tiles_kernel<<<(n_claims + 3) / 4, 128, 0, st>>>(reinterpret_cast<const long long*>(batch->ref_off),
+                                                         reinterpret_cast<const long long*>(batch->alt_off), batch->n_variants, tiles);
+  pack_tc_kernel<<<T.n_steps, 256, 0, st>>>(P.d, T, weights, image);
   TcArgs A;
-  A.wflat = weights; A.image = image; A.batch = *batch; A.out = *out;
-  const double avg = (double)(batch->n_rows > 0 ? batch->n_rows : 16LL * batch->n_variants) / batch->n_variants;
-  int claim = (int)(8.0 * TILE / (avg + 1.0));
-  const int ctas_per_sm = mode == PMT_PRECISION_TF32 ? 2 : 1;
-  if (claim > batch->n_variants / (2 * n_sm * ctas_per_sm)) claim = batch->n_variants / (2 * n_sm * ctas_per_sm);
-  if (claim < 1) claim = 1;
-  if (claim > 512) claim = 512;
-  A.claim = claim;
-  A.n_claims = (batch->n_variants + claim - 1) / claim;
-  int grid = n_sm * ctas_per_sm;
-  if (grid > A.n_claims) grid = A.n_claims;
+  A.wflat = weights; A.image = image; A.tiles = tiles; A.batch = *batch; A.out = *out;
+  // upper bound of the tile count (>= 1 row per variant... a tile holds >= 1 variant): size the grid from rows
+  const long long rows = batch->n_rows > 0 ? batch->n_rows : batch->n_variants;
+  long long est_tiles = rows / 100 + 1;
+  if (est_tiles > batch->n_variants) est_tiles = batch->n_variants;
+  int grid = (int)((est_tiles + 1) / 2);
+  if (grid > n_sm) grid = n_sm;
+  if (grid < 1) grid = 1;
   pmt_profile_begin(st);
-  const int rc = mode == PMT_PRECISION_TF32 ? launch_tc<1>(P, T, A, grid, st) : launch_tc<3>(P, T, A, grid, st);
+  const int rc = mode == PMT_PRECISION_TF32 ? launch_tc<1>(P.d, T, A, grid, st) : launch_tc<3>(P.d, T, A, grid, st);
   pmt_profile_end(st);
   return rc;
 }
