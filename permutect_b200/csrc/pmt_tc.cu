@@ -31,7 +31,9 @@
 namespace pmt {
 namespace tc {
 
-constexpr int THREADS = 320;
+constexpr int THREADS = 576;      // 16 epilogue warps (2 slots x 2 column halves x 4 lane quarters) + MMA warp + loader warp
+constexpr int MMA_WARP = 16, LOAD_WARP = 17;
+constexpr int SUMS_FLOATS = 2 * TILE * 11;   // per slot: [segment][MAXH]
 constexpr int MAX_STEPS = 64;
 constexpr int COL_X = 0, COL_Z = 64, COL_AHI = 128, COL_ALO = 192, SLOT_COLS = 256;
 constexpr int MAXH = 11;    // d_ffn / 2: the proj2 operand [t_ref | t_alt | is_ref, is_alt] must fit 24 columns
@@ -142,6 +144,9 @@ __device__ __forceinline__ void tmem_ld32(unsigned taddr, unsigned* r) {
       : PMT_R8(r, 0), PMT_R8(r, 8), PMT_R8(r, 16), PMT_R8(r, 24)
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_st4(unsigned taddr, const unsigned* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%4], {%0,%1,%2,%3};" ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_st8(unsigned taddr, const unsigned* r) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};" ::PMT_W8(r, 0), "r"(taddr) : "memory");
 }
@@ -168,7 +173,6 @@ __device__ __forceinline__ float selu_u(float x) {
 }
 
 struct SlotMeta {
-  int nv, v0, ref_pad, pad_;
   unsigned char rowvar[TILE];   // local variant of each row, 255 = padding
   unsigned char ref_start[TILE], ref_cnt[TILE], alt_start[TILE], alt_cnt[TILE];
 };
@@ -180,40 +184,47 @@ struct Shared {
   SlotMeta slot[2];
 };
 
-// Stores v[0..NC) as the operand columns [0, NC) of this thread's row: raw fp32 (the tensor core truncates to
-// TF32) into A_hi and, in the split mode, the truncation remainder into A_lo.
+// per gated block scalars staged in shared memory (gated_mlp.py:213-226)
+constexpr int BC_LN2W = 0, BC_LN2B = 12, BC_REG = 24, BC_AREF = 36, BC_AALT = 37, BC_BREF = 38, BC_BALT = 39, BC_GAMMA = 40,
+              BC_REGW = 41, BC_STRIDE = 48;
+
+__device__ __forceinline__ float lds_f32(unsigned a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_f32(unsigned a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ float2 lds_f32x2(unsigned a) { float2 v; asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_f32x2(unsigned a, float x, float y) { asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(a), "f"(x), "f"(y) : "memory"); }
+__device__ __forceinline__ unsigned lds_u8(unsigned a) { unsigned v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void named_barrier(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+template <int NC>
+__device__ __forceinline__ void tmem_st_n(unsigned taddr, const unsigned* r) {
+  static_assert(NC == 4 || NC == 8 || NC == 12 || NC == 16 || NC == 32, "unsupported operand width");
+  if (NC == 32) tmem_st32(taddr, r);
+  else if (NC == 16) tmem_st16(taddr, r);
+  else if (NC == 12) { tmem_st8(taddr, r); tmem_st4(taddr + 8, r + 8); }
+  else if (NC == 8) tmem_st8(taddr, r);
+  else tmem_st4(taddr, r);
+}
+
+// Stores v[0..NC) as operand columns [0, NC) (relative to the given addresses) of this thread's row: raw fp32 (the
+// tensor core truncates to TF32) into A_hi and, in the split mode, the truncation remainder into A_lo.
 template <int NC, int PASSES>
 __device__ __forceinline__ void store_operand(unsigned t_hi, unsigned t_lo, const float* v, bool lo_pass) {
   unsigned r[NC];
 #pragma unroll
   for (int i = 0; i < NC; ++i) r[i] = __float_as_uint(v[i]);
-#pragma unroll
-  for (int c = 0; c < NC; c += 32) {
-    if (NC - c >= 32) tmem_st32(t_hi + c, r + c);
-    else if (NC - c >= 16) { tmem_st16(t_hi + c, r + c); if (NC - c == 24) tmem_st8(t_hi + c + 16, r + c + 16); }
-    else tmem_st8(t_hi + c, r + c);
-  }
+  tmem_st_n<NC>(t_hi, r);
   if (PASSES == 3 && lo_pass) {
 #pragma unroll
     for (int i = 0; i < NC; ++i) r[i] = __float_as_uint(v[i] - __uint_as_float(r[i] & 0xFFFFE000u));
-#pragma unroll
-    for (int c = 0; c < NC; c += 32) {
-      if (NC - c >= 32) tmem_st32(t_lo + c, r + c);
-      else if (NC - c >= 16) { tmem_st16(t_lo + c, r + c); if (NC - c == 24) tmem_st8(t_lo + c + 16, r + c + 16); }
-      else tmem_st8(t_lo + c, r + c);
-    }
+    tmem_st_n<NC>(t_lo, r);
   }
 }
 
 template <int NC>
 __device__ __forceinline__ void load_cols(unsigned taddr, float* v) {
+  static_assert(NC == 16 || NC == 32, "unsupported load width");
   unsigned r[NC];
-#pragma unroll
-  for (int c = 0; c < NC; c += 32) {
-    if (NC - c >= 32) tmem_ld32(taddr + c, r + c);
-    else if (NC - c >= 16) { tmem_ld16(taddr + c, r + c); if (NC - c == 24) tmem_ld8(taddr + c + 16, r + c + 16); }
-    else tmem_ld8(taddr + c, r + c);
-  }
+  if (NC == 32) tmem_ld32(taddr, r); else tmem_ld16(taddr, r);
   tmem_wait_ld();
 #pragma unroll
   for (int i = 0; i < NC; ++i) v[i] = __uint_as_float(r[i]);
@@ -235,16 +246,37 @@ __device__ __forceinline__ void issue_chain(unsigned d, unsigned a_hi, unsigned 
   }
 }
 
+// 4-way partial sums: short dependency chains for the two warps that share an SM sub-partition
+template <int N>
+__device__ __forceinline__ float sum_n(const float* v) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+  for (int i = 0; i < N; i += 4) { a0 += v[i]; a1 += v[i + 1]; a2 += v[i + 2]; a3 += v[i + 3]; }
+  return (a0 + a1) + (a2 + a3);
+}
+template <int N>
+__device__ __forceinline__ float sumsq_centered_n(const float* v, float m) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+  for (int i = 0; i < N; i += 4) {
+    const float d0 = v[i] - m, d1 = v[i + 1] - m, d2 = v[i + 2] - m, d3 = v[i + 3] - m;
+    a0 = fmaf(d0, d0, a0); a1 = fmaf(d1, d1, a1); a2 = fmaf(d2, d2, a2); a3 = fmaf(d3, d3, a3);
+  }
+  return (a0 + a1) + (a2 + a3);
+}
+
 template <int PASSES>
 __global__ void __launch_bounds__(THREADS, 1)
 reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_constant__ TcPlan TP, const __grid_constant__ TcArgs A,
                         int n_stages, int stage_bytes) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  // carve: [weight ring: n_stages x stage_bytes][xch 2 slots][sums 2 slots][HeadConst][Shared]
+  // carve: [weight ring: n_stages x stage_bytes][xch 2 slots][sums 2 slots][pair exchange][block scalars][HeadConst][Shared]
   unsigned char* p = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const unsigned ring = smem_addr(p); p += (size_t)n_stages * stage_bytes;
-  float* xch_all = reinterpret_cast<float*>(p); p += 2 * XCH_ROWS * TILE * sizeof(float);
-  float* sums_all = reinterpret_cast<float*>(p); p += 2 * TILE * 2 * MAXH * sizeof(float);
+  const unsigned xch_all = smem_addr(p); p += 2 * XCH_ROWS * TILE * sizeof(float);
+  const unsigned sums_all = smem_addr(p); p += 2 * SUMS_FLOATS * sizeof(float);
+  const unsigned pairx_all = smem_addr(p); p += 2 * 2 * TILE * 2 * sizeof(float);
+  float* blkc = reinterpret_cast<float*>(p); p += PMT_MAX_BLOCKS * BC_STRIDE * sizeof(float);
   HeadConst* HC = reinterpret_cast<HeadConst*>(p); p += sizeof(HeadConst);
   Shared* S = reinterpret_cast<Shared*>((reinterpret_cast<uintptr_t>(p) + 15) & ~uintptr_t(15));
 
@@ -252,12 +284,27 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const float* W = A.wflat;
   if (tid == 0) {
-    for (int s = 0; s < 2; ++s) { mbar_init(smem_addr(&S->bar_a[s]), 4); mbar_init(smem_addr(&S->bar_d[s]), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(smem_addr(&S->bar_a[s]), 8); mbar_init(smem_addr(&S->bar_d[s]), 1); }
     for (int i = 0; i < n_stages; ++i) { mbar_init(smem_addr(&S->wfull[i]), 1); mbar_init(smem_addr(&S->wfree[i]), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     head_constants(D, W, HC);
   }
-  if (warp == 8) {
+  for (int i = tid; i < D.n_blocks * BC_STRIDE; i += THREADS) {
+    const PmtBlockOffsets& BO = D.blocks[i / BC_STRIDE];
+    const int c = i % BC_STRIDE, H = D.d_ffn / 2;
+    float v = 0.f;
+    if (c < BC_LN2B) { if (c < H) v = W[BO.ln2_w + c]; }
+    else if (c < BC_REG) { if (c - BC_LN2B < H) v = W[BO.ln2_b + c - BC_LN2B]; }
+    else if (c < BC_AREF) { if (c - BC_REG < H) v = W[BO.regularizer + c - BC_REG]; }
+    else if (c == BC_AREF) v = W[BO.alpha_ref];
+    else if (c == BC_AALT) v = W[BO.alpha_alt];
+    else if (c == BC_BREF) v = W[BO.beta_ref];
+    else if (c == BC_BALT) v = W[BO.beta_alt];
+    else if (c == BC_GAMMA) v = W[BO.gamma];
+    else if (c == BC_REGW) v = W[BO.reg_weight] + 0.25f;   // gated_mlp.py:237
+    blkc[i] = v;
+  }
+  if (warp == MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&S->tmem_base)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
@@ -267,13 +314,13 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
 
   const int n_tiles = __ldg(A.tiles);
   const int n_slots = 2 * gridDim.x;
-  // every slot of the CTA runs the same number of rounds (idle slots process an empty tile)
+  // every slot of the CTA runs the same number of rounds (an idle slot processes an empty tile)
   const int rounds = (n_tiles - 2 * (int)blockIdx.x + n_slots - 1) / n_slots;   // rounds of slot 0 >= rounds of slot 1
   const int n_steps = TP.n_steps;
   const unsigned tmem_base = __shfl_sync(0xffffffffu, S->tmem_base, 0);
   const bool l0_lo = A.batch.reads_kind != PMT_READS_U8;   // decoded reads k/32 and bits are exact in TF32
 
-  if (warp == 9) {
+  if (warp == LOAD_WARP) {
     // ===================================== weight loader =====================================
     if (elect_one()) {
       const long long total = (long long)rounds * n_steps;
@@ -290,30 +337,31 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
       }
     }
     __syncwarp();
-  } else if (warp == 8) {
+  } else if (warp == MMA_WARP) {
     // ===================================== MMA issuer =====================================
     int stage = 0;
     unsigned wparity = 0, aparity = 0;
     for (int round = 0; round < rounds; ++round) {
       for (int step = 0; step < n_steps; ++step) {
         const TcStep& o = TP.step[step];
-        mbar_wait(smem_addr(&S->wfull[stage]), wparity);
-        const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(o.N >> 3) << 17) | ((128u >> 4) << 24);
+        const int oN = o.N, oKS = o.KS, o_dst_x = o.dst_x, o_img_bytes = o.img_bytes;
+        const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(oN >> 3) << 17) | ((128u >> 4) << 24);
         const unsigned wb = ring + stage * stage_bytes;
-        const uint64_t b_hi = smem_desc(wb), b_lo = smem_desc(wb + o.img_bytes);
-        const unsigned kb_stride16 = (unsigned)(o.N * 128) >> 4;
+        const uint64_t b_hi = smem_desc(wb), b_lo = smem_desc(wb + o_img_bytes);
+        const unsigned kb_stride16 = (unsigned)(oN * 128) >> 4;
         const bool lo_pass = step > 0 || l0_lo;
+        mbar_wait(smem_addr(&S->wfull[stage]), wparity);
 #pragma unroll 1
         for (int s = 0; s < 2; ++s) {
+          const unsigned tb = tmem_base + s * SLOT_COLS;
+          const unsigned d = tb + (o_dst_x ? COL_X : COL_Z);
           mbar_wait(smem_addr(&S->bar_a[s]), aparity);
           tc_fence_after();
-          const unsigned tb = tmem_base + s * SLOT_COLS;
-          const unsigned d = tb + (o.dst_x ? COL_X : COL_Z);
           if (elect_one()) {
-            switch (o.KS) {
-              case 3: issue_chain<3, PASSES>(d, tb + COL_AHI, tb + COL_ALO, b_hi, b_lo, kb_stride16, idesc, o.dst_x, lo_pass); break;
-              case 4: issue_chain<4, PASSES>(d, tb + COL_AHI, tb + COL_ALO, b_hi, b_lo, kb_stride16, idesc, o.dst_x, lo_pass); break;
-              default: issue_chain<8, PASSES>(d, tb + COL_AHI, tb + COL_ALO, b_hi, b_lo, kb_stride16, idesc, o.dst_x, lo_pass); break;
+            switch (oKS) {
+              case 3: issue_chain<3, PASSES>(d, tb + COL_AHI, tb + COL_ALO, b_hi, b_lo, kb_stride16, idesc, o_dst_x, lo_pass); break;
+              case 4: issue_chain<4, PASSES>(d, tb + COL_AHI, tb + COL_ALO, b_hi, b_lo, kb_stride16, idesc, o_dst_x, lo_pass); break;
+              default: issue_chain<8, PASSES>(d, tb + COL_AHI, tb + COL_ALO, b_hi, b_lo, kb_stride16, idesc, o_dst_x, lo_pass); break;
             }
             mma_commit(smem_addr(&S->bar_d[s]));
             if (s == 1) mma_commit(smem_addr(&S->wfree[stage]));
@@ -325,20 +373,27 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
       }
     }
   } else {
-    // ===================================== epilogue: thread = row =====================================
-    const int slot = warp >> 2;
-    const int row = tid & 127;
+    // ============ epilogue: two threads per row; thread (row, half) owns 32 of the row's 64 columns ============
+    const int slot = warp >> 3, half = (warp >> 2) & 1, quarter = warp & 3;
     const int lane = tid & 31;
+    const int row = quarter * 32 + lane;
+    const int srow = half * TILE + row;              // 0..255 inside the slot
+    const int slot_bar = 1 + slot, pair_bar = 3 + slot * 4 + quarter;
     SlotMeta* M = &S->slot[slot];
-    float* xch = xch_all + slot * XCH_ROWS * TILE;
-    float* sums = sums_all + slot * TILE * 2 * MAXH;
+    const unsigned m_rowvar = smem_addr(M->rowvar), m_ref_start = smem_addr(M->ref_start), m_ref_cnt = smem_addr(M->ref_cnt),
+                   m_alt_start = smem_addr(M->alt_start), m_alt_cnt = smem_addr(M->alt_cnt);
+    const unsigned xch = xch_all + slot * XCH_ROWS * TILE * 4;      // [XCH_ROWS][TILE] floats
+    const unsigned sums = sums_all + slot * SUMS_FLOATS * 4;        // [segment = 2 * variant + side][MAXH]
+    const unsigned px_mine = pairx_all + ((slot * 2 + half) * TILE + row) * 8, px_other = pairx_all + ((slot * 2 + (half ^ 1)) * TILE + row) * 8;
     const unsigned bar_a = smem_addr(&S->bar_a[slot]), bar_d = smem_addr(&S->bar_d[slot]);
-    const unsigned trow = tmem_base + slot * SLOT_COLS + ((unsigned)((warp & 3) * 32) << 16);
+    const unsigned trow = tmem_base + slot * SLOT_COLS + ((unsigned)(quarter * 32) << 16);
     const unsigned t_x = trow + COL_X, t_z = trow + COL_Z, t_hi = trow + COL_AHI, t_lo = trow + COL_ALO;
     const int E = D.d_feat, K = D.n_clusters, Dm = D.d_model, H = D.d_ffn / 2, DR = D.d_read, F = D.n_read_features;
     const int DIS = D.d_info + D.d_seq;
     const int B = A.batch.n_variants;
     const long long total_ref = __ldg(A.batch.ref_off + B);
+    const unsigned inv_h = (65536u + (unsigned)H - 1u) / (unsigned)H, inv_e = (65536u + (unsigned)E - 1u) / (unsigned)E;
+    const int n_half = half ? DIS : DR;              // real columns of this thread's half of a d_model vector
     unsigned dparity = 0;
 
     for (int round = 0; round < rounds; ++round) {
@@ -348,14 +403,14 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
       if (t < n_tiles) { v0 = __ldg(A.tiles + 2 + 2 * t); nv = __ldg(A.tiles + 3 + 2 * t); }
       long long r_base = 0, a_base = 0;
       int ref_pad = 0;
-      M->rowvar[row] = 255;
-      slot_barrier(slot);   // previous tile's readers of the tables are done; rowvar cleared
+      if (half == 0) M->rowvar[row] = 255;
+      named_barrier(slot_bar, 256);   // previous tile's readers of the tables are done; rowvar cleared
       if (nv > 0) {
         r_base = __ldg(A.batch.ref_off + v0);
         a_base = __ldg(A.batch.alt_off + v0);
         const long long nr_tot = __ldg(A.batch.ref_off + v0 + nv) - r_base;
         ref_pad = (int)((nr_tot + 3) & ~3LL);
-        if (row < nv) {
+        if (half == 0 && row < nv) {
           const long long r0 = __ldg(A.batch.ref_off + v0 + row), r1 = __ldg(A.batch.ref_off + v0 + row + 1);
           const long long a0 = __ldg(A.batch.alt_off + v0 + row), a1 = __ldg(A.batch.alt_off + v0 + row + 1);
           const int rs = (int)(r0 - r_base), rc = (int)(r1 - r0), as = ref_pad + (int)(a0 - a_base), ac = (int)(a1 - a0);
@@ -365,184 +420,247 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
           for (int i = 0; i < ac; ++i) M->rowvar[as + i] = (unsigned char)row;
         }
       }
-      slot_barrier(slot);
-      const int my_var = M->rowvar[row] == 255 ? -1 : (int)M->rowvar[row];
+      named_barrier(slot_bar, 256);
+      const int rv = (int)lds_u8(m_rowvar + row);
+      const int my_var = rv == 255 ? -1 : rv;
       const bool is_alt = row >= ref_pad;
       long long my_idx = -1;
       if (my_var >= 0) my_idx = is_alt ? total_ref + a_base + (row - ref_pad) : r_base + row;
 
       for (int step = 0; step < n_steps; ++step) {
-        const TcStep& o = TP.step[step];
-        switch (o.epi) {
+        const int epi = TP.step[step].epi;
+        switch (epi) {
           case EPI_DECODE: {   // batch.py:51-56, plain_text_data.py:510-511 (quirk Q2: the uint8 de-quantisation wraps)
-            float v[64];
+            float v[32];
 #pragma unroll
-            for (int i = 0; i < 64; ++i) v[i] = 0.f;
+            for (int i = 0; i < 32; ++i) v[i] = 0.f;
             if (my_idx >= 0) {
               const long long src = A.batch.read_indices ? __ldg(A.batch.read_indices + my_idx) : my_idx;
               if (A.batch.reads_kind == PMT_READS_U8) {
                 const int rb = D.read_row_bytes;
                 const unsigned char* rp = reinterpret_cast<const unsigned char*>(A.batch.reads) + src * rb;
-                unsigned bytes[16];
+                unsigned bytes[8];   // this half's 8 source bytes: packed bytes 0..3, or packed bytes 4..6 + quantised 7..
                 if (rb == 12) {
                   const unsigned* wp = reinterpret_cast<const unsigned*>(rp);
-                  const unsigned w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
+                  if (half == 0) {
+                    const unsigned w0 = __ldg(wp);
 #pragma unroll
-                  for (int b = 0; b < 4; ++b) { bytes[b] = (w0 >> (8 * b)) & 255u; bytes[4 + b] = (w1 >> (8 * b)) & 255u; bytes[8 + b] = (w2 >> (8 * b)) & 255u; }
-                  bytes[12] = bytes[13] = bytes[14] = bytes[15] = 128u;
+                    for (int b = 0; b < 4; ++b) bytes[b] = (w0 >> (8 * b)) & 255u;
+                  } else {
+                    const unsigned w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) { bytes[b] = (w1 >> (8 * b)) & 255u; bytes[4 + b] = (w2 >> (8 * b)) & 255u; }
+                  }
                 } else {
 #pragma unroll
-                  for (int b = 0; b < 15; ++b) bytes[b] = b < rb ? (unsigned)__ldg(rp + b) : 128u;
-                  bytes[15] = 128u;
+                  for (int b = 0; b < 8; ++b) {
+                    const int sb = half * 4 + b;
+                    bytes[b] = (sb < rb && (half == 1 || b < 4)) ? (unsigned)__ldg(rp + sb) : 128u;
+                  }
                 }
+                if (half == 0) {
 #pragma unroll
-                for (int b = 0; b < 7; ++b)
+                  for (int b = 0; b < 4; ++b)
 #pragma unroll
-                  for (int bit = 0; bit < 8; ++bit) v[b * 8 + bit] = __uint_as_float((0u - ((bytes[b] >> (7 - bit)) & 1u)) & 0x3f800000u);
+                    for (int bit = 0; bit < 8; ++bit) v[b * 8 + bit] = __uint_as_float((0u - ((bytes[b] >> (7 - bit)) & 1u)) & 0x3f800000u);
+                } else {
 #pragma unroll
-                for (int b = 7; b < 14; ++b)
-                  if (b < rb) v[56 + b - 7] = (float)((bytes[b] + 128u) & 255u) * 0.03125f;
+                  for (int b = 0; b < 3; ++b)
+#pragma unroll
+                    for (int bit = 0; bit < 8; ++bit) v[b * 8 + bit] = __uint_as_float((0u - ((bytes[b] >> (7 - bit)) & 1u)) & 0x3f800000u);
+                  if (rb == 12) {
+#pragma unroll
+                    for (int b = 3; b < 8; ++b) v[24 + b - 3] = (float)((bytes[b] + 128u) & 255u) * 0.03125f;
+                  } else {
+#pragma unroll
+                    for (int b = 3; b < 8; ++b)
+                      if (4 + b < rb) v[24 + b - 3] = (float)((bytes[b] + 128u) & 255u) * 0.03125f;
+                  }
+                }
               } else {
 #pragma unroll
-                for (int f = 0; f < 63; ++f)
+                for (int i = 0; i < 32; ++i) {
+                  const int f = half * 32 + i;
                   if (f < F)
-                    v[f] = A.batch.reads_kind == PMT_READS_F16 ? __half2float(reinterpret_cast<const __half*>(A.batch.reads)[src * F + f])
+                    v[i] = A.batch.reads_kind == PMT_READS_F16 ? __half2float(reinterpret_cast<const __half*>(A.batch.reads)[src * F + f])
                                                                : reinterpret_cast<const float*>(A.batch.reads)[src * F + f];
+                }
               }
             }
-            v[63] = 1.f;
-            store_operand<64, PASSES>(t_hi, t_lo, v, l0_lo);
+            if (half == 1) v[31] = 1.f;   // operand column 63: bias
+            store_operand<32, PASSES>(t_hi + half * 32, t_lo + half * 32, v, l0_lo);
           } break;
           case EPI_FIRST32: {   // mlp.py:61-62 then the first DenseSkipBlock's leading SELU (mlp.py:8-22)
-            float v[32];
-            load_cols<32>(t_z, v);
-            unsigned r[32];
+            float v[16];
+            load_cols<16>(t_z + half * 16, v);
+            unsigned r[16];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) { v[i] = SELU_SCALE * selu_u(v[i]); r[i] = __float_as_uint(v[i]); }
-            tmem_st32(t_x, r);
+            for (int i = 0; i < 16; ++i) { v[i] = SELU_SCALE * selu_u(v[i]); r[i] = __float_as_uint(v[i]); }
+            tmem_st16(t_x + half * 16, r);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = selu_u(v[i]);
-            v[31] = 1.f;
-            store_operand<32, PASSES>(t_hi, t_lo, v, true);
+            for (int i = 0; i < 16; ++i) v[i] = selu_u(v[i]);
+            if (half == 1) v[15] = 1.f;   // operand column 31: bias
+            store_operand<16, PASSES>(t_hi + half * 16, t_lo + half * 16, v, true);
           } break;
           case EPI_ACT_Z32:
           case EPI_ACT_X32: {
-            float v[32];
-            load_cols<32>(o.epi == EPI_ACT_Z32 ? t_z : t_x, v);
+            float v[16];
+            load_cols<16>((epi == EPI_ACT_Z32 ? t_z : t_x) + half * 16, v);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = selu_u(v[i]);
-            v[31] = 1.f;
-            store_operand<32, PASSES>(t_hi, t_lo, v, true);
+            for (int i = 0; i < 16; ++i) v[i] = selu_u(v[i]);
+            if (half == 1) v[15] = 1.f;
+            store_operand<16, PASSES>(t_hi + half * 16, t_lo + half * 16, v, true);
           } break;
           case EPI_LN_FIRST:
           case EPI_LN: {   // gated_mlp.py:185 (LayerNorm affine folded into proj1); artifact_model.py:246-251 concat
-            float v[64];
-            if (o.epi == EPI_LN_FIRST) {
-              load_cols<32>(t_x, v);
+            float v[32];
+            if (epi == EPI_LN_FIRST && half == 1) {
               const float* src = my_var >= 0 ? A.out.info_seq_be + (long long)(v0 + my_var) * DIS : nullptr;
               unsigned r[32];
 #pragma unroll
-              for (int i = 0; i < 32; ++i) { v[32 + i] = (src && i < DIS) ? __ldg(src + i) : 0.f; r[i] = __float_as_uint(v[32 + i]); }
+              for (int i = 0; i < 32; ++i) { v[i] = (src && i < DIS) ? __ldg(src + i) : 0.f; r[i] = __float_as_uint(v[i]); }
               tmem_st32(t_x + 32, r);
             } else {
-              load_cols<64>(t_x, v);
+              load_cols<32>(t_x + half * 32, v);
             }
-            float sum = 0.f;
-#pragma unroll
-            for (int i = 0; i < 64; ++i) sum += v[i];
-            const float mean = sum / (float)Dm;
-            float sq = 0.f;
-#pragma unroll
-            for (int i = 0; i < 64; ++i) { v[i] -= mean; sq = fmaf(v[i], v[i], sq); }
-            const float var = (sq - (float)(64 - Dm) * mean * mean) / (float)Dm;   // padding columns hold -mean
+            // statistics of this half (padding columns are zero), combined with the partner's (Chan et al.)
+            const float nh = (float)n_half, no = (float)(Dm - n_half);
+            const float s_h = sum_n<32>(v);
+            const float m_h = s_h / nh;
+            const float q_h = sumsq_centered_n<32>(v, m_h) - (32.f - nh) * m_h * m_h;
+            sts_f32x2(px_mine, s_h, q_h);
+            named_barrier(pair_bar, 64);
+            const float2 oth = lds_f32x2(px_other);
+            const float mean = (s_h + oth.x) / (float)Dm;
+            const float dm = m_h - oth.x / no;
+            const float var = (q_h + oth.y + dm * dm * nh * no / (float)Dm) / (float)Dm;
             const float rstd = rsqrtf(fmaxf(var, 0.f) + LN_EPS);
+            const float shift = -mean * rstd;
 #pragma unroll
-            for (int i = 0; i < 64; ++i) v[i] *= rstd;
-            v[31] = 1.f;
-            store_operand<64, PASSES>(t_hi, t_lo, v, true);
+            for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], rstd, shift);
+            if (half == 0) v[31] = 1.f;   // operand column 31: bias
+            store_operand<32, PASSES>(t_hi + half * 32, t_lo + half * 32, v, true);
           } break;
-          case EPI_GATE: {   // gated_mlp.py:186-190, 228-251
-            const PmtBlockOffsets& BO = D.blocks[o.blk];
-            float zz[2 * NP1];
-            load_cols<2 * NP1>(t_z, zz);
-            // one weight set = [z1 at columns 0..H) | z2 at columns 12..12+H)]
-            float z1[MAXH], z2[MAXH];
-#pragma unroll
-            for (int k = 0; k < MAXH; ++k) {
-              z1[k] = SELU_SCALE * selu_u(is_alt ? zz[NP1 + k] : zz[k]);
-              z2[k] = SELU_SCALE * selu_u(is_alt ? zz[NP1 + NP1 / 2 + k] : zz[NP1 / 2 + k]);
-            }
-            float z2n[MAXH];
+          case EPI_GATE: {   // gated_mlp.py:186-190, 228-251; this thread gates hidden units [k0, k0 + 6)
+            const float* bc = blkc + TP.step[step].blk * BC_STRIDE;
+            const unsigned bcs = smem_addr(bc);
+            // proj1 output: [ref set | alt set], one set = [z1 at 0..H) | z2 at 12..12+H)]
+            float z1s[16], z2s[16];
             {
-              float mean = 0.f;
+              unsigned r1[16], r2[16];
+              const unsigned base = t_z + (is_alt ? NP1 : 0);
+              // addresses must be warp-uniform: load both sets when the warp mixes ref and alt rows
+              const bool all_ref = __all_sync(0xffffffffu, !is_alt), all_alt = __all_sync(0xffffffffu, is_alt);
+              if (all_ref || all_alt) {
+                const unsigned ub = t_z + (all_alt ? NP1 : 0);
+                tmem_ld8(ub + half * 6, r1); tmem_ld16(ub + NP1 / 2, r2);
+                tmem_wait_ld();
+              } else {
+                unsigned a1[8], a2[16];
+                tmem_ld8(t_z + half * 6, r1); tmem_ld16(t_z + NP1 / 2, r2);
+                tmem_ld8(t_z + NP1 + half * 6, a1); tmem_ld16(t_z + NP1 + NP1 / 2, a2);
+                tmem_wait_ld();
 #pragma unroll
-              for (int k = 0; k < MAXH; ++k) if (k < H) mean += z2[k];
-              mean /= (float)H;
-              float var = 0.f;
+                for (int i = 0; i < 8; ++i) r1[i] = is_alt ? a1[i] : r1[i];
 #pragma unroll
-              for (int k = 0; k < MAXH; ++k) if (k < H) { const float dd = z2[k] - mean; var = fmaf(dd, dd, var); }
-              const float rstd = rsqrtf(var / (float)H + LN_EPS);
+                for (int i = 0; i < 16; ++i) r2[i] = is_alt ? a2[i] : r2[i];
+              }
+              (void)base;
 #pragma unroll
-              for (int k = 0; k < MAXH; ++k) {
-                z2n[k] = 0.f;
-                if (k < H) {
-                  z2n[k] = (z2[k] - mean) * rstd * __ldg(W + BO.ln2_w + k) + __ldg(W + BO.ln2_b + k);
-                  xch[k * TILE + row] = z2n[k];
-                }
+              for (int i = 0; i < 8; ++i) z1s[i] = __uint_as_float(r1[i]);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) z2s[i] = __uint_as_float(r2[i]);
+            }
+            // z1s[j] = z1[k0 + j] (j < 6), z2s[k] = z2[k] (k < 12; columns >= H are zero)
+            const int k0 = half * 6;
+            float z2[12];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) z2[k] = k < H ? SELU_SCALE * selu_u(z2s[k]) : 0.f;
+            const float mean = sum_n<12>(z2) / (float)H;
+            float var;
+            {
+              float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+              for (int k = 0; k < 12; k += 2) {
+                const float d0 = k < H ? z2[k] - mean : 0.f, d1 = k + 1 < H ? z2[k + 1] - mean : 0.f;
+                a0 = fmaf(d0, d0, a0); a1 = fmaf(d1, d1, a1);
+              }
+              var = (a0 + a1) / (float)H;
+            }
+            const float rstd = rsqrtf(var + LN_EPS);
+            float z2n[6];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+              // z2[k0 + j]: k0 is 0 or 6 -> select between two compile-time registers
+              const float zz = half ? z2[j + 6] : z2[j];
+              z2n[j] = (zz - mean) * rstd * lds_f32(bcs + (BC_LN2W + k0 + j) * 4) + lds_f32(bcs + (BC_LN2B + k0 + j) * 4);
+              if (k0 + j < H) sts_f32(xch + ((k0 + j) * TILE + row) * 4, z2n[j]);
+            }
+            named_barrier(slot_bar, 256);
+            {   // per-variant mean fields (gated_mlp.py:236-239): one (segment, hidden unit) sum per thread
+              const float regw = lds_f32(bcs + BC_REGW * 4);
+              const int n_sums = nv * 2 * H;
+              for (int idx = srow; idx < n_sums; idx += 256) {
+                const int seg = (int)(((unsigned)idx * inv_h) >> 16), f = idx - seg * H;
+                const int j = seg >> 1, s = seg & 1;
+                const int start = (int)lds_u8((s ? m_alt_start : m_ref_start) + j), cnt = (int)lds_u8((s ? m_alt_cnt : m_ref_cnt) + j);
+                const unsigned src = xch + (f * TILE + start) * 4;
+                float a0 = 0.f, a1 = 0.f;
+                int i = 0;
+                for (; i + 1 < cnt; i += 2) { a0 += lds_f32(src + i * 4); a1 += lds_f32(src + i * 4 + 4); }
+                if (i < cnt) a0 += lds_f32(src + i * 4);
+                const float acc = a0 + a1;
+                const float m = s == 0 ? (acc + regw * lds_f32(bcs + (BC_REG + f) * 4)) / ((float)cnt + regw) : acc / ((float)cnt + 1e-4f);
+                sts_f32(sums + (seg * MAXH + f) * 4, m);
               }
             }
-            slot_barrier(slot);
-            {   // per-variant mean fields (gated_mlp.py:236-239)
-              const float regw = __ldg(W + BO.reg_weight) + 0.25f;
-              const int n_seg = nv * 2 * H;
-              for (int idx = row; idx < n_seg; idx += 128) {
-                const int j = idx / (2 * H), rem = idx - j * 2 * H, s = rem >= H ? 1 : 0, f = rem - s * H;
-                const int start = s ? M->alt_start[j] : M->ref_start[j], cnt = s ? M->alt_cnt[j] : M->ref_cnt[j];
-                float acc = 0.f;
-                for (int i = 0; i < cnt; ++i) acc += xch[f * TILE + start + i];
-                sums[(j * 2 + s) * MAXH + f] = s == 0 ? (acc + regw * __ldg(W + BO.regularizer + f)) / ((float)cnt + regw)
-                                                     : acc / ((float)cnt + 1e-4f);
-              }
-            }
-            slot_barrier(slot);
-            // proj2 operand [t_ref at 0..MAXH) | t_alt at MAXH..2 MAXH) | is_ref, is_alt]: a row feeds only its own weight set
-            float v[24];
+            named_barrier(slot_bar, 256);
+            // proj2 operand columns of this thread: [t_ref (6) | t_alt (6)]; the second thread's last two hidden
+            // slots (k = 10 would be unit 11; MAXH = 11 -> slot 5 of half 1 is unit 11 < MAXH only if H = 11)
+            // layout, half 0: [t_ref k 0..5 | t_alt k 0..5]; half 1: [t_ref k 6..10 | t_alt k 6..10 | is_ref, is_alt]
+            float v[12];
             {
-              const float alpha = __ldg(W + (is_alt ? BO.alpha_alt : BO.alpha_ref));
-              const float beta = __ldg(W + (is_alt ? BO.beta_alt : BO.beta_ref));
-              const float gamma = is_alt ? __ldg(W + BO.gamma) : 0.f;
+              const float alpha = lds_f32(bcs + (is_alt ? BC_AALT : BC_AREF) * 4);
+              const float beta = lds_f32(bcs + (is_alt ? BC_BALT : BC_BREF) * 4);
+              const float gamma = is_alt ? lds_f32(bcs + BC_GAMMA * 4) : 0.f;
               const int mv = my_var >= 0 ? my_var : 0;
+              const unsigned s_ref = sums + ((mv * 2 + 0) * MAXH + k0) * 4, s_own = sums + ((mv * 2 + (is_alt ? 1 : 0)) * MAXH + k0) * 4;
+              float tk[6];
 #pragma unroll
-              for (int k = 0; k < MAXH; ++k) {
-                float tk = 0.f;
-                if (k < H) {
-                  float gate = fmaf(z2n[k], alpha, 1.f);
+              for (int j = 0; j < 6; ++j) {
+                tk[j] = 0.f;
+                if (k0 + j < H) {
+                  float gate = fmaf(z2n[j], alpha, 1.f);
                   if (my_var >= 0) {
-                    const float m_ref = sums[(mv * 2 + 0) * MAXH + k];
-                    const float m_own = is_alt ? sums[(mv * 2 + 1) * MAXH + k] : m_ref;
+                    const float m_ref = lds_f32(s_ref + j * 4), m_own = lds_f32(s_own + j * 4);
                     gate = fmaf(beta, m_own, fmaf(gamma, m_ref, gate));
                   }
-                  tk = z1[k] * gate;
+                  tk[j] = SELU_SCALE * selu_u(z1s[j]) * gate;
                 }
-                v[k] = is_alt ? 0.f : tk;
-                v[MAXH + k] = is_alt ? tk : 0.f;
               }
-              v[2 * MAXH] = is_alt ? 0.f : 1.f;
-              v[2 * MAXH + 1] = is_alt ? 1.f : 0.f;
+              if (half == 0) {
+#pragma unroll
+                for (int j = 0; j < 6; ++j) { v[j] = is_alt ? 0.f : tk[j]; v[6 + j] = is_alt ? tk[j] : 0.f; }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 5; ++j) { v[j] = is_alt ? 0.f : tk[j]; v[5 + j] = is_alt ? tk[j] : 0.f; }
+                v[10] = is_alt ? 0.f : 1.f;
+                v[11] = is_alt ? 1.f : 0.f;
+              }
             }
-            store_operand<24, PASSES>(t_hi, t_lo, v, true);
+            store_operand<12, PASSES>(t_hi + half * 12, t_lo + half * 12, v, true);
           } break;
           case EPI_ACT_X64:
           case EPI_ACT_Z64:
           case EPI_COPY_X64: {
-            float v[64];
-            load_cols<64>(o.epi == EPI_ACT_Z64 ? t_z : t_x, v);
-            if (o.epi != EPI_COPY_X64) {
+            float v[32];
+            load_cols<32>((epi == EPI_ACT_Z64 ? t_z : t_x) + half * 32, v);
+            if (epi != EPI_COPY_X64) {
 #pragma unroll
-              for (int i = 0; i < 64; ++i) v[i] = selu_u(v[i]);
+              for (int i = 0; i < 32; ++i) v[i] = selu_u(v[i]);
             }
-            v[31] = 1.f;
-            store_operand<64, PASSES>(t_hi, t_lo, v, true);
+            if (half == 0) v[31] = 1.f;
+            store_operand<32, PASSES>(t_hi + half * 32, t_lo + half * 32, v, true);
           } break;
         }
         // ---- hand the operand to the MMA warp, wait for the accumulator ----
@@ -556,59 +674,69 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
       }
 
       // ---------------- clustering head (rotation folded into the last layer; feature_clustering.py:82-135) ----------------
+      // half 0: feature rows for the set means + non-artifact / outlier terms; half 1: the K cluster terms
       float f[MAXE];
       load_cols<MAXE>(t_z, f);
+      if (half == 0) {
 #pragma unroll
-      for (int i = 0; i < MAXE; ++i) if (i < E) xch[i * TILE + row] = f[i];
-      if (is_alt && my_var >= 0) {
-        float q = 0.f, q2 = 0.f;
+        for (int i = 0; i < MAXE; ++i) if (i < E) sts_f32(xch + (i * TILE + row) * 4, f[i]);
+        if (A.out.final_re && my_idx >= 0) {
 #pragma unroll
-        for (int e = 0; e < MAXE; ++e)
-          if (e < E) {
-            const float a = f[e] / HC->sigma[e], b = f[e] / (2.f * HC->sigma[e]);
-            q = fmaf(a, a, q); q2 = fmaf(b, b, q2);
-          }
-        xch[(MAXE + 0) * TILE + row] = HC->c_non - q / 2.f;
-        xch[(MAXE + 1) * TILE + row] = HC->c_out - q2 / 2.f;
-        for (int k = 0; k < K; ++k) {
-          const float* u = W + D.unit_ke + k * E;
-          float pr = 0.f;
-#pragma unroll
-          for (int e = 0; e < MAXE; ++e) if (e < E) pr = fmaf(f[e], __ldg(u + e), pr);
-          float o2 = 0.f;
-#pragma unroll
-          for (int e = 0; e < MAXE; ++e) if (e < E) { const float dd = f[e] - pr * __ldg(u + e); o2 = fmaf(dd, dd, o2); }
-          const float dist = sqrtf(o2);
-          const float ll_orth = HC->c_orth[k] - (dist * dist) / HC->two_tau2[k];
-          const float ll_par = HC->log_half_lambda[k] + logerfc((HC->shift[k] - pr) / HC->sqrt2_sigma[k]) +
-                               HC->half_lambda[k] * (HC->two_mu_plus[k] - 2.f * pr);
-          xch[(MAXE + 2 + k) * TILE + row] = ll_orth + ll_par;
+          for (int e = 0; e < MAXE; ++e) if (e < E) A.out.final_re[my_idx * E + e] = f[e];
         }
       }
-      if (A.out.final_re && my_idx >= 0) {
+      if (is_alt && my_var >= 0) {
+        if (half == 0) {
+          float q = 0.f, q2 = 0.f;
 #pragma unroll
-        for (int e = 0; e < MAXE; ++e) if (e < E) A.out.final_re[my_idx * E + e] = f[e];
+          for (int e = 0; e < MAXE; ++e)
+            if (e < E) {
+              const float a = f[e] / HC->sigma[e], b = f[e] / (2.f * HC->sigma[e]);
+              q = fmaf(a, a, q); q2 = fmaf(b, b, q2);
+            }
+          sts_f32(xch + ((MAXE + 0) * TILE + row) * 4, HC->c_non - q / 2.f);
+          sts_f32(xch + ((MAXE + 1) * TILE + row) * 4, HC->c_out - q2 / 2.f);
+        } else {
+          for (int k = 0; k < K; ++k) {
+            const float* u = W + D.unit_ke + k * E;
+            float pr = 0.f;
+#pragma unroll
+            for (int e = 0; e < MAXE; ++e) if (e < E) pr = fmaf(f[e], __ldg(u + e), pr);
+            float o2 = 0.f;
+#pragma unroll
+            for (int e = 0; e < MAXE; ++e) if (e < E) { const float dd = f[e] - pr * __ldg(u + e); o2 = fmaf(dd, dd, o2); }
+            const float dist = sqrtf(o2);
+            const float ll_orth = HC->c_orth[k] - (dist * dist) / HC->two_tau2[k];
+            const float ll_par = HC->log_half_lambda[k] + logerfc((HC->shift[k] - pr) / HC->sqrt2_sigma[k]) +
+                                 HC->half_lambda[k] * (HC->two_mu_plus[k] - 2.f * pr);
+            sts_f32(xch + ((MAXE + 2 + k) * TILE + row) * 4, ll_orth + ll_par);
+          }
+        }
       }
-      slot_barrier(slot);
+      named_barrier(slot_bar, 256);
       // ---- per-variant sums and outputs (ragged_sets.py:144-158; artifact_model.py:291-292) ----
-      for (int idx = row; idx < nv * 2 * E; idx += 128) {
-        const int j = idx / (2 * E), rem = idx - j * 2 * E, s = rem >= E ? 1 : 0, e = rem - s * E;
-        const int start = s ? M->alt_start[j] : M->ref_start[j], cnt = s ? M->alt_cnt[j] : M->ref_cnt[j];
+      for (int idx = srow; idx < nv * 2 * E; idx += 256) {
+        const int seg = (int)(((unsigned)idx * inv_e) >> 16), e = idx - seg * E;
+        const int j = seg >> 1, s = seg & 1;
+        const int start = (int)lds_u8((s ? m_alt_start : m_ref_start) + j), cnt = (int)lds_u8((s ? m_alt_cnt : m_ref_cnt) + j);
+        const unsigned src = xch + (e * TILE + start) * 4;
         float acc = 0.f;
-        for (int i = 0; i < cnt; ++i) acc += xch[e * TILE + start + i];
+        for (int i = 0; i < cnt; ++i) acc += lds_f32(src + i * 4);
         float* dst = s ? A.out.alt_means_be : A.out.ref_means_be;
         if (dst) dst[(long long)(v0 + j) * E + e] = acc / ((float)cnt + 1e-4f);
       }
-      if (row < nv) {
+      if (half == 1 && row < nv) {
         const int j = row;
         const long long v = v0 + j;
-        const int as = M->alt_start[j], ac = M->alt_cnt[j];
+        const int as = (int)lds_u8(m_alt_start + j), ac = (int)lds_u8(m_alt_cnt + j);
         float ll[MAXK + 2];
 #pragma unroll
         for (int k = 0; k < MAXK + 2; ++k) {
           float acc = 0.f;
-          if (k < K + 2)
-            for (int i = 0; i < ac; ++i) acc += xch[(MAXE + k) * TILE + as + i];
+          if (k < K + 2) {
+            const unsigned src = xch + ((MAXE + k) * TILE + as) * 4;
+            for (int i = 0; i < ac; ++i) acc += lds_f32(src + i * 4);
+          }
           ll[k] = acc;
         }
         float art_max = -INFINITY;
@@ -629,7 +757,7 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == MMA_WARP) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
 }
@@ -715,14 +843,20 @@ __device__ float tc_weight(const PmtModelDesc& D, const TcStep& o, const float* 
       if (kk < 0) return 0.f;
       return w[w_off + nn * Dm + kk] * w[BO.ln_w + kk];
     }
-    case PK_PROJ2: {   // ref and alt sets stacked along K: [t_ref (MAXH) | t_alt (MAXH) | is_ref, is_alt] (gated_mlp.py:197-198)
+    case PK_PROJ2: {   // ref and alt sets stacked along K (gated_mlp.py:197-198)
       const PmtBlockOffsets& BO = D.blocks[o.blk];
       const int nn = unperm64(n, DR, Dm);
       if (nn < 0) return 0.f;
-      if (k < MAXH) return k < H ? w[BO.p2_ref_w + nn * H + k] : 0.f;
-      if (k < 2 * MAXH) return k - MAXH < H ? w[BO.p2_alt_w + nn * H + (k - MAXH)] : 0.f;
-      if (k == 2 * MAXH) return w[BO.p2_ref_b + nn];
-      return w[BO.p2_alt_b + nn];
+      // operand layout: [t_ref k 0..5 | t_alt k 0..5 | t_ref k 6..10 | t_alt k 6..10 | is_ref | is_alt]
+      int unit = -1, set = 0;
+      if (k < 6) { unit = k; set = 0; }
+      else if (k < 12) { unit = k - 6; set = 1; }
+      else if (k < 17) { unit = 6 + (k - 12); set = 0; }
+      else if (k < 22) { unit = 6 + (k - 17); set = 1; }
+      else if (k == 22) return w[BO.p2_ref_b + nn];
+      else return w[BO.p2_alt_b + nn];
+      if (unit >= H) return 0.f;
+      return w[(set ? BO.p2_alt_w : BO.p2_ref_w) + nn * H + unit];
     }
     case PK_FINAL: {   // f = Q (W x + b + t): rotation and translation folded (euclidean_transformation.py:19-20)
       const int E = D.d_feat;
@@ -788,7 +922,7 @@ static int pad_to(int v, int m) { return (v + m - 1) / m * m; }
 // d_info + d_seq <= 32 (column 31 of every 64-wide operand carries the bias).
 bool pmt_tc_supported(const Plan& P) {
   const PmtModelDesc& d = P.d;
-  if (d.n_read_features > 63 || d.read_row_bytes > 14 || d.d_read > 31 || d.d_info + d.d_seq > 32 ||
+  if (d.n_read_features > 61 || d.read_row_bytes > 12 || d.d_read > 31 || d.d_info + d.d_seq > 32 ||
       d.d_model != d.d_read + d.d_info + d.d_seq || d.d_ffn / 2 > MAXH || d.d_ffn % 2 || d.d_feat > MAXE || d.n_clusters > MAXK ||
       d.n_blocks < 1)
     return false;
@@ -883,7 +1017,8 @@ size_t pmt_tc_workspace_bytes(const Plan& P, const PmtBatch* batch) {
 template <int PASSES>
 static int launch_tc(const PmtModelDesc& D, const TcPlan& T, const TcArgs& A, int grid, cudaStream_t st) {
   const int stage_bytes = PASSES == 3 ? T.slot_bytes : T.slot_bytes / 2;
-  const size_t fixed = 2 * XCH_ROWS * TILE * sizeof(float) + 2 * TILE * 2 * MAXH * sizeof(float) + sizeof(HeadConst) + sizeof(Shared) + 1024 + 64;
+  const size_t fixed = 2 * XCH_ROWS * TILE * sizeof(float) + 2 * SUMS_FLOATS * sizeof(float) + 2 * 2 * TILE * 2 * sizeof(float) +
+                       PMT_MAX_BLOCKS * BC_STRIDE * sizeof(float) + sizeof(HeadConst) + sizeof(Shared) + 1024 + 64;
   int n_stages = (int)((227 * 1024 - fixed) / stage_bytes);
   if (n_stages > NS_MAX) n_stages = NS_MAX;
   PMT_CHECK(n_stages >= 2, "tensor-core forward: weight ring does not fit in shared memory");
