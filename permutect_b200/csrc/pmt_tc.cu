@@ -3,11 +3,11 @@
 // One persistent CTA per SM keeps TWO tiles of 128 reads in flight (ping-pong): while the tensor core runs a
 // layer of tile A, the epilogue warps of tile B turn the previous accumulator into the next operand.
 //
-//   warps 0-3   epilogue of slot 0: thread r owns read (row) r of the tile -- TMEM lane r
-//   warps 4-7   epilogue of slot 1
-//   warp  8     MMA issuer: warp-uniform loop, one elected lane issues the tcgen05.mma chains (kind::tf32,
-//               M = 128, A operand in TMEM, B = weights in shared memory) and commits to mbarriers
-//   warp  9     weight loader: streams every layer's pre-swizzled weight image through a ring of shared-memory
+//   warps 0-7   epilogue of slot 0: two threads per read (row) r of the tile -- TMEM lane r, 32 columns each
+//   warps 8-15  epilogue of slot 1
+//   warps 16-17 MMA issuers, one per slot: warp-uniform loop, one elected lane issues the tcgen05.mma chains
+//               (kind::tf32, M = 128, A operand in TMEM, B = weights in shared memory) and commits to mbarriers
+//   warp  18    weight loader: streams every layer's pre-swizzled weight image through a ring of shared-memory
 //               stages with cp.async.bulk (mbarrier complete_tx); both slots consume a stage before it is refilled
 //
 // Tensor memory per slot (256 columns): X = residual stream (64), Z = layer output (64), A_hi / A_lo = next
@@ -31,8 +31,8 @@
 namespace pmt {
 namespace tc {
 
-constexpr int THREADS = 576;      // 16 epilogue warps (2 slots x 2 column halves x 4 lane quarters) + MMA warp + loader warp
-constexpr int MMA_WARP = 16, LOAD_WARP = 17;
+constexpr int THREADS = 608;      // 16 epilogue warps (2 slots x 2 column halves x 4 lane quarters) + 2 MMA warps + loader warp
+constexpr int MMA_WARP = 16, LOAD_WARP = 18;
 constexpr int SUMS_FLOATS = 2 * TILE * 11;   // per slot: [segment][MAXH]
 constexpr int MAX_STEPS = 64;
 constexpr int COL_X = 0, COL_Z = 64, COL_AHI = 128, COL_ALO = 192, SLOT_COLS = 256;
@@ -285,7 +285,7 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
   const float* W = A.wflat;
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) { mbar_init(smem_addr(&S->bar_a[s]), 8); mbar_init(smem_addr(&S->bar_d[s]), 1); }
-    for (int i = 0; i < n_stages; ++i) { mbar_init(smem_addr(&S->wfull[i]), 1); mbar_init(smem_addr(&S->wfree[i]), 1); }
+    for (int i = 0; i < n_stages; ++i) { mbar_init(smem_addr(&S->wfull[i]), 1); mbar_init(smem_addr(&S->wfree[i]), 2); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     head_constants(D, W, HC);
   }
@@ -337,8 +337,13 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
       }
     }
     __syncwarp();
-  } else if (warp == MMA_WARP) {
-    // ===================================== MMA issuer =====================================
+  } else if (warp >= MMA_WARP) {
+    // ===================================== MMA issuers: one warp per slot =====================================
+    // Each warp blocks only on ITS slot's operand barrier, so the two slots drift apart freely and one slot's
+    // MMA overlaps the other slot's epilogue; a weight stage is released when both warps have committed past it.
+    const int s = warp - MMA_WARP;
+    const unsigned tb = tmem_base + s * SLOT_COLS;
+    const unsigned bar_a = smem_addr(&S->bar_a[s]), bar_d = smem_addr(&S->bar_d[s]);
     int stage = 0;
     unsigned wparity = 0, aparity = 0;
     for (int round = 0; round < rounds; ++round) {
@@ -350,24 +355,20 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
         const uint64_t b_hi = smem_desc(wb), b_lo = smem_desc(wb + o_img_bytes);
         const unsigned kb_stride16 = (unsigned)(oN * 128) >> 4;
         const bool lo_pass = step > 0 || l0_lo;
+        const unsigned d = tb + (o_dst_x ? COL_X : COL_Z);
         mbar_wait(smem_addr(&S->wfull[stage]), wparity);
-#pragma unroll 1
-        for (int s = 0; s < 2; ++s) {
-          const unsigned tb = tmem_base + s * SLOT_COLS;
-          const unsigned d = tb + (o_dst_x ? COL_X : COL_Z);
-          mbar_wait(smem_addr(&S->bar_a[s]), aparity);
-          tc_fence_after();
-          if (elect_one()) {
-            switch (oKS) {
-              case 3: issue_chain<3, PASSES>(d, tb + COL_AHI, tb + COL_ALO, b_hi, b_lo, kb_stride16, idesc, o_dst_x, lo_pass); break;
-              case 4: issue_chain<4, PASSES>(d, tb + COL_AHI, tb + COL_ALO, b_hi, b_lo, kb_stride16, idesc, o_dst_x, lo_pass); break;
-              default: issue_chain<8, PASSES>(d, tb + COL_AHI, tb + COL_ALO, b_hi, b_lo, kb_stride16, idesc, o_dst_x, lo_pass); break;
-            }
-            mma_commit(smem_addr(&S->bar_d[s]));
-            if (s == 1) mma_commit(smem_addr(&S->wfree[stage]));
+        mbar_wait(bar_a, aparity);
+        tc_fence_after();
+        if (elect_one()) {
+          switch (oKS) {
+            case 3: issue_chain<3, PASSES>(d, tb + COL_AHI, tb + COL_ALO, b_hi, b_lo, kb_stride16, idesc, o_dst_x, lo_pass); break;
+            case 4: issue_chain<4, PASSES>(d, tb + COL_AHI, tb + COL_ALO, b_hi, b_lo, kb_stride16, idesc, o_dst_x, lo_pass); break;
+            default: issue_chain<8, PASSES>(d, tb + COL_AHI, tb + COL_ALO, b_hi, b_lo, kb_stride16, idesc, o_dst_x, lo_pass); break;
           }
-          __syncwarp();
+          mma_commit(bar_d);
+          mma_commit(smem_addr(&S->wfree[stage]));
         }
+        __syncwarp();
         aparity ^= 1;
         if (++stage == n_stages) { stage = 0; wparity ^= 1; }
       }
