@@ -943,7 +943,7 @@ extern "C" int pmt_backward(const PmtModelDesc* desc, const float* weights, cons
 
   cudaMemsetAsync(partials, 0, (size_t)kBwdGrid * desc->n_params * sizeof(float), st);
   pmt_launch_prepare(P, G, weights, image, st);
-  pmt_launch_variant_kernels(P, G, weights, image, batch, info_seq, st);
+  pmt_launch_variant_kernels(P, G, weights, image, batch, info_seq, PMT_PRECISION_FP32, nullptr, st);
 
   int dev = 0, n_sm = 148;
   cudaGetDevice(&dev);

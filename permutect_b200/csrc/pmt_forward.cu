@@ -529,7 +529,7 @@ extern "C" size_t pmt_workspace_size(const PmtModelDesc* desc, const PmtBatch* b
   bytes += pmt_image_bytes(P, G);
   if (batch) bytes += (size_t)batch->n_variants * (desc->d_info + desc->d_seq) * sizeof(float) + 256;  // info_seq when caller passes none
   bytes += long_scratch_floats_per_cta(P, batch) * sizeof(float) * 148 + 256;
-  bytes += pmt_tc_workspace_bytes(P, batch) + 1024;
+  bytes += pmt_tc_workspace_bytes(P, batch) + pmt_cnn_tc_image_bytes(P) + 256 + 1024;
   if (for_backward) bytes += pmt_backward_workspace_bytes(P, batch);
   return bytes;
 }
@@ -552,7 +552,7 @@ int pmt_launch_prepare(const Plan& P, const CnnGeom& G, const float* weights, fl
 }
 
 int pmt_launch_variant_kernels(const Plan& P, const CnnGeom& G, const float* weights, const float* image,
-                               const PmtBatch* batch, float* info_seq, cudaStream_t st) {
+                               const PmtBatch* batch, float* info_seq, int mode, unsigned char* cnn_tc_image, cudaStream_t st) {
   const int B = batch->n_variants;
   {
     const int in_rows = P.d.n_info_features > PMT_MAX_DIM ? PMT_MAX_INFO_DIM : PMT_MAX_DIM;
@@ -561,7 +561,13 @@ int pmt_launch_variant_kernels(const Plan& P, const CnnGeom& G, const float* wei
     info_mlp_kernel<<<(B + TILE - 1) / TILE, NTHREADS, smem, st>>>(P, weights, image, batch->info, batch->info_kind,
                                                                    batch->info_stride, B, info_seq);
   }
-  {
+  if (mode != PMT_PRECISION_FP32 && cnn_tc_image && pmt_cnn_tc_supported(P)) {
+    // tensor-core haplotype CNN (pmt_cnn_tc.cu); shapes outside its envelope run the FP32 SIMT kernel below
+    int dev = 0, n_sm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (pmt_launch_cnn_tc(P, weights, batch, info_seq, cnn_tc_image, n_sm, mode, st)) return 1;
+  } else {
     const size_t smem = (size_t)(2 * G.buf_floats + G.img_total + 2 * G.vt * 256) * sizeof(float);
     cudaFuncSetAttribute(hap_cnn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int grid = (B + G.vt - 1) / G.vt;
@@ -599,7 +605,11 @@ extern "C" int pmt_forward(const PmtModelDesc* desc, const float* weights, const
   if (!info_seq) info_seq = reinterpret_cast<float*>(ws + 256 + pmt_image_bytes(P, G));
   cudaMemsetAsync(counter, 0, 256, st);
   pmt_launch_prepare(P, G, weights, image, st);
-  pmt_launch_variant_kernels(P, G, weights, image, batch, info_seq, st);
+  const int mode = pmt_precision_mode();
+  unsigned char* tc_image = reinterpret_cast<unsigned char*>(ws) + workspace_bytes - pmt_tc_workspace_bytes(P, batch) - 512;
+  unsigned char* cnn_tc_image = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(tc_image) - pmt_cnn_tc_image_bytes(P) - 256) & ~uintptr_t(255));
+  if (pmt_launch_variant_kernels(P, G, weights, image, batch, info_seq, mode, cnn_tc_image, st)) return 1;
 
   int dev = 0, n_sm = 148;
   cudaGetDevice(&dev);
@@ -612,10 +622,8 @@ extern "C" int pmt_forward(const PmtModelDesc* desc, const float* weights, const
   cudaFuncSetAttribute(reads_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int n_claims = (batch->n_variants + P.claim_variants - 1) / P.claim_variants;
   const int grid = n_claims < n_sm ? n_claims : n_sm;
-  const int mode = pmt_precision_mode();
   if (mode != PMT_PRECISION_FP32) {
     PMT_CHECK(pmt_tc_supported(P), "this model shape is outside the tensor-core kernel's envelope; use PMT_PRECISION_FP32");
-    unsigned char* tc_image = reinterpret_cast<unsigned char*>(ws) + workspace_bytes - pmt_tc_workspace_bytes(P, batch) - 512;
     PmtOutputs o2 = *out;
     o2.info_seq_be = info_seq;
     if (pmt_launch_reads_tc(P, weights, batch, &o2, tc_image, n_sm, mode, st)) return 1;
