@@ -27,100 +27,114 @@ namespace cnntc {
 
 using namespace pmt::tc;
 
-constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARPS = 16;
 constexpr int THREADS = 32 * (EPI_WARPS + 1);
 constexpr int MMA_WARP = EPI_WARPS;
 constexpr int MAX_LAYERS = 10;
 constexpr int MAX_CHUNKS = 4;
-constexpr int CHUNK_COLS = 64;
-constexpr int PLANE_ROWS = 320;
+constexpr int CHUNK_COLS = 128;              // TMEM columns per chunk accumulator: [hi part N | lo part N]
+constexpr int PLANE_ROWS = 344;
 constexpr int PLANE_BYTES = PLANE_ROWS * 16;
 constexpr int BUF_BYTES = 8 * PLANE_BYTES;   // one activation buffer: 32 channels
 constexpr int C0 = 10;                       // one-hot channels: 2 haplotypes x 5 codes
-constexpr int MAX_CODES = 2048;              // staged haplotype codes per group (G * 2L)
+constexpr int MAX_ITEMS = 24;                // (layer, chunk) work items per group
+constexpr int MAX_TASKS = 8;                 // one-hot entries per lane in the im2col scatter
 
 struct Layer {
   int first;      // im2col'd one-hot conv
   int taps;       // shifted-window convs: kernel size; first: number of input positions per row (ksize + dup)
   int ksteps;     // first: k-steps of 8 columns
-  int N;          // MMA N
+  int N;          // output columns of the MMA (32, or 64 when dup)
   int dup, pool2; // fused MaxPool(2,1) after the first conv / MaxPool(2,2)
   int L_in, L_out, L_pool, L_next;
+  int inv_L;      // ceil(65536 / L_in) + : row / L_in == (row * inv_L) >> 16 for rows < 512
   int act, to_global, out_ch;
   int img_off, img_bytes;
   // packing
   int op, in_ch, ksize, flat_len, scale_in, is_linear;
 };
 
-struct Plan {
-  int n_layers, G, L0, image_bytes;
-  int n_chunks[MAX_LAYERS];
-  Layer layer[MAX_LAYERS];
+struct Item {
+  int layer, chunk;
+  int need;   // index of the last done_bar this item's MMAs must have observed (0 = im2col, 1 + i = epilogue of item i)
 };
 
-__device__ __forceinline__ uint64_t desc_ns(unsigned addr, unsigned lbo_bytes) {
-  // K-major, no swizzle: LBO = distance between K-adjacent core matrices, SBO = 128 B between 8-row groups
-  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)(lbo_bytes >> 4) << 16) | (8ull << 32) | (1ull << 46);
-}
-__device__ __forceinline__ void mma_ss(unsigned tmem_d, uint64_t adesc, uint64_t bdesc, unsigned idesc, unsigned accumulate) {
+struct Plan {
+  int n_layers, n_items, G, L0, image_bytes;
+  int n_chunks[MAX_LAYERS];
+  Layer layer[MAX_LAYERS];
+  Item item[MAX_ITEMS];
+};
+
+// Shared-memory matrix descriptor, K-major, no swizzle.  Low word: start address >> 4 | (LBO >> 4) << 16 with LBO = the
+// distance between K-adjacent core matrices; high word (constant): SBO = 128 B between 8-row groups, descriptor version 1.
+constexpr unsigned DESC_HI = 8u | (1u << 14);
+__device__ __forceinline__ unsigned desc_lo(unsigned addr, unsigned lbo_bytes) { return ((addr >> 4) & 0x3FFFu) | ((lbo_bytes >> 4) << 16); }
+template <unsigned IDESC>
+__device__ __forceinline__ void mma_ss(unsigned tmem_d, unsigned a_lo32, unsigned b_lo32, unsigned accumulate) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %3, 0;\n\t"
+      "mov.b64 da, {%1, %4};\n\t"
+      "mov.b64 db, {%2, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo32), "r"(b_lo32), "r"(accumulate), "n"(DESC_HI), "n"(IDESC)
       : "memory");
 }
-__device__ __forceinline__ unsigned make_idesc(int N) {
+__host__ __device__ constexpr unsigned make_idesc(int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(N >> 3) << 17) | ((128u >> 4) << 24);
 }
 
-// shifted-window conv: TAPS x 4 k-steps; all descriptor offsets are compile-time constants (16-byte units)
-template <int TAPS, int N, int PASSES>
-__device__ __forceinline__ void issue_shifted(unsigned d, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo, unsigned idesc) {
-#pragma unroll
-  for (int t = 0; t < TAPS; ++t) {
+// Split-precision scheme (PASSES == 3): the weight image stacks [W_hi ; W_lo] along N, so ONE MMA of width 2N computes
+// A_hi.W_hi (columns [0, N)) and A_hi.W_lo (columns [N, 2N)) from a single read of the A rows -- operand fetch from shared
+// memory, not the tensor pipe, bounds these small-N MMAs -- and a second MMA of width N adds A_lo.W_hi to columns [0, N).
+// The epilogue sums the two column ranges.  PASSES == 1 uses the W_hi rows only.
+//
+// shifted-window conv: taps x 4 k-steps.  The tap loop is a warp-uniform runtime loop (no jump table: an indirect
+// branch would push every descriptor out of the uniform registers); inside a tap all offsets are compile-time constants.
+template <int PASSES>
+__device__ __forceinline__ void issue_shifted(int taps, unsigned d, unsigned a_hi, unsigned a_lo, unsigned b) {
+  constexpr int R = 64;   // image rows per plane: 32 hi + 32 lo
+#pragma unroll 1
+  for (int t = 0; t < taps; ++t) {
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
-      const uint64_t ao = (uint64_t)(t + 2 * ks * (PLANE_BYTES / 16));
-      const uint64_t bo = (uint64_t)(t * 8 * N + 2 * ks * N);
-      mma_ss(d, a_hi + ao, b_hi + bo, idesc, (t | ks) != 0 ? 1u : 0u);
+      const unsigned ao = (unsigned)(2 * ks * (PLANE_BYTES / 16));
+      const unsigned bo = (unsigned)(2 * ks * R);
+      const unsigned acc = (ks == 0) ? (t > 0 ? 1u : 0u) : 1u;
       if (PASSES == 3) {
-        mma_ss(d, a_lo + ao, b_hi + bo, idesc, 1u);
-        mma_ss(d, a_hi + ao, b_lo + bo, idesc, 1u);
+        mma_ss<make_idesc(64)>(d, a_hi + ao, b + bo, acc);
+        mma_ss<make_idesc(32)>(d, a_lo + ao, b + bo, 1u);
+      } else {
+        mma_ss<make_idesc(32)>(d, a_hi + ao, b + bo, acc);
       }
     }
-  }
-}
-template <int N, int PASSES>
-__device__ __forceinline__ void issue_shifted_n(int taps, unsigned d, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo) {
-  const unsigned idesc = make_idesc(N);
-  switch (taps) {
-    case 1: issue_shifted<1, N, PASSES>(d, a_hi, a_lo, b_hi, b_lo, idesc); break;
-    case 2: issue_shifted<2, N, PASSES>(d, a_hi, a_lo, b_hi, b_lo, idesc); break;
-    case 3: issue_shifted<3, N, PASSES>(d, a_hi, a_lo, b_hi, b_lo, idesc); break;
-    case 4: issue_shifted<4, N, PASSES>(d, a_hi, a_lo, b_hi, b_lo, idesc); break;
-    case 5: issue_shifted<5, N, PASSES>(d, a_hi, a_lo, b_hi, b_lo, idesc); break;
-    case 6: issue_shifted<6, N, PASSES>(d, a_hi, a_lo, b_hi, b_lo, idesc); break;
-    case 7: issue_shifted<7, N, PASSES>(d, a_hi, a_lo, b_hi, b_lo, idesc); break;
-    default: issue_shifted<8, N, PASSES>(d, a_hi, a_lo, b_hi, b_lo, idesc); break;
+    a_hi += 1; a_lo += 1; b += 8 * R;
   }
 }
 // first conv: one-hot im2col rows (exact: no A lo pass), K = 8 * KS columns over consecutive planes
 template <int N, int PASSES>
-__device__ __forceinline__ void issue_first(int ksteps, unsigned d, uint64_t a, uint64_t b_hi, uint64_t b_lo) {
-  const unsigned idesc = make_idesc(N);
+__device__ __forceinline__ void issue_first(int ksteps, unsigned d, unsigned a, unsigned b) {
+  constexpr int R = 2 * N;
+  constexpr unsigned idesc = make_idesc(PASSES == 3 ? 2 * N : N);
 #pragma unroll
   for (int ks = 0; ks < 8; ++ks) {
     if (ks < ksteps) {
-      const uint64_t ao = (uint64_t)(2 * ks * (PLANE_BYTES / 16)), bo = (uint64_t)(2 * ks * N);
-      mma_ss(d, a + ao, b_hi + bo, idesc, ks != 0 ? 1u : 0u);
-      if (PASSES == 3) mma_ss(d, a + ao, b_lo + bo, idesc, 1u);
+      const unsigned ao = (unsigned)(2 * ks * (PLANE_BYTES / 16)), bo = (unsigned)(2 * ks * R);
+      mma_ss<idesc>(d, a + ao, b + bo, ks != 0 ? 1u : 0u);
     }
   }
 }
 
+struct ItemDev {   // per-item MMA operands, computed once per CTA
+  unsigned a_hi, a_lo, b, d;
+  int first, count, N, need;
+};
+
 struct Bars {
-  unsigned long long in_bar, acc_bar[MAX_CHUNKS];
+  unsigned long long done_bar[MAX_ITEMS + 1];   // [0]: im2col rows written; [1 + i]: epilogue of item i finished (16 warps)
+  unsigned long long acc_bar[MAX_ITEMS];        // accumulator of item i complete (tcgen05.commit)
+  ItemDev item[MAX_ITEMS];
   unsigned tmem_base;
   int pad_;
 };
@@ -129,23 +143,27 @@ template <int PASSES>
 __global__ void __launch_bounds__(THREADS, 1)
 hap_cnn_tc_kernel(const __grid_constant__ Plan TP, const unsigned char* __restrict__ image, const float* __restrict__ wflat,
                   const __grid_constant__ PmtModelDesc D, const void* __restrict__ haps, int hap_kind, long long hap_stride,
-                  int n_variants, float* __restrict__ info_seq) {
+                  int n_variants, float* __restrict__ info_seq, long long* __restrict__ trace) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* p = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const unsigned act = smem_addr(p); p += 2 * BUF_BYTES;                 // hi buffer, then lo buffer (planes 8..15)
   unsigned char* img_s = p; p += TP.image_bytes;
   float* bias_s = reinterpret_cast<float*>(p); p += MAX_LAYERS * 32 * sizeof(float);
-  signed char* codes = reinterpret_cast<signed char*>(p); p += MAX_CODES;
   Bars* S = reinterpret_cast<Bars*>((reinterpret_cast<uintptr_t>(p) + 15) & ~uintptr_t(15));
 
   const int tid = threadIdx.x;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int lane = tid & 31;
-  const int n_layers = TP.n_layers, G = TP.G, L0 = TP.L0;
+  const int n_layers = TP.n_layers, n_items = TP.n_items, G = TP.G, L0 = TP.L0;
+  // optional cycle trace of CTA 0 (profiles/trace_cnn.py): entries of (event id, clock) per recording thread
+  int tr_n = 0;
+  const bool tr_on = trace != nullptr && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 5 || warp == MMA_WARP);
+  long long* tr = trace + (warp == MMA_WARP ? 2 : (warp == 5 ? 1 : 0)) * 1024;
+  auto TR = [&](int id) { if (tr_on && tr_n < 510) { tr[2 * tr_n] = id; tr[2 * tr_n + 1] = clock64(); ++tr_n; } };
 
   if (tid == 0) {
-    mbar_init(smem_addr(&S->in_bar), EPI_WARPS);
-    for (int c = 0; c < MAX_CHUNKS; ++c) mbar_init(smem_addr(&S->acc_bar[c]), 1);
+    for (int i = 0; i <= n_items; ++i) mbar_init(smem_addr(&S->done_bar[i]), EPI_WARPS);
+    for (int i = 0; i < n_items; ++i) mbar_init(smem_addr(&S->acc_bar[i]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // resident weight images (no-swizzle K-major planes, built by pack_cnn_tc_kernel) and biases
@@ -157,7 +175,7 @@ hap_cnn_tc_kernel(const __grid_constant__ Plan TP, const unsigned char* __restri
     bias_s[i] = (n < Ly.out_ch && b_off >= 0) ? __ldg(wflat + b_off + n) : 0.f;
   }
   if (warp == MMA_WARP) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&S->tmem_base)), "r"(256));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&S->tmem_base)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -166,177 +184,190 @@ hap_cnn_tc_kernel(const __grid_constant__ Plan TP, const unsigned char* __restri
   tc_fence_after();
   const unsigned tmem_base = __shfl_sync(0xffffffffu, S->tmem_base, 0);
   const int n_groups = (n_variants + G - 1) / G;
-  const unsigned img_a = smem_addr(img_s);
+  if (tid < n_items) {
+    const Item& I = TP.item[tid];
+    const Layer& Ly = TP.layer[I.layer];
+    ItemDev& o = S->item[tid];
+    o.a_hi = desc_lo(act + I.chunk * 128 * 16, PLANE_BYTES);
+    o.a_lo = desc_lo(act + BUF_BYTES + I.chunk * 128 * 16, PLANE_BYTES);
+    o.b = desc_lo(smem_addr(img_s) + Ly.img_off, 2 * Ly.N * 16);
+    o.d = tmem_base + I.chunk * CHUNK_COLS;
+    o.first = Ly.first; o.count = Ly.first ? Ly.ksteps : Ly.taps; o.N = Ly.N; o.need = I.need;
+  }
+  __syncthreads();
 
   if (warp == MMA_WARP) {
     // ===================================== MMA issuer =====================================
-    unsigned in_par = 0;
-    for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
-      for (int l = 0; l < n_layers; ++l) {
-        const Layer& Ly = TP.layer[l];
-        const int nc = TP.n_chunks[l], N = Ly.N, taps = Ly.taps, first = Ly.first, ksteps = Ly.ksteps;
-        const unsigned b_addr = img_a + Ly.img_off;
-        const uint64_t b_hi = desc_ns(b_addr, N * 16), b_lo = desc_ns(b_addr + Ly.img_bytes, N * 16);
-        mbar_wait(smem_addr(&S->in_bar), in_par);
-        in_par ^= 1;
+    // Items (layer, chunk) are issued in order; item i waits only for the epilogue items that produce the input rows it
+    // reads (need), so a layer starts while the previous layer's last chunks are still in their epilogue.
+    unsigned gpar = 0;
+    for (int g = blockIdx.x; g < n_groups; g += gridDim.x, gpar ^= 1) {
+      int waited = 0;   // done_bar[0 .. waited) observed in this group
+      for (int it = 0; it < n_items; ++it) {
+        const ItemDev I = S->item[it];
+        TR(100 + it);
+        for (; waited <= I.need; ++waited) mbar_wait(smem_addr(&S->done_bar[waited]), gpar);
         tc_fence_after();
+        TR(130 + it);
         if (elect_one()) {
-          for (int c = 0; c < nc; ++c) {
-            const unsigned d = tmem_base + c * CHUNK_COLS;
-            const uint64_t a_hi = desc_ns(act + c * 128 * 16, PLANE_BYTES), a_lo = desc_ns(act + BUF_BYTES + c * 128 * 16, PLANE_BYTES);
-            if (first) {
-              if (N == 64) issue_first<64, PASSES>(ksteps, d, a_hi, b_hi, b_lo);
-              else issue_first<32, PASSES>(ksteps, d, a_hi, b_hi, b_lo);
-            } else {
-              issue_shifted_n<32, PASSES>(taps, d, a_hi, a_lo, b_hi, b_lo);
-            }
-            mma_commit(smem_addr(&S->acc_bar[c]));
+          if (I.first) {
+            if (I.N == 64) issue_first<64, PASSES>(I.count, I.d, I.a_hi, I.b);
+            else issue_first<32, PASSES>(I.count, I.d, I.a_hi, I.b);
+          } else {
+            issue_shifted<PASSES>(I.count, I.d, I.a_hi, I.a_lo, I.b);
           }
+          mma_commit(smem_addr(&S->acc_bar[it]));
         }
         __syncwarp();
+        TR(160 + it);
       }
     }
   } else {
     // ===================================== epilogue warps =====================================
-    const int grp = warp >> 2, quarter = warp & 3;
+    // every item is processed by all 16 warps: warp = (column quarter, lane quarter); a thread owns 8 channels of one row
+    const int quarter = warp & 3, cq = warp >> 2;
     const int row_c = quarter * 32 + lane;     // row inside a chunk = TMEM lane
-    const unsigned trow = tmem_base + ((unsigned)(quarter * 32) << 16);
-    unsigned acc_par = 0;                      // bit c: parity of acc_bar[c]
-    unsigned in_par = 0;
-    bool arrived = false;
-    // a warp may only arrive for the next phase of in_bar once the previous phase has completed (a warp without a
-    // chunk in some layer would otherwise arrive twice in one phase)
-    auto signal_input_ready = [&]() {
-      if (arrived) { mbar_wait(smem_addr(&S->in_bar), in_par); in_par ^= 1; }
-      arrived = true;
+    const unsigned trow = tmem_base + ((unsigned)(quarter * 32) << 16) + cq * 8;
+    const Layer& L0y = TP.layer[0];
+    const int rows0 = TP.n_chunks[0] * 128 < PLANE_ROWS ? TP.n_chunks[0] * 128 : PLANE_ROWS;
+    const int rpw = (rows0 + EPI_WARPS - 1) / EPI_WARPS;            // im2col rows per warp
+    const int r_lo = warp * rpw, r_hi = min(rows0, r_lo + rpw);
+    const int planes0 = 2 * L0y.ksteps, taps0 = L0y.taps;
+    // im2col scatter tasks of this lane: (row, input position, haplotype) -> one 1.0 of the one-hot row.  The mapping is
+    // the same for every group; the codes of the NEXT group are fetched one group ahead and stay in registers.
+    unsigned t_row[MAX_TASKS];   // shared address of the row (plane 0), 0 = no task
+    int t_col[MAX_TASKS], t_var[MAX_TASKS], t_off[MAX_TASKS];
+#pragma unroll
+    for (int k = 0; k < MAX_TASKS; ++k) {
+      const int task = lane + 32 * k;
+      const int h = task & 1, rt = task >> 1;
+      const int tt = rt % taps0, j = r_lo + rt / taps0;
+      const int v = j / L0, pos = j - v * L0 + tt;
+      const bool ok = j < r_hi && pos < L0;
+      t_row[k] = ok ? act + j * 16 : 0u;
+      t_col[k] = tt * C0 + h;
+      t_var[k] = ok ? v : (1 << 30);
+      t_off[k] = ok ? (int)(v * hap_stride) + h * L0 + pos : 0;
+    }
+    int codes[MAX_TASKS];
+    auto fetch_codes = [&](int g) {
+      const long long base = (long long)g * G * hap_stride;
+      const int nv = g < n_groups ? min(G, n_variants - g * G) : 0;
+      if (hap_kind == PMT_I64) {
+#pragma unroll
+        for (int k = 0; k < MAX_TASKS; ++k) codes[k] = t_var[k] < nv ? (int)__ldg(reinterpret_cast<const long long*>(haps) + base + t_off[k]) : -1;
+      } else {
+#pragma unroll
+        for (int k = 0; k < MAX_TASKS; ++k) codes[k] = t_var[k] < nv ? (int)__ldg(reinterpret_cast<const short*>(haps) + base + t_off[k]) : -1;
+      }
+    };
+    fetch_codes(blockIdx.x);
+    unsigned gpar = 0;
+    for (int g = blockIdx.x; g < n_groups; g += gridDim.x, gpar ^= 1) {
+      const int v0 = g * G, nv = min(G, n_variants - v0);
+      TR(1);
+      // ---- im2col rows of the first conv (batch.py:115-130): zero this warp's rows, then scatter the ones ----
+      for (int pl = 0; pl < planes0; ++pl)
+        for (int j = r_lo + lane; j < r_hi; j += 32) sts128(act + pl * PLANE_BYTES + j * 16, make_float4(0.f, 0.f, 0.f, 0.f));
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < MAX_TASKS; ++k) {
+        if ((unsigned)codes[k] < 5u) {
+          const int col = t_col[k] + 2 * codes[k];
+          sts_f32(t_row[k] + (col >> 2) * PLANE_BYTES + (col & 3) * 4, 1.f);
+        }
+      }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_addr(&S->in_bar));
-    };
-    const int L2 = 2 * L0;
-    for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
-      const int v0 = g * G, nv = min(G, n_variants - v0);
-      // ---- haplotype codes of the group, then the im2col rows of the first conv (batch.py:115-130) ----
-      for (int idx = tid; idx < nv * L2; idx += 32 * EPI_WARPS) {
-        const int v = idx / L2, hp = idx - v * L2;
-        const long long off = (long long)(v0 + v) * hap_stride + hp;
-        const int code = hap_kind == PMT_I64 ? (int)__ldg(reinterpret_cast<const long long*>(haps) + off)
-                                             : (int)__ldg(reinterpret_cast<const short*>(haps) + off);
-        codes[idx] = (signed char)((code >= 0 && code < 5) ? code : -1);
-      }
-      named_barrier(1, 32 * EPI_WARPS);
-      {
-        const Layer& Ly = TP.layer[0];
-        const int rows = TP.n_chunks[0] * 128 < PLANE_ROWS ? TP.n_chunks[0] * 128 : PLANE_ROWS;
-        const int planes = 2 * Ly.ksteps;
-        for (int j = tid; j < rows; j += 32 * EPI_WARPS) {
-          const unsigned rbase = act + j * 16;
-          for (int pl = 0; pl < planes; ++pl) sts128(rbase + pl * PLANE_BYTES, make_float4(0.f, 0.f, 0.f, 0.f));
-          const int v = j / L0, pos0 = j - v * L0;
-          if (v < nv) {
-            for (int tt = 0; tt < Ly.taps; ++tt) {
-              const int pos = pos0 + tt;
-              if (pos < L0) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                  const int c = codes[v * L2 + h * L0 + pos];
-                  if (c >= 0) {
-                    const int k = tt * C0 + 2 * c + h;
-                    sts_f32(rbase + (k >> 2) * PLANE_BYTES + (k & 3) * 4, 1.f);
-                  }
-                }
-              }
-            }
-          }
-        }
-      }
-      signal_input_ready();
+      if (lane == 0) mbar_arrive(smem_addr(&S->done_bar[0]));
+      TR(2);
+      fetch_codes(g + gridDim.x);
 
-      for (int l = 0; l < n_layers; ++l) {
+      for (int it = 0; it < n_items; ++it) {
+        const Item& I = TP.item[it];
+        const int l = I.layer, c = I.chunk;
         const Layer& Ly = TP.layer[l];
-        const int nc = TP.n_chunks[l];
-        const int L_in = Ly.L_in, L_next = Ly.L_next;
-        const unsigned bias_a = smem_addr(bias_s + l * 32);
-        for (int c = grp; c < nc; c += 2) {
-          mbar_wait(smem_addr(&S->acc_bar[c]), (acc_par >> c) & 1u);
-          acc_par ^= 1u << c;
-          tc_fence_after();
-          float x[32];
-          {
-            unsigned r[32];
-            tmem_ld32(trow + c * CHUNK_COLS, r);
-            if (Ly.dup) {
-              unsigned r2[32];
-              tmem_ld32(trow + c * CHUNK_COLS + 32, r2);
-              tmem_wait_ld();
+        const int N = Ly.N;
+        const int j = c * 128 + row_c;
+        const int v = (j * Ly.inv_L) >> 16, pos = j - v * Ly.L_in;
+        int pp = pos;
+        bool valid = v < nv;
+        if (Ly.pool2) { valid = valid && !(pos & 1); pp = pos >> 1; }
+        valid = valid && pp < Ly.L_pool;
+        const float4 b0 = lds128(smem_addr(bias_s + l * 32 + cq * 8)), b1 = lds128(smem_addr(bias_s + l * 32 + cq * 8 + 4));
+        const unsigned tcol = trow + c * CHUNK_COLS;
+        TR(200 + it);
+        mbar_wait(smem_addr(&S->acc_bar[it]), gpar);
+        tc_fence_after();
+        TR(230 + it);
+        float x[8];
+        {
+          unsigned r[8], rl[8];
+          tmem_ld8(tcol, r);
+          if (PASSES == 3) tmem_ld8(tcol + N, rl);
+          if (Ly.dup) {
+            unsigned r2[8], rl2[8];
+            tmem_ld8(tcol + 32, r2);
+            if (PASSES == 3) tmem_ld8(tcol + N + 32, rl2);
+            tmem_wait_ld();
 #pragma unroll
-              for (int i = 0; i < 32; ++i) x[i] = fmaxf(__uint_as_float(r[i]), __uint_as_float(r2[i]));
-            } else {
-              tmem_wait_ld();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(r[i]);
-            }
-          }
-          if (Ly.pool2) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) x[i] = fmaxf(x[i], __shfl_xor_sync(0xffffffffu, x[i], 1));
-          }
-          const int j = c * 128 + row_c;
-          const int v = j / L_in, pos = j - v * L_in;
-          int pp = pos;
-          bool valid = v < nv;
-          if (Ly.pool2) { valid = valid && !(pos & 1); pp = pos >> 1; }
-          valid = valid && pp < Ly.L_pool;
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 b = lds128(bias_a + i * 4);
-            x[i] += b.x; x[i + 1] += b.y; x[i + 2] += b.z; x[i + 3] += b.w;
-          }
-          if (Ly.to_global) {
-            if (valid) {
-              float* dst = info_seq + (long long)(v0 + v) * (D.d_info + D.d_seq) + D.d_info;
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (i < Ly.out_ch) dst[i] = Ly.act == PMT_ACT_SELU ? SELU_SCALE * selu_u(x[i]) : x[i];
+            for (int i = 0; i < 8; ++i) {
+              const float u0 = PASSES == 3 ? __uint_as_float(r[i]) + __uint_as_float(rl[i]) : __uint_as_float(r[i]);
+              const float u1 = PASSES == 3 ? __uint_as_float(r2[i]) + __uint_as_float(rl2[i]) : __uint_as_float(r2[i]);
+              x[i] = fmaxf(u0, u1);
             }
           } else {
-            if (Ly.act == PMT_ACT_SELU) {
+            tmem_wait_ld();
 #pragma unroll
-              for (int i = 0; i < 32; ++i) x[i] = selu_u(x[i]);
-            }
-            if (valid) {
-              const unsigned dst = act + (v * L_next + pp) * 16;
-#pragma unroll
-              for (int i = 0; i < 32; i += 4) sts128(dst + (i >> 2) * PLANE_BYTES, make_float4(x[i], x[i + 1], x[i + 2], x[i + 3]));
-              if (PASSES == 3) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) x[i] -= __uint_as_float(__float_as_uint(x[i]) & 0xFFFFE000u);
-#pragma unroll
-                for (int i = 0; i < 32; i += 4)
-                  sts128(dst + BUF_BYTES + (i >> 2) * PLANE_BYTES, make_float4(x[i], x[i + 1], x[i + 2], x[i + 3]));
-              }
-            }
+            for (int i = 0; i < 8; ++i) x[i] = PASSES == 3 ? __uint_as_float(r[i]) + __uint_as_float(rl[i]) : __uint_as_float(r[i]);
           }
         }
-        if (l + 1 < n_layers) {
-          tc_fence_before();
-          signal_input_ready();
+        tc_fence_before();   // the accumulator has been read: a later item may overwrite it once this warp has arrived
+        if (Ly.pool2) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) x[i] = fmaxf(x[i], __shfl_xor_sync(0xffffffffu, x[i], 1));
         }
+        x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w; x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+        if (Ly.to_global) {
+          if (valid) {
+            float* dst = info_seq + (long long)(v0 + v) * (D.d_info + D.d_seq) + D.d_info + cq * 8;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (cq * 8 + i < Ly.out_ch) dst[i] = Ly.act == PMT_ACT_SELU ? SELU_SCALE * selu_u(x[i]) : x[i];
+          }
+        } else {
+          if (Ly.act == PMT_ACT_SELU) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = selu_u(x[i]);
+          }
+          if (valid) {
+            const unsigned dst = act + (2 * cq) * PLANE_BYTES + (v * Ly.L_next + pp) * 16;
+            sts128(dst, make_float4(x[0], x[1], x[2], x[3]));
+            sts128(dst + PLANE_BYTES, make_float4(x[4], x[5], x[6], x[7]));
+            if (PASSES == 3) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) x[i] -= __uint_as_float(__float_as_uint(x[i]) & 0xFFFFE000u);
+              sts128(dst + BUF_BYTES, make_float4(x[0], x[1], x[2], x[3]));
+              sts128(dst + BUF_BYTES + PLANE_BYTES, make_float4(x[4], x[5], x[6], x[7]));
+            }
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_addr(&S->done_bar[1 + it]));
+        TR(260 + it);
       }
-      // the next group's im2col overwrites rows the last layer's MMAs have finished reading (their commit was
-      // observed by the epilogue above); all eight warps must be past that point
-      tc_fence_before();
-      named_barrier(1, 32 * EPI_WARPS);
     }
   }
+  if (tr_on) tr[1022] = tr_n;
   tc_fence_before();
   __syncthreads();
-  if (warp == MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+  if (warp == MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
 }
 
 // ------------------------------------------------------------------------------------------------
-// Weight images, B operand [N][K] in the no-swizzle K-major layout [tap][16-byte K chunk][n][4 floats];
-// hi = TF32-rounded, lo = remainder (at + img_bytes).
+// Weight images, B operand in the no-swizzle K-major layout [tap][16-byte K chunk][row][4 floats]; a plane holds
+// 2N rows: rows [0, N) = TF32-rounded W, rows [N, 2N) = the remainder W - W_hi.
 // ------------------------------------------------------------------------------------------------
 __device__ float cnn_weight(const PmtModelDesc& D, const Layer& Ly, const float* __restrict__ w, int tap, int n, int k) {
   const PmtCnnOp& op = D.cnn_ops[Ly.op];
@@ -355,17 +386,15 @@ __device__ float cnn_weight(const PmtModelDesc& D, const Layer& Ly, const float*
 __global__ void pack_cnn_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_constant__ Plan TP, const float* __restrict__ w,
                                    unsigned char* __restrict__ image) {
   const Layer& Ly = TP.layer[blockIdx.x];
-  const int N = Ly.N;
+  const int N = Ly.N, R = 2 * N;
   const int taps = Ly.first ? 1 : Ly.taps, chunks = Ly.first ? 2 * Ly.ksteps : 8;
-  for (int idx = threadIdx.x; idx < taps * chunks * N * 4; idx += blockDim.x) {
-    const int e = idx & 3, n = (idx >> 2) % N, ch = (idx >> 2) / N % chunks, tap = (idx >> 2) / N / chunks;
-    const float v = cnn_weight(D, Ly, w, tap, n, ch * 4 + e);
+  for (int idx = threadIdx.x; idx < taps * chunks * R * 4; idx += blockDim.x) {
+    const int e = idx & 3, r = (idx >> 2) % R, ch = (idx >> 2) / R % chunks, tap = (idx >> 2) / R / chunks;
+    const float v = cnn_weight(D, Ly, w, tap, r % N, ch * 4 + e);
     unsigned hb;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
     const float hi = __uint_as_float(hb);
-    const size_t off = (size_t)Ly.img_off + (size_t)idx * 4;
-    *reinterpret_cast<float*>(image + off) = hi;
-    *reinterpret_cast<float*>(image + off + Ly.img_bytes) = v - hi;
+    *reinterpret_cast<float*>(image + (size_t)Ly.img_off + (size_t)idx * 4) = r < N ? hi : v - hi;
   }
 }
 
@@ -449,18 +478,19 @@ static bool build_cnn_tc_plan(const pmt::Plan& P, cnntc::Plan* out) {
   for (int l = 0; l < T.n_layers; ++l) {
     Layer& Ly = T.layer[l];
     Ly.img_off = bytes;
-    Ly.img_bytes = (Ly.first ? 2 * Ly.ksteps : Ly.taps * 8) * Ly.N * 16;
-    bytes += 2 * Ly.img_bytes;
+    Ly.img_bytes = (Ly.first ? 2 * Ly.ksteps : Ly.taps * 8) * 2 * Ly.N * 16;   // hi and lo rows interleaved per plane
+    bytes += Ly.img_bytes;
+    Ly.inv_L = 65536 / Ly.L_in + 1;
   }
   T.image_bytes = bytes;
   // variants per group: every layer's rows must fit MAX_CHUNKS chunks and the planes; pick the G with the fewest MMA
   // cycles per variant
-  const int fixed = 2 * BUF_BYTES + bytes + MAX_LAYERS * 32 * 4 + MAX_CODES + (int)sizeof(Bars) + 1024 + 64;
+  const int fixed = 2 * BUF_BYTES + bytes + MAX_LAYERS * 32 * 4 + (int)sizeof(Bars) + 1024 + 64;
   if (fixed > 227 * 1024) return false;
   double best = 1e30;
   int best_g = 0;
   for (int G = 1; G <= 128; ++G) {
-    if (G * d.hap_len > PLANE_ROWS || G * 2 * d.hap_len > MAX_CODES) break;
+    if (G * d.hap_len > PLANE_ROWS) break;
     double cost = 0;
     bool ok = true;
     for (int l = 0; l < T.n_layers; ++l) {
@@ -474,6 +504,35 @@ static bool build_cnn_tc_plan(const pmt::Plan& P, cnntc::Plan* out) {
   if (best_g == 0) return false;
   T.G = best_g;
   for (int l = 0; l < T.n_layers; ++l) T.n_chunks[l] = (T.G * T.layer[l].L_in + 127) / 128;
+  {   // the im2col scatter keeps its one-hot entries in MAX_TASKS registers per lane
+    const int rows0 = T.n_chunks[0] * 128 < PLANE_ROWS ? T.n_chunks[0] * 128 : PLANE_ROWS;
+    const int rpw = (rows0 + EPI_WARPS - 1) / EPI_WARPS;
+    if ((rpw * T.layer[0].taps * 2 + 31) / 32 > MAX_TASKS) return false;
+  }
+  // work items in issue order, with the epilogue item each one depends on
+  int first_item[MAX_LAYERS];
+  for (int l = 0; l < T.n_layers; ++l) {
+    first_item[l] = T.n_items;
+    const Layer& Ly = T.layer[l];
+    for (int c = 0; c < T.n_chunks[l]; ++c) {
+      if (T.n_items >= MAX_ITEMS) return false;
+      Item& I = T.item[T.n_items];
+      I.layer = l; I.chunk = c; I.need = 0;
+      if (l > 0) {
+        const Layer& Pv = T.layer[l - 1];
+        const int taps = Ly.taps, s = Pv.pool2 ? 2 : 1;
+        int last_row = 128 * c + 128 + taps - 2;                    // last input row the chunk's MMAs read
+        if (last_row > T.G * Ly.L_in - 1) last_row = T.G * Ly.L_in - 1;
+        const int v = last_row / Ly.L_in, pq = last_row % Ly.L_in;  // written by the previous layer's row (v, pq * s)
+        int src_chunk = (v * Pv.L_in + pq * s) / 128;
+        if (src_chunk < c && c < T.n_chunks[l - 1]) src_chunk = c;   // the accumulator columns of (l-1, c) are reused
+        if (src_chunk > T.n_chunks[l - 1] - 1) src_chunk = T.n_chunks[l - 1] - 1;
+        I.need = 1 + first_item[l - 1] + src_chunk;
+        if (T.n_items > 0 && I.need < T.item[T.n_items - 1].need) I.need = T.item[T.n_items - 1].need;
+      }
+      ++T.n_items;
+    }
+  }
   return true;
 }
 
@@ -490,14 +549,19 @@ size_t pmt_cnn_tc_image_bytes(const pmt::Plan& P) {
 
 template <int PASSES>
 static void launch_cnn_tc(const cnntc::Plan& T, const unsigned char* image, const float* weights, const PmtModelDesc& D,
-                          const PmtBatch* batch, float* info_seq, int grid, cudaStream_t st) {
-  const size_t smem = 2 * BUF_BYTES + T.image_bytes + MAX_LAYERS * 32 * sizeof(float) + MAX_CODES + sizeof(Bars) + 1024 + 64;
+                          const PmtBatch* batch, float* info_seq, int grid, long long* trace, cudaStream_t st) {
+  const size_t smem = 2 * BUF_BYTES + T.image_bytes + MAX_LAYERS * 32 * sizeof(float) + sizeof(Bars) + 1024 + 64;
   cudaFuncSetAttribute(hap_cnn_tc_kernel<PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   hap_cnn_tc_kernel<PASSES><<<grid, THREADS, smem, st>>>(T, image, weights, D, batch->haplotypes, batch->hap_kind, batch->hap_stride,
-                                                         batch->n_variants, info_seq);
+                                                         batch->n_variants, info_seq, trace);
 }
 
 // `image` is a 16-byte aligned device buffer of pmt_cnn_tc_image_bytes(P) bytes.
+static long long* g_cnn_trace = nullptr;
+// Measurement hook: device buffer of 3 x 1024 int64 that CTA 0 of the next tensor-core CNN launches fills with
+// (event, clock64) pairs; NULL disarms.
+extern "C" int pmt_set_cnn_trace(long long* device_buffer) { g_cnn_trace = device_buffer; return 0; }
+
 int pmt_launch_cnn_tc(const pmt::Plan& P, const float* weights, const PmtBatch* batch, float* info_seq, unsigned char* image,
                       int n_sm, int mode, cudaStream_t st) {
   cnntc::Plan T;
@@ -505,7 +569,7 @@ int pmt_launch_cnn_tc(const pmt::Plan& P, const float* weights, const PmtBatch* 
   pack_cnn_tc_kernel<<<T.n_layers, 256, 0, st>>>(P.d, T, weights, image);
   const int n_groups = (batch->n_variants + T.G - 1) / T.G;
   const int grid = n_groups < n_sm ? n_groups : n_sm;
-  if (mode == PMT_PRECISION_TF32) launch_cnn_tc<1>(T, image, weights, P.d, batch, info_seq, grid, st);
-  else launch_cnn_tc<3>(T, image, weights, P.d, batch, info_seq, grid, st);
+  if (mode == PMT_PRECISION_TF32) launch_cnn_tc<1>(T, image, weights, P.d, batch, info_seq, grid, g_cnn_trace, st);
+  else launch_cnn_tc<3>(T, image, weights, P.d, batch, info_seq, grid, g_cnn_trace, st);
   return 0;
 }
