@@ -131,7 +131,15 @@ struct ItemDev {   // per-item MMA operands, computed once per CTA
   int first, count, N, need;
 };
 
+struct EpiItem {   // per-item epilogue constants (three 16-byte shared loads)
+  int flags, lo_col, tmem_col, bias_off;
+  int inv_L, L_in, L_pool, L_next;
+  int row0, out_ch, pad0_, pad1_;
+};
+constexpr int F_DUP = 1, F_POOL2 = 2, F_GLOBAL = 4, F_SELU = 8;
+
 struct Bars {
+  EpiItem epi[MAX_ITEMS];
   unsigned long long done_bar[MAX_ITEMS + 1];   // [0]: im2col rows written; [1 + i]: epilogue of item i finished (16 warps)
   unsigned long long acc_bar[MAX_ITEMS];        // accumulator of item i complete (tcgen05.commit)
   ItemDev item[MAX_ITEMS];
@@ -139,7 +147,7 @@ struct Bars {
   int pad_;
 };
 
-template <int PASSES>
+template <int PASSES, bool TRACE>
 __global__ void __launch_bounds__(THREADS, 1)
 hap_cnn_tc_kernel(const __grid_constant__ Plan TP, const unsigned char* __restrict__ image, const float* __restrict__ wflat,
                   const __grid_constant__ PmtModelDesc D, const void* __restrict__ haps, int hap_kind, long long hap_stride,
@@ -159,7 +167,7 @@ hap_cnn_tc_kernel(const __grid_constant__ Plan TP, const unsigned char* __restri
   int tr_n = 0;
   const bool tr_on = trace != nullptr && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 5 || warp == MMA_WARP);
   long long* tr = trace + (warp == MMA_WARP ? 2 : (warp == 5 ? 1 : 0)) * 1024;
-  auto TR = [&](int id) { if (tr_on && tr_n < 510) { tr[2 * tr_n] = id; tr[2 * tr_n + 1] = clock64(); ++tr_n; } };
+  auto TR = [&](int id) { if (TRACE && tr_on && tr_n < 510) { tr[2 * tr_n] = id; tr[2 * tr_n + 1] = clock64(); ++tr_n; } };
 
   if (tid == 0) {
     for (int i = 0; i <= n_items; ++i) mbar_init(smem_addr(&S->done_bar[i]), EPI_WARPS);
@@ -193,6 +201,11 @@ hap_cnn_tc_kernel(const __grid_constant__ Plan TP, const unsigned char* __restri
     o.b = desc_lo(smem_addr(img_s) + Ly.img_off, 2 * Ly.N * 16);
     o.d = tmem_base + I.chunk * CHUNK_COLS;
     o.first = Ly.first; o.count = Ly.first ? Ly.ksteps : Ly.taps; o.N = Ly.N; o.need = I.need;
+    EpiItem& e = S->epi[tid];
+    e.flags = (Ly.dup ? F_DUP : 0) | (Ly.pool2 ? F_POOL2 : 0) | (Ly.to_global ? F_GLOBAL : 0) | (Ly.act == PMT_ACT_SELU ? F_SELU : 0);
+    e.lo_col = Ly.N; e.tmem_col = I.chunk * CHUNK_COLS; e.bias_off = I.layer * 32 * (int)sizeof(float);
+    e.inv_L = Ly.inv_L; e.L_in = Ly.L_in; e.L_pool = Ly.L_pool; e.L_next = Ly.L_next;
+    e.row0 = I.chunk * 128; e.out_ch = Ly.out_ch; e.pad0_ = 0; e.pad1_ = 0;
   }
   __syncthreads();
 
@@ -228,6 +241,7 @@ hap_cnn_tc_kernel(const __grid_constant__ Plan TP, const unsigned char* __restri
     const int quarter = warp & 3, cq = warp >> 2;
     const int row_c = quarter * 32 + lane;     // row inside a chunk = TMEM lane
     const unsigned trow = tmem_base + ((unsigned)(quarter * 32) << 16) + cq * 8;
+    const unsigned bias_base = smem_addr(bias_s) + cq * 8 * (int)sizeof(float);
     const Layer& L0y = TP.layer[0];
     const int rows0 = TP.n_chunks[0] * 128 < PLANE_ROWS ? TP.n_chunks[0] * 128 : PLANE_ROWS;
     const int rpw = (rows0 + EPI_WARPS - 1) / EPI_WARPS;            // im2col rows per warp
@@ -270,6 +284,7 @@ hap_cnn_tc_kernel(const __grid_constant__ Plan TP, const unsigned char* __restri
       for (int pl = 0; pl < planes0; ++pl)
         for (int j = r_lo + lane; j < r_hi; j += 32) sts128(act + pl * PLANE_BYTES + j * 16, make_float4(0.f, 0.f, 0.f, 0.f));
       __syncwarp();
+      TR(3);
 #pragma unroll
       for (int k = 0; k < MAX_TASKS; ++k) {
         if ((unsigned)codes[k] < 5u) {
@@ -277,6 +292,7 @@ hap_cnn_tc_kernel(const __grid_constant__ Plan TP, const unsigned char* __restri
           sts_f32(t_row[k] + (col >> 2) * PLANE_BYTES + (col & 3) * 4, 1.f);
         }
       }
+      TR(4);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_addr(&S->done_bar[0]));
@@ -284,18 +300,20 @@ hap_cnn_tc_kernel(const __grid_constant__ Plan TP, const unsigned char* __restri
       fetch_codes(g + gridDim.x);
 
       for (int it = 0; it < n_items; ++it) {
-        const Item& I = TP.item[it];
-        const int l = I.layer, c = I.chunk;
-        const Layer& Ly = TP.layer[l];
-        const int N = Ly.N;
-        const int j = c * 128 + row_c;
-        const int v = (j * Ly.inv_L) >> 16, pos = j - v * Ly.L_in;
+        const unsigned ea = smem_addr(&S->epi[it]);
+        const float4 e0f = lds128(ea), e1f = lds128(ea + 16), e2f = lds128(ea + 32);
+        const int flags = __float_as_int(e0f.x), N = __float_as_int(e0f.y);
+        const unsigned tcol = trow + __float_as_int(e0f.z);
+        const unsigned bias_a = bias_base + __float_as_int(e0f.w);
+        const int inv_L = __float_as_int(e1f.x), L_in = __float_as_int(e1f.y), L_pool = __float_as_int(e1f.z), L_next = __float_as_int(e1f.w);
+        const int out_ch = __float_as_int(e2f.y);
+        const int j = __float_as_int(e2f.x) + row_c;
+        const int v = (j * inv_L) >> 16, pos = j - v * L_in;
         int pp = pos;
         bool valid = v < nv;
-        if (Ly.pool2) { valid = valid && !(pos & 1); pp = pos >> 1; }
-        valid = valid && pp < Ly.L_pool;
-        const float4 b0 = lds128(smem_addr(bias_s + l * 32 + cq * 8)), b1 = lds128(smem_addr(bias_s + l * 32 + cq * 8 + 4));
-        const unsigned tcol = trow + c * CHUNK_COLS;
+        if (flags & F_POOL2) { valid = valid && !(pos & 1); pp = pos >> 1; }
+        valid = valid && pp < L_pool;
+        const float4 b0 = lds128(bias_a), b1 = lds128(bias_a + 16);
         TR(200 + it);
         mbar_wait(smem_addr(&S->acc_bar[it]), gpar);
         tc_fence_after();
@@ -305,7 +323,7 @@ hap_cnn_tc_kernel(const __grid_constant__ Plan TP, const unsigned char* __restri
           unsigned r[8], rl[8];
           tmem_ld8(tcol, r);
           if (PASSES == 3) tmem_ld8(tcol + N, rl);
-          if (Ly.dup) {
+          if (flags & F_DUP) {
             unsigned r2[8], rl2[8];
             tmem_ld8(tcol + 32, r2);
             if (PASSES == 3) tmem_ld8(tcol + N + 32, rl2);
@@ -322,26 +340,27 @@ hap_cnn_tc_kernel(const __grid_constant__ Plan TP, const unsigned char* __restri
             for (int i = 0; i < 8; ++i) x[i] = PASSES == 3 ? __uint_as_float(r[i]) + __uint_as_float(rl[i]) : __uint_as_float(r[i]);
           }
         }
+        TR(500 + it);
         tc_fence_before();   // the accumulator has been read: a later item may overwrite it once this warp has arrived
-        if (Ly.pool2) {
+        if (flags & F_POOL2) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) x[i] = fmaxf(x[i], __shfl_xor_sync(0xffffffffu, x[i], 1));
         }
         x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w; x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
-        if (Ly.to_global) {
+        if (flags & F_GLOBAL) {
           if (valid) {
             float* dst = info_seq + (long long)(v0 + v) * (D.d_info + D.d_seq) + D.d_info + cq * 8;
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-              if (cq * 8 + i < Ly.out_ch) dst[i] = Ly.act == PMT_ACT_SELU ? SELU_SCALE * selu_u(x[i]) : x[i];
+              if (cq * 8 + i < out_ch) dst[i] = (flags & F_SELU) ? SELU_SCALE * selu_u(x[i]) : x[i];
           }
         } else {
-          if (Ly.act == PMT_ACT_SELU) {
+          if (flags & F_SELU) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) x[i] = selu_u(x[i]);
           }
           if (valid) {
-            const unsigned dst = act + (2 * cq) * PLANE_BYTES + (v * Ly.L_next + pp) * 16;
+            const unsigned dst = act + (2 * cq) * PLANE_BYTES + (v * L_next + pp) * 16;
             sts128(dst, make_float4(x[0], x[1], x[2], x[3]));
             sts128(dst + PLANE_BYTES, make_float4(x[4], x[5], x[6], x[7]));
             if (PASSES == 3) {
@@ -351,7 +370,9 @@ hap_cnn_tc_kernel(const __grid_constant__ Plan TP, const unsigned char* __restri
               sts128(dst + BUF_BYTES + PLANE_BYTES, make_float4(x[4], x[5], x[6], x[7]));
             }
           }
+          TR(530 + it);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          TR(560 + it);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_addr(&S->done_bar[1 + it]));
@@ -359,7 +380,7 @@ hap_cnn_tc_kernel(const __grid_constant__ Plan TP, const unsigned char* __restri
       }
     }
   }
-  if (tr_on) tr[1022] = tr_n;
+  if (TRACE && tr_on) tr[1022] = tr_n;
   tc_fence_before();
   __syncthreads();
   if (warp == MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
@@ -547,12 +568,12 @@ size_t pmt_cnn_tc_image_bytes(const pmt::Plan& P) {
   return (size_t)T.image_bytes + 256;
 }
 
-template <int PASSES>
+template <int PASSES, bool TRACE>
 static void launch_cnn_tc(const cnntc::Plan& T, const unsigned char* image, const float* weights, const PmtModelDesc& D,
                           const PmtBatch* batch, float* info_seq, int grid, long long* trace, cudaStream_t st) {
   const size_t smem = 2 * BUF_BYTES + T.image_bytes + MAX_LAYERS * 32 * sizeof(float) + sizeof(Bars) + 1024 + 64;
-  cudaFuncSetAttribute(hap_cnn_tc_kernel<PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  hap_cnn_tc_kernel<PASSES><<<grid, THREADS, smem, st>>>(T, image, weights, D, batch->haplotypes, batch->hap_kind, batch->hap_stride,
+  cudaFuncSetAttribute(hap_cnn_tc_kernel<PASSES, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  hap_cnn_tc_kernel<PASSES, TRACE><<<grid, THREADS, smem, st>>>(T, image, weights, D, batch->haplotypes, batch->hap_kind, batch->hap_stride,
                                                          batch->n_variants, info_seq, trace);
 }
 
@@ -569,7 +590,12 @@ int pmt_launch_cnn_tc(const pmt::Plan& P, const float* weights, const PmtBatch* 
   pack_cnn_tc_kernel<<<T.n_layers, 256, 0, st>>>(P.d, T, weights, image);
   const int n_groups = (batch->n_variants + T.G - 1) / T.G;
   const int grid = n_groups < n_sm ? n_groups : n_sm;
-  if (mode == PMT_PRECISION_TF32) launch_cnn_tc<1>(T, image, weights, P.d, batch, info_seq, grid, g_cnn_trace, st);
-  else launch_cnn_tc<3>(T, image, weights, P.d, batch, info_seq, grid, g_cnn_trace, st);
+  if (g_cnn_trace) {
+    if (mode == PMT_PRECISION_TF32) launch_cnn_tc<1, true>(T, image, weights, P.d, batch, info_seq, grid, g_cnn_trace, st);
+    else launch_cnn_tc<3, true>(T, image, weights, P.d, batch, info_seq, grid, g_cnn_trace, st);
+  } else {
+    if (mode == PMT_PRECISION_TF32) launch_cnn_tc<1, false>(T, image, weights, P.d, batch, info_seq, grid, nullptr, st);
+    else launch_cnn_tc<3, false>(T, image, weights, P.d, batch, info_seq, grid, nullptr, st);
+  }
   return 0;
 }
