@@ -17,14 +17,16 @@ __device__ __forceinline__ void mbar_arrive(unsigned bar) {
 __device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (or the hint expires) instead
+// of polling -- a polling loop takes issue slots from the epilogue warps that share the SM sub-partition.
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra DONE_%=;\n\t"
       "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" ::"r"(bar), "r"(parity)
+      "DONE_%=:\n\t}" ::"r"(bar), "r"(parity), "r"(0x989680u)
       : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
