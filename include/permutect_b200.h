@@ -191,6 +191,61 @@ int pmt_downsample_fill(const int64_t* ref_off, const int64_t* alt_off, const fl
 /* Batch.__init__ decode (batch.py:51-56, plain_text_data.py:510-511): compressed rows -> [R][F] float32. */
 int pmt_decode_reads(const uint8_t* reads_u8, int64_t n_rows, int32_t row_bytes, float* out, void* stream);
 
+/* ---- fused loss head -------------------------------------------------------------------------------
+ * Replaces ArtifactModel.compute_batch_losses (artifact_model.py:299-325) together with
+ * compute_alt_count_losses (:276-279), compute_source_prediction_losses (:267-274), the gradient reversal of the
+ * two adversarial heads (gradient_reversal/functional.py:6-22) and the autograd backward of all of it. */
+#define PMT_MAX_HEAD_DIM 32   /* widest layer / input of an adversarial head; also the largest number of sources */
+
+typedef struct PmtLossDesc {
+  int32_t d_feat;                          /* E: width of features_be */
+  int32_t n_sources;                       /* outputs of the source head */
+  int32_t n_alt_ops, n_src_ops;            /* n_src_ops == 0: the source loss is identically zero (num_sources == 1) */
+  PmtLinearOp alt_ops[PMT_MAX_MLP_OPS];    /* alt_count_predictor.wrapped_module, offsets into the flat weight buffer */
+  PmtLinearOp src_ops[PMT_MAX_MLP_OPS];    /* source_predictor.wrapped_module */
+  float alt_reversal, src_reversal;        /* GradientReversal.alpha of each head */
+  float max_outlier_logit;                 /* MAX_LOGIT clip of the unsupervised loss (artifact_model.py:32,314) */
+  float max_alt_count;                     /* alt-count regression target = alt_count / max_alt_count (:278) */
+  int32_t n_params;                        /* length of the flat weight / gradient buffers */
+} PmtLossDesc;
+
+typedef struct PmtLossBatch {
+  int32_t n_variants;
+  int32_t label_col, source_col, alt_count_col; /* columns of the per-variant int16 array (datum.py:51-60) */
+  const int16_t* int_array;                /* [B][int_stride] */
+  int64_t int_stride;
+  const int64_t* alt_counts;               /* [B] alt counts when they differ from the int array (DownsampledBatch), else NULL */
+  const float* logits_b;                   /* [B]    BatchOutput.logits_b */
+  const float* outlier_logits_b;           /* [B]    BatchOutput.outlier_binary_logits */
+  const float* features_be;                /* [B][E] BatchOutput.features_be */
+  const float* weights_b;                  /* [B] or NULL (= 1) BatchOutput.weights */
+  const float* source_weights_b;           /* [B] or NULL (= 1) BatchOutput.source_weights */
+} PmtLossBatch;
+
+/* BatchLosses fields (artifact_model.py:76-90); any pointer may be NULL. */
+typedef struct PmtLossOutputs {
+  float* supervised_b; float* unsupervised_b; float* alt_count_b; float* source_b; float* total_b;
+} PmtLossOutputs;
+
+/* Upstream gradients of the five per-variant loss vectors; NULL = zero. */
+typedef struct PmtLossGrads {
+  const float* g_supervised_b; const float* g_unsupervised_b; const float* g_alt_count_b; const float* g_source_b;
+  const float* g_total_b;
+} PmtLossGrads;
+
+int pmt_losses_forward(const PmtLossDesc* desc, const float* weights, const PmtLossBatch* batch, const PmtLossOutputs* out,
+                       void* stream);
+size_t pmt_losses_workspace_size(const PmtLossDesc* desc, int32_t n_variants);
+/* WRITES d_logits_b[B], d_outlier_logits_b[B], d_features_be[B][E] (any may be NULL) and d_weights[n_params]
+ * (zero outside the two heads' parameters).  Deterministic: bitwise identical from run to run. */
+int pmt_losses_backward(const PmtLossDesc* desc, const float* weights, const PmtLossBatch* batch, const PmtLossGrads* grads,
+                        float* d_logits_b, float* d_outlier_logits_b, float* d_features_be, float* d_weights,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* Measurement hook (no reference counterpart): device buffer of 3 x 1024 int64 that CTA 0 of the next tensor-core
+ * haplotype-CNN launches fills with (event id, clock64) pairs (profiles/trace_cnn.py); NULL disarms. */
+int pmt_set_cnn_trace(long long* device_buffer);
+
 #ifdef __cplusplus
 }
 #endif

@@ -114,6 +114,7 @@ class ArtifactModel(nn.Module):
         self.num_sources = 1
         self.to(device=self._device, dtype=self._dtype)
         self._desc = None
+        self._loss_desc = None
         self._flat_cache = None
 
     # ---- reference surface (artifact_model.py:199-230) -------------------------------------------------
@@ -123,6 +124,7 @@ class ArtifactModel(nn.Module):
                                             adversarial_strength=0.01).to(device=self._device, dtype=self._dtype)
         self.num_sources = num_sources
         self._desc = None
+        self._loss_desc = None
         self._flat_cache = None
 
     def ref_alt_seq_embedding_dimension(self) -> int:
@@ -196,9 +198,11 @@ class ArtifactModel(nn.Module):
         else:
             weights_b, source_weights_b = balancer.process_batch_and_compute_weights(
                 batch, artifact_probs_b=torch.sigmoid(logits_b).detach())
-        return BatchOutput(features_be=alt_means, ref_features_be=ref_means, logits_b=logits_b, logits_bk=logits_bk,
-                           weights=weights_b, source_weights=weights_b * source_weights_b,
-                           outlier_binary_logits=outlier)
+        output = BatchOutput(features_be=alt_means, ref_features_be=ref_means, logits_b=logits_b, logits_bk=logits_bk,
+                             weights=weights_b, source_weights=weights_b * source_weights_b,
+                             outlier_binary_logits=outlier)
+        output._flat = flat      # the loss head reads the same materialised weights (and shares their autograd node)
+        return output
 
     def compute_source_prediction_losses(self, features_be: Tensor, batch: Batch) -> Tensor:
         if self.num_sources > 1:
@@ -214,17 +218,23 @@ class ArtifactModel(nn.Module):
         target = batch.get(Data.ALT_COUNT).to(dtype=pred.dtype) / MAX_ALT_COUNT
         return self.alt_count_loss_func(pred, target)
 
+    def loss_descriptor(self):
+        if self._loss_desc is None or self._loss_desc[0] != (self.num_sources, float(self.alt_count_predictor.gradient_reversal.alpha),
+                                                             float(self.source_predictor.gradient_reversal.alpha)):
+            key = (self.num_sources, float(self.alt_count_predictor.gradient_reversal.alpha),
+                   float(self.source_predictor.gradient_reversal.alpha))
+            self._loss_desc = (key, planner.build_loss_desc(self, MAX_OUTLIER_LOGIT, MAX_ALT_COUNT))
+        return self._loss_desc[1]
+
     def compute_batch_losses(self, output: BatchOutput, batch: Batch) -> BatchLosses:
-        """artifact_model.py:299-325."""
-        labels_b = batch.get_training_labels()
-        is_labeled_b = batch.get_is_labeled_mask()
-        supervised = is_labeled_b * BCE(output.logits_b, labels_b)
-        clipped = torch.clip(output.outlier_binary_logits, max=MAX_OUTLIER_LOGIT)
-        unsupervised = (1 - is_labeled_b) * BCE(clipped, torch.zeros_like(clipped))
-        alt_count = self.compute_alt_count_losses(output.features_be, batch)
-        source = self.compute_source_prediction_losses(output.features_be, batch)
-        total = output.weights * (supervised + unsupervised + alt_count) + output.source_weights * source
-        return BatchLosses(supervised, unsupervised, alt_count, source, total)
+        """artifact_model.py:299-325, with the adversarial heads (:267-279): one fused kernel forward, one backward."""
+        flat = getattr(output, "_flat", None)
+        if flat is None:
+            flat = self.flat_weights()
+        sup, unsup, alt_count, source, total = engine.FusedLossFunction.apply(
+            flat, output.logits_b, output.outlier_binary_logits, output.features_be, output.weights, output.source_weights,
+            self.loss_descriptor(), batch)
+        return BatchLosses(sup, unsup, alt_count, source, total)
 
     # ---- persistence (artifact_model.py:327-342) -----------------------------------------------------
     def make_dict_for_saving(self, artifact_log_priors=None, artifact_spectra=None):

@@ -107,6 +107,67 @@ class FusedArtifactFunction(torch.autograd.Function):
         return d_flat, None, None
 
 
+def _loss_batch(batch, logits_b, outlier, features, weights, source_weights) -> L.PmtLossBatch:
+    from permutect_b200.data.datum import Data
+    b = L.PmtLossBatch()
+    b.n_variants = batch.size()
+    b.label_col, b.source_col, b.alt_count_col = Data.LABEL.idx, Data.SOURCE.idx, Data.ALT_COUNT.idx
+    b.int_array, b.int_stride = batch.int_tensor.data_ptr(), batch.int_tensor.shape[1]
+    dc = batch._device_counts
+    b.alt_counts = dc[1].data_ptr() if dc is not None else None
+    b.logits_b, b.outlier_logits_b, b.features_be = logits_b.data_ptr(), outlier.data_ptr(), features.data_ptr()
+    b.weights_b = weights.data_ptr() if weights is not None else None
+    b.source_weights_b = source_weights.data_ptr() if source_weights is not None else None
+    return b
+
+
+class FusedLossFunction(torch.autograd.Function):
+    """(flat weights, logits_b, outlier logits, features_be) -> the five per-variant loss vectors of
+    compute_batch_losses (artifact_model.py:299-325); forward and backward are one kernel each (pmt_losses_*)."""
+
+    @staticmethod
+    def forward(ctx, flat, logits_b, outlier, features, weights, source_weights, ldesc, batch):
+        lib = L.load()
+        _require_cuda(flat)
+        if batch.int_tensor.device != flat.device:
+            raise RuntimeError("the loss kernels need the batch on the model's CUDA device")
+        tensors = [t.detach().contiguous().float() for t in (flat, logits_b, outlier, features)]
+        w = None if weights is None else weights.detach().contiguous().float()
+        sw = None if source_weights is None else source_weights.detach().contiguous().float()
+        B = batch.size()
+        out = torch.empty((5, B), dtype=torch.float32, device=flat.device)
+        po = L.PmtLossOutputs(*[out[i].data_ptr() for i in range(5)])
+        pb = _loss_batch(batch, tensors[1], tensors[2], tensors[3], w, sw)
+        L.check(lib.pmt_losses_forward(C.byref(ldesc), tensors[0].data_ptr(), C.byref(pb), C.byref(po),
+                                       torch.cuda.current_stream(flat.device).cuda_stream))
+        ctx.ldesc, ctx.batch = ldesc, batch
+        ctx.save_for_backward(*tensors, *(t for t in (w, sw) if t is not None))
+        ctx.has_w, ctx.has_sw = w is not None, sw is not None
+        return out[0], out[1], out[2], out[3], out[4]
+
+    @staticmethod
+    def backward(ctx, g_sup, g_uns, g_alt, g_src, g_tot):
+        lib = L.load()
+        saved = list(ctx.saved_tensors)
+        flat, logits_b, outlier, features = saved[:4]
+        rest = saved[4:]
+        w = rest.pop(0) if ctx.has_w else None
+        sw = rest.pop(0) if ctx.has_sw else None
+        dev = flat.device
+        keep = [None if g is None else g.contiguous().float() for g in (g_sup, g_uns, g_alt, g_src, g_tot)]
+        pg = L.PmtLossGrads(*[None if g is None else g.data_ptr() for g in keep])
+        pb = _loss_batch(ctx.batch, logits_b, outlier, features, w, sw)
+        B = ctx.batch.size()
+        d_logits, d_outlier = torch.empty(B, dtype=torch.float32, device=dev), torch.empty(B, dtype=torch.float32, device=dev)
+        d_feat, d_flat = torch.empty_like(features), torch.empty_like(flat)
+        need = lib.pmt_losses_workspace_size(C.byref(ctx.ldesc), B)
+        ws = _workspace(dev, need)
+        L.check(lib.pmt_losses_backward(C.byref(ctx.ldesc), flat.data_ptr(), C.byref(pb), C.byref(pg), d_logits.data_ptr(),
+                                        d_outlier.data_ptr(), d_feat.data_ptr(), d_flat.data_ptr(), ws.data_ptr(), ws.numel(),
+                                        torch.cuda.current_stream(dev).cuda_stream))
+        return d_flat, d_logits, d_outlier, d_feat, None, None, None, None
+
+
 class ProfileEvents:
     """CUDA-event timing of the library's dominant kernel (pmt_set_profile_events).  ``arm()`` before a
     call gives that call a fresh event pair; ``mean_ms()`` (after a synchronize) averages the pairs."""

@@ -67,7 +67,32 @@ class PmtOutGrads(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("d_logits_bk", "d_alt_means_be", "d_ref_means_be")]
 
 
-EXPORTED_SYMBOLS = ["pmt_last_error", "pmt_abi_version", "pmt_workspace_size", "pmt_forward", "pmt_backward",
+MAX_HEAD_DIM = 32
+
+
+class PmtLossDesc(C.Structure):
+    _fields_ = [("d_feat", _i32), ("n_sources", _i32), ("n_alt_ops", _i32), ("n_src_ops", _i32),
+                ("alt_ops", PmtLinearOp * MAX_MLP_OPS), ("src_ops", PmtLinearOp * MAX_MLP_OPS),
+                ("alt_reversal", C.c_float), ("src_reversal", C.c_float), ("max_outlier_logit", C.c_float),
+                ("max_alt_count", C.c_float), ("n_params", _i32)]
+
+
+class PmtLossBatch(C.Structure):
+    _fields_ = [("n_variants", _i32), ("label_col", _i32), ("source_col", _i32), ("alt_count_col", _i32),
+                ("int_array", C.c_void_p), ("int_stride", C.c_int64), ("alt_counts", C.c_void_p),
+                ("logits_b", C.c_void_p), ("outlier_logits_b", C.c_void_p), ("features_be", C.c_void_p),
+                ("weights_b", C.c_void_p), ("source_weights_b", C.c_void_p)]
+
+
+class PmtLossOutputs(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("supervised_b", "unsupervised_b", "alt_count_b", "source_b", "total_b")]
+
+
+class PmtLossGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("g_supervised_b", "g_unsupervised_b", "g_alt_count_b", "g_source_b", "g_total_b")]
+
+
+EXPORTED_SYMBOLS = ["pmt_losses_forward", "pmt_losses_backward", "pmt_losses_workspace_size", "pmt_set_cnn_trace", "pmt_last_error", "pmt_abi_version", "pmt_workspace_size", "pmt_forward", "pmt_backward",
                     "pmt_decode_reads", "pmt_set_profile_events", "pmt_downsample_counts", "pmt_downsample_fill", "pmt_set_precision", "pmt_get_precision"]
 
 _LIB = None
@@ -110,6 +135,16 @@ def load():
     lib.pmt_get_precision.restype = C.c_int
     lib.pmt_set_profile_events.restype = C.c_int
     lib.pmt_set_profile_events.argtypes = [C.c_void_p, C.c_void_p]
+    lib.pmt_set_cnn_trace.restype = C.c_int
+    lib.pmt_set_cnn_trace.argtypes = [C.c_void_p]
+    lib.pmt_losses_forward.restype = C.c_int
+    lib.pmt_losses_forward.argtypes = [C.POINTER(PmtLossDesc), C.c_void_p, C.POINTER(PmtLossBatch), C.POINTER(PmtLossOutputs),
+                                       C.c_void_p]
+    lib.pmt_losses_workspace_size.restype = C.c_size_t
+    lib.pmt_losses_workspace_size.argtypes = [C.POINTER(PmtLossDesc), C.c_int32]
+    lib.pmt_losses_backward.restype = C.c_int
+    lib.pmt_losses_backward.argtypes = [C.POINTER(PmtLossDesc), C.c_void_p, C.POINTER(PmtLossBatch), C.POINTER(PmtLossGrads),
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     if lib.pmt_abi_version() != PMT_ABI_VERSION:
         raise RuntimeError(f"libpermutect_b200 ABI {lib.pmt_abi_version()} != binding {PMT_ABI_VERSION}")
     _LIB = lib

@@ -159,3 +159,29 @@ def build_desc(model, read_row_bytes: int = 12) -> L.PmtModelDesc:
     d.lambda_k = offsets[fc + ".artifact_emg.parametrizations.lambda_k.original"]
     d.n_params = n_params
     return d
+
+
+def build_loss_desc(model, max_outlier_logit: float, max_alt_count: float) -> L.PmtLossDesc:
+    """Kernel-facing description of the loss head (artifact_model.py:267-279, 299-325): the two adversarial MLP
+    programs with offsets into the same flat weight buffer as build_desc."""
+    offsets, n_params = flat_layout(model)
+    d = L.PmtLossDesc()
+    d.d_feat = model.reducer.output_dimension()
+    d.n_sources = model.num_sources
+    alt = _mlp_ops(offsets, "alt_count_predictor.wrapped_module", model.alt_count_predictor.wrapped_module.layer_sizes)
+    src = [] if model.num_sources == 1 else _mlp_ops(offsets, "source_predictor.wrapped_module",
+                                                     model.source_predictor.wrapped_module.layer_sizes)
+    for ops in (alt, src):
+        for op in ops:
+            if max(op.in_dim, op.out_dim) > L.MAX_HEAD_DIM:
+                raise NotImplementedError(f"adversarial head layers wider than {L.MAX_HEAD_DIM} are not supported")
+    d.n_alt_ops, d.n_src_ops = len(alt), len(src)
+    for i, op in enumerate(alt):
+        d.alt_ops[i] = op
+    for i, op in enumerate(src):
+        d.src_ops[i] = op
+    d.alt_reversal = float(model.alt_count_predictor.gradient_reversal.alpha)
+    d.src_reversal = float(model.source_predictor.gradient_reversal.alpha)
+    d.max_outlier_logit, d.max_alt_count = float(max_outlier_logit), float(max_alt_count)
+    d.n_params = n_params
+    return d
