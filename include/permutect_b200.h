@@ -246,6 +246,19 @@ int pmt_losses_backward(const PmtLossDesc* desc, const float* weights, const Pmt
  * haplotype-CNN launches fills with (event id, clock64) pairs (profiles/trace_cnn.py); NULL disarms. */
 int pmt_set_cnn_trace(long long* device_buffer);
 
+/* ---- flat optimiser step ---------------------------------------------------------------------------
+ * Replaces misc_utils.backpropagate's clip_grad_norm_(max_norm=1.0) + AdamW.step (misc_utils.py:125-129;
+ * optimiser built at model_training.py:68-72) for a model whose parameters are views of one flat fp32 buffer.
+ * grads is the flat gradient in the same layout (already summed across ranks for data-parallel training);
+ * mask (NULL = all ones) marks entries whose parameter has a gradient -- masked-out entries are not touched, as
+ * torch skips parameters whose .grad is None.  step_count[n] counts the updates each entry has taken (torch keeps one
+ * step counter per parameter; bias corrections use it).  max_norm <= 0 disables clipping.  The total gradient
+ * norm (before clipping) is written to total_norm_out when non-NULL.  Two launches, no host synchronisation. */
+size_t pmt_adamw_workspace_size(void);
+int pmt_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int32_t* step_count,
+                   const float* mask, int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, float max_norm,
+                   float* total_norm_out, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

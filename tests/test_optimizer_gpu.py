@@ -1,0 +1,62 @@
+"""FlatAdamW (pmt_adamw_step through the C-ABI) against torch's clip_grad_norm_ + AdamW on the same gradients,
+including frozen parameters (calibration epochs) and several steps of moment state."""
+import numpy as np
+import pytest
+import torch
+
+from golden_utils import load
+from helpers import golden_batch, model_from_golden
+from permutect_b200.training.step import FlatAdamW, backpropagate, make_optimizer
+from permutect_b200.utils.enums import Epoch
+
+pytestmark = pytest.mark.gpu
+
+
+def _models():
+    g = load("v040_seed0_b64")
+    dev = torch.device("cuda:0")
+    a, b = model_from_golden(g, dev), model_from_golden(g, dev)
+    return g, a, b
+
+
+def test_flat_adamw_matches_torch_clip_and_adamw():
+    g, ma, mb = _models()
+    opt_a = make_optimizer(ma, learning_rate=3e-3, weight_decay=0.02)
+    assert isinstance(opt_a, FlatAdamW)
+    opt_b = torch.optim.AdamW(mb.parameters(), lr=3e-3, weight_decay=0.02)
+    gen = torch.Generator().manual_seed(0)
+    for step in range(4):
+        scale = [30.0, 0.01, 1.0, 5.0][step]        # exercise both sides of the clip threshold
+        for (na, pa), (nb, pb) in zip(ma.named_parameters(), mb.named_parameters()):
+            gr = (torch.randn(pa.shape, generator=gen) * scale).to(pa.device)
+            pa.grad, pb.grad = gr.clone(), gr.clone()
+        if step == 2:                                # a frozen tensor: no gradient on either side
+            ma.feature_clustering.artifact_emg.mu_k.grad = None
+            mb.feature_clustering.artifact_emg.mu_k.grad = None
+        norm_b = torch.nn.utils.clip_grad_norm_(list(mb.parameters()), max_norm=1.0)
+        opt_b.step()
+        opt_a.step()
+        assert abs(float(opt_a.total_norm) - float(norm_b)) <= 1e-5 * float(norm_b)
+        for (na, pa), (nb, pb) in zip(ma.named_parameters(), mb.named_parameters()):
+            torch.testing.assert_close(pa, pb, rtol=2e-6, atol=2e-7, msg=lambda m: f"step {step} {na}: {m}")
+
+
+def test_training_step_with_flat_optimizer_changes_the_forward():
+    g, model, _ = _models()
+    dev = model._device
+    model.set_epoch_type(Epoch.TRAIN)
+    opt = make_optimizer(model)
+    batch = golden_batch(g, dev)
+    losses0 = model.compute_batch_losses(model.compute_batch_output(batch), batch)
+    first = float(losses0.total_loss.detach())
+    backpropagate(opt, losses0.total_loss, params_to_clip=model.parameters())
+    for _ in range(5):
+        losses = model.compute_batch_losses(model.compute_batch_output(batch), batch)
+        backpropagate(opt, losses.total_loss, params_to_clip=model.parameters())
+    model.set_epoch_type(Epoch.VALID)
+    with torch.inference_mode():                    # the cached materialised weights must see the in-place updates
+        out = model.compute_batch_output(batch)
+        last = float(model.compute_batch_losses(out, batch).total_loss)
+    assert np.isfinite(last) and last < first
+    sd = model.state_dict()                         # parameters are views of the flat buffer: state dict unchanged in form
+    assert set(sd.keys()) == set(g.sd.keys())
