@@ -1,0 +1,84 @@
+"""Host -> device batch pipeline (reference: permutect/data/prefetch_generator.py:9-20, whose overlapped variant is
+commented out at :22-36).  Batches produced by the loader (pinned host memory, reads still compressed: 12 B/read)
+are copied on a side CUDA stream into a ring of persistent device buffers, up to ``depth`` batches ahead of the batch
+the model is working on, so PCIe transfers overlap the kernels.  The consumer's stream waits on the copy's event and
+the copy stream waits on the event that marks the consumer's last use of a ring slot; there is no host
+synchronisation and, after the first pass, no device allocation."""
+import copy
+from typing import Iterable, Iterator, List, Optional
+
+import torch
+
+from permutect_b200.data.batch import Batch
+
+_FIELDS = ("reads", "int_tensor", "float_tensor", "read_indices")
+
+
+class _Slot:
+    """One ring entry: flat device buffers per batch field, grown on demand, plus the event of its last consumer."""
+
+    def __init__(self, device):
+        self.device = device
+        self.buffers = {}
+        self.released: Optional[torch.cuda.Event] = None
+
+    def view_like(self, name: str, t_cpu: torch.Tensor) -> torch.Tensor:
+        buf = self.buffers.get(name)
+        n = t_cpu.numel()
+        if buf is None or buf.dtype != t_cpu.dtype or buf.numel() < n:
+            buf = torch.empty(int(n * 1.1) + 64, dtype=t_cpu.dtype, device=self.device)
+            self.buffers[name] = buf
+        return buf[:n].view(t_cpu.shape)
+
+
+def prefetch_generator(dataloader: Iterable[Batch], device=None, depth: int = 2) -> Iterator[Batch]:
+    device = torch.device(device if device is not None else ("cuda" if torch.cuda.is_available() else "cpu"))
+    if device.type != "cuda":
+        for batch_cpu in dataloader:
+            yield batch_cpu.copy_to(device)
+        return
+    copy_stream = torch.cuda.Stream(device)
+    ring: List[_Slot] = [_Slot(device) for _ in range(depth + 1)]
+    queue = []
+    n_launched = 0
+
+    def launch(batch_cpu: Batch):
+        nonlocal n_launched
+        slot = ring[n_launched % len(ring)]
+        n_launched += 1
+        views = {name: slot.view_like(name, getattr(batch_cpu, name)) for name in _FIELDS if getattr(batch_cpu, name) is not None}
+        if slot.released is not None:
+            copy_stream.wait_event(slot.released)       # the consumer of this slot's previous batch is done with it
+        else:
+            copy_stream.wait_stream(torch.cuda.current_stream(device))   # buffers were just allocated on the caller's stream
+        with torch.cuda.stream(copy_stream):
+            for name, dst in views.items():
+                dst.copy_(getattr(batch_cpu, name), non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(copy_stream)
+        batch_gpu = copy.copy(batch_cpu)
+        for name, dst in views.items():
+            setattr(batch_gpu, name, dst)
+        batch_gpu._offsets = None
+        batch_gpu._decoded = None
+        queue.append((batch_gpu, done, slot))
+
+    def hand_over():
+        batch_gpu, done, slot = queue.pop(0)
+        torch.cuda.current_stream(device).wait_event(done)
+        return batch_gpu, slot
+
+    def release(slot: _Slot):
+        slot.released = torch.cuda.Event()
+        slot.released.record(torch.cuda.current_stream(device))   # everything the consumer enqueued on this batch
+
+    for batch_cpu in dataloader:
+        launch(batch_cpu)
+        if len(queue) >= depth:
+            batch_gpu, slot = hand_over()
+            yield batch_gpu
+            release(slot)
+    while queue:
+        batch_gpu, slot = hand_over()
+        yield batch_gpu
+        release(slot)
