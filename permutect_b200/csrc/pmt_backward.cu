@@ -364,7 +364,7 @@ reads_backward_kernel(const __grid_constant__ Plan P, const __grid_constant__ Bw
           const int offs[5] = {BO.alpha_ref, BO.alpha_alt, BO.beta_ref, BO.beta_alt, BO.gamma};
           float s = 0.f;
           for (int w = 0; w < NWARPS; ++w) s += wpart[w * acc_cap + tid];
-          part[offs[tid]] += s;
+          red_add(part + offs[tid], s);
         }
         segment_sums(M, Cz, 5 * H, H, dsums, P.sum_w, false, false);
         __syncthreads();
@@ -386,14 +386,14 @@ reads_backward_kernel(const __grid_constant__ Plan P, const __grid_constant__ Bw
               d_reg += dm * regw / den;
               d_w += dm * (reg - C.sums[(j * 2 + 0) * P.sum_w + tid]) / den;
             }
-            part[BO.regularizer + tid] += d_reg;
+            red_add(part + BO.regularizer + tid, d_reg);
             small[tid] = d_w;
           }
           __syncthreads();
           if (tid == 0) {
             float s = 0.f;
             for (int f = 0; f < H; ++f) s += small[f];
-            part[BO.reg_weight] += s;
+            red_add(part + BO.reg_weight, s);
           }
           for (int idx = tid; idx < M.nv * H; idx += NTHREADS) {
             const int j = idx / H, f = idx % H;
@@ -623,7 +623,7 @@ __device__ __forceinline__ void conv_wgrad(const PmtCnnOp& op, const float* __re
       const int co = cg * 4 + b;
       if (co < op.out_ch) {
 #pragma unroll
-        for (int t = 0; t < KS; ++t) part[op.w_off + (co * op.in_ch + ci) * KS + t] += acc[b][t];
+        for (int t = 0; t < KS; ++t) red_add(part + op.w_off + (co * op.in_ch + ci) * KS + t, acc[b][t]);
       }
     }
   }
@@ -727,12 +727,12 @@ hap_cnn_backward_kernel(const __grid_constant__ Plan P, const __grid_constant__ 
         const int n = idx / op.in_ch, k = idx % op.in_ch;
         float a = 0.f;
         for (int v = 0; v < nv; ++v) a = fmaf(dcur[v * VS + n], vin[v * VS + k], a);
-        part[op.w_off + idx] += a;
+        red_add(part + op.w_off + idx, a);
       }
       for (int n = tid; n < op.out_ch; n += NTHREADS) {
         float a = 0.f;
         for (int v = 0; v < nv; ++v) a += dcur[v * VS + n];
-        part[op.b_off + n] += a;
+        red_add(part + op.b_off + n, a);
       }
       for (int idx = tid; idx < VT * op.in_ch; idx += NTHREADS) {
         const int v = idx / op.in_ch, k = idx % op.in_ch;
@@ -803,7 +803,7 @@ hap_cnn_backward_kernel(const __grid_constant__ Plan P, const __grid_constant__ 
           float a = 0.f;
           for (int v = 0; v < VT; ++v)
             for (int p = 0; p < lo; ++p) a += gcur[co * ld_o + v * lp_o + p];
-          part[op.b_off + co] += a;
+          red_add(part + op.b_off + co, a);
         }
         if (i > 0) {
           // zero-padded copy of the output gradient, then the forward conv routine with the flipped image

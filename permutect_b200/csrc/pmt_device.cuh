@@ -248,6 +248,11 @@ __device__ __forceinline__ void gemm_tile_T(const float* dY, const GemmOp& op, c
                     alpha, as, rows_used)
 }
 
+// Fire-and-forget accumulation into a CTA-private gradient buffer: a reduction does not wait for the old value the way
+// a load-add-store does.  Every address is only ever updated by one thread of one CTA, in program order, so the result
+// is still bitwise reproducible.
+__device__ __forceinline__ void red_add(float* p, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+
 // Weight gradient: part[n*K + k] += sum_{r in [r_lo, r_hi)} dY[n][r] * A[k][r]   (r_lo, r_hi multiples of 4).
 // `part` is this CTA's private gradient buffer, so the read-modify-write needs no atomics and the
 // summation order is fixed.  Lanes 0-15 / 16-31 of a warp take two groups of 4 consecutive n; each
@@ -295,7 +300,7 @@ static __device__ __noinline__ void wgrad_tile(unsigned dy_s, int N, unsigned a_
 #pragma unroll
           for (int a = 0; a < 4; ++a) {
             const int k = k0 + kl + 16 * a;
-            if (a < ka && k < K) part[n * K + k] += acc[b][a];
+            if (a < ka && k < K) red_add(part + n * K + k, acc[b][a]);
           }
         }
       }
@@ -321,7 +326,7 @@ __device__ __forceinline__ void rowdot_tile(const float* buf, const float* other
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) part[f * stride] += s;
+    if (lane == 0) red_add(part + f * stride, s);
   }
 }
 
