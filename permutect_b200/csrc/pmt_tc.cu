@@ -161,10 +161,10 @@ __device__ __forceinline__ float sumsq_centered_n(const float* v, float m) {
   return (a0 + a1) + (a2 + a3);
 }
 
-template <int PASSES>
+template <int PASSES, bool TRACE>
 __global__ void __launch_bounds__(THREADS, 1)
 reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_constant__ TcPlan TP, const __grid_constant__ TcArgs A,
-                        int n_stages, int stage_bytes) {
+                        int n_stages, int stage_bytes, long long* __restrict__ trace) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // carve: [weight ring: n_stages x stage_bytes][xch 2 slots][sums 2 slots][pair exchange][block scalars][HeadConst][Shared]
   unsigned char* p = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -179,6 +179,12 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
   const int tid = threadIdx.x;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const float* W = A.wflat;
+  // optional cycle trace of CTA 0 (profiles/trace_reads.py): (event id, clock) pairs of four recording threads
+  int tr_n = 0;
+  const int tr_w = warp == 0 ? 0 : (warp == 8 ? 1 : (warp == MMA_WARP ? 2 : (warp == MMA_WARP + 1 ? 3 : -1)));
+  const bool tr_on = TRACE && trace != nullptr && blockIdx.x == 0 && (tid & 31) == 0 && tr_w >= 0;
+  long long* tr = trace + (tr_w < 0 ? 0 : tr_w) * 2048;
+  auto TR = [&](int id) { if (TRACE && tr_on && tr_n < 1020) { tr[2 * tr_n] = id; tr[2 * tr_n + 1] = clock64(); ++tr_n; } };
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) { mbar_init(smem_addr(&S->bar_a[s]), 8); mbar_init(smem_addr(&S->bar_d[s]), 1); }
     for (int i = 0; i < n_stages; ++i) { mbar_init(smem_addr(&S->wfull[i]), 1); mbar_init(smem_addr(&S->wfree[i]), 2); }
@@ -252,9 +258,11 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
         const unsigned kb_stride16 = (unsigned)(oN * 128) >> 4;
         const bool lo_pass = step > 0 || l0_lo;
         const unsigned d = tb + (o_dst_x ? COL_X : COL_Z);
+        TR(100 + step);
         mbar_wait(smem_addr(&S->wfull[stage]), wparity);
         mbar_wait(bar_a, aparity);
         tc_fence_after();
+        TR(200 + step);
         if (elect_one()) {
           switch (oKS) {
             case 3: issue_chain<3, PASSES>(d, tb + COL_AHI, tb + COL_ALO, b_hi, b_lo, kb_stride16, idesc, o_dst_x, lo_pass); break;
@@ -265,6 +273,7 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
           mma_commit(smem_addr(&S->wfree[stage]));
         }
         __syncwarp();
+        TR(300 + step);
         aparity ^= 1;
         if (++stage == n_stages) { stage = 0; wparity ^= 1; }
       }
@@ -324,8 +333,10 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
       long long my_idx = -1;
       if (my_var >= 0) my_idx = is_alt ? total_ref + a_base + (row - ref_pad) : r_base + row;
 
+      TR(1);
       for (int step = 0; step < n_steps; ++step) {
         const int epi = TP.step[step].epi;
+        TR(400 + step);
         switch (epi) {
           case EPI_DECODE: {   // batch.py:51-56, plain_text_data.py:510-511 (quirk Q2: the uint8 de-quantisation wraps)
             float v[32];
@@ -469,6 +480,7 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
               for (int i = 0; i < 16; ++i) z2s[i] = __uint_as_float(r2[i]);
             }
             // z1s[j] = z1[k0 + j] (j < 6), z2s[k] = z2[k] (k < 12; columns >= H are zero)
+            TR(800 + step);
             const int k0 = half * 6;
             float z2[12];
 #pragma unroll
@@ -493,7 +505,9 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
               z2n[j] = (zz - mean) * rstd * lds_f32(bcs + (BC_LN2W + k0 + j) * 4) + lds_f32(bcs + (BC_LN2B + k0 + j) * 4);
               if (k0 + j < H) sts_f32(xch + ((k0 + j) * TILE + row) * 4, z2n[j]);
             }
+            TR(900 + step);
             named_barrier(slot_bar, 256);
+            TR(1000 + step);
             {   // per-variant mean fields (gated_mlp.py:236-239): one (segment, hidden unit) sum per thread
               const float regw = lds_f32(bcs + BC_REGW * 4);
               const int n_sums = nv * 2 * H;
@@ -511,7 +525,9 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
                 sts_f32(sums + (seg * MAXH + f) * 4, m);
               }
             }
+            TR(1100 + step);
             named_barrier(slot_bar, 256);
+            TR(1200 + step);
             // proj2 operand columns of this thread: [t_ref (6) | t_alt (6)]; the second thread's last two hidden
             // slots (k = 10 would be unit 11; MAXH = 11 -> slot 5 of half 1 is unit 11 < MAXH only if H = 11)
             // layout, half 0: [t_ref k 0..5 | t_alt k 0..5]; half 1: [t_ref k 6..10 | t_alt k 6..10 | is_ref, is_alt]
@@ -561,13 +577,16 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
           } break;
         }
         // ---- hand the operand to the MMA warp, wait for the accumulator ----
+        TR(500 + step);
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_a);
+        TR(600 + step);
         mbar_wait(bar_d, dparity);
         dparity ^= 1;
         tc_fence_after();
+        TR(700 + step);
       }
 
       // ---------------- clustering head (rotation folded into the last layer; feature_clustering.py:82-135) ----------------
@@ -652,6 +671,7 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
       }
     }
   }
+  if (TRACE && tr_on) tr[2046] = tr_n;
   tc_fence_before();
   __syncthreads();
   if (warp == MMA_WARP) {
@@ -911,6 +931,11 @@ size_t pmt_tc_workspace_bytes(const Plan& P, const PmtBatch* batch) {
   return pmt_tc_image_bytes(P) + tiles_bytes(batch ? batch->n_variants : 0) + 1024;
 }
 
+static long long* g_reads_trace = nullptr;
+// Measurement hook: device buffer of 4 x 2048 int64 that CTA 0 of the next tensor-core read-kernel launches fills
+// with (event, clock64) pairs; NULL disarms.
+extern "C" int pmt_set_reads_trace(long long* device_buffer) { g_reads_trace = device_buffer; return 0; }
+
 template <int PASSES>
 static int launch_tc(const PmtModelDesc& D, const TcPlan& T, const TcArgs& A, int grid, cudaStream_t st) {
   const int stage_bytes = PASSES == 3 ? T.slot_bytes : T.slot_bytes / 2;
@@ -920,8 +945,13 @@ static int launch_tc(const PmtModelDesc& D, const TcPlan& T, const TcArgs& A, in
   if (n_stages > NS_MAX) n_stages = NS_MAX;
   PMT_CHECK(n_stages >= 2, "tensor-core forward: weight ring does not fit in shared memory");
   const size_t smem = fixed + (size_t)n_stages * stage_bytes;
-  cudaFuncSetAttribute(reads_forward_tc_kernel<PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  reads_forward_tc_kernel<PASSES><<<grid, THREADS, smem, st>>>(D, T, A, n_stages, stage_bytes);
+  if (g_reads_trace) {
+    cudaFuncSetAttribute(reads_forward_tc_kernel<PASSES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    reads_forward_tc_kernel<PASSES, true><<<grid, THREADS, smem, st>>>(D, T, A, n_stages, stage_bytes, g_reads_trace);
+  } else {
+    cudaFuncSetAttribute(reads_forward_tc_kernel<PASSES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    reads_forward_tc_kernel<PASSES, false><<<grid, THREADS, smem, st>>>(D, T, A, n_stages, stage_bytes, nullptr);
+  }
   return 0;
 }
 
