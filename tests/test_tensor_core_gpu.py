@@ -71,3 +71,55 @@ def test_tensor_core_modes_on_a_large_ragged_batch():
         out = model.compute_batch_output(batch)
     torch.testing.assert_close(out.logits_b.cpu(), want["logits_b"], rtol=0, atol=1e-3)
     torch.testing.assert_close(out.features_be.cpu(), want["features_be"], rtol=1e-4, atol=2e-4)
+
+
+@pytest.mark.parametrize("n_variants", [1, 15, 16, 17, 333, 5000])
+def test_tensor_core_haplotype_cnn_matches_the_oracle(n_variants):
+    """hap_cnn_tc_kernel (shifted-window MMAs, 16 variants per group): partial groups, single variants, many CTAs.
+    Indel codes (4) included; the reference sequence embedding is info_seq's last d_seq columns."""
+    from oracle import artifact_oracle as orc
+    from permutect_b200.data.batch import Batch
+    from permutect_b200.engine import function as engine
+    from permutect_b200.synthetic import make_wgs_arrays
+    g = load("v040_perturbed_edge")
+    dev = torch.device("cuda:0")
+    model = model_from_golden(g, dev)
+    model.set_epoch_type(Epoch.VALID)
+    ia, fa, reads = make_wgs_arrays(n_variants, seed=11 + n_variants)
+    rng = np.random.default_rng(n_variants)
+    ia[:, 16:] = rng.integers(0, 5, ia[:, 16:].shape)          # every code incl. the deletion marker, at every position
+    batch = Batch.from_arrays(ia, fa, reads).copy_to(dev)
+    raw = dict(reads_u8=reads, read_indices=None, ref_counts=ia[:, 0], alt_counts=ia[:, 1], info=fa[:, 6:].astype(np.float32),
+               haplotypes=ia[:, 16:], labels=ia[:, 2], sources=ia[:, 4])
+    with torch.no_grad():
+        want = orc.forward(g.sd, g.hp, raw)
+    d_info = model.descriptor().d_info
+    for mode, tol in (("tf32x3", 2e-5), ("tf32", 5e-3)):
+        L.set_precision(mode)
+        with torch.inference_mode():
+            out = engine.forward_call(model.descriptor(), model.flat_weights(), batch)
+        torch.testing.assert_close(out["info_seq"][:, d_info:].cpu(), want["ref_seq_emb"], rtol=0, atol=tol, msg=lambda m: f"{mode}: {m}")
+    L.set_precision("tf32x3")
+    with torch.inference_mode():
+        logits = model.compute_batch_output(batch).logits_b
+    torch.testing.assert_close(logits.cpu(), want["logits_b"], rtol=0, atol=1e-3)
+
+
+def test_cnn_outside_the_tensor_core_envelope_runs_the_simt_kernel():
+    """small_hp has a 64-channel CNN with flatten > 1: the tensor-core modes must still give reference results."""
+    g = load("small_hp")
+    dev = torch.device("cuda:0")
+    model = model_from_golden(g, dev)
+    model.set_epoch_type(Epoch.VALID)
+    batch = golden_batch(g, dev)
+    from permutect_b200.engine import function as engine
+    outs = {}
+    for mode in ("fp32", "tf32x3"):
+        L.set_precision(mode)
+        try:
+            with torch.inference_mode():
+                outs[mode] = engine.forward_call(model.descriptor(), model.flat_weights(), batch)["info_seq"].clone()
+        except RuntimeError as e:       # the READ kernel may be outside its own envelope for this shape: must fail loudly, not silently
+            assert "envelope" in str(e)
+            return
+    torch.testing.assert_close(outs["tf32x3"], outs["fp32"], rtol=1e-5, atol=1e-5)
