@@ -281,8 +281,12 @@ hap_cnn_tc_kernel(const __grid_constant__ Plan TP, const unsigned char* __restri
       const int v0 = g * G, nv = min(G, n_variants - v0);
       TR(1);
       // ---- im2col rows of the first conv (batch.py:115-130): zero this warp's rows, then scatter the ones ----
-      for (int pl = 0; pl < planes0; ++pl)
-        for (int j = r_lo + lane; j < r_hi; j += 32) sts128(act + pl * PLANE_BYTES + j * 16, make_float4(0.f, 0.f, 0.f, 0.f));
+      for (int j = r_lo + lane; j < r_hi; j += 32) {
+        const unsigned ra = act + j * 16;
+#pragma unroll
+        for (int pl = 0; pl < 16; ++pl)
+          if (pl < planes0) sts128(ra + pl * PLANE_BYTES, make_float4(0.f, 0.f, 0.f, 0.f));
+      }
       __syncwarp();
       TR(3);
 #pragma unroll

@@ -568,11 +568,13 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
           case EPI_COPY_X64: {
             float v[32];
             load_cols<32>((epi == EPI_ACT_Z64 ? t_z : t_x) + half * 32, v);
+            TR(1300 + step);
             if (epi != EPI_COPY_X64) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = selu_u(v[i]);
             }
             if (half == 0) v[31] = 1.f;
+            TR(1400 + step);
             store_operand<32, PASSES>(t_hi + half * 32, t_lo + half * 32, v, true);
           } break;
         }
