@@ -43,6 +43,10 @@ FLOP_PER_READ = 66260
 FLOP_PER_ALT_READ = 500
 FLOP_PER_VARIANT = 286424
 FP32_FMA_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12      # nominal B200 FP32 pipe
+WORKLOAD = "synthetic WGS-scale inference (SURVEY §8d config 3: 10M variants / 8 GPUs)"
+# DRAM bytes of one launch of the dominant kernel at the default shard (1.25M variants), from the ncu --set full capture
+# committed under profiles/ (dram__bytes_read.sum + dram__bytes_write.sum); scaled by variants for other shard sizes.
+NCU_TRAFFIC_BYTES_PER_VARIANT = {"tf32x3": (416.508e6 + 121.597e6) / 1.25e6, "tf32": None, "fp32": None}
 
 
 def load_peaks():
@@ -162,7 +166,8 @@ def run_reference(args, rank):
         "impl": "reference", "metric": "artifact_model_inference_variants_per_sec", "value": v, "unit": "variants/s",
         "n_gpus": args.gpus, "steps": len(ts), "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "synthetic WGS-scale inference (SURVEY §8d config 3), CPU sample", "variants_per_step": sample},
+        "config": {"workload": WORKLOAD, "precision": "fp32 (torch CPU, all host threads)", "variants_per_gpu": args.variants,
+                   "hyperparameters": "artifact-model-v0.4.0", "sample_variants_per_step": sample},
         "cpu_baseline": {"value": v, "unit": "variants/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample_txt},
         "e2e": {"value": v, "unit": "variants/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -372,7 +377,11 @@ def main():
                    "tf32": "reads_forward_tc_kernel<1> (tcgen05, TF32)"}[args.precision]
     roofline = {"bound": "tensor", "kernel": kernel_name, "achieved": achieved,
                 "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16"] if achieved else None,
-                "peak_source": peaks["source"] + " bf16 dense (sustained)", "traffic": None,
+                "peak_source": peaks["source"] + " bf16 dense (sustained)",
+                "traffic": (NCU_TRAFFIC_BYTES_PER_VARIANT[args.precision] * args.variants
+                            if NCU_TRAFFIC_BYTES_PER_VARIANT[args.precision] else None),
+                "traffic_unit": "bytes per launch (ncu dram read + write, profiles/r1_tensor_core_kernels.md)",
+                "algorithmic_bytes_per_launch": 12 * n_reads + (30 * 4 + 16 + 108) * args.variants,
                 "kernel_ms": read_kernel_ms, "kernel_share_of_step": read_kernel_ms / step_ms if read_kernel_ms else None,
                 "fp32_fma_peak_tflops_nominal": FP32_FMA_PEAK_TFLOPS,
                 "frac_of_fp32_fma_peak": achieved / FP32_FMA_PEAK_TFLOPS if achieved else None,
@@ -382,7 +391,7 @@ def main():
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms_max, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "f32 (3xTF32 split on tcgen05: hi/lo operands, fp32 accumulate)", "tf32": "tf32"}[args.precision],
         "data": "synthetic",
-        "config": {"workload": "synthetic WGS-scale inference (SURVEY §8d config 3: 10M variants / 8 GPUs)",
+        "config": {"workload": WORKLOAD,
                    "precision": args.precision,
                    "variants_per_gpu": args.variants, "reads_per_gpu": n_reads, "mean_reads_per_variant": n_reads / args.variants,
                    "hyperparameters": "artifact-model-v0.4.0", "timing": "inputs larger than L2 (compressed shard "
