@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PMT_ABI_VERSION 1
+#define PMT_ABI_VERSION 2
 #define PMT_MAX_MLP_OPS 16
 #define PMT_MAX_BLOCKS 12
 #define PMT_MAX_CNN_OPS 16
@@ -111,7 +111,8 @@ typedef struct PmtModelDesc {
 typedef struct PmtBatch {
   int32_t n_variants;
   int32_t reads_kind, info_kind, hap_kind;
-  int64_t n_rows;              /* total_ref + total_alt */
+  int64_t n_rows;              /* host-side upper bound of total_ref + total_alt (grid sizing hint; <= 0: unknown).
+                                  The kernels take the exact totals from ref_off[B] / alt_off[B]. */
   int64_t total_ref;
   int64_t max_rows_per_variant;/* >= max_b(ref_count+alt_count); sizes the long-set workspace */
   const void* reads;
@@ -140,6 +141,8 @@ typedef struct PmtOutGrads {
   const float* d_logits_bk;   /* [B][K+2] */
   const float* d_alt_means_be;/* [B][E] */
   const float* d_ref_means_be;/* [B][E] */
+  const float* info_seq_be;   /* [B][d_info+d_seq] PmtOutputs.info_seq_be saved from the forward of the same batch and
+                                 weights, or NULL: the per-variant embeddings are then recomputed */
 } PmtOutGrads;
 
 const char* pmt_last_error(void);

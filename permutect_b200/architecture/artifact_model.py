@@ -116,6 +116,7 @@ class ArtifactModel(nn.Module):
         self._desc = None
         self._loss_desc = None
         self._flat_cache = None
+        self._param_list = None
 
     # ---- reference surface (artifact_model.py:199-230) -------------------------------------------------
     def reset_source_predictor(self, num_sources: int = 1):
@@ -126,6 +127,7 @@ class ArtifactModel(nn.Module):
         self._desc = None
         self._loss_desc = None
         self._flat_cache = None
+        self._param_list = None
 
     def ref_alt_seq_embedding_dimension(self) -> int:
         return self.haplotypes_cnn.output_dimension()
@@ -156,13 +158,21 @@ class ArtifactModel(nn.Module):
             self._desc = planner.build_desc(self)
         return self._desc
 
+    def _parameter_list(self):
+        """Cached list of the module's parameters (walking the module tree costs ~0.5 ms per call).  Submodules are
+        only ever replaced through reset_source_predictor, which clears the cache; load_state_dict and optimisers
+        update parameters in place, which the version counters below pick up."""
+        if self._param_list is None:
+            self._param_list = list(self.parameters())
+        return self._param_list
+
     def flat_weights(self) -> Tensor:
         """Materialised weights as one flat fp32 tensor.  With grad enabled this is a fresh autograd
         node (torch.cat of the constrained tensors); without grad it is cached until a parameter changes."""
-        needs_graph = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
-        if needs_graph:
+        params = self._parameter_list()
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
             return torch.cat([t.reshape(-1) for t in planner.materialized_tensors(self)])
-        versions = tuple(p._version for p in self.parameters()) + tuple(id(p) for p in self.parameters())
+        versions = tuple(p._version for p in params) + tuple(p.data_ptr() for p in params[:4])
         if self._flat_cache is None or self._flat_cache[0] != versions:
             with torch.no_grad():
                 flat = torch.cat([t.reshape(-1) for t in planner.materialized_tensors(self)])

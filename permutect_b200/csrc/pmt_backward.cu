@@ -943,7 +943,11 @@ extern "C" int pmt_backward(const PmtModelDesc* desc, const float* weights, cons
 
   cudaMemsetAsync(partials, 0, (size_t)kBwdGrid * desc->n_params * sizeof(float), st);
   pmt_launch_prepare(P, G, weights, image, st);
-  pmt_launch_variant_kernels(P, G, weights, image, batch, info_seq, PMT_PRECISION_FP32, nullptr, st);
+  if (grads && grads->info_seq_be) {
+    cudaMemcpyAsync(info_seq, grads->info_seq_be, (size_t)B * w * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  } else if (pmt_launch_variant_kernels(P, G, weights, image, batch, info_seq, PMT_PRECISION_FP32, nullptr, st)) {
+    return 1;
+  }
 
   int dev = 0, n_sm = 148;
   cudaGetDevice(&dev);

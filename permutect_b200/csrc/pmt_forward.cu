@@ -580,7 +580,7 @@ int pmt_launch_variant_kernels(const Plan& P, const CnnGeom& G, const float* wei
 
 static int choose_claim(const PmtBatch* batch, int n_sm) {
   // aim for ~8 tiles per claim, but keep at least ~2 claims per SM when the batch is small
-  const double avg = batch->n_variants > 0 ? (double)batch->n_rows / batch->n_variants : 1.0;
+  const double avg = (batch->n_variants > 0 && batch->n_rows > 0) ? (double)batch->n_rows / batch->n_variants : 16.0;
   int claim = (int)(8.0 * TILE / (avg + 1.0));
   const int by_parallelism = batch->n_variants / (2 * n_sm);
   if (claim > by_parallelism) claim = by_parallelism;

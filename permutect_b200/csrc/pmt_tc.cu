@@ -217,7 +217,8 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
   const int n_tiles = __ldg(A.tiles);
   const int n_slots = 2 * gridDim.x;
   // every slot of the CTA runs the same number of rounds (an idle slot processes an empty tile)
-  const int rounds = (n_tiles - 2 * (int)blockIdx.x + n_slots - 1) / n_slots;   // rounds of slot 0 >= rounds of slot 1
+  // tile t of round r: slot 0 of every CTA first, then slot 1 (a small batch spreads over the SMs before it doubles up)
+  const int rounds = n_tiles > (int)blockIdx.x ? (n_tiles - (int)blockIdx.x + n_slots - 1) / n_slots : 0;   // rounds of slot 0 >= slot 1
   const int n_steps = TP.n_steps;
   const unsigned tmem_base = __shfl_sync(0xffffffffu, S->tmem_base, 0);
   const bool l0_lo = A.batch.reads_kind != PMT_READS_U8;   // decoded reads k/32 and bits are exact in TF32
@@ -303,7 +304,7 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
     unsigned dparity = 0;
 
     for (int round = 0; round < rounds; ++round) {
-      const int t = 2 * (int)blockIdx.x + slot + round * n_slots;
+      const int t = (int)blockIdx.x + slot * (int)gridDim.x + round * n_slots;
       // ---------------- tile meta ----------------
       int v0 = 0, nv = 0;
       if (t < n_tiles) { v0 = __ldg(A.tiles + 2 + 2 * t); nv = __ldg(A.tiles + 3 + 2 * t); }
@@ -687,13 +688,14 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
 // same).  One warp per claim of PLAN_CLAIM consecutive variants; tiles never span claims.  tiles[0] = tile count
 // (reserved with one atomicAdd per claim: tile ORDER is arbitrary, results do not depend on it).
 // ------------------------------------------------------------------------------------------------
-__global__ void plan_tiles_kernel(const long long* __restrict__ ref_off, const long long* __restrict__ alt_off, int B, int* __restrict__ tiles) {
+__global__ void plan_tiles_kernel(const long long* __restrict__ ref_off, const long long* __restrict__ alt_off, int B, int claim_variants,
+                                  int* __restrict__ tiles) {
   __shared__ int buf[4][2 * PLAN_CLAIM];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int claim = blockIdx.x * 4 + w;
-  const long long c0 = (long long)claim * PLAN_CLAIM;
+  const long long c0 = (long long)claim * claim_variants;
   if (c0 >= B) return;
-  const int c1 = (int)min((long long)B, c0 + PLAN_CLAIM);
+  const int c1 = (int)min((long long)B, c0 + claim_variants);
   int v = (int)c0, n = 0;
   while (v < c1) {
     const long long r_base = __ldg(ref_off + v), a_base = __ldg(alt_off + v);
@@ -966,18 +968,24 @@ int pmt_launch_reads_tc(const Plan& P, const float* weights, const PmtBatch* bat
   unsigned char* image = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_ws) + 1023) & ~uintptr_t(1023));
   int* tiles = reinterpret_cast<int*>(image + T.image_bytes);
   cudaMemsetAsync(tiles, 0, 2 * sizeof(int), st);
-  const int n_claims = (batch->n_variants + PLAN_CLAIM - 1) / PLAN_CLAIM;
+  // planner claims: large enough that the partial last tile of a claim is a small loss, small enough that a small
+  // batch is planned by many warps (each claim is walked sequentially)
+  int claim_variants = batch->n_variants / (2 * n_sm);
+  if (claim_variants < 64) claim_variants = 64;
+  if (claim_variants > PLAN_CLAIM) claim_variants = PLAN_CLAIM;
+  const int n_claims = (batch->n_variants + claim_variants - 1) / claim_variants;
   plan_tiles_kernel<<<(n_claims + 3) / 4, 128, 0, st>>>(reinterpret_cast<const long long*>(batch->ref_off),
-                                                         reinterpret_cast<const long long*>(batch->alt_off), batch->n_variants, tiles);
+                                                         reinterpret_cast<const long long*>(batch->alt_off), batch->n_variants,
+                                                         claim_variants, tiles);
   pack_tc_kernel<<<T.n_steps, 256, 0, st>>>(P.d, T, weights, image);
   TcArgs A;
   A.wflat = weights; A.image = image; A.tiles = tiles; A.batch = *batch; A.out = *out;
-  // upper bound of the tile count (>= 1 row per variant... a tile holds >= 1 variant): size the grid from rows
-  const long long rows = batch->n_rows > 0 ? batch->n_rows : batch->n_variants;
-  long long est_tiles = rows / 100 + 1;
+  // the tile count is only known on the device: size the grid from the row-count hint (a tile holds ~110 rows of
+  // whole variants); one CTA per tile until every SM has one, the second slot of each CTA after that
+  const long long rows = batch->n_rows > 0 ? batch->n_rows : 16LL * batch->n_variants;
+  long long est_tiles = rows / 100 + n_claims;
   if (est_tiles > batch->n_variants) est_tiles = batch->n_variants;
-  int grid = (int)((est_tiles + 1) / 2);
-  if (grid > n_sm) grid = n_sm;
+  int grid = est_tiles < n_sm ? (int)est_tiles : n_sm;
   if (grid < 1) grid = 1;
   pmt_profile_begin(st);
   const int rc = mode == PMT_PRECISION_TF32 ? launch_tc<1>(P.d, T, A, grid, st) : launch_tc<3>(P.d, T, A, grid, st);

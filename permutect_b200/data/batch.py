@@ -154,7 +154,8 @@ class Batch:
         else:
             b.reads_kind = L.READS_F16 if self.reads.dtype == torch.float16 else L.READS_F32
         b.info_kind, b.hap_kind = L.F16, L.I16
-        b.n_rows = -1          # the kernels take totals from ref_off[B] / alt_off[B]
+        # exact totals come from ref_off[B] / alt_off[B] on the device; the host only knows an upper bound (grid sizing)
+        b.n_rows = int(self.read_indices.shape[0] if self.read_indices is not None else self.reads.shape[0])
         b.total_ref = -1
         b.max_rows_per_variant = self.max_rows_per_variant
         b.reads = self.reads.data_ptr()

@@ -57,7 +57,8 @@ def forward_call(desc: L.PmtModelDesc, flat: torch.Tensor, batch, want_final: bo
 
 
 def backward_call(desc: L.PmtModelDesc, flat: torch.Tensor, batch, d_logits_bk: Optional[torch.Tensor],
-                  d_alt_means: Optional[torch.Tensor], d_ref_means: Optional[torch.Tensor]) -> torch.Tensor:
+                  d_alt_means: Optional[torch.Tensor], d_ref_means: Optional[torch.Tensor],
+                  info_seq: Optional[torch.Tensor] = None) -> torch.Tensor:
     """pmt_backward: gradient of the fused pass w.r.t. the flat materialised weights."""
     lib = L.load()
     _require_cuda(flat)
@@ -65,7 +66,7 @@ def backward_call(desc: L.PmtModelDesc, flat: torch.Tensor, batch, d_logits_bk: 
     pb = batch.pmt_batch()
     ptr = lambda t: None if t is None else t.contiguous().data_ptr()
     keep = [None if t is None else t.contiguous() for t in (d_logits_bk, d_alt_means, d_ref_means)]
-    pg = L.PmtOutGrads(*[None if t is None else t.data_ptr() for t in keep])
+    pg = L.PmtOutGrads(*[None if t is None else t.data_ptr() for t in keep], None if info_seq is None else info_seq.data_ptr())
     d_flat = torch.empty_like(flat)
     need = lib.pmt_workspace_size(C.byref(desc), C.byref(pb), 1)
     if need == 0:
@@ -103,7 +104,7 @@ class FusedArtifactFunction(torch.autograd.Function):
             g[:, 1] += g_out
             g[:, 0] -= g_out * sm[:, 0]
             g[:, 2:] -= g_out[:, None] * sm[:, 1:]
-        d_flat = backward_call(ctx.desc, flat, ctx.batch, g, g_alt, g_ref)
+        d_flat = backward_call(ctx.desc, flat, ctx.batch, g, g_alt, g_ref, ctx.info_seq)
         return d_flat, None, None
 
 

@@ -7,7 +7,7 @@ missing the compute entry points raise -- there is no fallback implementation.
 import ctypes as C
 import os
 
-PMT_ABI_VERSION = 1
+PMT_ABI_VERSION = 2
 MAX_MLP_OPS, MAX_BLOCKS, MAX_CNN_OPS = 16, 12, 16
 MAX_DIM, MAX_INFO_DIM, MAX_FEAT, MAX_CLUSTERS, TILE_ROWS = 64, 128, 32, 14, 128
 
@@ -64,7 +64,7 @@ class PmtOutputs(C.Structure):
 
 
 class PmtOutGrads(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("d_logits_bk", "d_alt_means_be", "d_ref_means_be")]
+    _fields_ = [(n, C.c_void_p) for n in ("d_logits_bk", "d_alt_means_be", "d_ref_means_be", "info_seq_be")]
 
 
 MAX_HEAD_DIM = 32

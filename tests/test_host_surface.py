@@ -148,7 +148,28 @@ def test_ctypes_structs_match_header_sizes():
     assert ctypes.sizeof(L.PmtLinearOp) == 24 and ctypes.sizeof(L.PmtCnnOp) == 40 and ctypes.sizeof(L.PmtBlockOffsets) == 76
     assert ctypes.sizeof(L.PmtModelDesc) == 17 * 4 + 3 * 16 * 24 + 16 * 40 + 12 * 76 + 10 * 4
     assert ctypes.sizeof(L.PmtBatch) == 16 + 3 * 8 + 4 * 8 + 8 + 8 + 8 + 8
-    assert ctypes.sizeof(L.PmtOutputs) == 7 * 8 and ctypes.sizeof(L.PmtOutGrads) == 3 * 8
+    assert ctypes.sizeof(L.PmtOutputs) == 7 * 8 and ctypes.sizeof(L.PmtOutGrads) == 4 * 8
+
+
+def test_ctypes_structs_match_the_compiled_header(tmp_path):
+    """sizeof of every structure of include/permutect_b200.h as gcc lays it out == the ctypes mirror."""
+    import os
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    names = ["PmtLinearOp", "PmtCnnOp", "PmtBlockOffsets", "PmtModelDesc", "PmtBatch", "PmtOutputs", "PmtOutGrads",
+             "PmtLossDesc", "PmtLossBatch", "PmtLossOutputs", "PmtLossGrads"]
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "permutect_b200.h"\nint main(void) {\n' +
+                   "".join(f'  printf("{n} %zu\\n", sizeof({n}));\n' for n in names) + "  return 0;\n}\n")
+    exe = tmp_path / "sizes"
+    subprocess.run(["gcc", "-I", os.path.join(repo, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    got = dict(line.split() for line in out.strip().splitlines())
+    for n in names:
+        assert int(got[n]) == ctypes.sizeof(getattr(L, n)), n
 
 
 def test_workspace_size_is_positive_without_a_gpu():
