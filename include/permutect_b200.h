@@ -264,6 +264,16 @@ int pmt_adamw_step(float* params, const float* grads, float* exp_avg, float* exp
                    const float* mask, int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, float max_norm,
                    float* total_norm_out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- inference caller tail --------------------------------------------------------------------------
+ * Replaces the per-variant Python loop of generate_posterior_data (tools/filter_variants.py:302-320): for every
+ * variant, int_out[n_int_columns] = its int16 record with REF_COUNT / ALT_COUNT zeroed, float_out[6 + d_feat] (fp32,
+ * the dtype np.hstack gives the Datum, datum.py:239-240, and the posterior memory map is created with,
+ * memory_mapped_data.py:321) = the six fp16 scalars, slot 5 (CACHED_ARTIFACT_LOGIT) = the fp16-rounded artifact
+ * logit (datum.py:207-208, quirk Q6), then the embedding row of features_be. */
+int pmt_pack_posterior(const int16_t* int_array, int64_t int_stride, int32_t n_int_columns, const void* float_array_f16,
+                       int64_t float_stride, const float* logits_b, const float* features_be, int32_t d_feat,
+                       int32_t n_variants, int16_t* int_out, float* float_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

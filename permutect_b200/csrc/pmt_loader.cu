@@ -88,3 +88,55 @@ extern "C" int pmt_downsample_fill(const int64_t* ref_off, const int64_t* alt_of
   PMT_CHECK(e == cudaSuccess, "pmt_downsample_fill launch failed: %s", cudaGetErrorString(e));
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Inference caller tail: the per-variant loop of generate_posterior_data (filter_variants.py:302-320) as one pass.
+// int_out = the variant's int16 record with both counts zeroed; float_out (fp32, as np.hstack promotes it,
+// datum.py:239-240) = the six fp16 scalars with the fp16-rounded artifact logit in slot 5 (quirk Q6), then the embedding.
+// ------------------------------------------------------------------------------------------------
+// fp16 -> fp32 keeping a NaN's payload the way numpy's astype does (hardware conversion canonicalises NaNs)
+__device__ __forceinline__ float half_bits_to_float(unsigned short h) {
+  if ((h & 0x7C00u) == 0x7C00u && (h & 0x03FFu) != 0u)
+    return __uint_as_float(((unsigned)(h & 0x8000u) << 16) | 0x7F800000u | ((unsigned)(h & 0x03FFu) << 13));
+  return __half2float(__ushort_as_half(h));
+}
+// fp32 -> fp16 -> fp32 (round to nearest even); a NaN becomes numpy's quiet NaN 0x7e00
+__device__ __forceinline__ float round_through_half(float x) {
+  if (x != x) return __uint_as_float((__float_as_uint(x) & 0x80000000u) | 0x7FC00000u);
+  return __half2float(__float2half_rn(x));
+}
+
+__global__ void pack_posterior_kernel(const int16_t* __restrict__ int_in, long long int_stride, int n_int,
+                                      const __half* __restrict__ float_in, long long float_stride,
+                                      const float* __restrict__ logits, const float* __restrict__ features, int E, int n_variants,
+                                      int16_t* __restrict__ int_out, float* __restrict__ float_out) {
+  const int wf = 6 + E;
+  const long long total = (long long)n_variants * (n_int + wf);
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long v = idx / (n_int + wf);
+    const int c = (int)(idx - v * (n_int + wf));
+    if (c < n_int) {
+      int_out[v * n_int + c] = c < 2 ? (int16_t)0 : int_in[v * int_stride + c];
+    } else {
+      const int f = c - n_int;
+      float val;
+      if (f == 5) val = round_through_half(logits[v]);
+      else if (f < 6) val = half_bits_to_float(__half_as_ushort(float_in[v * float_stride + f]));
+      else val = features[v * E + (f - 6)];
+      float_out[v * wf + f] = val;
+    }
+  }
+}
+
+extern "C" int pmt_pack_posterior(const int16_t* int_array, int64_t int_stride, int32_t n_int_columns, const void* float_array_f16,
+                                  int64_t float_stride, const float* logits_b, const float* features_be, int32_t d_feat,
+                                  int32_t n_variants, int16_t* int_out, float* float_out, void* stream) {
+  if (n_variants <= 0) return 0;
+  const long long total = (long long)n_variants * (n_int_columns + 6 + d_feat);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  pack_posterior_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      int_array, int_stride, n_int_columns, reinterpret_cast<const __half*>(float_array_f16), float_stride, logits_b, features_be,
+      d_feat, n_variants, int_out, float_out);
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}

@@ -75,3 +75,16 @@ class Datum:
 
     def get_alt_reads_re(self):
         return self.reads_re[len(self.reads_re) - int(self.int_array[Data.ALT_COUNT.idx]):]
+
+    def get_reads_array_re(self):
+        return self.reads_re
+
+    @classmethod
+    def from_posterior_record(cls, int_array: np.ndarray, float_array: np.ndarray, empty_reads: np.ndarray) -> "Datum":
+        """A posterior record (filter_variants.py:302-320) keeps the fp32 float array np.hstack gave it in the
+        reference (datum.py:239-240); the constructor's fp16 cast must not be applied to it."""
+        self = cls.__new__(cls)
+        self.int_array = np.asarray(int_array, dtype=INTEGER_DTYPE)
+        self.float_array = np.asarray(float_array)
+        self.reads_re = empty_reads
+        return self
