@@ -274,6 +274,15 @@ int pmt_pack_posterior(const int16_t* int_array, int64_t int_stride, int32_t n_i
                        int64_t float_stride, const float* logits_b, const float* features_be, int32_t d_feat,
                        int32_t n_variants, int16_t* int_out, float* float_out, void* stream);
 
+/* ---- batch assembly from the dataset memory maps ----------------------------------------------------
+ * Replaces the row re-stacking of Batch.__init__ (batch.py:41-62) for batches cut from a MemoryMappedData
+ * (memory_mapped_data.py:36-58, reads_dataset.py:109-196): the reads memory map holds, variant after variant, the ref
+ * rows then the alt rows; a batch is shipped as the contiguous slice of that map and read_indices[n_rows] receives,
+ * for every batch row (all ref rows by variant, then all alt rows, batch.py:45-47), its row in the slice.
+ * ref_off / alt_off: exclusive prefix sums [n_variants + 1] of the variants' counts (device). */
+int pmt_dataset_read_indices(const int64_t* ref_off, const int64_t* alt_off, int32_t n_variants, int64_t* read_indices,
+                             void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -140,3 +140,34 @@ extern "C" int pmt_pack_posterior(const int16_t* int_array, int64_t int_stride, 
       d_feat, n_variants, int_out, float_out);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Batch assembly from the dataset's memory maps (reads_dataset.py:109-196 + Batch.__init__, batch.py:41-62).
+// The reads memory map stores, variant after variant, the ref rows then the alt rows of each variant
+// (memory_mapped_data.py:36-44); a Batch wants all ref rows of all variants, then all alt rows (batch.py:45-47).
+// Instead of re-stacking rows on the host, the contiguous slice of the memory map is shipped as it is and this
+// kernel writes the gather indices batch row -> slice row; the read kernels consume them as they do a
+// DownsampledBatch's read_indices.
+// ------------------------------------------------------------------------------------------------
+__global__ void dataset_read_indices_kernel(const long long* __restrict__ ref_off, const long long* __restrict__ alt_off,
+                                            int n_variants, long long* __restrict__ read_indices) {
+  const long long total_ref = ref_off[n_variants];
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < n_variants; v += gridDim.x * blockDim.x) {
+    const long long r0 = ref_off[v], a0 = alt_off[v];
+    const long long nr = ref_off[v + 1] - r0, na = alt_off[v + 1] - a0;
+    const long long start = r0 + a0;                     // rows of all earlier variants
+    for (long long i = 0; i < nr; ++i) read_indices[r0 + i] = start + i;
+    for (long long j = 0; j < na; ++j) read_indices[total_ref + a0 + j] = start + nr + j;
+  }
+}
+
+extern "C" int pmt_dataset_read_indices(const int64_t* ref_off, const int64_t* alt_off, int32_t n_variants, int64_t* read_indices,
+                                        void* stream) {
+  if (n_variants <= 0) return 0;
+  int blocks = (n_variants + 127) / 128;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  dataset_read_indices_kernel<<<blocks, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const long long*>(ref_off), reinterpret_cast<const long long*>(alt_off), n_variants,
+      reinterpret_cast<long long*>(read_indices));
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}

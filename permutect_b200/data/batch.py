@@ -37,6 +37,16 @@ class Batch:
         self._init_from_arrays(int_array, float_array, reads)
         return self
 
+    @classmethod
+    def from_dataset_slice(cls, int_array: np.ndarray, float_array: np.ndarray, reads: np.ndarray) -> "Batch":
+        """Batch cut from a dataset's memory maps: ``reads`` is the CONTIGUOUS slice of the reads map for these variants,
+        still in dataset order (variant after variant: its ref rows, then its alt rows; memory_mapped_data.py:36-44).
+        No host re-stacking: on the device pmt_dataset_read_indices maps batch rows (batch.py:45-47) onto the slice."""
+        self = cls.__new__(cls)
+        self._init_from_arrays(int_array, float_array, reads)
+        self._dataset_order = True
+        return self
+
     def _init_from_arrays(self, int_array, float_array, reads):
         assert int_array.dtype == np.int16 and float_array.dtype == np.float16
         self.int_tensor = torch.from_numpy(np.ascontiguousarray(int_array))
@@ -47,6 +57,7 @@ class Batch:
         assert counts[:, 0].sum() + counts[:, 1].sum() == len(reads), "read rows do not match ref+alt counts"
         self.max_rows_per_variant = int((counts[:, 0] + counts[:, 1]).max()) if len(counts) else 0
         self.read_indices = None
+        self._dataset_order = False
         self._finish_initialization_from_arrays()
 
     def _finish_initialization_from_arrays(self):
@@ -86,7 +97,13 @@ class Batch:
         """Decoded reads [N, F] float32 (batch.py:132-133), produced on demand by the decode kernel."""
         if self._decoded is None:
             self._decoded = self._decode()
-        return self._decoded if self.read_indices is None else self._decoded[self.read_indices]
+        if self.read_indices is None:
+            return self._decoded
+        idx = self.read_indices
+        if self._device_counts is not None:      # downsampled: only the first sum(counts) indices are meaningful
+            n_rows = int(self._device_counts[0].sum() + self._device_counts[1].sum())   # API-parity accessor: may synchronise
+            idx = idx[:n_rows]
+        return self._decoded[idx]
 
     def _decode(self) -> torch.Tensor:
         if not self.reads_are_compressed:
@@ -121,7 +138,18 @@ class Batch:
             new_batch.read_indices = self.read_indices.to(device, non_blocking=non_blocking)
         new_batch._offsets = None
         new_batch._decoded = None
+        new_batch.finalize_on_device()
         return new_batch
+
+    def finalize_on_device(self):
+        """Device-side part of batch assembly: gather indices for reads that arrived in dataset order."""
+        if not getattr(self, "_dataset_order", False) or self.read_indices is not None or self.reads.device.type != "cuda":
+            return
+        ref_off, alt_off = self.offsets()
+        dev = self.reads.device
+        self.read_indices = torch.empty(self.reads.shape[0], dtype=torch.int64, device=dev)
+        L.check(L.load().pmt_dataset_read_indices(ref_off.data_ptr(), alt_off.data_ptr(), self._size, self.read_indices.data_ptr(),
+                                                  torch.cuda.current_stream(dev).cuda_stream))
 
     def h2d_bytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in (self.reads, self.int_tensor, self.float_tensor))
@@ -198,3 +226,8 @@ class DownsampledBatch(Batch):
             self._device_counts = (ref_c, alt_c)
             self._offsets = new_off
         self.ref_counts, self.alt_counts = self._device_counts
+        self._dataset_order = False
+        if original_batch.read_indices is not None:
+            # the parent's rows are themselves reached through gather indices (a dataset-order batch): compose them.
+            # (entries past the kept rows are zero, a valid index)
+            self.read_indices = original_batch.read_indices[self.read_indices]

@@ -61,11 +61,14 @@ def prefetch_generator(dataloader: Iterable[Batch], device=None, depth: int = 2)
             setattr(batch_gpu, name, dst)
         batch_gpu._offsets = None
         batch_gpu._decoded = None
+        if getattr(batch_cpu, "_dataset_order", False):
+            batch_gpu.read_indices = None
         queue.append((batch_gpu, done, slot))
 
     def hand_over():
         batch_gpu, done, slot = queue.pop(0)
         torch.cuda.current_stream(device).wait_event(done)
+        batch_gpu.finalize_on_device()      # e.g. gather indices of a dataset-order batch, on the consumer's stream
         return batch_gpu, slot
 
     def release(slot: _Slot):
