@@ -42,6 +42,7 @@ constexpr int NP1 = 24;     // padded width of one proj1 weight set (>= 2 * MAXH
 constexpr int MAXE = 16;    // final feature dimension
 constexpr int MAXK = 6;     // artifact clusters
 constexpr int XCH_ROWS = MAXE + MAXK + 2;
+constexpr int XCH_LD = TILE + 1;   // odd row stride: the per-variant gathers read one column range of MANY rows at once
 constexpr int NS_MAX = 8;
 constexpr int PLAN_CLAIM = 512;   // variants per planner claim
 
@@ -169,7 +170,7 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
   // carve: [weight ring: n_stages x stage_bytes][xch 2 slots][sums 2 slots][pair exchange][block scalars][HeadConst][Shared]
   unsigned char* p = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const unsigned ring = smem_addr(p); p += (size_t)n_stages * stage_bytes;
-  const unsigned xch_all = smem_addr(p); p += 2 * XCH_ROWS * TILE * sizeof(float);
+  const unsigned xch_all = smem_addr(p); p += 2 * XCH_ROWS * XCH_LD * sizeof(float);
   const unsigned sums_all = smem_addr(p); p += 2 * SUMS_FLOATS * sizeof(float);
   const unsigned pairx_all = smem_addr(p); p += 2 * 2 * TILE * 2 * sizeof(float);
   float* blkc = reinterpret_cast<float*>(p); p += PMT_MAX_BLOCKS * BC_STRIDE * sizeof(float);
@@ -289,7 +290,7 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
     SlotMeta* M = &S->slot[slot];
     const unsigned m_rowvar = smem_addr(M->rowvar), m_ref_start = smem_addr(M->ref_start), m_ref_cnt = smem_addr(M->ref_cnt),
                    m_alt_start = smem_addr(M->alt_start), m_alt_cnt = smem_addr(M->alt_cnt);
-    const unsigned xch = xch_all + slot * XCH_ROWS * TILE * 4;      // [XCH_ROWS][TILE] floats
+    const unsigned xch = xch_all + slot * XCH_ROWS * XCH_LD * 4;    // [XCH_ROWS][XCH_LD] floats
     const unsigned sums = sums_all + slot * SUMS_FLOATS * 4;        // [segment = 2 * variant + side][MAXH]
     const unsigned px_mine = pairx_all + ((slot * 2 + half) * TILE + row) * 8, px_other = pairx_all + ((slot * 2 + (half ^ 1)) * TILE + row) * 8;
     const unsigned bar_a = smem_addr(&S->bar_a[slot]), bar_d = smem_addr(&S->bar_d[slot]);
@@ -504,7 +505,7 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
               // z2[k0 + j]: k0 is 0 or 6 -> select between two compile-time registers
               const float zz = half ? z2[j + 6] : z2[j];
               z2n[j] = (zz - mean) * rstd * lds_f32(bcs + (BC_LN2W + k0 + j) * 4) + lds_f32(bcs + (BC_LN2B + k0 + j) * 4);
-              if (k0 + j < H) sts_f32(xch + ((k0 + j) * TILE + row) * 4, z2n[j]);
+              if (k0 + j < H) sts_f32(xch + ((k0 + j) * XCH_LD + row) * 4, z2n[j]);
             }
             TR(900 + step);
             named_barrier(slot_bar, 256);
@@ -516,13 +517,21 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
                 const int seg = (int)(((unsigned)idx * inv_h) >> 16), f = idx - seg * H;
                 const int j = seg >> 1, s = seg & 1;
                 const int start = (int)lds_u8((s ? m_alt_start : m_ref_start) + j), cnt = (int)lds_u8((s ? m_alt_cnt : m_ref_cnt) + j);
-                const unsigned src = xch + (f * TILE + start) * 4;
-                float a0 = 0.f, a1 = 0.f;
-                int i = 0;
-                for (; i + 1 < cnt; i += 2) { a0 += lds_f32(src + i * 4); a1 += lds_f32(src + i * 4 + 4); }
-                if (i < cnt) a0 += lds_f32(src + i * 4);
-                const float acc = a0 + a1;
-                const float m = s == 0 ? (acc + regw * lds_f32(bcs + (BC_REG + f) * 4)) / ((float)cnt + regw) : acc / ((float)cnt + 1e-4f);
+                const unsigned src = xch + (f * XCH_LD + start) * 4;
+                // four independent loads per trip (the tail reads inside the exchange buffer and is masked): the trip count
+                // of a warp is that of its longest set, so the loads of a trip must not wait for each other
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                for (int i = 0; i < cnt; i += 4) {
+                  const float v0 = lds_f32(src + i * 4), v1 = lds_f32(src + i * 4 + 4), v2 = lds_f32(src + i * 4 + 8), v3 = lds_f32(src + i * 4 + 12);
+                  a0 += v0;
+                  a1 += i + 1 < cnt ? v1 : 0.f;
+                  a2 += i + 2 < cnt ? v2 : 0.f;
+                  a3 += i + 3 < cnt ? v3 : 0.f;
+                }
+                const float acc = (a0 + a1) + (a2 + a3);
+                const float num = s == 0 ? acc + regw * lds_f32(bcs + (BC_REG + f) * 4) : acc;
+                const float den = (float)cnt + (s == 0 ? regw : 1e-4f);
+                const float m = num / den;
                 sts_f32(sums + (seg * MAXH + f) * 4, m);
               }
             }
@@ -598,7 +607,7 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
       load_cols<MAXE>(t_z, f);
       if (half == 0) {
 #pragma unroll
-        for (int i = 0; i < MAXE; ++i) if (i < E) sts_f32(xch + (i * TILE + row) * 4, f[i]);
+        for (int i = 0; i < MAXE; ++i) if (i < E) sts_f32(xch + (i * XCH_LD + row) * 4, f[i]);
         if (A.out.final_re && my_idx >= 0) {
 #pragma unroll
           for (int e = 0; e < MAXE; ++e) if (e < E) A.out.final_re[my_idx * E + e] = f[e];
@@ -613,8 +622,8 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
               const float a = f[e] / HC->sigma[e], b = f[e] / (2.f * HC->sigma[e]);
               q = fmaf(a, a, q); q2 = fmaf(b, b, q2);
             }
-          sts_f32(xch + ((MAXE + 0) * TILE + row) * 4, HC->c_non - q / 2.f);
-          sts_f32(xch + ((MAXE + 1) * TILE + row) * 4, HC->c_out - q2 / 2.f);
+          sts_f32(xch + ((MAXE + 0) * XCH_LD + row) * 4, HC->c_non - q / 2.f);
+          sts_f32(xch + ((MAXE + 1) * XCH_LD + row) * 4, HC->c_out - q2 / 2.f);
         } else {
           for (int k = 0; k < K; ++k) {
             const float* u = W + D.unit_ke + k * E;
@@ -628,7 +637,7 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
             const float ll_orth = HC->c_orth[k] - (dist * dist) / HC->two_tau2[k];
             const float ll_par = HC->log_half_lambda[k] + logerfc((HC->shift[k] - pr) / HC->sqrt2_sigma[k]) +
                                  HC->half_lambda[k] * (HC->two_mu_plus[k] - 2.f * pr);
-            sts_f32(xch + ((MAXE + 2 + k) * TILE + row) * 4, ll_orth + ll_par);
+            sts_f32(xch + ((MAXE + 2 + k) * XCH_LD + row) * 4, ll_orth + ll_par);
           }
         }
       }
@@ -638,7 +647,7 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
         const int seg = (int)(((unsigned)idx * inv_e) >> 16), e = idx - seg * E;
         const int j = seg >> 1, s = seg & 1;
         const int start = (int)lds_u8((s ? m_alt_start : m_ref_start) + j), cnt = (int)lds_u8((s ? m_alt_cnt : m_ref_cnt) + j);
-        const unsigned src = xch + (e * TILE + start) * 4;
+        const unsigned src = xch + (e * XCH_LD + start) * 4;
         float acc = 0.f;
         for (int i = 0; i < cnt; ++i) acc += lds_f32(src + i * 4);
         float* dst = s ? A.out.alt_means_be : A.out.ref_means_be;
@@ -653,7 +662,7 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
         for (int k = 0; k < MAXK + 2; ++k) {
           float acc = 0.f;
           if (k < K + 2) {
-            const unsigned src = xch + ((MAXE + k) * TILE + as) * 4;
+            const unsigned src = xch + ((MAXE + k) * XCH_LD + as) * 4;
             for (int i = 0; i < ac; ++i) acc += lds_f32(src + i * 4);
           }
           ll[k] = acc;
@@ -943,7 +952,7 @@ extern "C" int pmt_set_reads_trace(long long* device_buffer) { g_reads_trace = d
 template <int PASSES>
 static int launch_tc(const PmtModelDesc& D, const TcPlan& T, const TcArgs& A, int grid, cudaStream_t st) {
   const int stage_bytes = PASSES == 3 ? T.slot_bytes : T.slot_bytes / 2;
-  const size_t fixed = 2 * XCH_ROWS * TILE * sizeof(float) + 2 * SUMS_FLOATS * sizeof(float) + 2 * 2 * TILE * 2 * sizeof(float) +
+  const size_t fixed = 2 * XCH_ROWS * XCH_LD * sizeof(float) + 2 * SUMS_FLOATS * sizeof(float) + 2 * 2 * TILE * 2 * sizeof(float) +
                        PMT_MAX_BLOCKS * BC_STRIDE * sizeof(float) + sizeof(HeadConst) + sizeof(Shared) + 1024 + 64;
   int n_stages = (int)((227 * 1024 - fixed) / stage_bytes);
   if (n_stages > NS_MAX) n_stages = NS_MAX;
