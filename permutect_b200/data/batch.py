@@ -164,9 +164,10 @@ class Batch:
         """Exclusive prefix sums [B+1] (int64) of the ref and alt counts, on the batch's device."""
         if self._offsets is None:
             ref_counts, alt_counts = self.counts()
-            both = torch.stack((ref_counts, alt_counts)).to(torch.int64)
-            off = torch.zeros((2, self._size + 1), dtype=torch.int64, device=both.device)
-            torch.cumsum(both, dim=1, out=off[:, 1:])
+            off = torch.zeros((2, self._size + 1), dtype=torch.int64, device=ref_counts.device)
+            # two 1-D scans (single-pass device scan); a [2, B] scan along dim 1 takes torch's generic kernel, 50x slower
+            torch.cumsum(ref_counts.to(torch.int64), dim=0, out=off[0, 1:])
+            torch.cumsum(alt_counts.to(torch.int64), dim=0, out=off[1, 1:])
             self._offsets = off
         return self._offsets[0], self._offsets[1]
 

@@ -33,7 +33,8 @@ def downsample_on_device(parent, ref_fracs_b: torch.Tensor, alt_fracs_b: torch.T
     L.check(lib.pmt_downsample_counts(ref_off.data_ptr(), alt_off.data_ptr(), rf.data_ptr(), af.data_ptr(), B, seed,
                                       random_int, counts[0].data_ptr(), counts[1].data_ptr(), stream))
     new_off = torch.zeros((2, B + 1), dtype=torch.int64, device=dev)
-    torch.cumsum(counts, dim=1, out=new_off[:, 1:])
+    torch.cumsum(counts[0], dim=0, out=new_off[0, 1:])      # 1-D scans: single-pass device scan
+    torch.cumsum(counts[1], dim=0, out=new_off[1, 1:])
     read_indices = torch.zeros(parent.reads.shape[0], dtype=torch.int64, device=dev)   # the tail past N' stays a valid index
     L.check(lib.pmt_downsample_fill(ref_off.data_ptr(), alt_off.data_ptr(), rf.data_ptr(), af.data_ptr(), B, seed,
                                     random_int, new_off[0].data_ptr(), new_off[1].data_ptr(), int(offset_alt_rows),
