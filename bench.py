@@ -78,11 +78,12 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
-    def stop(self):
+    def stop(self, extra_rows=()):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
+        self.rows = list(extra_rows) + self.rows
         sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
         mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -302,7 +303,7 @@ def main():
             model.compute_batch_output(dev_batch)
         ev1.record()
         barrier()
-        clocks = sampler.stop()
+        sampler.stop()
         step_ms = ev0.elapsed_time(ev1) / args.steps
         read_kernel_ms = prof.mean_ms()
     t = torch.tensor([step_ms], device=dev)
@@ -335,12 +336,15 @@ def main():
         for _ in range(2):
             e2e_pass()
         barrier()
+        sampler2 = ClockSampler(local_rank)
+        sampler2.start()
         ev0.record()
         for _ in range(args.steps):
             e2e_pass()
         ev1.record()
         barrier()
         e2e_ms = ev0.elapsed_time(ev1) / args.steps
+    clocks = sampler2.stop(extra_rows=sampler.rows)      # samples of both timed regions (resident steps, e2e pipeline)
     t = torch.tensor([e2e_ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
