@@ -24,18 +24,39 @@ def _fingerprint() -> str:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compiles every translation unit for sm_100a (in parallel, objects under csrc/build/) and links the shared library."""
+    from concurrent.futures import ThreadPoolExecutor
     stamp = OUTPUT + ".stamp"
     fp = _fingerprint()
     if not force and os.path.exists(OUTPUT) and os.path.exists(stamp) and open(stamp).read() == fp:
         return OUTPUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", OUTPUT] + [os.path.join(HERE, s) for s in SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    log = res.stdout + res.stderr
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"]
+
+    def compile_one(src):
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        cmd = [nvcc] + compile_flags + ["-c", "-o", obj, os.path.join(HERE, src)]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        return src, obj, " ".join(cmd), res
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
+    log = ""
+    for src, obj, cmd, res in results:
+        log += cmd + "\n" + res.stdout + res.stderr
+    failed = [src for src, _, _, res in results if res.returncode != 0]
+    if not failed:
+        link = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-o", OUTPUT] + [r[1] for r in results]
+        res = subprocess.run(link, capture_output=True, text=True)
+        log += " ".join(link) + "\n" + res.stdout + res.stderr
+        if res.returncode != 0:
+            failed = ["link"]
     with open(os.path.join(HERE, "build.log"), "w") as f:
-        f.write(" ".join(cmd) + "\n" + log)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + log[-4000:])
+        f.write(log)
+    if failed:
+        raise RuntimeError(f"nvcc failed ({', '.join(failed)}):\n" + log[-4000:])
     if verbose:
         print(log)
     with open(stamp, "w") as f:
