@@ -389,7 +389,12 @@ def main():
                 "kernel_ms": read_kernel_ms, "kernel_share_of_step": read_kernel_ms / step_ms if read_kernel_ms else None,
                 "fp32_fma_peak_tflops_nominal": FP32_FMA_PEAK_TFLOPS,
                 "frac_of_fp32_fma_peak": achieved / FP32_FMA_PEAK_TFLOPS if achieved else None,
-                "flop_per_launch": flops}
+                "flop_per_launch": flops,
+                # what the tensor pipe actually executes for those algorithmic FLOP: zero-padded shapes (61->64, 30->32,
+                # 60->64, 20->2x24, 10->16) and, in the split-precision mode, three TF32 MMAs per k-step
+                "executed_tensor_flop_per_launch": 2 * 53248 * n_reads * (3 if args.precision == "tf32x3" else 1)
+                if args.precision != "fp32" else None,
+                "tf32_mma_peak_tflops_probe": 148 * 4096 * 1.965e9 / 1e12}
     result = {
         "metric": "artifact_model_inference_variants_per_sec", "value": value, "unit": "variants/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms_max, "higher_is_better": True,
@@ -404,6 +409,9 @@ def main():
         "e2e": {"value": e2e_value, "unit": "variants/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * args.variants},
         "roofline": roofline,
     }
+    if roofline.get("executed_tensor_flop_per_launch") and read_kernel_ms:
+        roofline["executed_tensor_tflops"] = roofline["executed_tensor_flop_per_launch"] / (read_kernel_ms / 1e3) / 1e12
+        roofline["frac_of_tf32_mma_peak_executed"] = roofline["executed_tensor_tflops"] / roofline["tf32_mma_peak_tflops_probe"]
     if parity is not None:
         result["parity"] = parity
     if train is not None:

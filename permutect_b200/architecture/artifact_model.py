@@ -117,6 +117,7 @@ class ArtifactModel(nn.Module):
         self._loss_desc = None
         self._flat_cache = None
         self._param_list = None
+        self._materialization_cache = None
 
     # ---- reference surface (artifact_model.py:199-230) -------------------------------------------------
     def reset_source_predictor(self, num_sources: int = 1):
@@ -128,6 +129,7 @@ class ArtifactModel(nn.Module):
         self._loss_desc = None
         self._flat_cache = None
         self._param_list = None
+        self._materialization_cache = None
 
     def ref_alt_seq_embedding_dimension(self) -> int:
         return self.haplotypes_cnn.output_dimension()

@@ -32,19 +32,34 @@ def _owner_and_attr(model, name: str):
     return module, attr
 
 
+def _materialization_recipe(model):
+    """[(parameter, owner module or None, attribute)] in named_parameters() order, cached on the model (walking the
+    module tree and splitting names costs ~1 ms per call).  Invalidated together with the descriptor."""
+    recipe = getattr(model, "_materialization_cache", None)
+    if recipe is None:
+        recipe = []
+        for name, p in model.named_parameters():
+            if _PARAM_TAG in name:
+                module, attr = _owner_and_attr(model, name)
+                recipe.append((p, module, attr))
+            else:
+                recipe.append((p, None, None))
+        model._materialization_cache = recipe
+    return recipe
+
+
 def materialized_tensors(model) -> List[torch.Tensor]:
     """Tensors to concatenate into the flat weight buffer (autograd-connected to the raw parameters)."""
     out = []
-    for name, p in model.named_parameters():
-        if _PARAM_TAG in name:
-            module, attr = _owner_and_attr(model, name)
-            t = getattr(module, attr)                       # evaluates the parametrisation
-            if attr == "artifact_directions_ke":
-                # the head normalises the (already unit) directions once more (feature_clustering.py:24, quirk Q5)
-                t = t / torch.norm(t, dim=-1, keepdim=True)
-            out.append(t)
-        else:
+    for p, module, attr in _materialization_recipe(model):
+        if module is None:
             out.append(p)
+            continue
+        t = getattr(module, attr)                       # evaluates the parametrisation
+        if attr == "artifact_directions_ke":
+            # the head normalises the (already unit) directions once more (feature_clustering.py:24, quirk Q5)
+            t = t / torch.norm(t, dim=-1, keepdim=True)
+        out.append(t)
     return out
 
 

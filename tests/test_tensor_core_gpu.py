@@ -123,3 +123,28 @@ def test_cnn_outside_the_tensor_core_envelope_runs_the_simt_kernel():
             assert "envelope" in str(e)
             return
     torch.testing.assert_close(outs["tf32x3"], outs["fp32"], rtol=1e-5, atol=1e-5)
+
+
+def test_sharded_evaluation_is_bitwise_identical_to_one_batch():
+    """Size-independent property (variants are independent): evaluating contiguous variant shards separately
+    gives bit-identical logits to one big batch, however the tile planner packs them."""
+    from permutect_b200.data.batch import Batch
+    from permutect_b200.synthetic import make_wgs_arrays
+    g = load("v040_perturbed_edge")
+    dev = torch.device("cuda:0")
+    model = model_from_golden(g, dev)
+    model.set_epoch_type(Epoch.VALID)
+    n = 40_000
+    ia, fa, reads = make_wgs_arrays(n, seed=99)
+    ref_off = np.concatenate(([0], np.cumsum(ia[:, 0].astype(np.int64))))
+    alt_off = np.concatenate(([0], np.cumsum(ia[:, 1].astype(np.int64))))
+    total_ref = int(ref_off[-1])
+    L.set_precision("tf32x3")
+    with torch.inference_mode():
+        whole = model.compute_batch_output(Batch.from_arrays(ia, fa, reads).copy_to(dev))
+        parts = []
+        for v0, v1 in ((0, 1), (1, 12_345), (12_345, 12_409), (12_409, n)):
+            sub = np.concatenate((reads[ref_off[v0]:ref_off[v1]], reads[total_ref + alt_off[v0]:total_ref + alt_off[v1]]))
+            parts.append(model.compute_batch_output(Batch.from_arrays(ia[v0:v1], fa[v0:v1], sub).copy_to(dev)))
+    for name in ("logits_b", "features_be", "ref_features_be", "logits_bk"):
+        assert torch.equal(torch.cat([getattr(p, name) for p in parts]), getattr(whole, name)), name
