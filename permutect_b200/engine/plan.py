@@ -32,6 +32,38 @@ def _owner_and_attr(model, name: str):
     return module, attr
 
 
+def _orthogonal_without_sync(module, attr):
+    """The rotation matrix of torch's ``orthogonal`` parametrisation (matrix-exponential map, square weight) evaluated
+    without ``torch.matrix_exp``: that routine picks its Pade degree from a norm it reads back on the host, i.e. it
+    synchronises the device twice per training step (forward and backward).  Here: scaling and squaring with FIXED
+    parameters in float64 (Taylor degree 14 of A / 2^6, six squarings), exact to fp32 rounding for ||A|| up to ~64 and
+    differentiable by autograd.  Mirrors torch/nn/utils/parametrizations.py:_Orthogonal.forward.
+    Returns None when the parametrisation is something else."""
+    plist = getattr(getattr(module, "parametrizations", None), attr, None) if hasattr(module, "parametrizations") else None
+    if plist is None or len(plist) != 1:
+        return None
+    orth = plist[0]
+    if type(orth).__name__ != "_Orthogonal" or getattr(getattr(orth, "orthogonal_map", None), "name", "") != "matrix_exp":
+        return None
+    X = plist.original
+    if X.dim() != 2 or X.shape[0] != X.shape[1]:
+        return None
+    Xl = X.double().tril()
+    A = Xl - Xl.mT
+    n = A.shape[0]
+    eye = torch.eye(n, dtype=A.dtype, device=A.device)
+    B = A * (2.0 ** -6)
+    T = eye + B / 14.0
+    for k in range(13, 0, -1):
+        T = eye + (B @ T) / float(k)
+    for _ in range(6):
+        T = T @ T
+    Q = T.to(X.dtype)
+    if hasattr(orth, "base"):
+        Q = orth.base @ Q
+    return Q
+
+
 def _materialization_recipe(model):
     """[(parameter, owner module or None, attribute)] in named_parameters() order, cached on the model (walking the
     module tree and splitting names costs ~1 ms per call).  Invalidated together with the descriptor."""
@@ -55,7 +87,9 @@ def materialized_tensors(model) -> List[torch.Tensor]:
         if module is None:
             out.append(p)
             continue
-        t = getattr(module, attr)                       # evaluates the parametrisation
+        t = _orthogonal_without_sync(module, attr)
+        if t is None:
+            t = getattr(module, attr)                   # evaluates the parametrisation
         if attr == "artifact_directions_ke":
             # the head normalises the (already unit) directions once more (feature_clustering.py:24, quirk Q5)
             t = t / torch.norm(t, dim=-1, keepdim=True)

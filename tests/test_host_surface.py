@@ -186,3 +186,24 @@ def test_compute_requires_cuda():
     model = model_from_golden(g, CPU)
     with pytest.raises(RuntimeError):
         model.compute_batch_output(golden_batch(g, None))
+
+
+def test_sync_free_rotation_equals_torch_orthogonal():
+    """engine/plan.py evaluates the orthogonal parametrisation without torch.matrix_exp (which synchronises the device);
+    value and gradient must agree with torch's own."""
+    from permutect_b200.engine.plan import _orthogonal_without_sync
+    model = model_from_golden(load("v040_seed0_b64"), CPU)
+    rot = model.pre_clustering_transform.rotation_ee
+    gen = torch.Generator().manual_seed(0)
+    for scale in (0.0, 0.3, 2.0, 6.0):
+        with torch.no_grad():
+            rot.parametrizations.weight.original.copy_(scale * torch.randn(rot.parametrizations.weight.original.shape, generator=gen))
+        want = rot.weight
+        got = _orthogonal_without_sync(rot, "weight")
+        assert got is not None
+        torch.testing.assert_close(got, want, rtol=0, atol=3e-6)
+        torch.testing.assert_close(got @ got.T, torch.eye(got.shape[0]), rtol=0, atol=5e-6)
+        w = torch.randn(want.shape, generator=gen)
+        g_want, = torch.autograd.grad((want * w).sum(), rot.parametrizations.weight.original)
+        g_got, = torch.autograd.grad((got * w).sum(), rot.parametrizations.weight.original)
+        torch.testing.assert_close(g_got, g_want, rtol=1e-4, atol=1e-5)
