@@ -230,7 +230,7 @@ def run_training(args, model, ia, fa, reads, dev, world, barrier):
     model.set_epoch_type(Epoch.VALID)
     return {"metric": "artifact_model_training_variants_per_sec", "value": bt * world / (ms_max / 1e3), "unit": "variants/s",
             "ms_per_step": ms_max, "batch_variants_per_gpu": bt, "last_loss_per_variant": float(losses.total_loss) / bt,
-            "backward_kernel_ms": prof.mean_ms(), "gpu_launches": 26 * args.steps,
+            "backward_kernel_ms": prof.mean_ms(), "gpu_launches": 24 * args.steps,   # library kernels per step (profiles/r1/launches_bench_default_summary.txt)
             "step": "device DownsampledBatch + compute_batch_output + compute_batch_losses (fused loss head) + backward (FP32 SIMT) + "
                     "flat grad all-reduce + clip(1.0) + AdamW (FlatAdamW)"}
 
