@@ -156,6 +156,13 @@ size_t pmt_workspace_size(const PmtModelDesc* desc, const PmtBatch* batch, int f
 int pmt_forward(const PmtModelDesc* desc, const float* weights, const PmtBatch* batch, const PmtOutputs* out,
                 void* workspace, size_t workspace_bytes, void* stream);
 
+/* Same as pmt_forward, for repeated inference with unchanged weights: skips rebuilding the packed weight images.
+ * Contract: the previous call on this workspace was pmt_forward or pmt_forward_prepared with the SAME desc, weights
+ * contents, precision mode and workspace base address (the images live at fixed offsets from the base; batches of any
+ * size may follow each other), and nothing else wrote to the workspace in between (pmt_backward does). */
+int pmt_forward_prepared(const PmtModelDesc* desc, const float* weights, const PmtBatch* batch, const PmtOutputs* out,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
 /* Backward of pmt_forward (autograd of artifact_model.py:239-297): accumulates nothing, WRITES
  * d_weights[n_params] (gradient w.r.t. the materialised flat weights). */
 int pmt_backward(const PmtModelDesc* desc, const float* weights, const PmtBatch* batch, const PmtOutGrads* grads,

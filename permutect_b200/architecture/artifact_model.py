@@ -174,10 +174,16 @@ class ArtifactModel(nn.Module):
         params = self._parameter_list()
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
             return torch.cat([t.reshape(-1) for t in planner.materialized_tensors(self)])
-        versions = tuple(p._version for p in params) + tuple(p.data_ptr() for p in params[:4])
-        if self._flat_cache is None or self._flat_cache[0] != versions:
+        try:
+            versions = tuple(p._version for p in params) + tuple(p.data_ptr() for p in params[:4])
+        except RuntimeError:         # inference tensors (a model built under torch.inference_mode) track no versions
+            versions = None
+        if versions is None or self._flat_cache is None or self._flat_cache[0] != versions:
             with torch.no_grad():
                 flat = torch.cat([t.reshape(-1) for t in planner.materialized_tensors(self)])
+            if versions is None:
+                self._flat_cache = None
+                return flat
             self._flat_cache = (versions, flat)
         return self._flat_cache[1]
 
@@ -201,7 +207,8 @@ class ArtifactModel(nn.Module):
         if flat.requires_grad:
             logits_bk, alt_means, ref_means, logits_b, outlier = engine.FusedArtifactFunction.apply(flat, desc, batch)
         else:
-            out = engine.forward_call(desc, flat, batch)
+            key = self._flat_cache[0] if (self._flat_cache is not None and self._flat_cache[1] is flat) else None
+            out = engine.forward_call(desc, flat, batch, weights_key=key)
             logits_bk, alt_means, ref_means = out["logits_bk"], out["alt_means"], out["ref_means"]
             logits_b, outlier = out["logits_b"], out["outlier_logits"]
         if balancer is None:

@@ -945,7 +945,7 @@ extern "C" int pmt_backward(const PmtModelDesc* desc, const float* weights, cons
   pmt_launch_prepare(P, G, weights, image, st);
   if (grads && grads->info_seq_be) {
     cudaMemcpyAsync(info_seq, grads->info_seq_be, (size_t)B * w * sizeof(float), cudaMemcpyDeviceToDevice, st);
-  } else if (pmt_launch_variant_kernels(P, G, weights, image, batch, info_seq, PMT_PRECISION_FP32, nullptr, st)) {
+  } else if (pmt_launch_variant_kernels(P, G, weights, image, batch, info_seq, PMT_PRECISION_FP32, nullptr, false, st)) {
     return 1;
   }
 

@@ -588,10 +588,10 @@ static long long* g_cnn_trace = nullptr;
 extern "C" int pmt_set_cnn_trace(long long* device_buffer) { g_cnn_trace = device_buffer; return 0; }
 
 int pmt_launch_cnn_tc(const pmt::Plan& P, const float* weights, const PmtBatch* batch, float* info_seq, unsigned char* image,
-                      int n_sm, int mode, cudaStream_t st) {
+                      bool reuse_image, int n_sm, int mode, cudaStream_t st) {
   cnntc::Plan T;
   PMT_CHECK(build_cnn_tc_plan(P, &T), "haplotype CNN outside the tensor-core envelope");
-  pack_cnn_tc_kernel<<<T.n_layers, 256, 0, st>>>(P.d, T, weights, image);
+  if (!reuse_image) pack_cnn_tc_kernel<<<T.n_layers, 256, 0, st>>>(P.d, T, weights, image);
   const int n_groups = (batch->n_variants + T.G - 1) / T.G;
   const int grid = n_groups < n_sm ? n_groups : n_sm;
   if (g_cnn_trace) {

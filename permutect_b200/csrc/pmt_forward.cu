@@ -521,15 +521,32 @@ size_t pmt_image_bytes(const Plan& P, const CnnGeom& G) {
 
 static size_t long_scratch_floats_per_cta(const Plan& P, const PmtBatch* batch);
 
+// Workspace layout of the forward: the packed weight images sit at FIXED offsets from the base (they depend on the model
+// only), the batch-dependent regions follow:
+//   [256 B counters][SIMT images][tcgen05 read-kernel images][tcgen05 CNN images] | [info_seq][long-set scratch][tile list]
+struct FwdLayout {
+  size_t image, tc_image, cnn_tc_image, info_seq, long_scratch, tiles, end;
+};
+static FwdLayout forward_layout(const Plan& P, const CnnGeom& G, const PmtModelDesc* desc, const PmtBatch* batch) {
+  FwdLayout L;
+  size_t off = 256;
+  L.image = off; off += pmt_image_bytes(P, G); off = (off + 1023) & ~(size_t)1023;
+  L.tc_image = off; off += pmt_tc_image_bytes(P); off = (off + 255) & ~(size_t)255;
+  L.cnn_tc_image = off; off += pmt_cnn_tc_image_bytes(P); off = (off + 255) & ~(size_t)255;
+  L.info_seq = off; off += (size_t)batch->n_variants * (desc->d_info + desc->d_seq) * sizeof(float); off = (off + 255) & ~(size_t)255;
+  L.long_scratch = off; off += long_scratch_floats_per_cta(P, batch) * sizeof(float) * 148; off = (off + 255) & ~(size_t)255;
+  L.tiles = off; off += pmt_tc_tiles_bytes(batch);
+  L.end = off;
+  return L;
+}
+
 extern "C" size_t pmt_workspace_size(const PmtModelDesc* desc, const PmtBatch* batch, int for_backward) {
   Plan P;
   CnnGeom G;
   if (pmt_build_plan(desc, &P) || pmt_cnn_geometry(P, &G)) return 0;
-  size_t bytes = 256;                       // claim counter + flags
-  bytes += pmt_image_bytes(P, G);
-  if (batch) bytes += (size_t)batch->n_variants * (desc->d_info + desc->d_seq) * sizeof(float) + 256;  // info_seq when caller passes none
-  bytes += long_scratch_floats_per_cta(P, batch) * sizeof(float) * 148 + 256;
-  bytes += pmt_tc_workspace_bytes(P, batch) + pmt_cnn_tc_image_bytes(P) + 256 + 1024;
+  PmtBatch none;
+  memset(&none, 0, sizeof(none));
+  size_t bytes = forward_layout(P, G, desc, batch ? batch : &none).end + 1024;
   if (for_backward) bytes += pmt_backward_workspace_bytes(P, batch);
   return bytes;
 }
@@ -552,7 +569,8 @@ int pmt_launch_prepare(const Plan& P, const CnnGeom& G, const float* weights, fl
 }
 
 int pmt_launch_variant_kernels(const Plan& P, const CnnGeom& G, const float* weights, const float* image,
-                               const PmtBatch* batch, float* info_seq, int mode, unsigned char* cnn_tc_image, cudaStream_t st) {
+                               const PmtBatch* batch, float* info_seq, int mode, unsigned char* cnn_tc_image, bool reuse_images,
+                               cudaStream_t st) {
   const int B = batch->n_variants;
   {
     const int in_rows = P.d.n_info_features > PMT_MAX_DIM ? PMT_MAX_INFO_DIM : PMT_MAX_DIM;
@@ -566,7 +584,7 @@ int pmt_launch_variant_kernels(const Plan& P, const CnnGeom& G, const float* wei
     int dev = 0, n_sm = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    if (pmt_launch_cnn_tc(P, weights, batch, info_seq, cnn_tc_image, n_sm, mode, st)) return 1;
+    if (pmt_launch_cnn_tc(P, weights, batch, info_seq, cnn_tc_image, reuse_images, n_sm, mode, st)) return 1;
   } else {
     const size_t smem = (size_t)(2 * G.buf_floats + G.img_total + 2 * G.vt * 256) * sizeof(float);
     cudaFuncSetAttribute(hap_cnn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -589,8 +607,8 @@ static int choose_claim(const PmtBatch* batch, int n_sm) {
   return claim;
 }
 
-extern "C" int pmt_forward(const PmtModelDesc* desc, const float* weights, const PmtBatch* batch, const PmtOutputs* out,
-                           void* workspace, size_t workspace_bytes, void* stream) {
+static int forward_impl(const PmtModelDesc* desc, const float* weights, const PmtBatch* batch, const PmtOutputs* out,
+                        void* workspace, size_t workspace_bytes, void* stream, bool reuse_images) {
   Plan P;
   CnnGeom G;
   if (pmt_build_plan(desc, &P) || pmt_cnn_geometry(P, &G)) return 1;
@@ -598,18 +616,19 @@ extern "C" int pmt_forward(const PmtModelDesc* desc, const float* weights, const
   const size_t need = pmt_workspace_size(desc, batch, 0);
   PMT_CHECK(workspace && workspace_bytes >= need, "workspace too small: %zu < %zu", workspace_bytes, need);
   PMT_CHECK(batch->n_variants > 0, "empty batch");
+  const FwdLayout L = forward_layout(P, G, desc, batch);
+  PMT_CHECK(L.end <= workspace_bytes, "workspace layout overflow");
   char* ws = reinterpret_cast<char*>(workspace);
   int* counter = reinterpret_cast<int*>(ws);
-  float* image = reinterpret_cast<float*>(ws + 256);
+  float* image = reinterpret_cast<float*>(ws + L.image);
   float* info_seq = out->info_seq_be;
-  if (!info_seq) info_seq = reinterpret_cast<float*>(ws + 256 + pmt_image_bytes(P, G));
+  if (!info_seq) info_seq = reinterpret_cast<float*>(ws + L.info_seq);
   cudaMemsetAsync(counter, 0, 256, st);
-  pmt_launch_prepare(P, G, weights, image, st);
+  if (!reuse_images) pmt_launch_prepare(P, G, weights, image, st);
   const int mode = pmt_precision_mode();
-  unsigned char* tc_image = reinterpret_cast<unsigned char*>(ws) + workspace_bytes - pmt_tc_workspace_bytes(P, batch) - 512;
-  unsigned char* cnn_tc_image = reinterpret_cast<unsigned char*>(
-      (reinterpret_cast<uintptr_t>(tc_image) - pmt_cnn_tc_image_bytes(P) - 256) & ~uintptr_t(255));
-  if (pmt_launch_variant_kernels(P, G, weights, image, batch, info_seq, mode, cnn_tc_image, st)) return 1;
+  unsigned char* tc_image = reinterpret_cast<unsigned char*>(ws + L.tc_image);
+  unsigned char* cnn_tc_image = reinterpret_cast<unsigned char*>(ws + L.cnn_tc_image);
+  if (pmt_launch_variant_kernels(P, G, weights, image, batch, info_seq, mode, cnn_tc_image, reuse_images, st)) return 1;
 
   int dev = 0, n_sm = 148;
   cudaGetDevice(&dev);
@@ -626,16 +645,15 @@ extern "C" int pmt_forward(const PmtModelDesc* desc, const float* weights, const
     PMT_CHECK(pmt_tc_supported(P), "this model shape is outside the tensor-core kernel's envelope; use PMT_PRECISION_FP32");
     PmtOutputs o2 = *out;
     o2.info_seq_be = info_seq;
-    if (pmt_launch_reads_tc(P, weights, batch, &o2, tc_image, n_sm, mode, st)) return 1;
+    if (pmt_launch_reads_tc(P, weights, batch, &o2, tc_image, reinterpret_cast<unsigned char*>(ws + L.tiles), reuse_images, n_sm, mode, st))
+      return 1;
   } else {
     pmt_profile_begin(st);
     reads_forward_kernel<<<grid, NTHREADS, smem, st>>>(P, A);
     pmt_profile_end(st);
   }
   if (batch->max_rows_per_variant > TILE) {
-    size_t off = 256 + pmt_image_bytes(P, G) + (size_t)batch->n_variants * (desc->d_info + desc->d_seq) * sizeof(float) + 256;
-    off = (off + 255) & ~(size_t)255;
-    A.scratch = reinterpret_cast<float*>(ws + off);
+    A.scratch = reinterpret_cast<float*>(ws + L.long_scratch);
     A.scratch_stride = (long long)long_scratch_floats_per_cta(P, batch);
     const int lgrid = long_grid(batch, n_sm < 148 ? n_sm : 148);
     cudaFuncSetAttribute(reads_forward_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -644,6 +662,16 @@ extern "C" int pmt_forward(const PmtModelDesc* desc, const float* weights, const
   cudaError_t e = cudaGetLastError();
   PMT_CHECK(e == cudaSuccess, "pmt_forward launch failed: %s", cudaGetErrorString(e));
   return 0;
+}
+
+extern "C" int pmt_forward(const PmtModelDesc* desc, const float* weights, const PmtBatch* batch, const PmtOutputs* out,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+  return forward_impl(desc, weights, batch, out, workspace, workspace_bytes, stream, false);
+}
+
+extern "C" int pmt_forward_prepared(const PmtModelDesc* desc, const float* weights, const PmtBatch* batch, const PmtOutputs* out,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+  return forward_impl(desc, weights, batch, out, workspace, workspace_bytes, stream, true);
 }
 
 extern "C" int pmt_decode_reads(const uint8_t* reads_u8, int64_t n_rows, int32_t row_bytes, float* out, void* stream) {

@@ -19,7 +19,8 @@ int pmt_cnn_geometry(const pmt::Plan& P, pmt::CnnGeom* out);
 size_t pmt_image_bytes(const pmt::Plan& P, const pmt::CnnGeom& G);
 int pmt_launch_prepare(const pmt::Plan& P, const pmt::CnnGeom& G, const float* weights, float* image, cudaStream_t st);
 int pmt_launch_variant_kernels(const pmt::Plan& P, const pmt::CnnGeom& G, const float* weights, const float* image,
-                               const PmtBatch* batch, float* info_seq, int mode, unsigned char* cnn_tc_image, cudaStream_t st);
+                               const PmtBatch* batch, float* info_seq, int mode, unsigned char* cnn_tc_image, bool reuse_images,
+                               cudaStream_t st);
 size_t pmt_backward_workspace_bytes(const pmt::Plan& P, const PmtBatch* batch);
 void pmt_profile_begin(cudaStream_t st);
 void pmt_profile_end(cudaStream_t st);
@@ -28,10 +29,10 @@ int pmt_launch_cnn_backward(const pmt::Plan& P, const pmt::CnnGeom& G, const flo
 int pmt_precision_mode();
 bool pmt_tc_supported(const pmt::Plan& P);
 size_t pmt_tc_image_bytes(const pmt::Plan& P);
-size_t pmt_tc_workspace_bytes(const pmt::Plan& P, const PmtBatch* batch);
+size_t pmt_tc_tiles_bytes(const PmtBatch* batch);
 int pmt_launch_reads_tc(const pmt::Plan& P, const float* weights, const PmtBatch* batch, const PmtOutputs* out,
-                        unsigned char* tc_image, int n_sm, int mode, cudaStream_t st);
+                        unsigned char* image_buf, unsigned char* tiles_buf, bool reuse_images, int n_sm, int mode, cudaStream_t st);
 bool pmt_cnn_tc_supported(const pmt::Plan& P);
 size_t pmt_cnn_tc_image_bytes(const pmt::Plan& P);
 int pmt_launch_cnn_tc(const pmt::Plan& P, const float* weights, const PmtBatch* batch, float* info_seq, unsigned char* image,
-                      int n_sm, int mode, cudaStream_t st);
+                      bool reuse_image, int n_sm, int mode, cudaStream_t st);

@@ -940,9 +940,7 @@ size_t pmt_tc_image_bytes(const Plan& P) {
   pmt_tc_plan(P, &T);
   return (size_t)T.image_bytes + 2048;
 }
-size_t pmt_tc_workspace_bytes(const Plan& P, const PmtBatch* batch) {
-  return pmt_tc_image_bytes(P) + tiles_bytes(batch ? batch->n_variants : 0) + 1024;
-}
+size_t pmt_tc_tiles_bytes(const PmtBatch* batch) { return tiles_bytes(batch ? batch->n_variants : 0) + 256; }
 
 static long long* g_reads_trace = nullptr;
 // Measurement hook: device buffer of 4 x 2048 int64 that CTA 0 of the next tensor-core read-kernel launches fills
@@ -968,14 +966,14 @@ static int launch_tc(const PmtModelDesc& D, const TcPlan& T, const TcArgs& A, in
   return 0;
 }
 
-// Launches the tile planner, the weight packer and the tensor-core read kernel.  `tc_ws` is a device buffer of
-// pmt_tc_workspace_bytes(P, batch) bytes.
+// Launches the tile planner, the weight packer (unless the images in `image_buf` are still valid) and the tensor-core
+// read kernel.  `image_buf`: pmt_tc_image_bytes(P) bytes; `tiles_buf`: pmt_tc_tiles_bytes(batch) bytes.
 int pmt_launch_reads_tc(const Plan& P, const float* weights, const PmtBatch* batch, const PmtOutputs* out,
-                        unsigned char* tc_ws, int n_sm, int mode, cudaStream_t st) {
+                        unsigned char* image_buf, unsigned char* tiles_buf, bool reuse_images, int n_sm, int mode, cudaStream_t st) {
   TcPlan T;
   pmt_tc_plan(P, &T);
-  unsigned char* image = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_ws) + 1023) & ~uintptr_t(1023));
-  int* tiles = reinterpret_cast<int*>(image + T.image_bytes);
+  unsigned char* image = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(image_buf) + 1023) & ~uintptr_t(1023));
+  int* tiles = reinterpret_cast<int*>((reinterpret_cast<uintptr_t>(tiles_buf) + 255) & ~uintptr_t(255));
   cudaMemsetAsync(tiles, 0, 2 * sizeof(int), st);
   // planner claims: large enough that the partial last tile of a claim is a small loss, small enough that a small
   // batch is planned by many warps (each claim is walked sequentially)
@@ -986,7 +984,7 @@ int pmt_launch_reads_tc(const Plan& P, const float* weights, const PmtBatch* bat
   plan_tiles_kernel<<<(n_claims + 3) / 4, 128, 0, st>>>(reinterpret_cast<const long long*>(batch->ref_off),
                                                          reinterpret_cast<const long long*>(batch->alt_off), batch->n_variants,
                                                          claim_variants, tiles);
-  pack_tc_kernel<<<T.n_steps, 256, 0, st>>>(P.d, T, weights, image);
+  if (!reuse_images) pack_tc_kernel<<<T.n_steps, 256, 0, st>>>(P.d, T, weights, image);
   TcArgs A;
   A.wflat = weights; A.image = image; A.tiles = tiles; A.batch = *batch; A.out = *out;
   // the tile count is only known on the device: size the grid from the row-count hint (a tile holds ~110 rows of

@@ -99,3 +99,46 @@ def test_large_ragged_batch_against_oracle():
     torch.testing.assert_close(out.logits_b.cpu(), want["logits_b"], rtol=0, atol=LOGIT_ATOL)
     torch.testing.assert_close(out.features_be.cpu(), want["features_be"], rtol=1e-4, atol=1e-4)
     torch.testing.assert_close(out.ref_features_be.cpu(), want["ref_features_be"], rtol=1e-4, atol=1e-4)
+
+
+def test_prepared_forward_reuses_images_only_while_the_weights_are_unchanged():
+    """Repeated inference goes through pmt_forward_prepared (packed weight images kept in the workspace); any parameter
+    update, precision switch, other model or intervening backward must rebuild them."""
+    from permutect_b200.data.batch import Batch
+    from permutect_b200.engine import function as engine
+    from permutect_b200.engine import library as L
+    from permutect_b200.synthetic import make_wgs_arrays
+    g = load("v040_seed0_b64")
+    dev = torch.device("cuda:0")
+    model = model_from_golden(g, dev)
+    model.set_epoch_type(Epoch.VALID)
+    other = model_from_golden(load("v040_perturbed_edge"), dev)
+    other.set_epoch_type(Epoch.VALID)
+    small = Batch.from_arrays(*make_wgs_arrays(300, seed=1)).copy_to(dev)
+    big = Batch.from_arrays(*make_wgs_arrays(5000, seed=2)).copy_to(dev)
+    fresh = model_from_golden(g, dev)
+    fresh.set_epoch_type(Epoch.VALID)
+    with torch.no_grad():
+        fresh.reducer._model[-1].bias.add_(0.05)
+    try:
+        for mode in ("tf32x3", "fp32"):
+            L.set_precision(mode)
+            with torch.inference_mode():
+                a1 = model.compute_batch_output(small).logits_b.clone()
+                assert engine._PREPARED[dev] is not None
+                b1 = model.compute_batch_output(big).logits_b.clone()          # prepared call, different batch size
+                a2 = model.compute_batch_output(small).logits_b.clone()
+                assert torch.equal(a1, a2)
+                o1 = other.compute_batch_output(small).logits_b.clone()        # another model: images rebuilt
+                a3 = model.compute_batch_output(small).logits_b.clone()
+                assert torch.equal(a1, a3) and not torch.equal(a1, o1)
+                with torch.no_grad():
+                    model.reducer._model[-1].bias.add_(0.05)                   # in-place update bumps the version
+                c1 = model.compute_batch_output(small).logits_b.clone()
+                assert not torch.equal(a1, c1)
+                assert torch.equal(c1, fresh.compute_batch_output(small).logits_b)
+                assert not torch.equal(model.compute_batch_output(big).logits_b, b1)
+                with torch.no_grad():
+                    model.reducer._model[-1].bias.sub_(0.05)
+    finally:
+        L.set_precision("fp32")
