@@ -10,6 +10,12 @@
 //   skip_fix_kernel           DenseSkipBlock.alpha gradients and the alpha scaling of its last layer
 #include <cstring>
 
+// The per-row phases are written for NPART = NTHREADS / TILE threads per tile row.  Measured on B200 (65 536 variants,
+// profiles/r1_tensor_core_kernels.md): 256 threads 30.4 ms, 384 threads 31.6 ms, 512 threads 32.5 ms (register cap 128,
+// spills), so the default of two threads per row stays.
+#ifndef PMT_NTHREADS
+#define PMT_NTHREADS 256
+#endif
 #include "pmt_cnn.cuh"
 #include "pmt_host.h"
 #include "pmt_tile.cuh"
@@ -29,7 +35,17 @@ struct BwdArgs {
   long long scratch_stride;   // floats
   float* partials;            // per-CTA flat gradient buffers [grid][n_params]
   int n_claims;
+  long long* trace;           // measurement hook (pmt_set_backward_trace): phase clocks of CTA 0's third tile, or null
 };
+
+// trace[0] = number of records; record i = (phase id, clock64()) at trace[1 + 2i]
+#define PMT_BWD_TRACE(id)                                                     \
+  do {                                                                        \
+    if (tracing && threadIdx.x == 0) {                                        \
+      const long long n_ = A.trace[0];                                        \
+      if (n_ < 250) { A.trace[1 + 2 * n_] = (id); A.trace[2 + 2 * n_] = clock64(); A.trace[0] = n_ + 1; } \
+    }                                                                         \
+  } while (0)
 
 __device__ __forceinline__ float* pick_free(float* const* bufs, const float* a, const float* b, const float* c) {
   for (int i = 0; i < 4; ++i)
@@ -150,7 +166,7 @@ reads_backward_kernel(const __grid_constant__ Plan P, const __grid_constant__ Bw
   acc.init(wpart, acc_cap);
 
   const int tid = threadIdx.x;
-  const int row = tid & (TILE - 1), half = tid >> 7;
+  const int row = tid & (TILE - 1), rp = tid / TILE;   // (row, row-part) of this thread
   const int B = A.batch.n_variants;
   Stage stage;
   stage.init(st0, st1, A.image, &P);
@@ -164,6 +180,7 @@ reads_backward_kernel(const __grid_constant__ Plan P, const __grid_constant__ Bw
   PmtOutputs no_out;
   memset(&no_out, 0, sizeof(no_out));
 
+  int tile_no = 0;
   // static round-robin assignment of claims to CTAs: the summation order of every gradient is fixed
   for (int c = blockIdx.x; c < A.n_claims; c += gridDim.x) {
     const long long cv0 = (long long)c * claim;
@@ -173,6 +190,9 @@ reads_backward_kernel(const __grid_constant__ Plan P, const __grid_constant__ Bw
       const int nv = build_tile(A.batch, v_cur, cv1, total_ref, M);
       if (nv == 0) { v_cur += 1; continue; }   // sets longer than a tile are rejected by the host for training
       v_cur += nv;
+      const bool tracing = A.trace != nullptr && blockIdx.x == 0 && tile_no == 2;
+      tile_no += 1;
+      PMT_BWD_TRACE(0);
       const int rows_used = (M.rows + 3) & ~3;
       C.rows_used = rows_used;
       const int ref_pad = M.ref_pad;
@@ -181,6 +201,7 @@ reads_backward_kernel(const __grid_constant__ Plan P, const __grid_constant__ Bw
 
       // ======================= forward recompute, activations to scratch =======================
       tile_embed(P, C, stage, A.batch, A.info_seq, scr);
+      PMT_BWD_TRACE(1);
       for (int blk = 0; blk < D.n_blocks; ++blk) {
         save_rows(C.X, Dm, scr + P.scr_x[blk]);
         block_phase_a(P, C, stage, blk, scr + P.scr_z[blk]);
@@ -188,9 +209,11 @@ reads_backward_kernel(const __grid_constant__ Plan P, const __grid_constant__ Bw
         __syncthreads();
         block_means(P, C, blk);
         block_phase_b(P, C, stage, blk, blk + 1 < D.n_blocks ? P.blk_g0 + 2 * blk + 2 : P.red_g0);
+        PMT_BWD_TRACE(2 + blk);
       }
       float *Yb, *Fb;
       tile_tail(P, C, stage, no_out, false, scr, Yb, Fb);
+      PMT_BWD_TRACE(20);
       float* Lb = pick_free(bufs, Yb, Fb, bufs[3]);   // the third forward buffer (held the log-likelihoods)
       float* Xtra = bufs[3];
 
@@ -200,10 +223,10 @@ reads_backward_kernel(const __grid_constant__ Plan P, const __grid_constant__ Bw
       {
         const bool live = is_alt && my_var >= 0;
         const long long v = live ? (long long)M.v0 + my_var : 0;
-        // half h writes its share of d f into Lb rows [h*E, (h+1)*E)
-        float* dfp = Lb + half * E * LD;
+        // row-part p writes its share of d f into Lb rows [p*E, (p+1)*E)
+        float* dfp = Lb + rp * E * LD;
         for (int e = 0; e < E; ++e) dfp[e * LD + row] = 0.f;
-        if (half == 0) {
+        if (rp == 0) {
           const float g0 = live ? ldg_or_zero(A.d_logits_bk, v * (K + 2) + 0) : 0.f;
           const float g1 = live ? ldg_or_zero(A.d_logits_bk, v * (K + 2) + 1) : 0.f;
           for (int e = 0; e < E; ++e) {
@@ -216,7 +239,7 @@ reads_backward_kernel(const __grid_constant__ Plan P, const __grid_constant__ Bw
             acc.add(e, contrib);
           }
         }
-        for (int k = half; k < K; k += 2) {
+        for (int k = rp; k < K; k += NPART) {
           const float* u = W + D.unit_ke + k * E;
           const float gk = live ? ldg_or_zero(A.d_logits_bk, v * (K + 2) + 2 + k) : 0.f;
           const float tau = __ldg(W + D.tau_k + k), lam = __ldg(W + D.lambda_k + k), sg = __ldg(W + D.emg_sigma_k + k),
@@ -254,11 +277,13 @@ reads_backward_kernel(const __grid_constant__ Plan P, const __grid_constant__ Bw
         const int offs[5] = {D.tau_k, D.mu_k, D.emg_sigma_k, D.lambda_k, D.logw_k};
         for (int q = 0; q < 5; ++q) acc.flush(part + offs[q], base + q * K, K);
       }
-      // d f = head part (both halves) + mean part; written in place over the final features
+      // d f = head part (all parts) + mean part; written in place over the final features
       {
-        const int e_lo = half ? E / 2 : 0, e_hi = half ? E : E / 2;
+        const int e_lo = part_lo(E, rp), e_hi = part_lo(E, rp + 1);
         for (int e = e_lo; e < e_hi; ++e) {
-          float d = Lb[e * LD + row] + Lb[(E + e) * LD + row];
+          float d = 0.f;
+#pragma unroll
+          for (int q = 0; q < NPART; ++q) d += Lb[(q * E + e) * LD + row];
           if (my_var >= 0) {
             const long long v = (long long)M.v0 + my_var;
             d += is_alt ? ldg_or_zero(A.d_alt_means, v * E + e) / (M.alt_total[my_var] + 1e-4f)
@@ -274,7 +299,7 @@ reads_backward_kernel(const __grid_constant__ Plan P, const __grid_constant__ Bw
       // rotation (euclidean_transformation.py:19-20): f = Q (y + t)
       wgrad_tile(smem_addr(Fb), E, smem_addr(Yb), E, part + D.rotation, 0, rows_used);
       {
-        const int e_lo = half ? E / 2 : 0, e_hi = half ? E : E / 2;
+        const int e_lo = part_lo(E, rp), e_hi = part_lo(E, rp + 1);
         for (int j = e_lo; j < e_hi; ++j) {
           float a = 0.f;
           for (int i = 0; i < E; ++i) a = fmaf(__ldg(W + D.rotation + i * E + j), Fb[i * LD + row], a);
@@ -283,10 +308,12 @@ reads_backward_kernel(const __grid_constant__ Plan P, const __grid_constant__ Bw
       }
       __syncthreads();
       rowdot_tile(Xtra, nullptr, E, part + D.translation, 0, rows_used);
+      PMT_BWD_TRACE(21);
 
       // ======================= reducer (artifact_model.py:258-259) =======================
       float* G = mlp_backward(P, D.red_ops, D.n_red_ops, P.red_g0, scr, P.scr_red, Xtra, bufs, stage, W, part,
                               rows_used, true);
+      PMT_BWD_TRACE(22);
 
       // ======================= gated blocks in reverse (gated_mlp.py:177-251) =======================
       float* Ab = nullptr; float* Bn = nullptr; float* Cz = nullptr;
@@ -302,8 +329,8 @@ reads_backward_kernel(const __grid_constant__ Plan P, const __grid_constant__ Bw
         const float alpha = __ldg(W + (is_alt ? BO.alpha_alt : BO.alpha_ref));
         const float beta = __ldg(W + (is_alt ? BO.beta_alt : BO.beta_ref));
         const float gamma = __ldg(W + BO.gamma);
-        const int f_lo = half ? H / 2 : 0, f_hi = half ? H : H / 2;
-        const int d_lo = half ? Dm / 2 : 0, d_hi = half ? Dm : Dm / 2;
+        const int f_lo = part_lo(H, rp), f_hi = part_lo(H, rp + 1);
+        const int d_lo = part_lo(Dm, rp), d_hi = part_lo(Dm, rp + 1);
         load_rows(Ab, Dm, scr + P.scr_x[blk]);
         load_rows(Cz, 2 * H, scr + P.scr_z[blk]);
         stage.prefetch(MAX_GEMM + g2);
@@ -331,6 +358,7 @@ reads_backward_kernel(const __grid_constant__ Plan P, const __grid_constant__ Bw
           Cz[(3 * H + f) * LD + row] = gate;
           Cz[(4 * H + f) * LD + row] = Cz[f * LD + row] * gate;   // u = z1 * gate
         }
+        PMT_BWD_TRACE(100 + blk * 10 + 0);
         // proj2: x_out = x + W2_s u + b2_s
         const float* imgT2 = stage.acquire(MAX_GEMM + g2);
         stage.prefetch(MAX_GEMM + g1);
@@ -340,6 +368,7 @@ reads_backward_kernel(const __grid_constant__ Plan P, const __grid_constant__ Bw
         rowdot_tile(G, nullptr, Dm, part + BO.p2_alt_b, ref_pad, rows_used);
         gemm_tile_T(G, P.gemm[g2], imgT2, ref_pad, Cz + 5 * H * LD, EPI_STORE, 1.f, nullptr, rows_used);   // du
         __syncthreads();
+        PMT_BWD_TRACE(100 + blk * 10 + 1);
         {  // d z1 = du * gate ; d gate = du * z1 ; scalar gradients of the gate
           float s_alpha = 0.f, s_beta = 0.f, s_gamma = 0.f;
           for (int f = f_lo; f < f_hi; ++f) {
@@ -423,6 +452,7 @@ reads_backward_kernel(const __grid_constant__ Plan P, const __grid_constant__ Bw
           }
         }
         __syncthreads();
+        PMT_BWD_TRACE(100 + blk * 10 + 2);
         mul_dselu(Cz + 4 * H * LD, Cz, 2 * H);   // through z = SELU(proj1 n)
         // proj1: z_pre = W1_s n + b1_s
         const float* imgT1 = stage.acquire(MAX_GEMM + g1);
@@ -434,6 +464,7 @@ reads_backward_kernel(const __grid_constant__ Plan P, const __grid_constant__ Bw
         __syncthreads();
         gemm_tile_T(Cz + 4 * H * LD, P.gemm[g1], imgT1, ref_pad, Bn, EPI_STORE, 1.f, nullptr, rows_used);   // d n
         __syncthreads();
+        PMT_BWD_TRACE(100 + blk * 10 + 3);
         rowdot_tile(Bn, Ab, Dm, part + BO.ln_w, 0, rows_used);
         rowdot_tile(Bn, nullptr, Dm, part + BO.ln_b, 0, rows_used);
         {  // LayerNorm backward, added to the residual gradient
@@ -449,6 +480,7 @@ reads_backward_kernel(const __grid_constant__ Plan P, const __grid_constant__ Bw
           }
         }
         __syncthreads();
+        PMT_BWD_TRACE(100 + blk * 10 + 4);
       }
 
       // ======================= concat (artifact_model.py:246-251): d info_seq of each variant =======================
@@ -463,9 +495,11 @@ reads_backward_kernel(const __grid_constant__ Plan P, const __grid_constant__ Bw
           A.d_info_seq[((long long)M.v0 + j) * w + f] = s;
         }
       }
+      PMT_BWD_TRACE(23);
       // ======================= read embedding (artifact_model.py:243) =======================
       mlp_backward(P, D.read_ops, D.n_read_ops, P.read_g0, scr, P.scr_read, G, bufs, stage, W, part, rows_used, false);
       __syncthreads();
+      PMT_BWD_TRACE(24);
     }
   }
 }
@@ -575,23 +609,24 @@ __device__ __forceinline__ void stage_image(float* dst, const float* __restrict_
 }
 
 // dW[co][ci][t] += sum_{v, p} g[co][v, p] * in[ci][v, p + t];  g must be zero at padding positions.
-// One (4 output channels, 1 input channel) unit per thread; lanes run over consecutive input channels.
+// One (WG_OC output channels, 1 input channel) unit per thread; lanes run over consecutive input channels.
+constexpr int WG_OC = NTHREADS >= 512 ? 2 : 4;
 template <int KS>
 __device__ __forceinline__ void conv_wgrad(const PmtCnnOp& op, const float* __restrict__ in, int in_ld, int lp_in,
                                            const float* __restrict__ g, int g_ld, int lp_out, int vt,
                                            float* __restrict__ part) {
-  const int n_cg = (op.out_ch + 3) / 4;
+  const int n_cg = (op.out_ch + WG_OC - 1) / WG_OC;
   for (int unit = threadIdx.x; unit < n_cg * op.in_ch; unit += NTHREADS) {
     const int cg = unit / op.in_ch, ci = unit % op.in_ch;
-    float acc[4][KS];
+    float acc[WG_OC][KS];
 #pragma unroll
-    for (int b = 0; b < 4; ++b)
+    for (int b = 0; b < WG_OC; ++b)
 #pragma unroll
       for (int t = 0; t < KS; ++t) acc[b][t] = 0.f;
     const float* xr = in + ci * in_ld;
-    const float* gr[4];
+    const float* gr[WG_OC];
 #pragma unroll
-    for (int b = 0; b < 4; ++b) gr[b] = g + min(cg * 4 + b, op.out_ch - 1) * g_ld;
+    for (int b = 0; b < WG_OC; ++b) gr[b] = g + min(cg * WG_OC + b, op.out_ch - 1) * g_ld;
     for (int v = 0; v < vt; ++v) {
       for (int p0 = 0; p0 < lp_out; p0 += 4) {
         float xw[12];
@@ -606,7 +641,7 @@ __device__ __forceinline__ void conv_wgrad(const PmtCnnOp& op, const float* __re
           xw[8] = c.x; xw[9] = c.y; xw[10] = c.z; xw[11] = c.w;
         }
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
+        for (int b = 0; b < WG_OC; ++b) {
           const float4 gv = *reinterpret_cast<const float4*>(gr[b] + v * lp_out + p0);
 #pragma unroll
           for (int t = 0; t < KS; ++t) {
@@ -619,8 +654,8 @@ __device__ __forceinline__ void conv_wgrad(const PmtCnnOp& op, const float* __re
       }
     }
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const int co = cg * 4 + b;
+    for (int b = 0; b < WG_OC; ++b) {
+      const int co = cg * WG_OC + b;
       if (co < op.out_ch) {
 #pragma unroll
         for (int t = 0; t < KS; ++t) red_add(part + op.w_off + (co * op.in_ch + ci) * KS + t, acc[b][t]);
@@ -905,6 +940,8 @@ static int info_rows(const Plan& P) {
   return r;
 }
 static const int kBwdGrid = 148;
+static long long* g_bwd_trace = nullptr;
+extern "C" int pmt_set_backward_trace(long long* device_buffer) { g_bwd_trace = device_buffer; return 0; }
 
 size_t pmt_backward_workspace_bytes(const Plan& P, const PmtBatch* batch) {
   size_t bytes = 1024;
@@ -927,6 +964,7 @@ extern "C" int pmt_backward(const PmtModelDesc* desc, const float* weights, cons
   PMT_CHECK(batch->max_rows_per_variant <= TILE,
             "pmt_backward: a variant has %lld reads; training on sets longer than %d reads is not supported yet "
             "(the reference caps reads at 10 ref + 15 alt at ingest)", (long long)batch->max_rows_per_variant, TILE);
+  PMT_CHECK(NPART * desc->d_feat <= P.bwd_rows, "d_feat %d too wide for the backward kernel's head scratch", desc->d_feat);
   const size_t smem = bwd_smem_bytes(P);
   PMT_CHECK(smem <= 227 * 1024, "model too wide for the backward kernel's shared-memory plan (%zu bytes)", smem);
 
@@ -966,6 +1004,7 @@ extern "C" int pmt_backward(const PmtModelDesc* desc, const float* weights, cons
   A.d_ref_means = grads ? grads->d_ref_means_be : nullptr;
   A.d_info_seq = d_info_seq; A.scratch = scratch; A.scratch_stride = (long long)scr_floats; A.partials = partials;
   A.n_claims = (B + claim - 1) / claim;
+  A.trace = g_bwd_trace;
   int grid = A.n_claims < kBwdGrid ? A.n_claims : kBwdGrid;
   if (grid > n_sm) grid = n_sm;
   cudaFuncSetAttribute(reads_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -16,8 +16,14 @@ namespace pmt {
 
 constexpr int TILE = PMT_TILE_ROWS;  // rows (reads, or variants in the per-variant kernels) per CTA tile
 constexpr int LD = TILE + 4;         // row stride of the feature-major activation buffers (floats)
-constexpr int NTHREADS = 256;
+#ifndef PMT_NTHREADS
+#define PMT_NTHREADS 256   // a translation unit may compile its kernels for more warps (pmt_backward.cu: 512)
+#endif
+constexpr int NTHREADS = PMT_NTHREADS;
 constexpr int NWARPS = NTHREADS / 32;
+constexpr int NPART = NTHREADS / TILE;   // threads per tile row; thread (row, part) = (tid % TILE, tid / TILE)
+// Part `part` of a per-row loop over n items covers [part_lo(n, part), part_lo(n, part + 1)).
+__device__ __forceinline__ int part_lo(int n, int part) { return (n * part) / NPART; }
 constexpr int MAX_GEMM = 96;
 constexpr int GROUP_STRIDE = 8;      // floats per column group in a packed weight image row
 

@@ -6,6 +6,7 @@
 //   reads_forward_kernel  decode -> read_embedding -> concat -> gated ref/alt blocks -> reducer ->
 //                         rotation -> clustering head -> per-variant sums (artifact_model.py:243-297)
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "pmt_host.h"
@@ -378,6 +379,7 @@ extern "C" int pmt_abi_version(void) { return PMT_ABI_VERSION; }
 
 static void choose_groups(int N, int* G, int* NT) {
   int g = N > 32 ? 8 : 4;
+  if (const char* e = getenv("PMT_GEMM_GROUPS")) { if (atoi(e) >= 4) g = atoi(e); }
   int nt = (N + g - 1) / g;
   if (nt < 1) nt = 1;
   g = (N + nt - 1) / nt;

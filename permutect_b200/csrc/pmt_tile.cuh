@@ -178,7 +178,7 @@ __device__ __forceinline__ void build_chunk(const PmtBatch& batch, int v, int c,
 
 // batch.py:51-56 + plain_text_data.py:510-511: decode the tile's reads into T1 (feature-major)
 __device__ __forceinline__ void tile_decode(const PmtModelDesc& D, const PmtBatch& batch, const TileMeta& M, float* T1) {
-  const int row = threadIdx.x & (TILE - 1), half = threadIdx.x >> 7;
+  const int row = threadIdx.x & (TILE - 1), part = threadIdx.x / TILE;
   const int F = D.n_read_features;
   const long long my_idx = M.rowidx[row];
   long long src = -1;
@@ -186,21 +186,21 @@ __device__ __forceinline__ void tile_decode(const PmtModelDesc& D, const PmtBatc
   if (batch.reads_kind == PMT_READS_U8) {
     const int rb = D.read_row_bytes;
     const uint8_t* rp = reinterpret_cast<const uint8_t*>(batch.reads) + src * rb;
-    // half 0 expands packed bytes 0..3, half 1 bytes 4..6 and the quantised floats
-    const int b_lo = half ? 4 : 0, b_hi = half ? 7 : 4;
+    // the packed bytes 0..6 are spread over the parts of a row; the last part also takes the quantised floats
+    const int b_lo = (8 * part) / NPART, b_hi = min(7, (8 * (part + 1)) / NPART);
     for (int b = b_lo; b < b_hi; ++b) {
       const unsigned byte = src >= 0 ? __ldg(rp + b) : 0u;
 #pragma unroll
       for (int bit = 0; bit < 8; ++bit) T1[(b * 8 + bit) * LD + row] = (float)((byte >> (7 - bit)) & 1u);
     }
-    if (half) {
+    if (part == NPART - 1) {
       for (int b = 7; b < rb; ++b) {
         const unsigned byte = src >= 0 ? __ldg(rp + b) : 128u;
         T1[(56 + b - 7) * LD + row] = (float)((byte + 128u) & 255u) * 0.03125f;   // wraps like the uint8 arithmetic, quirk Q2
       }
     }
   } else {
-    for (int f = half; f < F; f += 2) {
+    for (int f = part; f < F; f += NPART) {
       float v = 0.f;
       if (src >= 0) {
         v = batch.reads_kind == PMT_READS_F16 ? __half2float(reinterpret_cast<const __half*>(batch.reads)[src * F + f])
@@ -216,7 +216,7 @@ __device__ __forceinline__ void tile_decode(const PmtModelDesc& D, const PmtBatc
 __device__ __forceinline__ void tile_embed(const Plan& P, TileCtx& C, Stage& stage, const PmtBatch& batch,
                                            const float* info_seq, float* scr) {
   const PmtModelDesc& D = P.d;
-  const int row = threadIdx.x & (TILE - 1), half = threadIdx.x >> 7;
+  const int row = threadIdx.x & (TILE - 1), part = threadIdx.x / TILE;
   stage.prefetch(P.read_g0);
   tile_decode(D, batch, *C.M, C.T1);
   float* emb = run_mlp(P, D.read_ops, D.n_read_ops, P.read_g0, C.T1, C.X, C.T1, C.T2, stage, C.W, C.rows_used,
@@ -226,7 +226,7 @@ __device__ __forceinline__ void tile_embed(const Plan& P, TileCtx& C, Stage& sta
   const int w = D.d_info + D.d_seq;
   const int my_var = C.M->rowvar[row];
   const float* src = my_var >= 0 ? info_seq + (long long)(C.M->v0 + my_var) * w : nullptr;
-  for (int j = half; j < w; j += 2) C.X[(D.d_read + j) * LD + row] = src ? __ldg(src + j) : 0.f;
+  for (int j = part; j < w; j += NPART) C.X[(D.d_read + j) * LD + row] = src ? __ldg(src + j) : 0.f;
   __syncthreads();
 }
 
@@ -246,14 +246,14 @@ __device__ __forceinline__ void row_stats(const float* buf, int nf, int row, flo
 __device__ __forceinline__ void block_phase_a(const Plan& P, TileCtx& C, Stage& stage, int blk, float* z_save) {
   const PmtModelDesc& D = P.d;
   const PmtBlockOffsets& BO = D.blocks[blk];
-  const int row = threadIdx.x & (TILE - 1), half = threadIdx.x >> 7;
+  const int row = threadIdx.x & (TILE - 1), part = threadIdx.x / TILE;
   const int Dm = D.d_model, H = D.d_ffn / 2;
   const int g1 = P.blk_g0 + 2 * blk;
   const float* W = C.W;
   {
     float mean, rstd;
     row_stats(C.X, Dm, row, mean, rstd);
-    const int f_lo = half ? Dm / 2 : 0, f_hi = half ? Dm : Dm / 2;
+    const int f_lo = part_lo(Dm, part), f_hi = part_lo(Dm, part + 1);
     for (int f = f_lo; f < f_hi; ++f)
       C.T1[f * LD + row] = (C.X[f * LD + row] - mean) * rstd * __ldg(W + BO.ln_w + f) + __ldg(W + BO.ln_b + f);
   }
@@ -266,7 +266,7 @@ __device__ __forceinline__ void block_phase_a(const Plan& P, TileCtx& C, Stage& 
     float mean, rstd;
     row_stats(C.T2 + H * LD, H, row, mean, rstd);
     __syncthreads();  // both halves (and the save) have read the raw z2 of this row
-    const int f_lo = half ? H / 2 : 0, f_hi = half ? H : H / 2;
+    const int f_lo = part_lo(H, part), f_hi = part_lo(H, part + 1);
     for (int f = f_lo; f < f_hi; ++f)
       C.T2[(H + f) * LD + row] = (C.T2[(H + f) * LD + row] - mean) * rstd * __ldg(W + BO.ln2_w + f) + __ldg(W + BO.ln2_b + f);
   }
@@ -303,7 +303,7 @@ __device__ __forceinline__ float gate_value(const Plan& P, const TileCtx& C, con
 __device__ __forceinline__ void block_phase_b(const Plan& P, TileCtx& C, Stage& stage, int blk, int next_g) {
   const PmtModelDesc& D = P.d;
   const PmtBlockOffsets& BO = D.blocks[blk];
-  const int row = threadIdx.x & (TILE - 1), half = threadIdx.x >> 7;
+  const int row = threadIdx.x & (TILE - 1), part = threadIdx.x / TILE;
   const int H = D.d_ffn / 2;
   const int g2 = P.blk_g0 + 2 * blk + 1;
   const float* W = C.W;
@@ -312,7 +312,7 @@ __device__ __forceinline__ void block_phase_b(const Plan& P, TileCtx& C, Stage& 
   const float alpha = __ldg(W + (is_alt ? BO.alpha_alt : BO.alpha_ref));
   const float beta = __ldg(W + (is_alt ? BO.beta_alt : BO.beta_ref));
   const float gamma = __ldg(W + BO.gamma);
-  const int f_lo = half ? H / 2 : 0, f_hi = half ? H : H / 2;
+  const int f_lo = part_lo(H, part), f_hi = part_lo(H, part + 1);
   for (int f = f_lo; f < f_hi; ++f)
     C.T1[f * LD + row] = C.T2[f * LD + row] * gate_value(P, C, BO, row, f, C.T2[(H + f) * LD + row], my_var, is_alt, alpha, beta, gamma);
   const float* img2 = stage.acquire(g2);
@@ -330,9 +330,9 @@ __device__ __forceinline__ void other_two(const TileCtx& C, const float* used, f
 
 // euclidean_transformation.py:19-20: Fb = Q (y + t) per row
 __device__ __forceinline__ void tile_rotate(const PmtModelDesc& D, const float* W, const float* y, float* Fb) {
-  const int row = threadIdx.x & (TILE - 1), half = threadIdx.x >> 7;
+  const int row = threadIdx.x & (TILE - 1), part = threadIdx.x / TILE;
   const int E = D.d_feat;
-  const int e_lo = half ? E / 2 : 0, e_hi = half ? E : E / 2;
+  const int e_lo = part_lo(E, part), e_hi = part_lo(E, part + 1);
   for (int i = e_lo; i < e_hi; ++i) {
     float acc = 0.f;
     for (int j = 0; j < E; ++j) acc = fmaf(__ldg(W + D.rotation + i * E + j), y[j * LD + row] + __ldg(W + D.translation + j), acc);
@@ -343,10 +343,10 @@ __device__ __forceinline__ void tile_rotate(const PmtModelDesc& D, const float* 
 // feature_clustering.py:82-119: per alt read K+2 log-likelihoods into Lb[0..K+2)
 __device__ __forceinline__ void tile_head(const PmtModelDesc& D, const float* W, const HeadConst* HC, const TileMeta& M,
                                           const float* Fb, float* Lb) {
-  const int row = threadIdx.x & (TILE - 1), half = threadIdx.x >> 7;
+  const int row = threadIdx.x & (TILE - 1), part = threadIdx.x / TILE;
   const int E = D.d_feat, K = D.n_clusters;
   if (row >= M.ref_pad && M.rowvar[row] >= 0) {
-    if (half == 0) {
+    if (part == 0) {
       float q = 0.f, q2 = 0.f;
       for (int e = 0; e < E; ++e) {
         const float x = Fb[e * LD + row];
@@ -356,7 +356,7 @@ __device__ __forceinline__ void tile_head(const PmtModelDesc& D, const float* W,
       Lb[0 * LD + row] = HC->c_non - q / 2.f;
       Lb[1 * LD + row] = HC->c_out - q2 / 2.f;
     }
-    for (int k = half; k < K; k += 2) {
+    for (int k = part; k < K; k += NPART) {
       const float* u = W + D.unit_ke + k * E;
       float p = 0.f;
       for (int e = 0; e < E; ++e) p = fmaf(Fb[e * LD + row], __ldg(u + e), p);
