@@ -4,6 +4,7 @@
 //   reads_backward_kernel     per tile: forward recompute (activations to a per-CTA L2-resident scratch),
 //                             then head -> rotation -> reducer -> gated blocks -> read embedding in reverse;
 //                             weight gradients accumulate in a CTA-private flat buffer (no atomics, fixed order)
+//   reads_backward_long_kernel  the same pieces for sets longer than a tile, walked in chunks
 //   info_mlp_backward_kernel  info_embedding MLP, rows = variants
 //   hap_cnn_backward_kernel   DNASequenceConvolution
 //   reduce_partials_kernel    sum of the CTA-private buffers in CTA order (bitwise reproducible)
@@ -33,19 +34,14 @@ struct BwdArgs {
   float* d_info_seq;          // [B][d_info + d_seq] gradient handed to the variant kernels
   float* scratch;             // per-CTA activation scratch
   long long scratch_stride;   // floats
+  float* long_scratch;        // per-CTA scratch of the long-set kernel (one region per chunk of the longest set)
+  long long long_scratch_stride;
   float* partials;            // per-CTA flat gradient buffers [grid][n_params]
   int n_claims;
   long long* trace;           // measurement hook (pmt_set_backward_trace): phase clocks of CTA 0's third tile, or null
 };
 
-// trace[0] = number of records; record i = (phase id, clock64()) at trace[1 + 2i]
-#define PMT_BWD_TRACE(id)                                                     \
-  do {                                                                        \
-    if (tracing && threadIdx.x == 0) {                                        \
-      const long long n_ = A.trace[0];                                        \
-      if (n_ < 250) { A.trace[1 + 2 * n_] = (id); A.trace[2 + 2 * n_] = clock64(); A.trace[0] = n_ + 1; } \
-    }                                                                         \
-  } while (0)
+// trace[0] = number of records; record i = (phase id, clock64()) at trace[1 + 2i]  (PMT_TILE_TRACE)
 
 __device__ __forceinline__ float* pick_free(float* const* bufs, const float* a, const float* b, const float* c) {
   for (int i = 0; i < 4; ++i)
@@ -138,47 +134,457 @@ static __device__ __noinline__ float* mlp_backward(const Plan& P, const PmtLinea
 
 __device__ __forceinline__ float ldg_or_zero(const float* p, long long i) { return p ? __ldg(p + i) : 0.f; }
 
+// ------------------------------------------------------------------------------------------------
+// Per-tile pieces of the read-path backward, shared by the tile kernel (whole variants packed into one
+// tile) and the long-set kernel (one variant walked in chunks of TILE rows).  The only cross-read coupling
+// is the per-variant mean field of each gated block (gated_mlp.py:236-248), so a block's backward splits
+// into: bwd_block_gate (everything up to the sums of d gate over the set), bwd_block_meanfield (once per
+// set) and bwd_block_finish (the rest, which needs the mean-field gradient of the whole set).
+// ------------------------------------------------------------------------------------------------
+struct BwdTile {
+  const Plan& P;
+  const BwdArgs& A;
+  TileCtx& C;
+  Stage& stage;
+  BlockAccum& acc;
+  float* const* bufs;   // four [bwd_rows][LD] activation buffers
+  float* dsums;         // [nv][2][sum_w] gradients of the mean fields (same layout as C.sums)
+  float* wpart;         // BlockAccum storage [NWARPS][acc_cap]
+  float* small;         // [64] scratch for tiny reductions
+  float* part;          // this CTA's flat gradient buffer
+  int acc_cap;
+  bool tracing;
+};
+
+struct BwdSmem {
+  float* bufs[4];
+  float *st0, *st1, *dsums, *wpart, *small;
+  int acc_cap;
+};
+
+__device__ __forceinline__ void carve_bwd_smem(const Plan& P, float* smem, TileCtx& C, BwdSmem& S) {
+  const PmtModelDesc& D = P.d;
+  const int R = P.bwd_rows;
+  for (int i = 0; i < 4; ++i) S.bufs[i] = smem + i * R * LD;
+  S.st0 = smem + 4 * R * LD;
+  S.st1 = S.st0 + P.stage_floats;
+  C.X = S.bufs[0]; C.T1 = S.bufs[1]; C.T2 = S.bufs[2];
+  C.sums = S.st1 + P.stage_floats;
+  S.dsums = C.sums + TILE * 2 * P.sum_w;
+  C.llsum = S.dsums + TILE * 2 * P.sum_w;
+  const int n_head = D.d_feat + D.n_clusters * D.d_feat + 5 * D.n_clusters;
+  S.acc_cap = n_head > 8 ? n_head : 8;
+  S.wpart = C.llsum + TILE * 2 * 16;
+  S.small = S.wpart + NWARPS * S.acc_cap;
+  C.HC = reinterpret_cast<HeadConst*>(S.small + 64);
+  C.M = reinterpret_cast<TileMeta*>((reinterpret_cast<uintptr_t>(C.HC + 1) + 15) & ~uintptr_t(15));
+}
+
+#define PMT_TILE_TRACE(id)                                                    \
+  do {                                                                        \
+    if (T.tracing && threadIdx.x == 0) {                                      \
+      const long long n_ = T.A.trace[0];                                      \
+      if (n_ < 250) { T.A.trace[1 + 2 * n_] = (id); T.A.trace[2 + 2 * n_] = clock64(); T.A.trace[0] = n_ + 1; } \
+    }                                                                         \
+  } while (0)
+
+// Reducer -> rotation -> clustering head (recompute, activations to `scr`), then their backward
+// (feature_clustering.py:82-135, euclidean_transformation.py:19-20, artifact_model.py:258-259).
+// C.X holds the reducer's input.  Returns the buffer holding dL/d(output of the last gated block).
+static __device__ __forceinline__ float* bwd_tail(BwdTile& T, float* scr) {
+  const Plan& P = T.P;
+  const BwdArgs& A = T.A;
+  TileCtx& C = T.C;
+  const PmtModelDesc& D = P.d;
+  const TileMeta& M = *C.M;
+  const float* W = C.W;
+  float* part = T.part;
+  BlockAccum& acc = T.acc;
+  const int tid = threadIdx.x, row = tid & (TILE - 1), rp = tid / TILE;
+  const int E = D.d_feat, K = D.n_clusters, rows_used = C.rows_used;
+  const int my_var = M.rowvar[row];
+  const bool is_alt = row >= M.ref_pad;
+  PmtOutputs no_out;
+  memset(&no_out, 0, sizeof(no_out));
+  float *Yb, *Fb;
+  tile_tail(P, C, T.stage, no_out, false, scr, Yb, Fb);
+  PMT_TILE_TRACE(20);
+  float* Lb = pick_free(T.bufs, Yb, Fb, T.bufs[3]);   // the third forward buffer (held the log-likelihoods)
+  float* Xtra = T.bufs[3];
+
+  for (int i = tid; i < NWARPS * T.acc_cap; i += NTHREADS) T.wpart[i] = 0.f;
+  __syncthreads();
+  {
+    const bool live = is_alt && my_var >= 0;
+    const long long v = live ? (long long)M.v0 + my_var : 0;
+    // row-part p writes its share of d f into Lb rows [p*E, (p+1)*E)
+    float* dfp = Lb + rp * E * LD;
+    for (int e = 0; e < E; ++e) dfp[e * LD + row] = 0.f;
+    if (rp == 0) {
+      const float g0 = live ? ldg_or_zero(A.d_logits_bk, v * (K + 2) + 0) : 0.f;
+      const float g1 = live ? ldg_or_zero(A.d_logits_bk, v * (K + 2) + 1) : 0.f;
+      for (int e = 0; e < E; ++e) {
+        const float s = C.HC->sigma[e], f = Fb[e * LD + row];
+        float contrib = 0.f;
+        if (live) {
+          dfp[e * LD + row] += -g0 * f / (s * s) - g1 * f / (4.f * s * s);
+          contrib = g0 * (-1.f / s + f * f / (s * s * s)) + g1 * (-1.f / s + f * f / (4.f * s * s * s));
+        }
+        acc.add(e, contrib);
+      }
+    }
+    for (int k = rp; k < K; k += NPART) {
+      const float* u = W + D.unit_ke + k * E;
+      const float gk = live ? ldg_or_zero(A.d_logits_bk, v * (K + 2) + 2 + k) : 0.f;
+      const float tau = __ldg(W + D.tau_k + k), lam = __ldg(W + D.lambda_k + k), sg = __ldg(W + D.emg_sigma_k + k),
+                  mu = __ldg(W + D.mu_k + k);
+      float p = 0.f;
+      for (int e = 0; e < E; ++e) p = fmaf(Fb[e * LD + row], __ldg(u + e), p);
+      float o2 = 0.f, odu = 0.f;
+      for (int e = 0; e < E; ++e) {
+        const float o = Fb[e * LD + row] - p * __ldg(u + e);
+        o2 = fmaf(o, o, o2); odu = fmaf(o, __ldg(u + e), odu);
+      }
+      const float zarg = (C.HC->shift[k] - p) / C.HC->sqrt2_sigma[k];
+      const float dlp = dlogerfc(zarg);
+      const float dpar_dp = -dlp / C.HC->sqrt2_sigma[k] - lam;
+      const float c_orth = -1.f / C.HC->two_tau2[k];
+      for (int e = 0; e < E; ++e) {
+        const float f = Fb[e * LD + row], ue = __ldg(u + e), o = f - p * ue;
+        if (live) dfp[e * LD + row] += gk * (c_orth * (2.f * o - 2.f * odu * ue) + dpar_dp * ue);
+        acc.add(E + k * E + e, gk * (c_orth * (-2.f * f * odu - 2.f * p * o) + dpar_dp * f));
+      }
+      const int base = E + K * E;
+      acc.add(base + 0 * K + k, gk * (-(E - 1) / tau + o2 / (tau * tau * tau)));                       // tau
+      acc.add(base + 1 * K + k, gk * (dlp / C.HC->sqrt2_sigma[k] + lam));                              // mu
+      acc.add(base + 2 * K + k, gk * (dlp * (1.41421356237f * lam - zarg / sg) + lam * lam * sg));    // emg sigma
+      acc.add(base + 3 * K + k, gk * (1.f / lam + dlp * sg * 0.70710678118f + mu + lam * sg * sg - p));  // lambda
+      // the log cluster weight is added once per variant, after the sum over its reads (feature_clustering.py:115-116)
+      acc.add(base + 4 * K + k, (live && M.alt_head && row == M.alt_start[my_var]) ? gk : 0.f);
+    }
+  }
+  __syncthreads();
+  acc.flush(part + D.sigma_e, 0, E);
+  acc.flush(part + D.unit_ke, E, K * E);
+  {
+    const int base = E + K * E;
+    const int offs[5] = {D.tau_k, D.mu_k, D.emg_sigma_k, D.lambda_k, D.logw_k};
+    for (int q = 0; q < 5; ++q) acc.flush(part + offs[q], base + q * K, K);
+  }
+  // d f = head part (all row-parts) + mean part; written in place over the final features
+  {
+    const int e_lo = part_lo(E, rp), e_hi = part_lo(E, rp + 1);
+    for (int e = e_lo; e < e_hi; ++e) {
+      float d = 0.f;
+#pragma unroll
+      for (int q = 0; q < NPART; ++q) d += Lb[(q * E + e) * LD + row];
+      if (my_var >= 0) {
+        const long long v = (long long)M.v0 + my_var;
+        d += is_alt ? ldg_or_zero(A.d_alt_means, v * E + e) / (M.alt_total[my_var] + 1e-4f)
+                    : ldg_or_zero(A.d_ref_means, v * E + e) / (M.ref_total[my_var] + 1e-4f);
+      } else {
+        d = 0.f;
+      }
+      Fb[e * LD + row] = d;
+      Yb[e * LD + row] += __ldg(W + D.translation + e);   // y + t, the rotation's input
+    }
+  }
+  __syncthreads();
+  // rotation (euclidean_transformation.py:19-20): f = Q (y + t)
+  wgrad_tile(smem_addr(Fb), E, smem_addr(Yb), E, part + D.rotation, 0, rows_used);
+  {
+    const int e_lo = part_lo(E, rp), e_hi = part_lo(E, rp + 1);
+    for (int j = e_lo; j < e_hi; ++j) {
+      float a = 0.f;
+      for (int i = 0; i < E; ++i) a = fmaf(__ldg(W + D.rotation + i * E + j), Fb[i * LD + row], a);
+      Xtra[j * LD + row] = a;
+    }
+  }
+  __syncthreads();
+  rowdot_tile(Xtra, nullptr, E, part + D.translation, 0, rows_used);
+  PMT_TILE_TRACE(21);
+  float* G = mlp_backward(P, D.red_ops, D.n_red_ops, P.red_g0, scr, P.scr_red, Xtra, T.bufs, T.stage, W, part, rows_used, true);
+  PMT_TILE_TRACE(22);
+  return G;
+}
+
+struct RowNorm { float mean, rstd, mean2, rstd2; };
+
+// Reloads x (-> Ab) and z (-> Cz[0, 2H)) of gated block `blk` from the recompute scratch -- or, when `cz_state` is given,
+// the [0, 6H) rows bwd_block_gate left in Cz -- and redoes the block's LayerNorm: Ab = xhat, Bn = LN(x).
+static __device__ __forceinline__ RowNorm bwd_block_reload(BwdTile& T, int blk, const float* scr, const float* cz_state,
+                                                           float* Ab, float* Bn, float* Cz, int prefetch_key) {
+  const Plan& P = T.P;
+  const PmtModelDesc& D = P.d;
+  const PmtBlockOffsets& BO = D.blocks[blk];
+  const float* W = T.C.W;
+  const int row = threadIdx.x & (TILE - 1), rp = threadIdx.x / TILE;
+  const int Dm = D.d_model, H = D.d_ffn / 2;
+  load_rows(Ab, Dm, scr + P.scr_x[blk]);
+  if (cz_state) load_rows(Cz, 6 * H, cz_state);
+  else load_rows(Cz, 2 * H, scr + P.scr_z[blk]);
+  T.stage.prefetch(prefetch_key);
+  __syncthreads();
+  RowNorm n;
+  row_stats(Ab, Dm, row, n.mean, n.rstd);
+  row_stats(Cz + H * LD, H, row, n.mean2, n.rstd2);
+  __syncthreads();
+  const int d_lo = part_lo(Dm, rp), d_hi = part_lo(Dm, rp + 1);
+  for (int f = d_lo; f < d_hi; ++f) {
+    const float xh = (Ab[f * LD + row] - n.mean) * n.rstd;
+    Ab[f * LD + row] = xh;
+    Bn[f * LD + row] = xh * __ldg(W + BO.ln_w + f) + __ldg(W + BO.ln_b + f);
+  }
+  return n;
+}
+
+// First half of a gated block's backward (gated_mlp.py:177-251 in reverse) over the rows of this tile: proj2, the
+// gate, the scalar gate parameters, and the per-variant sums of d gate (into T.dsums; `accumulate` adds to them when
+// the set spans several chunks).  `means`: the block's forward mean fields [2][sum_w] when the set spans several
+// chunks (nullptr: computed here from the tile, which then holds whole sets).  Leaves Cz = [z1 z2 | xhat2 | gate | d z1 | d gate].
+static __device__ __forceinline__ RowNorm bwd_block_gate(BwdTile& T, int blk, const float* scr, const float* means, float* G,
+                                                         float* Ab, float* Bn, float* Cz, bool accumulate) {
+  const Plan& P = T.P;
+  TileCtx& C = T.C;
+  const PmtModelDesc& D = P.d;
+  const PmtBlockOffsets& BO = D.blocks[blk];
+  const TileMeta& M = *C.M;
+  const float* W = C.W;
+  float* part = T.part;
+  const int tid = threadIdx.x, row = tid & (TILE - 1), rp = tid / TILE;
+  const int Dm = D.d_model, H = D.d_ffn / 2, rows_used = C.rows_used, ref_pad = M.ref_pad;
+  const int my_var = M.rowvar[row];
+  const bool is_alt = row >= ref_pad;
+  const int g1 = P.blk_g0 + 2 * blk, g2 = g1 + 1;
+  const float alpha = __ldg(W + (is_alt ? BO.alpha_alt : BO.alpha_ref));
+  const float beta = __ldg(W + (is_alt ? BO.beta_alt : BO.beta_ref));
+  const float gamma = __ldg(W + BO.gamma);
+  const int f_lo = part_lo(H, rp), f_hi = part_lo(H, rp + 1);
+  const RowNorm n = bwd_block_reload(T, blk, scr, nullptr, Ab, Bn, Cz, MAX_GEMM + g2);
+  for (int f = f_lo; f < f_hi; ++f) {
+    const float xh2 = (Cz[(H + f) * LD + row] - n.mean2) * n.rstd2;
+    Cz[(2 * H + f) * LD + row] = xh2;
+    Cz[(3 * H + f) * LD + row] = xh2 * __ldg(W + BO.ln2_w + f) + __ldg(W + BO.ln2_b + f);   // z2n
+  }
+  __syncthreads();
+  if (means) {
+    for (int i = tid; i < 2 * P.sum_w; i += NTHREADS) C.sums[i] = means[i];
+    __syncthreads();
+  } else {
+    segment_sums(M, Cz, 3 * H, H, C.sums, P.sum_w, false, false);
+    __syncthreads();
+    block_means(P, C, blk);
+  }
+  for (int f = f_lo; f < f_hi; ++f) {
+    const float gate = gate_value(P, C, BO, row, f, Cz[(3 * H + f) * LD + row], my_var, is_alt, alpha, beta, gamma);
+    Cz[(3 * H + f) * LD + row] = gate;
+    Cz[(4 * H + f) * LD + row] = Cz[f * LD + row] * gate;   // u = z1 * gate
+  }
+  PMT_TILE_TRACE(100 + blk * 10 + 0);
+  // proj2: x_out = x + W2_s u + b2_s
+  const float* imgT2 = T.stage.acquire(MAX_GEMM + g2);
+  T.stage.prefetch(MAX_GEMM + g1);
+  wgrad_tile(smem_addr(G), Dm, smem_addr(Cz + 4 * H * LD), H, part + BO.p2_ref_w, 0, ref_pad);
+  wgrad_tile(smem_addr(G), Dm, smem_addr(Cz + 4 * H * LD), H, part + BO.p2_alt_w, ref_pad, rows_used);
+  rowdot_tile(G, nullptr, Dm, part + BO.p2_ref_b, 0, ref_pad);
+  rowdot_tile(G, nullptr, Dm, part + BO.p2_alt_b, ref_pad, rows_used);
+  gemm_tile_T(G, P.gemm[g2], imgT2, ref_pad, Cz + 5 * H * LD, EPI_STORE, 1.f, nullptr, rows_used);   // du
+  __syncthreads();
+  PMT_TILE_TRACE(100 + blk * 10 + 1);
+  {  // d z1 = du * gate ; d gate = du * z1 ; scalar gradients of the gate
+    float s_alpha = 0.f, s_beta = 0.f, s_gamma = 0.f;
+    for (int f = f_lo; f < f_hi; ++f) {
+      const float du = Cz[(5 * H + f) * LD + row], gate = Cz[(3 * H + f) * LD + row], z1 = Cz[f * LD + row];
+      const float dgate = du * z1;
+      Cz[(4 * H + f) * LD + row] = du * gate;
+      Cz[(5 * H + f) * LD + row] = dgate;
+      if (my_var >= 0) {
+        const float z2n = Cz[(2 * H + f) * LD + row] * __ldg(W + BO.ln2_w + f) + __ldg(W + BO.ln2_b + f);
+        const float m_ref = C.sums[(my_var * 2 + 0) * P.sum_w + f];
+        s_alpha = fmaf(dgate, z2n, s_alpha);
+        s_beta = fmaf(dgate, is_alt ? C.sums[(my_var * 2 + 1) * P.sum_w + f] : m_ref, s_beta);
+        if (is_alt) s_gamma = fmaf(dgate, m_ref, s_gamma);
+      }
+    }
+    T.acc.add(0, is_alt ? 0.f : s_alpha); T.acc.add(1, is_alt ? s_alpha : 0.f);
+    T.acc.add(2, is_alt ? 0.f : s_beta);  T.acc.add(3, is_alt ? s_beta : 0.f);
+    T.acc.add(4, s_gamma);
+  }
+  __syncthreads();
+  if (tid < 5) {
+    const int offs[5] = {BO.alpha_ref, BO.alpha_alt, BO.beta_ref, BO.beta_alt, BO.gamma};
+    float s = 0.f;
+    for (int w = 0; w < NWARPS; ++w) s += T.wpart[w * T.acc_cap + tid];
+    red_add(part + offs[tid], s);
+  }
+  segment_sums(M, Cz, 5 * H, H, T.dsums, P.sum_w, false, accumulate);
+  __syncthreads();
+  return n;
+}
+
+// Gradients of the mean fields of block `blk` (ragged_sets.py:144-155 backward), once per set: T.dsums goes from the
+// per-variant sums of d gate to d z2n's per-read share; C.sums holds the block's forward mean fields.
+static __device__ __forceinline__ void bwd_block_meanfield(BwdTile& T, int blk) {
+  const Plan& P = T.P;
+  TileCtx& C = T.C;
+  const PmtBlockOffsets& BO = P.d.blocks[blk];
+  const TileMeta& M = *C.M;
+  const float* W = C.W;
+  float* dsums = T.dsums;
+  const int tid = threadIdx.x, H = P.d.d_ffn / 2;
+  const float gamma = __ldg(W + BO.gamma);
+  const float regw = __ldg(W + BO.reg_weight) + 0.25f;
+  const float b_ref = __ldg(W + BO.beta_ref), b_alt = __ldg(W + BO.beta_alt);
+  for (int idx = tid; idx < M.nv * H; idx += NTHREADS) {
+    const int j = idx / H, f = idx % H;
+    const float s_ref = dsums[(j * 2 + 0) * P.sum_w + f], s_alt = dsums[(j * 2 + 1) * P.sum_w + f];
+    dsums[(j * 2 + 0) * P.sum_w + f] = b_ref * s_ref + gamma * s_alt;   // d m_ref
+    dsums[(j * 2 + 1) * P.sum_w + f] = b_alt * s_alt;                   // d m_alt
+  }
+  __syncthreads();
+  if (tid < H) {
+    float d_reg = 0.f, d_w = 0.f;
+    const float reg = __ldg(W + BO.regularizer + tid);
+    for (int j = 0; j < M.nv; ++j) {
+      const float dm = dsums[(j * 2 + 0) * P.sum_w + tid], den = M.ref_total[j] + regw;
+      d_reg += dm * regw / den;
+      d_w += dm * (reg - C.sums[(j * 2 + 0) * P.sum_w + tid]) / den;
+    }
+    red_add(T.part + BO.regularizer + tid, d_reg);
+    T.small[tid] = d_w;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float s = 0.f;
+    for (int f = 0; f < H; ++f) s += T.small[f];
+    red_add(T.part + BO.reg_weight, s);
+  }
+  for (int idx = tid; idx < M.nv * H; idx += NTHREADS) {
+    const int j = idx / H, f = idx % H;
+    dsums[(j * 2 + 0) * P.sum_w + f] /= (M.ref_total[j] + regw);
+    dsums[(j * 2 + 1) * P.sum_w + f] /= (M.alt_total[j] + 1e-4f);
+  }
+  __syncthreads();
+}
+
+// Second half of a gated block's backward: SGU LayerNorm, proj1, the block's LayerNorm; G += dL/dx through the block.
+// Expects Ab = xhat, Bn = LN(x), Cz as bwd_block_gate left it, and the row statistics of bwd_block_reload.
+static __device__ __forceinline__ void bwd_block_finish(BwdTile& T, int blk, float* G, float* Ab, float* Bn, float* Cz,
+                                                        const RowNorm& n) {
+  const Plan& P = T.P;
+  TileCtx& C = T.C;
+  const PmtModelDesc& D = P.d;
+  const PmtBlockOffsets& BO = D.blocks[blk];
+  const TileMeta& M = *C.M;
+  const float* W = C.W;
+  float* part = T.part;
+  float* dsums = T.dsums;
+  const int row = threadIdx.x & (TILE - 1), rp = threadIdx.x / TILE;
+  const int Dm = D.d_model, H = D.d_ffn / 2, rows_used = C.rows_used, ref_pad = M.ref_pad;
+  const int my_var = M.rowvar[row];
+  const bool is_alt = row >= ref_pad;
+  const int g1 = P.blk_g0 + 2 * blk;
+  const float alpha = __ldg(W + (is_alt ? BO.alpha_alt : BO.alpha_ref));
+  const int f_lo = part_lo(H, rp), f_hi = part_lo(H, rp + 1);
+  const int d_lo = part_lo(Dm, rp), d_hi = part_lo(Dm, rp + 1);
+  for (int f = f_lo; f < f_hi; ++f) {   // d z2n
+    float d = alpha * Cz[(5 * H + f) * LD + row];
+    if (my_var >= 0) d += dsums[(my_var * 2 + (is_alt ? 1 : 0)) * P.sum_w + f];
+    Cz[(3 * H + f) * LD + row] = d;
+  }
+  __syncthreads();
+  rowdot_tile(Cz + 3 * H * LD, Cz + 2 * H * LD, H, part + BO.ln2_w, 0, rows_used);
+  rowdot_tile(Cz + 3 * H * LD, nullptr, H, part + BO.ln2_b, 0, rows_used);
+  {  // SGU LayerNorm backward -> d z2 (pre-norm), placed after d z1 so that [4H, 6H) = d z
+    float m1 = 0.f, m2 = 0.f;
+    for (int f = 0; f < H; ++f) {
+      const float dxh = Cz[(3 * H + f) * LD + row] * __ldg(W + BO.ln2_w + f);
+      m1 += dxh; m2 = fmaf(dxh, Cz[(2 * H + f) * LD + row], m2);
+    }
+    m1 /= H; m2 /= H;
+    for (int f = f_lo; f < f_hi; ++f) {
+      const float dxh = Cz[(3 * H + f) * LD + row] * __ldg(W + BO.ln2_w + f);
+      Cz[(5 * H + f) * LD + row] = n.rstd2 * (dxh - m1 - Cz[(2 * H + f) * LD + row] * m2);
+    }
+  }
+  __syncthreads();
+  PMT_TILE_TRACE(100 + blk * 10 + 2);
+  mul_dselu(Cz + 4 * H * LD, Cz, 2 * H);   // through z = SELU(proj1 n)
+  // proj1: z_pre = W1_s n + b1_s
+  const float* imgT1 = T.stage.acquire(MAX_GEMM + g1);
+  if (blk > 0) T.stage.prefetch(MAX_GEMM + g1 - 1);
+  wgrad_tile(smem_addr(Cz + 4 * H * LD), 2 * H, smem_addr(Bn), Dm, part + BO.p1_ref_w, 0, ref_pad);
+  wgrad_tile(smem_addr(Cz + 4 * H * LD), 2 * H, smem_addr(Bn), Dm, part + BO.p1_alt_w, ref_pad, rows_used);
+  rowdot_tile(Cz + 4 * H * LD, nullptr, 2 * H, part + BO.p1_ref_b, 0, ref_pad);
+  rowdot_tile(Cz + 4 * H * LD, nullptr, 2 * H, part + BO.p1_alt_b, ref_pad, rows_used);
+  __syncthreads();
+  gemm_tile_T(Cz + 4 * H * LD, P.gemm[g1], imgT1, ref_pad, Bn, EPI_STORE, 1.f, nullptr, rows_used);   // d n
+  __syncthreads();
+  PMT_TILE_TRACE(100 + blk * 10 + 3);
+  rowdot_tile(Bn, Ab, Dm, part + BO.ln_w, 0, rows_used);
+  rowdot_tile(Bn, nullptr, Dm, part + BO.ln_b, 0, rows_used);
+  {  // LayerNorm backward, added to the residual gradient
+    float m1 = 0.f, m2 = 0.f;
+    for (int f = 0; f < Dm; ++f) {
+      const float dxh = Bn[f * LD + row] * __ldg(W + BO.ln_w + f);
+      m1 += dxh; m2 = fmaf(dxh, Ab[f * LD + row], m2);
+    }
+    m1 /= Dm; m2 /= Dm;
+    for (int f = d_lo; f < d_hi; ++f) {
+      const float dxh = Bn[f * LD + row] * __ldg(W + BO.ln_w + f);
+      G[f * LD + row] += n.rstd * (dxh - m1 - Ab[f * LD + row] * m2);
+    }
+  }
+  __syncthreads();
+  PMT_TILE_TRACE(100 + blk * 10 + 4);
+}
+
+// concat (artifact_model.py:246-251): d info_seq of each variant (added to it when the set spans several chunks), then
+// the read embedding's backward (artifact_model.py:243).  G = dL/d(input of the first gated block).
+static __device__ __forceinline__ void bwd_embed(BwdTile& T, float* scr, float* G, bool accumulate) {
+  const Plan& P = T.P;
+  const PmtModelDesc& D = P.d;
+  const TileMeta& M = *T.C.M;
+  {
+    const int w = D.d_info + D.d_seq;
+    for (int idx = threadIdx.x; idx < M.nv * w; idx += NTHREADS) {
+      const int j = idx / w, f = idx % w;
+      const float* p = G + (D.d_read + f) * LD;
+      float s = 0.f;
+      for (int i = 0; i < M.ref_cnt[j]; ++i) s += p[M.ref_start[j] + i];
+      for (int i = 0; i < M.alt_cnt[j]; ++i) s += p[M.alt_start[j] + i];
+      float* o = T.A.d_info_seq + ((long long)M.v0 + j) * w + f;
+      *o = accumulate ? *o + s : s;
+    }
+  }
+  PMT_TILE_TRACE(23);
+  mlp_backward(P, D.read_ops, D.n_read_ops, P.read_g0, scr, P.scr_read, G, T.bufs, T.stage, T.C.W, T.part, T.C.rows_used, false);
+  __syncthreads();
+  PMT_TILE_TRACE(24);
+}
+
 __global__ void __launch_bounds__(NTHREADS, 1)
 reads_backward_kernel(const __grid_constant__ Plan P, const __grid_constant__ BwdArgs A) {
   extern __shared__ __align__(16) float smem[];
   const PmtModelDesc& D = P.d;
-  const int R = P.bwd_rows;
-  float* bufs[4] = {smem, smem + R * LD, smem + 2 * R * LD, smem + 3 * R * LD};
-  float* st0 = smem + 4 * R * LD;
-  float* st1 = st0 + P.stage_floats;
   TileCtx C;
-  C.X = bufs[0]; C.T1 = bufs[1]; C.T2 = bufs[2];
-  C.sums = st1 + P.stage_floats;
-  float* dsums = C.sums + TILE * 2 * P.sum_w;   // same [nv][2][sum_w] layout, gradients of the mean fields
-  C.llsum = dsums + TILE * 2 * P.sum_w;
-  const int E = D.d_feat, K = D.n_clusters, Dm = D.d_model, H = D.d_ffn / 2;
-  const int n_head = E + K * E + 5 * K;
-  const int acc_cap = n_head > 8 ? n_head : 8;
-  float* wpart = C.llsum + TILE * 2 * 16;
-  float* stat = wpart + NWARPS * acc_cap;          // [2][TILE] LayerNorm rstd of the block being differentiated
-  float* small = stat + 2 * TILE;                  // [64] scratch for tiny reductions
-  C.HC = reinterpret_cast<HeadConst*>(small + 64);
-  C.M = reinterpret_cast<TileMeta*>((reinterpret_cast<uintptr_t>(C.HC + 1) + 15) & ~uintptr_t(15));
+  BwdSmem S;
+  carve_bwd_smem(P, smem, C, S);
   TileMeta& M = *C.M;
   C.W = A.wflat;
-  const float* W = A.wflat;
   BlockAccum acc;
-  acc.init(wpart, acc_cap);
-
+  acc.init(S.wpart, S.acc_cap);
   const int tid = threadIdx.x;
-  const int row = tid & (TILE - 1), rp = tid / TILE;   // (row, row-part) of this thread
-  const int B = A.batch.n_variants;
+  const int B = A.batch.n_variants, Dm = D.d_model, H = D.d_ffn / 2;
   Stage stage;
-  stage.init(st0, st1, A.image, &P);
-  if (tid == 0) head_constants(D, W, C.HC);
-  for (int i = tid; i < 4 * R * LD; i += NTHREADS) smem[i] = 0.f;
+  stage.init(S.st0, S.st1, A.image, &P);
+  if (tid == 0) head_constants(D, C.W, C.HC);
+  for (int i = tid; i < 4 * P.bwd_rows * LD; i += NTHREADS) smem[i] = 0.f;
   __syncthreads();
   const long long total_ref = __ldg(A.batch.ref_off + B);
   float* scr = A.scratch + (long long)blockIdx.x * A.scratch_stride;
-  float* part = A.partials + (long long)blockIdx.x * D.n_params;
+  BwdTile T{P, A, C, stage, acc, S.bufs, S.dsums, S.wpart, S.small, A.partials + (long long)blockIdx.x * D.n_params, S.acc_cap, false};
   const int claim = P.claim_variants;
-  PmtOutputs no_out;
-  memset(&no_out, 0, sizeof(no_out));
 
   int tile_no = 0;
   // static round-robin assignment of claims to CTAs: the summation order of every gradient is fixed
@@ -188,20 +594,16 @@ reads_backward_kernel(const __grid_constant__ Plan P, const __grid_constant__ Bw
     int v_cur = (int)cv0;
     while (v_cur < cv1) {
       const int nv = build_tile(A.batch, v_cur, cv1, total_ref, M);
-      if (nv == 0) { v_cur += 1; continue; }   // sets longer than a tile are rejected by the host for training
+      if (nv == 0) { v_cur += 1; continue; }   // a set longer than a tile: reads_backward_long_kernel
       v_cur += nv;
-      const bool tracing = A.trace != nullptr && blockIdx.x == 0 && tile_no == 2;
+      T.tracing = A.trace != nullptr && blockIdx.x == 0 && tile_no == 2;
       tile_no += 1;
-      PMT_BWD_TRACE(0);
-      const int rows_used = (M.rows + 3) & ~3;
-      C.rows_used = rows_used;
-      const int ref_pad = M.ref_pad;
-      const int my_var = M.rowvar[row];
-      const bool is_alt = row >= ref_pad;
+      PMT_TILE_TRACE(0);
+      C.rows_used = (M.rows + 3) & ~3;
 
       // ======================= forward recompute, activations to scratch =======================
       tile_embed(P, C, stage, A.batch, A.info_seq, scr);
-      PMT_BWD_TRACE(1);
+      PMT_TILE_TRACE(1);
       for (int blk = 0; blk < D.n_blocks; ++blk) {
         save_rows(C.X, Dm, scr + P.scr_x[blk]);
         block_phase_a(P, C, stage, blk, scr + P.scr_z[blk]);
@@ -209,298 +611,133 @@ reads_backward_kernel(const __grid_constant__ Plan P, const __grid_constant__ Bw
         __syncthreads();
         block_means(P, C, blk);
         block_phase_b(P, C, stage, blk, blk + 1 < D.n_blocks ? P.blk_g0 + 2 * blk + 2 : P.red_g0);
-        PMT_BWD_TRACE(2 + blk);
+        PMT_TILE_TRACE(2 + blk);
       }
-      float *Yb, *Fb;
-      tile_tail(P, C, stage, no_out, false, scr, Yb, Fb);
-      PMT_BWD_TRACE(20);
-      float* Lb = pick_free(bufs, Yb, Fb, bufs[3]);   // the third forward buffer (held the log-likelihoods)
-      float* Xtra = bufs[3];
-
-      // ======================= clustering head + set means (feature_clustering.py:82-135) =======================
-      for (int i = tid; i < NWARPS * acc_cap; i += NTHREADS) wpart[i] = 0.f;
-      __syncthreads();
-      {
-        const bool live = is_alt && my_var >= 0;
-        const long long v = live ? (long long)M.v0 + my_var : 0;
-        // row-part p writes its share of d f into Lb rows [p*E, (p+1)*E)
-        float* dfp = Lb + rp * E * LD;
-        for (int e = 0; e < E; ++e) dfp[e * LD + row] = 0.f;
-        if (rp == 0) {
-          const float g0 = live ? ldg_or_zero(A.d_logits_bk, v * (K + 2) + 0) : 0.f;
-          const float g1 = live ? ldg_or_zero(A.d_logits_bk, v * (K + 2) + 1) : 0.f;
-          for (int e = 0; e < E; ++e) {
-            const float s = C.HC->sigma[e], f = Fb[e * LD + row];
-            float contrib = 0.f;
-            if (live) {
-              dfp[e * LD + row] += -g0 * f / (s * s) - g1 * f / (4.f * s * s);
-              contrib = g0 * (-1.f / s + f * f / (s * s * s)) + g1 * (-1.f / s + f * f / (4.f * s * s * s));
-            }
-            acc.add(e, contrib);
-          }
-        }
-        for (int k = rp; k < K; k += NPART) {
-          const float* u = W + D.unit_ke + k * E;
-          const float gk = live ? ldg_or_zero(A.d_logits_bk, v * (K + 2) + 2 + k) : 0.f;
-          const float tau = __ldg(W + D.tau_k + k), lam = __ldg(W + D.lambda_k + k), sg = __ldg(W + D.emg_sigma_k + k),
-                      mu = __ldg(W + D.mu_k + k);
-          float p = 0.f;
-          for (int e = 0; e < E; ++e) p = fmaf(Fb[e * LD + row], __ldg(u + e), p);
-          float o2 = 0.f, odu = 0.f;
-          for (int e = 0; e < E; ++e) {
-            const float o = Fb[e * LD + row] - p * __ldg(u + e);
-            o2 = fmaf(o, o, o2); odu = fmaf(o, __ldg(u + e), odu);
-          }
-          const float zarg = (C.HC->shift[k] - p) / C.HC->sqrt2_sigma[k];
-          const float dlp = dlogerfc(zarg);
-          const float dpar_dp = -dlp / C.HC->sqrt2_sigma[k] - lam;
-          const float c_orth = -1.f / C.HC->two_tau2[k];
-          for (int e = 0; e < E; ++e) {
-            const float f = Fb[e * LD + row], ue = __ldg(u + e), o = f - p * ue;
-            if (live) dfp[e * LD + row] += gk * (c_orth * (2.f * o - 2.f * odu * ue) + dpar_dp * ue);
-            acc.add(E + k * E + e, gk * (c_orth * (-2.f * f * odu - 2.f * p * o) + dpar_dp * f));
-          }
-          const int base = E + K * E;
-          acc.add(base + 0 * K + k, gk * (-(E - 1) / tau + o2 / (tau * tau * tau)));                       // tau
-          acc.add(base + 1 * K + k, gk * (dlp / C.HC->sqrt2_sigma[k] + lam));                              // mu
-          acc.add(base + 2 * K + k, gk * (dlp * (1.41421356237f * lam - zarg / sg) + lam * lam * sg));    // emg sigma
-          acc.add(base + 3 * K + k, gk * (1.f / lam + dlp * sg * 0.70710678118f + mu + lam * sg * sg - p));  // lambda
-          // the log cluster weight is added once per variant, after the sum over its reads (feature_clustering.py:115-116)
-          acc.add(base + 4 * K + k, (live && row == M.alt_start[my_var]) ? gk : 0.f);
-        }
-      }
-      __syncthreads();
-      acc.flush(part + D.sigma_e, 0, E);
-      acc.flush(part + D.unit_ke, E, K * E);
-      {
-        const int base = E + K * E;
-        const int offs[5] = {D.tau_k, D.mu_k, D.emg_sigma_k, D.lambda_k, D.logw_k};
-        for (int q = 0; q < 5; ++q) acc.flush(part + offs[q], base + q * K, K);
-      }
-      // d f = head part (all parts) + mean part; written in place over the final features
-      {
-        const int e_lo = part_lo(E, rp), e_hi = part_lo(E, rp + 1);
-        for (int e = e_lo; e < e_hi; ++e) {
-          float d = 0.f;
-#pragma unroll
-          for (int q = 0; q < NPART; ++q) d += Lb[(q * E + e) * LD + row];
-          if (my_var >= 0) {
-            const long long v = (long long)M.v0 + my_var;
-            d += is_alt ? ldg_or_zero(A.d_alt_means, v * E + e) / (M.alt_total[my_var] + 1e-4f)
-                        : ldg_or_zero(A.d_ref_means, v * E + e) / (M.ref_total[my_var] + 1e-4f);
-          } else {
-            d = 0.f;
-          }
-          Fb[e * LD + row] = d;
-          Yb[e * LD + row] += __ldg(W + D.translation + e);   // y + t, the rotation's input
-        }
-      }
-      __syncthreads();
-      // rotation (euclidean_transformation.py:19-20): f = Q (y + t)
-      wgrad_tile(smem_addr(Fb), E, smem_addr(Yb), E, part + D.rotation, 0, rows_used);
-      {
-        const int e_lo = part_lo(E, rp), e_hi = part_lo(E, rp + 1);
-        for (int j = e_lo; j < e_hi; ++j) {
-          float a = 0.f;
-          for (int i = 0; i < E; ++i) a = fmaf(__ldg(W + D.rotation + i * E + j), Fb[i * LD + row], a);
-          Xtra[j * LD + row] = a;
-        }
-      }
-      __syncthreads();
-      rowdot_tile(Xtra, nullptr, E, part + D.translation, 0, rows_used);
-      PMT_BWD_TRACE(21);
-
-      // ======================= reducer (artifact_model.py:258-259) =======================
-      float* G = mlp_backward(P, D.red_ops, D.n_red_ops, P.red_g0, scr, P.scr_red, Xtra, bufs, stage, W, part,
-                              rows_used, true);
-      PMT_BWD_TRACE(22);
-
-      // ======================= gated blocks in reverse (gated_mlp.py:177-251) =======================
-      float* Ab = nullptr; float* Bn = nullptr; float* Cz = nullptr;
+      // ======================= backward =======================
+      float* G = bwd_tail(T, scr);
+      float* others[3];
       {
         int q = 0;
-        float* others[3];
-        for (int i = 0; i < 4; ++i) if (bufs[i] != G) others[q++] = bufs[i];
-        Ab = others[0]; Bn = others[1]; Cz = others[2];
+        for (int i = 0; i < 4; ++i) if (S.bufs[i] != G) others[q++] = S.bufs[i];
       }
       for (int blk = D.n_blocks - 1; blk >= 0; --blk) {
-        const PmtBlockOffsets& BO = D.blocks[blk];
-        const int g1 = P.blk_g0 + 2 * blk, g2 = g1 + 1;
-        const float alpha = __ldg(W + (is_alt ? BO.alpha_alt : BO.alpha_ref));
-        const float beta = __ldg(W + (is_alt ? BO.beta_alt : BO.beta_ref));
-        const float gamma = __ldg(W + BO.gamma);
-        const int f_lo = part_lo(H, rp), f_hi = part_lo(H, rp + 1);
-        const int d_lo = part_lo(Dm, rp), d_hi = part_lo(Dm, rp + 1);
-        load_rows(Ab, Dm, scr + P.scr_x[blk]);
-        load_rows(Cz, 2 * H, scr + P.scr_z[blk]);
-        stage.prefetch(MAX_GEMM + g2);
-        __syncthreads();
-        float mean, rstd, mean2, rstd2;
-        row_stats(Ab, Dm, row, mean, rstd);
-        row_stats(Cz + H * LD, H, row, mean2, rstd2);
-        __syncthreads();
-        for (int f = d_lo; f < d_hi; ++f) {
-          const float xh = (Ab[f * LD + row] - mean) * rstd;
-          Ab[f * LD + row] = xh;
-          Bn[f * LD + row] = xh * __ldg(W + BO.ln_w + f) + __ldg(W + BO.ln_b + f);
-        }
-        for (int f = f_lo; f < f_hi; ++f) {
-          const float xh2 = (Cz[(H + f) * LD + row] - mean2) * rstd2;
-          Cz[(2 * H + f) * LD + row] = xh2;
-          Cz[(3 * H + f) * LD + row] = xh2 * __ldg(W + BO.ln2_w + f) + __ldg(W + BO.ln2_b + f);   // z2n
-        }
-        __syncthreads();
-        segment_sums(M, Cz, 3 * H, H, C.sums, P.sum_w, false, false);
-        __syncthreads();
-        block_means(P, C, blk);
-        for (int f = f_lo; f < f_hi; ++f) {
-          const float gate = gate_value(P, C, BO, row, f, Cz[(3 * H + f) * LD + row], my_var, is_alt, alpha, beta, gamma);
-          Cz[(3 * H + f) * LD + row] = gate;
-          Cz[(4 * H + f) * LD + row] = Cz[f * LD + row] * gate;   // u = z1 * gate
-        }
-        PMT_BWD_TRACE(100 + blk * 10 + 0);
-        // proj2: x_out = x + W2_s u + b2_s
-        const float* imgT2 = stage.acquire(MAX_GEMM + g2);
-        stage.prefetch(MAX_GEMM + g1);
-        wgrad_tile(smem_addr(G), Dm, smem_addr(Cz + 4 * H * LD), H, part + BO.p2_ref_w, 0, ref_pad);
-        wgrad_tile(smem_addr(G), Dm, smem_addr(Cz + 4 * H * LD), H, part + BO.p2_alt_w, ref_pad, rows_used);
-        rowdot_tile(G, nullptr, Dm, part + BO.p2_ref_b, 0, ref_pad);
-        rowdot_tile(G, nullptr, Dm, part + BO.p2_alt_b, ref_pad, rows_used);
-        gemm_tile_T(G, P.gemm[g2], imgT2, ref_pad, Cz + 5 * H * LD, EPI_STORE, 1.f, nullptr, rows_used);   // du
-        __syncthreads();
-        PMT_BWD_TRACE(100 + blk * 10 + 1);
-        {  // d z1 = du * gate ; d gate = du * z1 ; scalar gradients of the gate
-          float s_alpha = 0.f, s_beta = 0.f, s_gamma = 0.f;
-          for (int f = f_lo; f < f_hi; ++f) {
-            const float du = Cz[(5 * H + f) * LD + row], gate = Cz[(3 * H + f) * LD + row], z1 = Cz[f * LD + row];
-            const float dgate = du * z1;
-            Cz[(4 * H + f) * LD + row] = du * gate;
-            Cz[(5 * H + f) * LD + row] = dgate;
-            if (my_var >= 0) {
-              const float z2n = Cz[(2 * H + f) * LD + row] * __ldg(W + BO.ln2_w + f) + __ldg(W + BO.ln2_b + f);
-              const float m_ref = C.sums[(my_var * 2 + 0) * P.sum_w + f];
-              s_alpha = fmaf(dgate, z2n, s_alpha);
-              s_beta = fmaf(dgate, is_alt ? C.sums[(my_var * 2 + 1) * P.sum_w + f] : m_ref, s_beta);
-              if (is_alt) s_gamma = fmaf(dgate, m_ref, s_gamma);
-            }
-          }
-          acc.add(0, is_alt ? 0.f : s_alpha); acc.add(1, is_alt ? s_alpha : 0.f);
-          acc.add(2, is_alt ? 0.f : s_beta);  acc.add(3, is_alt ? s_beta : 0.f);
-          acc.add(4, s_gamma);
-        }
-        __syncthreads();
-        if (tid < 5) {
-          const int offs[5] = {BO.alpha_ref, BO.alpha_alt, BO.beta_ref, BO.beta_alt, BO.gamma};
-          float s = 0.f;
-          for (int w = 0; w < NWARPS; ++w) s += wpart[w * acc_cap + tid];
-          red_add(part + offs[tid], s);
-        }
-        segment_sums(M, Cz, 5 * H, H, dsums, P.sum_w, false, false);
-        __syncthreads();
-        {  // gradients of the mean fields (ragged_sets.py:144-155 backward)
-          const float regw = __ldg(W + BO.reg_weight) + 0.25f;
-          const float b_ref = __ldg(W + BO.beta_ref), b_alt = __ldg(W + BO.beta_alt);
-          for (int idx = tid; idx < M.nv * H; idx += NTHREADS) {
-            const int j = idx / H, f = idx % H;
-            const float s_ref = dsums[(j * 2 + 0) * P.sum_w + f], s_alt = dsums[(j * 2 + 1) * P.sum_w + f];
-            dsums[(j * 2 + 0) * P.sum_w + f] = b_ref * s_ref + gamma * s_alt;   // d m_ref
-            dsums[(j * 2 + 1) * P.sum_w + f] = b_alt * s_alt;                   // d m_alt
-          }
-          __syncthreads();
-          if (tid < H) {
-            float d_reg = 0.f, d_w = 0.f;
-            const float reg = __ldg(W + BO.regularizer + tid);
-            for (int j = 0; j < M.nv; ++j) {
-              const float dm = dsums[(j * 2 + 0) * P.sum_w + tid], den = M.ref_total[j] + regw;
-              d_reg += dm * regw / den;
-              d_w += dm * (reg - C.sums[(j * 2 + 0) * P.sum_w + tid]) / den;
-            }
-            red_add(part + BO.regularizer + tid, d_reg);
-            small[tid] = d_w;
-          }
-          __syncthreads();
-          if (tid == 0) {
-            float s = 0.f;
-            for (int f = 0; f < H; ++f) s += small[f];
-            red_add(part + BO.reg_weight, s);
-          }
-          for (int idx = tid; idx < M.nv * H; idx += NTHREADS) {
-            const int j = idx / H, f = idx % H;
-            dsums[(j * 2 + 0) * P.sum_w + f] /= (M.ref_total[j] + regw);
-            dsums[(j * 2 + 1) * P.sum_w + f] /= (M.alt_total[j] + 1e-4f);
-          }
-        }
-        __syncthreads();
-        for (int f = f_lo; f < f_hi; ++f) {   // d z2n
-          float d = alpha * Cz[(5 * H + f) * LD + row];
-          if (my_var >= 0) d += dsums[(my_var * 2 + (is_alt ? 1 : 0)) * P.sum_w + f];
-          Cz[(3 * H + f) * LD + row] = d;
-        }
-        __syncthreads();
-        rowdot_tile(Cz + 3 * H * LD, Cz + 2 * H * LD, H, part + BO.ln2_w, 0, rows_used);
-        rowdot_tile(Cz + 3 * H * LD, nullptr, H, part + BO.ln2_b, 0, rows_used);
-        {  // SGU LayerNorm backward -> d z2 (pre-norm), placed after d z1 so that [4H, 6H) = d z
-          float m1 = 0.f, m2 = 0.f;
-          for (int f = 0; f < H; ++f) {
-            const float dxh = Cz[(3 * H + f) * LD + row] * __ldg(W + BO.ln2_w + f);
-            m1 += dxh; m2 = fmaf(dxh, Cz[(2 * H + f) * LD + row], m2);
-          }
-          m1 /= H; m2 /= H;
-          for (int f = f_lo; f < f_hi; ++f) {
-            const float dxh = Cz[(3 * H + f) * LD + row] * __ldg(W + BO.ln2_w + f);
-            Cz[(5 * H + f) * LD + row] = rstd2 * (dxh - m1 - Cz[(2 * H + f) * LD + row] * m2);
-          }
-        }
-        __syncthreads();
-        PMT_BWD_TRACE(100 + blk * 10 + 2);
-        mul_dselu(Cz + 4 * H * LD, Cz, 2 * H);   // through z = SELU(proj1 n)
-        // proj1: z_pre = W1_s n + b1_s
-        const float* imgT1 = stage.acquire(MAX_GEMM + g1);
-        if (blk > 0) stage.prefetch(MAX_GEMM + g1 - 1);
-        wgrad_tile(smem_addr(Cz + 4 * H * LD), 2 * H, smem_addr(Bn), Dm, part + BO.p1_ref_w, 0, ref_pad);
-        wgrad_tile(smem_addr(Cz + 4 * H * LD), 2 * H, smem_addr(Bn), Dm, part + BO.p1_alt_w, ref_pad, rows_used);
-        rowdot_tile(Cz + 4 * H * LD, nullptr, 2 * H, part + BO.p1_ref_b, 0, ref_pad);
-        rowdot_tile(Cz + 4 * H * LD, nullptr, 2 * H, part + BO.p1_alt_b, ref_pad, rows_used);
-        __syncthreads();
-        gemm_tile_T(Cz + 4 * H * LD, P.gemm[g1], imgT1, ref_pad, Bn, EPI_STORE, 1.f, nullptr, rows_used);   // d n
-        __syncthreads();
-        PMT_BWD_TRACE(100 + blk * 10 + 3);
-        rowdot_tile(Bn, Ab, Dm, part + BO.ln_w, 0, rows_used);
-        rowdot_tile(Bn, nullptr, Dm, part + BO.ln_b, 0, rows_used);
-        {  // LayerNorm backward, added to the residual gradient
-          float m1 = 0.f, m2 = 0.f;
-          for (int f = 0; f < Dm; ++f) {
-            const float dxh = Bn[f * LD + row] * __ldg(W + BO.ln_w + f);
-            m1 += dxh; m2 = fmaf(dxh, Ab[f * LD + row], m2);
-          }
-          m1 /= Dm; m2 /= Dm;
-          for (int f = d_lo; f < d_hi; ++f) {
-            const float dxh = Bn[f * LD + row] * __ldg(W + BO.ln_w + f);
-            G[f * LD + row] += rstd * (dxh - m1 - Ab[f * LD + row] * m2);
-          }
-        }
-        __syncthreads();
-        PMT_BWD_TRACE(100 + blk * 10 + 4);
+        const RowNorm n = bwd_block_gate(T, blk, scr, nullptr, G, others[0], others[1], others[2], false);
+        bwd_block_meanfield(T, blk);
+        bwd_block_finish(T, blk, G, others[0], others[1], others[2], n);
       }
-
-      // ======================= concat (artifact_model.py:246-251): d info_seq of each variant =======================
-      {
-        const int w = D.d_info + D.d_seq;
-        for (int idx = tid; idx < M.nv * w; idx += NTHREADS) {
-          const int j = idx / w, f = idx % w;
-          const float* p = G + (D.d_read + f) * LD;
-          float s = 0.f;
-          for (int i = 0; i < M.ref_cnt[j]; ++i) s += p[M.ref_start[j] + i];
-          for (int i = 0; i < M.alt_cnt[j]; ++i) s += p[M.alt_start[j] + i];
-          A.d_info_seq[((long long)M.v0 + j) * w + f] = s;
-        }
-      }
-      PMT_BWD_TRACE(23);
-      // ======================= read embedding (artifact_model.py:243) =======================
-      mlp_backward(P, D.read_ops, D.n_read_ops, P.read_g0, scr, P.scr_read, G, bufs, stage, W, part, rows_used, false);
-      __syncthreads();
-      PMT_BWD_TRACE(24);
+      bwd_embed(T, scr, G, false);
     }
+  }
+}
+
+// Sets longer than a tile (synthetic high-depth data, BASELINE config 5; real data is capped at 10 + 15 reads at ingest).
+// One CTA walks a variant in chunks of TILE rows, every chunk with its own recompute scratch (plus the running dL/dx
+// and the gate state of the block being differentiated); the mean fields and their gradients are accumulated over
+// the chunks between the two halves of each block's backward, exactly where reads_forward_long_kernel accumulates them.
+__global__ void __launch_bounds__(NTHREADS, 1)
+reads_backward_long_kernel(const __grid_constant__ Plan P, const __grid_constant__ BwdArgs A) {
+  extern __shared__ __align__(16) float smem[];
+  const PmtModelDesc& D = P.d;
+  TileCtx C;
+  BwdSmem S;
+  carve_bwd_smem(P, smem, C, S);
+  TileMeta& M = *C.M;
+  C.W = A.wflat;
+  BlockAccum acc;
+  acc.init(S.wpart, S.acc_cap);
+  const int tid = threadIdx.x;
+  const int B = A.batch.n_variants, Dm = D.d_model, H = D.d_ffn / 2;
+  Stage stage;
+  stage.init(S.st0, S.st1, A.image, &P);
+  if (tid == 0) head_constants(D, C.W, C.HC);
+  for (int i = tid; i < 4 * P.bwd_rows * LD; i += NTHREADS) smem[i] = 0.f;
+  __syncthreads();
+  const long long total_ref = __ldg(A.batch.ref_off + B);
+  float* scr0 = A.long_scratch + (long long)blockIdx.x * A.long_scratch_stride;
+  BwdTile T{P, A, C, stage, acc, S.bufs, S.dsums, S.wpart, S.small, A.partials + (long long)blockIdx.x * D.n_params, S.acc_cap, false};
+  // per-chunk scratch: the recompute images of the tile kernel, then dL/dx [Dm] and the gate state [6H]
+  const long long g_off = P.scratch_floats, cz_off = g_off + (long long)Dm * LD, chunk_stride = cz_off + 6LL * H * LD;
+  float* const G = S.bufs[0];
+  float* const Ab = S.bufs[1];
+  float* const Bn = S.bufs[2];
+  float* const Cz = S.bufs[3];
+  const int sw2 = 2 * P.sum_w;
+
+  for (int v = blockIdx.x; v < B; v += gridDim.x) {   // static assignment: fixed summation order
+    const long long nref = __ldg(A.batch.ref_off + v + 1) - __ldg(A.batch.ref_off + v);
+    const long long nalt = __ldg(A.batch.alt_off + v + 1) - __ldg(A.batch.alt_off + v);
+    const long long total = ((nref + 3) & ~3LL) + nalt;
+    if (total <= TILE) continue;
+    const int n_chunks = (int)((total + TILE - 1) / TILE);
+#define PMT_CHUNK(c)                                   \
+    build_chunk(A.batch, v, (c), total_ref, M);        \
+    C.rows_used = (M.rows + 3) & ~3;                   \
+    float* scr = scr0 + (long long)(c) * chunk_stride;
+
+    // ======================= forward recompute =======================
+    for (int c = 0; c < n_chunks; ++c) {
+      PMT_CHUNK(c)
+      tile_embed(P, C, stage, A.batch, A.info_seq, scr);
+      save_rows(C.X, Dm, scr + P.scr_x[0]);
+      __syncthreads();
+    }
+    for (int blk = 0; blk < D.n_blocks; ++blk) {
+      for (int c = 0; c < n_chunks; ++c) {
+        PMT_CHUNK(c)
+        load_rows(C.X, Dm, scr + P.scr_x[blk]);
+        __syncthreads();
+        block_phase_a(P, C, stage, blk, scr + P.scr_z[blk]);
+        segment_sums(M, C.T2, H, H, C.sums, P.sum_w, false, c > 0);
+        __syncthreads();
+      }
+      block_means(P, C, blk);
+      for (int i = tid; i < sw2; i += NTHREADS) C.sums[(1 + blk) * sw2 + i] = C.sums[i];   // kept for the backward
+      __syncthreads();
+      for (int c = 0; c < n_chunks; ++c) {
+        PMT_CHUNK(c)
+        load_rows(C.X, Dm, scr + P.scr_x[blk]);
+        load_rows(C.T2, 2 * H, scr + P.scr_z[blk]);
+        __syncthreads();
+        sgu_layernorm(P, C, blk);
+        block_phase_b(P, C, stage, blk, -1);
+        save_rows(C.X, Dm, blk + 1 < D.n_blocks ? scr + P.scr_x[blk + 1] : scr + P.scr_red[0]);
+        __syncthreads();
+      }
+    }
+    // ======================= backward =======================
+    for (int c = 0; c < n_chunks; ++c) {
+      PMT_CHUNK(c)
+      load_rows(C.X, Dm, scr + P.scr_red[0]);
+      __syncthreads();
+      float* g = bwd_tail(T, scr);
+      save_rows(g, Dm, scr + g_off);
+      __syncthreads();
+    }
+    for (int blk = D.n_blocks - 1; blk >= 0; --blk) {
+      for (int c = 0; c < n_chunks; ++c) {
+        PMT_CHUNK(c)
+        load_rows(G, Dm, scr + g_off);
+        bwd_block_gate(T, blk, scr, C.sums + (1 + blk) * sw2, G, Ab, Bn, Cz, c > 0);
+        save_rows(Cz, 6 * H, scr + cz_off);
+        __syncthreads();
+      }
+      bwd_block_meanfield(T, blk);
+      for (int c = 0; c < n_chunks; ++c) {
+        PMT_CHUNK(c)
+        load_rows(G, Dm, scr + g_off);
+        const RowNorm n = bwd_block_reload(T, blk, scr, scr + cz_off, Ab, Bn, Cz, MAX_GEMM + P.blk_g0 + 2 * blk);
+        bwd_block_finish(T, blk, G, Ab, Bn, Cz, n);
+        save_rows(G, Dm, scr + g_off);
+        __syncthreads();
+      }
+    }
+    for (int c = 0; c < n_chunks; ++c) {
+      PMT_CHUNK(c)
+      load_rows(G, Dm, scr + g_off);
+      __syncthreads();
+      bwd_embed(T, scr, G, c > 0);
+    }
+#undef PMT_CHUNK
   }
 }
 
@@ -932,7 +1169,7 @@ static size_t bwd_smem_bytes(const Plan& P) {
   const int n_head = P.d.d_feat + P.d.n_clusters * P.d.d_feat + 5 * P.d.n_clusters;
   const int acc_cap = n_head > 8 ? n_head : 8;
   return (size_t)(4 * P.bwd_rows * LD + 2 * P.stage_floats + 2 * TILE * 2 * P.sum_w + TILE * 2 * 16 + NWARPS * acc_cap +
-                  2 * TILE + 64) * sizeof(float) + sizeof(HeadConst) + sizeof(TileMeta) + 64;
+                  64) * sizeof(float) + sizeof(HeadConst) + sizeof(TileMeta) + 64;
 }
 static int info_rows(const Plan& P) {
   int r = P.d.n_info_features;
@@ -940,6 +1177,23 @@ static int info_rows(const Plan& P) {
   return r;
 }
 static const int kBwdGrid = 148;
+
+// Long-set kernel: every chunk of the longest set has its own recompute scratch + dL/dx + gate state (see the kernel).
+// The grid shrinks when the scratch of a full grid would pass kLongScratchBudget.
+static const size_t kLongScratchBudget = (size_t)16 << 30;
+static size_t long_bwd_floats_per_cta(const Plan& P, const PmtBatch* batch) {
+  if (!batch || !pmt_has_long_sets(batch)) return 0;
+  const size_t chunks = (size_t)((batch->max_rows_per_variant + 3 + TILE - 1) / TILE);
+  return chunks * ((size_t)P.scratch_floats + (size_t)(P.d.d_model + 3 * P.d.d_ffn) * LD);
+}
+static int long_bwd_grid(const Plan& P, const PmtBatch* batch) {
+  const size_t per_cta = long_bwd_floats_per_cta(P, batch) * sizeof(float);
+  if (per_cta == 0) return 0;
+  size_t grid = kLongScratchBudget / per_cta;
+  if (grid > (size_t)kBwdGrid) grid = kBwdGrid;
+  if (grid > (size_t)batch->n_variants) grid = batch->n_variants;
+  return grid < 1 ? 1 : (int)grid;
+}
 static long long* g_bwd_trace = nullptr;
 extern "C" int pmt_set_backward_trace(long long* device_buffer) { g_bwd_trace = device_buffer; return 0; }
 
@@ -949,6 +1203,7 @@ size_t pmt_backward_workspace_bytes(const Plan& P, const PmtBatch* batch) {
   const size_t scr = P.scratch_floats > P.info_scratch_floats ? P.scratch_floats : P.info_scratch_floats;
   bytes += (size_t)kBwdGrid * scr * sizeof(float);                                           // activation scratch
   if (batch) bytes += 2 * (size_t)batch->n_variants * (P.d.d_info + P.d.d_seq) * sizeof(float);   // info_seq, d_info_seq
+  bytes += (size_t)long_bwd_grid(P, batch) * long_bwd_floats_per_cta(P, batch) * sizeof(float) + 256;
   return bytes;
 }
 
@@ -961,9 +1216,6 @@ extern "C" int pmt_backward(const PmtModelDesc* desc, const float* weights, cons
   const size_t need = pmt_workspace_size(desc, batch, 1);
   PMT_CHECK(workspace && workspace_bytes >= need, "workspace too small: %zu < %zu", workspace_bytes, need);
   PMT_CHECK(batch->n_variants > 0, "empty batch");
-  PMT_CHECK(batch->max_rows_per_variant <= TILE,
-            "pmt_backward: a variant has %lld reads; training on sets longer than %d reads is not supported yet "
-            "(the reference caps reads at 10 ref + 15 alt at ingest)", (long long)batch->max_rows_per_variant, TILE);
   PMT_CHECK(NPART * desc->d_feat <= P.bwd_rows, "d_feat %d too wide for the backward kernel's head scratch", desc->d_feat);
   const size_t smem = bwd_smem_bytes(P);
   PMT_CHECK(smem <= 227 * 1024, "model too wide for the backward kernel's shared-memory plan (%zu bytes)", smem);
@@ -977,6 +1229,10 @@ extern "C" int pmt_backward(const PmtModelDesc* desc, const float* weights, cons
   float* scratch = reinterpret_cast<float*>(ws + off); off += (size_t)kBwdGrid * scr_floats * sizeof(float);
   float* info_seq = reinterpret_cast<float*>(ws + off); off += (size_t)B * w * sizeof(float);
   float* d_info_seq = reinterpret_cast<float*>(ws + off); off += (size_t)B * w * sizeof(float);
+  off = (off + 255) & ~(size_t)255;
+  const int lgrid = long_bwd_grid(P, batch);
+  const size_t long_floats = long_bwd_floats_per_cta(P, batch);
+  float* long_scratch = reinterpret_cast<float*>(ws + off); off += (size_t)lgrid * long_floats * sizeof(float);
   PMT_CHECK(off <= workspace_bytes, "workspace layout overflow");
 
   cudaMemsetAsync(partials, 0, (size_t)kBwdGrid * desc->n_params * sizeof(float), st);
@@ -1003,6 +1259,7 @@ extern "C" int pmt_backward(const PmtModelDesc* desc, const float* weights, cons
   A.d_alt_means = grads ? grads->d_alt_means_be : nullptr;
   A.d_ref_means = grads ? grads->d_ref_means_be : nullptr;
   A.d_info_seq = d_info_seq; A.scratch = scratch; A.scratch_stride = (long long)scr_floats; A.partials = partials;
+  A.long_scratch = long_scratch; A.long_scratch_stride = (long long)long_floats;
   A.n_claims = (B + claim - 1) / claim;
   A.trace = g_bwd_trace;
   int grid = A.n_claims < kBwdGrid ? A.n_claims : kBwdGrid;
@@ -1011,6 +1268,10 @@ extern "C" int pmt_backward(const PmtModelDesc* desc, const float* weights, cons
   pmt_profile_begin(st);
   reads_backward_kernel<<<grid, NTHREADS, smem, st>>>(P, A);
   pmt_profile_end(st);
+  if (lgrid > 0) {   // sets longer than a tile; same CTA-private gradient buffers, after the tile kernel: fixed order
+    cudaFuncSetAttribute(reads_backward_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    reads_backward_long_kernel<<<lgrid, NTHREADS, smem, st>>>(P, A);
+  }
   {
     const int rows = info_rows(P);
     const size_t ismem = (size_t)(4 * rows * LD + 2 * P.info_stage_floats) * sizeof(float);

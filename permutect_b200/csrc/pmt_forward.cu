@@ -558,7 +558,7 @@ static size_t reads_kernel_smem(const Plan& P) { return tile_ctx_bytes(P, P.stag
 // long-set scratch: per CTA, one (x, z) image pair per chunk of the longest variant
 static int long_grid(const PmtBatch* batch, int n_sm) { return batch->n_variants < n_sm ? batch->n_variants : n_sm; }
 static size_t long_scratch_floats_per_cta(const Plan& P, const PmtBatch* batch) {
-  if (!batch || batch->max_rows_per_variant <= TILE) return 0;
+  if (!batch || !pmt_has_long_sets(batch)) return 0;
   const size_t chunks = (size_t)((batch->max_rows_per_variant + 3 + TILE - 1) / TILE) + 1;
   return chunks * (size_t)(P.d.d_model + P.d.d_ffn) * LD;
 }
@@ -654,7 +654,7 @@ static int forward_impl(const PmtModelDesc* desc, const float* weights, const Pm
     reads_forward_kernel<<<grid, NTHREADS, smem, st>>>(P, A);
     pmt_profile_end(st);
   }
-  if (batch->max_rows_per_variant > TILE) {
+  if (pmt_has_long_sets(batch)) {
     A.scratch = reinterpret_cast<float*>(ws + L.long_scratch);
     A.scratch_stride = (long long)long_scratch_floats_per_cta(P, batch);
     const int lgrid = long_grid(batch, n_sm < 148 ? n_sm : 148);

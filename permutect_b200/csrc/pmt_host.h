@@ -14,6 +14,10 @@ void pmt_set_error(const char* fmt, ...);
     }                            \
   } while (0)
 
+// A set occupies pad4(ref rows) + alt rows of a tile, so a set of up to TILE - 3 rows always fits in one tile; anything
+// longer MAY be left to the long-set kernels by build_tile / plan_tiles_kernel (which then do nothing if it did fit).
+inline bool pmt_has_long_sets(const PmtBatch* batch) { return batch->max_rows_per_variant + 3 > PMT_TILE_ROWS; }
+
 int pmt_build_plan(const PmtModelDesc* d, pmt::Plan* out);
 int pmt_cnn_geometry(const pmt::Plan& P, pmt::CnnGeom* out);
 size_t pmt_image_bytes(const pmt::Plan& P, const pmt::CnnGeom& G);

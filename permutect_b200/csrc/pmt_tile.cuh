@@ -21,7 +21,7 @@ struct TileMeta {
   int v0;             // first variant (global index)
   int ref_pad;        // rows [0, ref_pad) are ref rows (incl. padding), rows [ref_pad, rows) alt rows
   int rows;
-  int pad_;
+  int alt_head;       // 1 if the first alt row of the tile's variants is inside this tile (0 for later chunks of a long set)
   int rowvar[TILE];         // local variant of each row, -1 for padding
   long long rowidx[TILE];   // batch row index (position in [0, n_rows)), -1 for padding
   int ref_start[TILE], ref_cnt[TILE], alt_start[TILE], alt_cnt[TILE];  // per local variant: rows inside THIS tile
@@ -141,7 +141,7 @@ __device__ __forceinline__ int build_tile(const PmtBatch& batch, int v_cur, int 
     for (int i = 0; i < rc; ++i) { M.rowvar[rs + i] = tid; M.rowidx[rs + i] = r0 + i; }
     for (int i = 0; i < ac; ++i) { M.rowvar[as + i] = tid; M.rowidx[as + i] = total_ref + a0 + i; }
   }
-  if (tid == 0) { M.nv = nv; M.v0 = v_cur; M.ref_pad = ref_pad; M.rows = ref_pad + (int)na_tot; }
+  if (tid == 0) { M.nv = nv; M.v0 = v_cur; M.ref_pad = ref_pad; M.rows = ref_pad + (int)na_tot; M.alt_head = 1; }
   __syncthreads();
   return nv;
 }
@@ -167,6 +167,7 @@ __device__ __forceinline__ void build_chunk(const PmtBatch& batch, int v, int c,
     const long long ref_lo = lo < nref ? lo : nref, ref_hi = hi < nref ? hi : nref;
     const long long alt_lo = (lo > ref_pad ? lo : ref_pad), alt_hi = (hi < total ? hi : total);
     M.nv = 1; M.v0 = v;
+    M.alt_head = (ref_pad >= lo && ref_pad < hi) ? 1 : 0;
     M.ref_pad = (int)(ref_pad <= lo ? 0 : (ref_pad >= hi ? TILE : ref_pad - lo));
     M.rows = (int)((hi < total ? hi : total) - lo);
     M.ref_start[0] = (int)(ref_lo - lo); M.ref_cnt[0] = (int)(ref_hi - ref_lo);
@@ -241,6 +242,21 @@ __device__ __forceinline__ void row_stats(const float* buf, int nf, int row, flo
   rstd = rsqrtf(var / nf + LN_EPS);
 }
 
+// gated_mlp.py:230-233: LayerNorm of the gating half z2 = T2[H..2H), in place.  Ends with a __syncthreads().
+__device__ __forceinline__ void sgu_layernorm(const Plan& P, TileCtx& C, int blk) {
+  const PmtBlockOffsets& BO = P.d.blocks[blk];
+  const int row = threadIdx.x & (TILE - 1), part = threadIdx.x / TILE;
+  const int H = P.d.d_ffn / 2;
+  const float* W = C.W;
+  float mean, rstd;
+  row_stats(C.T2 + H * LD, H, row, mean, rstd);
+  __syncthreads();  // every part (and a preceding save) has read the raw z2 of this row
+  const int f_lo = part_lo(H, part), f_hi = part_lo(H, part + 1);
+  for (int f = f_lo; f < f_hi; ++f)
+    C.T2[(H + f) * LD + row] = (C.T2[(H + f) * LD + row] - mean) * rstd * __ldg(W + BO.ln2_w + f) + __ldg(W + BO.ln2_b + f);
+  __syncthreads();
+}
+
 // gated_mlp.py:185-190, 230-233: T1 = LN(X); T2[0..d_ffn) = SELU(proj1_s T1); T2[H..2H) <- LN2 in place.
 // `z_save` (optional): global image receiving z = T2[0..d_ffn) BEFORE the SGU LayerNorm.
 __device__ __forceinline__ void block_phase_a(const Plan& P, TileCtx& C, Stage& stage, int blk, float* z_save) {
@@ -262,15 +278,7 @@ __device__ __forceinline__ void block_phase_a(const Plan& P, TileCtx& C, Stage& 
   gemm_tile(C.T1, P.gemm[g1], img1, W, C.M->ref_pad, C.T2, EPI_SELU, 1.f, C.rows_used);
   __syncthreads();
   if (z_save) save_rows(C.T2, D.d_ffn, z_save);
-  {
-    float mean, rstd;
-    row_stats(C.T2 + H * LD, H, row, mean, rstd);
-    __syncthreads();  // both halves (and the save) have read the raw z2 of this row
-    const int f_lo = part_lo(H, part), f_hi = part_lo(H, part + 1);
-    for (int f = f_lo; f < f_hi; ++f)
-      C.T2[(H + f) * LD + row] = (C.T2[(H + f) * LD + row] - mean) * rstd * __ldg(W + BO.ln2_w + f) + __ldg(W + BO.ln2_b + f);
-  }
-  __syncthreads();
+  sgu_layernorm(P, C, blk);
 }
 
 // gated_mlp.py:236-239, ragged_sets.py:144-155: turn per-variant sums of z2 into the ref / alt mean fields, in place
