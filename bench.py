@@ -235,6 +235,58 @@ def run_training(args, model, ia, fa, reads, dev, world, barrier):
                     "flat grad all-reduce + clip(1.0) + AdamW (FlatAdamW)"}
 
 
+def run_panel(args, model, dev, world, rank, barrier):
+    """BASELINE config 5 (high-depth panel stress, sets of ~2 000 reads): a bounded sample of it per GPU, inference and
+    training, through the long-set kernels.  Reported beside the headline, not as it."""
+    import torch.distributed as dist
+    from permutect_b200.data.batch import Batch, DownsampledBatch
+    from permutect_b200.synthetic import make_panel_arrays
+    from permutect_b200.training.step import make_optimizer, train_step
+    from permutect_b200.utils.enums import Epoch
+
+    n = args.panel_variants
+    ia, fa, reads = make_panel_arrays(n, seed=1000 * 5 + rank)
+    parent = Batch.from_arrays(ia, fa, reads).copy_to(dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, warm, steps):
+        for i in range(warm):
+            fn(i)
+        barrier()
+        ev0.record()
+        for i in range(steps):
+            fn(warm + i)
+        ev1.record()
+        barrier()
+        t = torch.tensor([ev0.elapsed_time(ev1) / steps], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    model.set_epoch_type(Epoch.VALID)
+    with torch.inference_mode():
+        infer_ms = timed(lambda i: model.compute_batch_output(parent), 2, 3)
+    model.set_epoch_type(Epoch.TRAIN)
+    opt = make_optimizer(model, learning_rate=1e-3, weight_decay=0.01)
+    frac = torch.full((n,), 0.8, device=dev)
+    kept = []
+
+    def step(i):
+        batch = DownsampledBatch(parent, frac, frac, seed=500 + i)
+        train_step(model, batch, opt)
+        if not kept:
+            kept.append(int(sum(int(c.sum()) for c in batch.counts())))
+
+    train_ms = timed(step, 1, 2)
+    model.set_epoch_type(Epoch.VALID)
+    return {"workload": "high-depth panel stress (SURVEY \u00a78d config 5), bounded sample", "variants_per_gpu": n,
+            "reads_per_gpu": len(reads), "mean_reads_per_variant": len(reads) / n,
+            "inference_variants_per_s": n * world / (infer_ms / 1e3), "inference_reads_per_s": len(reads) * world / (infer_ms / 1e3),
+            "inference_ms": infer_ms, "train_variants_per_s": n * world / (train_ms / 1e3),
+            "train_reads_per_s": kept[0] * world / (train_ms / 1e3), "train_ms": train_ms, "train_reads_per_step": kept[0],
+            "kernels": "reads_forward_long_kernel / reads_backward_long_kernel (FP32 SIMT, sets walked in chunks of 128 reads)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -250,6 +302,8 @@ def main():
                          "logits within 1e-3 of the reference), fp32 = FP32 SIMT, tf32 = plain TF32 (looser, stated tolerance); "
                          "the backward always runs FP32")
     ap.add_argument("--e2e-batches", type=int, default=8, help="host batches the shard is delivered in for the e2e leg")
+    ap.add_argument("--panel-variants", type=int, default=1024,
+                    help="variants per GPU of the high-depth panel sample (config 5, ~2 050 reads each); 0 skips it")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -369,6 +423,10 @@ def main():
     if not args.no_train:
         train = run_training(args, model, ia, fa, reads, dev, world, barrier)
 
+    panel = None
+    if args.panel_variants > 0 and not args.no_train:
+        panel = run_panel(args, model, dev, world, rank, barrier)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -417,6 +475,8 @@ def main():
     if train is not None:
         result["train"] = train
         result["gpu_launches"] = 9 * args.steps + train["gpu_launches"]
+    if panel is not None:
+        result["panel"] = panel
     if not args.no_cpu_baseline:
         sample = 8192
         v, n_it = time_oracle(model.state_dict(), sample, seed=3000, budget_s=15.0)
