@@ -834,6 +834,22 @@ struct CnnBwdGeom {
   int act_total, gbuf_floats, stage_floats;
 };
 
+// Walks idx = tid, tid + NTHREADS, ... of a [C][V][L] index space keeping (c, v, p) without per-element integer
+// divisions (they were a quarter of this kernel's instructions).
+struct Idx3 {
+  int c, v, p, sc, sv, sp, V, L;
+  __device__ __forceinline__ Idx3(int V_, int L_) : V(V_), L(L_) {
+    const int t = threadIdx.x;
+    p = t % L_; v = (t / L_) % V_; c = t / (V_ * L_);
+    sp = NTHREADS % L_; sv = (NTHREADS / L_) % V_; sc = NTHREADS / (V_ * L_);
+  }
+  __device__ __forceinline__ void next() {
+    p += sp; v += sv; c += sc;
+    if (p >= L) { p -= L; v += 1; }
+    if (v >= V) { v -= V; c += 1; }
+  }
+};
+
 __device__ __forceinline__ float act_grad_from_out(float y, int act) {
   if (act == PMT_ACT_SELU) return selu_grad_from_out(y);
   if (act == PMT_ACT_LEAKY_RELU) return y > 0.f ? 1.f : 0.01f;
@@ -946,8 +962,9 @@ hap_cnn_backward_kernel(const __grid_constant__ Plan P, const __grid_constant__ 
         PMT_CONV_DISPATCH(op.ksize, op, in, Gb.ld[i], Gb.lp[i], out, Gb.ld[i + 1], Gb.lp[i + 1], wst, wflat, VT)
       } else {
         const int lo = Gb.len[i + 1];
-        for (int idx = tid; idx < op.in_ch * VT * lo; idx += NTHREADS) {
-          const int c = idx / (VT * lo), v = (idx / lo) % VT, p = idx % lo;
+        Idx3 it(VT, lo);
+        for (int idx = tid; idx < op.in_ch * VT * lo; idx += NTHREADS, it.next()) {
+          const int c = it.c, v = it.v, p = it.p;
           const float* xr = in + c * Gb.ld[i] + v * Gb.lp[i] + p * op.stride;
           float m = xr[0];
           for (int t = 1; t < op.ksize; ++t) m = fmaxf(m, xr[t]);
@@ -1020,8 +1037,9 @@ hap_cnn_backward_kernel(const __grid_constant__ Plan P, const __grid_constant__ 
     float* gnxt = gB;
     {
       const int C = Gb.ch[ns], len = Gb.len[ns];
-      for (int idx = tid; idx < C * VT * len; idx += NTHREADS) {
-        const int c = idx / (VT * len), v = (idx / len) % VT, p = idx % len;
+      Idx3 it(VT, len);
+      for (int idx = tid; idx < C * VT * len; idx += NTHREADS, it.next()) {
+        const int c = it.c, v = it.v, p = it.p;
         gcur[c * Gb.ld[ns] + v * Gb.lp[ns] + p] = dcur[v * VS + c * len + p];
       }
       __syncthreads();
@@ -1035,8 +1053,9 @@ hap_cnn_backward_kernel(const __grid_constant__ Plan P, const __grid_constant__ 
       const int ld_i = Gb.ld[i], lp_i = Gb.lp[i], ld_o = Gb.ld[i + 1], lp_o = Gb.lp[i + 1];
       if (op.kind == PMT_CNN_POOL) {
         // gradient goes to the first maximum of each window (one thread per INPUT element: no atomics)
-        for (int idx = tid; idx < op.in_ch * VT * li; idx += NTHREADS) {
-          const int c = idx / (VT * li), v = (idx / li) % VT, q = idx % li;
+        Idx3 it(VT, li);
+        for (int idx = tid; idx < op.in_ch * VT * li; idx += NTHREADS, it.next()) {
+          const int c = it.c, v = it.v, q = it.p;
           float a = 0.f;
           int p_lo = q - op.ksize + 1;
           p_lo = p_lo <= 0 ? 0 : (p_lo + op.stride - 1) / op.stride;
@@ -1054,8 +1073,9 @@ hap_cnn_backward_kernel(const __grid_constant__ Plan P, const __grid_constant__ 
         float* t = gcur; gcur = gnxt; gnxt = t;
       } else {
         // through the activation folded into this conv; padding positions are forced to zero
-        for (int idx = tid; idx < op.out_ch * VT * lp_o; idx += NTHREADS) {
-          const int c = idx / (VT * lp_o), v = (idx / lp_o) % VT, p = idx % lp_o;
+        Idx3 it(VT, lp_o);
+        for (int idx = tid; idx < op.out_ch * VT * lp_o; idx += NTHREADS, it.next()) {
+          const int c = it.c, v = it.v, p = it.p;
           const int o = c * ld_o + v * lp_o + p;
           gcur[o] = p < lo ? gcur[o] * act_grad_from_out(out[o], op.act) : 0.f;
         }
@@ -1081,8 +1101,9 @@ hap_cnn_backward_kernel(const __grid_constant__ Plan P, const __grid_constant__ 
           // zero-padded copy of the output gradient, then the forward conv routine with the flipped image
           const int ldg = Gb.ldg[i], lpg = Gb.lpg[i], ks = op.ksize;
           stage_image(wst, conv_image + Gm.img_total + Gm.imgT_off[i], op.out_ch * ks * ((op.in_ch + 7) / 8) * GROUP_STRIDE);
-          for (int idx = tid; idx < op.out_ch * VT * lpg; idx += NTHREADS) {
-            const int c = idx / (VT * lpg), v = (idx / lpg) % VT, pp = idx % lpg, p = pp - (ks - 1);
+          Idx3 it(VT, lpg);
+          for (int idx = tid; idx < op.out_ch * VT * lpg; idx += NTHREADS, it.next()) {
+            const int c = it.c, v = it.v, pp = it.p, p = pp - (ks - 1);
             gnxt[c * ldg + v * lpg + pp] = (p >= 0 && p < lo) ? gcur[c * ld_o + v * lp_o + p] : 0.f;
           }
           __syncthreads();
