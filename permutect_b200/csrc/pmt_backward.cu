@@ -56,7 +56,14 @@ __device__ __forceinline__ float* pick_free(float* const* bufs, const float* a, 
 static __device__ __noinline__ float* mlp_backward(const Plan& P, const PmtLinearOp* ops, int n_ops, int g0,
                                                    const float* scr, const int* scr_off, float* g, float* const* bufs,
                                                    Stage& stage, const float* wflat, float* part, int rows_used,
-                                                   bool need_input_grad) {
+                                                   bool need_input_grad, long long* trace = nullptr) {
+#define PMT_MLP_TRACE(id)                                                                                        \
+  do {                                                                                                           \
+    if (trace && threadIdx.x == 0) {                                                                             \
+      const long long n_ = trace[0];                                                                             \
+      if (n_ < 250) { trace[1 + 2 * n_] = (id); trace[2 + 2 * n_] = clock64(); trace[0] = n_ + 1; }             \
+    }                                                                                                            \
+  } while (0)
   float* gcur = g;
   int i = n_ops - 1;
   while (i >= 0) {
@@ -72,15 +79,21 @@ static __device__ __noinline__ float* mlp_backward(const Plan& P, const PmtLinea
         const GemmOp& gop = P.gemm[g0 + j];
         float* A = pick_free(bufs, gres, din, nullptr);
         __syncthreads();
-        load_rows(A, lop.in_dim, scr + scr_off[j]);
+        PMT_MLP_TRACE(200);
+        load_rows_async(A, lop.in_dim, scr + scr_off[j]);   // acquire() waits for every cp.async of the thread
         const float* imgT = stage.acquire(MAX_GEMM + g0 + j);
+        PMT_MLP_TRACE(201);
         if (j == j0) { selu_copy(A, A, lop.in_dim); __syncthreads(); }   // A = s0 = SELU(x)
         if (j > 0) stage.prefetch(MAX_GEMM + g0 + j - 1);
+        PMT_MLP_TRACE(202);
         wgrad_tile(smem_addr(din), lop.out_dim, smem_addr(A), lop.in_dim, part + lop.w_off, 0, rows_used);
+        PMT_MLP_TRACE(203);
         rowdot_tile(din, nullptr, lop.out_dim, part + lop.b_off, 0, rows_used);
+        PMT_MLP_TRACE(204);
         const float scale = (j == j1) ? alpha : 1.f;
         float* dnext = pick_free(bufs, gres, din, A);
         gemm_tile_T(din, gop, imgT, 0, dnext, EPI_DSELU, scale, A, rows_used);
+        PMT_MLP_TRACE(205);
         if (j == j0) {   // gres += dnext (the SELU(x) branch joins the identity branch)
           __syncthreads();
           for (int t = threadIdx.x; t < lop.in_dim * (TILE / 4); t += NTHREADS) {
@@ -320,9 +333,10 @@ static __device__ __forceinline__ RowNorm bwd_block_reload(BwdTile& T, int blk, 
   const float* W = T.C.W;
   const int row = threadIdx.x & (TILE - 1), rp = threadIdx.x / TILE;
   const int Dm = D.d_model, H = D.d_ffn / 2;
-  load_rows(Ab, Dm, scr + P.scr_x[blk]);
-  if (cz_state) load_rows(Cz, 6 * H, cz_state);
-  else load_rows(Cz, 2 * H, scr + P.scr_z[blk]);
+  load_rows_async(Ab, Dm, scr + P.scr_x[blk]);
+  if (cz_state) load_rows_async(Cz, 6 * H, cz_state);
+  else load_rows_async(Cz, 2 * H, scr + P.scr_z[blk]);
+  cp_async_wait_all();
   T.stage.prefetch(prefetch_key);
   __syncthreads();
   RowNorm n;
@@ -558,7 +572,8 @@ static __device__ __forceinline__ void bwd_embed(BwdTile& T, float* scr, float* 
     }
   }
   PMT_TILE_TRACE(23);
-  mlp_backward(P, D.read_ops, D.n_read_ops, P.read_g0, scr, P.scr_read, G, T.bufs, T.stage, T.C.W, T.part, T.C.rows_used, false);
+  mlp_backward(P, D.read_ops, D.n_read_ops, P.read_g0, scr, P.scr_read, G, T.bufs, T.stage, T.C.W, T.part, T.C.rows_used, false,
+               T.tracing ? T.A.trace : nullptr);
   __syncthreads();
   PMT_TILE_TRACE(24);
 }
@@ -1267,11 +1282,15 @@ extern "C" int pmt_backward(const PmtModelDesc* desc, const float* weights, cons
   int dev = 0, n_sm = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-  const double avg = (double)(batch->n_rows > 0 ? batch->n_rows : 16LL * B) / B;
-  int claim = (int)(4.0 * TILE / (avg + 1.0));
-  if (claim > B / (2 * n_sm)) claim = B / (2 * n_sm);
+  // Claims go to CTAs round-robin (fixed summation order), so their number is a multiple of the grid; every claim ends
+  // with a partly filled tile, so a claim should hold >= 16 tiles (n_rows is an upper bound for a downsampled batch:
+  // claims of ~4 tiles left a fifth of the rows of every tile empty).
+  const double rows_total = (double)(batch->n_rows > 0 ? batch->n_rows : 16LL * B);
+  int per_cta = (int)(rows_total / ((double)n_sm * 16.0 * TILE));
+  if (per_cta < 1) per_cta = 1;
+  if (per_cta > 8) per_cta = 8;
+  int claim = (int)((B + (long long)n_sm * per_cta - 1) / ((long long)n_sm * per_cta));
   if (claim < 1) claim = 1;
-  if (claim > 512) claim = 512;
   P.claim_variants = claim;
 
   BwdArgs A;

@@ -392,10 +392,18 @@ __device__ __forceinline__ void save_rows(const float* buf, int nf, float* g) {
   float4* g4 = reinterpret_cast<float4*>(g);
   for (int i = threadIdx.x; i < nf * (LD / 4); i += NTHREADS) g4[i] = s4[i];
 }
-__device__ __forceinline__ void load_rows(float* buf, int nf, const float* g) {
+// global -> shared with cp.async: every copy of the thread is in flight at once (a register round trip serialised one
+// L2 / DRAM latency per 16 bytes: 4.5 k cycles per 30-feature image).  The thread waits for its own copies; the caller's
+// __syncthreads() publishes them.
+__device__ __forceinline__ void load_rows_async(float* buf, int nf, const float* g) {   // caller: cp_async_wait_all()
   float4* s4 = reinterpret_cast<float4*>(buf);
   const float4* g4 = reinterpret_cast<const float4*>(g);
-  for (int i = threadIdx.x; i < nf * (LD / 4); i += NTHREADS) s4[i] = g4[i];
+  for (int i = threadIdx.x; i < nf * (LD / 4); i += NTHREADS) cp_async16(s4 + i, g4 + i);
+  cp_async_commit();
+}
+__device__ __forceinline__ void load_rows(float* buf, int nf, const float* g) {
+  load_rows_async(buf, nf, g);
+  cp_async_wait_all();
 }
 
 // Runs an MLP program (mlp.py:25-76) over the tile.  `cur` holds the input; b0/b1/b2 are the three

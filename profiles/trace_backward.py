@@ -16,6 +16,8 @@ from permutect_b200.utils.enums import Epoch  # noqa: E402
 
 NAMES = {0: "tile built", 1: "recompute: read embedding", 20: "recompute: reducer, rotation, head", 21: "head + rotation backward",
          22: "reducer backward", 23: "concat (d info_seq)", 24: "read embedding backward"}
+NAMES.update({200: "  mlp layer: barrier", 201: "  mlp layer: reload input + weight image ready", 202: "  mlp layer: SELU of the block input, prefetch",
+              203: "  mlp layer: wgrad_tile", 204: "  mlp layer: bias rowdot", 205: "  mlp layer: dgrad gemm (thread 0 done)"})
 for b in range(8):
     NAMES[2 + b] = f"recompute: gated block {b}"
     for q, what in enumerate(["reload x, z; LayerNorms, means, gate", "proj2 wgrad + dgrad", "gate / mean-field / LN2 backward",
@@ -47,6 +49,8 @@ for (_, c0), (pid, c1) in zip(recs, recs[1:]):
         key = "block backward: " + key.split(": ", 1)[1]
     elif 2 <= pid < 20:
         key = "recompute: gated block"
+    elif pid >= 200:
+        key = "read embedding backward, skip-block layers:" + key
     agg[key] = agg.get(key, 0) + (c1 - c0)
     print(f"{pid:4d} {c1 - c0:9d}  {NAMES.get(pid, '')}")
 print("--- summed over blocks")
