@@ -263,6 +263,51 @@ __device__ __forceinline__ void red_add(float* p, float v) { asm volatile("red.g
 // `part` is this CTA's private gradient buffer, so the read-modify-write needs no atomics and the
 // summation order is fixed.  Lanes 0-15 / 16-31 of a warp take two groups of 4 consecutive n; each
 // lane takes k in {kl, kl+16, kl+32, kl+48}: 16 consecutive feature rows per LDS -> conflict-free.
+// (Giving a warp one n-group and 32 lanes along k when N <= 4 NWARPS was measured: no gain.)
+// One (4 n) x (KA k per lane) unit of wgrad_tile; KA is a template parameter so that no issue slot goes to
+// predicated-off FMAs (a runtime bound on a 4 x 4 unit wasted half of them at K = 30 and three quarters at K = 10).
+template <int KA>
+__device__ __forceinline__ void wgrad_unit(unsigned dy_s, int N, unsigned a_s, int K, float* __restrict__ part, int r_lo,
+                                           int r_hi, int ng, int k_first, int k_step) {
+  float acc[4][KA];
+#pragma unroll
+  for (int b = 0; b < 4; ++b)
+#pragma unroll
+    for (int a = 0; a < KA; ++a) acc[b][a] = 0.f;
+  unsigned dyp[4], ap[KA];
+#pragma unroll
+  for (int b = 0; b < 4; ++b) dyp[b] = dy_s + (min(ng * 4 + b, N - 1) * LD) * 4;
+#pragma unroll
+  for (int a = 0; a < KA; ++a) ap[a] = a_s + (min(k_first + k_step * a, K - 1) * LD) * 4;
+  for (int r = r_lo; r < r_hi; r += 4) {
+    float4 dy[4], av[KA];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) dy[b] = lds128(dyp[b] + r * 4);
+#pragma unroll
+    for (int a = 0; a < KA; ++a) av[a] = lds128(ap[a] + r * 4);
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+      for (int a = 0; a < KA; ++a) {
+        acc[b][a] = fmaf(dy[b].x, av[a].x, acc[b][a]);
+        acc[b][a] = fmaf(dy[b].y, av[a].y, acc[b][a]);
+        acc[b][a] = fmaf(dy[b].z, av[a].z, acc[b][a]);
+        acc[b][a] = fmaf(dy[b].w, av[a].w, acc[b][a]);
+      }
+  }
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    const int n = ng * 4 + b;
+    if (n < N) {
+#pragma unroll
+      for (int a = 0; a < KA; ++a) {
+        const int k = k_first + k_step * a;
+        if (k < K) red_add(part + n * K + k, acc[b][a]);
+      }
+    }
+  }
+}
+
 static __device__ __noinline__ void wgrad_tile(unsigned dy_s, int N, unsigned a_s, int K, float* __restrict__ part,
                                                int r_lo, int r_hi) {
   if (r_hi <= r_lo) return;
@@ -271,68 +316,45 @@ static __device__ __noinline__ void wgrad_tile(unsigned dy_s, int N, unsigned a_
   for (int k0 = 0; k0 < K; k0 += 64) {
     const int ka = min(4, (K - k0 + 15) >> 4);
     for (int ng = warp * 2 + (lane >> 4); ng * 4 < N; ng += 2 * NWARPS) {
-      float acc[4][4];
-#pragma unroll
-      for (int b = 0; b < 4; ++b)
-#pragma unroll
-        for (int a = 0; a < 4; ++a) acc[b][a] = 0.f;
-      unsigned dyp[4], ap[4];
-#pragma unroll
-      for (int b = 0; b < 4; ++b) dyp[b] = dy_s + (min(ng * 4 + b, N - 1) * LD) * 4;
-#pragma unroll
-      for (int a = 0; a < 4; ++a) ap[a] = a_s + (min(k0 + kl + 16 * a, K - 1) * LD) * 4;
-      for (int r = r_lo; r < r_hi; r += 4) {
-        float4 dy[4], av[4];
-#pragma unroll
-        for (int b = 0; b < 4; ++b) dy[b] = lds128(dyp[b] + r * 4);
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-          if (a < ka) av[a] = lds128(ap[a] + r * 4);
-#pragma unroll
-        for (int b = 0; b < 4; ++b)
-#pragma unroll
-          for (int a = 0; a < 4; ++a)
-            if (a < ka) {
-              acc[b][a] = fmaf(dy[b].x, av[a].x, acc[b][a]);
-              acc[b][a] = fmaf(dy[b].y, av[a].y, acc[b][a]);
-              acc[b][a] = fmaf(dy[b].z, av[a].z, acc[b][a]);
-              acc[b][a] = fmaf(dy[b].w, av[a].w, acc[b][a]);
-            }
-      }
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        const int n = ng * 4 + b;
-        if (n < N) {
-#pragma unroll
-          for (int a = 0; a < 4; ++a) {
-            const int k = k0 + kl + 16 * a;
-            if (a < ka && k < K) red_add(part + n * K + k, acc[b][a]);
-          }
-        }
+      switch (ka) {
+        case 1: wgrad_unit<1>(dy_s, N, a_s, K, part, r_lo, r_hi, ng, k0 + kl, 16); break;
+        case 2: wgrad_unit<2>(dy_s, N, a_s, K, part, r_lo, r_hi, ng, k0 + kl, 16); break;
+        case 3: wgrad_unit<3>(dy_s, N, a_s, K, part, r_lo, r_hi, ng, k0 + kl, 16); break;
+        default: wgrad_unit<4>(dy_s, N, a_s, K, part, r_lo, r_hi, ng, k0 + kl, 16); break;
       }
     }
   }
 }
 
-// part[f * stride] += sum_{r in [r_lo, r_hi)} buf[f][r] * (other ? other[f][r] : 1)  for f < nf.  One warp per feature.
+// part[f * stride] += sum_{r in [r_lo, r_hi)} buf[f][r] * (other ? other[f][r] : 1)  for f < nf.  A warp reduces four
+// features at a time (four independent shuffle trees in flight; one tree per iteration left the warp waiting on
+// shuffle latency: 1.7 k cycles per 30 features).
 __device__ __forceinline__ void rowdot_tile(const float* buf, const float* other, int nf, float* __restrict__ part,
                                             int r_lo, int r_hi, int stride = 1) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int f = warp; f < nf; f += NWARPS) {
-    float s = 0.f;
-    const int r = r_lo + lane * 4;
-    if (r < r_hi) {
-      const float4 v = *reinterpret_cast<const float4*>(buf + f * LD + r);
-      if (other) {
-        const float4 o = *reinterpret_cast<const float4*>(other + f * LD + r);
-        s = v.x * o.x + v.y * o.y + v.z * o.z + v.w * o.w;
-      } else {
-        s = v.x + v.y + v.z + v.w;
+  const int r = r_lo + lane * 4;
+  for (int f0 = warp * 4; f0 < nf; f0 += NWARPS * 4) {
+    float s[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int f = f0 + q;
+      s[q] = 0.f;
+      if (f < nf && r < r_hi) {
+        const float4 v = *reinterpret_cast<const float4*>(buf + f * LD + r);
+        if (other) {
+          const float4 o = *reinterpret_cast<const float4*>(other + f * LD + r);
+          s[q] = v.x * o.x + v.y * o.y + v.z * o.z + v.w * o.w;
+        } else {
+          s[q] = v.x + v.y + v.z + v.w;
+        }
       }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) red_add(part + f * stride, s);
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) s[q] += __shfl_xor_sync(0xffffffffu, s[q], o);
+    const float mine = lane == 0 ? s[0] : (lane == 1 ? s[1] : (lane == 2 ? s[2] : s[3]));
+    if (lane < 4 && f0 + lane < nf) red_add(part + (f0 + lane) * stride, mine);
   }
 }
 
