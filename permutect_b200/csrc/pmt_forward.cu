@@ -6,7 +6,6 @@
 //   reads_forward_kernel  decode -> read_embedding -> concat -> gated ref/alt blocks -> reducer ->
 //                         rotation -> clustering head -> per-variant sums (artifact_model.py:243-297)
 #include <cstdio>
-#include <cstdlib>
 #include <cstring>
 
 #include "pmt_host.h"
@@ -377,9 +376,10 @@ void pmt_profile_begin(cudaStream_t st) { if (g_prof_start && g_prof_stop) cudaE
 void pmt_profile_end(cudaStream_t st) { if (g_prof_start && g_prof_stop) cudaEventRecord(g_prof_stop, st); }
 extern "C" int pmt_abi_version(void) { return PMT_ABI_VERSION; }
 
+// Column groups of a tile GEMM: one warp per group, so eight groups keep all eight warps busy (four groups for N <= 32
+// left half the CTA at the barrier: 22.7 -> 21.4 ms on the backward kernel).
 static void choose_groups(int N, int* G, int* NT) {
-  int g = N > 32 ? 8 : 4;
-  if (const char* e = getenv("PMT_GEMM_GROUPS")) { if (atoi(e) >= 4) g = atoi(e); }
+  int g = 8;
   int nt = (N + g - 1) / g;
   if (nt < 1) nt = 1;
   g = (N + nt - 1) / nt;
