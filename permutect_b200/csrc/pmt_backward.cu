@@ -43,9 +43,19 @@ struct BwdArgs {
 
 // trace[0] = number of records; record i = (phase id, clock64()) at trace[1 + 2i]  (PMT_TILE_TRACE)
 
-__device__ __forceinline__ float* pick_free(float* const* bufs, const float* a, const float* b, const float* c) {
-  for (int i = 0; i < 4; ++i)
-    if (bufs[i] != a && bufs[i] != b && bufs[i] != c) return bufs[i];
+// The four activation buffers of a backward CTA, as (base, stride): an array of pointers would live in local memory,
+// and with nearly all of L1 carved out as shared memory every read of it is an L2 round trip.
+struct BufSet {
+  float* base;
+  int stride;   // floats
+  __device__ __forceinline__ float* operator[](int i) const { return base + i * stride; }
+};
+__device__ __forceinline__ float* pick_free(const BufSet& bufs, const float* a, const float* b, const float* c) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float* p = bufs[i];
+    if (p != a && p != b && p != c) return p;
+  }
   return nullptr;
 }
 
@@ -54,7 +64,7 @@ __device__ __forceinline__ float* pick_free(float* const* bufs, const float* a, 
 // Weight/bias gradients are accumulated into `part`; for the last layer of a DenseSkipBlock the un-scaled
 // U = dx_out . s^T is accumulated instead (skip_fix_kernel turns it into dW = alpha U and d alpha = <W, U> + <b, Ub>).
 static __device__ __noinline__ float* mlp_backward(const Plan& P, const PmtLinearOp* ops, int n_ops, int g0,
-                                                   const float* scr, const int* scr_off, float* g, float* const* bufs,
+                                                   const float* scr, const int* scr_off, float* g, const BufSet& bufs,
                                                    Stage& stage, const float* wflat, float* part, int rows_used,
                                                    bool need_input_grad, long long* trace = nullptr) {
 #define PMT_MLP_TRACE(id)                                                                                        \
@@ -160,7 +170,7 @@ struct BwdTile {
   TileCtx& C;
   Stage& stage;
   BlockAccum& acc;
-  float* const* bufs;   // four [bwd_rows][LD] activation buffers
+  BufSet bufs;          // four [bwd_rows][LD] activation buffers
   float* dsums;         // [nv][2][sum_w] gradients of the mean fields (same layout as C.sums)
   float* wpart;         // BlockAccum storage [NWARPS][acc_cap]
   float* small;         // [64] scratch for tiny reductions
@@ -170,15 +180,24 @@ struct BwdTile {
 };
 
 struct BwdSmem {
-  float* bufs[4];
+  BufSet bufs;
   float *st0, *st1, *dsums, *wpart, *small;
   int acc_cap;
 };
 
+static_assert(sizeof(Plan) % 16 == 0, "Plan is copied to shared memory in 16-byte units");
+__device__ __forceinline__ const Plan* stage_plan_in_smem(const Plan& param, float* smem) {
+  const int* src = reinterpret_cast<const int*>(&param);
+  int* dst = reinterpret_cast<int*>(smem);
+  for (int i = threadIdx.x; i < (int)(sizeof(Plan) / sizeof(int)); i += NTHREADS) dst[i] = src[i];
+  __syncthreads();
+  return reinterpret_cast<const Plan*>(smem);
+}
+
 __device__ __forceinline__ void carve_bwd_smem(const Plan& P, float* smem, TileCtx& C, BwdSmem& S) {
   const PmtModelDesc& D = P.d;
   const int R = P.bwd_rows;
-  for (int i = 0; i < 4; ++i) S.bufs[i] = smem + i * R * LD;
+  S.bufs.base = smem; S.bufs.stride = R * LD;
   S.st0 = smem + 4 * R * LD;
   S.st1 = S.st0 + P.stage_floats;
   C.X = S.bufs[0]; C.T1 = S.bufs[1]; C.T2 = S.bufs[2];
@@ -217,8 +236,7 @@ static __device__ __forceinline__ float* bwd_tail(BwdTile& T, float* scr) {
   const int E = D.d_feat, K = D.n_clusters, rows_used = C.rows_used;
   const int my_var = M.rowvar[row];
   const bool is_alt = row >= M.ref_pad;
-  PmtOutputs no_out;
-  memset(&no_out, 0, sizeof(no_out));
+  const PmtOutputs no_out{};
   float *Yb, *Fb;
   tile_tail(P, C, T.stage, no_out, false, scr, Yb, Fb);
   PMT_TILE_TRACE(20);
@@ -426,10 +444,10 @@ static __device__ __forceinline__ RowNorm bwd_block_gate(BwdTile& T, int blk, co
   }
   __syncthreads();
   if (tid < 5) {
-    const int offs[5] = {BO.alpha_ref, BO.alpha_alt, BO.beta_ref, BO.beta_alt, BO.gamma};
+    const int off = tid == 0 ? BO.alpha_ref : (tid == 1 ? BO.alpha_alt : (tid == 2 ? BO.beta_ref : (tid == 3 ? BO.beta_alt : BO.gamma)));
     float s = 0.f;
     for (int w = 0; w < NWARPS; ++w) s += T.wpart[w * T.acc_cap + tid];
-    red_add(part + offs[tid], s);
+    red_add(part + off, s);
   }
   segment_sums(M, Cz, 5 * H, H, T.dsums, P.sum_w, false, accumulate);
   __syncthreads();
@@ -572,15 +590,26 @@ static __device__ __forceinline__ void bwd_embed(BwdTile& T, float* scr, float* 
     }
   }
   PMT_TILE_TRACE(23);
+#ifdef PMT_GEMM_TRACE
+  if (T.tracing && threadIdx.x == 0) T.A.trace[511] = 1;
+#endif
   mlp_backward(P, D.read_ops, D.n_read_ops, P.read_g0, scr, P.scr_read, G, T.bufs, T.stage, T.C.W, T.part, T.C.rows_used, false,
                T.tracing ? T.A.trace : nullptr);
   __syncthreads();
+#ifdef PMT_GEMM_TRACE
+  if (T.tracing && threadIdx.x == 0) T.A.trace[511] = 0;
+#endif
   PMT_TILE_TRACE(24);
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
-reads_backward_kernel(const __grid_constant__ Plan P, const __grid_constant__ BwdArgs A) {
-  extern __shared__ __align__(16) float smem[];
+reads_backward_kernel(const __grid_constant__ Plan Pparam, const __grid_constant__ BwdArgs A) {
+  extern __shared__ __align__(16) float smem_all[];
+  // The plan is indexed dynamically everywhere (layer tables, GEMM descriptors, scratch offsets); from the kernel's
+  // parameter bank every such read is a constant-cache round trip (1-2.5 k cycles per GEMM call went to them), so it
+  // lives in shared memory.
+  const Plan& P = *stage_plan_in_smem(Pparam, smem_all);
+  float* smem = smem_all + sizeof(Plan) / sizeof(float);
   const PmtModelDesc& D = P.d;
   TileCtx C;
   BwdSmem S;
@@ -630,15 +659,13 @@ reads_backward_kernel(const __grid_constant__ Plan P, const __grid_constant__ Bw
       }
       // ======================= backward =======================
       float* G = bwd_tail(T, scr);
-      float* others[3];
-      {
-        int q = 0;
-        for (int i = 0; i < 4; ++i) if (S.bufs[i] != G) others[q++] = S.bufs[i];
-      }
+      float* const Ab = pick_free(S.bufs, G, nullptr, nullptr);
+      float* const Bn = pick_free(S.bufs, G, Ab, nullptr);
+      float* const Cz = pick_free(S.bufs, G, Ab, Bn);
       for (int blk = D.n_blocks - 1; blk >= 0; --blk) {
-        const RowNorm n = bwd_block_gate(T, blk, scr, nullptr, G, others[0], others[1], others[2], false);
+        const RowNorm n = bwd_block_gate(T, blk, scr, nullptr, G, Ab, Bn, Cz, false);
         bwd_block_meanfield(T, blk);
-        bwd_block_finish(T, blk, G, others[0], others[1], others[2], n);
+        bwd_block_finish(T, blk, G, Ab, Bn, Cz, n);
       }
       bwd_embed(T, scr, G, false);
     }
@@ -650,8 +677,13 @@ reads_backward_kernel(const __grid_constant__ Plan P, const __grid_constant__ Bw
 // and the gate state of the block being differentiated); the mean fields and their gradients are accumulated over
 // the chunks between the two halves of each block's backward, exactly where reads_forward_long_kernel accumulates them.
 __global__ void __launch_bounds__(NTHREADS, 1)
-reads_backward_long_kernel(const __grid_constant__ Plan P, const __grid_constant__ BwdArgs A) {
-  extern __shared__ __align__(16) float smem[];
+reads_backward_long_kernel(const __grid_constant__ Plan Pparam, const __grid_constant__ BwdArgs A) {
+  extern __shared__ __align__(16) float smem_all[];
+  // The plan is indexed dynamically everywhere (layer tables, GEMM descriptors, scratch offsets); from the kernel's
+  // parameter bank every such read is a constant-cache round trip (1-2.5 k cycles per GEMM call went to them), so it
+  // lives in shared memory.
+  const Plan& P = *stage_plan_in_smem(Pparam, smem_all);
+  float* smem = smem_all + sizeof(Plan) / sizeof(float);
   const PmtModelDesc& D = P.d;
   TileCtx C;
   BwdSmem S;
@@ -765,7 +797,7 @@ info_mlp_backward_kernel(const __grid_constant__ Plan P, const float* __restrict
                          const float* __restrict__ d_info_seq, float* scratch, long long scratch_stride, float* partials,
                          int rows_per_buf) {
   extern __shared__ __align__(16) float smem[];
-  float* bufs[4] = {smem, smem + rows_per_buf * LD, smem + 2 * rows_per_buf * LD, smem + 3 * rows_per_buf * LD};
+  const BufSet bufs{smem, rows_per_buf * LD};
   float* st0 = smem + 4 * rows_per_buf * LD;
   float* st1 = st0 + P.info_stage_floats;
   Stage stage;
@@ -1205,7 +1237,7 @@ static size_t bwd_smem_bytes(const Plan& P) {
   const int n_head = P.d.d_feat + P.d.n_clusters * P.d.d_feat + 5 * P.d.n_clusters;
   const int acc_cap = n_head > 8 ? n_head : 8;
   return (size_t)(4 * P.bwd_rows * LD + 2 * P.stage_floats + 2 * TILE * 2 * P.sum_w + TILE * 2 * 16 + NWARPS * acc_cap +
-                  64) * sizeof(float) + sizeof(HeadConst) + sizeof(TileMeta) + 64;
+                  64) * sizeof(float) + sizeof(HeadConst) + sizeof(TileMeta) + 64 + sizeof(Plan);
 }
 static int info_rows(const Plan& P) {
   int r = P.d.n_info_features;
@@ -1231,7 +1263,13 @@ static int long_bwd_grid(const Plan& P, const PmtBatch* batch) {
   return grid < 1 ? 1 : (int)grid;
 }
 static long long* g_bwd_trace = nullptr;
-extern "C" int pmt_set_backward_trace(long long* device_buffer) { g_bwd_trace = device_buffer; return 0; }
+extern "C" int pmt_set_backward_trace(long long* device_buffer) {
+  g_bwd_trace = device_buffer;
+#ifdef PMT_GEMM_TRACE
+  cudaMemcpyToSymbol(pmt::g_gemm_trace, &device_buffer, sizeof(device_buffer));
+#endif
+  return 0;
+}
 
 size_t pmt_backward_workspace_bytes(const Plan& P, const PmtBatch* batch) {
   size_t bytes = 1024;

@@ -17,7 +17,8 @@ from permutect_b200.utils.enums import Epoch  # noqa: E402
 NAMES = {0: "tile built", 1: "recompute: read embedding", 20: "recompute: reducer, rotation, head", 21: "head + rotation backward",
          22: "reducer backward", 23: "concat (d info_seq)", 24: "read embedding backward"}
 NAMES.update({200: "  mlp layer: barrier", 201: "  mlp layer: reload input + weight image ready", 202: "  mlp layer: SELU of the block input, prefetch",
-              203: "  mlp layer: wgrad_tile", 204: "  mlp layer: bias rowdot", 205: "  mlp layer: dgrad gemm (thread 0 done)"})
+              203: "  mlp layer: wgrad_tile", 204: "  mlp layer: bias rowdot", 205: "  mlp layer: dgrad gemm (thread 0 done)",
+              300: "    gemm: entered", 301: "    gemm: accumulators initialised", 302: "    gemm: k loop", 303: "    gemm: epilogue"})
 for b in range(8):
     NAMES[2 + b] = f"recompute: gated block {b}"
     for q, what in enumerate(["reload x, z; LayerNorms, means, gate", "proj2 wgrad + dgrad", "gate / mean-field / LN2 backward",
