@@ -965,11 +965,27 @@ __device__ __forceinline__ void conv_wgrad(const PmtCnnOp& op, const float* __re
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
-hap_cnn_backward_kernel(const __grid_constant__ Plan P, const __grid_constant__ CnnGeom Gm,
-                        const __grid_constant__ CnnBwdGeom Gb, const float* __restrict__ wflat,
+hap_cnn_backward_kernel(const __grid_constant__ Plan P, const __grid_constant__ CnnGeom Gm_param,
+                        const __grid_constant__ CnnBwdGeom Gb_param, const float* __restrict__ wflat,
                         const float* __restrict__ conv_image, const void* __restrict__ haps, int hap_kind,
                         long long hap_stride, int n_variants, const float* __restrict__ d_info_seq, float* partials) {
   extern __shared__ __align__(16) float smem[];
+  // layer tables and geometry are indexed by the layer loop: from the parameter bank each read is a constant-cache
+  // round trip (14 % of this kernel's stall samples sat on the two layer loops), so they are copied to shared memory
+  __shared__ PmtCnnOp s_ops[PMT_MAX_CNN_OPS];
+  __shared__ CnnBwdGeom s_gb;
+  __shared__ CnnGeom s_gm;
+  {
+    const int* src_ops = reinterpret_cast<const int*>(P.d.cnn_ops);
+    const int* src_gb = reinterpret_cast<const int*>(&Gb_param);
+    const int* src_gm = reinterpret_cast<const int*>(&Gm_param);
+    for (int i = threadIdx.x; i < (int)(sizeof(s_ops) / sizeof(int)); i += NTHREADS) reinterpret_cast<int*>(s_ops)[i] = src_ops[i];
+    for (int i = threadIdx.x; i < (int)(sizeof(CnnBwdGeom) / sizeof(int)); i += NTHREADS) reinterpret_cast<int*>(&s_gb)[i] = src_gb[i];
+    for (int i = threadIdx.x; i < (int)(sizeof(CnnGeom) / sizeof(int)); i += NTHREADS) reinterpret_cast<int*>(&s_gm)[i] = src_gm[i];
+    __syncthreads();
+  }
+  const CnnBwdGeom& Gb = s_gb;
+  const CnnGeom& Gm = s_gm;
   float* acts = smem;
   float* gA = acts + Gb.act_total;
   float* gB = gA + Gb.gbuf_floats;
@@ -1000,7 +1016,7 @@ hap_cnn_backward_kernel(const __grid_constant__ Plan P, const __grid_constant__ 
     }
     __syncthreads();
     for (int i = 0; i < ns; ++i) {
-      const PmtCnnOp& op = D.cnn_ops[i];
+      const PmtCnnOp& op = s_ops[i];
       const float* in = acts + Gb.act_off[i];
       float* out = acts + Gb.act_off[i + 1];
       if (op.kind == PMT_CNN_CONV) {
@@ -1029,7 +1045,7 @@ hap_cnn_backward_kernel(const __grid_constant__ Plan P, const __grid_constant__ 
       }
       __syncthreads();
       for (int l = 0; l < Gb.n_linear; ++l) {
-        const PmtCnnOp& op = D.cnn_ops[ns + l];
+        const PmtCnnOp& op = s_ops[ns + l];
         const float* vin = vec + l * VT * VS;
         float* vout = vec + (l + 1) * VT * VS;
         for (int idx = tid; idx < VT * op.out_ch; idx += NTHREADS) {
@@ -1051,7 +1067,7 @@ hap_cnn_backward_kernel(const __grid_constant__ Plan P, const __grid_constant__ 
     }
     __syncthreads();
     for (int l = Gb.n_linear - 1; l >= 0; --l) {
-      const PmtCnnOp& op = D.cnn_ops[ns + l];
+      const PmtCnnOp& op = s_ops[ns + l];
       const float* vin = vec + l * VT * VS;
       const float* vout = vec + (l + 1) * VT * VS;
       for (int idx = tid; idx < VT * op.out_ch; idx += NTHREADS) {
@@ -1093,20 +1109,22 @@ hap_cnn_backward_kernel(const __grid_constant__ Plan P, const __grid_constant__ 
     }
     // ---- backward: spatial ops in reverse ----
     for (int i = ns - 1; i >= 0; --i) {
-      const PmtCnnOp& op = D.cnn_ops[i];
+      const PmtCnnOp& op = s_ops[i];
       const float* in = acts + Gb.act_off[i];
       const float* out = acts + Gb.act_off[i + 1];
       const int li = Gb.len[i], lo = Gb.len[i + 1];
       const int ld_i = Gb.ld[i], lp_i = Gb.lp[i], ld_o = Gb.ld[i + 1], lp_o = Gb.lp[i + 1];
       if (op.kind == PMT_CNN_POOL) {
         // gradient goes to the first maximum of each window (one thread per INPUT element: no atomics)
+        const int stride_shift = op.stride == 1 ? 0 : (op.stride == 2 ? 1 : -1);
         Idx3 it(VT, li);
         for (int idx = tid; idx < op.in_ch * VT * li; idx += NTHREADS, it.next()) {
           const int c = it.c, v = it.v, q = it.p;
           float a = 0.f;
+          // windows p with p*stride <= q <= p*stride + ksize - 1 (shifts for the usual strides 1 and 2)
           int p_lo = q - op.ksize + 1;
-          p_lo = p_lo <= 0 ? 0 : (p_lo + op.stride - 1) / op.stride;
-          const int p_hi = min(lo - 1, q / op.stride);
+          p_lo = p_lo <= 0 ? 0 : (stride_shift >= 0 ? (p_lo + op.stride - 1) >> stride_shift : (p_lo + op.stride - 1) / op.stride);
+          const int p_hi = min(lo - 1, stride_shift >= 0 ? q >> stride_shift : q / op.stride);
           for (int p = p_lo; p <= p_hi; ++p) {
             const float* xr = in + c * ld_i + v * lp_i + p * op.stride;
             int arg = 0;
