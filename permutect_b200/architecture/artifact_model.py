@@ -118,6 +118,7 @@ class ArtifactModel(nn.Module):
         self._flat_cache = None
         self._param_list = None
         self._materialization_cache = None
+        self._flat_optimizer = None
 
     # ---- reference surface (artifact_model.py:199-230) -------------------------------------------------
     def reset_source_predictor(self, num_sources: int = 1):
@@ -173,6 +174,9 @@ class ArtifactModel(nn.Module):
         node (torch.cat of the constrained tensors); without grad it is cached until a parameter changes."""
         params = self._parameter_list()
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            opt = getattr(self, "_flat_optimizer", None)
+            if opt is not None and opt.backs(params):
+                return planner.materialize_flat(self, opt)          # one clone + 13 constrained slots (training/step.py)
             return torch.cat([t.reshape(-1) for t in planner.materialized_tensors(self)])
         try:
             versions = tuple(p._version for p in params) + tuple(p.data_ptr() for p in params[:4])

