@@ -3,7 +3,9 @@ commented out at :22-36).  Batches produced by the loader (pinned host memory, r
 are copied on a side CUDA stream into a ring of persistent device buffers, up to ``depth`` batches ahead of the batch
 the model is working on, so PCIe transfers overlap the kernels.  The consumer's stream waits on the copy's event and
 the copy stream waits on the event that marks the consumer's last use of a ring slot; there is no host
-synchronisation and, after the first pass, no device allocation."""
+synchronisation and, after the first pass, no device allocation.  The ring (buffers, copy stream, release events)
+outlives a generator: the next pass over a loader (the next epoch, the next evaluation pass) starts copying while the
+kernels of the previous pass are still running instead of waiting for the compute stream to drain."""
 import copy
 from typing import Iterable, Iterator, List, Optional
 
@@ -21,14 +23,27 @@ class _Slot:
         self.device = device
         self.buffers = {}
         self.released: Optional[torch.cuda.Event] = None
+        self.fresh = False    # a buffer was (re)allocated since the last copy: its memory may still be in use on the caller's stream
 
     def view_like(self, name: str, t_cpu: torch.Tensor) -> torch.Tensor:
         buf = self.buffers.get(name)
         n = t_cpu.numel()
         if buf is None or buf.dtype != t_cpu.dtype or buf.numel() < n:
-            buf = torch.empty(int(n * 1.1) + 64, dtype=t_cpu.dtype, device=self.device)
+            with torch.inference_mode(False):     # the ring outlives this pass: an inference tensor could not be refilled by a training pass
+                buf = torch.empty(int(n * 1.1) + 64, dtype=t_cpu.dtype, device=self.device)
             self.buffers[name] = buf
+            self.fresh = True
         return buf[:n].view(t_cpu.shape)
+
+
+class _Ring:
+    def __init__(self, device, depth: int):
+        self.copy_stream = torch.cuda.Stream(device)
+        self.slots: List[_Slot] = [_Slot(device) for _ in range(depth + 1)]
+        self.in_use = False
+
+
+_RINGS = {}   # (device, depth) -> _Ring kept between generators
 
 
 def prefetch_generator(dataloader: Iterable[Batch], device=None, depth: int = 2) -> Iterator[Batch]:
@@ -37,8 +52,22 @@ def prefetch_generator(dataloader: Iterable[Batch], device=None, depth: int = 2)
         for batch_cpu in dataloader:
             yield batch_cpu.copy_to(device)
         return
-    copy_stream = torch.cuda.Stream(device)
-    ring: List[_Slot] = [_Slot(device) for _ in range(depth + 1)]
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    shared = _RINGS.get((device, depth))
+    if shared is None:
+        shared = _RINGS[(device, depth)] = _Ring(device, depth)
+    owner = not shared.in_use          # two generators alive at once (nested loaders) must not share slots
+    holder = shared if owner else _Ring(device, depth)
+    holder.in_use = True
+    try:
+        yield from _pipeline(dataloader, device, depth, holder)
+    finally:
+        holder.in_use = False
+
+
+def _pipeline(dataloader: Iterable[Batch], device, depth: int, holder: "_Ring") -> Iterator[Batch]:
+    copy_stream, ring = holder.copy_stream, holder.slots
     queue = []
     n_launched = 0
 
@@ -49,8 +78,9 @@ def prefetch_generator(dataloader: Iterable[Batch], device=None, depth: int = 2)
         views = {name: slot.view_like(name, getattr(batch_cpu, name)) for name in _FIELDS if getattr(batch_cpu, name) is not None}
         if slot.released is not None:
             copy_stream.wait_event(slot.released)       # the consumer of this slot's previous batch is done with it
-        else:
+        if slot.fresh or slot.released is None:
             copy_stream.wait_stream(torch.cuda.current_stream(device))   # buffers were just allocated on the caller's stream
+            slot.fresh = False
         with torch.cuda.stream(copy_stream):
             for name, dst in views.items():
                 dst.copy_(getattr(batch_cpu, name), non_blocking=True)
@@ -79,9 +109,13 @@ def prefetch_generator(dataloader: Iterable[Batch], device=None, depth: int = 2)
         launch(batch_cpu)
         if len(queue) >= depth:
             batch_gpu, slot = hand_over()
-            yield batch_gpu
-            release(slot)
+            try:
+                yield batch_gpu
+            finally:
+                release(slot)                  # also when the consumer stops early: the ring outlives this generator
     while queue:
         batch_gpu, slot = hand_over()
-        yield batch_gpu
-        release(slot)
+        try:
+            yield batch_gpu
+        finally:
+            release(slot)

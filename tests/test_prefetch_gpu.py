@@ -38,3 +38,32 @@ def test_prefetch_generator_on_cpu_is_a_plain_copy_loop():
     host = [Batch.from_arrays(*make_wgs_arrays(10, seed=1))]
     out = list(prefetch_generator(host, torch.device("cpu")))
     assert len(out) == 1 and out[0].size() == 10
+
+
+@GPU
+def test_ring_is_shared_between_passes_and_survives_early_exit_and_nesting():
+    g = load("v040_seed0_b64")
+    dev = torch.device("cuda:0")
+    model = model_from_golden(g, dev)
+    model.set_epoch_type(Epoch.VALID)
+    sizes = [300, 1200, 64, 800, 5]
+    host = [Batch.from_arrays(*make_wgs_arrays(n, seed=70 + i)).pin_memory() for i, n in enumerate(sizes)]
+    with torch.inference_mode():
+        want = [model.compute_batch_output(b.copy_to(dev)).logits_b.cpu() for b in host]
+        for _ in range(3):                                   # consecutive passes reuse the ring
+            got = [model.compute_batch_output(b).logits_b.cpu() for b in prefetch_generator(host, dev)]
+            assert all(torch.equal(a, w) for a, w in zip(got, want))
+        for b in prefetch_generator(host, dev):              # the consumer stops early
+            break
+        got = [model.compute_batch_output(b).logits_b.cpu() for b in prefetch_generator(host, dev)]
+        assert all(torch.equal(a, w) for a, w in zip(got, want))
+        outer_got, inner_got = [], []
+        for i, b in enumerate(prefetch_generator(host, dev)):    # a second generator while the first is alive
+            if i == 1:
+                inner_got = [model.compute_batch_output(c).logits_b.cpu() for c in prefetch_generator(host, dev)]
+            outer_got.append(model.compute_batch_output(b).logits_b.cpu())
+        assert all(torch.equal(a, w) for a, w in zip(outer_got, want))
+        assert all(torch.equal(a, w) for a, w in zip(inner_got, want))
+    # a ring filled under inference_mode must be refillable by a training pass (its buffers are ordinary tensors)
+    got = [model.compute_batch_output(b).logits_b.detach().cpu() for b in prefetch_generator(host, dev)]
+    assert all(torch.equal(a, w) for a, w in zip(got, want))
