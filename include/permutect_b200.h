@@ -284,6 +284,38 @@ int pmt_pack_posterior(const int16_t* int_array, int64_t int_stride, int32_t n_i
                        int64_t float_stride, const float* logits_b, const float* features_be, int32_t d_feat,
                        int32_t n_variants, int16_t* int_out, float* float_out, void* stream);
 
+/* ---- posterior model (inference half) ------------------------------------------------------------------
+ * Replaces PosteriorModel.log_posterior_and_ingredients (architecture/posterior_model.py:69-99) with
+ * PosteriorModelPriors.log_priors_bc (posterior_model_priors.py:121-139) and
+ * PosteriorModelSpectra.spectra_log_likelihoods_bc (spectra/posterior_model_spectra.py:78-124) for a batch of posterior
+ * records: int_array[n][int_stride] int16 (VARIANT_TYPE 3, ORIGINAL_DEPTH 5, ORIGINAL_ALT_COUNT 6,
+ * ORIGINAL_NORMAL_DEPTH 7, ORIGINAL_NORMAL_ALT_COUNT 8, haplotype codes from hap_start), float_array[n][float_stride]
+ * (SEQ_ERROR_LOG_LK 0, NORMAL_SEQ_ERROR_LOG_LK 1, ALLELE_FREQUENCY 2, MAF 3, NORMAL_MAF 4, CACHED_ARTIFACT_LOGIT 5;
+ * datum.py:51-81).  `params`: pmt_posterior_param_count(K) floats of CONSTRAINED values in this order: cell
+ * fractions cf_k[K], log weights[K], log background weight, log non-background weight, background alpha, beta,
+ * artifact alpha_dv[3][5], beta_dv[3][5], normal-artifact alpha_dv[3][5], beta_dv[3][5], mean_multiplier_v[5],
+ * concentration_v[5], log_priors_vc[5][5], somatic_snv_log_priors_rrra[5][5][5][5].  Outputs are [n][5] in Call order
+ * (SOMATIC, ARTIFACT, SEQ_ERROR, GERMLINE, NORMAL_ARTIFACT); any may be NULL. */
+#define PMT_POSTERIOR_MAX_COMPONENTS 16
+typedef struct PmtPosteriorDesc {
+  int32_t n_components;                     /* K of SomaticSpectrum (somatic_spectrum.py:46) */
+  int32_t hap_start, hap_len;               /* column of the first haplotype code, bases per haplotype (ref then alt) */
+  int32_t no_germline_mode;                 /* posterior_model.py:37 */
+  int32_t use_context_dependent_snv_priors; /* posterior_model_priors.py:99-103 */
+  float het_beta;                           /* < 0: None (binomial het likelihood, posterior_model_spectra.py:46-51) */
+} PmtPosteriorDesc;
+typedef struct PmtPosteriorOutputs {
+  float* log_priors_bc;
+  float* spectra_log_lks_bc;
+  float* normal_log_lks_bc;
+  float* log_posteriors_bc;
+  float* posterior_probabilities_bc;        /* softmax of log_posteriors_bc (posterior_model.py:51-56) */
+} PmtPosteriorOutputs;
+int pmt_posterior_param_count(int32_t n_components);
+int pmt_posterior_log_posteriors(const PmtPosteriorDesc* desc, const float* params, const int16_t* int_array,
+                                 int64_t int_stride, const void* float_array, int32_t float_kind, int64_t float_stride,
+                                 int32_t n_variants, const PmtPosteriorOutputs* out, void* stream);
+
 /* ---- batch assembly from the dataset memory maps ----------------------------------------------------
  * Replaces the row re-stacking of Batch.__init__ (batch.py:41-62) for batches cut from a MemoryMappedData
  * (memory_mapped_data.py:36-58, reads_dataset.py:109-196): the reads memory map holds, variant after variant, the ref

@@ -1,0 +1,179 @@
+"""The inference half of the reference's PosteriorModel (permutect/architecture/posterior_model.py:29-99) on
+libpermutect_b200: same module tree, parameter names, parametrisations and state-dict keys as the reference
+(``spectra.somatic_spectrum``, ``spectra.artifact_spectra``, ``spectra.normal_artifact_spectra``, ``priors``), so a
+posterior model fitted by the reference loads here and ``log_posterior_and_ingredients`` /
+``posterior_probabilities_bc`` / ``error_probabilities_b`` are one kernel launch (pmt_posterior_log_posteriors).
+
+Not here: ``learn_priors_and_spectra`` (SGD on the spectra + the PyMC M step of the priors,
+posterior_model_priors.py:141-215) and ``calculate_probability_thresholds`` (plotting).  There is no CPU path.
+"""
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor, nn
+from torch.nn import Parameter
+from torch.nn.utils import parametrize
+
+from permutect_b200.architecture.layers import BoundedNumber, LogWeights, PositiveNumber
+from permutect_b200.data.datum import HAPLOTYPES_START_IDX
+from permutect_b200.engine import library as L
+from permutect_b200.utils.enums import Variation
+
+NUM_DEPTH_BINS = 3                    # spectra/artifact_spectra.py:17-18
+NUM_CALLS = 5
+CALL_SOMATIC, CALL_ARTIFACT, CALL_SEQ_ERROR, CALL_GERMLINE, CALL_NORMAL_ARTIFACT = range(NUM_CALLS)   # utils/enums.py Call
+
+
+class SomaticSpectrum(nn.Module):
+    """Parameters of spectra/somatic_spectrum.py:46-72."""
+
+    def __init__(self, num_components: int):
+        super().__init__()
+        self.K = num_components
+        self.cf_k = Parameter(torch.sigmoid(6 * ((torch.arange(num_components) / num_components) - 0.5)))
+        parametrize.register_parametrization(self, "cf_k", BoundedNumber(0, 1))
+        self.log_weights_k = Parameter(torch.log(torch.square(self.cf_k.detach())))
+        parametrize.register_parametrization(self, "log_weights_k", LogWeights())
+        self.log_background_weight = Parameter(torch.log(torch.tensor(0.0001)), requires_grad=False)
+        self.log_non_background_weight = Parameter(torch.log(torch.tensor(1 - 0.0001)), requires_grad=False)
+        self.background_alpha = Parameter(torch.tensor([1]), requires_grad=False)
+        self.background_beta = Parameter(torch.tensor([1]), requires_grad=False)
+
+
+class ArtifactSpectra(nn.Module):
+    """Parameters of spectra/artifact_spectra.py:32-43."""
+
+    def __init__(self):
+        super().__init__()
+        V = len(Variation)
+        self.alpha_dv = Parameter(2 * torch.ones(NUM_DEPTH_BINS, V))
+        parametrize.register_parametrization(self, "alpha_dv", PositiveNumber())
+        self.beta_dv = Parameter(30 * torch.ones(NUM_DEPTH_BINS, V))
+        parametrize.register_parametrization(self, "beta_dv", PositiveNumber())
+
+
+class NormalArtifactSpectrum(nn.Module):
+    """Parameters of spectra/normal_artifact_spectrum.py:25-36."""
+
+    def __init__(self):
+        super().__init__()
+        V = len(Variation)
+        self.normal_spectrum = ArtifactSpectra()
+        self.mean_multiplier_v = Parameter(0.5 * torch.ones(V))
+        parametrize.register_parametrization(self, "mean_multiplier_v", BoundedNumber(0, 1))
+        self.concentration_v = Parameter(30 * torch.ones(V))
+        parametrize.register_parametrization(self, "concentration_v", PositiveNumber())
+
+
+class PosteriorModelSpectra(nn.Module):
+    def __init__(self, het_beta: Optional[float] = None):
+        super().__init__()
+        self.het_beta = het_beta
+        self.somatic_spectrum = SomaticSpectrum(num_components=5)      # spectra/posterior_model_spectra.py:74
+        self.artifact_spectra = ArtifactSpectra()
+        self.normal_artifact_spectra = NormalArtifactSpectrum()
+
+
+class PosteriorModelPriors(nn.Module):
+    """Parameters and switches of posterior_model_priors.py:68-103 (the M step is not part of this repository)."""
+
+    def __init__(self, variant_log_prior: float, artifact_log_prior: float, no_germline_mode: bool):
+        super().__init__()
+        self.no_germline_mode = no_germline_mode
+        self.use_context_dependent_snv_priors = True
+        log_priors_vc = torch.zeros(len(Variation), NUM_CALLS)
+        log_priors_vc[:, CALL_SOMATIC] = variant_log_prior
+        log_priors_vc[:, CALL_ARTIFACT] = artifact_log_prior
+        log_priors_vc[:, CALL_GERMLINE] = -9999 if no_germline_mode else 0
+        log_priors_vc[:, CALL_NORMAL_ARTIFACT] = artifact_log_prior
+        self.log_priors_vc = Parameter(log_priors_vc)
+        self.somatic_snv_log_priors_rrra = Parameter(variant_log_prior * torch.ones((5, 5, 5, 5)))
+
+    def enable_context_dependent_snv_priors(self) -> None:
+        self.use_context_dependent_snv_priors = True
+
+    def disable_context_dependent_snv_priors(self) -> None:
+        self.use_context_dependent_snv_priors = False
+
+
+class PosteriorModel(nn.Module):
+    def __init__(self, variant_log_prior: float, artifact_log_prior: float, no_germline_mode: bool = False,
+                 device=None, het_beta: Optional[float] = None):
+        super().__init__()
+        self._device = torch.device(device if device is not None else "cuda")
+        self._dtype = torch.float32
+        self.no_germline_mode = no_germline_mode
+        self.het_beta = het_beta
+        self.spectra = PosteriorModelSpectra(het_beta=het_beta)
+        self.priors = PosteriorModelPriors(variant_log_prior, artifact_log_prior, no_germline_mode)
+        self.to(device=self._device, dtype=self._dtype)
+
+    # ---- kernel-facing view --------------------------------------------------------------------------------
+    def flat_parameters(self) -> Tensor:
+        """The constrained values in the order pmt_posterior_log_posteriors documents (include/permutect_b200.h)."""
+        s, na = self.spectra.somatic_spectrum, self.spectra.normal_artifact_spectra
+        parts = [s.cf_k, s.log_weights_k, s.log_background_weight, s.log_non_background_weight, s.background_alpha,
+                 s.background_beta, self.spectra.artifact_spectra.alpha_dv, self.spectra.artifact_spectra.beta_dv,
+                 na.normal_spectrum.alpha_dv, na.normal_spectrum.beta_dv, na.mean_multiplier_v, na.concentration_v,
+                 self.priors.log_priors_vc, self.priors.somatic_snv_log_priors_rrra]
+        with torch.no_grad():
+            flat = torch.cat([p.detach().reshape(-1).to(torch.float32) for p in parts]).contiguous()
+        assert flat.numel() == L.load().pmt_posterior_param_count(s.K)
+        return flat
+
+    def _run(self, batch, want: Tuple[str, ...]):
+        it, ft = batch.int_tensor, batch.float_tensor
+        if it.device.type != "cuda" or ft.device != it.device:
+            raise RuntimeError("PosteriorModel computes on CUDA devices only (no CPU fallback): move the batch to the GPU")
+        if it.dtype != torch.int16:
+            it = it.to(torch.int16)
+        if ft.dtype not in (torch.float16, torch.float32):
+            ft = ft.to(torch.float32)
+        it, ft = it.contiguous(), ft.contiguous()
+        B = it.shape[0]
+        flat = self.flat_parameters().to(it.device)
+        outs = {k: torch.empty((B, NUM_CALLS), dtype=torch.float32, device=it.device) for k in want}
+        po = L.PmtPosteriorOutputs(*[outs[k].data_ptr() if k in outs else None for k in
+                                     ("log_priors_bc", "spectra_log_lks_bc", "normal_log_lks_bc", "log_posteriors_bc",
+                                      "posterior_probabilities_bc")])
+        desc = L.PmtPosteriorDesc(self.spectra.somatic_spectrum.K, HAPLOTYPES_START_IDX, (it.shape[1] - HAPLOTYPES_START_IDX) // 2,
+                                  int(self.no_germline_mode), int(self.priors.use_context_dependent_snv_priors),
+                                  -1.0 if self.het_beta is None else float(self.het_beta))
+        lib = L.load()
+        L.check(lib.pmt_posterior_log_posteriors(C.byref(desc), flat.data_ptr(), it.data_ptr(), it.stride(0), ft.data_ptr(),
+                                                 L.F16 if ft.dtype == torch.float16 else L.F32, ft.stride(0), B, C.byref(po),
+                                                 torch.cuda.current_stream(it.device).cuda_stream))
+        return outs
+
+    # ---- reference surface (posterior_model.py:51-99) ----------------------------------------------------
+    def log_posterior_and_ingredients(self, batch) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+        o = self._run(batch, ("log_priors_bc", "spectra_log_lks_bc", "normal_log_lks_bc", "log_posteriors_bc"))
+        return o["log_priors_bc"], o["spectra_log_lks_bc"], o["normal_log_lks_bc"], o["log_posteriors_bc"]
+
+    def log_relative_posteriors_bc(self, batch) -> Tensor:
+        return self._run(batch, ("log_posteriors_bc",))["log_posteriors_bc"]
+
+    def posterior_probabilities_bc(self, batch) -> Tensor:
+        return self._run(batch, ("posterior_probabilities_bc",))["posterior_probabilities_bc"]
+
+    def error_probabilities_b(self, batch, germline_mode: bool = False) -> Tensor:
+        assert not (germline_mode and self.no_germline_mode), "germline mode and no-germline mode are incompatible"
+        return 1 - self.posterior_probabilities_bc(batch)[:, CALL_GERMLINE if germline_mode else CALL_SOMATIC]
+
+    def learn_priors_and_spectra(self, *args, **kwargs):
+        raise NotImplementedError("fitting the posterior model (posterior_model.py:101-165) is not part of this repository yet; "
+                                  "fit with the reference and load the state dict here")
+
+
+class PosteriorBatch:
+    """The two arrays of a batch of posterior records (generate_posterior_arrays, tools/filter_variants.py) on a device."""
+
+    def __init__(self, int_array, float_array, device=None):
+        self.int_tensor = torch.as_tensor(int_array)
+        self.float_tensor = torch.as_tensor(float_array)
+        if device is not None:
+            self.int_tensor, self.float_tensor = self.int_tensor.to(device), self.float_tensor.to(device)
+
+    def size(self) -> int:
+        return self.int_tensor.shape[0]

@@ -263,7 +263,7 @@ __device__ __forceinline__ void block_phase_a(const Plan& P, TileCtx& C, Stage& 
   const PmtModelDesc& D = P.d;
   const PmtBlockOffsets& BO = D.blocks[blk];
   const int row = threadIdx.x & (TILE - 1), part = threadIdx.x / TILE;
-  const int Dm = D.d_model, H = D.d_ffn / 2;
+  const int Dm = D.d_model;
   const int g1 = P.blk_g0 + 2 * blk;
   const float* W = C.W;
   {

@@ -92,8 +92,18 @@ class PmtLossGrads(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("g_supervised_b", "g_unsupervised_b", "g_alt_count_b", "g_source_b", "g_total_b")]
 
 
-EXPORTED_SYMBOLS = ["pmt_dataset_read_indices", "pmt_pack_posterior", "pmt_adamw_step", "pmt_adamw_workspace_size", "pmt_losses_forward", "pmt_losses_backward", "pmt_losses_workspace_size", "pmt_set_cnn_trace", "pmt_set_reads_trace", "pmt_set_backward_trace", "pmt_last_error", "pmt_abi_version", "pmt_workspace_size", "pmt_forward", "pmt_forward_prepared", "pmt_backward",
+EXPORTED_SYMBOLS = ["pmt_posterior_param_count", "pmt_posterior_log_posteriors", "pmt_dataset_read_indices", "pmt_pack_posterior", "pmt_adamw_step", "pmt_adamw_workspace_size", "pmt_losses_forward", "pmt_losses_backward", "pmt_losses_workspace_size", "pmt_set_cnn_trace", "pmt_set_reads_trace", "pmt_set_backward_trace", "pmt_last_error", "pmt_abi_version", "pmt_workspace_size", "pmt_forward", "pmt_forward_prepared", "pmt_backward",
                     "pmt_decode_reads", "pmt_set_profile_events", "pmt_downsample_counts", "pmt_downsample_fill", "pmt_set_precision", "pmt_get_precision"]
+
+class PmtPosteriorDesc(C.Structure):
+    _fields_ = [("n_components", C.c_int32), ("hap_start", C.c_int32), ("hap_len", C.c_int32), ("no_germline_mode", C.c_int32),
+                ("use_context_dependent_snv_priors", C.c_int32), ("het_beta", C.c_float)]
+
+
+class PmtPosteriorOutputs(C.Structure):
+    _fields_ = [("log_priors_bc", C.c_void_p), ("spectra_log_lks_bc", C.c_void_p), ("normal_log_lks_bc", C.c_void_p),
+                ("log_posteriors_bc", C.c_void_p), ("posterior_probabilities_bc", C.c_void_p)]
+
 
 _LIB = None
 
@@ -142,6 +152,11 @@ def load():
     lib.pmt_pack_posterior.restype = C.c_int
     lib.pmt_pack_posterior.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32,
                                        C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.pmt_posterior_param_count.restype = C.c_int
+    lib.pmt_posterior_param_count.argtypes = [C.c_int32]
+    lib.pmt_posterior_log_posteriors.restype = C.c_int
+    lib.pmt_posterior_log_posteriors.argtypes = [C.POINTER(PmtPosteriorDesc), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
+                                                 C.c_int64, C.c_int32, C.POINTER(PmtPosteriorOutputs), C.c_void_p]
     lib.pmt_adamw_workspace_size.restype = C.c_size_t
     lib.pmt_adamw_step.restype = C.c_int
     lib.pmt_adamw_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float,

@@ -1,0 +1,113 @@
+"""PosteriorModel inference: the oracle against the reference-generated golden on the CPU, the kernel
+(pmt_posterior_log_posteriors through the C-ABI, behind the reference's PosteriorModel surface) against both on the GPU.
+Tolerance: every table entry is a sum of ~7 fp32 lgamma terms as large as lgamma(depth + 1) (279 000 at depth 30 000,
+one ulp = 0.03) that cancel to O(10); the reference's own fp32 result carries that rounding, so rows are held to
+2e-5 relative + 2e-4 + 8 ulp(lgamma(depth + 2)) absolute (3e-4 at depth 100, 6e-3 at 1 000, 0.27 at 30 000).
+Calls (argmax) identical wherever the top two posteriors differ by more than that."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import posterior_model_oracle as orc
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "posterior_model.npz")
+CASES = ["default", "no_context", "het_beta", "no_germline"]
+TABLES = ["log_priors_bc", "spectra_log_lks_bc", "normal_log_lks_bc", "log_posteriors_bc"]
+
+
+def _row_atol(int_array):
+    from scipy.special import gammaln
+    depth = np.maximum(int_array[:, 5], int_array[:, 7]).astype(np.float64)
+    return (2e-4 + 8 * np.finfo(np.float32).eps * gammaln(depth + 2.0))[:, None]
+
+
+def _assert_tables_close(got, want, int_array, msg):
+    excess = np.abs(got - want) - (_row_atol(int_array) + 2e-5 * np.abs(want))
+    worst = np.unravel_index(np.argmax(excess), excess.shape)
+    assert excess.max() <= 0, f"{msg}: row {worst[0]} call {worst[1]}: got {got[worst]} want {want[worst]} (depth {int_array[worst[0], 5]})"
+
+
+def _case(z, tag):
+    sd = {k[len(tag) + 4:]: z[k] for k in z.files if k.startswith(tag + "/sd/")}
+    cfg = z[tag + "/cfg"]
+    return sd, bool(cfg[0]), (None if cfg[1] < 0 else float(cfg[1])), bool(cfg[2])
+
+
+@pytest.mark.parametrize("tag", CASES)
+def test_oracle_matches_reference_golden(tag):
+    z = np.load(GOLDEN)
+    sd, no_germline, het_beta, context = _case(z, tag)
+    out = orc.log_posterior_and_ingredients(sd, z["int_array"], z["float_array"], no_germline, het_beta, context)
+    for k in TABLES + ["posterior_probabilities_bc", "error_probabilities_b"]:
+        np.testing.assert_allclose(out[k].numpy(), z[f"{tag}/out/{k}"], rtol=2e-6, atol=1e-5, err_msg=k)
+
+
+def test_state_dict_keys_and_initial_values_match_the_reference():
+    from permutect_b200.architecture.posterior_model import PosteriorModel
+    z = np.load(GOLDEN)
+    model = PosteriorModel(-10.0, -10.0, device="cpu")
+    sd = model.state_dict()
+    want = {k[len("default/sd/"):]: z[k] for k in z.files if k.startswith("default/sd/")}
+    assert set(sd.keys()) == set(want.keys())
+    for k, v in sd.items():
+        assert tuple(v.shape) == tuple(want[k].shape), k
+    # un-perturbed constants of the reference's constructor (somatic_spectrum.py:62-69)
+    np.testing.assert_allclose(sd["spectra.somatic_spectrum.log_background_weight"].numpy(), np.log(np.float32(0.0001)), rtol=1e-6)
+    assert float(sd["spectra.somatic_spectrum.background_alpha"][0]) == 1.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", CASES)
+def test_kernel_matches_reference_golden_and_oracle(tag):
+    from permutect_b200.architecture.posterior_model import PosteriorBatch, PosteriorModel
+    z = np.load(GOLDEN)
+    sd, no_germline, het_beta, context = _case(z, tag)
+    dev = torch.device("cuda:0")
+    model = PosteriorModel(-3.0, -4.0, no_germline_mode=no_germline, device=dev, het_beta=het_beta)
+    model.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sd.items()})
+    if not context:
+        model.priors.disable_context_dependent_snv_priors()
+    batch = PosteriorBatch(z["int_array"], z["float_array"], dev)
+    got = dict(zip(TABLES, model.log_posterior_and_ingredients(batch)))
+    for k in TABLES:
+        _assert_tables_close(got[k].cpu().numpy(), z[f"{tag}/out/{k}"], z["int_array"], k)
+    probs = model.posterior_probabilities_bc(batch).cpu().numpy()
+    shallow = z["int_array"][:, 5] <= 400            # probabilities: rows whose log-table tolerance is below 3e-3
+    np.testing.assert_allclose(probs[shallow], z[f"{tag}/out/posterior_probabilities_bc"][shallow], rtol=0, atol=3e-3)
+    np.testing.assert_allclose(model.error_probabilities_b(batch).cpu().numpy()[shallow],
+                               z[f"{tag}/out/error_probabilities_b"][shallow], rtol=0, atol=3e-3)
+    want_post = z[f"{tag}/out/log_posteriors_bc"]
+    top2 = np.sort(want_post, axis=1)[:, -2:]
+    decided = (top2[:, 1] - top2[:, 0]) > 2 * _row_atol(z["int_array"])[:, 0] + 1e-3
+    assert decided.mean() > 0.9
+    assert np.array_equal(probs.argmax(1)[decided], want_post.argmax(1)[decided])       # identical calls
+    # fp16 float block (an ArtifactModel Batch keeps its side arrays in fp16): same tables, the inputs are fp16-exact
+    half = PosteriorBatch(z["int_array"], z["float_array"].astype(np.float16), dev)
+    _assert_tables_close(model.log_relative_posteriors_bc(half).cpu().numpy(), want_post, z["int_array"], "fp16 float block")
+
+
+@pytest.mark.gpu
+def test_kernel_matches_oracle_on_a_large_random_batch_and_rejects_cpu():
+    from permutect_b200.architecture.posterior_model import PosteriorBatch, PosteriorModel
+    z = np.load(GOLDEN)
+    sd, _, _, _ = _case(z, "default")
+    rng = np.random.default_rng(3)
+    reps = 40
+    ia = np.tile(z["int_array"], (reps, 1))
+    fa = np.tile(z["float_array"], (reps, 1))
+    depth = rng.integers(1, 2000, len(ia))
+    ia[:, 5] = depth
+    ia[:, 6] = np.maximum(1, rng.binomial(depth, rng.uniform(0.001, 0.9, len(ia))))
+    ia[:, 7] = rng.integers(0, 500, len(ia))
+    ia[:, 8] = rng.binomial(ia[:, 7], 0.03)
+    fa[:, 5] = np.float16(rng.normal(0, 6, len(ia)))
+    dev = torch.device("cuda:0")
+    model = PosteriorModel(-3.0, -4.0, device=dev)
+    model.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sd.items()})
+    got = model.log_relative_posteriors_bc(PosteriorBatch(ia, fa, dev)).cpu().numpy()
+    want = orc.log_posterior_and_ingredients(sd, ia, fa)["log_posteriors_bc"].numpy()
+    _assert_tables_close(got, want, ia, "random batch")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model.log_relative_posteriors_bc(PosteriorBatch(ia[:4], fa[:4]))
