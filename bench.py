@@ -229,7 +229,7 @@ def run_training(args, model, ia, fa, reads, dev, world, barrier):
     ms_max = float(t.item())
     model.set_epoch_type(Epoch.VALID)
     return {"metric": "artifact_model_training_variants_per_sec", "value": bt * world / (ms_max / 1e3), "unit": "variants/s",
-            "ms_per_step": ms_max, "batch_variants_per_gpu": bt, "last_loss_per_variant": float(losses.total_loss) / bt,
+            "ms_per_step": ms_max, "batch_variants_per_gpu": bt, "last_loss_per_variant": float(losses.total_loss.detach()) / bt,
             "backward_kernel_ms": prof.mean_ms(), "gpu_launches": 24 * args.steps,   # library kernels per step (profiles/r1/launches_bench_default_summary.txt)
             "step": "device DownsampledBatch + compute_batch_output + compute_batch_losses (fused loss head) + backward (FP32 SIMT) + "
                     "flat grad all-reduce + clip(1.0) + AdamW (FlatAdamW)"}
@@ -285,6 +285,41 @@ def run_panel(args, model, dev, world, rank, barrier):
             "inference_ms": infer_ms, "train_variants_per_s": n * world / (train_ms / 1e3),
             "train_reads_per_s": kept[0] * world / (train_ms / 1e3), "train_ms": train_ms, "train_reads_per_step": kept[0],
             "kernels": "reads_forward_long_kernel / reads_backward_long_kernel (FP32 SIMT, sets walked in chunks of 128 reads)"}
+
+
+def run_posterior(n, dev):
+    """SURVEY §8 f3 (inference half): PosteriorModel.posterior_probabilities_bc over n synthetic posterior records."""
+    from permutect_b200.architecture.posterior_model import PosteriorBatch, PosteriorModel
+    g = torch.Generator(device=dev).manual_seed(9)
+    it = torch.zeros((n, 16 + 42), dtype=torch.int16, device=dev)
+    depth = torch.randint(8, 300, (n,), generator=g, device=dev)
+    it[:, 3] = torch.randint(0, 5, (n,), generator=g, device=dev)
+    it[:, 5] = depth
+    it[:, 6] = torch.clamp((depth * torch.rand(n, generator=g, device=dev) * 0.6).long(), min=1)
+    it[:, 7] = torch.randint(0, 200, (n,), generator=g, device=dev)
+    it[:, 8] = (it[:, 7].float() * 0.03 * torch.rand(n, generator=g, device=dev)).long()
+    it[:, 16:] = torch.randint(0, 4, (n, 42), generator=g, device=dev)
+    ft = torch.zeros((n, 16), dtype=torch.float32, device=dev)
+    ft[:, 0] = -30 * torch.rand(n, generator=g, device=dev)
+    ft[:, 1] = -5 * torch.rand(n, generator=g, device=dev)
+    ft[:, 2] = 10 ** (-4 * torch.rand(n, generator=g, device=dev) - 0.3)
+    ft[:, 3] = 0.05 + 0.45 * torch.rand(n, generator=g, device=dev)
+    ft[:, 4] = 0.05 + 0.45 * torch.rand(n, generator=g, device=dev)
+    ft[:, 5] = 8 * torch.randn(n, generator=g, device=dev)
+    model = PosteriorModel(-10.0, -10.0, device=dev)
+    batch = PosteriorBatch(it, ft)
+    for _ in range(3):
+        model.posterior_probabilities_bc(batch)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(5):
+        model.posterior_probabilities_bc(batch)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / 5
+    return {"what": "PosteriorModel.posterior_probabilities_bc (pmt_posterior_log_posteriors), records resident", "variants": n,
+            "ms": ms, "variants_per_s": n / (ms / 1e3)}
 
 
 def main():
@@ -477,6 +512,7 @@ def main():
         result["gpu_launches"] = 9 * args.steps + train["gpu_launches"]
     if panel is not None:
         result["panel"] = panel
+        result["posterior"] = run_posterior(args.variants, dev)
     if not args.no_cpu_baseline:
         sample = 8192
         v, n_it = time_oracle(model.state_dict(), sample, seed=3000, budget_s=15.0)
