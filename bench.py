@@ -287,6 +287,30 @@ def run_panel(args, model, dev, world, rank, barrier):
             "kernels": "reads_forward_long_kernel / reads_backward_long_kernel (FP32 SIMT, sets walked in chunks of 128 reads)"}
 
 
+def run_small_batch_training(model, dev, batch_variants=64, steps=100):
+    """The reference's default training batch (parameters.py:214: 64 variants): the step is bound by the host side
+    (autograd over the parametrised tensors, ctypes, launches), not by the kernels."""
+    from permutect_b200.data.batch import Batch, DownsampledBatch
+    from permutect_b200.synthetic import make_wgs_arrays
+    from permutect_b200.training.step import make_optimizer, train_step
+    from permutect_b200.utils.enums import Epoch
+    model.set_epoch_type(Epoch.TRAIN)
+    opt = make_optimizer(model, learning_rate=1e-3, weight_decay=0.01)
+    parent = Batch.from_arrays(*make_wgs_arrays(batch_variants, seed=4000)).copy_to(dev)
+    frac = torch.full((batch_variants,), 0.8, device=dev)
+    for i in range(10):
+        train_step(model, DownsampledBatch(parent, frac, frac, seed=i), opt)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        train_step(model, DownsampledBatch(parent, frac, frac, seed=100 + i), opt)
+    torch.cuda.synchronize()
+    ms = 1e3 * (time.perf_counter() - t0) / steps
+    model.set_epoch_type(Epoch.VALID)
+    return {"batch_variants": batch_variants, "ms_per_step": ms, "variants_per_s": batch_variants / (ms / 1e3), "steps": steps,
+            "timing": "wall clock around the loop with a synchronize on both sides (host-bound regime)"}
+
+
 def run_posterior(n, dev):
     """SURVEY §8 f3 (inference half): PosteriorModel.posterior_probabilities_bc over n synthetic posterior records."""
     from permutect_b200.architecture.posterior_model import PosteriorBatch, PosteriorModel
@@ -513,11 +537,17 @@ def main():
     if panel is not None:
         result["panel"] = panel
         result["posterior"] = run_posterior(args.variants, dev)
+        result["train"]["small_batch"] = run_small_batch_training(model, dev)
     if not args.no_cpu_baseline:
         sample = 8192
         v, n_it = time_oracle(model.state_dict(), sample, seed=3000, budget_s=15.0)
         result["cpu_baseline"] = {"value": v, "unit": "variants/s", "cores": torch.get_num_threads(), "kind": "port",
                                   "sample": f"oracle forward on {sample} WGS-shaped variants per batch, median of {n_it} batches"}
+        if train is not None:
+            vt, n_it = time_oracle(model.state_dict(), 2048, seed=3001, budget_s=10.0, train=True)
+            result["cpu_baseline"]["train_value"] = vt
+            result["cpu_baseline"]["train_sample"] = (f"oracle forward + losses + autograd backward on 2048 WGS-shaped variants per "
+                                                      f"step, median of {n_it} steps")
     print(json.dumps(result))
     if world > 1:
         dist.destroy_process_group()

@@ -274,6 +274,14 @@ int pmt_adamw_step(float* params, const float* grads, float* exp_avg, float* exp
                    const float* mask, int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, float max_norm,
                    float* total_norm_out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- rotation matrix of the orthogonal parametrisation --------------------------------------------------
+ * EuclideanTransformation's rotation (architecture/euclidean_transformation.py:11-14) is a torch orthogonal
+ * parametrisation with the matrix-exponential map: Q = base @ exp(tril(X) - tril(X)^T).  x, base (may be NULL), q, d_q,
+ * d_x: [n][n] fp32 on the device, n <= 16.  Forward and its vector-Jacobian product, each one single-CTA launch
+ * (the torch formulation costs ~135 tensor ops of host time per training step). */
+int pmt_orthogonal_forward(const float* x, const float* base, int32_t n, float* q, void* stream);
+int pmt_orthogonal_backward(const float* x, const float* base, const float* d_q, int32_t n, float* d_x, void* stream);
+
 /* ---- inference caller tail --------------------------------------------------------------------------
  * Replaces the per-variant Python loop of generate_posterior_data (tools/filter_variants.py:302-320): for every
  * variant, int_out[n_int_columns] = its int16 record with REF_COUNT / ALT_COUNT zeroed, float_out[6 + d_feat] (fp32,

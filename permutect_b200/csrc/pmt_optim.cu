@@ -98,3 +98,139 @@ extern "C" int pmt_adamw_step(float* params, const float* grads, float* exp_avg,
   PMT_CHECK(e == cudaSuccess, "pmt_adamw_step launch failed: %s", cudaGetErrorString(e));
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Rotation matrix of torch's orthogonal parametrisation (matrix-exponential map, square weight;
+// torch/nn/utils/parametrizations.py:_Orthogonal.forward as used by euclidean_transformation.py:11-14):
+//   A = tril(X) - tril(X)^T,  Q = base @ exp(A).
+// exp by scaling and squaring with fixed parameters in double (Taylor degree 14 of A / 2^6, six squarings), the same
+// recipe as engine/plan.py:_orthogonal_without_sync, which needs ~45 tensor ops forward and ~90 backward on the host
+// side of every training step.  One CTA, one thread per matrix element; the backward kernel recomputes the forward
+// intermediates in shared memory and walks them in reverse.
+// ------------------------------------------------------------------------------------------------
+namespace expm {
+
+constexpr int DEG = 14, SQ = 6, MAXN = 16;
+
+// C = A @ B (n x n, row-major, shared memory); every thread (i, j) of the n x n grid computes one element
+__device__ __forceinline__ double mm(const double* A, const double* B, int n, int i, int j) {
+  double s = 0.0;
+  for (int k = 0; k < n; ++k) s = fma(A[i * n + k], B[k * n + j], s);
+  return s;
+}
+__device__ __forceinline__ double mm_nt(const double* A, const double* B, int n, int i, int j) {   // A @ B^T
+  double s = 0.0;
+  for (int k = 0; k < n; ++k) s = fma(A[i * n + k], B[j * n + k], s);
+  return s;
+}
+__device__ __forceinline__ double mm_tn(const double* A, const double* B, int n, int i, int j) {   // A^T @ B
+  double s = 0.0;
+  for (int k = 0; k < n; ++k) s = fma(A[k * n + i], B[k * n + j], s);
+  return s;
+}
+
+// Fills Bm (= A / 2^SQ) and the DEG + SQ + 1 intermediates: T[0..DEG-1] = Horner iterates (T[0] = I + B/DEG, T[m] for
+// k = DEG-m), T[DEG-1] = Taylor polynomial, T[DEG-1+s] after s squarings.  Caller syncs afterwards.
+__device__ void forward_chain(const float* __restrict__ X, int n, double* Bm, double* T, int i, int j, bool active) {
+  const int nn = n * n;
+  if (active) {
+    const double xl_ij = j <= i ? (double)X[i * n + j] : 0.0, xl_ji = i <= j ? (double)X[j * n + i] : 0.0;
+    Bm[i * n + j] = (xl_ij - xl_ji) * (1.0 / (double)(1 << SQ));
+  }
+  __syncthreads();
+  if (active) T[i * n + j] = (i == j ? 1.0 : 0.0) + Bm[i * n + j] / (double)DEG;
+  __syncthreads();
+  for (int m = 1; m < DEG; ++m) {          // k = DEG - m
+    if (active) T[m * nn + i * n + j] = (i == j ? 1.0 : 0.0) + mm(Bm, T + (m - 1) * nn, n, i, j) / (double)(DEG - m);
+    __syncthreads();
+  }
+  for (int s = 0; s < SQ; ++s) {
+    const double* S = T + (DEG - 1 + s) * nn;
+    if (active) T[(DEG + s) * nn + i * n + j] = mm(S, S, n, i, j);
+    __syncthreads();
+  }
+}
+
+__global__ void forward_kernel(const float* __restrict__ X, const float* __restrict__ base, int n, float* __restrict__ Q) {
+  extern __shared__ double sm[];
+  const int nn = n * n, i = threadIdx.x / n, j = threadIdx.x % n;
+  const bool active = threadIdx.x < nn;
+  double* Bm = sm;
+  double* T = sm + nn;
+  forward_chain(X, n, Bm, T, i, j, active);
+  const double* E = T + (DEG - 1 + SQ) * nn;
+  if (active) {
+    double q = E[i * n + j];
+    if (base) {
+      q = 0.0;
+      for (int k = 0; k < n; ++k) q = fma((double)base[i * n + k], E[k * n + j], q);
+    }
+    Q[i * n + j] = (float)q;
+  }
+}
+
+__global__ void backward_kernel(const float* __restrict__ X, const float* __restrict__ base, const float* __restrict__ dQ, int n,
+                                float* __restrict__ dX) {
+  extern __shared__ double sm[];
+  const int nn = n * n, i = threadIdx.x / n, j = threadIdx.x % n;
+  const bool active = threadIdx.x < nn;
+  double* Bm = sm;
+  double* T = sm + nn;
+  double* G = T + (DEG + SQ) * nn;     // running gradient
+  double* G2 = G + nn;
+  double* dB = G2 + nn;
+  forward_chain(X, n, Bm, T, i, j, active);
+  if (active) {
+    double g = (double)dQ[i * n + j];
+    if (base) {                          // Q = base @ E  ->  dE = base^T @ dQ
+      g = 0.0;
+      for (int k = 0; k < n; ++k) g = fma((double)base[k * n + i], (double)dQ[k * n + j], g);
+    }
+    G[i * n + j] = g;
+    dB[i * n + j] = 0.0;
+  }
+  __syncthreads();
+  for (int s = SQ - 1; s >= 0; --s) {    // S' = S @ S  ->  dS = dS' @ S^T + S^T @ dS'
+    const double* S = T + (DEG - 1 + s) * nn;
+    if (active) G2[i * n + j] = mm_nt(G, S, n, i, j) + mm_tn(S, G, n, i, j);
+    __syncthreads();
+    double* t = G; G = G2; G2 = t;
+  }
+  for (int m = DEG - 1; m >= 1; --m) {   // T[m] = I + (B @ T[m-1]) / k,  k = DEG - m
+    const double inv_k = 1.0 / (double)(DEG - m);
+    if (active) {
+      dB[i * n + j] += mm_nt(G, T + (m - 1) * nn, n, i, j) * inv_k;
+      G2[i * n + j] = mm_tn(Bm, G, n, i, j) * inv_k;
+    }
+    __syncthreads();
+    double* t = G; G = G2; G2 = t;
+  }
+  if (active) dB[i * n + j] += G[i * n + j] / (double)DEG;     // T[0] = I + B / DEG
+  __syncthreads();
+  if (active) {                          // B = (Xl - Xl^T) / 2^SQ, Xl = tril(X)
+    const double d = (dB[i * n + j] - dB[j * n + i]) * (1.0 / (double)(1 << SQ));
+    dX[i * n + j] = j <= i ? (float)d : 0.f;
+  }
+}
+
+}  // namespace expm
+
+extern "C" int pmt_orthogonal_forward(const float* x, const float* base, int32_t n, float* q, void* stream) {
+  PMT_CHECK(x && q && n >= 1 && n <= expm::MAXN, "pmt_orthogonal_forward: n must be in 1..%d", expm::MAXN);
+  const size_t smem = (size_t)(1 + expm::DEG + expm::SQ) * n * n * sizeof(double);
+  expm::forward_kernel<<<1, ((n * n + 31) / 32) * 32, smem, reinterpret_cast<cudaStream_t>(stream)>>>(x, base, n, q);
+  cudaError_t e = cudaGetLastError();
+  PMT_CHECK(e == cudaSuccess, "pmt_orthogonal_forward launch failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+extern "C" int pmt_orthogonal_backward(const float* x, const float* base, const float* d_q, int32_t n, float* d_x, void* stream) {
+  PMT_CHECK(x && d_q && d_x && n >= 1 && n <= expm::MAXN, "pmt_orthogonal_backward: n must be in 1..%d", expm::MAXN);
+  const size_t smem = (size_t)(4 + expm::DEG + expm::SQ) * n * n * sizeof(double);
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(expm::backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  expm::backward_kernel<<<1, ((n * n + 31) / 32) * 32, smem, reinterpret_cast<cudaStream_t>(stream)>>>(x, base, d_q, n, d_x);
+  cudaError_t e = cudaGetLastError();
+  PMT_CHECK(e == cudaSuccess, "pmt_orthogonal_backward launch failed: %s", cudaGetErrorString(e));
+  return 0;
+}

@@ -32,6 +32,36 @@ def _owner_and_attr(model, name: str):
     return module, attr
 
 
+_ROTATION_KERNEL_MAX_N = 16
+
+
+class _RotationFunction(torch.autograd.Function):
+    """Q = base @ exp(tril(X) - tril(X)^T) and its vector-Jacobian product as single-CTA kernels (csrc/pmt_optim.cu),
+    same scaling-and-squaring recipe as the torch formulation below."""
+
+    @staticmethod
+    def forward(ctx, X, base):
+        lib = L.load()
+        Xc = X.detach().contiguous()
+        bc = None if base is None else base.detach().contiguous()
+        Q = torch.empty_like(Xc)
+        L.check(lib.pmt_orthogonal_forward(Xc.data_ptr(), None if bc is None else bc.data_ptr(), Xc.shape[0], Q.data_ptr(),
+                                           torch.cuda.current_stream(Xc.device).cuda_stream))
+        ctx.save_for_backward(Xc, bc if bc is not None else Xc.new_empty(0))
+        ctx.has_base = bc is not None
+        return Q
+
+    @staticmethod
+    def backward(ctx, dQ):
+        Xc, bc = ctx.saved_tensors
+        lib = L.load()
+        dQ = dQ.contiguous().float()
+        dX = torch.empty_like(Xc)
+        L.check(lib.pmt_orthogonal_backward(Xc.data_ptr(), bc.data_ptr() if ctx.has_base else None, dQ.data_ptr(), Xc.shape[0],
+                                            dX.data_ptr(), torch.cuda.current_stream(Xc.device).cuda_stream))
+        return dX, None
+
+
 def _orthogonal_without_sync(module, attr):
     """The rotation matrix of torch's ``orthogonal`` parametrisation (matrix-exponential map, square weight) evaluated
     without ``torch.matrix_exp``: that routine picks its Pade degree from a norm it reads back on the host, i.e. it
@@ -48,6 +78,9 @@ def _orthogonal_without_sync(module, attr):
     X = plist.original
     if X.dim() != 2 or X.shape[0] != X.shape[1]:
         return None
+    base = getattr(orth, "base", None)
+    if X.is_cuda and X.dtype == torch.float32 and X.shape[0] <= _ROTATION_KERNEL_MAX_N and (base is None or base.dtype == torch.float32):
+        return _RotationFunction.apply(X, base)          # pmt_orthogonal_forward / _backward: two launches instead of ~135 ops
     Xl = X.double().tril()
     A = Xl - Xl.mT
     n = A.shape[0]
@@ -132,13 +165,122 @@ class _FlatMaterialize(torch.autograd.Function):
         return (None, None, *grads)
 
 
+class _ConstraintPack:
+    """The parametrised tensors of a model grouped by constraint, as positions in the optimiser's flat buffer, so that
+    their values and Jacobians are a dozen batched tensor ops instead of 12 module-property evaluations and their autograd
+    chains (≈1.5 ms of host time per training step).  ``rotation``: the one tensor that stays on autograd (matrix
+    exponential).  ``ok`` is False when a parametrisation other than the reference's five is present."""
+
+    def __init__(self, model, opt):
+        recipe = _materialization_recipe(model)
+        dev = opt.flat.device
+        exp_idx, bnd_idx, bnd_size, bnd_min = [], [], [], []
+        self.units, self.logws, self.rotation, self.ok = [], [], None, True
+        for i in constrained_parameter_indices(model):
+            p, module, attr = recipe[i]
+            off, n = opt._offsets[i], opt._sizes[i]
+            plist = getattr(module.parametrizations, attr)
+            kind = type(plist[0]).__name__ if len(plist) == 1 else "?"
+            if kind == "PositiveNumber":
+                exp_idx.append(torch.arange(off, off + n))
+            elif kind == "BoundedNumber":
+                bnd_idx.append(torch.arange(off, off + n))
+                bnd_size.append(torch.full((n,), float(plist[0].size)))
+                bnd_min.append(torch.full((n,), float(plist[0].min_val)))
+            elif kind == "UnitVector" and p.dim() == 2:
+                self.units.append((off, p.shape[0], p.shape[1], attr == "artifact_directions_ke"))
+            elif kind == "LogWeights" and p.dim() == 1:
+                self.logws.append((off, n))
+            elif kind == "_Orthogonal" and self.rotation is None:
+                self.rotation = (i, module, attr, off, n)
+            else:
+                self.ok = False
+        cat = lambda xs, dt=torch.long: torch.cat(xs).to(dev) if xs else torch.zeros(0, dtype=dt, device=dev)
+        self.exp_idx, self.bnd_idx = cat(exp_idx), cat(bnd_idx)
+        self.bnd_size, self.bnd_min = cat(bnd_size, torch.float32), cat(bnd_min, torch.float32)
+
+
+class _FastMaterialize(torch.autograd.Function):
+    """_FlatMaterialize with the constraint Jacobians of parameterizations.py written out (PositiveNumber: exp;
+    BoundedNumber: size * sigmoid + min; UnitVector: x / |x|, applied twice for the cluster directions, quirk Q5;
+    LogWeights: log_softmax); only the rotation matrix is an autograd input."""
+
+    @staticmethod
+    def forward(ctx, opt, pack, anchor, rot_q):
+        raw = opt.flat.detach()
+        w = raw.clone()
+        e = torch.exp(raw[pack.exp_idx])
+        w[pack.exp_idx] = e
+        sg = torch.sigmoid(raw[pack.bnd_idx])
+        w[pack.bnd_idx] = pack.bnd_size * sg + pack.bnd_min
+        units = []
+        for off, k, d, twice in pack.units:
+            x = raw[off:off + k * d].view(k, d)
+            n1 = torch.norm(x, dim=-1, keepdim=True)
+            u = x / n1
+            if twice:
+                n2 = torch.norm(u, dim=-1, keepdim=True)
+                u2 = u / n2
+            else:
+                n2, u2 = None, u
+            w[off:off + k * d] = u2.reshape(-1)
+            units.append((n1, u, n2, u2))
+        lws = []
+        for off, n in pack.logws:
+            lw = torch.log_softmax(raw[off:off + n], dim=-1)
+            w[off:off + n] = lw
+            lws.append(lw)
+        if pack.rotation is not None:
+            _, _, _, off, n = pack.rotation
+            w[off:off + n] = rot_q.detach().reshape(-1)
+        ctx.opt, ctx.pack, ctx.saved_small = opt, pack, (e, sg, units, lws)
+        ctx.rot_shape = None if rot_q is None else rot_q.shape
+        return w
+
+    @staticmethod
+    def backward(ctx, d_flat):
+        opt, pack = ctx.opt, ctx.pack
+        e, sg, units, lws = ctx.saved_small
+        g = d_flat.clone()
+        g[pack.exp_idx] = d_flat[pack.exp_idx] * e
+        g[pack.bnd_idx] = d_flat[pack.bnd_idx] * pack.bnd_size * sg * (1 - sg)
+        for (off, k, d, twice), (n1, u, n2, u2) in zip(pack.units, units):
+            gu = d_flat[off:off + k * d].view(k, d)
+            if twice:
+                gu = (gu - u2 * (u2 * gu).sum(-1, keepdim=True)) / n2
+            gx = (gu - u * (u * gu).sum(-1, keepdim=True)) / n1
+            g[off:off + k * d] = gx.reshape(-1)
+        for (off, n), lw in zip(pack.logws, lws):
+            gl = d_flat[off:off + n]
+            g[off:off + n] = gl - torch.exp(lw) * gl.sum()
+        d_rot = None
+        if pack.rotation is not None:
+            _, _, _, off, n = pack.rotation
+            d_rot = d_flat[off:off + n].view(ctx.rot_shape)
+        opt.receive_flat_gradient(g)
+        return None, None, None, d_rot
+
+
 def materialize_flat(model, opt) -> torch.Tensor:
     """The training-time fast path of ``ArtifactModel.flat_weights`` when a FlatAdamW backs the parameters."""
-    recipe = _materialization_recipe(model)
-    constrained = [_constrained_value(recipe[i][1], recipe[i][2]) for i in opt._constrained]
+    pack = getattr(opt, "_constraint_pack", None)
+    if pack is None:
+        pack = opt._constraint_pack = _ConstraintPack(model, opt)
     anchor = getattr(opt, "_anchor", None)
     if anchor is None:
         anchor = opt._anchor = torch.zeros((), device=opt.flat.device, requires_grad=True)   # keeps the node in the graph
+    recipe = _materialization_recipe(model)
+    if pack.ok:
+        rot_q = None
+        if pack.rotation is not None:
+            rot_q = _constrained_value(pack.rotation[1], pack.rotation[2])
+        if getattr(pack, "installed", None) is not opt:      # from now on only the rotation's gradient arrives through autograd
+            opt._constrained = [] if pack.rotation is None else [pack.rotation[0]]
+            opt._constrained_index = None if pack.rotation is None else torch.arange(
+                pack.rotation[3], pack.rotation[3] + pack.rotation[4], device=opt.flat.device)
+            pack.installed = opt
+        return _FastMaterialize.apply(opt, pack, anchor, rot_q)
+    constrained = [_constrained_value(recipe[i][1], recipe[i][2]) for i in opt._constrained]
     return _FlatMaterialize.apply(opt, anchor, *constrained)
 
 

@@ -106,3 +106,29 @@ def test_flat_gradient_path_equals_per_parameter_path():
         step(ma, opts[0]); step(mb, opts[1])
         compare(f"calibration step {i}")
     assert torch.equal(frozen_before, ma.read_embedding._model[0].weight.detach())
+
+
+def test_rotation_kernels_match_the_torch_formulation():
+    """pmt_orthogonal_forward / _backward against the float64 scaling-and-squaring written with torch ops (itself checked
+    against the reference's orthogonal parametrisation by the golden fixtures), with and without a base matrix."""
+    from permutect_b200.engine import plan as planner
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(4)
+    for n in (1, 3, 10, 16):
+        for with_base in (False, True):
+            X = (torch.randn((n, n), generator=gen) * 1.5).to(dev).requires_grad_(True)
+            base = None
+            if with_base:
+                base = torch.linalg.qr(torch.randn((n, n), generator=gen))[0].to(dev)
+            Q = planner._RotationFunction.apply(X, base)
+            Xl = X.detach().double().tril().requires_grad_(True)
+            A = Xl - Xl.mT
+            want = torch.matrix_exp(A)
+            if with_base:
+                want = base.double() @ want
+            torch.testing.assert_close(Q.double(), want.detach(), rtol=1e-5, atol=2e-6)
+            torch.testing.assert_close((Q @ Q.mT).cpu(), torch.eye(n), rtol=0, atol=1e-5)
+            dQ = torch.randn((n, n), generator=gen).to(dev)
+            Q.backward(dQ)
+            want.backward(dQ.double())
+            torch.testing.assert_close(X.grad.double(), Xl.grad.tril(), rtol=1e-4, atol=1e-5)
