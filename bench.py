@@ -482,9 +482,11 @@ def main():
     if not args.no_train:
         train = run_training(args, model, ia, fa, reads, dev, world, barrier)
 
-    panel = None
+    panel, small_batch = None, None
     if args.panel_variants > 0 and not args.no_train:
         panel = run_panel(args, model, dev, world, rank, barrier)
+        small_batch = run_small_batch_training(model, dev)     # every rank: the optimiser step all-reduces the gradient
+        barrier()
 
     if rank != 0:
         if world > 1:
@@ -537,7 +539,7 @@ def main():
     if panel is not None:
         result["panel"] = panel
         result["posterior"] = run_posterior(args.variants, dev)
-        result["train"]["small_batch"] = run_small_batch_training(model, dev)
+        result["train"]["small_batch"] = small_batch
     if not args.no_cpu_baseline:
         sample = 8192
         v, n_it = time_oracle(model.state_dict(), sample, seed=3000, budget_s=15.0)
