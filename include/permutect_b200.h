@@ -164,7 +164,8 @@ int pmt_forward_prepared(const PmtModelDesc* desc, const float* weights, const P
                          void* workspace, size_t workspace_bytes, void* stream);
 
 /* Backward of pmt_forward (autograd of artifact_model.py:239-297): accumulates nothing, WRITES
- * d_weights[n_params] (gradient w.r.t. the materialised flat weights). */
+ * d_weights[n_params] (gradient w.r.t. the materialised flat weights).  Read sets of any length: sets longer than a
+ * tile (PMT_TILE_ROWS rows) are walked in chunks, like the forward.  Bitwise reproducible from run to run. */
 int pmt_backward(const PmtModelDesc* desc, const float* weights, const PmtBatch* batch, const PmtOutGrads* grads,
                  float* d_weights, void* workspace, size_t workspace_bytes, void* stream);
 
