@@ -325,6 +325,21 @@ int pmt_posterior_log_posteriors(const PmtPosteriorDesc* desc, const float* para
                                  int64_t int_stride, const void* float_array, int32_t float_kind, int64_t float_stride,
                                  int32_t n_variants, const PmtPosteriorOutputs* out, void* stream);
 
+/* One E step of PosteriorModel.learn_priors_and_spectra (posterior_model.py:131-151) over a batch: loss_out[1] =
+ * -mean_b logsumexp_c log_posteriors_bc; grads_out[2K + 70] = its gradient w.r.t. the CONSTRAINED spectra tensors in
+ * the order cf_k[K], log_weights_k[K], artifact alpha_dv[3][5], beta_dv[3][5], normal-artifact alpha_dv[3][5],
+ * beta_dv[3][5], mean_multiplier_v[5], concentration_v[5] (the caller chains the parametrisations);
+ * posterior_totals_tc[5][5] += sum of the posteriors by variant type (:143), somatic_snv_totals_rrra /
+ * snv_context_totals_rrra [5][5][5][5] += the SNV context totals (posterior_model_priors.py:105-119).  Any output may be
+ * NULL.  Loss, gradients and posterior_totals_tc are summed in a fixed order (bitwise reproducible); the context totals
+ * use atomics. */
+size_t pmt_posterior_fit_workspace_size(int32_t n_variants, int32_t n_components);
+int pmt_posterior_fit_step(const PmtPosteriorDesc* desc, const float* params, const int16_t* int_array,
+                           int64_t int_stride, const void* float_array, int32_t float_kind, int64_t float_stride,
+                           int32_t n_variants, float* loss_out, float* grads_out, float* posterior_totals_tc,
+                           float* somatic_snv_totals_rrra, float* snv_context_totals_rrra, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
 /* ---- batch assembly from the dataset memory maps ----------------------------------------------------
  * Replaces the row re-stacking of Batch.__init__ (batch.py:41-62) for batches cut from a MemoryMappedData
  * (memory_mapped_data.py:36-58, reads_dataset.py:109-196): the reads memory map holds, variant after variant, the ref

@@ -44,7 +44,7 @@ def uniform_binomial_log_lk(n, k, x1, x2):                                     #
 
 def constrained(sd: Dict[str, Tensor]) -> Dict[str, Tensor]:
     """The tensors the reference's forward sees: parametrisations applied (parameterizations.py)."""
-    g = lambda k: torch.as_tensor(np.asarray(sd[k]), dtype=torch.float32)
+    g = lambda k: sd[k].float() if isinstance(sd[k], Tensor) else torch.as_tensor(np.asarray(sd[k]), dtype=torch.float32)
     s = "spectra."
     return dict(
         cf_k=torch.sigmoid(g(s + "somatic_spectrum.parametrizations.cf_k.original")),                  # BoundedNumber(0, 1)
@@ -84,7 +84,40 @@ def germline_log_likelihood(afs, mafs, alt, depths, het_beta):                  
 
 def log_posterior_and_ingredients(sd, int_array: np.ndarray, float_array: np.ndarray, no_germline_mode: bool = False,
                                   het_beta=None, use_context_dependent_snv_priors: bool = True):
-    P = constrained(sd)
+    return tables(constrained(sd), int_array, float_array, no_germline_mode, het_beta, use_context_dependent_snv_priors)
+
+
+SPECTRA_RAW = {"cf_k": "spectra.somatic_spectrum.parametrizations.cf_k.original",
+               "log_weights_k": "spectra.somatic_spectrum.parametrizations.log_weights_k.original",
+               "art_alpha_dv": "spectra.artifact_spectra.parametrizations.alpha_dv.original",
+               "art_beta_dv": "spectra.artifact_spectra.parametrizations.beta_dv.original",
+               "na_alpha_dv": "spectra.normal_artifact_spectra.normal_spectrum.parametrizations.alpha_dv.original",
+               "na_beta_dv": "spectra.normal_artifact_spectra.normal_spectrum.parametrizations.beta_dv.original",
+               "na_mean_mult_v": "spectra.normal_artifact_spectra.parametrizations.mean_multiplier_v.original",
+               "na_conc_v": "spectra.normal_artifact_spectra.parametrizations.concentration_v.original"}
+
+
+def negative_log_evidence_and_grads(sd, int_array, float_array, no_germline_mode=False, het_beta=None,
+                                    use_context_dependent_snv_priors=True):
+    """The loss of learn_priors_and_spectra (posterior_model.py:139-146: -mean logsumexp of the log posteriors) with its
+    gradients by autograd through this restatement: (loss, d/d constrained tensor, d/d raw parameter = what
+    ``loss.backward()`` leaves in ``.grad`` of the spectra parameters)."""
+    leaf = {k: (torch.as_tensor(np.asarray(v), dtype=torch.float32).clone().requires_grad_(k in SPECTRA_RAW.values())
+                if not isinstance(v, Tensor) else v.detach().float().clone().requires_grad_(k in SPECTRA_RAW.values()))
+            for k, v in sd.items()}
+    P = constrained(leaf)
+    for k in SPECTRA_RAW:
+        P[k].retain_grad()
+    out = tables(P, int_array, float_array, no_germline_mode, het_beta, use_context_dependent_snv_priors)
+    loss = -torch.mean(torch.logsumexp(out["log_posteriors_bc"], dim=1))
+    loss.backward()
+    zero = lambda t: torch.zeros_like(t)
+    return (loss.detach(), {k: (P[k].grad if P[k].grad is not None else zero(P[k])) for k in SPECTRA_RAW},
+            {raw: (leaf[raw].grad if leaf[raw].grad is not None else zero(leaf[raw])) for raw in SPECTRA_RAW.values()})
+
+
+def tables(P, int_array: np.ndarray, float_array: np.ndarray, no_germline_mode: bool = False,
+           het_beta=None, use_context_dependent_snv_priors: bool = True):
     it = torch.as_tensor(np.asarray(int_array)).long()
     ft = torch.as_tensor(np.asarray(float_array), dtype=torch.float32)
     B = len(it)
@@ -108,37 +141,36 @@ def log_posterior_and_ingredients(sd, int_array: np.ndarray, float_array: np.nda
     pri = torch.log_softmax(pri, dim=-1)
 
     # ---- spectra (posterior_model_spectra.py:78-124) ----
-    spec = torch.zeros((B, 5))
+    spec_cols = [None] * 5
     mafs_bk = torch.clamp(maf, max=0.49).view(-1, 1)
     cf = P["cf_k"].view(1, -1)
     ub = uniform_binomial_log_lk(depth.view(-1, 1).expand(-1, cf.shape[1]), alt.view(-1, 1).expand(-1, cf.shape[1]),
                                  mafs_bk * cf, (1 - mafs_bk) * cf)
     non_bg = torch.logsumexp(P["log_weights_k"].view(1, -1) + ub, dim=-1)
     bg = beta_binomial_log_lk(depth, alt, P["bg_alpha"], P["bg_beta"])
-    spec[:, SOMATIC] = torch.logaddexp(P["log_non_bg"] + non_bg, P["log_bg"] + bg)          # math_utils.add_in_log_space
+    spec_cols[SOMATIC] = torch.logaddexp(P["log_non_bg"] + non_bg, P["log_bg"] + bg)          # math_utils.add_in_log_space
     db = depth_bins(depth)
-    spec[:, ARTIFACT] = beta_binomial_log_lk(depth, alt, P["art_alpha_dv"][db, vt], P["art_beta_dv"][db, vt])
+    spec_cols[ARTIFACT] = beta_binomial_log_lk(depth, alt, P["art_alpha_dv"][db, vt], P["art_beta_dv"][db, vt])
     ndb = depth_bins(ndepth)
     na_normal = beta_binomial_log_lk(ndepth, nalt, P["na_alpha_dv"][ndb, vt], P["na_beta_dv"][ndb, vt])
     conc = P["na_conc_v"][vt]
     a_b = 0.001 + (nalt / (ndepth + 0.001)) * P["na_mean_mult_v"][vt] * conc
     b_b = torch.clamp(conc - a_b, min=0.001)
-    spec[:, NORMAL_ARTIFACT] = beta_binomial_log_lk(depth, alt, a_b, b_b)
-    spec[:, SEQ_ERROR] = ft[:, FIDX["SEQ_ERROR_LOG_LK"]]
-    spec[:, GERMLINE] = germline_log_likelihood(af, maf, alt, depth, het_beta)
+    spec_cols[NORMAL_ARTIFACT] = beta_binomial_log_lk(depth, alt, a_b, b_b)
+    spec_cols[SEQ_ERROR] = ft[:, FIDX["SEQ_ERROR_LOG_LK"]]
+    spec_cols[GERMLINE] = germline_log_likelihood(af, maf, alt, depth, het_beta)
+    spec = torch.stack(spec_cols, dim=1)          # (the reference fills a zeros tensor column by column: same values)
 
     nse = ft[:, FIDX["NORMAL_SEQ_ERROR_LOG_LK"]]
-    norm = torch.zeros((B, 5))
-    norm[:, SOMATIC] = nse
-    norm[:, ARTIFACT] = nse
-    norm[:, SEQ_ERROR] = nse
-    norm[:, NORMAL_ARTIFACT] = torch.where(nalt < 1, torch.tensor(-9999.0), na_normal)
-    norm[:, GERMLINE] = germline_log_likelihood(af, nmaf, nalt, ndepth, het_beta)
+    norm_cols = [nse, nse, nse, germline_log_likelihood(af, nmaf, nalt, ndepth, het_beta),
+                 torch.where(nalt < 1, torch.tensor(-9999.0), na_normal)]
+    norm = torch.stack(norm_cols, dim=1)
 
-    post = pri + spec + norm
-    post[:, ARTIFACT] += logit
-    post[:, NORMAL_ARTIFACT] += logit
-    post[:, ARTIFACT] = torch.where(logit < 0, torch.tensor(-9999.0), post[:, ARTIFACT])      # posterior_model.py:90-93
+    post_cols = list((pri + spec + norm).unbind(dim=1))
+    post_cols[ARTIFACT] = post_cols[ARTIFACT] + logit
+    post_cols[NORMAL_ARTIFACT] = post_cols[NORMAL_ARTIFACT] + logit
+    post_cols[ARTIFACT] = torch.where(logit < 0, torch.tensor(-9999.0), post_cols[ARTIFACT])  # posterior_model.py:90-93
+    post = torch.stack(post_cols, dim=1)
     return dict(log_priors_bc=pri, spectra_log_lks_bc=spec, normal_log_lks_bc=norm, log_posteriors_bc=post,
                 posterior_probabilities_bc=torch.softmax(post, dim=1),
                 error_probabilities_b=1 - torch.softmax(post, dim=1)[:, SOMATIC])

@@ -4,8 +4,11 @@ libpermutect_b200: same module tree, parameter names, parametrisations and state
 posterior model fitted by the reference loads here and ``log_posterior_and_ingredients`` /
 ``posterior_probabilities_bc`` / ``error_probabilities_b`` are one kernel launch (pmt_posterior_log_posteriors).
 
-Not here: ``learn_priors_and_spectra`` (SGD on the spectra + the PyMC M step of the priors,
-posterior_model_priors.py:141-215) and ``calculate_probability_thresholds`` (plotting).  There is no CPU path.
+``learn_priors_and_spectra`` (posterior_model.py:101-165) runs its E step -- negative log evidence, its gradient w.r.t.
+the spectra, the posterior totals -- as pmt_posterior_fit_step and the optimiser / M step on the host, with one
+difference: the reference's context-dependent SNV prior M step is a PyMC ADVI fit (posterior_model_priors.py:157-203),
+which is not reproduced, so the fit runs with context-independent priors throughout (the reference does so for the
+first half of its iterations).  ``calculate_probability_thresholds`` (plotting) is not here.  There is no CPU path.
 """
 import ctypes as C
 from typing import Optional, Tuple
@@ -122,7 +125,7 @@ class PosteriorModel(nn.Module):
         assert flat.numel() == L.load().pmt_posterior_param_count(s.K)
         return flat
 
-    def _run(self, batch, want: Tuple[str, ...]):
+    def _inputs(self, batch):
         it, ft = batch.int_tensor, batch.float_tensor
         if it.device.type != "cuda" or ft.device != it.device:
             raise RuntimeError("PosteriorModel computes on CUDA devices only (no CPU fallback): move the batch to the GPU")
@@ -131,15 +134,18 @@ class PosteriorModel(nn.Module):
         if ft.dtype not in (torch.float16, torch.float32):
             ft = ft.to(torch.float32)
         it, ft = it.contiguous(), ft.contiguous()
+        desc = L.PmtPosteriorDesc(self.spectra.somatic_spectrum.K, HAPLOTYPES_START_IDX, (it.shape[1] - HAPLOTYPES_START_IDX) // 2,
+                                  int(self.no_germline_mode), int(self.priors.use_context_dependent_snv_priors),
+                                  -1.0 if self.het_beta is None else float(self.het_beta))
+        return it, ft, desc, self.flat_parameters().to(it.device)
+
+    def _run(self, batch, want: Tuple[str, ...]):
+        it, ft, desc, flat = self._inputs(batch)
         B = it.shape[0]
-        flat = self.flat_parameters().to(it.device)
         outs = {k: torch.empty((B, NUM_CALLS), dtype=torch.float32, device=it.device) for k in want}
         po = L.PmtPosteriorOutputs(*[outs[k].data_ptr() if k in outs else None for k in
                                      ("log_priors_bc", "spectra_log_lks_bc", "normal_log_lks_bc", "log_posteriors_bc",
                                       "posterior_probabilities_bc")])
-        desc = L.PmtPosteriorDesc(self.spectra.somatic_spectrum.K, HAPLOTYPES_START_IDX, (it.shape[1] - HAPLOTYPES_START_IDX) // 2,
-                                  int(self.no_germline_mode), int(self.priors.use_context_dependent_snv_priors),
-                                  -1.0 if self.het_beta is None else float(self.het_beta))
         lib = L.load()
         L.check(lib.pmt_posterior_log_posteriors(C.byref(desc), flat.data_ptr(), it.data_ptr(), it.stride(0), ft.data_ptr(),
                                                  L.F16 if ft.dtype == torch.float16 else L.F32, ft.stride(0), B, C.byref(po),
@@ -161,9 +167,91 @@ class PosteriorModel(nn.Module):
         assert not (germline_mode and self.no_germline_mode), "germline mode and no-germline mode are incompatible"
         return 1 - self.posterior_probabilities_bc(batch)[:, CALL_GERMLINE if germline_mode else CALL_SOMATIC]
 
-    def learn_priors_and_spectra(self, *args, **kwargs):
-        raise NotImplementedError("fitting the posterior model (posterior_model.py:101-165) is not part of this repository yet; "
-                                  "fit with the reference and load the state dict here")
+    # ---- fitting (posterior_model.py:101-165) -------------------------------------------------------------
+    def _spectra_tensors(self):
+        s, na = self.spectra.somatic_spectrum, self.spectra.normal_artifact_spectra
+        return [s.cf_k, s.log_weights_k, self.spectra.artifact_spectra.alpha_dv, self.spectra.artifact_spectra.beta_dv,
+                na.normal_spectrum.alpha_dv, na.normal_spectrum.beta_dv, na.mean_multiplier_v, na.concentration_v]
+
+    def negative_log_evidence(self, batch, posterior_totals_tc: Optional[Tensor] = None, somatic_snv_totals_rrra: Optional[Tensor] = None,
+                              snv_context_totals_rrra: Optional[Tensor] = None) -> Tensor:
+        """The E-step loss -mean(logsumexp(log_relative_posteriors_bc)) of :139-146 as a scalar that ``backward()`` turns
+        into the same ``.grad`` of the spectra parameters as the reference's autograd; the optional buffers receive the
+        E-step totals (+=) as :131-143 accumulates them."""
+        it, ft, desc, flat = self._inputs(batch)
+        dev = it.device
+        lib = L.load()
+        K = desc.n_components
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        grads = torch.empty(2 * K + 70, dtype=torch.float32, device=dev)
+        ws = torch.empty(int(lib.pmt_posterior_fit_workspace_size(it.shape[0], K)), dtype=torch.uint8, device=dev)
+        ptr = lambda t: None if t is None else t.data_ptr()
+        for t in (posterior_totals_tc, somatic_snv_totals_rrra, snv_context_totals_rrra):
+            assert t is None or (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous())
+        L.check(lib.pmt_posterior_fit_step(C.byref(desc), flat.data_ptr(), it.data_ptr(), it.stride(0), ft.data_ptr(),
+                                           L.F16 if ft.dtype == torch.float16 else L.F32, ft.stride(0), it.shape[0], loss.data_ptr(),
+                                           grads.data_ptr(), ptr(posterior_totals_tc), ptr(somatic_snv_totals_rrra),
+                                           ptr(snv_context_totals_rrra), ws.data_ptr(), ws.numel(),
+                                           torch.cuda.current_stream(dev).cuda_stream))
+        return _EvidenceLoss.apply(loss, grads, *self._spectra_tensors())
+
+    def update_priors_m_step(self, posterior_totals_vc: Tensor, ignored_to_non_ignored_ratio: float):
+        """posterior_model_priors.py:141-155 and the context-independent branch :204-206."""
+        total_nonignored = torch.sum(posterior_totals_vc)
+        overall_total = (1 + ignored_to_non_ignored_ratio) * total_nonignored
+        with torch.no_grad():
+            pri = self.priors
+            pri.log_priors_vc.copy_(torch.log(posterior_totals_vc / (posterior_totals_vc + overall_total)))
+            pri.log_priors_vc[:, CALL_SEQ_ERROR] = 0
+            pri.log_priors_vc[:, CALL_GERMLINE] = -9999 if self.no_germline_mode else 0
+            pri.somatic_snv_log_priors_rrra.fill_(pri.log_priors_vc[int(Variation.SNV), CALL_SOMATIC])
+
+    def learn_priors_and_spectra(self, posterior_loader, num_iterations, ignored_to_non_ignored_ratio: float, summary_writer=None,
+                                 learning_rate: float = 0.001):
+        """posterior_model.py:101-165 with context-independent SNV priors throughout (module docstring).  ``posterior_loader``
+        yields batches of posterior records on the model's device.  Returns the mean loss of every iteration."""
+        optimizer = torch.optim.Adam(self.spectra.parameters(), lr=learning_rate)
+        self.priors.disable_context_dependent_snv_priors()
+        history = []
+        for epoch in range(1, num_iterations + 1):
+            totals_tc = torch.zeros((len(Variation), NUM_CALLS), device=self._device)
+            somatic_snv_rrra = torch.zeros((5, 5, 5, 5), device=self._device)
+            snv_context_rrra = torch.zeros((5, 5, 5, 5), device=self._device)
+            loss_sum = torch.zeros((), device=self._device)
+            count = 0
+            for batch in posterior_loader:
+                loss = self.negative_log_evidence(batch, totals_tc, somatic_snv_rrra, snv_context_rrra)
+                optimizer.zero_grad(set_to_none=True)          # misc_utils.backpropagate (:125-129) without parameters to clip
+                loss.backward()
+                optimizer.step()
+                loss_sum += loss.detach() * batch.size()
+                count += batch.size()
+            self.update_priors_m_step(totals_tc, ignored_to_non_ignored_ratio)
+            history.append(float(loss_sum) / max(count, 1))
+            if summary_writer is not None:
+                summary_writer.add_scalar("spectrum negative log evidence", history[-1], epoch)
+        return history
+
+
+class _EvidenceLoss(torch.autograd.Function):
+    """Connects the kernel's loss and its gradient w.r.t. the constrained spectra tensors to autograd, which chains the
+    parametrisations (sigmoid / exp / log_softmax) down to the raw parameters."""
+
+    @staticmethod
+    def forward(ctx, loss, grads, *tensors):
+        ctx.save_for_backward(grads)
+        ctx.shapes = [t.shape for t in tensors]
+        return loss.clone()
+
+    @staticmethod
+    def backward(ctx, d_loss):
+        (grads,) = ctx.saved_tensors
+        out, off = [], 0
+        for shape in ctx.shapes:
+            n = int(torch.Size(shape).numel())
+            out.append(d_loss * grads[off:off + n].view(shape))
+            off += n
+        return (None, None, *out)
 
 
 class PosteriorBatch:

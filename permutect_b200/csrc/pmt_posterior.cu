@@ -27,6 +27,30 @@ struct Online {   // streaming logsumexp
   __device__ __forceinline__ float value() const { return m + logf(s); }
 };
 
+struct OnlineD {   // streaming logsumexp that also carries sum_j softmax_j * q_j (q_j: a derivative attached to term j)
+  float m = -INFINITY, s = 0.f, d = 0.f;
+  __device__ __forceinline__ void add(float v, float q) {
+    if (v > m) { const float sc = expf(m - v); s = s * sc + 1.f; d = d * sc + q; m = v; }
+    else { const float e = expf(v - m); s += e; d += e * q; }
+  }
+  __device__ __forceinline__ float value() const { return m + logf(s); }
+  __device__ __forceinline__ float mean_q() const { return d / s; }
+};
+
+// digamma for x > 0: recurrence up to x >= 6, then the asymptotic series
+__device__ __forceinline__ float digammaf(float x) {
+  float r = 0.f;
+  while (x < 6.f) { r -= 1.f / x; x += 1.f; }
+  const float i = 1.f / x, i2 = i * i;
+  return r + logf(x) - 0.5f * i - i2 * (1.f / 12.f - i2 * (1.f / 120.f - i2 * (1.f / 252.f)));
+}
+// d beta_binomial / d alpha, d beta (stats_utils.py:29-41)
+__device__ __forceinline__ void beta_binomial_grads(float n, float k, float a, float b, float& ga, float& gb) {
+  const float common = digammaf(a + b) - digammaf(n + a + b);
+  ga = digammaf(k + a) + common - digammaf(a);
+  gb = digammaf(n - k + b) + common - digammaf(b);
+}
+
 __device__ __forceinline__ float comb_term(float n, float k) { return lgammaf(n + 1.f) - lgammaf(n - k + 1.f) - lgammaf(k + 1.f); }
 // stats_utils.py:29-41
 __device__ __forceinline__ float beta_binomial(float n, float k, float comb, float a, float b) {
@@ -58,10 +82,30 @@ __device__ __forceinline__ float load_float(const void* p, int kind, long long i
   return kind == PMT_F16 ? __half2float(reinterpret_cast<const __half*>(p)[i]) : reinterpret_cast<const float*>(p)[i];
 }
 
-__global__ void __launch_bounds__(128)
+constexpr int THREADS = 128, WARPS = THREADS / 32;
+constexpr int MAXK = PMT_POSTERIOR_MAX_COMPONENTS;
+// slots of the fitting pass, per CTA then summed over CTAs in order: loss, d cf_k, d log_weights_k, d artifact alpha / beta
+// [3][5], d normal-artifact alpha / beta [3][5], d mean_multiplier_v, d concentration_v, E-step totals [type][call]
+__host__ __device__ constexpr int slot_count(int K) { return 1 + 2 * K + 4 * N_DEPTH_BINS * N_TYPES + 2 * N_TYPES + N_TYPES * N_CALLS; }
+
+struct FitArgs {
+  float* partials;                 // [n_blocks][slot_count]
+  float* somatic_snv_totals_rrra;  // [5][5][5][5] += posterior(SOMATIC) of SNVs (posterior_model_priors.py:111-119), may be null
+  float* snv_context_totals_rrra;  // [5][5][5][5] += 1 per SNV, may be null
+};
+
+// Deterministic CTA sum of one slot: warp shuffle tree, lane 0 of each warp owns wsum[warp][slot]
+__device__ __forceinline__ void slot_add(float* wsum, int n_slots, int slot, float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) wsum[(threadIdx.x >> 5) * n_slots + slot] += v;
+}
+
+template <bool FIT>
+__global__ void __launch_bounds__(THREADS)
 log_posteriors_kernel(const PmtPosteriorDesc D, const float* __restrict__ P, const int16_t* __restrict__ ints, long long int_stride,
                       const void* __restrict__ floats, int float_kind, long long float_stride, int n_variants,
-                      PmtPosteriorOutputs out) {
+                      PmtPosteriorOutputs out, FitArgs fit) {
   __shared__ float sp[PMT_POSTERIOR_MAX_COMPONENTS * 2 + 4 + 4 * N_DEPTH_BINS * N_TYPES + 2 * N_TYPES + N_TYPES * N_CALLS];
   const int K = D.n_components;
   const int n_small = 2 * K + 4 + 4 * N_DEPTH_BINS * N_TYPES + 2 * N_TYPES + N_TYPES * N_CALLS;
@@ -79,8 +123,16 @@ log_posteriors_kernel(const PmtPosteriorDesc D, const float* __restrict__ P, con
   const float* log_priors_vc = na_conc + N_TYPES;
   const float* snv_rrra = P + n_small;   // [5][5][5][5], global (L1 / L2)
 
-  const int v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= n_variants) return;
+  extern __shared__ float wsum[];   // FIT: [WARPS][slot_count]
+  const int n_slots = slot_count(K);
+  if (FIT) {
+    for (int i = threadIdx.x; i < WARPS * n_slots; i += blockDim.x) wsum[i] = 0.f;
+    __syncthreads();
+  }
+  const int v_raw = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = v_raw < n_variants;
+  if (!FIT && !valid) return;
+  const int v = valid ? v_raw : n_variants - 1;     // FIT: out-of-range threads take part in the reductions with weight 0
   const int16_t* ir = ints + (long long)v * int_stride;
   const long long fo = (long long)v * float_stride;
   int vt = ir[3];
@@ -117,33 +169,40 @@ log_posteriors_kernel(const PmtPosteriorDesc D, const float* __restrict__ P, con
 
   // ---- spectra ----
   float spec[N_CALLS], norm[N_CALLS];
+  float mix_term[FIT ? MAXK : 1], mix_dcf[FIT ? MAXK : 1], non_bg_share = 0.f;
   const float comb = comb_term(depth, alt), ncomb = comb_term(ndepth, nalt);
   {
     const float mafc = fminf(maf, 0.49f);                        // somatic_spectrum.py:78
     Online mix;
     for (int k = 0; k < K; ++k) {
       const float x1 = mafc * cf_k[k], x2 = (1.f - mafc) * cf_k[k];
-      Online u;
+      OnlineD u;
       for (int j = 0; j < N_INTERP; ++j) {
         const float t = 0.001f + 0.01f * (float)j;
         const float p = x2 * t + x1 * (1.f - t);
-        u.add(comb + alt * logf(p) + (depth - alt) * logf(1.f - p));
+        // d/d cf_k of this term: (alt / p - (depth - alt) / (1 - p)) * p / cf_k
+        u.add(comb + alt * logf(p) + (depth - alt) * logf(1.f - p), FIT ? (alt - (depth - alt) * p / (1.f - p)) / cf_k[k] : 0.f);
       }
-      mix.add(logw_k[k] + u.value() - logf((float)N_INTERP));
+      const float term = logw_k[k] + u.value() - logf((float)N_INTERP);
+      mix.add(term);
+      if (FIT) { mix_term[k] = term; mix_dcf[k] = u.mean_q(); }
     }
-    const float a = log_non_bg + mix.value(), b = log_bg + beta_binomial(depth, alt, comb, bg_alpha, bg_beta);
+    const float mixv = mix.value();
+    const float a = log_non_bg + mixv, b = log_bg + beta_binomial(depth, alt, comb, bg_alpha, bg_beta);
     const float m = fmaxf(a, b);
     spec[SOMATIC] = m + logf(expf(a - m) + expf(b - m));
+    if (FIT) {
+      non_bg_share = expf(a - spec[SOMATIC]);
+      for (int k = 0; k < K; ++k) mix_term[k] = expf(mix_term[k] - mixv);     // responsibilities of the components
+    }
   }
   const int db = depth_bin(depth), ndb = depth_bin(ndepth);
   spec[ARTIFACT] = beta_binomial(depth, alt, comb, art_alpha[db * N_TYPES + vt], art_beta[db * N_TYPES + vt]);
   const float na_normal = beta_binomial(ndepth, nalt, ncomb, na_alpha[ndb * N_TYPES + vt], na_beta[ndb * N_TYPES + vt]);
-  {
-    const float conc = na_conc[vt];
-    const float a_b = 0.001f + (nalt / (ndepth + 0.001f)) * na_mult[vt] * conc;
-    const float b_b = fmaxf(conc - a_b, 0.001f);
-    spec[NORMAL_ARTIFACT] = beta_binomial(depth, alt, comb, a_b, b_b);
-  }
+  const float conc = na_conc[vt], naf = nalt / (ndepth + 0.001f);
+  const float a_b = 0.001f + naf * na_mult[vt] * conc;
+  const float b_b = fmaxf(conc - a_b, 0.001f);
+  spec[NORMAL_ARTIFACT] = beta_binomial(depth, alt, comb, a_b, b_b);
   spec[SEQ_ERROR] = seq_err;
   spec[GERMLINE] = germline(af, maf, alt, depth, comb, D.het_beta);
 
@@ -166,6 +225,67 @@ log_posteriors_kernel(const PmtPosteriorDesc D, const float* __restrict__ P, con
     if (out.normal_log_lks_bc) out.normal_log_lks_bc[o + c] = norm[c];
     if (out.log_posteriors_bc) out.log_posteriors_bc[o + c] = post[c];
   }
+  if (FIT) {
+    // ---- E step + gradient of -mean log evidence (posterior_model.py:139-151) ----
+    float pm = post[0];
+#pragma unroll
+    for (int c = 1; c < N_CALLS; ++c) pm = fmaxf(pm, post[c]);
+    float r[N_CALLS], rs = 0.f;
+#pragma unroll
+    for (int c = 0; c < N_CALLS; ++c) { r[c] = expf(post[c] - pm); rs += r[c]; }
+    const float w = valid ? 1.f : 0.f;
+#pragma unroll
+    for (int c = 0; c < N_CALLS; ++c) r[c] = w * r[c] / rs;
+    int slot = 0;
+    slot_add(wsum, n_slots, slot++, w * (pm + logf(rs)));                                  // log evidence
+    const float ws = r[SOMATIC] * non_bg_share;
+    for (int k = 0; k < K; ++k) slot_add(wsum, n_slots, slot + k, ws * mix_term[k] * mix_dcf[k]);
+    slot += K;
+    for (int k = 0; k < K; ++k) slot_add(wsum, n_slots, slot + k, ws * mix_term[k]);
+    slot += K;
+    float ga, gb;
+    beta_binomial_grads(depth, alt, art_alpha[db * N_TYPES + vt], art_beta[db * N_TYPES + vt], ga, gb);
+    const float wa = logit < 0.f ? 0.f : r[ARTIFACT];                                       // the -9999 branch is a constant
+    const int cell = db * N_TYPES + vt, ncell = ndb * N_TYPES + vt;
+    for (int c = 0; c < N_DEPTH_BINS * N_TYPES; ++c) slot_add(wsum, n_slots, slot + c, c == cell ? wa * ga : 0.f);
+    slot += N_DEPTH_BINS * N_TYPES;
+    for (int c = 0; c < N_DEPTH_BINS * N_TYPES; ++c) slot_add(wsum, n_slots, slot + c, c == cell ? wa * gb : 0.f);
+    slot += N_DEPTH_BINS * N_TYPES;
+    const float wn = r[NORMAL_ARTIFACT], wn2 = nalt < 1.f ? 0.f : wn;
+    beta_binomial_grads(ndepth, nalt, na_alpha[ncell], na_beta[ncell], ga, gb);
+    for (int c = 0; c < N_DEPTH_BINS * N_TYPES; ++c) slot_add(wsum, n_slots, slot + c, c == ncell ? wn2 * ga : 0.f);
+    slot += N_DEPTH_BINS * N_TYPES;
+    for (int c = 0; c < N_DEPTH_BINS * N_TYPES; ++c) slot_add(wsum, n_slots, slot + c, c == ncell ? wn2 * gb : 0.f);
+    slot += N_DEPTH_BINS * N_TYPES;
+    beta_binomial_grads(depth, alt, a_b, b_b, ga, gb);
+    const float unclamped = (conc - a_b) > 0.001f ? 1.f : 0.f, mult = na_mult[vt];
+    const float d_mult = ga * naf * conc - gb * unclamped * naf * conc;
+    const float d_conc = ga * naf * mult + gb * unclamped * (1.f - naf * mult);
+    for (int t = 0; t < N_TYPES; ++t) slot_add(wsum, n_slots, slot + t, t == vt ? wn * d_mult : 0.f);
+    slot += N_TYPES;
+    for (int t = 0; t < N_TYPES; ++t) slot_add(wsum, n_slots, slot + t, t == vt ? wn * d_conc : 0.f);
+    slot += N_TYPES;
+    for (int t = 0; t < N_TYPES; ++t)
+#pragma unroll
+      for (int c = 0; c < N_CALLS; ++c) slot_add(wsum, n_slots, slot + t * N_CALLS + c, t == vt ? r[c] : 0.f);
+    if (valid && vt == 0 && (fit.somatic_snv_totals_rrra || fit.snv_context_totals_rrra)) {
+      const int L = D.hap_len, c = (L - 1) / 2;
+      const int16_t* hap = ir + D.hap_start;
+      const int i0 = min(max((int)hap[c - 1], 0), 4), i1 = min(max((int)hap[c], 0), 4), i2 = min(max((int)hap[c + 1], 0), 4),
+                i3 = min(max((int)hap[c + L], 0), 4);
+      const int at = ((i0 * 5 + i1) * 5 + i2) * 5 + i3;
+      if (fit.somatic_snv_totals_rrra) atomicAdd(fit.somatic_snv_totals_rrra + at, r[SOMATIC]);
+      if (fit.snv_context_totals_rrra) atomicAdd(fit.snv_context_totals_rrra + at, 1.f);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_slots; i += blockDim.x) {
+      float t = 0.f;
+#pragma unroll
+      for (int wq = 0; wq < WARPS; ++wq) t += wsum[wq * n_slots + i];
+      fit.partials[(long long)blockIdx.x * n_slots + i] = t;
+    }
+    if (!valid) return;
+  }
   if (out.posterior_probabilities_bc) {
     float m = post[0];
 #pragma unroll
@@ -176,6 +296,18 @@ log_posteriors_kernel(const PmtPosteriorDesc D, const float* __restrict__ P, con
 #pragma unroll
     for (int c = 0; c < N_CALLS; ++c) out.posterior_probabilities_bc[o + c] = e[c] / s;
   }
+}
+
+// Sums the per-CTA slots in CTA order (bitwise reproducible) and applies -1/B to the loss and gradient slots.
+__global__ void fit_reduce_kernel(const float* __restrict__ partials, int n_blocks, int n_slots, int n_grad_slots, float inv_b,
+                                  float* __restrict__ loss_out, float* __restrict__ grads_out, float* __restrict__ totals_tc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_slots) return;
+  float s = 0.f;
+  for (int b = 0; b < n_blocks; ++b) s += partials[(long long)b * n_slots + i];
+  if (i == 0) { if (loss_out) *loss_out = -s * inv_b; }
+  else if (i <= n_grad_slots) { if (grads_out) grads_out[i - 1] = -s * inv_b; }
+  else if (totals_tc) totals_tc[i - 1 - n_grad_slots] += s;
 }
 
 }  // namespace post
@@ -194,9 +326,41 @@ extern "C" int pmt_posterior_log_posteriors(const PmtPosteriorDesc* desc, const 
   PMT_CHECK(!desc->use_context_dependent_snv_priors || desc->hap_len >= 3, "context-dependent SNV priors need haplotypes of >= 3 bases");
   if (n_variants <= 0) return 0;
   const int threads = 128, blocks = (n_variants + threads - 1) / threads;
-  post::log_posteriors_kernel<<<blocks, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      *desc, params, int_array, int_stride, float_array, float_kind, float_stride, n_variants, *out);
+  post::log_posteriors_kernel<false><<<blocks, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      *desc, params, int_array, int_stride, float_array, float_kind, float_stride, n_variants, *out, post::FitArgs{});
   cudaError_t e = cudaGetLastError();
   PMT_CHECK(e == cudaSuccess, "pmt_posterior_log_posteriors launch failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+extern "C" size_t pmt_posterior_fit_workspace_size(int32_t n_variants, int32_t n_components) {
+  const size_t blocks = (size_t)(n_variants + post::THREADS - 1) / post::THREADS;
+  return blocks * post::slot_count(n_components) * sizeof(float) + 256;
+}
+
+extern "C" int pmt_posterior_fit_step(const PmtPosteriorDesc* desc, const float* params, const int16_t* int_array,
+                                      int64_t int_stride, const void* float_array, int32_t float_kind, int64_t float_stride,
+                                      int32_t n_variants, float* loss_out, float* grads_out, float* posterior_totals_tc,
+                                      float* somatic_snv_totals_rrra, float* snv_context_totals_rrra, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
+  PMT_CHECK(desc && params && int_array && float_array && workspace, "pmt_posterior_fit_step: null argument");
+  PMT_CHECK(desc->n_components >= 1 && desc->n_components <= PMT_POSTERIOR_MAX_COMPONENTS, "somatic spectrum components %d outside 1..%d",
+            desc->n_components, PMT_POSTERIOR_MAX_COMPONENTS);
+  PMT_CHECK(float_kind == PMT_F16 || float_kind == PMT_F32, "float_kind must be PMT_F16 or PMT_F32");
+  PMT_CHECK(n_variants > 0, "empty batch");
+  PMT_CHECK(workspace_bytes >= pmt_posterior_fit_workspace_size(n_variants, desc->n_components), "workspace too small");
+  PMT_CHECK((!somatic_snv_totals_rrra && !snv_context_totals_rrra) || desc->hap_len >= 3, "SNV context totals need haplotypes of >= 3 bases");
+  const int K = desc->n_components, n_slots = post::slot_count(K), blocks = (n_variants + post::THREADS - 1) / post::THREADS;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  post::FitArgs fit{reinterpret_cast<float*>(workspace), somatic_snv_totals_rrra, snv_context_totals_rrra};
+  PmtPosteriorOutputs none{};
+  const size_t smem = (size_t)post::WARPS * n_slots * sizeof(float);
+  post::log_posteriors_kernel<true><<<blocks, post::THREADS, smem, st>>>(*desc, params, int_array, int_stride, float_array, float_kind,
+                                                                         float_stride, n_variants, none, fit);
+  const int n_grad = 2 * K + 4 * post::N_DEPTH_BINS * post::N_TYPES + 2 * post::N_TYPES;
+  post::fit_reduce_kernel<<<(n_slots + 127) / 128, 128, 0, st>>>(fit.partials, blocks, n_slots, n_grad, 1.f / (float)n_variants, loss_out,
+                                                                grads_out, posterior_totals_tc);
+  cudaError_t e = cudaGetLastError();
+  PMT_CHECK(e == cudaSuccess, "pmt_posterior_fit_step launch failed: %s", cudaGetErrorString(e));
   return 0;
 }

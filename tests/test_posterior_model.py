@@ -111,3 +111,69 @@ def test_kernel_matches_oracle_on_a_large_random_batch_and_rejects_cpu():
     _assert_tables_close(got, want, ia, "random batch")
     with pytest.raises(RuntimeError, match="CUDA"):
         model.log_relative_posteriors_bc(PosteriorBatch(ia[:4], fa[:4]))
+
+
+def test_gradient_oracle_matches_reference_autograd():
+    """The loss of learn_priors_and_spectra and what its backward leaves in .grad of the spectra parameters
+    (tests/golden/make_posterior_model_golden.py ran them through the unmodified reference)."""
+    z = np.load(GOLDEN)
+    for tag in ("default", "het_beta", "no_germline"):
+        sd, no_germline, het_beta, context = _case(z, tag)
+        loss, _, raw = orc.negative_log_evidence_and_grads(sd, z["int_array"], z["float_array"], no_germline, het_beta, context)
+        np.testing.assert_allclose(float(loss), float(z[f"{tag}/loss"]), rtol=1e-6)
+        for name, g in raw.items():
+            np.testing.assert_allclose(g.numpy(), z[f"{tag}/grad/{name}"], rtol=1e-5, atol=1e-7, err_msg=name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["default", "het_beta", "no_germline"])
+def test_fit_step_matches_reference_loss_gradients_and_totals(tag):
+    from permutect_b200.architecture.posterior_model import PosteriorBatch, PosteriorModel
+    z = np.load(GOLDEN)
+    sd, no_germline, het_beta, context = _case(z, tag)
+    keep = z["int_array"][:, 5] <= 400          # rows whose fp32 lgamma rounding stays below 3e-3 (module docstring)
+    ia, fa = z["int_array"][keep], z["float_array"][keep]
+    dev = torch.device("cuda:0")
+    model = PosteriorModel(-3.0, -4.0, no_germline_mode=no_germline, device=dev, het_beta=het_beta)
+    model.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sd.items()})
+    totals = torch.zeros((5, 5), device=dev)
+    snv = torch.zeros((5, 5, 5, 5), device=dev)
+    ctx = torch.zeros((5, 5, 5, 5), device=dev)
+    loss = model.negative_log_evidence(PosteriorBatch(ia, fa, dev), totals, snv, ctx)
+    loss.backward()
+    want_loss, _, want_raw = orc.negative_log_evidence_and_grads(sd, ia, fa, no_germline, het_beta, context)
+    np.testing.assert_allclose(float(loss.detach()), float(want_loss), rtol=2e-5, atol=2e-4)
+    got = {k: v for k, v in model.named_parameters()}
+    for name, w in want_raw.items():
+        g = got[name].grad.cpu().numpy()
+        scale = max(float(np.abs(w.numpy()).max()), 1e-4)
+        assert np.abs(g - w.numpy()).max() <= 2e-3 * scale + 1e-6, (name, np.abs(g - w.numpy()).max(), scale)
+    post = orc.log_posterior_and_ingredients(sd, ia, fa, no_germline, het_beta, context)["posterior_probabilities_bc"].numpy()
+    want_totals = np.zeros((5, 5))
+    np.add.at(want_totals, ia[:, 3].astype(int), post)
+    np.testing.assert_allclose(totals.cpu().numpy(), want_totals, rtol=1e-3, atol=2e-3)
+    is_snv = ia[:, 3] == 0
+    assert abs(float(ctx.sum()) - is_snv.sum()) < 1e-3 and abs(float(snv.sum()) - post[is_snv, 0].sum()) < 2e-3
+    # reproducible: the fixed-order sums give the same loss and gradients again
+    model.zero_grad()
+    loss2 = model.negative_log_evidence(PosteriorBatch(ia, fa, dev))
+    loss2.backward()
+    assert float(loss2.detach()) == float(loss.detach())
+    for name in want_raw:
+        assert torch.equal(got[name].grad, dict(model.named_parameters())[name].grad)
+
+
+@pytest.mark.gpu
+def test_learn_priors_and_spectra_lowers_the_negative_log_evidence():
+    from permutect_b200.architecture.posterior_model import PosteriorBatch, PosteriorModel
+    z = np.load(GOLDEN)
+    keep = z["int_array"][:, 5] <= 400
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    model = PosteriorModel(-10.0, -10.0, device=dev)
+    batches = [PosteriorBatch(z["int_array"][keep][i::3], z["float_array"][keep][i::3], dev) for i in range(3)]
+    history = model.learn_priors_and_spectra(batches, num_iterations=15, ignored_to_non_ignored_ratio=10.0, learning_rate=0.05)
+    assert len(history) == 15 and np.all(np.isfinite(history)) and history[-1] < history[0]
+    pri = model.priors.log_priors_vc.detach().cpu().numpy()
+    assert np.all(pri[:, 2] == 0) and np.all(pri[:, 3] == 0) and np.all(pri[:, [0, 1, 4]] < 0)
+    assert torch.all(model.priors.somatic_snv_log_priors_rrra == model.priors.log_priors_vc[0, 0])
