@@ -177,3 +177,37 @@ def test_learn_priors_and_spectra_lowers_the_negative_log_evidence():
     pri = model.priors.log_priors_vc.detach().cpu().numpy()
     assert np.all(pri[:, 2] == 0) and np.all(pri[:, 3] == 0) and np.all(pri[:, [0, 1, 4]] < 0)
     assert torch.all(model.priors.somatic_snv_log_priors_rrra == model.priors.log_priors_vc[0, 0])
+
+
+@pytest.mark.gpu
+def test_artifact_model_records_flow_into_the_posterior_model():
+    """filter_variants' chain (tools/filter_variants.py:292-320 then posterior_model.py:58-67): ArtifactModel logits ->
+    posterior records (pmt_pack_posterior) -> error probabilities (pmt_posterior_log_posteriors), against the oracles fed
+    with the same records."""
+    import bench
+    from permutect_b200.architecture.posterior_model import PosteriorBatch, PosteriorModel
+    from permutect_b200.data.batch import Batch
+    from permutect_b200.synthetic import make_wgs_arrays
+    from permutect_b200.tools.filter_variants import generate_posterior_arrays
+    from permutect_b200.utils.enums import Epoch
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(5)
+    ia, fa, reads = make_wgs_arrays(500, seed=21)
+    depth = rng.integers(10, 300, len(ia))
+    ia[:, 5], ia[:, 6] = depth, np.maximum(1, rng.binomial(depth, 0.2))
+    ia[:, 7] = rng.integers(0, 200, len(ia))
+    ia[:, 8] = rng.binomial(ia[:, 7], 0.02)
+    fa[:, 0], fa[:, 1] = -rng.uniform(1, 40, len(ia)), -rng.uniform(0, 5, len(ia))
+    fa[:, 2], fa[:, 3], fa[:, 4] = 10.0 ** rng.uniform(-4, -0.5, len(ia)), rng.uniform(0.1, 0.5, len(ia)), rng.uniform(0.1, 0.5, len(ia))
+    model = bench.make_model(dev)
+    model.set_epoch_type(Epoch.VALID)
+    loader = [Batch.from_arrays(ia[:300], fa[:300], np.concatenate((reads[:ia[:300, 0].sum()],
+                                reads[ia[:, 0].sum():ia[:, 0].sum() + ia[:300, 1].sum()])))]
+    (int_out, float_out), = list(generate_posterior_arrays(loader, model, dev))
+    assert int_out.shape[0] == 300 and float_out.dtype == np.float32
+    pm = PosteriorModel(-10.0, -10.0, device=dev)
+    err = pm.error_probabilities_b(PosteriorBatch(int_out, float_out, dev)).cpu().numpy()
+    sd = {k: v.detach().cpu() for k, v in pm.state_dict().items()}
+    want = orc.log_posterior_and_ingredients(sd, int_out, float_out)["error_probabilities_b"].numpy()
+    np.testing.assert_allclose(err, want, rtol=0, atol=3e-3)
+    assert np.all((err >= 0) & (err <= 1)) and 0.01 < err.mean() < 0.999
