@@ -8,7 +8,8 @@ posterior model fitted by the reference loads here and ``log_posterior_and_ingre
 the spectra, the posterior totals -- as pmt_posterior_fit_step and the optimiser / M step on the host, with one
 difference: the reference's context-dependent SNV prior M step is a PyMC ADVI fit (posterior_model_priors.py:157-203),
 which is not reproduced, so the fit runs with context-independent priors throughout (the reference does so for the
-first half of its iterations).  ``calculate_probability_thresholds`` (plotting) is not here.  There is no CPU path.
+first half of its iterations).  ``calculate_probability_thresholds`` (posterior_model.py:171-264) returns the same thresholds; its ROC plots are not
+drawn.  There is no CPU path for the model itself.
 """
 import ctypes as C
 from typing import Optional, Tuple
@@ -167,6 +168,19 @@ class PosteriorModel(nn.Module):
         assert not (germline_mode and self.no_germline_mode), "germline mode and no-germline mode are incompatible"
         return 1 - self.posterior_probabilities_bc(batch)[:, CALL_GERMLINE if germline_mode else CALL_SOMATIC]
 
+    @torch.no_grad()
+    def calculate_probability_thresholds(self, posterior_loader, summary_writer=None, germline_mode: bool = False,
+                                         recall_weight: float = 1.0):
+        """posterior_model.py:171-264 without the plots: {Variation: error-probability threshold maximising F_beta}."""
+        probs, types = [], []
+        for batch in posterior_loader:
+            probs.append(self.error_probabilities_b(batch, germline_mode))
+            types.append(batch.int_tensor[:, 3].to(probs[-1].device).long())
+        probs_b = torch.cat(probs) if probs else torch.zeros(0, device=self._device)
+        types_b = torch.cat(types) if types else torch.zeros(0, dtype=torch.long, device=self._device)
+        return {var_type: theoretical_roc_best_threshold(probs_b[types_b == int(var_type)], recall_weight)[0]
+                for var_type in Variation}
+
     # ---- fitting (posterior_model.py:101-165) -------------------------------------------------------------
     def _spectra_tensors(self):
         s, na = self.spectra.somatic_spectrum, self.spectra.normal_artifact_spectra
@@ -231,6 +245,29 @@ class PosteriorModel(nn.Module):
             if summary_writer is not None:
                 summary_writer.add_scalar("spectrum negative log evidence", history[-1], epoch)
         return history
+
+
+def theoretical_roc_best_threshold(error_probs_b: Tensor, recall_weight: float = 1.0) -> Tuple[float, float, float]:
+    """(threshold, precision, sensitivity) maximising the F_beta score of the theoretical ROC: the second output of
+    get_theoretical_roc_data (metrics/plotting.py:153-190), whose Python loop over the sorted probabilities becomes one
+    sort, two prefix sums and an argmax on the tensor's device (float64, like the reference's Python floats)."""
+    p = torch.sort(error_probs_b.detach().double().reshape(-1)).values
+    if p.numel() == 0:
+        return 0, 1, 0
+    beta_sqr = recall_weight ** 2
+    total_artifact = p.sum() + 0.0001
+    total_non_artifact = p.numel() - total_artifact + 0.0002
+    art_found = total_artifact - torch.cumsum(p, dim=0)
+    tp = torch.cumsum(1 - p, dim=0)
+    fp = total_artifact - art_found
+    sensitivity = tp / total_non_artifact
+    precision = tp / (tp + fp)
+    harmonic_mean = (1 + beta_sqr) * sensitivity * precision / (sensitivity + (beta_sqr * precision) + 0.0001)
+    best = harmonic_mean.max()
+    if not bool(best > 0):
+        return 0, 1, 0
+    idx = int(torch.nonzero(harmonic_mean == best)[0])          # the loop keeps the FIRST maximum (strict >)
+    return float(p[idx]), float(precision[idx]), float(sensitivity[idx])
 
 
 class _EvidenceLoss(torch.autograd.Function):

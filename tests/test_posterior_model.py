@@ -211,3 +211,63 @@ def test_artifact_model_records_flow_into_the_posterior_model():
     want = orc.log_posterior_and_ingredients(sd, int_out, float_out)["error_probabilities_b"].numpy()
     np.testing.assert_allclose(err, want, rtol=0, atol=3e-3)
     assert np.all((err >= 0) & (err <= 1)) and 0.01 < err.mean() < 0.999
+
+
+def _reference_roc_loop(artifact_probs, recall_weight=1.0):
+    """get_theoretical_roc_data's loop (metrics/plotting.py:153-190), second output only."""
+    beta_sqr = recall_weight ** 2
+    artifact_probs = sorted(artifact_probs)
+    total_artifact = sum(artifact_probs) + 0.0001
+    total_non_artifact = len(artifact_probs) - total_artifact + 0.0002
+    art_found, non_art_found = total_artifact, 0
+    best_threshold, best_hm = (0, 1, 0), 0
+    for prob in artifact_probs:
+        art_found -= prob
+        non_art_found += 1 - prob
+        tp, fp = non_art_found, total_artifact - art_found
+        sensitivity, precision = tp / total_non_artifact, tp / (tp + fp)
+        hm = (1 + beta_sqr) * sensitivity * precision / (sensitivity + (beta_sqr * precision) + 0.0001)
+        if hm > best_hm:
+            best_hm, best_threshold = hm, (prob, precision, sensitivity)
+    return best_threshold
+
+
+def test_probability_threshold_search_matches_the_reference_loop():
+    from permutect_b200.architecture.posterior_model import theoretical_roc_best_threshold
+    rng = np.random.default_rng(8)
+    for n, recall_weight in ((1, 1.0), (7, 1.0), (500, 1.0), (5000, 2.0), (5000, 0.5)):
+        probs = np.clip(rng.beta(0.3, 0.3, n), 0, 1).astype(np.float32)
+        want = _reference_roc_loop([float(x) for x in probs], recall_weight)
+        got = theoretical_roc_best_threshold(torch.from_numpy(probs), recall_weight)
+        assert got[0] == want[0], (n, got, want)
+        np.testing.assert_allclose(got[1:], want[1:], rtol=1e-9)
+    assert theoretical_roc_best_threshold(torch.zeros(0)) == (0, 1, 0)
+
+
+@pytest.mark.gpu
+def test_calculate_probability_thresholds_per_variant_type():
+    from permutect_b200.architecture.posterior_model import PosteriorBatch, PosteriorModel
+    from permutect_b200.utils.enums import Variation
+    z = np.load(GOLDEN)
+    sd, _, _, _ = _case(z, "default")
+    dev = torch.device("cuda:0")
+    model = PosteriorModel(-3.0, -4.0, device=dev)
+    model.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sd.items()})
+    batches = [PosteriorBatch(z["int_array"][i::2], z["float_array"][i::2], dev) for i in range(2)]
+    got = model.calculate_probability_thresholds(batches)
+    err = np.concatenate([model.error_probabilities_b(b).cpu().numpy() for b in batches])
+    types = np.concatenate([z["int_array"][i::2, 3] for i in range(2)])
+    assert set(got.keys()) == set(Variation)
+    for var_type in Variation:
+        mine = sorted(float(x) for x in err[types == int(var_type)])
+        want = _reference_roc_loop(mine)
+        if got[var_type] != want[0]:
+            # a parallel prefix sum rounds differently from the reference's sequential one: only an exact tie of the
+            # F score may then pick another element; the F score at the chosen threshold must still be the maximum
+            k = mine.index(got[var_type])
+            total_art = sum(mine) + 0.0001
+            tp = sum(1 - x for x in mine[:k + 1])
+            fp = sum(mine[:k + 1])
+            sens, prec = tp / (len(mine) - total_art + 0.0002), tp / (tp + fp)
+            best = 2 * want[2] * want[1] / (want[2] + want[1] + 0.0001)
+            assert abs(2 * sens * prec / (sens + prec + 0.0001) - best) < 1e-9, var_type
