@@ -53,7 +53,8 @@ class FlatAdamW(torch.optim.Optimizer):
         """Called by make_optimizer: from now on ``model.flat_weights()`` builds the materialised weight buffer from
         ``self.flat`` directly (engine/plan.py:materialize_flat) and its backward writes the whole gradient into
         ``self.flat_grad`` instead of ~190 per-parameter accumulations; only the parametrised tensors (13 for the shipped
-        architecture) still go through autograd.  The host side of a training step drops from 5.7 to ≈3 ms."""
+        architecture) keep a constraint Jacobian, and engine/plan.py writes those out (only the rotation matrix stays an
+        autograd input, itself a kernel pair).  The host side of a training step drops from 5.7 to 1.8 ms."""
         self._constrained = list(constrained_indices)
         offsets = [0]
         for n in self._sizes:
