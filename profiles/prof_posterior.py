@@ -22,4 +22,14 @@ for _ in range(2):
     probs = model.posterior_probabilities_bc(batch)
     loss = model.negative_log_evidence(batch)
 torch.cuda.synchronize()
-print("ok", float(probs[:, 0].mean()), float(loss.detach()))
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+ev[0].record()
+for _ in range(10):
+    model.posterior_probabilities_bc(batch)
+ev[1].record()
+for _ in range(10):
+    model.negative_log_evidence(batch)
+ev[2].record()
+torch.cuda.synchronize()
+print(f"ok n={n} posterior_probabilities_bc {ev[0].elapsed_time(ev[1]) / 10:.3f} ms, negative_log_evidence (E step) "
+      f"{ev[1].elapsed_time(ev[2]) / 10:.3f} ms; mean P(somatic)={float(probs[:, 0].mean()):.4f} loss={float(loss.detach()):.4f}")
