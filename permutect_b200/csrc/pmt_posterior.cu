@@ -350,6 +350,7 @@ extern "C" int pmt_posterior_fit_step(const PmtPosteriorDesc* desc, const float*
   PMT_CHECK(n_variants > 0, "empty batch");
   PMT_CHECK(workspace_bytes >= pmt_posterior_fit_workspace_size(n_variants, desc->n_components), "workspace too small");
   PMT_CHECK((!somatic_snv_totals_rrra && !snv_context_totals_rrra) || desc->hap_len >= 3, "SNV context totals need haplotypes of >= 3 bases");
+  PMT_CHECK(!desc->use_context_dependent_snv_priors || desc->hap_len >= 3, "context-dependent SNV priors need haplotypes of >= 3 bases");
   const int K = desc->n_components, n_slots = post::slot_count(K), blocks = (n_variants + post::THREADS - 1) / post::THREADS;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   post::FitArgs fit{reinterpret_cast<float*>(workspace), somatic_snv_totals_rrra, snv_context_totals_rrra};
