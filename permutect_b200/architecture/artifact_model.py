@@ -23,7 +23,6 @@ from permutect_b200.utils.enums import Epoch
 
 MAX_OUTLIER_LOGIT = 10      # artifact_model.py:32
 MAX_ALT_COUNT = 15          # count_binning.py:10
-BCE = nn.BCEWithLogitsLoss(reduction="none")
 
 
 def gpu_if_available() -> torch.device:
@@ -56,31 +55,6 @@ class BatchLosses:
         self.source_prediction_losses_b = source_prediction_losses_b
         self.total_losses_b = total_losses_b
         self.total_loss = torch.sum(total_losses_b)
-
-
-class _RevGrad(torch.autograd.Function):
-    """gradient_reversal/functional.py:6-22."""
-
-    @staticmethod
-    def forward(ctx, x, alpha):
-        ctx.alpha = alpha
-        return x.view_as(x)
-
-    @staticmethod
-    def backward(ctx, g):
-        return -ctx.alpha * g, None
-
-
-def _head_mlp(mlp: MLP, x: Tensor) -> Tensor:
-    """Per-variant adversarial heads ([B, E] -> [B, out]); B-length side work, kept on torch ops."""
-    for layer in mlp._model:
-        if isinstance(layer, nn.Linear):
-            x = torch.nn.functional.linear(x, layer.weight, layer.bias)
-        elif isinstance(layer, nn.SELU):
-            x = torch.nn.functional.selu(x)
-        else:   # DenseSkipBlock
-            x = x + layer.alpha * _head_mlp(layer.mlp, x)
-    return x
 
 
 class ArtifactModel(nn.Module):
@@ -227,19 +201,20 @@ class ArtifactModel(nn.Module):
         output._flat = flat      # the loss head reads the same materialised weights (and shares their autograd node)
         return output
 
+    def _loss_component(self, which: int, features_be: Tensor, batch: Batch) -> Tensor:
+        """One per-variant component of the fused loss head (pmt_losses_forward; 2 = alt count, 3 = source prediction),
+        differentiable w.r.t. the features and the head weights like the reference's stand-alone methods."""
+        zeros = torch.zeros(batch.size(), device=self._device, dtype=self._dtype)
+        return engine.FusedLossFunction.apply(self.flat_weights(), zeros, zeros, features_be, None, None,
+                                              self.loss_descriptor(), batch)[which]
+
     def compute_source_prediction_losses(self, features_be: Tensor, batch: Batch) -> Tensor:
-        if self.num_sources > 1:
-            x = _RevGrad.apply(features_be, self.source_predictor.gradient_reversal.alpha)
-            probs = torch.softmax(_head_mlp(self.source_predictor.wrapped_module, x), dim=-1)
-            targets = torch.nn.functional.one_hot(batch.get(Data.SOURCE).long(), self.num_sources)
-            return torch.sum(torch.square(probs - targets), dim=-1)
-        return torch.zeros(batch.size(), device=self._device, dtype=self._dtype)
+        """artifact_model.py:267-274."""
+        return self._loss_component(3, features_be, batch)
 
     def compute_alt_count_losses(self, features_be: Tensor, batch: Batch) -> Tensor:
-        x = _RevGrad.apply(features_be, self.alt_count_predictor.gradient_reversal.alpha)
-        pred = torch.sigmoid(_head_mlp(self.alt_count_predictor.wrapped_module, x).view(-1))
-        target = batch.get(Data.ALT_COUNT).to(dtype=pred.dtype) / MAX_ALT_COUNT
-        return self.alt_count_loss_func(pred, target)
+        """artifact_model.py:276-279."""
+        return self._loss_component(2, features_be, batch)
 
     def loss_descriptor(self):
         if self._loss_desc is None or self._loss_desc[0] != (self.num_sources, float(self.alt_count_predictor.gradient_reversal.alpha),

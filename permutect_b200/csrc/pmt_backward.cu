@@ -1245,7 +1245,7 @@ int pmt_launch_cnn_backward(const Plan& P, const CnnGeom& G, const float* weight
   const int B = batch->n_variants;
   int grid = (B + vt - 1) / vt;
   if (grid > n_partials) grid = n_partials;
-  cudaFuncSetAttribute(hap_cnn_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  PMT_CUDA(cudaFuncSetAttribute(hap_cnn_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   hap_cnn_backward_kernel<<<grid, NTHREADS, smem, st>>>(P, G, Gb, weights, image + P.img_total, batch->haplotypes,
                                                         batch->hap_kind, batch->hap_stride, B, d_info_seq, partials);
   return 0;
@@ -1327,7 +1327,7 @@ extern "C" int pmt_backward(const PmtModelDesc* desc, const float* weights, cons
   float* long_scratch = reinterpret_cast<float*>(ws + off); off += (size_t)lgrid * long_floats * sizeof(float);
   PMT_CHECK(off <= workspace_bytes, "workspace layout overflow");
 
-  cudaMemsetAsync(partials, 0, (size_t)kBwdGrid * desc->n_params * sizeof(float), st);
+  PMT_CUDA(cudaMemsetAsync(partials, 0, (size_t)kBwdGrid * desc->n_params * sizeof(float), st));
   pmt_launch_prepare(P, G, weights, image, st);
   if (grads && grads->info_seq_be) {
     cudaMemcpyAsync(info_seq, grads->info_seq_be, (size_t)B * w * sizeof(float), cudaMemcpyDeviceToDevice, st);
@@ -1360,12 +1360,12 @@ extern "C" int pmt_backward(const PmtModelDesc* desc, const float* weights, cons
   A.trace = g_bwd_trace;
   int grid = A.n_claims < kBwdGrid ? A.n_claims : kBwdGrid;
   if (grid > n_sm) grid = n_sm;
-  cudaFuncSetAttribute(reads_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  PMT_CUDA(cudaFuncSetAttribute(reads_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   pmt_profile_begin(st);
   reads_backward_kernel<<<grid, NTHREADS, smem, st>>>(P, A);
   pmt_profile_end(st);
   if (lgrid > 0) {   // sets longer than a tile; same CTA-private gradient buffers, after the tile kernel: fixed order
-    cudaFuncSetAttribute(reads_backward_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    PMT_CUDA(cudaFuncSetAttribute(reads_backward_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     reads_backward_long_kernel<<<lgrid, NTHREADS, smem, st>>>(P, A);
   }
   {
@@ -1374,7 +1374,7 @@ extern "C" int pmt_backward(const PmtModelDesc* desc, const float* weights, cons
     PMT_CHECK(ismem <= 227 * 1024, "info MLP too wide for the backward kernel (%zu bytes of shared memory)", ismem);
     const int n_tiles = (B + TILE - 1) / TILE;
     const int igrid = n_tiles < kBwdGrid ? n_tiles : kBwdGrid;
-    cudaFuncSetAttribute(info_mlp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ismem);
+    PMT_CUDA(cudaFuncSetAttribute(info_mlp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ismem));
     info_mlp_backward_kernel<<<igrid, NTHREADS, ismem, st>>>(P, weights, image, batch->info, batch->info_kind,
                                                              batch->info_stride, B, d_info_seq, scratch,
                                                              (long long)scr_floats, partials, rows);

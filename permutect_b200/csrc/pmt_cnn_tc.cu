@@ -573,12 +573,13 @@ size_t pmt_cnn_tc_image_bytes(const pmt::Plan& P) {
 }
 
 template <int PASSES, bool TRACE>
-static void launch_cnn_tc(const cnntc::Plan& T, const unsigned char* image, const float* weights, const PmtModelDesc& D,
+static int launch_cnn_tc(const cnntc::Plan& T, const unsigned char* image, const float* weights, const PmtModelDesc& D,
                           const PmtBatch* batch, float* info_seq, int grid, long long* trace, cudaStream_t st) {
   const size_t smem = 2 * BUF_BYTES + T.image_bytes + MAX_LAYERS * 32 * sizeof(float) + sizeof(Bars) + 1024 + 64;
-  cudaFuncSetAttribute(hap_cnn_tc_kernel<PASSES, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  PMT_CUDA(cudaFuncSetAttribute(hap_cnn_tc_kernel<PASSES, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   hap_cnn_tc_kernel<PASSES, TRACE><<<grid, THREADS, smem, st>>>(T, image, weights, D, batch->haplotypes, batch->hap_kind, batch->hap_stride,
                                                          batch->n_variants, info_seq, trace);
+  return 0;
 }
 
 // `image` is a 16-byte aligned device buffer of pmt_cnn_tc_image_bytes(P) bytes.
@@ -595,11 +596,11 @@ int pmt_launch_cnn_tc(const pmt::Plan& P, const float* weights, const PmtBatch* 
   const int n_groups = (batch->n_variants + T.G - 1) / T.G;
   const int grid = n_groups < n_sm ? n_groups : n_sm;
   if (g_cnn_trace) {
-    if (mode == PMT_PRECISION_TF32) launch_cnn_tc<1, true>(T, image, weights, P.d, batch, info_seq, grid, g_cnn_trace, st);
-    else launch_cnn_tc<3, true>(T, image, weights, P.d, batch, info_seq, grid, g_cnn_trace, st);
+    if (mode == PMT_PRECISION_TF32) { if (launch_cnn_tc<1, true>(T, image, weights, P.d, batch, info_seq, grid, g_cnn_trace, st)) return 1; }
+    else { if (launch_cnn_tc<3, true>(T, image, weights, P.d, batch, info_seq, grid, g_cnn_trace, st)) return 1; }
   } else {
-    if (mode == PMT_PRECISION_TF32) launch_cnn_tc<1, false>(T, image, weights, P.d, batch, info_seq, grid, nullptr, st);
-    else launch_cnn_tc<3, false>(T, image, weights, P.d, batch, info_seq, grid, nullptr, st);
+    if (mode == PMT_PRECISION_TF32) { if (launch_cnn_tc<1, false>(T, image, weights, P.d, batch, info_seq, grid, nullptr, st)) return 1; }
+    else { if (launch_cnn_tc<3, false>(T, image, weights, P.d, batch, info_seq, grid, nullptr, st)) return 1; }
   }
   return 0;
 }

@@ -577,7 +577,7 @@ int pmt_launch_variant_kernels(const Plan& P, const CnnGeom& G, const float* wei
   {
     const int in_rows = P.d.n_info_features > PMT_MAX_DIM ? PMT_MAX_INFO_DIM : PMT_MAX_DIM;
     const size_t smem = (size_t)((in_rows + 2 * PMT_MAX_DIM) * LD + 2 * P.info_stage_floats) * sizeof(float);
-    cudaFuncSetAttribute(info_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    PMT_CUDA(cudaFuncSetAttribute(info_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     info_mlp_kernel<<<(B + TILE - 1) / TILE, NTHREADS, smem, st>>>(P, weights, image, batch->info, batch->info_kind,
                                                                    batch->info_stride, B, info_seq);
   }
@@ -589,7 +589,7 @@ int pmt_launch_variant_kernels(const Plan& P, const CnnGeom& G, const float* wei
     if (pmt_launch_cnn_tc(P, weights, batch, info_seq, cnn_tc_image, reuse_images, n_sm, mode, st)) return 1;
   } else {
     const size_t smem = (size_t)(2 * G.buf_floats + G.img_total + 2 * G.vt * 256) * sizeof(float);
-    cudaFuncSetAttribute(hap_cnn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    PMT_CUDA(cudaFuncSetAttribute(hap_cnn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = (B + G.vt - 1) / G.vt;
     if (grid > 148 * 4) grid = 148 * 4;
     hap_cnn_kernel<<<grid, NTHREADS, smem, st>>>(P, G, weights, image + P.img_total, batch->haplotypes, batch->hap_kind,
@@ -625,7 +625,7 @@ static int forward_impl(const PmtModelDesc* desc, const float* weights, const Pm
   float* image = reinterpret_cast<float*>(ws + L.image);
   float* info_seq = out->info_seq_be;
   if (!info_seq) info_seq = reinterpret_cast<float*>(ws + L.info_seq);
-  cudaMemsetAsync(counter, 0, 256, st);
+  PMT_CUDA(cudaMemsetAsync(counter, 0, 256, st));
   if (!reuse_images) pmt_launch_prepare(P, G, weights, image, st);
   const int mode = pmt_precision_mode();
   unsigned char* tc_image = reinterpret_cast<unsigned char*>(ws + L.tc_image);
@@ -640,7 +640,7 @@ static int forward_impl(const PmtModelDesc* desc, const float* weights, const Pm
   A.wflat = weights; A.image = image; A.batch = *batch; A.out = *out; A.out.info_seq_be = info_seq; A.claim_counter = counter;
   A.scratch = nullptr; A.scratch_stride = 0;
   const size_t smem = reads_kernel_smem(P);
-  cudaFuncSetAttribute(reads_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  PMT_CUDA(cudaFuncSetAttribute(reads_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int n_claims = (batch->n_variants + P.claim_variants - 1) / P.claim_variants;
   const int grid = n_claims < n_sm ? n_claims : n_sm;
   if (mode != PMT_PRECISION_FP32) {
@@ -658,7 +658,7 @@ static int forward_impl(const PmtModelDesc* desc, const float* weights, const Pm
     A.scratch = reinterpret_cast<float*>(ws + L.long_scratch);
     A.scratch_stride = (long long)long_scratch_floats_per_cta(P, batch);
     const int lgrid = long_grid(batch, n_sm < 148 ? n_sm : 148);
-    cudaFuncSetAttribute(reads_forward_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    PMT_CUDA(cudaFuncSetAttribute(reads_forward_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     reads_forward_long_kernel<<<lgrid, NTHREADS, smem, st>>>(P, A);
   }
   cudaError_t e = cudaGetLastError();

@@ -14,6 +14,16 @@ void pmt_set_error(const char* fmt, ...);
     }                            \
   } while (0)
 
+// CUDA runtime calls whose failure would otherwise only surface as a later launch error (opt-in shared memory, memsets)
+#define PMT_CUDA(call)                                                                        \
+  do {                                                                                        \
+    cudaError_t pmt_cuda_err_ = (call);                                                       \
+    if (pmt_cuda_err_ != cudaSuccess) {                                                       \
+      pmt_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(pmt_cuda_err_), __FILE__, __LINE__); \
+      return 1;                                                                               \
+    }                                                                                         \
+  } while (0)
+
 // A set occupies pad4(ref rows) + alt rows of a tile, so a set of up to TILE - 3 rows always fits in one tile; anything
 // longer MAY be left to the long-set kernels by build_tile / plan_tiles_kernel (which then do nothing if it did fit).
 inline bool pmt_has_long_sets(const PmtBatch* batch) { return batch->max_rows_per_variant + 3 > PMT_TILE_ROWS; }

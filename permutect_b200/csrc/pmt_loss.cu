@@ -349,7 +349,7 @@ extern "C" int pmt_losses_forward(const PmtLossDesc* desc, const float* weights,
   A.d = *desc; A.b = *batch; A.wflat = weights;
   const size_t smem = (size_t)((ra.hi - ra.lo) + (rs.hi - rs.lo)) * sizeof(float);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  cudaFuncSetAttribute(losses_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  PMT_CUDA(cudaFuncSetAttribute(losses_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   losses_forward_kernel<<<loss_grid(batch->n_variants), NT, smem, st>>>(A, *out);
   cudaError_t e = cudaGetLastError();
   PMT_CHECK(e == cudaSuccess, "pmt_losses_forward launch failed: %s", cudaGetErrorString(e));
@@ -372,7 +372,7 @@ extern "C" int pmt_losses_backward(const PmtLossDesc* desc, const float* weights
   const int grid = loss_grid(batch->n_variants);
   const size_t smem = (size_t)(2 * (na + ns) + (2 * MAXW + 1) * NT) * sizeof(float);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  cudaFuncSetAttribute(losses_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  PMT_CUDA(cudaFuncSetAttribute(losses_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   losses_backward_kernel<<<grid, NT, smem, st>>>(B);
   losses_reduce_kernel<<<(desc->n_params + 255) / 256, 256, 0, st>>>(B.partials, grid, na, ns, ra.lo, rs.lo, desc->n_params, d_weights);
   cudaError_t e = cudaGetLastError();

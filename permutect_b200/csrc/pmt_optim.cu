@@ -228,7 +228,7 @@ extern "C" int pmt_orthogonal_backward(const float* x, const float* base, const 
   PMT_CHECK(x && d_q && d_x && n >= 1 && n <= expm::MAXN, "pmt_orthogonal_backward: n must be in 1..%d", expm::MAXN);
   const size_t smem = (size_t)(4 + expm::DEG + expm::SQ) * n * n * sizeof(double);
   if (smem > 48 * 1024)
-    cudaFuncSetAttribute(expm::backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    PMT_CUDA(cudaFuncSetAttribute(expm::backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   expm::backward_kernel<<<1, ((n * n + 31) / 32) * 32, smem, reinterpret_cast<cudaStream_t>(stream)>>>(x, base, d_q, n, d_x);
   cudaError_t e = cudaGetLastError();
   PMT_CHECK(e == cudaSuccess, "pmt_orthogonal_backward launch failed: %s", cudaGetErrorString(e));

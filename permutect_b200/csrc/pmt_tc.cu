@@ -957,10 +957,10 @@ static int launch_tc(const PmtModelDesc& D, const TcPlan& T, const TcArgs& A, in
   PMT_CHECK(n_stages >= 2, "tensor-core forward: weight ring does not fit in shared memory");
   const size_t smem = fixed + (size_t)n_stages * stage_bytes;
   if (g_reads_trace) {
-    cudaFuncSetAttribute(reads_forward_tc_kernel<PASSES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    PMT_CUDA(cudaFuncSetAttribute(reads_forward_tc_kernel<PASSES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     reads_forward_tc_kernel<PASSES, true><<<grid, THREADS, smem, st>>>(D, T, A, n_stages, stage_bytes, g_reads_trace);
   } else {
-    cudaFuncSetAttribute(reads_forward_tc_kernel<PASSES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    PMT_CUDA(cudaFuncSetAttribute(reads_forward_tc_kernel<PASSES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     reads_forward_tc_kernel<PASSES, false><<<grid, THREADS, smem, st>>>(D, T, A, n_stages, stage_bytes, nullptr);
   }
   return 0;
@@ -974,7 +974,7 @@ int pmt_launch_reads_tc(const Plan& P, const float* weights, const PmtBatch* bat
   pmt_tc_plan(P, &T);
   unsigned char* image = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(image_buf) + 1023) & ~uintptr_t(1023));
   int* tiles = reinterpret_cast<int*>((reinterpret_cast<uintptr_t>(tiles_buf) + 255) & ~uintptr_t(255));
-  cudaMemsetAsync(tiles, 0, 2 * sizeof(int), st);
+  PMT_CUDA(cudaMemsetAsync(tiles, 0, 2 * sizeof(int), st));
   // planner claims: large enough that the partial last tile of a claim is a small loss, small enough that a small
   // batch is planned by many warps (each claim is walked sequentially)
   int claim_variants = batch->n_variants / (2 * n_sm);

@@ -12,14 +12,18 @@ Row order is the reference's: all ref reads of all variants, then all alt reads 
 from __future__ import annotations
 
 import copy
+import enum
 from typing import List, Optional
 
 import numpy as np
 import torch
+from torch import Tensor
 
-from permutect_b200.data.datum import (COMPRESSED_READS_ARRAY_DTYPE, HAPLOTYPES_START_IDX, INFO_START_IDX, Data, Datum)
+from permutect_b200.data import count_binning as bins
+from permutect_b200.data.datum import (COMPRESSED_READS_ARRAY_DTYPE, HAPLOTYPES_START_IDX, INFO_START_IDX, Data, Datum,
+                                       field_kind, uint32_from_two_int16s)
 from permutect_b200.engine import library as L
-from permutect_b200.utils.enums import Label
+from permutect_b200.utils.enums import Label, Variation
 
 
 class Batch:
@@ -65,14 +69,36 @@ class Batch:
         self._offsets = None
         self._decoded = None
         self._device_counts = None      # (ref_counts, alt_counts) int64 when they differ from the int array (downsampling)
+        self.lazy_batch_indices = {False: None, True: None}
 
-    # ---- reference accessors (batch.py:87-133,182) ------------------------------------------------
-    def get(self, data_field: Data) -> torch.Tensor:
-        if self._device_counts is not None and data_field in (Data.REF_COUNT, Data.ALT_COUNT):
-            return self._device_counts[0 if data_field == Data.REF_COUNT else 1]
-        if data_field.kind == "int":
-            return self.int_tensor[:, data_field.idx].long()
-        return self.float_tensor[:, data_field.idx].float()
+    # ---- reference accessors (batch.py:68-133,176-182) ----------------------------------------------
+    def batch_indices(self, use_original_counts: bool = False) -> "BatchIndices":
+        """batch.py:68-85: the (source, label, variant type, ref bin, alt bin) strata of every variant, cached; built from
+        the int16 columns on whichever device the batch lives on."""
+        cached = self.lazy_batch_indices[use_original_counts]
+        if cached is None:
+            if use_original_counts:
+                ref_counts = self.get(Data.ORIGINAL_DEPTH) - self.get(Data.ORIGINAL_ALT_COUNT)
+                alt_counts = self.get(Data.ORIGINAL_ALT_COUNT)
+            else:
+                ref_counts, alt_counts = self.get(Data.REF_COUNT), self.get(Data.ALT_COUNT)
+            cached = BatchIndices(sources=self.get(Data.SOURCE), labels=self.get(Data.LABEL), var_types=self.get(Data.VARIANT_TYPE),
+                                  ref_counts=ref_counts, alt_counts=alt_counts)
+            self.lazy_batch_indices[use_original_counts] = cached
+        return cached
+
+    def get(self, data_field) -> torch.Tensor:
+        """batch.py:87-97.  ``data_field`` is a column descriptor of this package or of the reference
+        (``permutect.data.datum.Data``): anything with ``idx`` and ``kind`` or ``dtype``.  Integer columns come back int64
+        and float columns fp32, the dtypes the reference's batch tensors have."""
+        kind, idx = field_kind(data_field), data_field.idx
+        if self._device_counts is not None and kind == "int" and idx in (Data.REF_COUNT.idx, Data.ALT_COUNT.idx):
+            return self._device_counts[0 if idx == Data.REF_COUNT.idx else 1]
+        if kind == "int":
+            return self.int_tensor[:, idx].long()
+        if kind == "large":
+            return uint32_from_two_int16s(self.int_tensor[:, idx].long(), self.int_tensor[:, idx + 1].long())
+        return self.float_tensor[:, idx].float()
 
     def get_training_labels(self) -> torch.Tensor:
         labels = self.int_tensor[:, Data.LABEL.idx]
@@ -117,6 +143,28 @@ class Batch:
                                      torch.cuda.current_stream(self.reads.device).cuda_stream))
         return out
 
+    def get_list_of_reads_re(self):
+        """batch.py:137-153: each variant's decoded reads (its ref rows, then its alt rows) as one numpy array."""
+        ref_counts, alt_counts = (c.cpu() for c in self.counts())
+        reads = self.get_reads_re()
+        total_ref = int(ref_counts.sum())
+        ref_list = torch.tensor_split(reads[:total_ref], torch.cumsum(ref_counts, dim=0)[:-1])
+        alt_list = torch.tensor_split(reads[total_ref:], torch.cumsum(alt_counts, dim=0)[:-1])
+        return [torch.vstack((refs, alts)).cpu().numpy() for refs, alts in zip(ref_list, alt_list)]
+
+    def get_int_array_be(self) -> np.ndarray:
+        """batch.py:176-177 (int16 here, the records' own dtype; the reference widens to int64 and Datum narrows it back)."""
+        result = self.int_tensor.cpu().numpy()
+        if self._device_counts is not None:          # DownsampledBatch override, batch.py:451-456
+            result = result.copy()
+            result[:, Data.REF_COUNT.idx] = self._device_counts[0].cpu().numpy()
+            result[:, Data.ALT_COUNT.idx] = self._device_counts[1].cpu().numpy()
+        return result
+
+    def get_float_array_be(self) -> np.ndarray:
+        """batch.py:179-180."""
+        return self.float_tensor.cpu().numpy()
+
     def size(self) -> int:
         return self._size
 
@@ -138,6 +186,7 @@ class Batch:
             new_batch.read_indices = self.read_indices.to(device, non_blocking=non_blocking)
         new_batch._offsets = None
         new_batch._decoded = None
+        new_batch.lazy_batch_indices = {False: None, True: None}     # rebuilt on the new device when first asked for
         new_batch.finalize_on_device()
         return new_batch
 
@@ -150,6 +199,18 @@ class Batch:
         self.read_indices = torch.empty(self.reads.shape[0], dtype=torch.int64, device=dev)
         L.check(L.load().pmt_dataset_read_indices(ref_off.data_ptr(), alt_off.data_ptr(), self._size, self.read_indices.data_ptr(),
                                                   torch.cuda.current_stream(dev).cuda_stream))
+
+    def detach_from_ring(self) -> "Batch":
+        """Give this batch its own device memory.  Batches yielded by prefetch_generator are views into a ring of persistent
+        buffers that is refilled a few iterations later; call this before keeping one (or a DownsampledBatch of it) longer."""
+        for name in ("reads", "int_tensor", "float_tensor", "read_indices"):
+            t = getattr(self, name, None)
+            if t is not None:
+                setattr(self, name, t.clone())
+        self._offsets = None
+        self._decoded = None
+        self.lazy_batch_indices = {False: None, True: None}
+        return self
 
     def h2d_bytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in (self.reads, self.int_tensor, self.float_tensor))
@@ -195,6 +256,126 @@ class Batch:
         b.haplotypes = self.int_tensor.data_ptr() + HAPLOTYPES_START_IDX * self.int_tensor.element_size()
         b.hap_stride = self.int_tensor.shape[1]
         return b
+
+
+class BatchProperty(enum.IntEnum):
+    """Axes of a batch-indexed tensor and the display names of their bins (batch.py:185-201)."""
+    SOURCE = (0, None)
+    LABEL = (1, [label.name for label in Label])
+    VARIANT_TYPE = (2, [var_type.name for var_type in Variation])
+    REF_COUNT_BIN = (3, [bins.ref_count_bin_name(i) for i in range(bins.NUM_REF_COUNT_BINS)])
+    ALT_COUNT_BIN = (4, [bins.alt_count_bin_name(i) for i in range(bins.NUM_ALT_COUNT_BINS)])
+    LOGIT_BIN = (5, [bins.logit_bin_name(i) for i in range(bins.NUM_LOGIT_BINS)])
+
+    def __new__(cls, value, names_list):
+        member = int.__new__(cls, value)
+        member._value_ = value
+        member.names_list = names_list
+        return member
+
+    def get_name(self, n: int) -> str:
+        return str(n) if self.names_list is None else self.names_list[n]
+
+
+_LABEL_STRIDE = len(Variation) * bins.NUM_REF_COUNT_BINS * bins.NUM_ALT_COUNT_BINS      # 100
+_SOURCE_STRIDE = len(Label) * _LABEL_STRIDE                                              # 300
+
+
+class BatchIndices:
+    """Row-major position of every variant in a ``[source, label, variant type, ref bin, alt bin]`` table
+    (batch.py:204-291).  Source is the leading axis, so the position does not depend on the number of sources."""
+
+    def __init__(self, sources: Tensor, labels: Tensor, var_types: Tensor, ref_counts: Tensor, alt_counts: Tensor):
+        self.sources, self.labels, self.var_types = sources, labels, var_types
+        self.ref_count_bins = bins.ref_count_bin_indices(ref_counts)
+        self.alt_count_bins = bins.alt_count_bin_indices(alt_counts)
+        self.flattened_idx = (sources * _SOURCE_STRIDE + labels * _LABEL_STRIDE
+                              + (var_types * bins.NUM_REF_COUNT_BINS + self.ref_count_bins) * bins.NUM_ALT_COUNT_BINS
+                              + self.alt_count_bins)
+
+    def _flattened_idx(self, source_override: Tensor = None, pseudolabels: Tensor = None, logits: Tensor = None) -> Tensor:
+        """Positions with the source and / or label replaced (a shift by whole strides), optionally extended by the logit
+        bin as the innermost axis (batch.py:230-262)."""
+        idx = self.flattened_idx
+        if source_override is not None:
+            assert len(source_override) == len(self.sources)
+            idx = idx + _SOURCE_STRIDE * (source_override - self.sources)
+        if pseudolabels is not None:
+            assert len(pseudolabels) == len(self.labels)
+            idx = idx + _LABEL_STRIDE * (pseudolabels - self.labels)
+        if logits is not None:
+            idx = bins.logit_bin_indices(logits) + bins.NUM_LOGIT_BINS * idx
+        return idx
+
+    def index_into_tensor(self, tens, sources: Tensor = None, labels: Tensor = None, logits: Tensor = None) -> Tensor:
+        """result[i] = tens[source[i], label[i], variant type[i], ref bin[i], alt bin[i] (, logit bin[i])] (batch.py:264-278)."""
+        assert (logits is None) == (not tens.has_logits()), "Logits used iff batch-indexed tensor has logit dimension."
+        return tens.view(-1)[self._flattened_idx(source_override=sources, pseudolabels=labels, logits=logits)]
+
+    def increment_tensor(self, tens, values: Tensor, sources: Tensor = None, labels: Tensor = None, logits: Tensor = None):
+        """tens[strata of variant i] += values[i], in place (batch.py:280-291)."""
+        assert (logits is None) == (not tens.has_logits()), "Logits used iff batch-indexed tensor has logit dimension."
+        idx = self._flattened_idx(source_override=sources, pseudolabels=labels, logits=logits)
+        return tens.view(-1).index_add_(dim=0, index=idx, source=values)
+
+
+class BatchIndexedTensor(Tensor):
+    """Sums stratified by source, label, variant type, ref bin, alt bin and optionally logit bin (batch.py:294-380):
+    a plain tensor of 5 or 6 dimensions that knows its axes."""
+
+    @staticmethod
+    def __new__(cls, data: Tensor):
+        return torch.Tensor._make_subclass(cls, data)
+
+    def __init__(self, data: Tensor):
+        assert data.dim() in (5, 6), "batch-indexed tensors have either 5 or 6 dimensions"
+
+    def has_logits(self) -> bool:
+        return self.dim() == 6
+
+    def num_sources(self) -> int:
+        return self.shape[0]
+
+    @classmethod
+    def shape_without_logits(cls, num_sources: int):
+        return (num_sources, len(Label), len(Variation), bins.NUM_REF_COUNT_BINS, bins.NUM_ALT_COUNT_BINS)
+
+    @classmethod
+    def _filled(cls, value: float, num_sources: int, include_logits: bool, device):
+        shape = cls.shape_without_logits(num_sources) + ((bins.NUM_LOGIT_BINS,) if include_logits else ())
+        return cls(torch.full(shape, value, dtype=torch.float32, device=device))
+
+    @classmethod
+    def zeros(cls, num_sources: int, include_logits: bool = False, device=None):
+        return cls._filled(0.0, num_sources, include_logits, device)
+
+    @classmethod
+    def ones(cls, num_sources: int, include_logits: bool = False, device=None):
+        return cls._filled(1.0, num_sources, include_logits, device)
+
+    def resize_sources(self, new_num_sources: int):
+        old = self.num_sources()
+        shape = self.shape_without_logits(new_num_sources) + ((bins.NUM_LOGIT_BINS,) if self.has_logits() else ())
+        self.resize_(shape)
+        self[old:] = 0
+
+    def record_datum(self, datum: Datum, value: float = 1.0, grow_source_if_necessary: bool = True):
+        assert not self.has_logits(), "this only works when not including logits"
+        source = int(datum.get(Data.SOURCE))
+        if source >= self.num_sources():
+            if not grow_source_if_necessary:
+                raise Exception("Datum source doesn't fit.")
+            self.resize_sources(source + 1)
+        self[source, int(datum.get(Data.LABEL)), int(datum.get(Data.VARIANT_TYPE)),
+             bins.ref_count_bin_index(int(datum.get(Data.REF_COUNT))), bins.alt_count_bin_index(int(datum.get(Data.ALT_COUNT)))] += value
+
+    def record(self, batch: Batch, values: Tensor, logits: Tensor = None, use_original_counts: bool = False):
+        batch.batch_indices(use_original_counts).increment_tensor(self, values=values, logits=logits)
+
+    def get_marginal(self, *properties: BatchProperty) -> Tensor:
+        """Sum over every axis that is not listed (batch.py:371-380)."""
+        keep = set(int(p) for p in properties)
+        return torch.sum(self, dim=tuple(n for n in range(self.dim()) if n not in keep))
 
 
 class DownsampledBatch(Batch):

@@ -8,7 +8,9 @@ import enum
 import numpy as np
 
 INTEGER_DTYPE = np.int16
+LARGE_INTEGER_DTYPE = np.uint32      # stored as TWO consecutive int16 columns (datum.py:24,41-47)
 FLOAT_DTYPE = np.float16
+BIGGEST_UINT16, BIGGEST_INT16 = 65535, 32767   # datum.py:28-29 (the pair is a base-65535 number in the reference, sic)
 COMPRESSED_READS_ARRAY_DTYPE = np.uint8
 RAW_READS_ARRAY_DTYPE = np.float16
 NUMBER_OF_BYTES_IN_PACKED_READ = 7   # datum.py:38
@@ -26,6 +28,9 @@ class Data(enum.Enum):
     ORIGINAL_NORMAL_DEPTH = ("int", 7)
     ORIGINAL_NORMAL_ALT_COUNT = ("int", 8)
     CONTIG = ("int", 9)
+    POSITION = ("large", 10)
+    REF_ALLELE_AS_BASE_5 = ("large", 12)
+    ALT_ALLELE_AS_BASE_5 = ("large", 14)
     SEQ_ERROR_LOG_LK = ("float", 0)
     NORMAL_SEQ_ERROR_LOG_LK = ("float", 1)
     ALLELE_FREQUENCY = ("float", 2)
@@ -36,6 +41,22 @@ class Data(enum.Enum):
     def __init__(self, kind: str, idx: int):
         self.kind = kind
         self.idx = idx
+        # the reference's enum carries the numpy dtype instead of a kind (datum.py:76-78); both spellings work here
+        self.dtype = {"int": INTEGER_DTYPE, "large": LARGE_INTEGER_DTYPE, "float": FLOAT_DTYPE}[kind]
+
+
+def field_kind(field) -> str:
+    """'int' / 'large' / 'float' for a column descriptor of this module or of the reference (permutect.data.datum.Data)."""
+    kind = getattr(field, "kind", None)
+    if kind is not None:
+        return kind
+    dt = np.dtype(field.dtype)
+    return "int" if dt == INTEGER_DTYPE else ("large" if dt == LARGE_INTEGER_DTYPE else "float")
+
+
+def uint32_from_two_int16s(int16_1, int16_2):
+    """datum.py:45-47; works on Python ints, numpy arrays and torch tensors alike."""
+    return BIGGEST_UINT16 * (int16_1 + (BIGGEST_INT16 + 1)) + (int16_2 + (BIGGEST_INT16 + 1))
 
 
 NUM_SCALAR_INT_ELEMENTS = 16     # datum.py:83
@@ -62,7 +83,12 @@ class Datum:
         assert self.reads_re.dtype == (COMPRESSED_READS_ARRAY_DTYPE if compressed else RAW_READS_ARRAY_DTYPE)
 
     def get(self, field: Data):
-        return self.int_array[field.idx] if field.kind == "int" else self.float_array[field.idx]
+        kind = field_kind(field)
+        if kind == "int":
+            return self.int_array[field.idx]
+        if kind == "large":
+            return uint32_from_two_int16s(int(self.int_array[field.idx]), int(self.int_array[field.idx + 1]))
+        return self.float_array[field.idx]
 
     def get_int_array(self):
         return self.int_array

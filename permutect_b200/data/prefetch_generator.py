@@ -47,11 +47,15 @@ _RINGS = {}   # (device, depth) -> _Ring kept between generators
 
 
 def prefetch_generator(dataloader: Iterable[Batch], device=None, depth: int = 2) -> Iterator[Batch]:
-    device = torch.device(device if device is not None else ("cuda" if torch.cuda.is_available() else "cpu"))
+    """LIFETIME CONTRACT: a yielded batch's tensors are views into a ring of ``depth + 1`` persistent device buffers; the
+    slot is refilled (on the copy stream, ordered after everything the consumer queued on its CURRENT stream up to the moment
+    it asks for the next batch) once ``depth`` further batches have been requested.  A consumer that keeps a batch, or
+    anything derived from its int / float / reads views, beyond its own iteration -- ``list(prefetch_generator(...))``, a
+    recorder holding references, work queued on another stream -- must call ``batch.detach_from_ring()`` (device-side
+    clone) first.  The reference's generator yields independent tensors (prefetch_generator.py:9-20)."""
+    device = torch.device(device if device is not None else "cuda")
     if device.type != "cuda":
-        for batch_cpu in dataloader:
-            yield batch_cpu.copy_to(device)
-        return
+        raise RuntimeError("prefetch_generator feeds the CUDA kernels: there is no CPU path (device must be a CUDA device)")
     if device.index is None:
         device = torch.device("cuda", torch.cuda.current_device())
     shared = _RINGS.get((device, depth))
@@ -91,6 +95,7 @@ def _pipeline(dataloader: Iterable[Batch], device, depth: int, holder: "_Ring") 
             setattr(batch_gpu, name, dst)
         batch_gpu._offsets = None
         batch_gpu._decoded = None
+        batch_gpu.lazy_batch_indices = {False: None, True: None}
         if getattr(batch_cpu, "_dataset_order", False):
             batch_gpu.read_indices = None
         queue.append((batch_gpu, done, slot))

@@ -55,6 +55,48 @@ def allreduce_counters(tensors: List[torch.Tensor], group=None) -> None:
     allreduce_flat_(tensors, group)
 
 
+class SyncedBalancer:
+    """Keeps a ``Balancer``'s stratified counters global under data parallelism (balancer.py:57-72).
+
+    Before the wrapped balancer sees a rank's batch, the increments every rank is about to make -- one per variant into
+    ``counts_slvra``, the artifact / non-artifact probability mass of unlabeled variants into ``pseudo_counts_slvra``, the
+    batch size into ``count_since_last_recomputation`` -- are summed with ONE all-reduce, and the other ranks' share is added
+    to the wrapped balancer's state.  The balancer then processes its own batch exactly as in a single process, so its
+    periodic weight recomputation (balancer.py:74-104) fires on the same step and from the same totals on every rank.
+    Everything else (``weights_slvra``, plots, ``state_dict``) is the wrapped object's: attribute access falls through."""
+
+    def __init__(self, balancer, group=None):
+        self.balancer, self.group = balancer, group
+
+    def __getattr__(self, name):
+        return getattr(self.balancer, name)
+
+    def process_batch_and_compute_weights(self, batch, artifact_probs_b: torch.Tensor):
+        b = self.balancer
+        counts, pseudo = b.counts_slvra, b.pseudo_counts_slvra
+        dev = counts.device
+        idx = batch.batch_indices()
+        probs = artifact_probs_b.to(dev)
+        unlabeled = (1 - batch.get_is_labeled_mask()).to(dev)
+        n = counts.numel()
+        local = torch.zeros(2 * n + 1, dtype=counts.dtype, device=dev)
+        flat_idx = idx.flattened_idx.to(dev)
+        stride = counts[0, 0].numel()         # one label to the next
+        local[:n].index_add_(0, flat_idx, torch.ones(batch.size(), dtype=counts.dtype, device=dev))
+        base = flat_idx - stride * idx.labels.to(dev)        # label axis zeroed; ARTIFACT = 0, VARIANT = 1 (utils/enums.py)
+        local[n:2 * n].index_add_(0, base, (unlabeled * probs).to(counts.dtype))
+        local[n:2 * n].index_add_(0, base + stride, (unlabeled * (1 - probs)).to(counts.dtype))
+        local[2 * n] = batch.size()
+        total = local.clone()
+        dist.all_reduce(total, op=dist.ReduceOp.SUM, group=self.group)
+        others = total - local
+        with torch.no_grad():
+            counts.view(-1).add_(others[:n])
+            pseudo.view(-1).add_(others[n:2 * n])
+        b.count_since_last_recomputation += int(round(float(others[2 * n])))
+        return b.process_batch_and_compute_weights(batch, artifact_probs_b)
+
+
 def gather_variant_outputs(local: torch.Tensor, n_total: int, group=None) -> Optional[torch.Tensor]:
     """Concatenate rank-local per-variant outputs in variant order on every rank (inference needs the order
     only to re-associate logits with their Datum, filter_variants.py:302-320)."""

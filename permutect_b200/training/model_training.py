@@ -20,6 +20,7 @@ import torch
 from permutect_b200.data.batch import Batch, DownsampledBatch
 from permutect_b200.data.datum import Data
 from permutect_b200.data.prefetch_generator import prefetch_generator
+from permutect_b200.training import distributed as pdist
 from permutect_b200.training.step import backpropagate
 from permutect_b200.utils.enums import Epoch, Label
 
@@ -57,11 +58,34 @@ def describe_variant(int_array: np.ndarray) -> str:
             + "->" + bases5_as_base_string(uint32_from_two_int16s(int_array[_ALT_ALLELE_IDX], int_array[_ALT_ALLELE_IDX + 1])))
 
 
+def freeze(parameters):
+    """misc_utils.py:143-145."""
+    for p in parameters:
+        p.requires_grad = False
+
+
+def unfreeze(parameters):
+    """misc_utils.py:148-151."""
+    for p in parameters:
+        if p.dtype.is_floating_point:
+            p.requires_grad = True
+
+
 def run_epoch(model, loader: Iterable[Batch], downsampler, epoch_type: Epoch, optimizer=None, balancer=None,
-              loss_recorder=None, process_group=None, on_step: Optional[Callable] = None) -> int:
-    """The batch loop of train_one_epoch (model_training.py:146-165): two downsampled draws of every parent batch, losses
-    recorded, and in a TRAIN epoch one optimiser step per draw.  Returns the number of downsampled batches processed."""
+              loss_recorder=None, process_group=None, on_step: Optional[Callable] = None,
+              is_calibration_epoch: bool = False) -> int:
+    """The batch loop of train_one_epoch (model_training.py:143-165): two downsampled draws of every parent batch, losses
+    recorded, and in a TRAIN epoch one optimiser step per draw.  In a calibration epoch only
+    ``model.calibration_parameters()`` train (:146-149).  With a process group (or an initialised default group of more than
+    one rank) the gradient is summed across ranks inside the optimiser step and the balancer's counters are kept global
+    (training/distributed.py:SyncedBalancer), so every rank holds the same weights and the same balancing state.
+    Returns the number of downsampled batches processed."""
     model.set_epoch_type(epoch_type)
+    if is_calibration_epoch and epoch_type == Epoch.TRAIN:
+        freeze(model.parameters())
+        unfreeze(model.calibration_parameters())
+    if balancer is not None and (process_group is not None or pdist.is_initialized()) and not isinstance(balancer, pdist.SyncedBalancer):
+        balancer = pdist.SyncedBalancer(balancer, process_group)
     device = model._device
     n = 0
     for parent_batch in prefetch_generator(loader, device):

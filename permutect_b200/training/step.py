@@ -161,7 +161,7 @@ def make_optimizer(model: nn.Module, learning_rate: float = 1e-3, weight_decay: 
             from permutect_b200.engine import plan as planner
             opt.attach(model, planner.constrained_parameter_indices(model))
         return opt
-    return torch.optim.AdamW(params, lr=learning_rate, weight_decay=weight_decay)
+    raise RuntimeError("make_optimizer needs the model's parameters on a CUDA device (FlatAdamW; there is no CPU optimiser path)")
 
 
 def backpropagate(optimizer: torch.optim.Optimizer, loss: torch.Tensor, params_to_clip: Iterable[nn.Parameter] = (),

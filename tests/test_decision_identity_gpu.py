@@ -1,0 +1,116 @@
+"""Filter-decision identity of the DEFAULT arithmetic mode (tf32x3 on tcgen05) against the oracle chain, at scale.
+
+What the reference's posterior model consumes is ``fp16(logit)`` (datum.py:25,76; tools/filter_variants.py:318) and the
+call is the argmax of ``log priors + spectra + normal + logit`` (architecture/posterior_model.py:90-92), so "identical
+PASS / FILTER decisions" (BASELINE north star; the integration datasets are absent) is checked as:
+
+    oracle logits -> fp16 -> posterior records (posterior_tail_oracle) -> posterior_model_oracle -> call
+    tf32x3 logits -> pmt_pack_posterior -> pmt_posterior_log_posteriors                          -> call
+
+on >= 100 k WGS-shaped variants with a model whose logits straddle 0 (the calibration spread of the scalar-perturbed
+bench model is narrowed so that half of the variants are called artifacts and a fifth sit within |logit| < 1, where
+20 tanh(x / 20) has slope 1 and hides nothing).  Reported: sign flips, fp16 changes, call flips.  Asserted: |logit error|
+<= 1e-3; sign flips only where |oracle logit| < 1e-3; no call flip wherever the oracle's top two posteriors are further
+apart than the logit's fp16 spacing; fp16 changes <= 3 %.
+"""
+import numpy as np
+import pytest
+import torch
+
+import bench
+from oracle import artifact_oracle as orc
+from oracle import posterior_model_oracle as porc
+from oracle import posterior_tail_oracle as tail
+
+pytestmark = pytest.mark.gpu
+N_VARIANTS = 131072
+CHUNK = 16384
+
+
+def straddling_model(dev):
+    model = bench.make_model(dev)
+    with torch.no_grad():
+        model.feature_clustering.parametrizations.nonartifact_stdev_e.original.add_(-0.25)
+    return model
+
+
+def posterior_columns(ia, fa, rng):
+    """Depths / alt counts / likelihood scalars a posterior record carries (datum.py:57-76), WGS-like."""
+    n = len(ia)
+    depth = rng.integers(12, 120, n)
+    ia[:, 5] = depth
+    ia[:, 6] = np.maximum(1, (depth * rng.random(n) * 0.6).astype(np.int64))
+    ia[:, 7] = rng.integers(0, 100, n)
+    ia[:, 8] = (ia[:, 7] * 0.03 * rng.random(n)).astype(np.int64)
+    fa[:, 0] = (-30 * rng.random(n)).astype(np.float16)
+    fa[:, 1] = (-5 * rng.random(n)).astype(np.float16)
+    fa[:, 2] = (10 ** (-4 * rng.random(n) - 0.3)).astype(np.float16)
+    fa[:, 3] = (0.05 + 0.45 * rng.random(n)).astype(np.float16)
+    fa[:, 4] = (0.05 + 0.45 * rng.random(n)).astype(np.float16)
+
+
+def decision_counts(model, dev, n_variants, seed, chunk=CHUNK):
+    """Runs both chains; returns a dict of counts and the per-variant arrays the assertions need."""
+    from permutect_b200.architecture.posterior_model import PosteriorBatch, PosteriorModel
+    from permutect_b200.data.batch import Batch
+    from permutect_b200.synthetic import make_wgs_arrays
+    from permutect_b200.tools.filter_variants import posterior_arrays_on_device
+    from permutect_b200.utils.enums import Epoch
+    model.set_epoch_type(Epoch.VALID)
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    posterior = PosteriorModel(-10.0, -10.0, device=dev)
+    psd = {k: v.detach().cpu() for k, v in posterior.state_dict().items()}
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    want_logits, got_logits, want_calls, got_calls, gaps = [], [], [], [], []
+    for c, v0 in enumerate(range(0, n_variants, chunk)):
+        n = min(chunk, n_variants - v0)
+        ia, fa, reads = make_wgs_arrays(n, seed=seed + c)
+        posterior_columns(ia, fa, np.random.default_rng(seed + 500 + c))
+        with torch.no_grad():
+            ref = orc.forward(sd, bench.V040, bench.oracle_inputs(ia, fa, reads))
+        o_int, o_float = tail.posterior_arrays(ia, fa, ref["logits_b"].numpy(), ref["features_be"].numpy())
+        o_post = porc.log_posterior_and_ingredients(psd, o_int, o_float)["log_posteriors_bc"]
+        top2 = torch.topk(o_post, 2, dim=1).values
+        batch = Batch.from_arrays(ia, fa, reads).copy_to(dev)
+        with torch.inference_mode():
+            out = model.compute_batch_output(batch)
+            g_int, g_float = posterior_arrays_on_device(batch, out.logits_b, out.features_be)
+            g_post = posterior.log_relative_posteriors_bc(PosteriorBatch(g_int, g_float, dev))
+        want_logits.append(ref["logits_b"].numpy())
+        got_logits.append(out.logits_b.cpu().numpy())
+        want_calls.append(o_post.argmax(dim=1).numpy())
+        got_calls.append(g_post.argmax(dim=1).cpu().numpy())
+        gaps.append((top2[:, 0] - top2[:, 1]).numpy())
+    want, got = np.concatenate(want_logits), np.concatenate(got_logits)
+    wc, gc, gap = np.concatenate(want_calls), np.concatenate(got_calls), np.concatenate(gaps)
+    sign_flip = (want > 0) != (got > 0)
+    fp16_change = want.astype(np.float16) != got.astype(np.float16)
+    call_flip = wc != gc
+    return dict(n=len(want), max_abs_logit_diff=float(np.abs(want - got).max()), n_over_1e_3=int((np.abs(want - got) > 1e-3).sum()),
+                sign_flips=int(sign_flip.sum()), fp16_rounding_changes=int(fp16_change.sum()), call_flips=int(call_flip.sum()),
+                frac_positive=float((want > 0).mean()), frac_abs_below_1=float((np.abs(want) < 1).mean()),
+                calls_histogram=np.bincount(wc, minlength=5).tolist()), dict(want=want, got=got, sign_flip=sign_flip,
+                                                                             call_flip=call_flip, gap=gap)
+
+
+def test_filter_decisions_match_the_oracle_chain_in_the_default_mode():
+    from permutect_b200.engine import library
+    dev = torch.device("cuda:0")
+    library.set_precision("tf32x3")
+    try:
+        counts, arrays = decision_counts(straddling_model(dev), dev, N_VARIANTS, seed=9100)
+    finally:
+        library.set_precision("fp32")
+    print("decision identity vs the oracle chain:", counts)
+    assert counts["n"] >= 100_000
+    assert 0.3 < counts["frac_positive"] < 0.7 and counts["frac_abs_below_1"] > 0.1          # the logits do straddle 0
+    assert min(counts["calls_histogram"][:2]) > 1000                                         # somatic and artifact calls both occur
+    assert counts["max_abs_logit_diff"] <= 1e-3, counts
+    want = arrays["want"]
+    assert (np.abs(want[arrays["sign_flip"]]) < 1e-3).all(), want[arrays["sign_flip"]]
+    # a call can only flip where the posterior's top two entries are closer than the logit can move: one fp16 step of the
+    # logit (2^-6 at |logit| in [16, 20], datum.py:25) plus the posterior kernel's own fp32 tolerance
+    decisive = arrays["gap"] > 2.0 ** -6 + 2e-3
+    assert not arrays["call_flip"][decisive].any(), int(arrays["call_flip"][decisive].sum())
+    assert counts["call_flips"] <= 1e-3 * counts["n"], counts
+    assert counts["fp16_rounding_changes"] <= 0.03 * counts["n"], counts

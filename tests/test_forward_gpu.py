@@ -47,8 +47,9 @@ def test_forward_matches_oracle_and_filter_decisions(case):
     # what filter_variants persists and gates on (quirk Q6): sign and fp16 rounding of the logit
     far_from_boundary = (want["logits_b"].abs() > 2 * LOGIT_ATOL)
     assert torch.equal(torch.sign(logits)[far_from_boundary], torch.sign(want["logits_b"])[far_from_boundary])
-    mismatch = (logits.half() != want["logits_b"].half()).float().mean().item()
-    assert mismatch <= 0.1, f"{mismatch:.3f} of fp16-rounded logits differ"
+    # measured 1.5 % at 1.25 M variants (quirk Q6); the fixtures hold 64 variants, so at most 3 % or two of them
+    mismatch = int((logits.half() != want["logits_b"].half()).sum())
+    assert mismatch <= max(2, 0.03 * len(logits)), f"{mismatch} of {len(logits)} fp16-rounded logits differ"
 
 
 @pytest.mark.parametrize("case", ["v040_seed0_b64", "small_hp"])

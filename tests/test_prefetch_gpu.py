@@ -34,10 +34,18 @@ def test_prefetched_batches_give_the_same_logits_as_direct_copies():
                 assert torch.equal(a, w)
 
 
-def test_prefetch_generator_on_cpu_is_a_plain_copy_loop():
+def test_prefetch_generator_has_no_cpu_path():
+    import pytest as _pytest
     host = [Batch.from_arrays(*make_wgs_arrays(10, seed=1))]
-    out = list(prefetch_generator(host, torch.device("cpu")))
-    assert len(out) == 1 and out[0].size() == 10
+    with _pytest.raises(RuntimeError, match="no CPU path"):
+        list(prefetch_generator(host, torch.device("cpu")))
+
+
+def test_make_optimizer_has_no_cpu_path():
+    import pytest as _pytest
+    from permutect_b200.training.step import make_optimizer
+    with _pytest.raises(RuntimeError, match="no CPU optimiser path"):
+        make_optimizer(torch.nn.Linear(3, 2))
 
 
 @GPU
