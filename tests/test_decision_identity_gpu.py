@@ -11,7 +11,11 @@ on >= 100 k WGS-shaped variants with a model whose logits straddle 0 (the calibr
 bench model is narrowed so that half of the variants are called artifacts and a fifth sit within |logit| < 1, where
 20 tanh(x / 20) has slope 1 and hides nothing).  Reported: sign flips, fp16 changes, call flips.  Asserted: |logit error|
 <= 1e-3; sign flips only where |oracle logit| < 1e-3; no call flip wherever the oracle's top two posteriors are further
-apart than the logit's fp16 spacing; fp16 changes <= 3 %.
+apart than the logit's fp16 spacing; the number of fp16 changes is what the
+logit error itself predicts (a change needs an fp16 rounding boundary between the two fp32 values: probability
+|error| / spacing, and the spacing is 2^-11 ... 2^-10 for |logit| in [0.5, 2) -- near 0 almost any two fp32 summation
+orders disagree in fp16, the reference on another device included; in the saturated regime of the random-init fixtures the
+same error changes 1.5 % of the roundings, tests/test_forward_gpu.py).
 """
 import numpy as np
 import pytest
@@ -113,4 +117,12 @@ def test_filter_decisions_match_the_oracle_chain_in_the_default_mode():
     decisive = arrays["gap"] > 2.0 ** -6 + 2e-3
     assert not arrays["call_flip"][decisive].any(), int(arrays["call_flip"][decisive].sum())
     assert counts["call_flips"] <= 1e-3 * counts["n"], counts
-    assert counts["fp16_rounding_changes"] <= 0.03 * counts["n"], counts
+    got = arrays["got"]
+    w16, g16 = want.astype(np.float16), got.astype(np.float16)
+    changed = w16 != g16
+    ulp16 = np.spacing(np.maximum(np.abs(w16), np.abs(g16)).astype(np.float16)).astype(np.float32)
+    # rounding moves a value by at most half a spacing: the fp16 pair is never further apart than the fp32 pair plus one spacing
+    assert (np.abs(w16.astype(np.float32) - g16.astype(np.float32)) <= np.abs(want - got) + ulp16).all()
+    expected = float(np.minimum(1.0, np.abs(want - got) / np.spacing(np.abs(w16)).astype(np.float32)).sum())
+    print(f"fp16 rounding changes: {int(changed.sum())} observed, {expected:.0f} predicted from |logit error| / fp16 spacing")
+    assert changed.sum() <= 1.25 * expected + 50, (int(changed.sum()), expected)
