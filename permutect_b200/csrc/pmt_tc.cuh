@@ -1,0 +1,216 @@
+// Declarations shared by the tensor-core read-path kernels: the forward (pmt_tc.cu) and the backward (pmt_tc_bwd.cu).
+#pragma once
+#include <cstring>
+
+#include "pmt_host.h"
+#include "pmt_tile.cuh"
+#include "pmt_tc_ptx.cuh"
+
+namespace pmt {
+namespace tc {
+
+constexpr int THREADS = 608;      // 16 epilogue warps (2 slots x 2 column halves x 4 lane quarters) + 2 MMA warps + loader warp
+constexpr int MMA_WARP = 16, LOAD_WARP = 18;
+constexpr int SUMS_FLOATS = 2 * TILE * 11;   // per slot: [segment][MAXH]
+constexpr int MAX_STEPS = 64;
+constexpr int COL_X = 0, COL_Z = 64, COL_AHI = 128, COL_ALO = 192, SLOT_COLS = 256;
+constexpr int MAXH = 11;    // d_ffn / 2: the proj2 operand [t_ref | t_alt | is_ref, is_alt] must fit 24 columns
+constexpr int NP1 = 24;     // padded width of one proj1 weight set (>= 2 * MAXH)
+constexpr int MAXE = 16;    // final feature dimension
+constexpr int MAXK = 6;     // artifact clusters
+constexpr int XCH_ROWS = MAXE + MAXK + 2;
+constexpr int XCH_LD = TILE + 1;   // odd row stride: the per-variant gathers read one column range of MANY rows at once
+constexpr int NS_MAX = 8;
+constexpr int PLAN_CLAIM = 512;   // variants per planner claim
+
+enum EpiKind { EPI_DECODE = 0, EPI_FIRST32, EPI_ACT_Z32, EPI_ACT_X32, EPI_LN_FIRST, EPI_LN, EPI_GATE, EPI_ACT_X64,
+               EPI_ACT_Z64, EPI_COPY_X64 };
+enum PackKind { PK_LINEAR = 0, PK_PROJ1, PK_PROJ2, PK_FINAL };
+
+struct TcStep {
+  int epi;          // epilogue kind that PRODUCES this step's A operand
+  int N, KS;        // MMA shape: N columns (multiple of 8), KS k-steps of 8
+  int dst_x;        // 1: accumulate into X, 0: overwrite Z
+  int img_off;      // byte offset of the hi image (1024-aligned); the lo image follows at + img_bytes
+  int img_bytes;    // bytes of ONE image
+  int blk;          // gated block of EPI_LN* / EPI_GATE
+  // packing
+  int pk, k_real, n_real, w_off, b_off, alpha_off, k_perm, n_perm, k_selu_scale, bias_col;
+};
+
+struct TcPlan {
+  int n_steps;
+  int image_bytes;   // total bytes of the image buffer
+  int slot_bytes;    // bytes of one ring stage for the x3 mode (largest hi + lo image)
+  TcStep step[MAX_STEPS];
+};
+
+struct TcArgs {
+  const float* wflat;
+  const unsigned char* image;
+  const int* tiles;       // [0] = number of tiles, then (v0, nv) pairs from entry 2
+  PmtBatch batch;
+  PmtOutputs out;
+};
+
+struct SlotMeta {
+  unsigned char rowvar[TILE];   // local variant of each row, 255 = padding
+  unsigned char ref_start[TILE], ref_cnt[TILE], alt_start[TILE], alt_cnt[TILE];
+};
+
+struct Shared {
+  unsigned long long bar_a[2], bar_d[2], wfull[NS_MAX], wfree[NS_MAX];
+  unsigned tmem_base;
+  int pad_;
+  SlotMeta slot[2];
+};
+
+// per gated block scalars staged in shared memory (gated_mlp.py:213-226)
+constexpr int BC_LN2W = 0, BC_LN2B = 12, BC_REG = 24, BC_AREF = 36, BC_AALT = 37, BC_BREF = 38, BC_BALT = 39, BC_GAMMA = 40,
+              BC_REGW = 41, BC_STRIDE = 48;
+
+template <int NC>
+__device__ __forceinline__ void tmem_st_n(unsigned taddr, const unsigned* r) {
+  static_assert(NC == 4 || NC == 8 || NC == 12 || NC == 16 || NC == 32, "unsupported operand width");
+  if (NC == 32) tmem_st32(taddr, r);
+  else if (NC == 16) tmem_st16(taddr, r);
+  else if (NC == 12) { tmem_st8(taddr, r); tmem_st4(taddr + 8, r + 8); }
+  else if (NC == 8) tmem_st8(taddr, r);
+  else tmem_st4(taddr, r);
+}
+
+// Stores v[0..NC) as operand columns [0, NC) (relative to the given addresses) of this thread's row: raw fp32 (the
+// tensor core truncates to TF32) into A_hi and, in the split mode, the truncation remainder into A_lo.
+template <int NC, int PASSES>
+__device__ __forceinline__ void store_operand(unsigned t_hi, unsigned t_lo, const float* v, bool lo_pass) {
+  unsigned r[NC];
+#pragma unroll
+  for (int i = 0; i < NC; ++i) r[i] = __float_as_uint(v[i]);
+  tmem_st_n<NC>(t_hi, r);
+  if (PASSES == 3 && lo_pass) {
+#pragma unroll
+    for (int i = 0; i < NC; ++i) r[i] = __float_as_uint(v[i] - __uint_as_float(r[i] & 0xFFFFE000u));
+    tmem_st_n<NC>(t_lo, r);
+  }
+}
+
+template <int NC>
+__device__ __forceinline__ void load_cols(unsigned taddr, float* v) {
+  static_assert(NC == 16 || NC == 32, "unsupported load width");
+  unsigned r[NC];
+  if (NC == 32) tmem_ld32(taddr, r); else tmem_ld16(taddr, r);
+  tmem_wait_ld();
+#pragma unroll
+  for (int i = 0; i < NC; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// One layer's MMA chain, fully unrolled over k-steps so that every descriptor is a constant offset (the chain then
+// runs at the tensor-core floor of N/2 cycles per instruction, profiles/r1/tc_probe_b200.log).
+template <int KS, int PASSES>
+__device__ __forceinline__ void issue_chain(unsigned d, unsigned a_hi, unsigned a_lo, uint64_t b_hi, uint64_t b_lo, unsigned kb_stride16,
+                                            unsigned idesc, unsigned first_acc, bool lo_pass) {
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+    const uint64_t off = (uint64_t)((ks >> 2) * kb_stride16 + (ks & 3) * 2);
+    mma_ts(d, a_hi + ks * 8, b_hi + off, idesc, ks > 0 ? 1u : first_acc);
+    if (PASSES == 3) {
+      if (lo_pass) mma_ts(d, a_lo + ks * 8, b_hi + off, idesc, 1u);
+      mma_ts(d, a_hi + ks * 8, b_lo + off, idesc, 1u);
+    }
+  }
+}
+
+// 4-way partial sums: short dependency chains for the two warps that share an SM sub-partition
+template <int N>
+__device__ __forceinline__ float sum_n(const float* v) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+  for (int i = 0; i < N; i += 4) { a0 += v[i]; a1 += v[i + 1]; a2 += v[i + 2]; a3 += v[i + 3]; }
+  return (a0 + a1) + (a2 + a3);
+}
+template <int N>
+__device__ __forceinline__ float sumsq_centered_n(const float* v, float m) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+  for (int i = 0; i < N; i += 4) {
+    const float d0 = v[i] - m, d1 = v[i + 1] - m, d2 = v[i + 2] - m, d3 = v[i + 3] - m;
+    a0 = fmaf(d0, d0, a0); a1 = fmaf(d1, d1, a1); a2 = fmaf(d2, d2, a2); a3 = fmaf(d3, d3, a3);
+  }
+  return (a0 + a1) + (a2 + a3);
+}
+
+
+__device__ __forceinline__ int perm64(int j, int d_read) { return j < d_read ? j : 32 + (j - d_read); }   // d_model vector -> X column
+__device__ __forceinline__ int unperm64(int c, int d_read, int d_model) {   // X column -> d_model index or -1
+  if (c < 32) return c < d_read ? c : -1;
+  const int j = d_read + (c - 32);
+  return j < d_model ? j : -1;
+}
+
+__device__ inline float tc_weight(const PmtModelDesc& D, const TcStep& o, const float* __restrict__ w, int n, int k) {
+  const int DR = D.d_read, Dm = D.d_model, H = D.d_ffn / 2;
+  switch (o.pk) {
+    case PK_LINEAR: {
+      const int nn = o.n_perm ? unperm64(n, DR, Dm) : (n < o.n_real ? n : -1);
+      if (nn < 0) return 0.f;
+      const float alpha = o.alpha_off >= 0 ? w[o.alpha_off] : 1.f;
+      if (k == o.bias_col) return alpha * w[o.b_off + nn];
+      const int kk = o.k_perm ? unperm64(k, DR, Dm) : (k < o.k_real ? k : -1);
+      if (kk < 0) return 0.f;
+      return alpha * (o.k_selu_scale ? SELU_SCALE : 1.f) * w[o.w_off + nn * o.k_real + kk];
+    }
+    case PK_PROJ1: {   // [ref set | alt set] side by side in N; LayerNorm affine folded (gated_mlp.py:185-187)
+      const PmtBlockOffsets& BO = D.blocks[o.blk];
+      const int set = n / NP1, c = n - set * NP1;
+      // set layout: z1 (outputs 0..H) at columns 0..H), z2 (outputs H..2H) at columns 12..12+H)
+      int nn = -1;
+      if (c < H) nn = c;
+      else if (c >= NP1 / 2 && c - NP1 / 2 < H) nn = H + (c - NP1 / 2);
+      if (set > 1 || nn < 0) return 0.f;
+      const int w_off = set ? BO.p1_alt_w : BO.p1_ref_w, b_off = set ? BO.p1_alt_b : BO.p1_ref_b;
+      if (k == o.bias_col) {
+        float acc = w[b_off + nn];
+        for (int j = 0; j < Dm; ++j) acc = fmaf(w[w_off + nn * Dm + j], w[BO.ln_b + j], acc);
+        return acc;
+      }
+      const int kk = unperm64(k, DR, Dm);
+      if (kk < 0) return 0.f;
+      return w[w_off + nn * Dm + kk] * w[BO.ln_w + kk];
+    }
+    case PK_PROJ2: {   // ref and alt sets stacked along K (gated_mlp.py:197-198)
+      const PmtBlockOffsets& BO = D.blocks[o.blk];
+      const int nn = unperm64(n, DR, Dm);
+      if (nn < 0) return 0.f;
+      // operand layout: [t_ref k 0..5 | t_alt k 0..5 | t_ref k 6..10 | t_alt k 6..10 | is_ref | is_alt]
+      int unit = -1, set = 0;
+      if (k < 6) { unit = k; set = 0; }
+      else if (k < 12) { unit = k - 6; set = 1; }
+      else if (k < 17) { unit = 6 + (k - 12); set = 0; }
+      else if (k < 22) { unit = 6 + (k - 17); set = 1; }
+      else if (k == 22) return w[BO.p2_ref_b + nn];
+      else return w[BO.p2_alt_b + nn];
+      if (unit >= H) return 0.f;
+      return w[(set ? BO.p2_alt_w : BO.p2_ref_w) + nn * H + unit];
+    }
+    case PK_FINAL: {   // f = Q (W x + b + t): rotation and translation folded (euclidean_transformation.py:19-20)
+      const int E = D.d_feat;
+      if (n >= E) return 0.f;
+      float acc = 0.f;
+      if (k == o.bias_col) {
+        for (int j = 0; j < E; ++j) acc = fmaf(w[D.rotation + n * E + j], w[o.b_off + j] + w[D.translation + j], acc);
+        return acc;
+      }
+      const int kk = unperm64(k, DR, Dm);
+      if (kk < 0) return 0.f;
+      for (int j = 0; j < E; ++j) acc = fmaf(w[D.rotation + n * E + j], w[o.w_off + j * o.k_real + kk], acc);
+      return acc;
+    }
+  }
+  return 0.f;
+}
+
+}  // namespace tc
+}  // namespace pmt
+
+// host: the step program of the forward (pmt_tc.cu)
+void pmt_tc_plan(const pmt::Plan& P, pmt::tc::TcPlan* out);
