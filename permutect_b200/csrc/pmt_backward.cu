@@ -1296,6 +1296,7 @@ size_t pmt_backward_workspace_bytes(const Plan& P, const PmtBatch* batch) {
   bytes += (size_t)kBwdGrid * scr * sizeof(float);                                           // activation scratch
   if (batch) bytes += 2 * (size_t)batch->n_variants * (P.d.d_info + P.d.d_seq) * sizeof(float);   // info_seq, d_info_seq
   bytes += (size_t)long_bwd_grid(P, batch) * long_bwd_floats_per_cta(P, batch) * sizeof(float) + 256;
+  if (pmt_tc_supported(P)) bytes += pmt_tc_bwd_workspace_bytes(P, batch) + 1024;
   return bytes;
 }
 
@@ -1325,6 +1326,12 @@ extern "C" int pmt_backward(const PmtModelDesc* desc, const float* weights, cons
   const int lgrid = long_bwd_grid(P, batch);
   const size_t long_floats = long_bwd_floats_per_cta(P, batch);
   float* long_scratch = reinterpret_cast<float*>(ws + off); off += (size_t)lgrid * long_floats * sizeof(float);
+  // Tile-sized sets go through the tensor-core backward (pmt_tc_bwd.cu) unless the FP32 mode is selected
+  const bool use_tc = pmt_precision_mode() != PMT_PRECISION_FP32 && pmt_tc_supported(P);
+  off = (off + 255) & ~(size_t)255;
+  unsigned char* tc_ws = reinterpret_cast<unsigned char*>(ws + off);
+  const size_t tc_ws_bytes = use_tc ? pmt_tc_bwd_workspace_bytes(P, batch) + 1024 : 0;
+  off += tc_ws_bytes;
   PMT_CHECK(off <= workspace_bytes, "workspace layout overflow");
 
   PMT_CUDA(cudaMemsetAsync(partials, 0, (size_t)kBwdGrid * desc->n_params * sizeof(float), st));
@@ -1360,10 +1367,17 @@ extern "C" int pmt_backward(const PmtModelDesc* desc, const float* weights, cons
   A.trace = g_bwd_trace;
   int grid = A.n_claims < kBwdGrid ? A.n_claims : kBwdGrid;
   if (grid > n_sm) grid = n_sm;
-  PMT_CUDA(cudaFuncSetAttribute(reads_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  pmt_profile_begin(st);
-  reads_backward_kernel<<<grid, NTHREADS, smem, st>>>(P, A);
-  pmt_profile_end(st);
+  int tc_grid = 0;
+  if (use_tc) {
+    if (pmt_launch_reads_tc_backward(P, weights, batch, info_seq, A.d_logits_bk, A.d_alt_means, A.d_ref_means, d_info_seq, tc_ws,
+                                     tc_ws_bytes, n_sm, &tc_grid, st))
+      return 1;
+  } else {
+    PMT_CUDA(cudaFuncSetAttribute(reads_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pmt_profile_begin(st);
+    reads_backward_kernel<<<grid, NTHREADS, smem, st>>>(P, A);
+    pmt_profile_end(st);
+  }
   if (lgrid > 0) {   // sets longer than a tile; same CTA-private gradient buffers, after the tile kernel: fixed order
     PMT_CUDA(cudaFuncSetAttribute(reads_backward_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     reads_backward_long_kernel<<<lgrid, NTHREADS, smem, st>>>(P, A);
@@ -1381,6 +1395,7 @@ extern "C" int pmt_backward(const PmtModelDesc* desc, const float* weights, cons
   }
   if (pmt_launch_cnn_backward(P, G, weights, image, batch, d_info_seq, partials, kBwdGrid, st)) return 1;
   reduce_partials_kernel<<<(desc->n_params + 255) / 256, 256, 0, st>>>(partials, kBwdGrid, desc->n_params, d_weights);
+  if (use_tc && pmt_finish_reads_tc_backward(P, weights, batch, d_weights, tc_ws, tc_grid, st)) return 1;
   if (P.n_skipfix > 0) skip_fix_kernel<<<P.n_skipfix, 256, 0, st>>>(P, weights, d_weights);
   cudaError_t e = cudaGetLastError();
   PMT_CHECK(e == cudaSuccess, "pmt_backward launch failed: %s", cudaGetErrorString(e));

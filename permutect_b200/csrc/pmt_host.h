@@ -46,6 +46,12 @@ size_t pmt_tc_image_bytes(const pmt::Plan& P);
 size_t pmt_tc_tiles_bytes(const PmtBatch* batch);
 int pmt_launch_reads_tc(const pmt::Plan& P, const float* weights, const PmtBatch* batch, const PmtOutputs* out,
                         unsigned char* image_buf, unsigned char* tiles_buf, bool reuse_images, int n_sm, int mode, cudaStream_t st);
+size_t pmt_tc_bwd_workspace_bytes(const pmt::Plan& P, const PmtBatch* batch);
+int pmt_launch_reads_tc_backward(const pmt::Plan& P, const float* weights, const PmtBatch* batch, const float* info_seq,
+                                 const float* d_logits_bk, const float* d_alt_means, const float* d_ref_means, float* d_info_seq,
+                                 unsigned char* ws, size_t ws_bytes, int n_sm, int* grid_out, cudaStream_t st);
+int pmt_finish_reads_tc_backward(const pmt::Plan& P, const float* weights, const PmtBatch* batch, float* d_weights, unsigned char* ws,
+                                 int grid, cudaStream_t st);
 bool pmt_cnn_tc_supported(const pmt::Plan& P);
 size_t pmt_cnn_tc_image_bytes(const pmt::Plan& P);
 int pmt_launch_cnn_tc(const pmt::Plan& P, const float* weights, const PmtBatch* batch, float* info_seq, unsigned char* image,

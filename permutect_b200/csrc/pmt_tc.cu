@@ -31,7 +31,21 @@
 namespace pmt {
 namespace tc {
 
-template <int PASSES, bool TRACE>
+__device__ __forceinline__ float rna_tf32(float v) {
+  unsigned r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+// Training recompute: operand columns [col0, col0 + NC) of `row`, rounded to TF32, into the step's panels (pmt_tc.cuh).
+template <int NC>
+__device__ __forceinline__ void save_operand(unsigned char* op, int row, int col0, const float* v) {
+#pragma unroll
+  for (int i = 0; i < NC / 4; ++i)
+    *reinterpret_cast<float4*>(op + panel_off(row, col0 / 4 + i)) =
+        make_float4(rna_tf32(v[4 * i]), rna_tf32(v[4 * i + 1]), rna_tf32(v[4 * i + 2]), rna_tf32(v[4 * i + 3]));
+}
+
+template <int PASSES, bool TRACE, bool SAVE>
 __global__ void __launch_bounds__(THREADS, 1)
 reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_constant__ TcPlan TP, const __grid_constant__ TcArgs A,
                         int n_stages, int stage_bytes, long long* __restrict__ trace) {
@@ -84,7 +98,9 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
   __syncthreads();
   tc_fence_after();
 
-  const int n_tiles = __ldg(A.tiles);
+  // tiles [tile_first, n_tiles) of the list (the training recompute walks the list in bounded ranges)
+  const int tile_first = SAVE ? A.tile_first : 0;
+  const int n_tiles = SAVE ? min(__ldg(A.tiles), A.tile_limit) - tile_first : __ldg(A.tiles);
   const int n_slots = 2 * gridDim.x;
   // every slot of the CTA runs the same number of rounds (an idle slot processes an empty tile)
   // tile t of round r: slot 0 of every CTA first, then slot 1 (a small batch spreads over the SMs before it doubles up)
@@ -177,7 +193,8 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
       const int t = (int)blockIdx.x + slot * (int)gridDim.x + round * n_slots;
       // ---------------- tile meta ----------------
       int v0 = 0, nv = 0;
-      if (t < n_tiles) { v0 = __ldg(A.tiles + 2 + 2 * t); nv = __ldg(A.tiles + 3 + 2 * t); }
+      if (t < n_tiles) { v0 = __ldg(A.tiles + 2 + 2 * (tile_first + t)); nv = __ldg(A.tiles + 3 + 2 * (tile_first + t)); }
+      unsigned char* const scr = (SAVE && t < n_tiles) ? A.scratch + (size_t)t * TP.tile_bytes : nullptr;
       long long r_base = 0, a_base = 0;
       int ref_pad = 0;
       if (half == 0) M->rowvar[row] = 255;
@@ -207,6 +224,7 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
       TR(1);
       for (int step = 0; step < n_steps; ++step) {
         const int epi = TP.step[step].epi;
+        unsigned char* const scr_op = (SAVE && scr) ? scr + TP.step[step].scr_off : nullptr;
         TR(400 + step);
         switch (epi) {
           case EPI_DECODE: {   // batch.py:51-56, plain_text_data.py:510-511 (quirk Q2: the uint8 de-quantisation wraps)
@@ -267,6 +285,7 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
               }
             }
             if (half == 1) v[31] = 1.f;   // operand column 63: bias
+            if (SAVE && scr_op) save_operand<32>(scr_op, row, half * 32, v);
             store_operand<32, PASSES>(t_hi + half * 32, t_lo + half * 32, v, l0_lo);
           } break;
           case EPI_FIRST32: {   // mlp.py:61-62 then the first DenseSkipBlock's leading SELU (mlp.py:8-22)
@@ -276,9 +295,15 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
 #pragma unroll
             for (int i = 0; i < 16; ++i) { v[i] = SELU_SCALE * selu_u(v[i]); r[i] = __float_as_uint(v[i]); }
             tmem_st16(t_x + half * 16, r);
+            if (SAVE && scr) {
+              float* x0 = reinterpret_cast<float*>(scr + TP.x0_off) + (half * 16) * TILE + row;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) x0[i * TILE] = v[i];
+            }
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = selu_u(v[i]);
             if (half == 1) v[15] = 1.f;   // operand column 31: bias
+            if (SAVE && scr_op) save_operand<16>(scr_op, row, half * 16, v);
             store_operand<16, PASSES>(t_hi + half * 16, t_lo + half * 16, v, true);
           } break;
           case EPI_ACT_Z32:
@@ -288,6 +313,7 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = selu_u(v[i]);
             if (half == 1) v[15] = 1.f;
+            if (SAVE && scr_op) save_operand<16>(scr_op, row, half * 16, v);
             store_operand<16, PASSES>(t_hi + half * 16, t_lo + half * 16, v, true);
           } break;
           case EPI_LN_FIRST:
@@ -318,6 +344,10 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], rstd, shift);
             if (half == 0) v[31] = 1.f;   // operand column 31: bias
+            if (SAVE && scr_op) {
+              save_operand<32>(scr_op, row, half * 32, v);
+              if (half == 0) reinterpret_cast<float*>(scr + TP.rstd_off)[TP.step[step].blk * TILE + row] = rstd;
+            }
             store_operand<32, PASSES>(t_hi + half * 32, t_lo + half * 32, v, true);
           } break;
           case EPI_GATE: {   // gated_mlp.py:186-190, 228-251; this thread gates hidden units [k0, k0 + 6)
@@ -375,6 +405,12 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
               const float zz = half ? z2[j + 6] : z2[j];
               z2n[j] = (zz - mean) * rstd * lds_f32(bcs + (BC_LN2W + k0 + j) * 4) + lds_f32(bcs + (BC_LN2B + k0 + j) * 4);
               if (k0 + j < H) sts_f32(xch + ((k0 + j) * XCH_LD + row) * 4, z2n[j]);
+              if (SAVE && scr) {   // what the backward of the gate needs: xhat2, selu'(z2), (z1 below), 1 / std
+                float* gi = reinterpret_cast<float*>(scr + TP.gate_off) + ((TP.step[step].blk * GATE_ITEMS) * 2 + half) * TILE + row;
+                gi[(6 + j) * 2 * TILE] = (zz - mean) * rstd;
+                gi[(12 + j) * 2 * TILE] = zz > 0.f ? SELU_SCALE : zz + SELU_SCALE * SELU_ALPHA;
+                if (j == 0) gi[18 * 2 * TILE] = rstd;
+              }
             }
             TR(900 + step);
             named_barrier(slot_bar, 256);
@@ -402,6 +438,7 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
                 const float den = (float)cnt + (s == 0 ? regw : 1e-4f);
                 const float m = num / den;
                 sts_f32(sums + (seg * MAXH + f) * 4, m);
+                if (SAVE && scr) reinterpret_cast<float*>(scr + TP.means_off)[(TP.step[step].blk * 2 * BWD_MAXV + seg) * MAXH + f] = m;
               }
             }
             TR(1100 + step);
@@ -427,7 +464,10 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
                     const float m_ref = lds_f32(s_ref + j * 4), m_own = lds_f32(s_own + j * 4);
                     gate = fmaf(beta, m_own, fmaf(gamma, m_ref, gate));
                   }
-                  tk[j] = SELU_SCALE * selu_u(z1s[j]) * gate;
+                  const float z1 = SELU_SCALE * selu_u(z1s[j]);
+                  tk[j] = z1 * gate;
+                  if (SAVE && scr)
+                    reinterpret_cast<float*>(scr + TP.gate_off)[((TP.step[step].blk * GATE_ITEMS + j) * 2 + half) * TILE + row] = z1;
                 }
               }
               if (half == 0) {
@@ -440,6 +480,7 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
                 v[11] = is_alt ? 1.f : 0.f;
               }
             }
+            if (SAVE && scr_op) save_operand<12>(scr_op, row, half * 12, v);
             store_operand<12, PASSES>(t_hi + half * 12, t_lo + half * 12, v, true);
           } break;
           case EPI_ACT_X64:
@@ -454,6 +495,7 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
             }
             if (half == 0) v[31] = 1.f;
             TR(1400 + step);
+            if (SAVE && scr_op) save_operand<32>(scr_op, row, half * 32, v);
             store_operand<32, PASSES>(t_hi + half * 32, t_lo + half * 32, v, true);
           } break;
         }
@@ -480,6 +522,11 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
         if (A.out.final_re && my_idx >= 0) {
 #pragma unroll
           for (int e = 0; e < MAXE; ++e) if (e < E) A.out.final_re[my_idx * E + e] = f[e];
+        }
+        if (SAVE && scr) {
+          float* fo = reinterpret_cast<float*>(scr + TP.f_off) + row;
+#pragma unroll
+          for (int e = 0; e < MAXE; ++e) fo[e * TILE] = e < E ? f[e] : 0.f;
         }
       }
       if (is_alt && my_var >= 0) {
@@ -566,8 +613,11 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
 // same).  One warp per claim of PLAN_CLAIM consecutive variants; tiles never span claims.  tiles[0] = tile count
 // (reserved with one atomicAdd per claim: tile ORDER is arbitrary, results do not depend on it).
 // ------------------------------------------------------------------------------------------------
+// `stage` != nullptr (training): the claim's tiles go to its own region [claim][2 * claim_variants] and their number to
+// counts[claim]; compact_tiles_kernel then lists them in claim order, so the list -- and with it the order in which the
+// backward sums every gradient -- is the same from run to run.
 __global__ void plan_tiles_kernel(const long long* __restrict__ ref_off, const long long* __restrict__ alt_off, int B, int claim_variants,
-                                  int* __restrict__ tiles) {
+                                  int max_nv, int* __restrict__ tiles, int* __restrict__ counts, int* __restrict__ stage) {
   __shared__ int buf[4][2 * PLAN_CLAIM];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int claim = blockIdx.x * 4 + w;
@@ -581,7 +631,7 @@ __global__ void plan_tiles_kernel(const long long* __restrict__ ref_off, const l
     for (int base = 0; base < TILE; base += 32) {
       const int cand = v + base + lane + 1;   // tile would cover [v, cand)
       int fits = 0;
-      if (cand <= c1) {
+      if (cand <= c1 && base + lane < max_nv) {
         const long long nr = __ldg(ref_off + cand) - r_base, na = __ldg(alt_off + cand) - a_base;
         fits = (((nr + 3) & ~3LL) + na <= TILE) ? 1 : 0;
       }
@@ -594,11 +644,43 @@ __global__ void plan_tiles_kernel(const long long* __restrict__ ref_off, const l
     ++n;
     v += nv;
   }
+  __syncwarp();
+  if (stage) {
+    if (lane == 0) counts[claim] = n;
+    for (int i = lane; i < 2 * n; i += 32) stage[(size_t)claim * 2 * claim_variants + i] = buf[w][i];
+    return;
+  }
   int base = 0;
   if (lane == 0) base = atomicAdd(tiles, n);
   base = __shfl_sync(0xffffffffu, base, 0);
-  __syncwarp();
   for (int i = lane; i < 2 * n; i += 32) tiles[2 + 2 * base + i] = buf[w][i];
+}
+
+// One CTA: exclusive scan of the per-claim tile counts, then the claims' tiles copied behind each other.
+__global__ void compact_tiles_kernel(const int* __restrict__ counts, const int* __restrict__ stage, int n_claims, int claim_variants,
+                                     int* __restrict__ tiles) {
+  __shared__ int warp_tot[32];
+  __shared__ int running;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (tid == 0) running = 0;
+  __syncthreads();
+  for (int c0 = 0; c0 < n_claims; c0 += blockDim.x) {
+    const int c = c0 + tid;
+    const int n = c < n_claims ? counts[c] : 0;
+    int inc = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) warp_tot[w] = inc;
+    __syncthreads();
+    int before = running;
+    for (int i = 0; i < w; ++i) before += warp_tot[i];
+    const int first = before + inc - n;
+    for (int i = 0; i < 2 * n; ++i) tiles[2 + 2 * first + i] = stage[(size_t)c * 2 * claim_variants + i];
+    __syncthreads();
+    if (tid == blockDim.x - 1) running = before + inc;
+    __syncthreads();
+  }
+  if (tid == 0) tiles[0] = running;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -731,6 +813,41 @@ void pmt_tc_plan(const Plan& P, TcPlan* out) {
     o.pk = PK_FINAL; o.k_real = l.in_dim; o.n_real = l.out_dim; o.w_off = l.w_off; o.b_off = l.b_off; o.bias_col = 31;
   }
   T.image_bytes = pad_to(T.image_bytes, 1024);
+
+  // ---- training: saved operands, backward program, gradient accumulators (pmt_tc_bwd.cu) ----
+  int scr = 0, timg = 0, part = 0;
+  for (int s = 0; s < T.n_steps; ++s) {
+    TcStep& o = T.step[s];
+    const int width = o.KS * 8, n_panels = (width + 31) / 32;
+    o.scr_off = scr; o.scr_bytes = n_panels * PANEL_BYTES; scr += o.scr_bytes;
+    o.Nd = pad_to(width, 16); o.KSd = o.N / 8;
+    o.t_img_off = timg;
+    o.t_img_bytes = s == 0 ? 0 : ((o.N + 31) / 32) * o.Nd * 128;   // the first layer's input is data: no data gradient
+    timg += pad_to(o.t_img_bytes, 1024);
+    if (o.t_img_bytes > T.t_stage_bytes) T.t_stage_bytes = o.t_img_bytes;
+    o.kw = 32 * n_panels; o.part_off = part; part += o.N * o.kw;
+    if (s + 1 == T.n_steps) { o.bepi = BE_HEAD; continue; }
+    switch (T.step[s + 1].epi) {
+      case EPI_COPY_X64: o.bepi = BE_GINIT64; break;
+      case EPI_ACT_Z64: o.bepi = BE_DZ64; break;
+      case EPI_ACT_X64: o.bepi = BE_GACC64; break;
+      case EPI_GATE: o.bepi = BE_GATE; break;
+      case EPI_LN: o.bepi = BE_LN64; break;
+      case EPI_LN_FIRST: o.bepi = BE_LN_EMBED; break;
+      case EPI_ACT_Z32: o.bepi = BE_DZ32; break;
+      case EPI_ACT_X32: o.bepi = BE_GACC32; break;
+      default: o.bepi = BE_FIRST; break;   // EPI_FIRST32
+    }
+  }
+  T.t_image_bytes = pad_to(timg, 1024);
+  T.x0_off = scr; scr += 32 * TILE * (int)sizeof(float);
+  T.f_off = scr; scr += MAXE * TILE * (int)sizeof(float);
+  T.rstd_off = scr; scr += d.n_blocks * TILE * (int)sizeof(float);
+  T.gate_off = scr; scr += d.n_blocks * GATE_ITEMS * 2 * TILE * (int)sizeof(float);
+  T.means_off = scr; scr += d.n_blocks * 2 * BWD_MAXV * MAXH * (int)sizeof(float);
+  T.tile_bytes = pad_to(scr, 1024);
+  T.scal_off = part;
+  T.part_floats = pad_to(part + 8 * SCAL_W, 64);
 }
 
 static size_t tiles_bytes(int n_variants) { return ((size_t)(2 + 2 * (size_t)n_variants) * sizeof(int) + 255) & ~(size_t)255; }
@@ -747,6 +864,40 @@ static long long* g_reads_trace = nullptr;
 // with (event, clock64) pairs; NULL disarms.
 extern "C" int pmt_set_reads_trace(long long* device_buffer) { g_reads_trace = device_buffer; return 0; }
 
+static int plan_claim_variants(int n_variants, int n_sm) {
+  // planner claims: large enough that the partial last tile of a claim is a small loss, small enough that a small
+  // batch is planned by many warps (each claim is walked sequentially)
+  int claim_variants = n_variants / (2 * n_sm);
+  if (claim_variants < 64) claim_variants = 64;
+  if (claim_variants > PLAN_CLAIM) claim_variants = PLAN_CLAIM;
+  return claim_variants;
+}
+size_t pmt_plan_claim_bytes(int n_variants, int n_sm) {
+  const int cv = plan_claim_variants(n_variants, n_sm);
+  const size_t n_claims = ((size_t)n_variants + cv - 1) / cv;
+  return (n_claims * (1 + 2 * (size_t)cv) * sizeof(int) + 255) & ~(size_t)255;
+}
+// Tile list of a batch: tiles[0] = count, (first variant, variants) pairs from tiles[2].  deterministic: the list order is
+// fixed (claim order); claim_buf: pmt_plan_claim_bytes() bytes.
+int pmt_plan_tiles(const PmtBatch* batch, int max_variants, bool deterministic, int n_sm, int* tiles, int* claim_buf, int* n_claims_out,
+                   cudaStream_t st) {
+  const int claim_variants = plan_claim_variants(batch->n_variants, n_sm);
+  const int n_claims = (batch->n_variants + claim_variants - 1) / claim_variants;
+  if (n_claims_out) *n_claims_out = n_claims;
+  const long long* ro = reinterpret_cast<const long long*>(batch->ref_off);
+  const long long* ao = reinterpret_cast<const long long*>(batch->alt_off);
+  if (!deterministic) {
+    PMT_CUDA(cudaMemsetAsync(tiles, 0, 2 * sizeof(int), st));
+    plan_tiles_kernel<<<(n_claims + 3) / 4, 128, 0, st>>>(ro, ao, batch->n_variants, claim_variants, max_variants, tiles, nullptr, nullptr);
+    return 0;
+  }
+  int* counts = claim_buf;
+  int* stage = claim_buf + n_claims;
+  plan_tiles_kernel<<<(n_claims + 3) / 4, 128, 0, st>>>(ro, ao, batch->n_variants, claim_variants, max_variants, tiles, counts, stage);
+  compact_tiles_kernel<<<1, 1024, 0, st>>>(counts, stage, n_claims, claim_variants, tiles);
+  return 0;
+}
+
 template <int PASSES>
 static int launch_tc(const PmtModelDesc& D, const TcPlan& T, const TcArgs& A, int grid, cudaStream_t st) {
   const int stage_bytes = PASSES == 3 ? T.slot_bytes : T.slot_bytes / 2;
@@ -757,12 +908,31 @@ static int launch_tc(const PmtModelDesc& D, const TcPlan& T, const TcArgs& A, in
   PMT_CHECK(n_stages >= 2, "tensor-core forward: weight ring does not fit in shared memory");
   const size_t smem = fixed + (size_t)n_stages * stage_bytes;
   if (g_reads_trace) {
-    PMT_CUDA(cudaFuncSetAttribute(reads_forward_tc_kernel<PASSES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    reads_forward_tc_kernel<PASSES, true><<<grid, THREADS, smem, st>>>(D, T, A, n_stages, stage_bytes, g_reads_trace);
+    PMT_CUDA(cudaFuncSetAttribute(reads_forward_tc_kernel<PASSES, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    reads_forward_tc_kernel<PASSES, true, false><<<grid, THREADS, smem, st>>>(D, T, A, n_stages, stage_bytes, g_reads_trace);
   } else {
-    PMT_CUDA(cudaFuncSetAttribute(reads_forward_tc_kernel<PASSES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    reads_forward_tc_kernel<PASSES, false><<<grid, THREADS, smem, st>>>(D, T, A, n_stages, stage_bytes, nullptr);
+    PMT_CUDA(cudaFuncSetAttribute(reads_forward_tc_kernel<PASSES, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    reads_forward_tc_kernel<PASSES, false, false><<<grid, THREADS, smem, st>>>(D, T, A, n_stages, stage_bytes, nullptr);
   }
+  return 0;
+}
+
+int pmt_launch_pack_tc(const Plan& P, const TcPlan& T, const float* weights, unsigned char* image, cudaStream_t st) {
+  pack_tc_kernel<<<T.n_steps, 256, 0, st>>>(P.d, T, weights, image);
+  return 0;
+}
+
+// Training recompute (always the split-precision mode: the saved activations are the fp32-parity ones).
+int pmt_launch_reads_tc_save(const Plan& P, const TcPlan& T, const TcArgs& A, int grid, cudaStream_t st) {
+  const int stage_bytes = T.slot_bytes;
+  const size_t fixed = 2 * XCH_ROWS * XCH_LD * sizeof(float) + 2 * SUMS_FLOATS * sizeof(float) + 2 * 2 * TILE * 2 * sizeof(float) +
+                       PMT_MAX_BLOCKS * BC_STRIDE * sizeof(float) + sizeof(HeadConst) + sizeof(Shared) + 1024 + 64;
+  int n_stages = (int)((227 * 1024 - fixed) / stage_bytes);
+  if (n_stages > NS_MAX) n_stages = NS_MAX;
+  PMT_CHECK(n_stages >= 2, "tensor-core forward: weight ring does not fit in shared memory");
+  const size_t smem = fixed + (size_t)n_stages * stage_bytes;
+  PMT_CUDA(cudaFuncSetAttribute(reads_forward_tc_kernel<3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  reads_forward_tc_kernel<3, false, true><<<grid, THREADS, smem, st>>>(P.d, T, A, n_stages, stage_bytes, nullptr);
   return 0;
 }
 
@@ -774,23 +944,16 @@ int pmt_launch_reads_tc(const Plan& P, const float* weights, const PmtBatch* bat
   pmt_tc_plan(P, &T);
   unsigned char* image = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(image_buf) + 1023) & ~uintptr_t(1023));
   int* tiles = reinterpret_cast<int*>((reinterpret_cast<uintptr_t>(tiles_buf) + 255) & ~uintptr_t(255));
-  PMT_CUDA(cudaMemsetAsync(tiles, 0, 2 * sizeof(int), st));
-  // planner claims: large enough that the partial last tile of a claim is a small loss, small enough that a small
-  // batch is planned by many warps (each claim is walked sequentially)
-  int claim_variants = batch->n_variants / (2 * n_sm);
-  if (claim_variants < 64) claim_variants = 64;
-  if (claim_variants > PLAN_CLAIM) claim_variants = PLAN_CLAIM;
-  const int n_claims = (batch->n_variants + claim_variants - 1) / claim_variants;
-  plan_tiles_kernel<<<(n_claims + 3) / 4, 128, 0, st>>>(reinterpret_cast<const long long*>(batch->ref_off),
-                                                         reinterpret_cast<const long long*>(batch->alt_off), batch->n_variants,
-                                                         claim_variants, tiles);
+  int n_claims = 0;
+  if (pmt_plan_tiles(batch, TILE, false, n_sm, tiles, nullptr, &n_claims, st)) return 1;
   if (!reuse_images) pack_tc_kernel<<<T.n_steps, 256, 0, st>>>(P.d, T, weights, image);
   TcArgs A;
   A.wflat = weights; A.image = image; A.tiles = tiles; A.batch = *batch; A.out = *out;
+  A.scratch = nullptr; A.tile_first = 0; A.tile_limit = 0x7fffffff;
   // the tile count is only known on the device: size the grid from the row-count hint (a tile holds ~110 rows of
   // whole variants); one CTA per tile until every SM has one, the second slot of each CTA after that
   const long long rows = batch->n_rows > 0 ? batch->n_rows : 16LL * batch->n_variants;
-  long long est_tiles = rows / 100 + n_claims;
+  long long est_tiles = rows / 100 + n_claims;   // n_claims from pmt_plan_tiles
   if (est_tiles > batch->n_variants) est_tiles = batch->n_variants;
   int grid = est_tiles < n_sm ? (int)est_tiles : n_sm;
   if (grid < 1) grid = 1;

@@ -26,6 +26,23 @@ constexpr int PLAN_CLAIM = 512;   // variants per planner claim
 enum EpiKind { EPI_DECODE = 0, EPI_FIRST32, EPI_ACT_Z32, EPI_ACT_X32, EPI_LN_FIRST, EPI_LN, EPI_GATE, EPI_ACT_X64,
                EPI_ACT_Z64, EPI_COPY_X64 };
 enum PackKind { PK_LINEAR = 0, PK_PROJ1, PK_PROJ2, PK_FINAL };
+// Backward epilogue that turns the data gradient coming out of step s + 1 into dL/d(output of step s) (pmt_tc_bwd.cu)
+enum BwdEpi { BE_HEAD = 0, BE_GINIT64, BE_DZ64, BE_GACC64, BE_GATE, BE_LN64, BE_LN_EMBED, BE_DZ32, BE_GACC32, BE_FIRST };
+
+// ---- training recompute: what the forward leaves in global memory for the tensor-core backward ----
+// An operand of W features is saved as ceil(W / 32) PANELS of [TILE rows][32 floats] (128 bytes per row) whose 32-byte
+// units are XOR-swizzled with row % 4: tcgen05's SWIZZLE_128B_BASE32B layout, the only one an MN-major tf32 operand may
+// have (profiles/microbench/wgrad_probe.cu).  A panel is copied to shared memory with one bulk copy and is then the A
+// operand of the weight-gradient MMA (reduction over the tile's rows) as it lies.
+constexpr int PANEL_BYTES = TILE * 128;
+constexpr int GATE_ITEMS = 19;     // per (row, half) of a gated block: z1[6], xhat2[6], selu'(z2)[6], rstd2
+constexpr int BWD_MAXV = 32;       // variants per tile when the tile list is planned for training
+constexpr int SCAL_BLOCK = 24;     // per-warp scalar gradient slots of one gated block
+constexpr int SCAL_HEAD = 16 + 128;
+constexpr int SCAL_W = PMT_MAX_BLOCKS * SCAL_BLOCK + SCAL_HEAD;
+__host__ __device__ __forceinline__ unsigned panel_off(int row, int chunk) {   // byte offset of 16-byte chunk `chunk` of `row`
+  return (unsigned)((chunk >> 3) * PANEL_BYTES + row * 128 + ((((chunk & 7) >> 1) ^ (row & 3)) << 5) + (chunk & 1) * 16);
+}
 
 struct TcStep {
   int epi;          // epilogue kind that PRODUCES this step's A operand
@@ -36,12 +53,28 @@ struct TcStep {
   int blk;          // gated block of EPI_LN* / EPI_GATE
   // packing
   int pk, k_real, n_real, w_off, b_off, alpha_off, k_perm, n_perm, k_selu_scale, bias_col;
+  // training: saved operand (byte offset / bytes inside a tile's scratch), backward program
+  int scr_off, scr_bytes;
+  int bepi;         // BwdEpi producing dL/d(output of this step)
+  int Nd, KSd;      // data-gradient MMA: N = operand width padded to 16, k-steps = N / 8
+  int t_img_off, t_img_bytes;   // transposed image (hi part only) inside the backward image buffer
+  int part_off, kw; // weight-gradient accumulator [N][kw] (floats) inside a slot's private gradient buffer
 };
 
 struct TcPlan {
   int n_steps;
   int image_bytes;   // total bytes of the image buffer
   int slot_bytes;    // bytes of one ring stage for the x3 mode (largest hi + lo image)
+  // training scratch of one tile (bytes): operand panels (TcStep.scr_off), then
+  int x0_off;        // [32][TILE]  read embedding before the first DenseSkipBlock
+  int f_off;         // [MAXE][TILE] final features
+  int rstd_off;      // [n_blocks][TILE] LayerNorm 1/std of each gated block
+  int gate_off;      // [n_blocks][GATE_ITEMS][2][TILE]
+  int means_off;     // [n_blocks][2 * BWD_MAXV][MAXH] mean fields
+  int tile_bytes;
+  int t_image_bytes, t_stage_bytes;   // backward images: total, largest
+  int part_floats;   // floats of one slot's private gradient buffer: step accumulators, then [8 warps][SCAL_W] scalars
+  int scal_off;
   TcStep step[MAX_STEPS];
 };
 
@@ -51,6 +84,24 @@ struct TcArgs {
   const int* tiles;       // [0] = number of tiles, then (v0, nv) pairs from entry 2
   PmtBatch batch;
   PmtOutputs out;
+  // training recompute (SAVE kernels): tiles [tile_first, tile_limit) of the list, scratch of tile t at
+  // scratch + (t - tile_first) * TcPlan.tile_bytes
+  unsigned char* scratch;
+  int tile_first, tile_limit;
+};
+
+struct TcBwdArgs {
+  const float* wflat;
+  const unsigned char* image_t;   // transposed weight images
+  const int* tiles;
+  PmtBatch batch;
+  const float* d_logits_bk;       // upstream gradients (may be null)
+  const float* d_alt_means;
+  const float* d_ref_means;
+  float* d_info_seq;              // [B][d_info + d_seq]
+  const unsigned char* scratch;
+  int tile_first, tile_limit;
+  float* partials;                // [2 * grid][TcPlan.part_floats]: slot s of CTA b owns buffer 2 b + s
 };
 
 struct SlotMeta {
@@ -209,8 +260,28 @@ __device__ inline float tc_weight(const PmtModelDesc& D, const TcStep& o, const 
   return 0.f;
 }
 
+// value of the backward's dY column nb of a proj1 step as a forward output column (-1: padding).  Backward layout:
+// [half 0: ref z1 (6) | ref z2 (6) | alt z1 (6) | alt z2 (6)][half 1: the same for hidden units 6..11]
+__host__ __device__ __forceinline__ int proj1_bwd_col(int nb, int H) {
+  const int h = nb / 24, r = nb % 24, set = r / 12, z2 = (r % 12) / 6, unit = 6 * h + r % 6;
+  if (unit >= H) return -1;
+  return set * NP1 + (z2 ? NP1 / 2 + unit : unit);
+}
+
 }  // namespace tc
 }  // namespace pmt
 
 // host: the step program of the forward (pmt_tc.cu)
 void pmt_tc_plan(const pmt::Plan& P, pmt::tc::TcPlan* out);
+// host: tensor-core backward of the tile-sized sets (pmt_tc_bwd.cu)
+size_t pmt_tc_bwd_workspace_bytes(const pmt::Plan& P, const PmtBatch* batch);
+int pmt_launch_reads_tc_backward(const pmt::Plan& P, const float* weights, const PmtBatch* batch, const float* info_seq,
+                                 const float* d_logits_bk, const float* d_alt_means, const float* d_ref_means, float* d_info_seq,
+                                 unsigned char* ws, size_t ws_bytes, int n_sm, int* grid_out, cudaStream_t st);
+int pmt_finish_reads_tc_backward(const pmt::Plan& P, const float* weights, const PmtBatch* batch, float* d_weights, unsigned char* ws,
+                                 int grid, cudaStream_t st);
+int pmt_launch_pack_tc(const pmt::Plan& P, const pmt::tc::TcPlan& T, const float* weights, unsigned char* image, cudaStream_t st);
+// training recompute: the forward over tiles [tile_first, tile_limit) of a planned tile list, operands saved to `scratch`
+int pmt_launch_reads_tc_save(const pmt::Plan& P, const pmt::tc::TcPlan& T, const pmt::tc::TcArgs& A, int grid, cudaStream_t st);
+int pmt_plan_tiles(const PmtBatch* batch, int max_variants, bool deterministic, int n_sm, int* tiles, int* claim_buf, int* n_claims_out,
+                   cudaStream_t st);
