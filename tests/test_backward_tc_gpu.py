@@ -1,0 +1,119 @@
+"""Gradient parity of the TENSOR-CORE backward (pmt_backward with a tensor-core precision mode selected: recompute in the
+split-precision mode, then data- and weight-gradient MMAs on TF32 operands rounded to nearest, fp32 accumulation) against
+the gradients the unmodified reference left in param.grad (tests/golden) and against the FP32 kernels.
+
+Stated tolerance of this mode: every tensor with eight or more entries within 4e-3 of its largest entry
+(measured: <= 1.7e-3); the one-entry tensors (gate scalars, DenseSkipBlock.alpha, reg_weight) are sums in which the
+TF32 rounding of the chain does not average out against the tensor's own size, so they are held to 4e-3 of the largest
+small-tensor gradient of the same top-level module.  The FP32 mode keeps the 2e-3 contract (test_backward_gpu.py)."""
+import numpy as np
+import pytest
+import torch
+
+from golden_utils import load
+from helpers import golden_batch, model_from_golden
+from permutect_b200.engine import library as L
+from permutect_b200.utils.enums import Epoch
+
+pytestmark = pytest.mark.gpu
+CASES = ["v040_seed0_b64", "v040_seed0_downsampled", "v040_perturbed_edge", "v040_two_sources"]
+BIG, SMALL = 4e-3, 4e-3
+
+
+@pytest.fixture(autouse=True)
+def _tensor_core_mode():
+    L.set_precision("tf32x3")
+    yield
+    L.set_precision("fp32")
+
+
+def _grads(case):
+    g = load(case)
+    dev = torch.device("cuda:0")
+    model = model_from_golden(g, dev)
+    model.set_epoch_type(Epoch.TRAIN)
+    batch = golden_batch(g, dev)
+    losses = model.compute_batch_losses(model.compute_batch_output(batch), batch)
+    losses.total_loss.backward()
+    return g, {n: (p.grad.detach().cpu().numpy() if p.grad is not None else np.zeros(tuple(p.shape), np.float32))
+               for n, p in model.named_parameters()}
+
+
+def _violations(got, want):
+    family = {}
+    for name, w in want.items():
+        if w.size < 8:
+            top = name.split(".")[0]
+            family[top] = max(family.get(top, 1e-3), float(np.abs(w).max()))
+    bad = []
+    for name, w in want.items():
+        err = float(np.abs(got[name] - w).max())
+        if w.size >= 8:
+            rel, tol = err / max(float(np.abs(w).max()), 1e-3), BIG
+        else:
+            rel, tol = err / family[name.split(".")[0]], SMALL
+        if rel > tol:
+            bad.append((rel, name))
+    return sorted(bad, reverse=True)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_tensor_core_gradients_match_reference(case):
+    g, got = _grads(case)
+    bad = _violations(got, g.grad)
+    assert not bad, "gradient error too large:\n" + "\n".join(f"{e:.3e} {n}" for e, n in bad[:25])
+
+
+def test_tensor_core_gradients_are_bitwise_reproducible():
+    _, a = _grads("v040_perturbed_edge")
+    _, b = _grads("v040_perturbed_edge")
+    for k in a:
+        np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+
+
+def test_large_batch_several_recompute_ranges_against_fp32_kernels():
+    """40 000 WGS-shaped variants: more tiles than one recompute range holds (the backward walks the tile list in bounded
+    ranges), every slot of every CTA busy; compared with the FP32 kernels, which the reference pins."""
+    import bench
+    from permutect_b200.data.batch import Batch
+    from permutect_b200.synthetic import make_wgs_arrays
+    dev = torch.device("cuda:0")
+    model = bench.make_model(dev)
+    model.set_epoch_type(Epoch.TRAIN)
+    batch = Batch.from_arrays(*make_wgs_arrays(40000, seed=3000)).copy_to(dev)
+
+    def grads(mode):
+        L.set_precision(mode)
+        for p in model.parameters():
+            p.grad = None
+        model.compute_batch_losses(model.compute_batch_output(batch), batch).total_loss.backward()
+        return {k: p.grad.detach().cpu().numpy().copy() for k, p in model.named_parameters() if p.grad is not None}
+
+    tc, fp32, tc2 = grads("tf32x3"), grads("fp32"), grads("tf32x3")
+    bad = _violations(tc, fp32)
+    assert not bad, "gradient error too large:\n" + "\n".join(f"{e:.3e} {n}" for e, n in bad[:25])
+    for k in tc:
+        np.testing.assert_array_equal(tc[k], tc2[k], err_msg=k)
+    flat = lambda d: np.concatenate([d[k].ravel() for k in sorted(d)])
+    rel = np.linalg.norm(flat(tc) - flat(fp32)) / np.linalg.norm(flat(fp32))
+    assert rel < 1e-3, f"whole-gradient relative error {rel:.3e}"
+
+
+def test_mixed_long_and_tile_sized_sets():
+    """Sets longer than a tile keep the FP32 long-set kernels; the tile-sized sets around them take the tensor cores."""
+    from helpers import batch_from_raw
+    from oracle import artifact_oracle as orc
+    from test_backward_gpu import _long_set_raw
+    g = load("v040_perturbed_edge")
+    raw = _long_set_raw(11, [(7, 3), (125, 3), (300, 100), (10, 15), (0, 20), (130, 1), (3, 1), (9, 2), (0, 1), (40, 60)])
+    dev = torch.device("cuda:0")
+    model = model_from_golden(g, dev)
+    model.set_epoch_type(Epoch.TRAIN)
+    batch = batch_from_raw(raw, dev)
+    model.compute_batch_losses(model.compute_batch_output(batch), batch).total_loss.backward()
+    names = [n for n, _ in model.named_parameters()]
+    _, _, want = orc.loss_and_grads(g.sd, g.hp, raw, names)
+    got = {n: (p.grad.detach().cpu().numpy() if p.grad is not None else np.zeros(tuple(p.shape), np.float32))
+           for n, p in model.named_parameters()}
+    bad = _violations(got, {k: v.numpy() for k, v in want.items()})
+    assert not bad, "gradient error too large:\n" + "\n".join(f"{e:.3e} {n}" for e, n in bad[:25])
