@@ -44,9 +44,19 @@ FLOP_PER_ALT_READ = 500
 FLOP_PER_VARIANT = 286424
 FP32_FMA_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12      # nominal B200 FP32 pipe
 WORKLOAD = "synthetic WGS-scale inference (SURVEY §8d config 3: 10M variants / 8 GPUs)"
-# DRAM bytes of one launch of the dominant kernel at the default shard (1.25M variants), from the ncu --set full capture
-# committed under profiles/ (dram__bytes_read.sum + dram__bytes_write.sum); scaled by variants for other shard sizes.
-NCU_TRAFFIC_BYTES_PER_VARIANT = {"tf32x3": (416.508e6 + 121.597e6) / 1.25e6, "tf32": None, "fp32": None}
+
+
+def ncu_traffic(precision, n_variants):
+    """DRAM bytes of one launch of the dominant kernel: dram__bytes_read.sum + dram__bytes_write.sum of the `ncu --set full`
+    capture summarised in profiles/ncu_traffic.json (written by profiles/ncu_traffic.py from the .ncu-rep), scaled by variants
+    when the capture ran another shard size.  None when no capture of this precision mode is committed."""
+    path = os.path.join(REPO, "profiles", "ncu_traffic.json")
+    if not os.path.exists(path):
+        return None, None
+    rec = json.load(open(path)).get(precision)
+    if not rec:
+        return None, None
+    return (rec["dram_bytes_read"] + rec["dram_bytes_write"]) * n_variants / rec["variants"], rec.get("source")
 
 
 def load_peaks():
@@ -90,6 +100,26 @@ class ClockSampler:
         reasons = sorted({names[i] for r in self.rows if len(r) >= 8 for i in range(4) if r[4 + i].lower() == "active"})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm)}
+
+
+LIBRARY_KERNEL_PREFIXES = ("pmt::", "tc::", "cnntc::", "loss::", "optim::", "expm::", "post::", "void pmt::", "void tc::")
+
+
+def count_library_launches(fn):
+    """Kernels of libpermutect_b200 launched by one call of fn(), counted from a CUPTI trace (torch.profiler) taken OUTSIDE
+    every timed region.  Returns (library kernels, all kernels) or (None, None) when CUPTI is unavailable."""
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            fn()
+            torch.cuda.synchronize()
+        names = [e.name for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and "Memcpy" not in e.name
+                 and "Memset" not in e.name]
+        mine = [n for n in names if any(tag in n for tag in ("pmt::", "tc::", "cnntc::", "loss::", "optim::", "expm::", "post::"))]
+        return (len(mine), len(names)) if names else (None, None)
+    except Exception:   # noqa: BLE001 - no CUPTI on this box: the claim is then absent, not invented
+        return None, None
 
 
 def make_model(device):
@@ -138,39 +168,119 @@ def time_oracle(model_sd, n_variants, seed, budget_s=20.0, train=False):
     return n_variants / float(np.median(times)), len(times)
 
 
+def reference_setup(state_dict, sizes, seed):
+    """The UNMODIFIED reference (oracle/_ref, oracle/build_ref.py) on the CPU: its ArtifactModel with the bench model's weights
+    and reference Batch objects (collated from its own Datum class) of the same synthetic distribution, one per size."""
+    from oracle import reference
+    from permutect_b200.synthetic import make_wgs_arrays
+    reference.load()
+    import permutect.data.batch as rb
+    import permutect.data.datum as rd
+    from permutect.architecture.artifact_model import ArtifactModel as RefModel
+    from permutect.parameters import ModelParameters as RefParams
+    hp = V040
+    params = RefParams(read_layers=hp["read_layers"], self_attention_hidden_dimension=hp["self_attention_hidden_dimension"],
+                       num_self_attention_layers=hp["num_self_attention_layers"], info_layers=hp["info_layers"],
+                       aggregation_layers=hp["aggregation_layers"], num_artifact_clusters=hp["num_artifact_clusters"],
+                       calibration_layers=hp["calibration_layers"], ref_seq_layers_strings=hp["ref_seq_layer_strings"],
+                       dropout_p=hp["dropout_p"], reweighting_range=hp["reweighting_range"], batch_normalize=hp["batch_normalize"])
+    model = RefModel(params, 61, 71, 42, device=torch.device("cpu"))
+    model.load_state_dict({k: v.detach().cpu() for k, v in state_dict.items()})
+    batches = {}
+    for size in sizes:
+        ia, fa, reads = make_wgs_arrays(size, seed=seed)
+        ref_c, alt_c = ia[:, 0].astype(int), ia[:, 1].astype(int)
+        ref_off, alt_off = np.concatenate(([0], np.cumsum(ref_c))), np.concatenate(([0], np.cumsum(alt_c)))
+        total_ref = ref_off[-1]
+        data = [rd.Datum(ia[v], fa[v], np.vstack((reads[ref_off[v]:ref_off[v + 1]],
+                                                  reads[total_ref + alt_off[v]:total_ref + alt_off[v + 1]])), compressed=True)
+                for v in range(size)]
+        batches[size] = rb.Batch(data)
+    return model, batches
+
+
+def time_reference(model, batch, n_variants, train, budget_s, min_steps=2, max_steps=10, warm=1):
+    """Median step time of the reference's own code path: compute_batch_output (inference) or compute_batch_output +
+    compute_batch_losses + misc_utils.backpropagate (one optimiser step, training/model_training.py:151-165)."""
+    from permutect.misc_utils import backpropagate
+    from permutect.utils.enums import Epoch as RefEpoch
+    torch.set_num_threads(os.cpu_count())
+    opt = None
+    if train:
+        model.set_epoch_type(RefEpoch.TRAIN)
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=0.01)
+    else:
+        model.set_epoch_type(RefEpoch.VALID)
+    times = []
+    t_end = time.perf_counter() + budget_s
+    it = 0
+    while True:
+        t0 = time.perf_counter()
+        if train:
+            out = model.compute_batch_output(batch)
+            losses = model.compute_batch_losses(out, batch)
+            backpropagate(opt, losses.total_loss, params_to_clip=model.parameters())
+        else:
+            with torch.inference_mode():
+                model.compute_batch_output(batch)
+        dt = time.perf_counter() - t0
+        if it >= warm:
+            times.append(dt)
+        it += 1
+        if (time.perf_counter() > t_end and len(times) >= min_steps) or len(times) >= max_steps:
+            break
+    med = float(np.median(times))
+    return {"variants_per_s": n_variants / med, "ms_per_step": 1e3 * med, "steps": len(times), "batch_variants": n_variants}
+
+
+def reference_available():
+    from oracle import reference
+    return reference.available()
+
+
 def run_reference(args, rank):
+    """Reference arm: the reference's own CPU implementation of the path with every host thread, on bounded samples of the
+    workload -- the reference tools' default batch (64 variants: parameters.py:214, filter_variants.py:81) and a large one."""
     if rank != 0:
         return
     model = make_model(torch.device("cpu"))
-    sample = 8192
     steps, warm = max(args.steps, 1), args.warmup
-    from oracle import artifact_oracle as orc
-    from permutect_b200.synthetic import make_wgs_arrays
-    torch.set_num_threads(os.cpu_count())
-    ia, fa, reads = make_wgs_arrays(sample, seed=3000)
-    raw = oracle_inputs(ia, fa, reads)
-    sd = {k: v.detach() for k, v in model.state_dict().items()}
-    ts = []
-    budget_end = time.perf_counter() + 150.0
-    for i in range(warm + steps):
-        t0 = time.perf_counter()
-        with torch.no_grad():
-            orc.forward(sd, V040, raw)
-        if i >= warm:
-            ts.append(time.perf_counter() - t0)
-        if time.perf_counter() > budget_end and len(ts) >= 1:
-            break
-    ms = 1e3 * float(np.mean(ts))
-    v = sample / (ms / 1e3)
-    sample_txt = f"{sample} WGS-shaped variants per step (batch of the same synthetic distribution), {len(ts)} steps"
+    big = 8192
+    if reference_available():
+        kind = "reference"
+        ref_model, batches = reference_setup(model.state_dict(), [64, big, 2048], seed=3000)
+        per_step = max(8.0, 120.0 / (warm + steps))
+        infer_big = time_reference(ref_model, batches[big], big, False, budget_s=90.0, min_steps=1, max_steps=steps, warm=max(warm, 1))
+        infer_64 = time_reference(ref_model, batches[64], 64, False, budget_s=10.0, max_steps=50, warm=3)
+        train_big = time_reference(ref_model, batches[2048], 2048, True, budget_s=30.0, min_steps=1, max_steps=5)
+        train_64 = time_reference(ref_model, batches[64], 64, True, budget_s=10.0, max_steps=30, warm=2)
+        how = "unmodified reference from oracle/_ref (ArtifactModel.compute_batch_output on torch CPU, all host threads)"
+    else:
+        kind = "port"
+        v, n_it = time_oracle(model.state_dict(), big, seed=3000, budget_s=60.0)
+        infer_big = {"variants_per_s": v, "ms_per_step": 1e3 * big / v, "steps": n_it, "batch_variants": big}
+        v, n_it = time_oracle(model.state_dict(), 64, seed=3000, budget_s=10.0)
+        infer_64 = {"variants_per_s": v, "ms_per_step": 1e3 * 64 / v, "steps": n_it, "batch_variants": 64}
+        v, n_it = time_oracle(model.state_dict(), 2048, seed=3001, budget_s=20.0, train=True)
+        train_big = {"variants_per_s": v, "ms_per_step": 1e3 * 2048 / v, "steps": n_it, "batch_variants": 2048}
+        v, n_it = time_oracle(model.state_dict(), 64, seed=3001, budget_s=10.0, train=True)
+        train_64 = {"variants_per_s": v, "ms_per_step": 1e3 * 64 / v, "steps": n_it, "batch_variants": 64}
+        how = "oracle port of the reference (oracle/_ref not built)"
+    best = infer_big if infer_big["variants_per_s"] >= infer_64["variants_per_s"] else infer_64
+    v = best["variants_per_s"]
+    sample_txt = (f"{best['batch_variants']} WGS-shaped variants per step (same synthetic distribution as the shard), "
+                  f"median of {best['steps']} steps; {how}")
     print(json.dumps({
         "impl": "reference", "metric": "artifact_model_inference_variants_per_sec", "value": v, "unit": "variants/s",
-        "n_gpus": args.gpus, "steps": len(ts), "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
+        "n_gpus": args.gpus, "steps": best["steps"], "warmup": warm, "ms_per_step": best["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "precision": "fp32 (torch CPU, all host threads)", "variants_per_gpu": args.variants,
-                   "hyperparameters": "artifact-model-v0.4.0", "sample_variants_per_step": sample},
-        "cpu_baseline": {"value": v, "unit": "variants/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample_txt},
+                   "hyperparameters": "artifact-model-v0.4.0", "sample_variants_per_step": best["batch_variants"]},
+        "cpu_baseline": {"value": v, "unit": "variants/s", "cores": torch.get_num_threads(), "kind": kind, "sample": sample_txt},
         "e2e": {"value": v, "unit": "variants/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "inference": {"batch_64": infer_64, f"batch_{big}": infer_big},
+        "train": {"metric": "artifact_model_training_variants_per_sec", "batch_64": train_64, "batch_2048": train_big,
+                  "step": "compute_batch_output + compute_batch_losses + misc_utils.backpropagate (clip 1.0 + AdamW)"},
     }))
 
 
@@ -227,11 +337,32 @@ def run_training(args, model, ia, fa, reads, dev, world, barrier):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
+    mine, total = count_library_launches(lambda: step(args.warmup + args.steps))
+    # the data-parallel exchange alone: all-reduce of the flat gradient, CUDA events, max over ranks
+    allreduce_us = None
+    if world > 1:
+        buf = torch.zeros_like(opt.flat_grad)
+        for _ in range(5):
+            dist.all_reduce(buf)
+        barrier()
+        ev0.record()
+        for _ in range(20):
+            dist.all_reduce(buf)
+        ev1.record()
+        barrier()
+        ta = torch.tensor([ev0.elapsed_time(ev1) / 20 * 1e3], device=dev)
+        dist.all_reduce(ta, op=dist.ReduceOp.MAX)
+        allreduce_us = float(ta.item())
     model.set_epoch_type(Epoch.VALID)
+    from permutect_b200.engine import library as pmt_lib
     return {"metric": "artifact_model_training_variants_per_sec", "value": bt * world / (ms_max / 1e3), "unit": "variants/s",
             "ms_per_step": ms_max, "batch_variants_per_gpu": bt, "last_loss_per_variant": float(losses.total_loss.detach()) / bt,
-            "backward_kernel_ms": prof.mean_ms(), "gpu_launches": 24 * args.steps,   # library kernels per step (profiles/r1/launches_bench_default_summary.txt)
-            "step": "device DownsampledBatch + compute_batch_output + compute_batch_losses (fused loss head) + backward (FP32 SIMT) + "
+            "backward_kernel_ms": prof.mean_ms(), "gpu_launches_per_step": mine, "all_kernels_per_step": total,
+            "gpu_launches": mine * args.steps if mine is not None else None,
+            "allreduce_us": allreduce_us, "allreduce_bytes": 4 * opt.flat_grad.numel(),
+            "backward": ("tcgen05 (recompute + TF32 data / weight gradient MMAs, pmt_tc_bwd.cu)" if pmt_lib.get_precision() != "fp32"
+                         else "FP32 SIMT"),
+            "step": "device DownsampledBatch + compute_batch_output + compute_batch_losses (fused loss head) + backward + "
                     "flat grad all-reduce + clip(1.0) + AdamW (FlatAdamW)"}
 
 
@@ -359,7 +490,7 @@ def main():
     ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "tf32"],
                     help="arithmetic of the forward's dense layers: tf32x3 = split-precision TF32 on tcgen05 (fp32 parity, "
                          "logits within 1e-3 of the reference), fp32 = FP32 SIMT, tf32 = plain TF32 (looser, stated tolerance); "
-                         "the backward always runs FP32")
+                         "the backward of the tensor-core modes runs on tcgen05 in TF32 (stated gradient tolerance), fp32's on the FP32 pipe")
     ap.add_argument("--e2e-batches", type=int, default=8, help="host batches the shard is delivered in for the e2e leg")
     ap.add_argument("--panel-variants", type=int, default=1024,
                     help="variants per GPU of the high-depth panel sample (config 5, ~2 050 reads each); 0 skips it")
@@ -424,6 +555,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     step_ms_max = float(t.item())
     value = args.variants * world / (step_ms_max / 1e3)
+    with torch.inference_mode():
+        fwd_launches, _ = count_library_launches(lambda: model.compute_batch_output(dev_batch))
 
     # ---- end to end through the public API: pinned host batches -> prefetch_generator (H2D on a side stream) ->
     #      compute_batch_output -> D2H of the logits; every byte of the shard crosses PCIe inside the timed region ----
@@ -477,6 +610,15 @@ def main():
                       "sign_flips": int(((got > 0) != (want > 0)).sum()),
                       "fp16_rounding_changes": int((got.half() != want.half()).sum()), "n": int(got.numel())}
 
+    # ---- decision identity against the ORACLE chain (outside every timed region): sign flips, fp16 changes of the cached
+    #      logit, posterior call flips on a 65 536-variant sample whose logits straddle 0 (tests/test_decision_identity_gpu.py) ----
+    if parity is not None and rank == 0 and not args.no_cpu_baseline:
+        from test_decision_identity_gpu import decision_counts, straddling_model
+        counts, _ = decision_counts(straddling_model(dev), dev, 65536, seed=9100)
+        parity["oracle_chain"] = dict(counts, against="oracle logits -> fp16 -> posterior oracle vs this path -> pmt_pack_posterior -> "
+                                                      "pmt_posterior_log_posteriors; bench model with the calibration spread narrowed")
+        pmt_lib.set_precision(args.precision)
+
     # ---- training: downsample -> forward -> losses -> backward -> (all-reduce) -> clip -> AdamW ----------------
     train = None
     if not args.no_train:
@@ -494,6 +636,7 @@ def main():
         return
 
     peaks = load_peaks()
+    traffic, traffic_source = ncu_traffic(args.precision, args.variants)
     flops = FLOP_PER_READ * n_reads + FLOP_PER_ALT_READ * n_alt        # the read kernel's algorithmic work
     achieved = flops / (read_kernel_ms / 1e3) / 1e12 if read_kernel_ms else None
     kernel_name = {"fp32": "reads_forward_kernel (FP32 SIMT)", "tf32x3": "reads_forward_tc_kernel<3> (tcgen05, split TF32x3)",
@@ -501,9 +644,7 @@ def main():
     roofline = {"bound": "tensor", "kernel": kernel_name, "achieved": achieved,
                 "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16"] if achieved else None,
                 "peak_source": peaks["source"] + " bf16 dense (sustained)",
-                "traffic": (NCU_TRAFFIC_BYTES_PER_VARIANT[args.precision] * args.variants
-                            if NCU_TRAFFIC_BYTES_PER_VARIANT[args.precision] else None),
-                "traffic_unit": "bytes per launch (ncu dram read + write, profiles/r1_tensor_core_kernels.md)",
+                "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read + write)", "traffic_source": traffic_source,
                 "algorithmic_bytes_per_launch": 12 * n_reads + (30 * 4 + 16 + 108) * args.variants,
                 "kernel_ms": read_kernel_ms, "kernel_share_of_step": read_kernel_ms / step_ms if read_kernel_ms else None,
                 "fp32_fma_peak_tflops_nominal": FP32_FMA_PEAK_TFLOPS,
@@ -524,7 +665,8 @@ def main():
                    "variants_per_gpu": args.variants, "reads_per_gpu": n_reads, "mean_reads_per_variant": n_reads / args.variants,
                    "hyperparameters": "artifact-model-v0.4.0", "timing": "inputs larger than L2 (compressed shard "
                    f"{h2d / 2**20:.0f} MiB), CUDA events, max over ranks"},
-        "clocks": clocks, "gpu_launches": 9 * args.steps,
+        "clocks": clocks, "gpu_launches": fwd_launches * args.steps if fwd_launches is not None else None,
+        "gpu_launches_per_step": fwd_launches, "gpu_launches_how": "library kernels of one step counted from a CUPTI trace outside the timed region",
         "e2e": {"value": e2e_value, "unit": "variants/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * args.variants},
         "roofline": roofline,
     }
@@ -535,21 +677,37 @@ def main():
         result["parity"] = parity
     if train is not None:
         result["train"] = train
-        result["gpu_launches"] = 9 * args.steps + train["gpu_launches"]
+        if result["gpu_launches"] is not None and train.get("gpu_launches") is not None:
+            result["gpu_launches"] += train["gpu_launches"]
     if panel is not None:
         result["panel"] = panel
         result["posterior"] = run_posterior(args.variants, dev)
         result["train"]["small_batch"] = small_batch
     if not args.no_cpu_baseline:
         sample = 8192
-        v, n_it = time_oracle(model.state_dict(), sample, seed=3000, budget_s=15.0)
-        result["cpu_baseline"] = {"value": v, "unit": "variants/s", "cores": torch.get_num_threads(), "kind": "port",
-                                  "sample": f"oracle forward on {sample} WGS-shaped variants per batch, median of {n_it} batches"}
-        if train is not None:
-            vt, n_it = time_oracle(model.state_dict(), 2048, seed=3001, budget_s=10.0, train=True)
-            result["cpu_baseline"]["train_value"] = vt
-            result["cpu_baseline"]["train_sample"] = (f"oracle forward + losses + autograd backward on 2048 WGS-shaped variants per "
-                                                      f"step, median of {n_it} steps")
+        if reference_available():
+            ref_model, batches = reference_setup(model.state_dict(), [64, sample, 2048], seed=3000)
+            big = time_reference(ref_model, batches[sample], sample, False, budget_s=10.0, min_steps=2, max_steps=5)
+            b64 = time_reference(ref_model, batches[64], 64, False, budget_s=3.0, max_steps=30, warm=2)
+            result["cpu_baseline"] = {"value": big["variants_per_s"], "unit": "variants/s", "cores": torch.get_num_threads(), "kind": "reference",
+                                      "sample": f"unmodified reference (oracle/_ref) compute_batch_output on {sample} WGS-shaped variants per "
+                                                f"batch, median of {big['steps']} batches", "batch_64": b64}
+            if train is not None:
+                tb = time_reference(ref_model, batches[2048], 2048, True, budget_s=8.0, min_steps=2, max_steps=4)
+                t64 = time_reference(ref_model, batches[64], 64, True, budget_s=3.0, max_steps=20, warm=2)
+                result["cpu_baseline"]["train_value"] = tb["variants_per_s"]
+                result["cpu_baseline"]["train_sample"] = ("reference compute_batch_output + compute_batch_losses + misc_utils.backpropagate on "
+                                                          f"2048 WGS-shaped variants per step, median of {tb['steps']} steps")
+                result["cpu_baseline"]["train_batch_64"] = t64
+        else:
+            v, n_it = time_oracle(model.state_dict(), sample, seed=3000, budget_s=15.0)
+            result["cpu_baseline"] = {"value": v, "unit": "variants/s", "cores": torch.get_num_threads(), "kind": "port",
+                                      "sample": f"oracle forward on {sample} WGS-shaped variants per batch, median of {n_it} batches"}
+            if train is not None:
+                vt, n_it = time_oracle(model.state_dict(), 2048, seed=3001, budget_s=10.0, train=True)
+                result["cpu_baseline"]["train_value"] = vt
+                result["cpu_baseline"]["train_sample"] = (f"oracle forward + losses + autograd backward on 2048 WGS-shaped variants per "
+                                                          f"step, median of {n_it} steps")
     print(json.dumps(result))
     if world > 1:
         dist.destroy_process_group()
