@@ -437,9 +437,40 @@ def run_small_batch_training(model, dev, batch_variants=64, steps=100):
         train_step(model, DownsampledBatch(parent, frac, frac, seed=100 + i), opt)
     torch.cuda.synchronize()
     ms = 1e3 * (time.perf_counter() - t0) / steps
+    # the same step replayed from a CUDA graph (engine/graphs.py): the downsampling draw stays eager (fresh seed per step)
+    from permutect_b200.engine.graphs import GraphedInference, GraphedTrainStep
+    graphed = GraphedTrainStep(model, opt, DownsampledBatch(parent, frac, frac, seed=1))
+    for i in range(10):
+        graphed(DownsampledBatch(parent, frac, frac, seed=i))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        graphed(DownsampledBatch(parent, frac, frac, seed=100 + i))
+    torch.cuda.synchronize()
+    ms_graph = 1e3 * (time.perf_counter() - t0) / steps
     model.set_epoch_type(Epoch.VALID)
+    # inference at the same batch size: eager call and graph replay
+    infer = GraphedInference(model, parent)
+
+    def per_call(fn, n=300):
+        for _ in range(20):
+            fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        torch.cuda.synchronize()
+        return 1e6 * (time.perf_counter() - t0) / n
+
+    with torch.inference_mode():
+        us_eager = per_call(lambda: model.compute_batch_output(parent))
+    us_graph = per_call(lambda: infer(parent))
     return {"batch_variants": batch_variants, "ms_per_step": ms, "variants_per_s": batch_variants / (ms / 1e3), "steps": steps,
-            "timing": "wall clock around the loop with a synchronize on both sides (host-bound regime)"}
+            "graphed_ms_per_step": ms_graph, "graphed_variants_per_s": batch_variants / (ms_graph / 1e3),
+            "inference_us_per_call": us_eager, "inference_graphed_us_per_call": us_graph,
+            "inference_variants_per_s": batch_variants / (min(us_eager, us_graph) / 1e6),
+            "timing": "wall clock around the loop with a synchronize on both sides; eager = host-bound, graphed = bound by the "
+                      "latency of the kernel chain (one tile walks 24 layers forward, 48 backward)"}
 
 
 def run_posterior(n, dev):

@@ -15,7 +15,36 @@ _WORKSPACES: Dict[torch.device, torch.Tensor] = {}
 _PREPARED: Dict[torch.device, tuple] = {}
 
 
+_WS_OVERRIDE: Dict[torch.device, torch.Tensor] = {}
+
+
+class use_workspace:
+    """Route the library calls of this device to a caller-owned workspace (engine/graphs.py: a captured CUDA graph must keep
+    writing to the memory it was captured with, whatever later eager calls do to the shared workspace)."""
+
+    def __init__(self, device: torch.device, tensor: torch.Tensor):
+        self.device, self.tensor = torch.device(device), tensor
+
+    def __enter__(self):
+        self.prev = _WS_OVERRIDE.get(self.device)
+        _WS_OVERRIDE[self.device] = self.tensor
+        _PREPARED[self.device] = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev is None:
+            _WS_OVERRIDE.pop(self.device, None)
+        else:
+            _WS_OVERRIDE[self.device] = self.prev
+        _PREPARED[self.device] = None
+
+
 def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    own = _WS_OVERRIDE.get(device)
+    if own is not None:
+        if own.numel() < nbytes:
+            raise RuntimeError(f"private workspace too small: {own.numel()} < {nbytes}")
+        return own
     ws = _WORKSPACES.get(device)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=device)
