@@ -7,12 +7,14 @@ slower than the model on a CPU.  Here a batch is three contiguous slices -- rows
 map, and the matching slice of the compressed-reads map in DATASET order -- and the ref/alt regrouping becomes a
 gather-index array written on the device (``Batch.from_dataset_slice`` -> pmt_dataset_read_indices).
 """
-from typing import Iterator, Optional
+import random
+from typing import Iterator, List, Optional
 
 import numpy as np
+import torch
 
-from permutect_b200.data.batch import Batch
-from permutect_b200.data.datum import Data
+from permutect_b200.data.batch import Batch, BatchIndexedTensor, BatchProperty
+from permutect_b200.data.datum import Data, Datum, HAPLOTYPES_START_IDX, INFO_START_IDX, num_read_features
 
 
 class MemoryMappedBatches:
@@ -42,3 +44,160 @@ class MemoryMappedBatches:
             batch = Batch.from_dataset_slice(np.asarray(self.int_mmap[v0:v1]), np.asarray(self.float_mmap[v0:v1]),
                                              np.asarray(self.reads_mmap[r0:r1]))
             yield batch.pin_memory() if self.pin_memory else batch
+
+
+# ---- fold helpers (reads_dataset.py:26-40) ---------------------------------------------------------------------------
+def last_fold_only(num_folds: int):
+    return [num_folds - 1]
+
+
+def all_but_last_fold(num_folds: int):
+    return list(range(num_folds - 1))
+
+
+def all_but_one_fold(num_folds: int, fold_to_exclude: int):
+    return list(range(fold_to_exclude)) + list(range(fold_to_exclude + 1, num_folds))
+
+
+def all_folds(num_folds: int):
+    return list(range(num_folds))
+
+
+def batch_order_rows(read_start: np.ndarray, ref_counts: np.ndarray, alt_counts: np.ndarray, order: np.ndarray) -> np.ndarray:
+    """Row indices into a dataset-order reads array that lay the variants ``order`` out as a batch: all their ref rows, then
+    all their alt rows (batch.py:45-47).  ``read_start[v]`` is the first row of variant v."""
+    rc, ac = ref_counts[order], alt_counts[order]
+    n_ref, n_alt = int(rc.sum()), int(ac.sum())
+    ref_first = np.concatenate(([0], np.cumsum(rc)))[:-1]
+    alt_first = np.concatenate(([0], np.cumsum(ac)))[:-1]
+    ref_rows = np.repeat(read_start[order] - ref_first, rc) + np.arange(n_ref)
+    alt_rows = np.repeat(read_start[order] + rc - alt_first, ac) + np.arange(n_alt)
+    return np.concatenate((ref_rows, alt_rows))
+
+
+class ReadsDataset:
+    """reads_dataset.py:46-196 over a ``MemoryMappedData``: fold selection, totals by source / label / variant type / counts,
+    and the reference's iteration order -- the variant range is cut into chunks that fit in RAM, the chunks are visited in
+    shuffled order and the variants of a chunk in shuffled order (``random.shuffle``, so a seeded ``random`` reproduces the
+    reference's order exactly).  ``__iter__`` yields Datum objects like the reference; ``batches()`` / ``make_data_loader()``
+    yield the same variants in the same order already collated: one fancy-index gather per array and batch instead of one
+    Python object per variant."""
+
+    def __init__(self, memory_mapped_data, num_folds: int = 1, folds_to_use: Optional[List[int]] = None, keep_probs_by_label_l=None,
+                 chunks: Optional[int] = None):
+        self.memory_mapped_data = memory_mapped_data.restrict_to_folds(num_folds, folds_to_use, keep_probs_by_label_l)
+        d = self.memory_mapped_data
+        self._size = d.num_data
+        self._read_end_indices = d.read_end_indices
+        self._int_array_ve, self._float_array_ve, self._stacked_reads_re = d.int_mmap, d.float_mmap, d.reads_mmap
+        self._chunks = chunks
+        ints = np.asarray(d.int_mmap[: d.num_data])
+        self._num_read_features = num_read_features(d.reads_mmap.shape[1]) if d.reads_mmap is not None else 0
+        self._num_info_features = d.float_mmap.shape[1] - INFO_START_IDX
+        self._haplotypes_length = d.int_mmap.shape[1] - HAPLOTYPES_START_IDX
+        # totals_slvra (reads_dataset.py:83-88) without a Datum loop: one scatter-add over the whole int array
+        n_sources = int(ints[:, Data.SOURCE.idx].max()) + 1 if len(ints) else 1
+        self.totals_slvra = BatchIndexedTensor.zeros(num_sources=n_sources, include_logits=False, device=torch.device("cpu"))
+        if len(ints):
+            probe = Batch.__new__(Batch)
+            probe.int_tensor = torch.from_numpy(np.ascontiguousarray(ints))
+            probe._size = len(ints)
+            probe._device_counts = None
+            probe.lazy_batch_indices = {False: None, True: None}
+            self.totals_slvra.record(probe, torch.ones(len(ints)))
+        self.totals_by_label_l = self.totals_slvra.get_marginal(BatchProperty.LABEL)
+
+    def __len__(self):
+        return self._size
+
+    def totals_by_label(self):
+        return self.totals_by_label_l
+
+    def num_read_features(self) -> int:
+        return self._num_read_features
+
+    def num_info_features(self) -> int:
+        return self._num_info_features
+
+    def haplotypes_length(self) -> int:
+        return self._haplotypes_length
+
+    def num_sources(self) -> int:
+        return self.totals_slvra.num_sources()
+
+    def _chunk_count(self) -> int:
+        if self._chunks is not None:
+            return self._chunks
+        import psutil
+        return 1 + ((8 * self.memory_mapped_data.num_bytes()) // psutil.virtual_memory().available)   # reads_dataset.py:126-128
+
+    def _chunk_plan(self, start: int, stop: int):
+        """(chunk start, chunk stop, shuffled local order) in the reference's visiting order (reads_dataset.py:141-176)."""
+        n_chunks = self._chunk_count()
+        per_chunk = (stop - start) // n_chunks
+        chunks = list(range(n_chunks))
+        random.shuffle(chunks)
+        for chunk in chunks:
+            c0 = start + chunk * per_chunk
+            c1 = start + (chunk + 1) * per_chunk if chunk < n_chunks - 1 else stop
+            indices = list(range(c1 - c0))
+            random.shuffle(indices)
+            yield c0, c1, np.asarray(indices, dtype=np.int64)
+
+    def __iter__(self) -> Iterator[Datum]:
+        d = self.memory_mapped_data
+        for c0, c1, order in self._chunk_plan(0, self._size):
+            for idx in order + c0:
+                r0, r1 = int(d.read_start_indices[idx]), int(d.read_start_indices[idx + 1])
+                yield Datum(d.int_mmap[idx], d.float_mmap[idx], d.reads_mmap[r0:r1], compressed=True)
+
+    def batches(self, batch_size: int, pin_memory: bool = False, start: int = 0, stop: Optional[int] = None) -> Iterator[Batch]:
+        """The batches ``DataLoader(self, batch_size, collate_fn=Batch)`` builds from ``__iter__`` (make_data_loader,
+        reads_dataset.py:200-209), for variants [start, stop) -- the contiguous shard of one rank."""
+        d = self.memory_mapped_data
+        stop = self._size if stop is None else min(stop, self._size)
+        carry = None       # variants of a chunk's tail wait for the next chunk (a DataLoader batch may straddle chunks)
+        for c0, c1, order in self._chunk_plan(start, stop):
+            r0, r1 = int(d.read_start_indices[c0]), int(d.read_start_indices[c1])
+            ints, floats = np.asarray(d.int_mmap[c0:c1]), np.asarray(d.float_mmap[c0:c1])     # the chunk, sequentially, into RAM
+            reads = np.asarray(d.reads_mmap[r0:r1])
+            rstart = d.read_start_indices[c0:c1] - r0
+            rc = ints[:, Data.REF_COUNT.idx].astype(np.int64)
+            ac = ints[:, Data.ALT_COUNT.idx].astype(np.int64)
+            pos = 0
+            if carry is not None:
+                take = min(batch_size - len(carry[0]), len(order))
+                sel = order[:take]
+                pos = take
+                part = (ints[sel], floats[sel], [reads[rstart[v]:rstart[v] + rc[v]] for v in sel], [reads[rstart[v] + rc[v]:rstart[v] + rc[v] + ac[v]] for v in sel])
+                carry = (np.concatenate((carry[0], part[0])), np.concatenate((carry[1], part[1])), carry[2] + part[2], carry[3] + part[3])
+                if len(carry[0]) == batch_size:
+                    yield self._finish(Batch.from_arrays(carry[0], carry[1], np.concatenate(carry[2] + carry[3])), pin_memory)
+                    carry = None
+            while pos + batch_size <= len(order):
+                sel = order[pos:pos + batch_size]
+                pos += batch_size
+                yield self._finish(Batch.from_arrays(ints[sel], floats[sel], reads[batch_order_rows(rstart, rc, ac, sel)]), pin_memory)
+            if pos < len(order):
+                sel = order[pos:]
+                carry = (ints[sel], floats[sel], [reads[rstart[v]:rstart[v] + rc[v]] for v in sel],
+                         [reads[rstart[v] + rc[v]:rstart[v] + rc[v] + ac[v]] for v in sel])
+        if carry is not None:
+            yield self._finish(Batch.from_arrays(carry[0], carry[1], np.concatenate(carry[2] + carry[3])), pin_memory)
+
+    @staticmethod
+    def _finish(batch: Batch, pin_memory: bool) -> Batch:
+        return batch.pin_memory() if pin_memory else batch
+
+    def make_data_loader(self, batch_size: int, pin_memory: bool = False, num_workers: int = 0):
+        """An iterable of Batch (a fresh shuffled pass per ``iter()``).  ``num_workers`` is accepted for API parity: collation
+        is a handful of numpy gathers per batch, there is nothing left to hand to worker processes."""
+        dataset = self
+
+        class _Loader:
+            def __iter__(self_inner):
+                return dataset.batches(batch_size, pin_memory)
+
+            def __len__(self_inner):
+                return (len(dataset) + batch_size - 1) // batch_size
+        return _Loader()

@@ -124,9 +124,15 @@ class FlatAdamW(torch.optim.Optimizer):
         assert closure is None
         grad, mask = self._flat_path_gradient() if self._flat_grad_valid else self.flat_gradient()
         if process_group is not None or pdist.is_initialized():
-            torch.distributed.all_reduce(grad, op=torch.distributed.ReduceOp.SUM, group=process_group)
-            if mask is not None:     # a parameter frozen on this rank only must still be updated
-                torch.distributed.all_reduce(mask, op=torch.distributed.ReduceOp.MAX, group=process_group)
+            if mask is None:
+                torch.distributed.all_reduce(grad, op=torch.distributed.ReduceOp.SUM, group=process_group)
+            else:
+                # ONE collective for both: a parameter frozen on this rank only must still be updated, and the kernel only
+                # tests mask != 0, so the masks are summed along with the gradients
+                n = grad.numel()
+                packed = torch.cat((grad, mask))
+                torch.distributed.all_reduce(packed, op=torch.distributed.ReduceOp.SUM, group=process_group)
+                grad, mask = packed[:n], packed[n:]
         g = self.param_groups[0]
         self._step += 1
         lib = L.load()
