@@ -23,8 +23,8 @@
 // and TF32x3 (hi/lo split of both operands, Ahi.Bhi + Alo.Bhi + Ahi.Blo, ~2^-20 relative error: the fp32-parity
 // mode).  Tiles are planned by plan_tiles_kernel (greedy packing of whole variants, one warp per claim) so that
 // every role of every CTA knows its tile list up front.
+#include <cstdlib>
 #include <cstring>
-
 
 #include "pmt_tc.cuh"
 
@@ -46,7 +46,7 @@ __device__ __forceinline__ void save_operand(unsigned char* op, int row, int col
 }
 
 template <int PASSES, bool TRACE, bool SAVE>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(FWD_THREADS, 1)
 reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_constant__ TcPlan TP, const __grid_constant__ TcArgs A,
                         int n_stages, int stage_bytes, long long* __restrict__ trace) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -57,7 +57,8 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
   const unsigned sums_all = smem_addr(p); p += 2 * SUMS_FLOATS * sizeof(float);
   const unsigned pairx_all = smem_addr(p); p += 2 * 2 * TILE * 2 * sizeof(float);
   float* blkc = reinterpret_cast<float*>(p); p += PMT_MAX_BLOCKS * BC_STRIDE * sizeof(float);
-  HeadConst* HC = reinterpret_cast<HeadConst*>(p); p += sizeof(HeadConst);
+  HeadConstTc* HCT = reinterpret_cast<HeadConstTc*>(p); p += sizeof(HeadConstTc);
+  HeadConst* HC = &HCT->h;
   Shared* S = reinterpret_cast<Shared*>((reinterpret_cast<uintptr_t>(p) + 15) & ~uintptr_t(15));
 
   const int tid = threadIdx.x;
@@ -70,12 +71,22 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
   long long* tr = trace + (tr_w < 0 ? 0 : tr_w) * 2048;
   auto TR = [&](int id) { if (TRACE && tr_on && tr_n < 1020) { tr[2 * tr_n] = id; tr[2 * tr_n + 1] = clock64(); ++tr_n; } };
   if (tid == 0) {
-    for (int s = 0; s < 2; ++s) { mbar_init(smem_addr(&S->bar_a[s]), 8); mbar_init(smem_addr(&S->bar_d[s]), 1); }
-    for (int i = 0; i < n_stages; ++i) { mbar_init(smem_addr(&S->wfull[i]), 1); mbar_init(smem_addr(&S->wfree[i]), 2); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_addr(&S->bar_a[s]), 8); mbar_init(smem_addr(&S->bar_d[s]), 1);
+      for (int b = 0; b < 2; ++b) { mbar_init(smem_addr(&S->meta_full[s][b]), 1); mbar_init(smem_addr(&S->meta_free[s][b]), 8); }
+    }
+    for (int i = 0; i < n_stages; ++i) { mbar_init(smem_addr(&S->wfull[i]), 1); mbar_init(smem_addr(&S->wfree[i]), A.sched == 1 ? 1 : 2); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     head_constants(D, W, HC);
+    for (int e = 0; e < MAXE; ++e) HCT->inv_sigma[e] = e < D.d_feat ? 1.f / HC->sigma[e] : 0.f;
+    for (int k = 0; k < MAXK; ++k) {
+      const bool on = k < D.n_clusters;
+      HCT->inv_two_tau2[k] = on ? 1.f / HC->two_tau2[k] : 0.f;
+      HCT->inv_sqrt2_sigma[k] = on ? 1.f / HC->sqrt2_sigma[k] : 0.f;
+      for (int e = 0; e < MAXE; ++e) HCT->unit[k][e] = (on && e < D.d_feat) ? W[D.unit_ke + k * D.d_feat + e] : 0.f;
+    }
   }
-  for (int i = tid; i < D.n_blocks * BC_STRIDE; i += THREADS) {
+  for (int i = tid; i < D.n_blocks * BC_STRIDE; i += FWD_THREADS) {
     const PmtBlockOffsets& BO = D.blocks[i / BC_STRIDE];
     const int c = i % BC_STRIDE, H = D.d_ffn / 2;
     float v = 0.f;
@@ -101,7 +112,8 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
   // tiles [tile_first, n_tiles) of the list (the training recompute walks the list in bounded ranges)
   const int tile_first = SAVE ? A.tile_first : 0;
   const int n_tiles = SAVE ? min(__ldg(A.tiles), A.tile_limit) - tile_first : __ldg(A.tiles);
-  const int n_slots = 2 * gridDim.x;
+  const int sched = A.sched;
+  const int n_slots = (sched == 1 ? 1 : 2) * gridDim.x;
   // every slot of the CTA runs the same number of rounds (an idle slot processes an empty tile)
   // tile t of round r: slot 0 of every CTA first, then slot 1 (a small batch spreads over the SMs before it doubles up)
   const int rounds = n_tiles > (int)blockIdx.x ? (n_tiles - (int)blockIdx.x + n_slots - 1) / n_slots : 0;   // rounds of slot 0 >= slot 1
@@ -109,7 +121,78 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
   const unsigned tmem_base = __shfl_sync(0xffffffffu, S->tmem_base, 0);
   const bool l0_lo = A.batch.reads_kind != PMT_READS_U8;   // decoded reads k/32 and bits are exact in TF32
 
-  if (warp == LOAD_WARP) {
+  if (warp == META_WARP) {
+    // ===================================== tile meta producer =====================================
+    // Everything a tile's set-up needs from global memory -- which variants, their row ranges, the gather indices and the
+    // compressed rows themselves -- is a chain of four dependent loads.  This warp walks the chain one round ahead of the
+    // epilogue warps and leaves the result in shared memory, so neither the tile set-up nor the decode step waits for it.
+    const int lane = tid & 31;
+    const long long total_ref = __ldg(A.batch.ref_off + A.batch.n_variants);
+    const bool u8_rows = A.batch.reads_kind == PMT_READS_U8 && D.read_row_bytes == 12;
+    const int DIS = D.d_info + D.d_seq;
+    for (int round = 0; round < rounds; ++round) {
+      const int b = round & 1;
+      const unsigned fparity = ((round >> 1) & 1) ^ 1;   // the first use of each buffer finds it free
+      for (int slot = 0; slot < (sched == 1 ? 1 : 2); ++slot) {
+        TileBuf* TB = &S->tb[slot][b];
+        mbar_wait(smem_addr(&S->meta_free[slot][b]), fparity);
+        const int t = (int)blockIdx.x + slot * (int)gridDim.x + round * n_slots;
+        int v0 = 0, nv = 0;
+        if (t < n_tiles) { v0 = __ldg(A.tiles + 2 + 2 * (tile_first + t)); nv = __ldg(A.tiles + 3 + 2 * (tile_first + t)); }
+        long long r_base = 0, a_base = 0;
+        int nr_tot = 0, na_tot = 0, ref_pad = 0;
+        if (nv > 0) {
+          r_base = __ldg(A.batch.ref_off + v0); a_base = __ldg(A.batch.alt_off + v0);
+          nr_tot = (int)(__ldg(A.batch.ref_off + v0 + nv) - r_base); na_tot = (int)(__ldg(A.batch.alt_off + v0 + nv) - a_base);
+          ref_pad = (nr_tot + 3) & ~3;
+        }
+        if (lane == 0) { TB->v0 = v0; TB->nv = nv; TB->ref_pad = ref_pad; }
+        reinterpret_cast<unsigned*>(TB->m.rowvar)[lane] = 0xFFFFFFFFu;   // 255 = padding row
+        __syncwarp();
+        for (int j = lane; j < nv; j += 32) {
+          const long long r0 = __ldg(A.batch.ref_off + v0 + j), r1 = __ldg(A.batch.ref_off + v0 + j + 1);
+          const long long a0 = __ldg(A.batch.alt_off + v0 + j), a1 = __ldg(A.batch.alt_off + v0 + j + 1);
+          const int rs = (int)(r0 - r_base), rc = (int)(r1 - r0), as = ref_pad + (int)(a0 - a_base), ac = (int)(a1 - a0);
+          TB->m.ref_start[j] = (unsigned char)rs; TB->m.ref_cnt[j] = (unsigned char)rc;
+          TB->m.alt_start[j] = (unsigned char)as; TB->m.alt_cnt[j] = (unsigned char)ac;
+          for (int i = 0; i < rc; ++i) TB->m.rowvar[rs + i] = (unsigned char)j;
+          for (int i = 0; i < ac; ++i) TB->m.rowvar[as + i] = (unsigned char)j;
+          if (A.out.info_seq_be) {   // the concat step's embedding rows: towards L2
+            const char* e = reinterpret_cast<const char*>(A.out.info_seq_be + (long long)(v0 + j) * DIS);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(e));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(e + DIS * 4 - 4));
+          }
+        }
+        long long idx[4], src[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int r = q * 32 + lane;
+          idx[q] = -1;
+          if (r < nr_tot) idx[q] = r_base + r;
+          else if (r >= ref_pad && r - ref_pad < na_tot) idx[q] = total_ref + a_base + (r - ref_pad);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) src[q] = (idx[q] >= 0 && A.batch.read_indices) ? __ldg(A.batch.read_indices + idx[q]) : idx[q];
+        unsigned w[4][3];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          w[q][0] = w[q][1] = w[q][2] = 0u;
+          if (u8_rows && src[q] >= 0) {
+            const unsigned* wp = reinterpret_cast<const unsigned*>(reinterpret_cast<const unsigned char*>(A.batch.reads) + src[q] * 12);
+            w[q][0] = __ldg(wp); w[q][1] = __ldg(wp + 1); w[q][2] = __ldg(wp + 2);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int r = q * 32 + lane;
+          TB->idx[r] = idx[q]; TB->src[r] = src[q];
+          TB->words[r * 3] = w[q][0]; TB->words[r * 3 + 1] = w[q][1]; TB->words[r * 3 + 2] = w[q][2];
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_addr(&S->meta_full[slot][b]));   // release semantics: the stores above are visible
+      }
+    }
+  } else if (warp == LOAD_WARP) {
     // ===================================== weight loader =====================================
     if (elect_one()) {
       const long long total = (long long)rounds * n_steps;
@@ -126,6 +209,8 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
       }
     }
     __syncwarp();
+  } else if (sched == 1 && (warp == MMA_WARP + 1 || (warp >= 8 && warp < 16))) {
+    // measurement mode: slot 1 stays idle
   } else if (warp >= MMA_WARP) {
     // ===================================== MMA issuers: one warp per slot =====================================
     // Each warp blocks only on ITS slot's operand barrier, so the two slots drift apart freely and one slot's
@@ -172,9 +257,6 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
     const int row = quarter * 32 + lane;
     const int srow = half * TILE + row;              // 0..255 inside the slot
     const int slot_bar = 1 + slot, pair_bar = 3 + slot * 4 + quarter;
-    SlotMeta* M = &S->slot[slot];
-    const unsigned m_rowvar = smem_addr(M->rowvar), m_ref_start = smem_addr(M->ref_start), m_ref_cnt = smem_addr(M->ref_cnt),
-                   m_alt_start = smem_addr(M->alt_start), m_alt_cnt = smem_addr(M->alt_cnt);
     const unsigned xch = xch_all + slot * XCH_ROWS * XCH_LD * 4;    // [XCH_ROWS][XCH_LD] floats
     const unsigned sums = sums_all + slot * SUMS_FLOATS * 4;        // [segment = 2 * variant + side][MAXH]
     const unsigned px_mine = pairx_all + ((slot * 2 + half) * TILE + row) * 8, px_other = pairx_all + ((slot * 2 + (half ^ 1)) * TILE + row) * 8;
@@ -191,35 +273,17 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
 
     for (int round = 0; round < rounds; ++round) {
       const int t = (int)blockIdx.x + slot * (int)gridDim.x + round * n_slots;
-      // ---------------- tile meta ----------------
-      int v0 = 0, nv = 0;
-      if (t < n_tiles) { v0 = __ldg(A.tiles + 2 + 2 * (tile_first + t)); nv = __ldg(A.tiles + 3 + 2 * (tile_first + t)); }
+      // ---------------- tile meta: prepared by the meta warp while the previous tile was computed ----------------
+      TileBuf* const TB = &S->tb[slot][round & 1];
+      const unsigned m_rowvar = smem_addr(TB->m.rowvar), m_ref_start = smem_addr(TB->m.ref_start), m_ref_cnt = smem_addr(TB->m.ref_cnt),
+                     m_alt_start = smem_addr(TB->m.alt_start), m_alt_cnt = smem_addr(TB->m.alt_cnt);
+      mbar_wait(smem_addr(&S->meta_full[slot][round & 1]), (round >> 1) & 1);
+      const int v0 = TB->v0, nv = TB->nv, ref_pad = TB->ref_pad;
+      const long long my_idx = TB->idx[row], my_src = TB->src[row];
       unsigned char* const scr = (SAVE && t < n_tiles) ? A.scratch + (size_t)t * TP.tile_bytes : nullptr;
-      long long r_base = 0, a_base = 0;
-      int ref_pad = 0;
-      if (half == 0) M->rowvar[row] = 255;
-      named_barrier(slot_bar, 256);   // previous tile's readers of the tables are done; rowvar cleared
-      if (nv > 0) {
-        r_base = __ldg(A.batch.ref_off + v0);
-        a_base = __ldg(A.batch.alt_off + v0);
-        const long long nr_tot = __ldg(A.batch.ref_off + v0 + nv) - r_base;
-        ref_pad = (int)((nr_tot + 3) & ~3LL);
-        if (half == 0 && row < nv) {
-          const long long r0 = __ldg(A.batch.ref_off + v0 + row), r1 = __ldg(A.batch.ref_off + v0 + row + 1);
-          const long long a0 = __ldg(A.batch.alt_off + v0 + row), a1 = __ldg(A.batch.alt_off + v0 + row + 1);
-          const int rs = (int)(r0 - r_base), rc = (int)(r1 - r0), as = ref_pad + (int)(a0 - a_base), ac = (int)(a1 - a0);
-          M->ref_start[row] = (unsigned char)rs; M->ref_cnt[row] = (unsigned char)rc;
-          M->alt_start[row] = (unsigned char)as; M->alt_cnt[row] = (unsigned char)ac;
-          for (int i = 0; i < rc; ++i) M->rowvar[rs + i] = (unsigned char)row;
-          for (int i = 0; i < ac; ++i) M->rowvar[as + i] = (unsigned char)row;
-        }
-      }
-      named_barrier(slot_bar, 256);
       const int rv = (int)lds_u8(m_rowvar + row);
       const int my_var = rv == 255 ? -1 : rv;
       const bool is_alt = row >= ref_pad;
-      long long my_idx = -1;
-      if (my_var >= 0) my_idx = is_alt ? total_ref + a_base + (row - ref_pad) : r_base + row;
 
       TR(1);
       for (int step = 0; step < n_steps; ++step) {
@@ -232,19 +296,18 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = 0.f;
             if (my_idx >= 0) {
-              const long long src = A.batch.read_indices ? __ldg(A.batch.read_indices + my_idx) : my_idx;
+              const long long src = my_src;
               if (A.batch.reads_kind == PMT_READS_U8) {
                 const int rb = D.read_row_bytes;
                 const unsigned char* rp = reinterpret_cast<const unsigned char*>(A.batch.reads) + src * rb;
                 unsigned bytes[8];   // this half's 8 source bytes: packed bytes 0..3, or packed bytes 4..6 + quantised 7..
-                if (rb == 12) {
-                  const unsigned* wp = reinterpret_cast<const unsigned*>(rp);
+                if (rb == 12) {      // the meta warp fetched the row
                   if (half == 0) {
-                    const unsigned w0 = __ldg(wp);
+                    const unsigned w0 = TB->words[row * 3];
 #pragma unroll
                     for (int b = 0; b < 4; ++b) bytes[b] = (w0 >> (8 * b)) & 255u;
                   } else {
-                    const unsigned w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
+                    const unsigned w1 = TB->words[row * 3 + 1], w2 = TB->words[row * 3 + 2];
 #pragma unroll
                     for (int b = 0; b < 4; ++b) { bytes[b] = (w1 >> (8 * b)) & 255u; bytes[4 + b] = (w2 >> (8 * b)) & 255u; }
                   }
@@ -412,33 +475,46 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
                 if (j == 0) gi[18 * 2 * TILE] = rstd;
               }
             }
+            // the z1 activations do not depend on the other rows: computed while the slower warps reach the barrier
+            float z1a[6];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) z1a[j] = SELU_SCALE * selu_u(z1s[j]);
             TR(900 + step);
             named_barrier(slot_bar, 256);
             TR(1000 + step);
-            {   // per-variant mean fields (gated_mlp.py:236-239): one (segment, hidden unit) sum per thread
+            {   // per-variant mean fields (gated_mlp.py:236-239)
+              // two threads (a lane pair) per sum: even / odd rows of the set, combined with one shuffle
               const float regw = lds_f32(bcs + BC_REGW * 4);
               const int n_sums = nv * 2 * H;
-              for (int idx = srow; idx < n_sums; idx += 256) {
-                const int seg = (int)(((unsigned)idx * inv_h) >> 16), f = idx - seg * H;
+              const int part = lane & 1;
+              for (int base = (srow >> 1) & ~15; base < n_sums; base += 128) {
+                const int idx = base + (lane >> 1);
+                const bool on = idx < n_sums;
+                const int seg = on ? (int)(((unsigned)idx * inv_h) >> 16) : 0, f = on ? idx - seg * H : 0;
                 const int j = seg >> 1, s = seg & 1;
-                const int start = (int)lds_u8((s ? m_alt_start : m_ref_start) + j), cnt = (int)lds_u8((s ? m_alt_cnt : m_ref_cnt) + j);
-                const unsigned src = xch + (f * XCH_LD + start) * 4;
-                // four independent loads per trip (the tail reads inside the exchange buffer and is masked): the trip count
-                // of a warp is that of its longest set, so the loads of a trip must not wait for each other
+                const int start = (int)lds_u8((s ? m_alt_start : m_ref_start) + j);
+                const int cnt = on ? (int)lds_u8((s ? m_alt_cnt : m_ref_cnt) + j) : 0;
+                const unsigned src = xch + (f * XCH_LD + start + part) * 4;
+                // this thread's rows: part, part + 2, ...; four independent loads per trip (the tail reads inside the exchange
+                // buffer and is masked): the trip count of a warp is that of its longest set
+                const int mine = (cnt - part + 1) >> 1;
                 float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-                for (int i = 0; i < cnt; i += 4) {
-                  const float v0 = lds_f32(src + i * 4), v1 = lds_f32(src + i * 4 + 4), v2 = lds_f32(src + i * 4 + 8), v3 = lds_f32(src + i * 4 + 12);
-                  a0 += v0;
-                  a1 += i + 1 < cnt ? v1 : 0.f;
-                  a2 += i + 2 < cnt ? v2 : 0.f;
-                  a3 += i + 3 < cnt ? v3 : 0.f;
+                for (int i = 0; i < mine; i += 4) {
+                  const float x0 = lds_f32(src + i * 8), x1 = lds_f32(src + i * 8 + 8), x2 = lds_f32(src + i * 8 + 16), x3 = lds_f32(src + i * 8 + 24);
+                  a0 += x0;
+                  a1 += i + 1 < mine ? x1 : 0.f;
+                  a2 += i + 2 < mine ? x2 : 0.f;
+                  a3 += i + 3 < mine ? x3 : 0.f;
                 }
-                const float acc = (a0 + a1) + (a2 + a3);
-                const float num = s == 0 ? acc + regw * lds_f32(bcs + (BC_REG + f) * 4) : acc;
-                const float den = (float)cnt + (s == 0 ? regw : 1e-4f);
-                const float m = num / den;
-                sts_f32(sums + (seg * MAXH + f) * 4, m);
-                if (SAVE && scr) reinterpret_cast<float*>(scr + TP.means_off)[(TP.step[step].blk * 2 * BWD_MAXV + seg) * MAXH + f] = m;
+                float acc = (a0 + a1) + (a2 + a3);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                if (on && part == 0) {
+                  const float num = s == 0 ? acc + regw * lds_f32(bcs + (BC_REG + f) * 4) : acc;
+                  const float den = (float)cnt + (s == 0 ? regw : 1e-4f);
+                  const float m = __fdividef(num, den);
+                  sts_f32(sums + (seg * MAXH + f) * 4, m);
+                  if (SAVE && scr) reinterpret_cast<float*>(scr + TP.means_off)[(TP.step[step].blk * 2 * BWD_MAXV + seg) * MAXH + f] = m;
+                }
               }
             }
             TR(1100 + step);
@@ -464,7 +540,7 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
                     const float m_ref = lds_f32(s_ref + j * 4), m_own = lds_f32(s_own + j * 4);
                     gate = fmaf(beta, m_own, fmaf(gamma, m_ref, gate));
                   }
-                  const float z1 = SELU_SCALE * selu_u(z1s[j]);
+                  const float z1 = z1a[j];
                   tk[j] = z1 * gate;
                   if (SAVE && scr)
                     reinterpret_cast<float*>(scr + TP.gate_off)[((TP.step[step].blk * GATE_ITEMS + j) * 2 + half) * TILE + row] = z1;
@@ -513,7 +589,9 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
       }
 
       // ---------------- clustering head (rotation folded into the last layer; feature_clustering.py:82-135) ----------------
-      // half 0: feature rows for the set means + non-artifact / outlier terms; half 1: the K cluster terms
+      // Both threads of a row hold its features.  half 0: feature rows for the set means, the non-artifact term and the
+      // even clusters; half 1: the outlier term and the odd clusters.
+      TR(2);
       float f[MAXE];
       load_cols<MAXE>(t_z, f);
       if (half == 0) {
@@ -530,73 +608,93 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
         }
       }
       if (is_alt && my_var >= 0) {
-        if (half == 0) {
-          float q = 0.f, q2 = 0.f;
+        {   // (f / (2 sigma))^2 == (f / sigma)^2 / 4 exactly: one sum serves the non-artifact and the outlier Gaussians
+          float q = 0.f;
 #pragma unroll
-          for (int e = 0; e < MAXE; ++e)
-            if (e < E) {
-              const float a = f[e] / HC->sigma[e], b = f[e] / (2.f * HC->sigma[e]);
-              q = fmaf(a, a, q); q2 = fmaf(b, b, q2);
-            }
-          sts_f32(xch + ((MAXE + 0) * XCH_LD + row) * 4, HC->c_non - q / 2.f);
-          sts_f32(xch + ((MAXE + 1) * XCH_LD + row) * 4, HC->c_out - q2 / 2.f);
-        } else {
-          for (int k = 0; k < K; ++k) {
-            const float* u = W + D.unit_ke + k * E;
-            float pr = 0.f;
+          for (int e = 0; e < MAXE; ++e) { const float a = f[e] * HCT->inv_sigma[e]; q = fmaf(a, a, q); }
+          sts_f32(xch + ((MAXE + half) * XCH_LD + row) * 4, half ? HC->c_out - q * 0.125f : HC->c_non - q * 0.5f);
+        }
+        for (int k = half; k < K; k += 2) {
+          const float* u = HCT->unit[k];
+          float pr = 0.f;
 #pragma unroll
-            for (int e = 0; e < MAXE; ++e) if (e < E) pr = fmaf(f[e], __ldg(u + e), pr);
-            float o2 = 0.f;
+          for (int e = 0; e < MAXE; ++e) pr = fmaf(f[e], u[e], pr);
+          float o2 = 0.f;
 #pragma unroll
-            for (int e = 0; e < MAXE; ++e) if (e < E) { const float dd = f[e] - pr * __ldg(u + e); o2 = fmaf(dd, dd, o2); }
-            const float dist = sqrtf(o2);
-            const float ll_orth = HC->c_orth[k] - (dist * dist) / HC->two_tau2[k];
-            const float ll_par = HC->log_half_lambda[k] + logerfc((HC->shift[k] - pr) / HC->sqrt2_sigma[k]) +
-                                 HC->half_lambda[k] * (HC->two_mu_plus[k] - 2.f * pr);
-            sts_f32(xch + ((MAXE + 2 + k) * XCH_LD + row) * 4, ll_orth + ll_par);
-          }
+          for (int e = 0; e < MAXE; ++e) { const float dd = fmaf(-pr, u[e], f[e]); o2 = fmaf(dd, dd, o2); }
+          const float dist = sqrtf(o2);
+          const float ll_orth = HC->c_orth[k] - (dist * dist) * HCT->inv_two_tau2[k];
+          const float ll_par = HC->log_half_lambda[k] + logerfc((HC->shift[k] - pr) * HCT->inv_sqrt2_sigma[k]) +
+                               HC->half_lambda[k] * (HC->two_mu_plus[k] - 2.f * pr);
+          sts_f32(xch + ((MAXE + 2 + k) * XCH_LD + row) * 4, ll_orth + ll_par);
         }
       }
+      TR(3);
       named_barrier(slot_bar, 256);
+      TR(4);
       // ---- per-variant sums and outputs (ragged_sets.py:144-158; artifact_model.py:291-292) ----
+      // set means: one (variant, side, feature) per thread, low threads first
       for (int idx = srow; idx < nv * 2 * E; idx += 256) {
         const int seg = (int)(((unsigned)idx * inv_e) >> 16), e = idx - seg * E;
         const int j = seg >> 1, s = seg & 1;
         const int start = (int)lds_u8((s ? m_alt_start : m_ref_start) + j), cnt = (int)lds_u8((s ? m_alt_cnt : m_ref_cnt) + j);
         const unsigned src = xch + (e * XCH_LD + start) * 4;
-        float acc = 0.f;
-        for (int i = 0; i < cnt; ++i) acc += lds_f32(src + i * 4);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        for (int i = 0; i < cnt; i += 4) {
+          const float x0 = lds_f32(src + i * 4), x1 = lds_f32(src + i * 4 + 4), x2 = lds_f32(src + i * 4 + 8), x3 = lds_f32(src + i * 4 + 12);
+          a0 += x0;
+          a1 += i + 1 < cnt ? x1 : 0.f;
+          a2 += i + 2 < cnt ? x2 : 0.f;
+          a3 += i + 3 < cnt ? x3 : 0.f;
+        }
         float* dst = s ? A.out.alt_means_be : A.out.ref_means_be;
-        if (dst) dst[(long long)(v0 + j) * E + e] = acc / ((float)cnt + 1e-4f);
+        if (dst) dst[(long long)(v0 + j) * E + e] = __fdividef((a0 + a1) + (a2 + a3), (float)cnt + 1e-4f);
       }
-      if (half == 1 && row < nv) {
-        const int j = row;
-        const long long v = v0 + j;
-        const int as = (int)lds_u8(m_alt_start + j), ac = (int)lds_u8(m_alt_cnt + j);
-        float ll[MAXK + 2];
-#pragma unroll
-        for (int k = 0; k < MAXK + 2; ++k) {
+      // log-likelihood sums: one (variant, term) per thread in groups of eight lanes, HIGH threads first (the two gathers
+      // run side by side on different warps); the terms of a variant meet through shuffles
+      {
+        const int ridx = 255 - srow;
+        const int k = ridx & 7;
+        for (int base = ridx & ~31; base < nv * 8; base += 256) {
+          const int j = (base + (ridx & 31)) >> 3;
+          const bool term = j < nv && k < K + 2;
           float acc = 0.f;
-          if (k < K + 2) {
+          if (term) {
+            const int as = (int)lds_u8(m_alt_start + j), ac = (int)lds_u8(m_alt_cnt + j);
             const unsigned src = xch + ((MAXE + k) * XCH_LD + as) * 4;
-            for (int i = 0; i < ac; ++i) acc += lds_f32(src + i * 4);
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            for (int i = 0; i < ac; i += 4) {
+              const float x0 = lds_f32(src + i * 4), x1 = lds_f32(src + i * 4 + 4), x2 = lds_f32(src + i * 4 + 8), x3 = lds_f32(src + i * 4 + 12);
+              a0 += x0;
+              a1 += i + 1 < ac ? x1 : 0.f;
+              a2 += i + 2 < ac ? x2 : 0.f;
+              a3 += i + 3 < ac ? x3 : 0.f;
+            }
+            acc = (a0 + a1) + (a2 + a3);
+            if (k >= 2) acc += HC->logw[k - 2];
           }
-          ll[k] = acc;
+          const bool art_term = term && k >= 2;
+          float art_max = art_term ? acc : -INFINITY;
+#pragma unroll
+          for (int m = 1; m < 8; m <<= 1) art_max = fmaxf(art_max, __shfl_xor_sync(0xffffffffu, art_max, m));
+          float sacc = art_term ? expf(acc - art_max) : 0.f;
+#pragma unroll
+          for (int m = 1; m < 8; m <<= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, m);
+          // ridx runs against the lane number: term k of the group sits in lane (lane | 7) - k
+          const int lane_k0 = (lane | 7);
+          const float ll0 = __shfl_sync(0xffffffffu, acc, lane_k0), ll1 = __shfl_sync(0xffffffffu, acc, lane_k0 - 1);
+          if (term) {
+            const long long v = v0 + j;
+            const float art = art_max + logf(sacc);
+            if (A.out.logits_bk) A.out.logits_bk[v * (K + 2) + k] = acc;
+            if (k == 0 && A.out.logits_b) A.out.logits_b[v] = 20.f * tanhf((art - ll0) / 20.f);
+            if (k == 1 && A.out.outlier_logits_b) A.out.outlier_logits_b[v] = ll1 - logsumexp2(ll0, art);
+          }
         }
-        float art_max = -INFINITY;
-#pragma unroll
-        for (int k = 0; k < MAXK; ++k) if (k < K) { ll[2 + k] += HC->logw[k]; art_max = fmaxf(art_max, ll[2 + k]); }
-        float sacc = 0.f;
-#pragma unroll
-        for (int k = 0; k < MAXK; ++k) if (k < K) sacc += expf(ll[2 + k] - art_max);
-        const float art = art_max + logf(sacc);
-        if (A.out.logits_bk) {
-#pragma unroll
-          for (int k = 0; k < MAXK + 2; ++k) if (k < K + 2) A.out.logits_bk[v * (K + 2) + k] = ll[k];
-        }
-        if (A.out.logits_b) A.out.logits_b[v] = 20.f * tanhf((art - ll[0]) / 20.f);
-        if (A.out.outlier_logits_b) A.out.outlier_logits_b[v] = ll[1] - logsumexp2(ll[0], art);
       }
+      TR(5);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_addr(&S->meta_free[slot][round & 1]));   // the tile's tables may be refilled
     }
   }
   if (TRACE && tr_on) tr[2046] = tr_n;
@@ -902,17 +1000,17 @@ template <int PASSES>
 static int launch_tc(const PmtModelDesc& D, const TcPlan& T, const TcArgs& A, int grid, cudaStream_t st) {
   const int stage_bytes = PASSES == 3 ? T.slot_bytes : T.slot_bytes / 2;
   const size_t fixed = 2 * XCH_ROWS * XCH_LD * sizeof(float) + 2 * SUMS_FLOATS * sizeof(float) + 2 * 2 * TILE * 2 * sizeof(float) +
-                       PMT_MAX_BLOCKS * BC_STRIDE * sizeof(float) + sizeof(HeadConst) + sizeof(Shared) + 1024 + 64;
+                       PMT_MAX_BLOCKS * BC_STRIDE * sizeof(float) + sizeof(HeadConstTc) + sizeof(Shared) + 1024 + 64;
   int n_stages = (int)((227 * 1024 - fixed) / stage_bytes);
   if (n_stages > NS_MAX) n_stages = NS_MAX;
   PMT_CHECK(n_stages >= 2, "tensor-core forward: weight ring does not fit in shared memory");
   const size_t smem = fixed + (size_t)n_stages * stage_bytes;
   if (g_reads_trace) {
     PMT_CUDA(cudaFuncSetAttribute(reads_forward_tc_kernel<PASSES, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    reads_forward_tc_kernel<PASSES, true, false><<<grid, THREADS, smem, st>>>(D, T, A, n_stages, stage_bytes, g_reads_trace);
+    reads_forward_tc_kernel<PASSES, true, false><<<grid, FWD_THREADS, smem, st>>>(D, T, A, n_stages, stage_bytes, g_reads_trace);
   } else {
     PMT_CUDA(cudaFuncSetAttribute(reads_forward_tc_kernel<PASSES, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    reads_forward_tc_kernel<PASSES, false, false><<<grid, THREADS, smem, st>>>(D, T, A, n_stages, stage_bytes, nullptr);
+    reads_forward_tc_kernel<PASSES, false, false><<<grid, FWD_THREADS, smem, st>>>(D, T, A, n_stages, stage_bytes, nullptr);
   }
   return 0;
 }
@@ -926,13 +1024,13 @@ int pmt_launch_pack_tc(const Plan& P, const TcPlan& T, const float* weights, uns
 int pmt_launch_reads_tc_save(const Plan& P, const TcPlan& T, const TcArgs& A, int grid, cudaStream_t st) {
   const int stage_bytes = T.slot_bytes;
   const size_t fixed = 2 * XCH_ROWS * XCH_LD * sizeof(float) + 2 * SUMS_FLOATS * sizeof(float) + 2 * 2 * TILE * 2 * sizeof(float) +
-                       PMT_MAX_BLOCKS * BC_STRIDE * sizeof(float) + sizeof(HeadConst) + sizeof(Shared) + 1024 + 64;
+                       PMT_MAX_BLOCKS * BC_STRIDE * sizeof(float) + sizeof(HeadConstTc) + sizeof(Shared) + 1024 + 64;
   int n_stages = (int)((227 * 1024 - fixed) / stage_bytes);
   if (n_stages > NS_MAX) n_stages = NS_MAX;
   PMT_CHECK(n_stages >= 2, "tensor-core forward: weight ring does not fit in shared memory");
   const size_t smem = fixed + (size_t)n_stages * stage_bytes;
   PMT_CUDA(cudaFuncSetAttribute(reads_forward_tc_kernel<3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  reads_forward_tc_kernel<3, false, true><<<grid, THREADS, smem, st>>>(P.d, T, A, n_stages, stage_bytes, nullptr);
+  reads_forward_tc_kernel<3, false, true><<<grid, FWD_THREADS, smem, st>>>(P.d, T, A, n_stages, stage_bytes, nullptr);
   return 0;
 }
 
@@ -950,6 +1048,7 @@ int pmt_launch_reads_tc(const Plan& P, const float* weights, const PmtBatch* bat
   TcArgs A;
   A.wflat = weights; A.image = image; A.tiles = tiles; A.batch = *batch; A.out = *out;
   A.scratch = nullptr; A.tile_first = 0; A.tile_limit = 0x7fffffff;
+  { const char* e = getenv("PMT_TC_SCHED"); A.sched = (e && atoi(e) == 1) ? 1 : 0; }   // measurement: one slot only
   // the tile count is only known on the device: size the grid from the row-count hint (a tile holds ~110 rows of
   // whole variants); one CTA per tile until every SM has one, the second slot of each CTA after that
   const long long rows = batch->n_rows > 0 ? batch->n_rows : 16LL * batch->n_variants;

@@ -11,6 +11,7 @@ namespace tc {
 
 constexpr int THREADS = 608;      // 16 epilogue warps (2 slots x 2 column halves x 4 lane quarters) + 2 MMA warps + loader warp
 constexpr int MMA_WARP = 16, LOAD_WARP = 18;
+constexpr int META_WARP = 19, FWD_THREADS = 640;   // forward only: one more warp prepares the NEXT tile's tables and rows
 constexpr int SUMS_FLOATS = 2 * TILE * 11;   // per slot: [segment][MAXH]
 constexpr int MAX_STEPS = 64;
 constexpr int COL_X = 0, COL_Z = 64, COL_AHI = 128, COL_ALO = 192, SLOT_COLS = 256;
@@ -88,6 +89,7 @@ struct TcArgs {
   // scratch + (t - tile_first) * TcPlan.tile_bytes
   unsigned char* scratch;
   int tile_first, tile_limit;
+  int sched;              // 0 = both slots; 1 = one slot only (measurement: what a tile costs without its neighbour)
 };
 
 struct TcBwdArgs {
@@ -109,11 +111,29 @@ struct SlotMeta {
   unsigned char ref_start[TILE], ref_cnt[TILE], alt_start[TILE], alt_cnt[TILE];
 };
 
+// What the forward's meta warp prepares for a tile while the previous tile of the slot is still being computed
+struct TileBuf {
+  long long idx[TILE];         // batch row of each tile row (-1: padding)
+  long long src[TILE];         // row of the reads array (idx through the gather indices of a downsampled / dataset-order batch)
+  unsigned words[TILE * 3];    // the compressed row itself (12-byte rows)
+  int v0, nv, ref_pad, pad_;
+  SlotMeta m;
+};
+
 struct Shared {
   unsigned long long bar_a[2], bar_d[2], wfull[NS_MAX], wfree[NS_MAX];
+  unsigned long long meta_full[2][2], meta_free[2][2];   // [slot][buffer]
   unsigned tmem_base;
   int pad_;
-  SlotMeta slot[2];
+  TileBuf tb[2][2];  // [slot][round & 1]
+};
+
+// Forward head constants in shared memory: the clustering head's (pmt_tile.cuh) plus reciprocals and the cluster directions
+struct HeadConstTc {
+  HeadConst h;
+  float inv_sigma[MAXE];
+  float unit[MAXK][MAXE];
+  float inv_two_tau2[MAXK], inv_sqrt2_sigma[MAXK];
 };
 
 // per gated block scalars staged in shared memory (gated_mlp.py:213-226)

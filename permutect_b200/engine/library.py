@@ -109,6 +109,9 @@ _LIB = None
 
 
 def library_path() -> str:
+    override = os.environ.get("PERMUTECT_B200_LIBRARY")     # a differently built libpermutect_b200.so (A/B measurements)
+    if override:
+        return override
     return os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc", "libpermutect_b200.so")
 
 
