@@ -77,3 +77,61 @@ def test_downsampled_forward_equals_explicit_indices():
         a = model.compute_batch_output(ds).logits_b
         b = model.compute_batch_output(explicit).logits_b
     assert torch.equal(a, b)
+
+
+def test_index_builder_against_the_reference_with_a_forced_keep_mask(monkeypatch):
+    """The UNMODIFIED reference's DownsampledBatch (batch.py:383-439) builds counts and gather indices from Bernoulli masks;
+    torch's generator cannot be reproduced on the device, so its ``bernoulli_`` is made to return the device kernel's own
+    counter-hash decisions and everything downstream -- the forced alt read, the segment sums, nonzero + hstack (quirk Q1
+    included) -- is the reference's code.  Counts and indices must be identical."""
+    import random
+    from oracle import reference
+    if not reference.available():
+        pytest.skip("oracle/_ref not built (python oracle/build_ref.py)")
+    reference.load()
+    import permutect.data.batch as rb
+    import permutect.data.datum as rd
+    n = 400
+    ia, fa, reads = make_wgs_arrays(n, seed=17)
+    ia[::7, 0] = 0                                  # some empty ref sets
+    keep_rows = np.ones(len(reads), dtype=bool)
+    ref_c, alt_c = make_wgs_arrays(n, seed=17)[0][:, 0].astype(int), ia[:, 1].astype(int)
+    ref_off = np.concatenate(([0], np.cumsum(ref_c)))
+    for v in range(0, n, 7):
+        keep_rows[ref_off[v]:ref_off[v + 1]] = False
+    reads = reads[keep_rows]
+    ref_c = ia[:, 0].astype(int)
+    ref_off, alt_off = np.concatenate(([0], np.cumsum(ref_c))), np.concatenate(([0], np.cumsum(alt_c)))
+    total_ref = int(ref_off[-1])
+    dev = torch.device("cuda:0")
+    parent = Batch.from_arrays(ia, fa, reads).copy_to(dev)
+    ref_parent = rb.Batch([rd.Datum(ia[v], fa[v], np.vstack((reads[ref_off[v]:ref_off[v + 1]],
+                                                              reads[total_ref + alt_off[v]:total_ref + alt_off[v + 1]])), compressed=True)
+                           for v in range(n)])
+    rng = np.random.default_rng(3)
+    rf = torch.from_numpy(rng.uniform(0.1, 1.0, n).astype(np.float32))
+    af = torch.from_numpy(rng.uniform(0.1, 1.0, n).astype(np.float32))
+    seed = 987654321
+    calls = []
+
+    def forced_bernoulli_(self, p):
+        first_row = 0 if not calls else total_ref                      # the ref mask is drawn first, then the alt mask
+        calls.append(len(self))
+        u = _hash_uniform(seed, first_row + np.arange(len(self)))
+        self.copy_(torch.from_numpy((u < p.cpu().numpy()).astype(np.int64)))
+        return self
+
+    monkeypatch.setattr(torch.Tensor, "bernoulli_", forced_bernoulli_)
+    random.seed(31)
+    want = rb.DownsampledBatch(ref_parent, ref_fracs_b=rf, alt_fracs_b=af)
+    monkeypatch.undo()
+    assert calls == [total_ref, int(alt_off[-1])]
+    random.seed(31)
+    got = DownsampledBatch(parent, rf, af, seed=seed)
+    got_ref, got_alt = (t.cpu() for t in got.counts())
+    assert torch.equal(got_ref.int(), want.ref_counts) and torch.equal(got_alt.int(), want.alt_counts)
+    n_kept = int(want.ref_counts.sum() + want.alt_counts.sum())
+    assert len(want.read_indices) == n_kept
+    assert torch.equal(got.read_indices[:n_kept].cpu(), want.read_indices)
+    # and the rows the model will read are the reference's (decoded on the device vs the reference's host decode)
+    np.testing.assert_array_equal(got.get_reads_re().cpu().numpy(), want.get_reads_re().numpy())
