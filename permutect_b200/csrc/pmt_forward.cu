@@ -114,6 +114,170 @@ info_mlp_kernel(const __grid_constant__ Plan P, const float* __restrict__ wflat,
 }
 
 // ------------------------------------------------------------------------------------------------
+// info_embedding MLP, one THREAD per variant (artifact_model.py:244; mlp.py:8-76).  The whole MLP is ~4 k multiply-adds
+// per variant on vectors of d_info (20) numbers: a tile GEMM spends its time in barriers and weight staging, so here the
+// weights of every layer sit in shared memory for the life of the CTA ([k][W] rows: one broadcast 16-byte load feeds four
+// multiply-adds), a thread keeps the running vector, the DenseSkipBlock residual and the layer output in registers, and
+// the input block of a tile is staged feature-major through shared memory with coalesced loads.
+// W4 = ceil(widest hidden vector / 4); layers after the first have in_dim <= 4 * W4.
+// ------------------------------------------------------------------------------------------------
+constexpr int INFO_TPB = 128;
+template <int W4>
+__global__ void __launch_bounds__(INFO_TPB)
+info_mlp_rows_kernel(const __grid_constant__ PmtModelDesc D, const float* __restrict__ wflat, const void* __restrict__ info, int info_kind,
+                     long long info_stride, int n_variants, float* __restrict__ info_seq) {
+  constexpr int W = 4 * W4;
+  extern __shared__ __align__(16) float smem[];
+  const int I = D.n_info_features, n_ops = D.n_info_ops;
+  // carve: per op [in_dim][W] transposed weights + [W] bias, then the input tile [I][INFO_TPB + 1]
+  float* wt = smem;
+  int off = 0;
+  for (int i = 0; i < n_ops; ++i) off += (D.info_ops[i].in_dim + 1) * W;
+  float* sx = smem + off;
+  {
+    int base = 0;
+    for (int i = 0; i < n_ops; ++i) {
+      const PmtLinearOp& op = D.info_ops[i];
+      for (int idx = threadIdx.x; idx < (op.in_dim + 1) * W; idx += INFO_TPB) {
+        const int k = idx / W, n = idx - k * W;
+        float v = 0.f;
+        if (n < op.out_dim) v = k < op.in_dim ? __ldg(wflat + op.w_off + n * op.in_dim + k) : __ldg(wflat + op.b_off + n);
+        wt[base + idx] = v;
+      }
+      base += (op.in_dim + 1) * W;
+    }
+  }
+  const int out_w = D.d_info + D.d_seq;
+  const int n_tiles = (n_variants + INFO_TPB - 1) / INFO_TPB;
+  const int r = threadIdx.x;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int v0 = tile * INFO_TPB, nv = min(INFO_TPB, n_variants - v0);
+    __syncthreads();   // weights staged / previous tile's readers done
+    const bool raw16 = info_kind == PMT_F16 && info_stride >= I && info_stride <= I + 8 && (reinterpret_cast<uintptr_t>(info) & 3) == 0;
+    if (raw16) {
+      // fp16 rows a few columns apart (the float array of the dataset): the tile's rows are one contiguous span, copied as
+      // 32-bit words; every thread then converts its own row
+      const unsigned* src = reinterpret_cast<const unsigned*>(reinterpret_cast<const __half*>(info) + (long long)v0 * info_stride);
+      unsigned* raw = reinterpret_cast<unsigned*>(sx);
+      const int n_halves = (int)((nv - 1) * info_stride) + I;     // up to the last row's last feature, not a byte further
+      const int n_words = n_halves >> 1;
+      for (int idx = threadIdx.x; idx < n_words; idx += INFO_TPB) raw[idx] = __ldg(src + idx);
+      if ((n_halves & 1) && threadIdx.x == 0)
+        reinterpret_cast<__half*>(sx)[n_halves - 1] = __ldg(reinterpret_cast<const __half*>(src) + n_halves - 1);
+    } else {
+      for (int idx = threadIdx.x; idx < nv * I; idx += INFO_TPB) {
+        const int rr = idx / I, f = idx - rr * I;
+        const long long o = (long long)(v0 + rr) * info_stride + f;
+        sx[f * (INFO_TPB + 1) + rr] = info_kind == PMT_F16 ? __half2float(__ldg(reinterpret_cast<const __half*>(info) + o))
+                                                            : __ldg(reinterpret_cast<const float*>(info) + o);
+      }
+    }
+    __syncthreads();
+    if (r >= nv) continue;
+    float cur[W], res[W];
+#pragma unroll
+    for (int n = 0; n < W; ++n) { cur[n] = 0.f; res[n] = 0.f; }
+    int base = 0;
+    for (int i = 0; i < n_ops; ++i) {
+      const PmtLinearOp op = D.info_ops[i];
+      const float* w = wt + base;
+      float y[W];
+      {
+        const float4* b4 = reinterpret_cast<const float4*>(w + op.in_dim * W);
+#pragma unroll
+        for (int q = 0; q < W4; ++q) { const float4 b = b4[q]; y[4 * q] = b.x; y[4 * q + 1] = b.y; y[4 * q + 2] = b.z; y[4 * q + 3] = b.w; }
+      }
+      if (i == 0) {   // input layer: the staged tile (raw fp16 rows, or feature-major floats)
+        const float* xr = sx + r;
+        const __half* hr = reinterpret_cast<const __half*>(sx) + (long long)r * info_stride;
+#pragma unroll 4
+        for (int k = 0; k < op.in_dim; ++k) {
+          const float x = raw16 ? __half2float(hr[k]) : xr[k * (INFO_TPB + 1)];
+          const float4* w4 = reinterpret_cast<const float4*>(w + k * W);
+#pragma unroll
+          for (int q = 0; q < W4; ++q) {
+            const float4 ww = w4[q];
+            y[4 * q] = fmaf(x, ww.x, y[4 * q]); y[4 * q + 1] = fmaf(x, ww.y, y[4 * q + 1]);
+            y[4 * q + 2] = fmaf(x, ww.z, y[4 * q + 2]); y[4 * q + 3] = fmaf(x, ww.w, y[4 * q + 3]);
+          }
+        }
+      } else {
+        float src[W];
+        if (op.flags & PMT_OP_SKIP_BEGIN) {
+#pragma unroll
+          for (int n = 0; n < W; ++n) { res[n] = cur[n]; src[n] = selu(cur[n]); }
+        } else {
+#pragma unroll
+          for (int n = 0; n < W; ++n) src[n] = cur[n];
+        }
+#pragma unroll
+        for (int k = 0; k < W; ++k) {
+          if (k < op.in_dim) {
+            const float x = src[k];
+            const float4* w4 = reinterpret_cast<const float4*>(w + k * W);
+#pragma unroll
+            for (int q = 0; q < W4; ++q) {
+              const float4 ww = w4[q];
+              y[4 * q] = fmaf(x, ww.x, y[4 * q]); y[4 * q + 1] = fmaf(x, ww.y, y[4 * q + 1]);
+              y[4 * q + 2] = fmaf(x, ww.z, y[4 * q + 2]); y[4 * q + 3] = fmaf(x, ww.w, y[4 * q + 3]);
+            }
+          }
+        }
+      }
+      if (op.flags & PMT_OP_SKIP_END) {
+        const float alpha = __ldg(wflat + op.alpha_off);
+#pragma unroll
+        for (int n = 0; n < W; ++n) cur[n] = fmaf(alpha, y[n], res[n]);
+      } else if (op.flags & PMT_OP_POST_SELU) {
+#pragma unroll
+        for (int n = 0; n < W; ++n) cur[n] = n < op.out_dim ? selu(y[n]) : 0.f;
+      } else {
+#pragma unroll
+        for (int n = 0; n < W; ++n) cur[n] = y[n];
+      }
+      base += (op.in_dim + 1) * W;
+    }
+    float* dst = info_seq + (long long)(v0 + r) * out_w;
+#pragma unroll
+    for (int n = 0; n < W; ++n) if (n < D.d_info) dst[n] = cur[n];
+  }
+}
+
+// The thread-per-variant kernel covers MLPs whose hidden vectors are at most 32 wide, with the input layer first and no
+// DenseSkipBlock opening on the raw input; anything else takes the tile-GEMM kernel above.
+static int info_rows_w4(const PmtModelDesc& d) {
+  if (d.n_info_ops < 1 || d.n_info_features > 256) return 0;
+  int widest = 0;
+  for (int i = 0; i < d.n_info_ops; ++i) {
+    const PmtLinearOp& op = d.info_ops[i];
+    if (op.out_dim > widest) widest = op.out_dim;
+    if (i > 0 && op.in_dim > widest) return 0;
+    if (i == 0 && (op.flags & (PMT_OP_SKIP_BEGIN | PMT_OP_SKIP_END))) return 0;
+    if (i == 0 && op.in_dim != d.n_info_features) return 0;
+  }
+  if (d.info_ops[d.n_info_ops - 1].out_dim != d.d_info) return 0;
+  const int w4 = (widest + 3) / 4;
+  return (w4 >= 1 && w4 <= 8) ? w4 : 0;
+}
+
+template <int W4>
+static int launch_info_rows(const PmtModelDesc& d, const float* weights, const PmtBatch* batch, float* info_seq, cudaStream_t st) {
+  const int W = 4 * W4;
+  size_t floats = (size_t)d.n_info_features * (INFO_TPB + 1);
+  for (int i = 0; i < d.n_info_ops; ++i) floats += (size_t)(d.info_ops[i].in_dim + 1) * W;
+  const size_t smem = floats * sizeof(float) + 16;
+  PMT_CHECK(smem <= 200 * 1024, "info MLP does not fit in shared memory");
+  PMT_CUDA(cudaFuncSetAttribute(info_mlp_rows_kernel<W4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int n_tiles = (batch->n_variants + INFO_TPB - 1) / INFO_TPB;
+  int per_sm = (int)((220 * 1024) / smem);
+  if (per_sm > 8) per_sm = 8;
+  if (per_sm < 1) per_sm = 1;
+  const int grid = n_tiles < 148 * per_sm ? n_tiles : 148 * per_sm;
+  info_mlp_rows_kernel<W4><<<grid, INFO_TPB, smem, st>>>(d, weights, batch->info, batch->info_kind, batch->info_stride, batch->n_variants, info_seq);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // haplotype CNN
 // ------------------------------------------------------------------------------------------------
 
@@ -574,7 +738,21 @@ int pmt_launch_variant_kernels(const Plan& P, const CnnGeom& G, const float* wei
                                const PmtBatch* batch, float* info_seq, int mode, unsigned char* cnn_tc_image, bool reuse_images,
                                cudaStream_t st) {
   const int B = batch->n_variants;
-  {
+  const int w4 = info_rows_w4(P.d);
+  if (w4 > 0) {
+    int rc = 1;
+    switch (w4) {
+      case 1: rc = launch_info_rows<1>(P.d, weights, batch, info_seq, st); break;
+      case 2: rc = launch_info_rows<2>(P.d, weights, batch, info_seq, st); break;
+      case 3: rc = launch_info_rows<3>(P.d, weights, batch, info_seq, st); break;
+      case 4: rc = launch_info_rows<4>(P.d, weights, batch, info_seq, st); break;
+      case 5: rc = launch_info_rows<5>(P.d, weights, batch, info_seq, st); break;
+      case 6: rc = launch_info_rows<6>(P.d, weights, batch, info_seq, st); break;
+      case 7: rc = launch_info_rows<7>(P.d, weights, batch, info_seq, st); break;
+      default: rc = launch_info_rows<8>(P.d, weights, batch, info_seq, st); break;
+    }
+    if (rc) return 1;
+  } else {
     const int in_rows = P.d.n_info_features > PMT_MAX_DIM ? PMT_MAX_INFO_DIM : PMT_MAX_DIM;
     const size_t smem = (size_t)((in_rows + 2 * PMT_MAX_DIM) * LD + 2 * P.info_stage_floats) * sizeof(float);
     PMT_CUDA(cudaFuncSetAttribute(info_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
