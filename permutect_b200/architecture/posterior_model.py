@@ -5,10 +5,11 @@ posterior model fitted by the reference loads here and ``log_posterior_and_ingre
 ``posterior_probabilities_bc`` / ``error_probabilities_b`` are one kernel launch (pmt_posterior_log_posteriors).
 
 ``learn_priors_and_spectra`` (posterior_model.py:101-165) runs its E step -- negative log evidence, its gradient w.r.t.
-the spectra, the posterior totals -- as pmt_posterior_fit_step and the optimiser / M step on the host, with one
-difference: the reference's context-dependent SNV prior M step is a PyMC ADVI fit (posterior_model_priors.py:157-203),
-which is not reproduced, so the fit runs with context-independent priors throughout (the reference does so for the
-first half of its iterations).  ``calculate_probability_thresholds`` (posterior_model.py:171-264) returns the same thresholds; its ROC plots are not
+the spectra, the posterior totals -- as pmt_posterior_fit_step and the optimiser / M step on the host.  Context-dependent
+SNV priors are switched on for the second half of the iterations as in the reference (:125-127); its M step for them, a
+PyMC ADVI fit (posterior_model_priors.py:157-203), is replaced by a deterministic fit of the same model and variational
+family (architecture/snv_context_priors.py; pymc is absent from the image, so that one step has no reference golden).
+``calculate_probability_thresholds`` (posterior_model.py:171-264) returns the same thresholds; its ROC plots are not
 drawn.  There is no CPU path for the model itself.
 """
 import ctypes as C
@@ -20,6 +21,7 @@ from torch.nn import Parameter
 from torch.nn.utils import parametrize
 
 from permutect_b200.architecture.layers import BoundedNumber, LogWeights, PositiveNumber
+from permutect_b200.architecture.snv_context_priors import context_m_step
 from permutect_b200.data.datum import HAPLOTYPES_START_IDX
 from permutect_b200.engine import library as L
 from permutect_b200.utils.enums import Variation
@@ -80,7 +82,7 @@ class PosteriorModelSpectra(nn.Module):
 
 
 class PosteriorModelPriors(nn.Module):
-    """Parameters and switches of posterior_model_priors.py:68-103 (the M step is not part of this repository)."""
+    """Parameters and switches of posterior_model_priors.py:68-103; the M step is PosteriorModel.update_priors_m_step."""
 
     def __init__(self, variant_log_prior: float, artifact_log_prior: float, no_germline_mode: bool):
         super().__init__()
@@ -209,8 +211,11 @@ class PosteriorModel(nn.Module):
                                            torch.cuda.current_stream(dev).cuda_stream))
         return _EvidenceLoss.apply(loss, grads, *self._spectra_tensors())
 
-    def update_priors_m_step(self, posterior_totals_vc: Tensor, ignored_to_non_ignored_ratio: float):
-        """posterior_model_priors.py:141-155 and the context-independent branch :204-206."""
+    def update_priors_m_step(self, posterior_totals_vc: Tensor, ignored_to_non_ignored_ratio: float,
+                             somatic_snv_totals_rrra: Optional[Tensor] = None, snv_context_totals_rrra: Optional[Tensor] = None):
+        """posterior_model_priors.py:141-224.  With context-dependent SNV priors switched on and both rrra totals given,
+        ``somatic_snv_log_priors_rrra`` gets the log mutation rates of the hierarchical substitution x context model
+        (snv_context_priors.context_m_step); otherwise it is filled with the SNV somatic log prior (:223-225)."""
         total_nonignored = torch.sum(posterior_totals_vc)
         overall_total = (1 + ignored_to_non_ignored_ratio) * total_nonignored
         with torch.no_grad():
@@ -218,16 +223,27 @@ class PosteriorModel(nn.Module):
             pri.log_priors_vc.copy_(torch.log(posterior_totals_vc / (posterior_totals_vc + overall_total)))
             pri.log_priors_vc[:, CALL_SEQ_ERROR] = 0
             pri.log_priors_vc[:, CALL_GERMLINE] = -9999 if self.no_germline_mode else 0
-            pri.somatic_snv_log_priors_rrra.fill_(pri.log_priors_vc[int(Variation.SNV), CALL_SOMATIC])
+            if pri.use_context_dependent_snv_priors:
+                if somatic_snv_totals_rrra is None or snv_context_totals_rrra is None:
+                    raise ValueError("context-dependent SNV priors are on: the M step needs both rrra totals")
+                total_ignored_per_context = float(ignored_to_non_ignored_ratio * total_nonignored) / 64      # :150-153
+                context_m_step(pri.somatic_snv_log_priors_rrra, somatic_snv_totals_rrra, snv_context_totals_rrra,
+                               total_ignored_per_context)
+            else:
+                pri.somatic_snv_log_priors_rrra.fill_(pri.log_priors_vc[int(Variation.SNV), CALL_SOMATIC])
 
     def learn_priors_and_spectra(self, posterior_loader, num_iterations, ignored_to_non_ignored_ratio: float, summary_writer=None,
                                  learning_rate: float = 0.001):
-        """posterior_model.py:101-165 with context-independent SNV priors throughout (module docstring).  ``posterior_loader``
-        yields batches of posterior records on the model's device.  Returns the mean loss of every iteration."""
+        """posterior_model.py:101-165: Adam on the spectra against the negative log evidence (E step, one kernel per
+        batch), then the priors' M step; context-dependent SNV priors from the second half of the iterations on.
+        ``posterior_loader`` yields batches of posterior records on the model's device.  Returns the mean loss of every
+        iteration."""
         optimizer = torch.optim.Adam(self.spectra.parameters(), lr=learning_rate)
         self.priors.disable_context_dependent_snv_priors()
         history = []
         for epoch in range(1, num_iterations + 1):
+            if epoch > (num_iterations / 2):
+                self.priors.enable_context_dependent_snv_priors()
             totals_tc = torch.zeros((len(Variation), NUM_CALLS), device=self._device)
             somatic_snv_rrra = torch.zeros((5, 5, 5, 5), device=self._device)
             snv_context_rrra = torch.zeros((5, 5, 5, 5), device=self._device)
@@ -240,7 +256,7 @@ class PosteriorModel(nn.Module):
                 optimizer.step()
                 loss_sum += loss.detach() * batch.size()
                 count += batch.size()
-            self.update_priors_m_step(totals_tc, ignored_to_non_ignored_ratio)
+            self.update_priors_m_step(totals_tc, ignored_to_non_ignored_ratio, somatic_snv_rrra, snv_context_rrra)
             history.append(float(loss_sum) / max(count, 1))
             if summary_writer is not None:
                 summary_writer.add_scalar("spectrum negative log evidence", history[-1], epoch)

@@ -176,7 +176,17 @@ def test_learn_priors_and_spectra_lowers_the_negative_log_evidence():
     assert len(history) == 15 and np.all(np.isfinite(history)) and history[-1] < history[0]
     pri = model.priors.log_priors_vc.detach().cpu().numpy()
     assert np.all(pri[:, 2] == 0) and np.all(pri[:, 3] == 0) and np.all(pri[:, [0, 1, 4]] < 0)
-    assert torch.all(model.priors.somatic_snv_log_priors_rrra == model.priors.log_priors_vc[0, 0])
+    # context-dependent SNV priors are on from the second half (posterior_model.py:125-127): the SNV entries hold the fitted
+    # log mutation rates (snv_context_priors.py), the deletion / ref == alt entries what the first half's M steps filled in
+    assert model.priors.use_context_dependent_snv_priors
+    rrra = model.priors.somatic_snv_log_priors_rrra.detach().cpu()
+    from permutect_b200.architecture.snv_context_priors import convert_rrra_tensor_to_sc
+    sc = convert_rrra_tensor_to_sc(rrra)
+    assert torch.all(torch.isfinite(sc)) and torch.all(sc < 0) and float(sc.max() - sc.min()) > 0
+    assert float(rrra[4, 0, 0, 0]) == float(rrra[0, 1, 0, 1]) and float(rrra[4, 0, 0, 0]) < 0
+    # and the kernel consumes them: posteriors stay normalised and finite
+    probs = model.posterior_probabilities_bc(batches[0])
+    assert torch.all(torch.isfinite(probs)) and torch.allclose(probs.sum(1), torch.ones_like(probs[:, 0]), atol=1e-4)
 
 
 @pytest.mark.gpu
