@@ -366,6 +366,35 @@ def run_training(args, model, ia, fa, reads, dev, world, barrier):
                     "flat grad all-reduce + clip(1.0) + AdamW (FlatAdamW)"}
 
 
+def run_config3_single_gpu(args, model, ia, fa, reads, dev, total_variants=10_000_000, steps=3):
+    """BASELINE config 3 as ONE device-resident batch on ONE GPU (the 10 M variants fit a B200 many times over): the
+    rank's shard repeated until it holds ``total_variants`` -- the same synthetic read sets eight times, inputs far larger
+    than L2 either way.  Reported beside the headline (whose per-GPU shard is what 8 GPUs each get of this config)."""
+    from permutect_b200.data.batch import Batch
+    k = max(1, total_variants // len(ia))
+    total_ref = int(ia[:, 0].astype(np.int64).sum())
+    big_reads = np.concatenate([reads[:total_ref]] * k + [reads[total_ref:]] * k)
+    batch = Batch.from_arrays(np.tile(ia, (k, 1)), np.tile(fa, (k, 1)), big_reads).copy_to(dev)
+    del big_reads
+    batch.offsets()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.inference_mode():
+        first = model.compute_batch_output(batch).logits_b[:len(ia)].clone()
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(steps):
+            out = model.compute_batch_output(batch)
+        ev1.record()
+        torch.cuda.synchronize()
+        # every copy of the shard gets the shard's logits (tiles never straddle the copies' boundaries differently: compare)
+        same = bool(torch.equal(out.logits_b[-len(ia):], first))
+    ms = ev0.elapsed_time(ev1) / steps
+    n = k * len(ia)
+    return {"workload": "BASELINE config 3 on one GPU: 10 M WGS-shaped variants in one device-resident batch",
+            "variants": n, "reads": int(k * len(reads)), "ms_per_step": ms, "variants_per_s": n / (ms / 1e3), "steps": steps,
+            "data": f"the {len(ia)}-variant shard repeated {k}x", "last_copy_equals_first": same}
+
+
 def run_panel(args, model, dev, world, rank, barrier):
     """BASELINE config 5 (high-depth panel stress, sets of ~2 000 reads): a bounded sample of it per GPU, inference and
     training, through the long-set kernels.  Reported beside the headline, not as it."""
@@ -518,6 +547,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--train-batch", type=int, default=65536, help="variants per optimiser step")
     ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--no-config3", action="store_true", help="skip the 10 M-variants-on-one-GPU record (N = 1 only)")
     ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "tf32"],
                     help="arithmetic of the forward's dense layers: tf32x3 = split-precision TF32 on tcgen05 (fp32 parity, "
                          "logits within 1e-3 of the reference), fp32 = FP32 SIMT, tf32 = plain TF32 (looser, stated tolerance); "
@@ -590,7 +620,7 @@ def main():
         fwd_launches, _ = count_library_launches(lambda: model.compute_batch_output(dev_batch))
 
     # ---- end to end through the public API: pinned host batches -> prefetch_generator (H2D on a side stream) ->
-    #      compute_batch_output -> D2H of the logits; every byte of the shard crosses PCIe inside the timed region ----
+    #      compute_batch_output -> posterior records -> D2H; every byte of the shard crosses PCIe inside the timed region ----
     from permutect_b200.data.prefetch_generator import prefetch_generator
     nb = max(1, args.e2e_batches)
     ref_c, alt_c = ia[:, 0].astype(np.int64), ia[:, 1].astype(np.int64)
@@ -602,12 +632,16 @@ def main():
         sub = np.concatenate((reads[ref_off[v0]:ref_off[v1]], reads[total_ref + alt_off[v0]:total_ref + alt_off[v1]]))
         host_batches.append(Batch.from_arrays(ia[v0:v1], fa[v0:v1], sub).pin_memory())
     h2d = sum(b.h2d_bytes() for b in host_batches)
-    logits_host = torch.empty(args.variants, dtype=torch.float32).pin_memory()
+    from permutect_b200.tools.filter_variants import generate_posterior_arrays
+    d2h_seen = [0]
 
     def e2e_pass():
-        for (v0, v1), b in zip(zip(bounds[:-1], bounds[1:]), prefetch_generator(host_batches, dev)):
-            out = model.compute_batch_output(b)
-            logits_host[v0:v1].copy_(out.logits_b, non_blocking=True)
+        # the call filter_variants makes (tools/filter_variants.py:generate_posterior_arrays): per batch the posterior records
+        # (int16 row + fp16-rounded logit + embedding, fp32) come back to host memory
+        n = 0
+        for int_rec, float_rec in generate_posterior_arrays(host_batches, model, dev):
+            n += int_rec.nbytes + float_rec.nbytes
+        d2h_seen[0] = n
 
     with torch.inference_mode():
         for _ in range(2):
@@ -655,6 +689,11 @@ def main():
     if not args.no_train:
         train = run_training(args, model, ia, fa, reads, dev, world, barrier)
 
+    config3 = None
+    if world == 1 and not args.no_config3:
+        config3 = run_config3_single_gpu(args, model, ia, fa, reads, dev)
+        torch.cuda.empty_cache()
+
     panel, small_batch = None, None
     if args.panel_variants > 0 and not args.no_train:
         panel = run_panel(args, model, dev, world, rank, barrier)
@@ -698,12 +737,16 @@ def main():
                    f"{h2d / 2**20:.0f} MiB), CUDA events, max over ranks"},
         "clocks": clocks, "gpu_launches": fwd_launches * args.steps if fwd_launches is not None else None,
         "gpu_launches_per_step": fwd_launches, "gpu_launches_how": "library kernels of one step counted from a CUPTI trace outside the timed region",
-        "e2e": {"value": e2e_value, "unit": "variants/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * args.variants},
+        "e2e": {"value": e2e_value, "unit": "variants/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_seen[0],
+                "call": "tools.filter_variants.generate_posterior_arrays over pinned host batches (prefetch_generator H2D on a side "
+                        "stream, compute_batch_output, pmt_pack_posterior, posterior records D2H into pinned host arrays)"},
         "roofline": roofline,
     }
     if roofline.get("executed_tensor_flop_per_launch") and read_kernel_ms:
         roofline["executed_tensor_tflops"] = roofline["executed_tensor_flop_per_launch"] / (read_kernel_ms / 1e3) / 1e12
         roofline["frac_of_tf32_mma_peak_executed"] = roofline["executed_tensor_tflops"] / roofline["tf32_mma_peak_tflops_probe"]
+    if config3 is not None:
+        result["config3_single_gpu"] = config3
     if parity is not None:
         result["parity"] = parity
     if train is not None:

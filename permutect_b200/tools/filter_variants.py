@@ -39,12 +39,32 @@ def posterior_arrays_on_device(batch: Batch, logits_b: torch.Tensor, features_be
 @torch.inference_mode()
 def generate_posterior_arrays(loader: Iterable[Batch], model, device=None) -> Iterator[Tuple[np.ndarray, np.ndarray]]:
     """Per batch: (int16 [B, n_int], fp32 [B, 6 + E]) host arrays, exactly what MemoryMappedData.from_generator would store
-    for the reference's posterior Datum objects (memory_mapped_data.py:319-338)."""
-    device = model._device if device is None else device
+    for the reference's posterior Datum objects (memory_mapped_data.py:319-338).
+
+    The records of batch i return to pinned host memory on a copy stream while batch i + 1 is computed (its inputs are already
+    on their way through prefetch_generator), so the arrays of a batch are yielded one iteration late; order and content are
+    those of the plain loop."""
+    device = torch.device(model._device if device is None else device)
+    copy_stream = torch.cuda.Stream(device)
+    pending = None
     for batch in prefetch_generator(loader, device):
         output = model.compute_batch_output(batch)
         int_out, float_out = posterior_arrays_on_device(batch, output.logits_b, output.features_be)
-        yield int_out.cpu().numpy(), float_out.cpu().numpy()
+        copy_stream.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(copy_stream):
+            int_host = torch.empty(int_out.shape, dtype=int_out.dtype, pin_memory=True).copy_(int_out, non_blocking=True)
+            float_host = torch.empty(float_out.shape, dtype=float_out.dtype, pin_memory=True).copy_(float_out, non_blocking=True)
+            int_out.record_stream(copy_stream)
+            float_out.record_stream(copy_stream)
+            done = torch.cuda.Event()
+            done.record(copy_stream)
+        if pending is not None:
+            pending[2].synchronize()
+            yield pending[0].numpy(), pending[1].numpy()
+        pending = (int_host, float_host, done)
+    if pending is not None:
+        pending[2].synchronize()
+        yield pending[0].numpy(), pending[1].numpy()
 
 
 def generate_posterior_data(loader: Iterable[Batch], model, device=None) -> Iterator[Datum]:
