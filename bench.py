@@ -423,9 +423,34 @@ def run_panel(args, model, dev, world, rank, barrier):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    from permutect_b200.engine import library as pmt_lib
     model.set_epoch_type(Epoch.VALID)
     with torch.inference_mode():
         infer_ms = timed(lambda i: model.compute_batch_output(parent), 2, 3)
+        # the same sample through the FP32 long-set kernel (what every mode used before the sets went onto the tile pipeline)
+        simt_ms = None
+        if pmt_lib.get_precision() != "fp32":
+            os.environ["PMT_LONG_SIMT"] = "1"
+            try:
+                simt_ms = timed(lambda i: model.compute_batch_output(parent), 1, 2)
+            finally:
+                os.environ.pop("PMT_LONG_SIMT", None)
+    # a larger inference sample: 32 768 sets per GPU (a 4 096-set sample repeated 8 times, ~67 M reads)
+    big = None
+    if args.panel_big_variants > 0:
+        base_n = min(4096, args.panel_big_variants)
+        k = max(1, args.panel_big_variants // base_n)
+        bia, bfa, breads = make_panel_arrays(base_n, seed=1000 * 7 + rank)
+        tref = int(bia[:, 0].astype(np.int64).sum())
+        big_batch = Batch.from_arrays(np.tile(bia, (k, 1)), np.tile(bfa, (k, 1)),
+                                      np.concatenate([breads[:tref]] * k + [breads[tref:]] * k)).copy_to(dev)
+        with torch.inference_mode():
+            big_ms = timed(lambda i: model.compute_batch_output(big_batch), 1, 3)
+        big = {"variants_per_gpu": k * base_n, "reads_per_gpu": k * len(breads), "inference_ms": big_ms,
+               "inference_variants_per_s": k * base_n * world / (big_ms / 1e3), "inference_reads_per_s": k * len(breads) * world / (big_ms / 1e3),
+               "data": f"a {base_n}-set sample repeated {k}x"}
+        del big_batch
+        torch.cuda.empty_cache()
     model.set_epoch_type(Epoch.TRAIN)
     opt = make_optimizer(model, learning_rate=1e-3, weight_decay=0.01)
     frac = torch.full((n,), 0.8, device=dev)
@@ -444,7 +469,14 @@ def run_panel(args, model, dev, world, rank, barrier):
             "inference_variants_per_s": n * world / (infer_ms / 1e3), "inference_reads_per_s": len(reads) * world / (infer_ms / 1e3),
             "inference_ms": infer_ms, "train_variants_per_s": n * world / (train_ms / 1e3),
             "train_reads_per_s": kept[0] * world / (train_ms / 1e3), "train_ms": train_ms, "train_reads_per_step": kept[0],
-            "kernels": "reads_forward_long_kernel / reads_backward_long_kernel (FP32 SIMT, sets walked in chunks of 128 reads)"}
+            "inference_ms_fp32_long_kernel": simt_ms,
+            "inference_reads_per_s_fp32_long_kernel": len(reads) * world / (simt_ms / 1e3) if simt_ms else None,
+            "inference_large_sample": big,
+            "kernels": ("inference: reads_forward_tc_kernel<.., LONG> (tcgen05; a set is cut into single-side tiles of 128 reads that are in "
+                        "flight together and exchange their mean-field / set-sum partials through global memory); training: "
+                        "reads_forward_long_kernel / reads_backward_long_kernel (FP32 SIMT, sets walked in chunks of 128 reads)"
+                        if pmt_lib.get_precision() != "fp32" else
+                        "reads_forward_long_kernel / reads_backward_long_kernel (FP32 SIMT, sets walked in chunks of 128 reads)")}
 
 
 def run_small_batch_training(model, dev, batch_variants=64, steps=100):
@@ -547,6 +579,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--train-batch", type=int, default=65536, help="variants per optimiser step")
     ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--panel-big-variants", type=int, default=32768, help="sets per GPU of the larger panel inference sample (0: skip)")
     ap.add_argument("--no-config3", action="store_true", help="skip the 10 M-variants-on-one-GPU record (N = 1 only)")
     ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "tf32"],
                     help="arithmetic of the forward's dense layers: tf32x3 = split-precision TF32 on tcgen05 (fp32 parity, "

@@ -691,7 +691,7 @@ static size_t long_scratch_floats_per_cta(const Plan& P, const PmtBatch* batch);
 // only), the batch-dependent regions follow:
 //   [256 B counters][SIMT images][tcgen05 read-kernel images][tcgen05 CNN images] | [info_seq][long-set scratch][tile list]
 struct FwdLayout {
-  size_t image, tc_image, cnn_tc_image, info_seq, long_scratch, tiles, end;
+  size_t image, tc_image, cnn_tc_image, info_seq, long_scratch, tiles, long_tc, long_tc_bytes, end;
 };
 static FwdLayout forward_layout(const Plan& P, const CnnGeom& G, const PmtModelDesc* desc, const PmtBatch* batch) {
   FwdLayout L;
@@ -701,7 +701,9 @@ static FwdLayout forward_layout(const Plan& P, const CnnGeom& G, const PmtModelD
   L.cnn_tc_image = off; off += pmt_cnn_tc_image_bytes(P); off = (off + 255) & ~(size_t)255;
   L.info_seq = off; off += (size_t)batch->n_variants * (desc->d_info + desc->d_seq) * sizeof(float); off = (off + 255) & ~(size_t)255;
   L.long_scratch = off; off += long_scratch_floats_per_cta(P, batch) * sizeof(float) * 148; off = (off + 255) & ~(size_t)255;
-  L.tiles = off; off += pmt_tc_tiles_bytes(batch);
+  L.tiles = off; off += pmt_tc_tiles_bytes(batch); off = (off + 255) & ~(size_t)255;
+  L.long_tc_bytes = pmt_tc_long_bytes(P, batch);
+  L.long_tc = off; off += L.long_tc_bytes;
   L.end = off;
   return L;
 }
@@ -832,7 +834,12 @@ static int forward_impl(const PmtModelDesc* desc, const float* weights, const Pm
     reads_forward_kernel<<<grid, NTHREADS, smem, st>>>(P, A);
     pmt_profile_end(st);
   }
-  if (pmt_has_long_sets(batch)) {
+  if (pmt_has_long_sets(batch) && mode != PMT_PRECISION_FP32 && L.long_tc_bytes > 0) {
+    // sets longer than a tile, cut into single-side tiles on the same tensor-core pipeline (pmt_tc.cuh: LongTile)
+    PmtOutputs o2 = *out;
+    o2.info_seq_be = info_seq;
+    if (pmt_launch_reads_tc_long(P, weights, batch, &o2, tc_image, reinterpret_cast<unsigned char*>(ws + L.long_tc), mode, st)) return 1;
+  } else if (pmt_has_long_sets(batch)) {
     A.scratch = reinterpret_cast<float*>(ws + L.long_scratch);
     A.scratch_stride = (long long)long_scratch_floats_per_cta(P, batch);
     const int lgrid = long_grid(batch, n_sm < 148 ? n_sm : 148);

@@ -44,6 +44,11 @@ int pmt_precision_mode();
 bool pmt_tc_supported(const pmt::Plan& P);
 size_t pmt_tc_image_bytes(const pmt::Plan& P);
 size_t pmt_tc_tiles_bytes(const PmtBatch* batch);
+// host: sets longer than a tile on the tensor-core forward.  pmt_tc_long_bytes() == 0: not available for this batch (no long
+// sets, unknown row count, or a set longer than one round of tiles) -- the FP32 long-set kernel takes them.
+size_t pmt_tc_long_bytes(const pmt::Plan& P, const PmtBatch* batch);
+int pmt_launch_reads_tc_long(const pmt::Plan& P, const float* weights, const PmtBatch* batch, const PmtOutputs* out,
+                             unsigned char* image_buf, unsigned char* long_buf, int mode, cudaStream_t st);
 int pmt_launch_reads_tc(const pmt::Plan& P, const float* weights, const PmtBatch* batch, const PmtOutputs* out,
                         unsigned char* image_buf, unsigned char* tiles_buf, bool reuse_images, int n_sm, int mode, cudaStream_t st);
 size_t pmt_tc_bwd_workspace_bytes(const pmt::Plan& P, const PmtBatch* batch);

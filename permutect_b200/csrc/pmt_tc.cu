@@ -45,7 +45,13 @@ __device__ __forceinline__ void save_operand(unsigned char* op, int row, int col
         make_float4(rna_tf32(v[4 * i]), rna_tf32(v[4 * i + 1]), rna_tf32(v[4 * i + 2]), rna_tf32(v[4 * i + 3]));
 }
 
-template <int PASSES, bool TRACE, bool SAVE>
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <int PASSES, bool TRACE, bool SAVE, bool LONG = false>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_constant__ TcPlan TP, const __grid_constant__ TcArgs A,
                         int n_stages, int stage_bytes, long long* __restrict__ trace) {
@@ -110,8 +116,9 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
   tc_fence_after();
 
   // tiles [tile_first, n_tiles) of the list (the training recompute walks the list in bounded ranges)
+  static_assert(!(LONG && SAVE), "the long-set tiles are forward only");
   const int tile_first = SAVE ? A.tile_first : 0;
-  const int n_tiles = SAVE ? min(__ldg(A.tiles), A.tile_limit) - tile_first : __ldg(A.tiles);
+  const int n_tiles = LONG ? __ldg(A.lng.n_tiles) : (SAVE ? min(__ldg(A.tiles), A.tile_limit) - tile_first : __ldg(A.tiles));
   const int sched = A.sched;
   const int n_slots = (sched == 1 ? 1 : 2) * gridDim.x;
   // every slot of the CTA runs the same number of rounds (an idle slot processes an empty tile)
@@ -138,18 +145,51 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
         mbar_wait(smem_addr(&S->meta_free[slot][b]), fparity);
         const int t = (int)blockIdx.x + slot * (int)gridDim.x + round * n_slots;
         int v0 = 0, nv = 0;
-        if (t < n_tiles) { v0 = __ldg(A.tiles + 2 + 2 * (tile_first + t)); nv = __ldg(A.tiles + 3 + 2 * (tile_first + t)); }
         long long r_base = 0, a_base = 0;
         int nr_tot = 0, na_tot = 0, ref_pad = 0;
-        if (nv > 0) {
-          r_base = __ldg(A.batch.ref_off + v0); a_base = __ldg(A.batch.alt_off + v0);
-          nr_tot = (int)(__ldg(A.batch.ref_off + v0 + nv) - r_base); na_tot = (int)(__ldg(A.batch.alt_off + v0 + nv) - a_base);
-          ref_pad = (nr_tot + 3) & ~3;
+        if (LONG) {
+          // one tile = up to TILE rows of one side of one long set: a ref tile is "all ref rows" (ref_pad = TILE), an alt
+          // tile "all alt rows" (ref_pad = 0), so the per-row code below and in the epilogue warps needs no other change
+          int4 d0 = make_int4(-1, 0, 0, 0), d1 = make_int4(0, 0, 0, 0);
+          if (t < n_tiles) {
+            const int4* lp = reinterpret_cast<const int4*>(A.lng.tiles + t);
+            d0 = __ldg(lp); d1 = __ldg(lp + 1);
+          }
+          nv = d0.x >= 0 ? 1 : 0;
+          v0 = nv ? d0.x : 0;
+          int set_ref = 0, set_alt = 0;
+          if (nv) {
+            const long long r0 = __ldg(A.batch.ref_off + v0), a0 = __ldg(A.batch.alt_off + v0);
+            set_ref = (int)(__ldg(A.batch.ref_off + v0 + 1) - r0); set_alt = (int)(__ldg(A.batch.alt_off + v0 + 1) - a0);
+            r_base = r0 + (d0.y == 0 ? d0.z : 0); a_base = a0 + (d0.y == 1 ? d0.z : 0);
+            nr_tot = d0.y == 0 ? d0.w : 0; na_tot = d0.y == 1 ? d0.w : 0;
+            ref_pad = d0.y == 0 ? TILE : 0;
+          }
+          if (lane == 0) {
+            TB->v0 = v0; TB->nv = nv; TB->ref_pad = ref_pad;
+            TB->lt[0] = d1.y; TB->lt[1] = d1.x; TB->lt[2] = d1.z; TB->lt[3] = d1.w; TB->lt[4] = d0.y; TB->lt[5] = d0.w;
+            TB->lt[6] = set_ref; TB->lt[7] = set_alt;
+            TB->m.ref_start[0] = 0; TB->m.ref_cnt[0] = (unsigned char)nr_tot;
+            TB->m.alt_start[0] = (unsigned char)(ref_pad & 127); TB->m.alt_cnt[0] = (unsigned char)na_tot;
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) TB->m.rowvar[q * 32 + lane] = (q * 32 + lane < nr_tot + na_tot) ? (unsigned char)0 : (unsigned char)255;
+          if (nv && lane == 0 && A.out.info_seq_be) {
+            const char* e = reinterpret_cast<const char*>(A.out.info_seq_be + (long long)v0 * DIS);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(e));
+          }
+        } else {
+          if (t < n_tiles) { v0 = __ldg(A.tiles + 2 + 2 * (tile_first + t)); nv = __ldg(A.tiles + 3 + 2 * (tile_first + t)); }
+          if (nv > 0) {
+            r_base = __ldg(A.batch.ref_off + v0); a_base = __ldg(A.batch.alt_off + v0);
+            nr_tot = (int)(__ldg(A.batch.ref_off + v0 + nv) - r_base); na_tot = (int)(__ldg(A.batch.alt_off + v0 + nv) - a_base);
+            ref_pad = (nr_tot + 3) & ~3;
+          }
+          if (lane == 0) { TB->v0 = v0; TB->nv = nv; TB->ref_pad = ref_pad; }
+          reinterpret_cast<unsigned*>(TB->m.rowvar)[lane] = 0xFFFFFFFFu;   // 255 = padding row
         }
-        if (lane == 0) { TB->v0 = v0; TB->nv = nv; TB->ref_pad = ref_pad; }
-        reinterpret_cast<unsigned*>(TB->m.rowvar)[lane] = 0xFFFFFFFFu;   // 255 = padding row
         __syncwarp();
-        for (int j = lane; j < nv; j += 32) {
+        for (int j = lane; j < (LONG ? 0 : nv); j += 32) {
           const long long r0 = __ldg(A.batch.ref_off + v0 + j), r1 = __ldg(A.batch.ref_off + v0 + j + 1);
           const long long a0 = __ldg(A.batch.alt_off + v0 + j), a1 = __ldg(A.batch.alt_off + v0 + j + 1);
           const int rs = (int)(r0 - r_base), rc = (int)(r1 - r0), as = ref_pad + (int)(a0 - a_base), ac = (int)(a1 - a0);
@@ -279,6 +319,8 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
                      m_alt_start = smem_addr(TB->m.alt_start), m_alt_cnt = smem_addr(TB->m.alt_cnt);
       mbar_wait(smem_addr(&S->meta_full[slot][round & 1]), (round >> 1) & 1);
       const int v0 = TB->v0, nv = TB->nv, ref_pad = TB->ref_pad;
+      const int lt_first = LONG ? TB->lt[0] : 0, lt_k = LONG ? TB->lt[1] : 0, lt_tref = LONG ? TB->lt[2] : 0, lt_talt = LONG ? TB->lt[3] : 0,
+                lt_side = LONG ? TB->lt[4] : 0, lt_rows = LONG ? TB->lt[5] : 0, set_ref = LONG ? TB->lt[6] : 0, set_alt = LONG ? TB->lt[7] : 0;
       const long long my_idx = TB->idx[row], my_src = TB->src[row];
       unsigned char* const scr = (SAVE && t < n_tiles) ? A.scratch + (size_t)t * TP.tile_bytes : nullptr;
       const int rv = (int)lds_u8(m_rowvar + row);
@@ -482,7 +524,51 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
             TR(900 + step);
             named_barrier(slot_bar, 256);
             TR(1000 + step);
-            {   // per-variant mean fields (gated_mlp.py:236-239)
+            if (LONG) {   // mean fields of a set spread over many tiles (pmt_tc.cuh: LongTile)
+              const float regw = lds_f32(bcs + BC_REGW * 4);
+              const int blk = TP.step[step].blk, nb = D.n_blocks;
+              // (a) column sums of this tile's rows -> the tile's slot in global memory; a lane pair per hidden unit
+              if (srow < 32) {
+                const int f = lane >> 1, part = lane & 1;
+                const bool on = f < H && nv > 0;
+                const unsigned src = xch + ((on ? f : 0) * XCH_LD + part) * 4;
+                const int mine = on ? (lt_rows - part + 1) >> 1 : 0;
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                for (int i = 0; i < mine; i += 4) {
+                  const float x0 = lds_f32(src + i * 8), x1 = lds_f32(src + i * 8 + 8), x2 = lds_f32(src + i * 8 + 16), x3 = lds_f32(src + i * 8 + 24);
+                  a0 += x0;
+                  a1 += i + 1 < mine ? x1 : 0.f;
+                  a2 += i + 2 < mine ? x2 : 0.f;
+                  a3 += i + 3 < mine ? x3 : 0.f;
+                }
+                float acc = (a0 + a1) + (a2 + a3);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                if (on && part == 0) A.lng.mf_part[((size_t)(lt_first + lt_k) * nb + blk) * MAXH + f] = acc;
+                __threadfence();
+                __syncwarp();
+                // (b) arrive, then wait for the set's other tiles (all in flight: the list never lets a set straddle a round)
+                if (lane == 0 && nv > 0) {
+                  int* c = A.lng.mf_cnt + (size_t)lt_first * nb + blk;
+                  atomicAdd(c, 1);
+                  const int T = lt_tref + lt_talt;
+                  while (ld_acquire_gpu(c) < T) __nanosleep(20);
+                  __threadfence();
+                }
+                __syncwarp();
+                // (c) totals in tile order -> the slot's mean-field table (segment 0 = ref, 1 = alt)
+                if (lane < 2 * MAXH && nv > 0) {
+                  const int s = lane >= MAXH ? 1 : 0, ff = lane - s * MAXH;
+                  if (ff < H) {
+                    const int t0 = s ? lt_tref : 0, tn = s ? lt_talt : lt_tref;
+                    float tot = 0.f;
+                    for (int tt = 0; tt < tn; ++tt) tot += __ldcg(A.lng.mf_part + ((size_t)(lt_first + t0 + tt) * nb + blk) * MAXH + ff);
+                    const float num = s == 0 ? tot + regw * lds_f32(bcs + (BC_REG + ff) * 4) : tot;
+                    const float den = s == 0 ? (float)set_ref + regw : (float)set_alt + 1e-4f;
+                    sts_f32(sums + (s * MAXH + ff) * 4, __fdividef(num, den));
+                  }
+                }
+              }
+            } else {   // per-variant mean fields (gated_mlp.py:236-239)
               // two threads (a lane pair) per sum: even / odd rows of the set, combined with one shuffle
               const float regw = lds_f32(bcs + BC_REGW * 4);
               const int n_sums = nv * 2 * H;
@@ -633,6 +719,76 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
       named_barrier(slot_bar, 256);
       TR(4);
       // ---- per-variant sums and outputs (ragged_sets.py:144-158; artifact_model.py:291-292) ----
+      if (LONG) {
+        // This tile's raw sums (features of its side; for an alt tile also the K + 2 log-likelihood terms) go to its slot of
+        // fin_part; the tile that arrives last adds the set's partials up in tile order and writes the set's outputs.
+        float* fp = A.lng.fin_part + (size_t)(lt_first + lt_k) * LONG_FIN_W;
+        const int n_items = nv > 0 ? E + (lt_side ? K + 2 : 0) : 0;
+        {   // four threads per sum (rows i, i + 4, ...), combined with two shuffles; groups of four lanes stay inside a warp
+          const int item = srow >> 2, part = srow & 3;
+          const bool on = item < n_items;
+          const int xr = item < E ? item : MAXE + (item - E);
+          const unsigned src = xch + ((on ? xr : 0) * XCH_LD + part) * 4;
+          const int mine = on ? (lt_rows - part + 3) >> 2 : 0;
+          float a0 = 0.f, a1 = 0.f;
+          for (int i = 0; i < mine; i += 2) {
+            const float x0 = lds_f32(src + i * 16), x1 = lds_f32(src + i * 16 + 16);
+            a0 += x0;
+            a1 += i + 1 < mine ? x1 : 0.f;
+          }
+          float acc = a0 + a1;
+          acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+          acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+          if (on && part == 0) fp[xr] = acc;
+        }
+        __threadfence();
+        named_barrier(slot_bar, 256);
+        if (srow < 32) {
+          int last = 0;
+          if (lane == 0 && nv > 0) {
+            __threadfence();
+            last = atomicAdd(A.lng.fin_cnt + lt_first, 1) == lt_tref + lt_talt - 1 ? 1 : 0;
+            if (last) __threadfence();
+          }
+          last = __shfl_sync(0xffffffffu, last, 0);
+          if (last) {
+            const float* base = A.lng.fin_part + (size_t)lt_first * LONG_FIN_W;
+            // set means (ragged_sets.py:144-158): lane = feature, both sides
+            for (int s2 = 0; s2 < 2; ++s2) {
+              float* dst = s2 ? A.out.alt_means_be : A.out.ref_means_be;
+              const int t0 = s2 ? lt_tref : 0, tn = s2 ? lt_talt : lt_tref;
+              if (dst && lane < E) {
+                float tot = 0.f;
+                for (int tt = 0; tt < tn; ++tt) tot += __ldcg(base + (size_t)(t0 + tt) * LONG_FIN_W + lane);
+                dst[(long long)v0 * E + lane] = __fdividef(tot, (float)(s2 ? set_alt : set_ref) + 1e-4f);
+              }
+            }
+            // log-likelihood sums over the alt reads (feature_clustering.py:82-135): lane = term
+            const int k = lane;
+            const bool term = k < K + 2;
+            float acc = 0.f;
+            if (term) {
+              for (int tt = 0; tt < lt_talt; ++tt) acc += __ldcg(base + (size_t)(lt_tref + tt) * LONG_FIN_W + MAXE + k);
+              if (k >= 2) acc += HC->logw[k - 2];
+            }
+            const bool art_term = term && k >= 2;
+            float art_max = art_term ? acc : -INFINITY;
+#pragma unroll
+            for (int m = 1; m < 8; m <<= 1) art_max = fmaxf(art_max, __shfl_xor_sync(0xffffffffu, art_max, m));
+            float sacc = art_term ? expf(acc - art_max) : 0.f;
+#pragma unroll
+            for (int m = 1; m < 8; m <<= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, m);
+            const float ll0 = __shfl_sync(0xffffffffu, acc, 0), ll1 = __shfl_sync(0xffffffffu, acc, 1);
+            if (term) {
+              const long long v = v0;
+              const float art = art_max + logf(sacc);
+              if (A.out.logits_bk) A.out.logits_bk[v * (K + 2) + k] = acc;
+              if (k == 0 && A.out.logits_b) A.out.logits_b[v] = 20.f * tanhf((art - ll0) / 20.f);
+              if (k == 1 && A.out.outlier_logits_b) A.out.outlier_logits_b[v] = ll1 - logsumexp2(ll0, art);
+            }
+          }
+        }
+      } else {
       // set means: one (variant, side, feature) per thread, low threads first
       for (int idx = srow; idx < nv * 2 * E; idx += 256) {
         const int seg = (int)(((unsigned)idx * inv_e) >> 16), e = idx - seg * E;
@@ -692,6 +848,7 @@ reads_forward_tc_kernel(const __grid_constant__ PmtModelDesc D, const __grid_con
           }
         }
       }
+      }   // !LONG
       TR(5);
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_addr(&S->meta_free[slot][round & 1]));   // the tile's tables may be refilled
@@ -779,6 +936,79 @@ __global__ void compact_tiles_kernel(const int* __restrict__ counts, const int* 
     __syncthreads();
   }
   if (tid == 0) tiles[0] = running;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Long-set tile list (pmt_tc.cuh: LongTile).  long_list_kernel appends every set plan_tiles_kernel leaves out (same rule:
+// pad4(ref rows) + alt rows > TILE) to a list, in arbitrary order; long_layout_kernel places the sets' tiles so that no
+// set straddles a round of R slots (padding tiles fill the gaps: the array is preset to -1) and writes the descriptors.
+// ------------------------------------------------------------------------------------------------
+__global__ void long_list_kernel(const long long* __restrict__ ref_off, const long long* __restrict__ alt_off, int B, int cap,
+                                 int* __restrict__ list) {
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < B; v += gridDim.x * blockDim.x) {
+    const long long nr = __ldg(ref_off + v + 1) - __ldg(ref_off + v), na = __ldg(alt_off + v + 1) - __ldg(alt_off + v);
+    if (((nr + 3) & ~3LL) + na > TILE) {
+      const int i = atomicAdd(list, 1);
+      if (i < cap) list[1 + i] = v;
+    }
+  }
+}
+
+__global__ void long_layout_kernel(const long long* __restrict__ ref_off, const long long* __restrict__ alt_off, const int* __restrict__ list,
+                                   int cap, int R, int max_tiles, LongTile* __restrict__ tiles, int* __restrict__ n_tiles) {
+  __shared__ __align__(16) int s_T[1024], s_first[1024];
+  __shared__ int s_pos;
+  const int tid = threadIdx.x;
+  const int n = min(list[0], cap);
+  if (tid == 0) s_pos = 0;
+  __syncthreads();
+  for (int c0 = 0; c0 < n; c0 += blockDim.x) {
+    const int i = c0 + tid;
+    int v = -1, nr = 0, na = 0, tr = 0, ta = 0;
+    if (i < n) {
+      v = list[1 + i];
+      nr = (int)(__ldg(ref_off + v + 1) - __ldg(ref_off + v)); na = (int)(__ldg(alt_off + v + 1) - __ldg(alt_off + v));
+      tr = (nr + TILE - 1) / TILE; ta = (na + TILE - 1) / TILE;
+    }
+    s_T[tid] = tr + ta;
+    __syncthreads();
+    if (tid == 0) {
+      // the only sequential part: positions with round padding (running `room` = slots left in the round, no divisions)
+      int pos = s_pos, room = R - pos % R;
+      const int m = min((int)blockDim.x, n - c0);
+      for (int j0 = 0; j0 < m; j0 += 4) {
+        const int4 t4 = *reinterpret_cast<const int4*>(s_T + j0);
+        const int tt[4] = {t4.x, t4.y, t4.z, t4.w};
+        int f[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int T = tt[q];
+          if (j0 + q >= m || T > R) { f[q] = -1; continue; }   // T > R: host-side guard, never taken
+          if (T > room) { pos += room; room = R; }
+          f[q] = pos;
+          pos += T; room -= T;
+          if (room == 0) room = R;
+        }
+        *reinterpret_cast<int4*>(s_first + j0) = make_int4(f[0], f[1], f[2], f[3]);
+      }
+      s_pos = pos;
+    }
+    __syncthreads();
+    if (i < n) {
+      const int first = s_first[tid];
+      if (first >= 0 && first + tr + ta <= max_tiles) {
+        for (int k = 0; k < tr + ta; ++k) {
+          const int side = k < tr ? 0 : 1, kk = side ? k - tr : k;
+          LongTile t;
+          t.v = v; t.side = side; t.start = kk * TILE; t.cnt = min(TILE, (side ? na : nr) - kk * TILE);
+          t.k = k; t.first = first; t.t_ref = tr; t.t_alt = ta;
+          tiles[first + k] = t;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) *n_tiles = min(s_pos, max_tiles);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1060,4 +1290,101 @@ int pmt_launch_reads_tc(const Plan& P, const float* weights, const PmtBatch* bat
   const int rc = mode == PMT_PRECISION_TF32 ? launch_tc<1>(P.d, T, A, grid, st) : launch_tc<3>(P.d, T, A, grid, st);
   pmt_profile_end(st);
   return rc;
+}
+
+// ---- sets longer than a tile (pmt_tc.cuh: LongTile) ----
+static int long_grid_sms() {
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0, v = 148;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) v = 148;
+    n_sm = v;
+  }
+  return n_sm;
+}
+struct LongLayout {
+  int cap, max_tiles, R;
+  size_t list, n_tiles, tiles, counters, counters_bytes, mf_part, fin_part, end;
+};
+static bool long_layout(const Plan& P, const PmtBatch* batch, LongLayout* L) {
+  if (!batch || !pmt_has_long_sets(batch) || batch->n_rows <= 0 || !pmt_tc_supported(P)) return false;
+  if (getenv("PMT_LONG_SIMT") && atoi(getenv("PMT_LONG_SIMT")) == 1) return false;   // measurement: the FP32 long-set kernel
+  const int R = 2 * long_grid_sms();
+  const long long t_max = (batch->max_rows_per_variant + TILE - 1) / TILE + 1;        // ceil per side
+  if (t_max > R) return false;
+  long long cap = batch->n_rows / (TILE - 2);
+  if (cap > batch->n_variants) cap = batch->n_variants;
+  if (cap < 1) cap = 1;
+  const long long sum_t = batch->n_rows / TILE + 2 * cap;
+  const long long rounds = sum_t / (R - t_max + 1) + 1;
+  const long long max_tiles = sum_t + rounds * (t_max - 1) + R;
+  if (max_tiles > 0x3fffffff) return false;
+  L->cap = (int)cap; L->max_tiles = (int)max_tiles; L->R = R;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  L->list = take((size_t)(1 + cap) * sizeof(int));
+  L->n_tiles = take(256);
+  L->tiles = take((size_t)max_tiles * sizeof(LongTile));
+  L->counters = off;
+  take((size_t)max_tiles * P.d.n_blocks * sizeof(int));
+  take((size_t)max_tiles * sizeof(int));
+  L->counters_bytes = off - L->counters;
+  L->mf_part = take((size_t)max_tiles * P.d.n_blocks * MAXH * sizeof(float));
+  L->fin_part = take((size_t)max_tiles * LONG_FIN_W * sizeof(float));
+  L->end = off;
+  return true;
+}
+size_t pmt_tc_long_bytes(const Plan& P, const PmtBatch* batch) {
+  LongLayout L;
+  return long_layout(P, batch, &L) ? L.end + 1024 : 0;
+}
+
+template <int PASSES>
+static int launch_tc_long(const PmtModelDesc& D, const TcPlan& T, const TcArgs& A, int grid, cudaStream_t st) {
+  const int stage_bytes = PASSES == 3 ? T.slot_bytes : T.slot_bytes / 2;
+  const size_t fixed = 2 * XCH_ROWS * XCH_LD * sizeof(float) + 2 * SUMS_FLOATS * sizeof(float) + 2 * 2 * TILE * 2 * sizeof(float) +
+                       PMT_MAX_BLOCKS * BC_STRIDE * sizeof(float) + sizeof(HeadConstTc) + sizeof(Shared) + 1024 + 64;
+  int n_stages = (int)((227 * 1024 - fixed) / stage_bytes);
+  if (n_stages > NS_MAX) n_stages = NS_MAX;
+  PMT_CHECK(n_stages >= 2, "tensor-core forward: weight ring does not fit in shared memory");
+  const size_t smem = fixed + (size_t)n_stages * stage_bytes;
+  PMT_CUDA(cudaFuncSetAttribute(reads_forward_tc_kernel<PASSES, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  reads_forward_tc_kernel<PASSES, false, false, true><<<grid, FWD_THREADS, smem, st>>>(D, T, A, n_stages, stage_bytes, nullptr);
+  return 0;
+}
+
+// The sets plan_tiles_kernel left out, on the same tensor-core pipeline (the weight images in `image_buf` must be packed:
+// call after pmt_launch_reads_tc).  Every CTA of the grid has to be resident (a tile waits for the other tiles of its
+// set): one CTA per SM, grid = number of SMs.
+int pmt_launch_reads_tc_long(const Plan& P, const float* weights, const PmtBatch* batch, const PmtOutputs* out,
+                             unsigned char* image_buf, unsigned char* long_buf, int mode, cudaStream_t st) {
+  LongLayout L;
+  PMT_CHECK(long_layout(P, batch, &L), "long-set tensor-core path not available for this batch");
+  TcPlan T;
+  pmt_tc_plan(P, &T);
+  unsigned char* image = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(image_buf) + 1023) & ~uintptr_t(1023));
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(long_buf) + 255) & ~uintptr_t(255));
+  int* list = reinterpret_cast<int*>(base + L.list);
+  int* n_tiles = reinterpret_cast<int*>(base + L.n_tiles);
+  LongTile* tiles = reinterpret_cast<LongTile*>(base + L.tiles);
+  const long long* ro = reinterpret_cast<const long long*>(batch->ref_off);
+  const long long* ao = reinterpret_cast<const long long*>(batch->alt_off);
+  PMT_CUDA(cudaMemsetAsync(list, 0, sizeof(int), st));
+  PMT_CUDA(cudaMemsetAsync(tiles, 0xFF, (size_t)L.max_tiles * sizeof(LongTile), st));
+  PMT_CUDA(cudaMemsetAsync(base + L.counters, 0, L.counters_bytes, st));
+  int blocks = (batch->n_variants + 255) / 256;
+  if (blocks > 4 * long_grid_sms()) blocks = 4 * long_grid_sms();
+  long_list_kernel<<<blocks, 256, 0, st>>>(ro, ao, batch->n_variants, L.cap, list);
+  long_layout_kernel<<<1, 1024, 0, st>>>(ro, ao, list, L.cap, L.R, L.max_tiles, tiles, n_tiles);
+  TcArgs A;
+  memset(&A, 0, sizeof(A));
+  A.wflat = weights; A.image = image; A.tiles = nullptr; A.batch = *batch; A.out = *out;
+  A.scratch = nullptr; A.tile_first = 0; A.tile_limit = 0x7fffffff; A.sched = 0;
+  A.lng.tiles = tiles; A.lng.n_tiles = n_tiles;
+  A.lng.mf_cnt = reinterpret_cast<int*>(base + L.counters);
+  A.lng.fin_cnt = A.lng.mf_cnt + (size_t)(((size_t)L.max_tiles * P.d.n_blocks * sizeof(int) + 255) & ~(size_t)255) / sizeof(int);
+  A.lng.mf_part = reinterpret_cast<float*>(base + L.mf_part);
+  A.lng.fin_part = reinterpret_cast<float*>(base + L.fin_part);
+  const int grid = L.R / 2;
+  return mode == PMT_PRECISION_TF32 ? launch_tc_long<1>(P.d, T, A, grid, st) : launch_tc_long<3>(P.d, T, A, grid, st);
 }

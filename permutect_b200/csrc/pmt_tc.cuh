@@ -79,6 +79,32 @@ struct TcPlan {
   TcStep step[MAX_STEPS];
 };
 
+// ---- sets longer than a tile on the tensor-core forward (reads_forward_tc_kernel<.., LONG = true>) ----
+// A long set is cut into tiles of <= TILE rows of ONE side (all its ref tiles, then all its alt tiles, at consecutive
+// positions [first, first + t_ref + t_alt) of the long-tile list).  The tiles of a set are in flight at the same time -- the
+// list is padded so that a set never straddles a round of 2 x grid slots -- and meet twice per gated block and once at
+// the end through global memory: every tile leaves its partial column sums in its own slot, bumps the set's counter, waits
+// for the counter to reach the set's tile count and adds the partials up in tile order (bitwise reproducible).  That is the
+// whole cross-read coupling of the model (gated_mlp.py:236-248, ragged_sets.py:144-158).
+struct LongTile {
+  int v;        // variant (-1: padding tile)
+  int side;     // 0 = ref rows, 1 = alt rows
+  int start;    // first row of the tile inside the set's side
+  int cnt;      // rows
+  int k;        // index of the tile inside its set (ref tiles first)
+  int first;    // position of the set's first tile in the list
+  int t_ref, t_alt;
+};
+constexpr int LONG_FIN_W = MAXE + MAXK + 2;   // per tile: feature sums, then the K + 2 log-likelihood sums (alt tiles)
+struct LongArgs {
+  const LongTile* tiles;
+  const int* n_tiles;      // device: list length incl. padding tiles
+  float* mf_part;          // [tile][n_blocks][MAXH] column sums of the normalised z2 of the tile's rows
+  int* mf_cnt;             // [first][n_blocks] arrival counters (zeroed before the launch)
+  float* fin_part;         // [tile][LONG_FIN_W]
+  int* fin_cnt;            // [first]
+};
+
 struct TcArgs {
   const float* wflat;
   const unsigned char* image;
@@ -90,6 +116,7 @@ struct TcArgs {
   unsigned char* scratch;
   int tile_first, tile_limit;
   int sched;              // 0 = both slots; 1 = one slot only (measurement: what a tile costs without its neighbour)
+  LongArgs lng;           // LONG kernels only
 };
 
 struct TcBwdArgs {
@@ -117,6 +144,7 @@ struct TileBuf {
   long long src[TILE];         // row of the reads array (idx through the gather indices of a downsampled / dataset-order batch)
   unsigned words[TILE * 3];    // the compressed row itself (12-byte rows)
   int v0, nv, ref_pad, pad_;
+  int lt[8];                   // LONG: first, k, t_ref, t_alt, side, rows, set's ref reads, set's alt reads
   SlotMeta m;
 };
 

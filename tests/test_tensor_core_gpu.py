@@ -148,3 +148,60 @@ def test_sharded_evaluation_is_bitwise_identical_to_one_batch():
             parts.append(model.compute_batch_output(Batch.from_arrays(ia[v0:v1], fa[v0:v1], sub).copy_to(dev)))
     for name in ("logits_b", "features_be", "ref_features_be", "logits_bk"):
         assert torch.equal(torch.cat([getattr(p, name) for p in parts]), getattr(whole, name)), name
+
+
+# ---- sets longer than a tile on the tensor cores (BASELINE config 5; pmt_tc.cuh: LongTile) ----
+LONG_SHAPES = [(7, 3), (125, 3), (700, 300), (10, 15), (0, 200), (130, 1), (3, 1), (257, 255), (9, 2), (2900, 1500), (128, 128), (129, 1)]
+
+
+def _long_forward(raw, mode, simt=False):
+    import os
+    from helpers import batch_from_raw
+    g = load("v040_perturbed_edge")
+    dev = torch.device("cuda:0")
+    model = model_from_golden(g, dev)
+    model.set_epoch_type(Epoch.VALID)
+    batch = batch_from_raw(raw, dev)
+    L.set_precision(mode)
+    os.environ["PMT_LONG_SIMT"] = "1" if simt else "0"
+    try:
+        with torch.inference_mode():
+            out = model.compute_batch_output(batch)
+        torch.cuda.synchronize()
+    finally:
+        os.environ.pop("PMT_LONG_SIMT", None)
+    return g, out
+
+
+@pytest.mark.parametrize("mode,atol", [("tf32x3", 1e-3), ("tf32", 0.25)])
+def test_long_sets_on_the_tensor_cores_match_the_oracle(mode, atol):
+    """Sets of up to 4 400 reads cut into single-side tiles that meet through global memory in every gated block
+    (gated_mlp.py:236-248) and for the set sums (ragged_sets.py:144-158), interleaved with tile-sized sets, sets without ref
+    reads and sets that only just pass a tile (125 + 3 padded, 128 + 128, 129 + 1)."""
+    from oracle import artifact_oracle as orc
+    from test_backward_gpu import _long_set_raw
+    raw = _long_set_raw(11, LONG_SHAPES)
+    g, out = _long_forward(raw, mode)
+    with torch.no_grad():
+        want = orc.forward(g.sd, g.hp, raw)
+    torch.testing.assert_close(out.logits_b.cpu(), want["logits_b"], rtol=0, atol=atol)
+    if mode == "tf32x3":
+        torch.testing.assert_close(out.logits_bk.cpu(), want["logits_bk"], rtol=5e-5, atol=2e-3)
+        torch.testing.assert_close(out.features_be.cpu(), want["features_be"], rtol=1e-4, atol=2e-4)
+        torch.testing.assert_close(out.ref_features_be.cpu(), want["ref_features_be"], rtol=1e-4, atol=2e-4)
+        # and against the FP32 long-set kernel on the same batch
+        _, simt = _long_forward(raw, mode, simt=True)
+        torch.testing.assert_close(out.logits_b, simt.logits_b, rtol=0, atol=1e-3)
+
+
+def test_long_sets_on_the_tensor_cores_are_bitwise_reproducible():
+    """Partials are summed in tile order, not in arrival order: two runs (and two different tile placements -- the list of
+    long sets is built with an atomic append) give identical bits."""
+    from test_backward_gpu import _long_set_raw
+    rng = np.random.default_rng(3)
+    shapes = [(int(rng.integers(0, 900)), int(rng.integers(1, 700))) for _ in range(60)]
+    raw = _long_set_raw(13, shapes)
+    _, a = _long_forward(raw, "tf32x3")
+    _, b = _long_forward(raw, "tf32x3")
+    for name in ("logits_b", "logits_bk", "features_be", "ref_features_be"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
