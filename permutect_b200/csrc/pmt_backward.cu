@@ -9,6 +9,7 @@
 //   hap_cnn_backward_kernel   DNASequenceConvolution
 //   reduce_partials_kernel    sum of the CTA-private buffers in CTA order (bitwise reproducible)
 //   skip_fix_kernel           DenseSkipBlock.alpha gradients and the alpha scaling of its last layer
+#include <cstdlib>
 #include <cstring>
 
 // The per-row phases are written for NPART = NTHREADS / TILE threads per tile row.  Measured on B200 (65 536 variants,
@@ -1297,6 +1298,7 @@ size_t pmt_backward_workspace_bytes(const Plan& P, const PmtBatch* batch) {
   if (batch) bytes += 2 * (size_t)batch->n_variants * (P.d.d_info + P.d.d_seq) * sizeof(float);   // info_seq, d_info_seq
   bytes += (size_t)long_bwd_grid(P, batch) * long_bwd_floats_per_cta(P, batch) * sizeof(float) + 256;
   if (pmt_tc_supported(P)) bytes += pmt_tc_bwd_workspace_bytes(P, batch) + 1024;
+  bytes += pmt_cnn_bwd_mma_workspace_bytes(P, batch) + 256;
   return bytes;
 }
 
@@ -1332,6 +1334,13 @@ extern "C" int pmt_backward(const PmtModelDesc* desc, const float* weights, cons
   unsigned char* tc_ws = reinterpret_cast<unsigned char*>(ws + off);
   const size_t tc_ws_bytes = use_tc ? pmt_tc_bwd_workspace_bytes(P, batch) + 1024 : 0;
   off += tc_ws_bytes;
+  // The haplotype CNN's backward follows the precision mode too: tensor-core kernel (pmt_cnn_bwd.cu) unless FP32 is selected
+  const char* cnn_env = getenv("PMT_CNN_BWD_SIMT");   // measurement: the FP32 SIMT kernel in every mode
+  const bool cnn_mma = pmt_precision_mode() != PMT_PRECISION_FP32 && pmt_cnn_bwd_mma_supported(P) && !(cnn_env && atoi(cnn_env) == 1);
+  off = (off + 255) & ~(size_t)255;
+  unsigned char* cnn_ws = reinterpret_cast<unsigned char*>(ws + off);
+  const size_t cnn_ws_bytes = cnn_mma ? pmt_cnn_bwd_mma_workspace_bytes(P, batch) : 0;
+  off += cnn_ws_bytes;
   PMT_CHECK(off <= workspace_bytes, "workspace layout overflow");
 
   PMT_CUDA(cudaMemsetAsync(partials, 0, (size_t)kBwdGrid * desc->n_params * sizeof(float), st));
@@ -1393,7 +1402,11 @@ extern "C" int pmt_backward(const PmtModelDesc* desc, const float* weights, cons
                                                              batch->info_stride, B, d_info_seq, scratch,
                                                              (long long)scr_floats, partials, rows);
   }
-  if (pmt_launch_cnn_backward(P, G, weights, image, batch, d_info_seq, partials, kBwdGrid, st)) return 1;
+  if (cnn_mma) {
+    if (pmt_launch_cnn_backward_mma(P, weights, batch, info_seq, d_info_seq, partials, kBwdGrid, cnn_ws, cnn_ws_bytes, n_sm, st)) return 1;
+  } else if (pmt_launch_cnn_backward(P, G, weights, image, batch, d_info_seq, partials, kBwdGrid, st)) {
+    return 1;
+  }
   reduce_partials_kernel<<<(desc->n_params + 255) / 256, 256, 0, st>>>(partials, kBwdGrid, desc->n_params, d_weights);
   if (use_tc && pmt_finish_reads_tc_backward(P, weights, batch, d_weights, tc_ws, tc_grid, st)) return 1;
   if (P.n_skipfix > 0) skip_fix_kernel<<<P.n_skipfix, 256, 0, st>>>(P, weights, d_weights);

@@ -19,52 +19,12 @@
 // the whole remaining length.  SELU scales are folded into the consuming weights.  Precision modes as pmt_tc.cu.
 #include <cstring>
 
-#include "pmt_host.h"
-#include "pmt_tc_ptx.cuh"
+#include "pmt_cnn_tc.cuh"
 
 namespace pmt {
 namespace cnntc {
 
 using namespace pmt::tc;
-
-constexpr int EPI_WARPS = 16;
-constexpr int THREADS = 32 * (EPI_WARPS + 1);
-constexpr int MMA_WARP = EPI_WARPS;
-constexpr int MAX_LAYERS = 10;
-constexpr int MAX_CHUNKS = 4;
-constexpr int CHUNK_COLS = 128;              // TMEM columns per chunk accumulator: [hi part N | lo part N]
-constexpr int PLANE_ROWS = 344;
-constexpr int PLANE_BYTES = PLANE_ROWS * 16;
-constexpr int BUF_BYTES = 8 * PLANE_BYTES;   // one activation buffer: 32 channels
-constexpr int C0 = 10;                       // one-hot channels: 2 haplotypes x 5 codes
-constexpr int MAX_ITEMS = 24;                // (layer, chunk) work items per group
-constexpr int MAX_TASKS = 8;                 // one-hot entries per lane in the im2col scatter
-
-struct Layer {
-  int first;      // im2col'd one-hot conv
-  int taps;       // shifted-window convs: kernel size; first: number of input positions per row (ksize + dup)
-  int ksteps;     // first: k-steps of 8 columns
-  int N;          // output columns of the MMA (32, or 64 when dup)
-  int dup, pool2; // fused MaxPool(2,1) after the first conv / MaxPool(2,2)
-  int L_in, L_out, L_pool, L_next;
-  int inv_L;      // ceil(65536 / L_in) + : row / L_in == (row * inv_L) >> 16 for rows < 512
-  int act, to_global, out_ch;
-  int img_off, img_bytes;
-  // packing
-  int op, in_ch, ksize, flat_len, scale_in, is_linear;
-};
-
-struct Item {
-  int layer, chunk;
-  int need;   // index of the last done_bar this item's MMAs must have observed (0 = im2col, 1 + i = epilogue of item i)
-};
-
-struct Plan {
-  int n_layers, n_items, G, L0, image_bytes;
-  int n_chunks[MAX_LAYERS];
-  Layer layer[MAX_LAYERS];
-  Item item[MAX_ITEMS];
-};
 
 // Shared-memory matrix descriptor, K-major, no swizzle.  Low word: start address >> 4 | (LBO >> 4) << 16 with LBO = the
 // distance between K-adjacent core matrices; high word (constant): SBO = 128 B between 8-row groups, descriptor version 1.
@@ -134,7 +94,7 @@ struct ItemDev {   // per-item MMA operands, computed once per CTA
 struct EpiItem {   // per-item epilogue constants (three 16-byte shared loads)
   int flags, lo_col, tmem_col, bias_off;
   int inv_L, L_in, L_pool, L_next;
-  int row0, out_ch, pad0_, pad1_;
+  int row0, out_ch, save_a, save_bits;   // SAVE: float offsets inside a group's block of the save buffer (-1: none)
 };
 constexpr int F_DUP = 1, F_POOL2 = 2, F_GLOBAL = 4, F_SELU = 8;
 
@@ -147,11 +107,12 @@ struct Bars {
   int pad_;
 };
 
-template <int PASSES, bool TRACE>
+template <int PASSES, bool TRACE, bool SAVE = false>
 __global__ void __launch_bounds__(THREADS, 1)
 hap_cnn_tc_kernel(const __grid_constant__ Plan TP, const unsigned char* __restrict__ image, const float* __restrict__ wflat,
                   const __grid_constant__ PmtModelDesc D, const void* __restrict__ haps, int hap_kind, long long hap_stride,
-                  int n_variants, float* __restrict__ info_seq, long long* __restrict__ trace) {
+                  int n_variants, float* __restrict__ info_seq, long long* __restrict__ trace,
+                  const __grid_constant__ SaveLayout SL, float* __restrict__ save) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* p = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const unsigned act = smem_addr(p); p += 2 * BUF_BYTES;                 // hi buffer, then lo buffer (planes 8..15)
@@ -205,7 +166,8 @@ hap_cnn_tc_kernel(const __grid_constant__ Plan TP, const unsigned char* __restri
     e.flags = (Ly.dup ? F_DUP : 0) | (Ly.pool2 ? F_POOL2 : 0) | (Ly.to_global ? F_GLOBAL : 0) | (Ly.act == PMT_ACT_SELU ? F_SELU : 0);
     e.lo_col = Ly.N; e.tmem_col = I.chunk * CHUNK_COLS; e.bias_off = I.layer * 32 * (int)sizeof(float);
     e.inv_L = Ly.inv_L; e.L_in = Ly.L_in; e.L_pool = Ly.L_pool; e.L_next = Ly.L_next;
-    e.row0 = I.chunk * 128; e.out_ch = Ly.out_ch; e.pad0_ = 0; e.pad1_ = 0;
+    e.row0 = I.chunk * 128; e.out_ch = Ly.out_ch;
+    e.save_a = SAVE ? SL.a_off[I.layer] : -1; e.save_bits = SAVE ? SL.bits_off[I.layer] : -1;
   }
   __syncthreads();
 
@@ -311,6 +273,8 @@ hap_cnn_tc_kernel(const __grid_constant__ Plan TP, const unsigned char* __restri
         const unsigned bias_a = bias_base + __float_as_int(e0f.w);
         const int inv_L = __float_as_int(e1f.x), L_in = __float_as_int(e1f.y), L_pool = __float_as_int(e1f.z), L_next = __float_as_int(e1f.w);
         const int out_ch = __float_as_int(e2f.y);
+        const int save_a = __float_as_int(e2f.z), save_bits = __float_as_int(e2f.w);
+        unsigned win = 0;   // SAVE: bit i = the second element of the pooling window won for channel 8 cq + i
         const int j = __float_as_int(e2f.x) + row_c;
         const int v = (j * inv_L) >> 16, pos = j - v * L_in;
         int pp = pos;
@@ -337,6 +301,7 @@ hap_cnn_tc_kernel(const __grid_constant__ Plan TP, const unsigned char* __restri
               const float u0 = PASSES == 3 ? __uint_as_float(r[i]) + __uint_as_float(rl[i]) : __uint_as_float(r[i]);
               const float u1 = PASSES == 3 ? __uint_as_float(r2[i]) + __uint_as_float(rl2[i]) : __uint_as_float(r2[i]);
               x[i] = fmaxf(u0, u1);
+              if (SAVE) win |= (u1 > u0 ? 1u : 0u) << i;
             }
           } else {
             tmem_wait_ld();
@@ -348,7 +313,11 @@ hap_cnn_tc_kernel(const __grid_constant__ Plan TP, const unsigned char* __restri
         tc_fence_before();   // the accumulator has been read: a later item may overwrite it once this warp has arrived
         if (flags & F_POOL2) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) x[i] = fmaxf(x[i], __shfl_xor_sync(0xffffffffu, x[i], 1));
+          for (int i = 0; i < 8; ++i) {
+            const float o = __shfl_xor_sync(0xffffffffu, x[i], 1);
+            if (SAVE) win |= (o > x[i] ? 1u : 0u) << i;   // read on the even row of the pair: o is the odd row's value
+            x[i] = fmaxf(x[i], o);
+          }
         }
         x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w; x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
         if (flags & F_GLOBAL) {
@@ -362,6 +331,18 @@ hap_cnn_tc_kernel(const __grid_constant__ Plan TP, const unsigned char* __restri
           if (flags & F_SELU) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) x[i] = selu_u(x[i]);
+          }
+          if (SAVE && valid && save_a >= 0) {   // training: a_l (and the window bits) for the backward (pmt_cnn_bwd.cu)
+            const int cols = G * L_next, col = v * L_next + pp;
+            float* sg = save + (size_t)g * SL.group_floats;
+            float* dstg = sg + save_a + (cq * 8) * cols + col;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {   // rounded to TF32: the backward's MMAs read them as they lie
+              unsigned rb;
+              asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(rb) : "f"(x[i]));
+              dstg[i * cols] = __uint_as_float(rb);
+            }
+            if (save_bits >= 0) reinterpret_cast<unsigned char*>(sg + save_bits)[cq * cols + col] = (unsigned char)win;
           }
           if (valid) {
             const unsigned dst = act + (2 * cq) * PLANE_BYTES + (v * L_next + pp) * 16;
@@ -434,7 +415,7 @@ using namespace pmt::cnntc;
 
 // Builds the layer program; returns false when the CNN is outside this kernel's envelope (the FP32 SIMT kernel
 // hap_cnn_kernel then runs instead).
-static bool build_cnn_tc_plan(const pmt::Plan& P, cnntc::Plan* out) {
+bool pmt_build_cnn_tc_plan(const pmt::Plan& P, cnntc::Plan* out) {
   cnntc::Plan& T = *out;
   memset(&T, 0, sizeof(T));
   const PmtModelDesc& d = P.d;
@@ -563,12 +544,12 @@ static bool build_cnn_tc_plan(const pmt::Plan& P, cnntc::Plan* out) {
 
 bool pmt_cnn_tc_supported(const pmt::Plan& P) {
   cnntc::Plan T;
-  return build_cnn_tc_plan(P, &T);
+  return pmt_build_cnn_tc_plan(P, &T);
 }
 
 size_t pmt_cnn_tc_image_bytes(const pmt::Plan& P) {
   cnntc::Plan T;
-  if (!build_cnn_tc_plan(P, &T)) return 0;
+  if (!pmt_build_cnn_tc_plan(P, &T)) return 0;
   return (size_t)T.image_bytes + 256;
 }
 
@@ -576,9 +557,49 @@ template <int PASSES, bool TRACE>
 static int launch_cnn_tc(const cnntc::Plan& T, const unsigned char* image, const float* weights, const PmtModelDesc& D,
                           const PmtBatch* batch, float* info_seq, int grid, long long* trace, cudaStream_t st) {
   const size_t smem = 2 * BUF_BYTES + T.image_bytes + MAX_LAYERS * 32 * sizeof(float) + sizeof(Bars) + 1024 + 64;
+  SaveLayout SL;
+  memset(&SL, 0, sizeof(SL));
   PMT_CUDA(cudaFuncSetAttribute(hap_cnn_tc_kernel<PASSES, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   hap_cnn_tc_kernel<PASSES, TRACE><<<grid, THREADS, smem, st>>>(T, image, weights, D, batch->haplotypes, batch->hap_kind, batch->hap_stride,
-                                                         batch->n_variants, info_seq, trace);
+                                                         batch->n_variants, info_seq, trace, SL, nullptr);
+  return 0;
+}
+
+void pmt_cnn_save_layout(const cnntc::Plan& T, SaveLayout* out) {
+  SaveLayout& S = *out;
+  memset(&S, 0, sizeof(S));
+  S.G = T.G; S.n_layers = T.n_layers;
+  int off = 0;
+  for (int l = 0; l < MAX_LAYERS; ++l) { S.a_off[l] = -1; S.bits_off[l] = -1; }
+  for (int l = 0; l < T.n_layers; ++l) {
+    const Layer& Ly = T.layer[l];
+    if (Ly.to_global) continue;
+    const int cols = T.G * Ly.L_next;
+    S.a_off[l] = off; off += 32 * cols;
+    if (Ly.dup || Ly.pool2) { S.bits_off[l] = off; off += cols; }   // [4][cols] bytes
+  }
+  S.group_floats = (off + 3) & ~3;
+}
+
+// Training recompute: always the split-precision mode (the saved activations are the fp32-parity ones).
+int pmt_launch_cnn_tc_save(const pmt::Plan& P, const cnntc::Plan& T, const float* weights, const PmtBatch* batch, int v_first, int n,
+                           float* info_seq, const unsigned char* image, float* save, int n_sm, cudaStream_t st) {
+  const size_t smem = 2 * BUF_BYTES + T.image_bytes + MAX_LAYERS * 32 * sizeof(float) + sizeof(Bars) + 1024 + 64;
+  SaveLayout SL;
+  pmt_cnn_save_layout(T, &SL);
+  const int n_groups = (n + T.G - 1) / T.G;
+  const int grid = n_groups < n_sm ? n_groups : n_sm;
+  const size_t esz = batch->hap_kind == PMT_I64 ? 8 : 2;
+  const void* haps = reinterpret_cast<const unsigned char*>(batch->haplotypes) + (size_t)v_first * batch->hap_stride * esz;
+  float* out = info_seq + (size_t)v_first * (P.d.d_info + P.d.d_seq);
+  PMT_CUDA(cudaFuncSetAttribute(hap_cnn_tc_kernel<3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  hap_cnn_tc_kernel<3, false, true><<<grid, THREADS, smem, st>>>(T, image, weights, P.d, haps, batch->hap_kind, batch->hap_stride, n, out,
+                                                                  nullptr, SL, save);
+  return 0;
+}
+
+int pmt_pack_cnn_tc_images(const pmt::Plan& P, const cnntc::Plan& T, const float* weights, unsigned char* image, cudaStream_t st) {
+  pack_cnn_tc_kernel<<<T.n_layers, 256, 0, st>>>(P.d, T, weights, image);
   return 0;
 }
 
@@ -591,7 +612,7 @@ extern "C" int pmt_set_cnn_trace(long long* device_buffer) { g_cnn_trace = devic
 int pmt_launch_cnn_tc(const pmt::Plan& P, const float* weights, const PmtBatch* batch, float* info_seq, unsigned char* image,
                       bool reuse_image, int n_sm, int mode, cudaStream_t st) {
   cnntc::Plan T;
-  PMT_CHECK(build_cnn_tc_plan(P, &T), "haplotype CNN outside the tensor-core envelope");
+  PMT_CHECK(pmt_build_cnn_tc_plan(P, &T), "haplotype CNN outside the tensor-core envelope");
   if (!reuse_image) pack_cnn_tc_kernel<<<T.n_layers, 256, 0, st>>>(P.d, T, weights, image);
   const int n_groups = (batch->n_variants + T.G - 1) / T.G;
   const int grid = n_groups < n_sm ? n_groups : n_sm;

@@ -61,3 +61,8 @@ bool pmt_cnn_tc_supported(const pmt::Plan& P);
 size_t pmt_cnn_tc_image_bytes(const pmt::Plan& P);
 int pmt_launch_cnn_tc(const pmt::Plan& P, const float* weights, const PmtBatch* batch, float* info_seq, unsigned char* image,
                       bool reuse_image, int n_sm, int mode, cudaStream_t st);
+// host (pmt_cnn_bwd.cu): tensor-core (mma.sync TF32) backward of the haplotype CNN
+bool pmt_cnn_bwd_mma_supported(const pmt::Plan& P);
+size_t pmt_cnn_bwd_mma_workspace_bytes(const pmt::Plan& P, const PmtBatch* batch);
+int pmt_launch_cnn_backward_mma(const pmt::Plan& P, const float* weights, const PmtBatch* batch, float* info_seq, const float* d_info_seq,
+                                float* partials, int n_partials, unsigned char* ws, size_t ws_bytes, int n_sm, cudaStream_t st);
