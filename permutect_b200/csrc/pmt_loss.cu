@@ -16,6 +16,7 @@ namespace pmt {
 namespace loss {
 
 constexpr int NT = 128;          // variants per tile = threads per CTA
+constexpr int NTP = NT + 4;      // row stride of the staged (dL/dy, input) pairs: 16-byte rows that start 4 banks apart
 constexpr int MAXW = PMT_MAX_HEAD_DIM;
 constexpr int MAXOPS = PMT_MAX_MLP_OPS;
 
@@ -38,6 +39,24 @@ __device__ __forceinline__ HeadRange head_range(const PmtLinearOp* ops, int n) {
   return r;
 }
 
+// y[n] = b[n] + sum_k W[n][k] h[k] for n < N: four outputs at a time (independent accumulators; h[k] is read once per four
+// FMAs -- the per-thread vectors live in local memory because the programs are run-time data)
+__device__ __forceinline__ void dense4(const float* __restrict__ w, const float* __restrict__ b, int N, int K, const float* h, float* y) {
+  for (int n0 = 0; n0 < N; n0 += 4) {
+    const int n1 = min(n0 + 1, N - 1), n2 = min(n0 + 2, N - 1), n3 = min(n0 + 3, N - 1);
+    const float *w0 = w + n0 * K, *w1 = w + n1 * K, *w2 = w + n2 * K, *w3 = w + n3 * K;
+    float a0 = b[n0], a1 = b[n1], a2 = b[n2], a3 = b[n3];
+    for (int k = 0; k < K; ++k) {
+      const float hk = h[k];
+      a0 = fmaf(w0[k], hk, a0); a1 = fmaf(w1[k], hk, a1); a2 = fmaf(w2[k], hk, a2); a3 = fmaf(w3[k], hk, a3);
+    }
+    y[n0] = a0;
+    if (n0 + 1 < N) y[n0 + 1] = a1;
+    if (n0 + 2 < N) y[n0 + 2] = a2;
+    if (n0 + 3 < N) y[n0 + 3] = a3;
+  }
+}
+
 // Forward of an MLP program on one vector.  hin[i] = the vector fed to Linear i (after the block's leading SELU);
 // xin[i] = the block input at a SKIP_BEGIN op.  Returns the output in `x` (width of the last op).
 __device__ void mlp_forward(const PmtLinearOp* ops, int n_ops, const float* w /* smem, offset by -lo */, float* x,
@@ -52,11 +71,7 @@ __device__ void mlp_forward(const PmtLinearOp* ops, int n_ops, const float* w /*
       for (int k = 0; k < K; ++k) h[k] = x[k];
     }
     if (hin) for (int k = 0; k < K; ++k) hin[i][k] = h[k];
-    for (int n = 0; n < N; ++n) {
-      float acc = w[o.b_off + n];
-      for (int k = 0; k < K; ++k) acc = fmaf(w[o.w_off + n * K + k], h[k], acc);
-      y[n] = acc;
-    }
+    dense4(w + o.w_off, w + o.b_off, N, K, h, y);
     if (o.flags & PMT_OP_SKIP_END) {
       const float alpha = w[o.alpha_off];
       for (int n = 0; n < N; ++n) x[n] = res[n] + alpha * y[n];
@@ -88,7 +103,7 @@ __device__ __forceinline__ void load_variant(const LossArgs& A, int v, float& la
 }
 
 __global__ void __launch_bounds__(NT) losses_forward_kernel(const __grid_constant__ LossArgs A, PmtLossOutputs out) {
-  extern __shared__ float ws[];
+  extern __shared__ __align__(16) float ws[];
   const PmtLossDesc& D = A.d;
   const HeadRange ra = head_range(D.alt_ops, D.n_alt_ops), rs = head_range(D.src_ops, D.n_src_ops);
   float* wa = ws;
@@ -138,11 +153,10 @@ __device__ void mlp_backward_tile(const PmtLinearOp* ops, int n_ops, const float
     float gdot = 0.f;
     if (o.flags & PMT_OP_SKIP_END) {
       const float alpha = w[o.alpha_off];
+      dense4(w + o.w_off, w + o.b_off, N, K, hin[i], gin);   // gin: scratch for the block's un-scaled output y
       for (int n = 0; n < N; ++n) {
         gres[n] = g[n];
-        float y = w[o.b_off + n];
-        for (int k = 0; k < K; ++k) y = fmaf(w[o.w_off + n * K + k], hin[i][k], y);
-        gdot = fmaf(g[n], y, gdot);           // d alpha
+        gdot = fmaf(g[n], gin[n], gdot);           // d alpha
         gy[n] = alpha * g[n];
       }
     } else if (o.flags & PMT_OP_POST_SELU) {
@@ -154,31 +168,48 @@ __device__ void mlp_backward_tile(const PmtLinearOp* ops, int n_ops, const float
     }
     // ---- weight / bias / alpha gradients: stage (gy, hin) variant-minor, then each thread sums its (n, k) entries ----
     __syncthreads();
-    for (int n = 0; n < N; ++n) sD[n * NT + t] = gy[n];
-    for (int k = 0; k < K; ++k) sA[k * NT + t] = hin[i][k];
-    sD[MAXW * NT + t] = gdot;
+    for (int n = 0; n < N; ++n) sD[n * NTP + t] = gy[n];
+    for (int k = 0; k < K; ++k) sA[k * NTP + t] = hin[i][k];
+    sD[MAXW * NTP + t] = gdot;
     __syncthreads();
+    // lanes of a warp read different rows k of sA (16 bytes each, rows 4 banks apart: conflict-free) and mostly one row n
+    // of sD (broadcast); four partial sums, added in a fixed order
     for (int p = t; p < N * K; p += NT) {
       const int n = p / K, k = p - n * K;
-      float s = 0.f;
-      for (int r = 0; r < NT; ++r) s = fmaf(sD[n * NT + r], sA[k * NT + r], s);
-      acc[o.w_off + p] += s;
+      const float4* dr = reinterpret_cast<const float4*>(sD + n * NTP);
+      const float4* ar = reinterpret_cast<const float4*>(sA + k * NTP);
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 4
+      for (int r = 0; r < NT / 4; ++r) {
+        const float4 dv = dr[r], av = ar[r];
+        s0 = fmaf(dv.x, av.x, s0); s1 = fmaf(dv.y, av.y, s1); s2 = fmaf(dv.z, av.z, s2); s3 = fmaf(dv.w, av.w, s3);
+      }
+      acc[o.w_off + p] += (s0 + s1) + (s2 + s3);
     }
     if (t < N) {
-      float s = 0.f;
-      for (int r = 0; r < NT; ++r) s += sD[t * NT + r];
-      acc[o.b_off + t] += s;
+      const float4* dr = reinterpret_cast<const float4*>(sD + t * NTP);
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      for (int r = 0; r < NT / 4; ++r) { const float4 dv = dr[r]; s0 += dv.x; s1 += dv.y; s2 += dv.z; s3 += dv.w; }
+      acc[o.b_off + t] += (s0 + s1) + (s2 + s3);
     }
-    if ((o.flags & PMT_OP_SKIP_END) && t == 0) {
+    if ((o.flags & PMT_OP_SKIP_END) && t == 32) {   // a lane of the second warp: the first one carries the bias sums too
       float s = 0.f;
-      for (int r = 0; r < NT; ++r) s += sD[MAXW * NT + r];
+      for (int r = 0; r < NT; ++r) s += sD[MAXW * NTP + r];
       acc[o.alpha_off] += s;
     }
-    // ---- data gradient ----
-    for (int k = 0; k < K; ++k) {
-      float s = 0.f;
-      for (int n = 0; n < N; ++n) s = fmaf(w[o.w_off + n * K + k], gy[n], s);
-      gin[k] = s;
+    // ---- data gradient: four inputs k at a time ----
+    for (int k0 = 0; k0 < K; k0 += 4) {
+      const int k1 = min(k0 + 1, K - 1), k2 = min(k0 + 2, K - 1), k3 = min(k0 + 3, K - 1);
+      const float* wr = w + o.w_off;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      for (int n = 0; n < N; ++n) {
+        const float gn = gy[n];
+        s0 = fmaf(wr[n * K + k0], gn, s0); s1 = fmaf(wr[n * K + k1], gn, s1); s2 = fmaf(wr[n * K + k2], gn, s2); s3 = fmaf(wr[n * K + k3], gn, s3);
+      }
+      gin[k0] = s0;
+      if (k0 + 1 < K) gin[k0 + 1] = s1;
+      if (k0 + 2 < K) gin[k0 + 2] = s2;
+      if (k0 + 3 < K) gin[k0 + 3] = s3;
     }
     if (o.flags & PMT_OP_SKIP_BEGIN) {
       for (int k = 0; k < K; ++k) g[k] = gres[k] + gin[k] * selu_grad_from_out(hin[i][k]);   // hin = SELU(block input)
@@ -198,7 +229,7 @@ struct LossBwdArgs {
 };
 
 __global__ void __launch_bounds__(NT) losses_backward_kernel(const __grid_constant__ LossBwdArgs B) {
-  extern __shared__ float ws[];
+  extern __shared__ __align__(16) float ws[];
   const LossArgs& A = B.a;
   const PmtLossDesc& D = A.d;
   const HeadRange ra = head_range(D.alt_ops, D.n_alt_ops), rs = head_range(D.src_ops, D.n_src_ops);
@@ -207,8 +238,8 @@ __global__ void __launch_bounds__(NT) losses_backward_kernel(const __grid_consta
   float* wsrc = wa + na;
   float* acca = wsrc + ns;
   float* accs = acca + na;
-  float* sD = accs + ns;                 // [MAXW + 1][NT]
-  float* sA = sD + (MAXW + 1) * NT;      // [MAXW][NT]
+  float* sD = ws + ((2 * (na + ns) + 3) & ~3);   // [MAXW + 1][NTP], 16-byte aligned
+  float* sA = sD + (MAXW + 1) * NTP;     // [MAXW][NTP]
   const int t = threadIdx.x;
   for (int i = t; i < na; i += NT) { wa[i] = A.wflat[ra.lo + i]; acca[i] = 0.f; }
   for (int i = t; i < ns; i += NT) { wsrc[i] = A.wflat[rs.lo + i]; accs[i] = 0.f; }
@@ -370,7 +401,7 @@ extern "C" int pmt_losses_backward(const PmtLossDesc* desc, const float* weights
   B.d_logits_b = d_logits_b; B.d_outlier_logits_b = d_outlier_logits_b; B.d_features_be = d_features_be;
   B.partials = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
   const int grid = loss_grid(batch->n_variants);
-  const size_t smem = (size_t)(2 * (na + ns) + (2 * MAXW + 1) * NT) * sizeof(float);
+  const size_t smem = (size_t)(2 * (na + ns) + 8 + (2 * MAXW + 1) * NTP) * sizeof(float);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   PMT_CUDA(cudaFuncSetAttribute(losses_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   losses_backward_kernel<<<grid, NT, smem, st>>>(B);
