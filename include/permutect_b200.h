@@ -283,6 +283,28 @@ int pmt_adamw_step(float* params, const float* grads, float* exp_avg, float* exp
 int pmt_orthogonal_forward(const float* x, const float* base, int32_t n, float* q, void* stream);
 int pmt_orthogonal_backward(const float* x, const float* base, const float* d_q, int32_t n, float* d_x, void* stream);
 
+/* ---- constraint maps of the parametrised tensors -------------------------------------------------------
+ * The reference registers torch parametrisations on a dozen tensors (utils/parameterizations.py: PositiveNumber = exp,
+ * BoundedNumber = size * sigmoid + min, UnitVector = x / |x| per row, LogWeights = log_softmax); the kernels read the
+ * CONSTRAINED values from the flat buffer.  Forward: w = raw with every group replaced by its constrained value; backward:
+ * g = d_w with every group replaced by its vector-Jacobian product.  mask[n] marks the entries that belong to a group
+ * (the others are copied); groups live in device memory.  One launch each, no host synchronisation.  The rotation of
+ * the orthogonal parametrisation is separate (pmt_orthogonal_forward / _backward): mark its entries in the mask and
+ * fill them afterwards. */
+#define PMT_CONSTRAINT_EXP 0
+#define PMT_CONSTRAINT_BOUNDED 1
+#define PMT_CONSTRAINT_UNIT 2
+#define PMT_CONSTRAINT_UNIT_TWICE 3   /* feature_clustering.py:24 normalises the unit directions once more */
+#define PMT_CONSTRAINT_LOGSOFTMAX 4
+typedef struct PmtConstraintGroup {
+  int32_t type, off, rows, cols;
+  float a, b;                         /* BoundedNumber: size, minimum */
+} PmtConstraintGroup;
+int pmt_constraints_forward(const float* raw, const uint8_t* mask, int64_t n, const PmtConstraintGroup* groups, int32_t n_groups,
+                            float* w, void* stream);
+int pmt_constraints_backward(const float* raw, const float* w, const float* d_w, const uint8_t* mask, int64_t n,
+                             const PmtConstraintGroup* groups, int32_t n_groups, float* g, void* stream);
+
 /* ---- inference caller tail --------------------------------------------------------------------------
  * Replaces the per-variant Python loop of generate_posterior_data (tools/filter_variants.py:302-320): for every
  * variant, int_out[n_int_columns] = its int16 record with REF_COUNT / ALT_COUNT zeroed, float_out[6 + d_feat] (fp32,

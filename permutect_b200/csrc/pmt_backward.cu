@@ -1344,7 +1344,9 @@ extern "C" int pmt_backward(const PmtModelDesc* desc, const float* weights, cons
   PMT_CHECK(off <= workspace_bytes, "workspace layout overflow");
 
   PMT_CUDA(cudaMemsetAsync(partials, 0, (size_t)kBwdGrid * desc->n_params * sizeof(float), st));
-  pmt_launch_prepare(P, G, weights, image, st);
+  // conv images: only the SIMT haplotype-CNN kernels read them (the recompute below when the forward's embeddings are not
+  // passed in, and the SIMT backward)
+  pmt_launch_prepare(P, G, weights, image, st, true, !cnn_mma || !(grads && grads->info_seq_be));
   if (grads && grads->info_seq_be) {
     cudaMemcpyAsync(info_seq, grads->info_seq_be, (size_t)B * w * sizeof(float), cudaMemcpyDeviceToDevice, st);
   } else if (pmt_launch_variant_kernels(P, G, weights, image, batch, info_seq, PMT_PRECISION_FP32, nullptr, false, st)) {

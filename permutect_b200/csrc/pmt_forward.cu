@@ -729,10 +729,13 @@ static size_t long_scratch_floats_per_cta(const Plan& P, const PmtBatch* batch) 
   return chunks * (size_t)(P.d.d_model + P.d.d_ffn) * LD;
 }
 
-int pmt_launch_prepare(const Plan& P, const CnnGeom& G, const float* weights, float* image, cudaStream_t st) {
-  pack_weights_kernel<<<P.n_gemm, 256, 0, st>>>(P, weights, image);
-  if (G.n_spatial > 0) pack_conv_kernel<<<G.n_spatial, 256, 0, st>>>(P, G, weights, image + P.img_total);
-  if (G.n_spatial > 0) pack_convT_kernel<<<G.n_spatial, 256, 0, st>>>(P, G, weights, image + P.img_total);
+// Weight images of the FP32 SIMT kernels.  need_gemm: the tile GEMMs (read path, info MLP, their backward); need_conv: the
+// SIMT haplotype CNN and its backward.  The tensor-core modes skip what none of their kernels reads.
+int pmt_launch_prepare(const Plan& P, const CnnGeom& G, const float* weights, float* image, cudaStream_t st, bool need_gemm,
+                       bool need_conv) {
+  if (need_gemm) pack_weights_kernel<<<P.n_gemm, 256, 0, st>>>(P, weights, image);
+  if (need_conv && G.n_spatial > 0) pack_conv_kernel<<<G.n_spatial, 256, 0, st>>>(P, G, weights, image + P.img_total);
+  if (need_conv && G.n_spatial > 0) pack_convT_kernel<<<G.n_spatial, 256, 0, st>>>(P, G, weights, image + P.img_total);
   return 0;
 }
 
@@ -806,8 +809,16 @@ static int forward_impl(const PmtModelDesc* desc, const float* weights, const Pm
   float* info_seq = out->info_seq_be;
   if (!info_seq) info_seq = reinterpret_cast<float*>(ws + L.info_seq);
   PMT_CUDA(cudaMemsetAsync(counter, 0, 256, st));
-  if (!reuse_images) pmt_launch_prepare(P, G, weights, image, st);
   const int mode = pmt_precision_mode();
+  {
+    // who still reads the SIMT images in a tensor-core mode: the tile-GEMM info MLP (widths outside info_mlp_rows_kernel),
+    // the SIMT haplotype CNN (shapes outside the tensor-core envelope), the FP32 long-set kernel
+    const bool simt_long = pmt_has_long_sets(batch) && !(mode != PMT_PRECISION_FP32 && L.long_tc_bytes > 0);
+    const bool need_gemm = mode == PMT_PRECISION_FP32 || info_rows_w4(P.d) == 0;
+    const bool need_conv = mode == PMT_PRECISION_FP32 || !pmt_cnn_tc_supported(P);
+    if (!reuse_images) pmt_launch_prepare(P, G, weights, image, st, need_gemm || simt_long, need_conv);
+    else if (simt_long && !need_gemm) pmt_launch_prepare(P, G, weights, image, st, true, false);   // depends on the batch: not covered by a prepared call
+  }
   unsigned char* tc_image = reinterpret_cast<unsigned char*>(ws + L.tc_image);
   unsigned char* cnn_tc_image = reinterpret_cast<unsigned char*>(ws + L.cnn_tc_image);
   if (pmt_launch_variant_kernels(P, G, weights, image, batch, info_seq, mode, cnn_tc_image, reuse_images, st)) return 1;

@@ -31,7 +31,8 @@ inline bool pmt_has_long_sets(const PmtBatch* batch) { return batch->max_rows_pe
 int pmt_build_plan(const PmtModelDesc* d, pmt::Plan* out);
 int pmt_cnn_geometry(const pmt::Plan& P, pmt::CnnGeom* out);
 size_t pmt_image_bytes(const pmt::Plan& P, const pmt::CnnGeom& G);
-int pmt_launch_prepare(const pmt::Plan& P, const pmt::CnnGeom& G, const float* weights, float* image, cudaStream_t st);
+int pmt_launch_prepare(const pmt::Plan& P, const pmt::CnnGeom& G, const float* weights, float* image, cudaStream_t st,
+                       bool need_gemm = true, bool need_conv = true);
 int pmt_launch_variant_kernels(const pmt::Plan& P, const pmt::CnnGeom& G, const float* weights, const float* image,
                                const PmtBatch* batch, float* info_seq, int mode, unsigned char* cnn_tc_image, bool reuse_images,
                                cudaStream_t st);

@@ -234,3 +234,133 @@ extern "C" int pmt_orthogonal_backward(const float* x, const float* base, const 
   PMT_CHECK(e == cudaSuccess, "pmt_orthogonal_backward launch failed: %s", cudaGetErrorString(e));
   return 0;
 }
+
+// ================================================================================================
+// Constraint maps of the parametrised tensors on the flat parameter buffer (parameterizations.py: PositiveNumber,
+// BoundedNumber, UnitVector, LogWeights) and their vector-Jacobian products: one launch each instead of ~20 / ~30 tensor
+// ops per training step.  Every CTA copies its share of the unconstrained entries (mask 0); the groups are walked by the
+// warps of CTA 0, one group per warp trip.
+// ================================================================================================
+namespace pmt {
+namespace optim {
+
+struct GroupDesc { int type, off, rows, cols; float a, b; };   // PMT_CONSTRAINT_*; a, b: BoundedNumber size and minimum
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+template <bool BACKWARD>
+__global__ void constraints_kernel(const float* __restrict__ raw, const float* __restrict__ w_in, const float* __restrict__ d_w,
+                                   const unsigned char* __restrict__ mask, long long n, const GroupDesc* __restrict__ groups, int n_groups,
+                                   float* __restrict__ out) {
+  // unconstrained entries: forward w = raw, backward g = d_w
+  const float* src = BACKWARD ? d_w : raw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    if (!mask[i]) out[i] = src[i];
+  if (blockIdx.x != 0) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  for (int gi = warp; gi < n_groups; gi += n_warps) {
+    const GroupDesc G = groups[gi];
+    if (G.type == PMT_CONSTRAINT_EXP) {                    // PositiveNumber: exp(x)
+      for (int i = lane; i < G.rows * G.cols; i += 32) {
+        const int p = G.off + i;
+        out[p] = BACKWARD ? d_w[p] * w_in[p] : expf(raw[p]);
+      }
+    } else if (G.type == PMT_CONSTRAINT_BOUNDED) {         // BoundedNumber: size * sigmoid(x) + min
+      for (int i = lane; i < G.rows * G.cols; i += 32) {
+        const int p = G.off + i;
+        const float sg = 1.f / (1.f + expf(-raw[p]));
+        out[p] = BACKWARD ? d_w[p] * G.a * sg * (1.f - sg) : fmaf(G.a, sg, G.b);
+      }
+    } else if (G.type == PMT_CONSTRAINT_LOGSOFTMAX) {      // LogWeights: log_softmax over the whole tensor
+      const int cnt = G.rows * G.cols;
+      float mx = -INFINITY;
+      for (int i = lane; i < cnt; i += 32) mx = fmaxf(mx, raw[G.off + i]);
+      mx = warp_max(mx);
+      float se = 0.f;
+      for (int i = lane; i < cnt; i += 32) se += expf(raw[G.off + i] - mx);
+      const float lse = mx + logf(warp_sum(se));
+      if (!BACKWARD) {
+        for (int i = lane; i < cnt; i += 32) out[G.off + i] = raw[G.off + i] - lse;
+      } else {
+        float sg = 0.f;
+        for (int i = lane; i < cnt; i += 32) sg += d_w[G.off + i];
+        sg = warp_sum(sg);
+        for (int i = lane; i < cnt; i += 32) out[G.off + i] = d_w[G.off + i] - expf(raw[G.off + i] - lse) * sg;
+      }
+    } else {                                               // UnitVector rows x / |x| (TWICE: normalised once more, quirk Q5)
+      const bool twice = G.type == PMT_CONSTRAINT_UNIT_TWICE;
+      for (int r = 0; r < G.rows; ++r) {
+        const int base = G.off + r * G.cols;
+        float ss = 0.f;
+        for (int c = lane; c < G.cols; c += 32) { const float x = raw[base + c]; ss = fmaf(x, x, ss); }
+        const float n1 = sqrtf(warp_sum(ss));
+        float n2 = 1.f;
+        if (twice) {
+          float s2 = 0.f;
+          for (int c = lane; c < G.cols; c += 32) { const float u = raw[base + c] / n1; s2 = fmaf(u, u, s2); }
+          n2 = sqrtf(warp_sum(s2));
+        }
+        if (!BACKWARD) {
+          for (int c = lane; c < G.cols; c += 32) { const float u = raw[base + c] / n1; out[base + c] = twice ? u / n2 : u; }
+        } else {
+          // gu <- (gu - u2 (u2 . gu)) / n2 (when normalised twice), then gx = (gu - u (u . gu)) / n1
+          float dot2 = 0.f;
+          if (twice) {
+            for (int c = lane; c < G.cols; c += 32) { const float u2 = raw[base + c] / n1 / n2; dot2 = fmaf(u2, d_w[base + c], dot2); }
+            dot2 = warp_sum(dot2);
+          }
+          float dot1 = 0.f;
+          for (int c = lane; c < G.cols; c += 32) {
+            const float u = raw[base + c] / n1;
+            const float gu = twice ? (d_w[base + c] - (u / n2) * dot2) / n2 : d_w[base + c];
+            dot1 = fmaf(u, gu, dot1);
+          }
+          dot1 = warp_sum(dot1);
+          for (int c = lane; c < G.cols; c += 32) {
+            const float u = raw[base + c] / n1;
+            const float gu = twice ? (d_w[base + c] - (u / n2) * dot2) / n2 : d_w[base + c];
+            out[base + c] = (gu - u * dot1) / n1;
+          }
+        }
+      }
+    }
+  }
+}
+
+}  // namespace optim
+}  // namespace pmt
+
+static int constraints_launch(bool backward, const float* raw, const float* w, const float* d_w, const uint8_t* mask, int64_t n,
+                              const PmtConstraintGroup* groups, int32_t n_groups, float* out, void* stream) {
+  static_assert(sizeof(PmtConstraintGroup) == sizeof(pmt::optim::GroupDesc), "PmtConstraintGroup layout");
+  PMT_CHECK(raw && mask && out && n > 0 && (n_groups == 0 || groups), "pmt_constraints: missing arguments");
+  PMT_CHECK(!backward || (w && d_w), "pmt_constraints_backward: missing arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int grid = (int)((n + 4 * 256 - 1) / (4 * 256));
+  if (grid > 148) grid = 148;
+  if (grid < 1) grid = 1;
+  const pmt::optim::GroupDesc* g = reinterpret_cast<const pmt::optim::GroupDesc*>(groups);
+  if (backward) pmt::optim::constraints_kernel<true><<<grid, 256, 0, st>>>(raw, w, d_w, mask, n, g, n_groups, out);
+  else pmt::optim::constraints_kernel<false><<<grid, 256, 0, st>>>(raw, nullptr, nullptr, mask, n, g, n_groups, out);
+  cudaError_t e = cudaGetLastError();
+  PMT_CHECK(e == cudaSuccess, "pmt_constraints launch failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+extern "C" int pmt_constraints_forward(const float* raw, const uint8_t* mask, int64_t n, const PmtConstraintGroup* groups, int32_t n_groups,
+                                       float* w, void* stream) {
+  return constraints_launch(false, raw, nullptr, nullptr, mask, n, groups, n_groups, w, stream);
+}
+extern "C" int pmt_constraints_backward(const float* raw, const float* w, const float* d_w, const uint8_t* mask, int64_t n,
+                                        const PmtConstraintGroup* groups, int32_t n_groups, float* g, void* stream) {
+  return constraints_launch(true, raw, w, d_w, mask, n, groups, n_groups, g, stream);
+}

@@ -93,7 +93,7 @@ class PmtLossGrads(C.Structure):
 
 
 EXPORTED_SYMBOLS = ["pmt_posterior_fit_step", "pmt_posterior_fit_workspace_size", "pmt_orthogonal_forward", "pmt_orthogonal_backward", "pmt_posterior_param_count", "pmt_posterior_log_posteriors", "pmt_dataset_read_indices", "pmt_pack_posterior", "pmt_adamw_step", "pmt_adamw_workspace_size", "pmt_losses_forward", "pmt_losses_backward", "pmt_losses_workspace_size", "pmt_set_cnn_trace", "pmt_set_reads_trace", "pmt_set_backward_trace", "pmt_last_error", "pmt_abi_version", "pmt_workspace_size", "pmt_forward", "pmt_forward_prepared", "pmt_backward",
-                    "pmt_decode_reads", "pmt_set_profile_events", "pmt_downsample_counts", "pmt_downsample_fill", "pmt_set_precision", "pmt_get_precision"]
+                    "pmt_decode_reads", "pmt_set_profile_events", "pmt_downsample_counts", "pmt_downsample_fill", "pmt_set_precision", "pmt_get_precision", "pmt_constraints_forward", "pmt_constraints_backward"]
 
 class PmtPosteriorDesc(C.Structure):
     _fields_ = [("n_components", C.c_int32), ("hap_start", C.c_int32), ("hap_len", C.c_int32), ("no_germline_mode", C.c_int32),
@@ -104,6 +104,12 @@ class PmtPosteriorOutputs(C.Structure):
     _fields_ = [("log_priors_bc", C.c_void_p), ("spectra_log_lks_bc", C.c_void_p), ("normal_log_lks_bc", C.c_void_p),
                 ("log_posteriors_bc", C.c_void_p), ("posterior_probabilities_bc", C.c_void_p)]
 
+
+class PmtConstraintGroup(C.Structure):
+    _fields_ = [("type", C.c_int32), ("off", C.c_int32), ("rows", C.c_int32), ("cols", C.c_int32), ("a", C.c_float), ("b", C.c_float)]
+
+
+CONSTRAINT_EXP, CONSTRAINT_BOUNDED, CONSTRAINT_UNIT, CONSTRAINT_UNIT_TWICE, CONSTRAINT_LOGSOFTMAX = 0, 1, 2, 3, 4
 
 _LIB = None
 
@@ -159,6 +165,11 @@ def load():
     lib.pmt_orthogonal_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     lib.pmt_orthogonal_backward.restype = C.c_int
     lib.pmt_orthogonal_backward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.pmt_constraints_forward.restype = C.c_int
+    lib.pmt_constraints_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.pmt_constraints_backward.restype = C.c_int
+    lib.pmt_constraints_backward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
+                                             C.c_void_p, C.c_void_p]
     lib.pmt_posterior_fit_workspace_size.restype = C.c_size_t
     lib.pmt_posterior_fit_workspace_size.argtypes = [C.c_int32, C.c_int32]
     lib.pmt_posterior_fit_step.restype = C.c_int

@@ -198,6 +198,27 @@ class _ConstraintPack:
         cat = lambda xs, dt=torch.long: torch.cat(xs).to(dev) if xs else torch.zeros(0, dtype=dt, device=dev)
         self.exp_idx, self.bnd_idx = cat(exp_idx), cat(bnd_idx)
         self.bnd_size, self.bnd_min = cat(bnd_size, torch.float32), cat(bnd_min, torch.float32)
+        # the same grouping for pmt_constraints_forward / _backward (one launch each on a CUDA device): a byte mask of the
+        # entries that belong to a group and the group table, both resident on the device
+        self.device_groups = None
+        if self.ok and dev.type == "cuda":
+            import numpy as np
+            groups = []
+            for idx in exp_idx:
+                groups.append((L.CONSTRAINT_EXP, int(idx[0]), 1, idx.numel(), 0.0, 0.0))
+            for idx, size, lo in zip(bnd_idx, bnd_size, bnd_min):
+                groups.append((L.CONSTRAINT_BOUNDED, int(idx[0]), 1, idx.numel(), float(size[0]), float(lo[0])))
+            for off, k, d, twice in self.units:
+                groups.append((L.CONSTRAINT_UNIT_TWICE if twice else L.CONSTRAINT_UNIT, off, k, d, 0.0, 0.0))
+            for off, n in self.logws:
+                groups.append((L.CONSTRAINT_LOGSOFTMAX, off, 1, n, 0.0, 0.0))
+            mask = np.zeros(opt.flat.numel(), np.uint8)
+            table = np.zeros(max(len(groups), 1), dtype=[("type", "<i4"), ("off", "<i4"), ("rows", "<i4"), ("cols", "<i4"),
+                                                         ("a", "<f4"), ("b", "<f4")])
+            for j, (t, off, rows, cols, a, b) in enumerate(groups):
+                table[j] = (t, off, rows, cols, a, b)
+                mask[off:off + rows * cols] = 1
+            self.device_groups = (torch.from_numpy(mask).to(dev), torch.from_numpy(table.view(np.uint8).copy()).to(dev), len(groups))
 
 
 class _FastMaterialize(torch.autograd.Function):
@@ -208,6 +229,18 @@ class _FastMaterialize(torch.autograd.Function):
     @staticmethod
     def forward(ctx, opt, pack, anchor, rot_q):
         raw = opt.flat.detach()
+        if pack.device_groups is not None:       # CUDA: the whole map is one kernel (pmt_constraints_forward)
+            mask, table, n_groups = pack.device_groups
+            w = torch.empty_like(raw)
+            L.check(L.load().pmt_constraints_forward(raw.data_ptr(), mask.data_ptr(), raw.numel(), table.data_ptr(), n_groups,
+                                                     w.data_ptr(), torch.cuda.current_stream(raw.device).cuda_stream))
+            if pack.rotation is not None:
+                _, _, _, off, n = pack.rotation
+                w[off:off + n] = rot_q.detach().reshape(-1)
+            ctx.opt, ctx.pack = opt, pack
+            ctx.save_for_backward(raw, w)
+            ctx.rot_shape = None if rot_q is None else rot_q.shape
+            return w
         w = raw.clone()
         e = torch.exp(raw[pack.exp_idx])
         w[pack.exp_idx] = e
@@ -240,6 +273,20 @@ class _FastMaterialize(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_flat):
         opt, pack = ctx.opt, ctx.pack
+        if pack.device_groups is not None:
+            mask, table, n_groups = pack.device_groups
+            raw, w = ctx.saved_tensors
+            d_flat = d_flat.contiguous()
+            g = torch.empty_like(d_flat)
+            L.check(L.load().pmt_constraints_backward(raw.data_ptr(), w.data_ptr(), d_flat.data_ptr(), mask.data_ptr(), d_flat.numel(),
+                                                      table.data_ptr(), n_groups, g.data_ptr(),
+                                                      torch.cuda.current_stream(d_flat.device).cuda_stream))
+            d_rot = None
+            if pack.rotation is not None:
+                _, _, _, off, n = pack.rotation
+                d_rot = d_flat[off:off + n].view(ctx.rot_shape)
+            opt.receive_flat_gradient(g)
+            return None, None, None, d_rot
         e, sg, units, lws = ctx.saved_small
         g = d_flat.clone()
         g[pack.exp_idx] = d_flat[pack.exp_idx] * e

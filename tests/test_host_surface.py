@@ -163,7 +163,8 @@ def test_ctypes_structs_match_the_compiled_header(tmp_path):
     if shutil.which("gcc") is None:
         pytest.skip("gcc not available")
     names = ["PmtLinearOp", "PmtCnnOp", "PmtBlockOffsets", "PmtModelDesc", "PmtBatch", "PmtOutputs", "PmtOutGrads",
-             "PmtLossDesc", "PmtLossBatch", "PmtLossOutputs", "PmtLossGrads", "PmtPosteriorDesc", "PmtPosteriorOutputs"]
+             "PmtLossDesc", "PmtLossBatch", "PmtLossOutputs", "PmtLossGrads", "PmtPosteriorDesc", "PmtPosteriorOutputs",
+             "PmtConstraintGroup"]
     repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     src = tmp_path / "sizes.c"
     src.write_text('#include <stdio.h>\n#include "permutect_b200.h"\nint main(void) {\n' +
