@@ -360,7 +360,8 @@ def run_training(args, model, ia, fa, reads, dev, world, barrier):
             "backward_kernel_ms": prof.mean_ms(), "gpu_launches_per_step": mine, "all_kernels_per_step": total,
             "gpu_launches": mine * args.steps if mine is not None else None,
             "allreduce_us": allreduce_us, "allreduce_bytes": 4 * opt.flat_grad.numel(),
-            "backward": ("tcgen05 (recompute + TF32 data / weight gradient MMAs, pmt_tc_bwd.cu)" if pmt_lib.get_precision() != "fp32"
+            "backward": ("read path: tcgen05 (recompute + TF32 data / weight gradient MMAs, pmt_tc_bwd.cu); haplotype CNN: tcgen05 "
+                         "recompute with saved activations + warp-level TF32 MMAs (pmt_cnn_bwd.cu)" if pmt_lib.get_precision() != "fp32"
                          else "FP32 SIMT"),
             "step": "device DownsampledBatch + compute_batch_output + compute_batch_losses (fused loss head) + backward + "
                     "flat grad all-reduce + clip(1.0) + AdamW (FlatAdamW)"}

@@ -109,6 +109,7 @@ struct TcArgs {
   const float* wflat;
   const unsigned char* image;
   const int* tiles;       // [0] = number of tiles, then (v0, nv) pairs from entry 2
+  const int* perm;        // packed planner: a tile covers positions [v0, v0 + nv) of this variant list; NULL: variants [v0, v0 + nv)
   PmtBatch batch;
   PmtOutputs out;
   // training recompute (SAVE kernels): tiles [tile_first, tile_limit) of the list, scratch of tile t at
@@ -143,6 +144,7 @@ struct TileBuf {
   long long idx[TILE];         // batch row of each tile row (-1: padding)
   long long src[TILE];         // row of the reads array (idx through the gather indices of a downsampled / dataset-order batch)
   unsigned words[TILE * 3];    // the compressed row itself (12-byte rows)
+  int var[TILE];               // the tile's variants (tile list position -> variant through the planner's permutation)
   int v0, nv, ref_pad, pad_;
   int lt[8];                   // LONG: first, k, t_ref, t_alt, side, rows, set's ref reads, set's alt reads
   SlotMeta m;

@@ -932,7 +932,7 @@ int pmt_launch_reads_tc_backward(const Plan& P, const float* weights, const PmtB
   memset(&no_out, 0, sizeof(no_out));
   no_out.info_seq_be = const_cast<float*>(info_seq);   // read by the first gated block's concat
   TcArgs F;
-  F.wflat = weights; F.image = image_f; F.tiles = tiles; F.batch = *batch; F.out = no_out; F.scratch = scratch; F.sched = 0;
+  F.wflat = weights; F.image = image_f; F.tiles = tiles; F.perm = nullptr; F.batch = *batch; F.out = no_out; F.scratch = scratch; F.sched = 0;
   TcBwdArgs Bk;
   Bk.wflat = weights; Bk.image_t = image_t; Bk.tiles = tiles; Bk.batch = *batch; Bk.d_logits_bk = d_logits_bk;
   Bk.d_alt_means = d_alt_means; Bk.d_ref_means = d_ref_means; Bk.d_info_seq = d_info_seq; Bk.scratch = scratch; Bk.partials = partials;
