@@ -382,14 +382,31 @@ class DownsampledBatch(Batch):
     """Read-downsampled view of a parent batch without copying reads (batch.py:383-459).
 
     ``read_indices`` lists the kept rows: kept ref rows followed by kept alt rows.  As in the reference
-    the alt entries index the alt block WITHOUT the ref-block offset (quirk Q1, batch.py:436-439) unless
-    ``offset_alt_rows=True`` is requested explicitly.
+    the alt entries index the alt block WITHOUT the ref-block offset (quirk Q1, batch.py:436-439): a downsampled alt set
+    is gathered from the rows of the REF block.  That is the reference's behaviour, so it is the default here (a model
+    trained here sees what a model trained there sees); the first default draw of a process says so once.
+    ``offset_alt_rows=True`` -- per call, or for every call through ``DownsampledBatch.OFFSET_ALT_ROWS = True`` -- gathers
+    the alt rows the keep mask selected (what upstream presumably intended); ``tests/test_downsample_gpu.py`` pins both.
     """
+
+    OFFSET_ALT_ROWS: Optional[bool] = None     # None: the reference's behaviour (quirk Q1) with a one-time warning
+    _warned_q1 = False
 
     def __init__(self, original_batch: Batch, ref_fracs_b: Optional[torch.Tensor] = None,
                  alt_fracs_b: Optional[torch.Tensor] = None, *, read_indices: Optional[torch.Tensor] = None,
                  ref_counts: Optional[torch.Tensor] = None, alt_counts: Optional[torch.Tensor] = None,
-                 offset_alt_rows: bool = False, seed: Optional[int] = None):
+                 offset_alt_rows: Optional[bool] = None, seed: Optional[int] = None):
+        if offset_alt_rows is None:
+            offset_alt_rows = DownsampledBatch.OFFSET_ALT_ROWS
+        if offset_alt_rows is None:
+            offset_alt_rows = False
+            if read_indices is None and not DownsampledBatch._warned_q1:
+                DownsampledBatch._warned_q1 = True
+                import warnings
+                warnings.warn("DownsampledBatch reproduces the reference's alt-row indexing (batch.py:436-439: kept alt indices lack "
+                              "the ref-block offset, so downsampled alt sets are gathered from ref rows). Set "
+                              "DownsampledBatch.OFFSET_ALT_ROWS = True (or pass offset_alt_rows=True) for the corrected gather, "
+                              "False to keep the reference's behaviour without this message.", stacklevel=2)
         self.int_tensor = original_batch.int_tensor
         self.float_tensor = original_batch.float_tensor
         self.reads = original_batch.reads
