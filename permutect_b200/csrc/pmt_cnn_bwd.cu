@@ -78,7 +78,7 @@ __global__ void pack_cnn_bwd_kernel(const __grid_constant__ BPlan BP, const floa
   const BLayer& Ly = BP.layer[blockIdx.x];
   if (blockIdx.x == 0) return;
   const int n = Ly.ks * Ly.Cout8 * Ly.Mt_d * 128;
-  for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+  for (int idx = blockIdx.y * blockDim.x + threadIdx.x; idx < n; idx += gridDim.y * blockDim.x) {
     const int r = idx & 3, lane = (idx >> 2) & 31, frag = idx >> 7;
     const int m = frag % Ly.Mt_d, kc = (frag / Ly.Mt_d) % Ly.Cout8, t = frag / (Ly.Mt_d * Ly.Cout8);
     const int co = kc * 8 + (lane & 3) + ((r & 2) ? 4 : 0), ci = m * 16 + (lane >> 2) + ((r & 1) ? 8 : 0);
@@ -520,7 +520,7 @@ int pmt_launch_cnn_backward_mma(const pmt::Plan& P, const float* weights, const 
   float* save = reinterpret_cast<float*>(p);
   // weight images: the forward's (split precision) and the data gradient's
   if (pmt_pack_cnn_tc_images(P, T, weights, fwd_image, st)) return 1;
-  pack_cnn_bwd_kernel<<<B.n_layers, 256, 0, st>>>(B, weights, bwd_image);
+  pack_cnn_bwd_kernel<<<dim3(B.n_layers, 8), 256, 0, st>>>(B, weights, bwd_image);
   PMT_CUDA(cudaFuncSetAttribute(cnn_backward_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B.smem_bytes));
   const int out_w = P.d.d_info + P.d.d_seq;
   const size_t esz = batch->hap_kind == PMT_I64 ? 8 : 2;

@@ -394,7 +394,7 @@ __global__ void pack_cnn_tc_kernel(const __grid_constant__ PmtModelDesc D, const
   const Layer& Ly = TP.layer[blockIdx.x];
   const int N = Ly.N, R = 2 * N;
   const int taps = Ly.first ? 1 : Ly.taps, chunks = Ly.first ? 2 * Ly.ksteps : 8;
-  for (int idx = threadIdx.x; idx < taps * chunks * R * 4; idx += blockDim.x) {
+  for (int idx = blockIdx.y * blockDim.x + threadIdx.x; idx < taps * chunks * R * 4; idx += gridDim.y * blockDim.x) {
     const int e = idx & 3, r = (idx >> 2) % R, ch = (idx >> 2) / R % chunks, tap = (idx >> 2) / R / chunks;
     const float v = cnn_weight(D, Ly, w, tap, r % N, ch * 4 + e);
     unsigned hb;
@@ -599,7 +599,7 @@ int pmt_launch_cnn_tc_save(const pmt::Plan& P, const cnntc::Plan& T, const float
 }
 
 int pmt_pack_cnn_tc_images(const pmt::Plan& P, const cnntc::Plan& T, const float* weights, unsigned char* image, cudaStream_t st) {
-  pack_cnn_tc_kernel<<<T.n_layers, 256, 0, st>>>(P.d, T, weights, image);
+  pack_cnn_tc_kernel<<<dim3(T.n_layers, 16), 256, 0, st>>>(P.d, T, weights, image);
   return 0;
 }
 
@@ -613,7 +613,7 @@ int pmt_launch_cnn_tc(const pmt::Plan& P, const float* weights, const PmtBatch* 
                       bool reuse_image, int n_sm, int mode, cudaStream_t st) {
   cnntc::Plan T;
   PMT_CHECK(pmt_build_cnn_tc_plan(P, &T), "haplotype CNN outside the tensor-core envelope");
-  if (!reuse_image) pack_cnn_tc_kernel<<<T.n_layers, 256, 0, st>>>(P.d, T, weights, image);
+  if (!reuse_image) pack_cnn_tc_kernel<<<dim3(T.n_layers, 16), 256, 0, st>>>(P.d, T, weights, image);
   const int n_groups = (batch->n_variants + T.G - 1) / T.G;
   const int grid = n_groups < n_sm ? n_groups : n_sm;
   if (g_cnn_trace) {

@@ -21,7 +21,7 @@ __global__ void pack_weights_kernel(const __grid_constant__ Plan P, const float*
   const GemmOp& op = P.gemm[blockIdx.x];
   const int per_image = op.K * op.G * GROUP_STRIDE;
   const int n_images = op.w_alt_off >= 0 ? 2 : 1;
-  for (int idx = threadIdx.x; idx < per_image * n_images; idx += blockDim.x) {
+  for (int idx = blockIdx.y * blockDim.x + threadIdx.x; idx < per_image * n_images; idx += gridDim.y * blockDim.x) {
     const int which = idx / per_image, rem = idx % per_image;
     const int k = rem / (op.G * GROUP_STRIDE), slot = rem % (op.G * GROUP_STRIDE);
     const int grp = slot / GROUP_STRIDE, j = slot % GROUP_STRIDE;
@@ -31,7 +31,7 @@ __global__ void pack_weights_kernel(const __grid_constant__ Plan P, const float*
   }
   // transposed image for the data-gradient GEMM: reduction over n (N rows), K outputs
   const int per_imageT = op.N * op.GT * GROUP_STRIDE;
-  for (int idx = threadIdx.x; idx < per_imageT * n_images; idx += blockDim.x) {
+  for (int idx = blockIdx.y * blockDim.x + threadIdx.x; idx < per_imageT * n_images; idx += gridDim.y * blockDim.x) {
     const int which = idx / per_imageT, rem = idx % per_imageT;
     const int n = rem / (op.GT * GROUP_STRIDE), slot = rem % (op.GT * GROUP_STRIDE);
     const int grp = slot / GROUP_STRIDE, j = slot % GROUP_STRIDE;
@@ -733,7 +733,7 @@ static size_t long_scratch_floats_per_cta(const Plan& P, const PmtBatch* batch) 
 // SIMT haplotype CNN and its backward.  The tensor-core modes skip what none of their kernels reads.
 int pmt_launch_prepare(const Plan& P, const CnnGeom& G, const float* weights, float* image, cudaStream_t st, bool need_gemm,
                        bool need_conv) {
-  if (need_gemm) pack_weights_kernel<<<P.n_gemm, 256, 0, st>>>(P, weights, image);
+  if (need_gemm) pack_weights_kernel<<<dim3(P.n_gemm, 4), 256, 0, st>>>(P, weights, image);
   if (need_conv && G.n_spatial > 0) pack_conv_kernel<<<G.n_spatial, 256, 0, st>>>(P, G, weights, image + P.img_total);
   if (need_conv && G.n_spatial > 0) pack_convT_kernel<<<G.n_spatial, 256, 0, st>>>(P, G, weights, image + P.img_total);
   return 0;

@@ -1169,7 +1169,7 @@ __global__ void pack_tc_kernel(const __grid_constant__ PmtModelDesc D, const __g
   const TcStep& o = TP.step[blockIdx.x];
   const int K = o.KS * 8;
   const int n_kb = (K + 31) / 32;
-  for (int idx = threadIdx.x; idx < n_kb * o.N * 32; idx += blockDim.x) {
+  for (int idx = blockIdx.y * blockDim.x + threadIdx.x; idx < n_kb * o.N * 32; idx += gridDim.y * blockDim.x) {
     const int kb = idx / (o.N * 32), rem = idx % (o.N * 32), n = rem / 32, kk = rem % 32;
     const int k = kb * 32 + kk;
     const float v = k < K ? tc_weight(D, o, w, n, k) : 0.f;
@@ -1402,7 +1402,7 @@ static int launch_tc(const PmtModelDesc& D, const TcPlan& T, const TcArgs& A, in
 }
 
 int pmt_launch_pack_tc(const Plan& P, const TcPlan& T, const float* weights, unsigned char* image, cudaStream_t st) {
-  pack_tc_kernel<<<T.n_steps, 256, 0, st>>>(P.d, T, weights, image);
+  pack_tc_kernel<<<dim3(T.n_steps, 8), 256, 0, st>>>(P.d, T, weights, image);
   return 0;
 }
 
@@ -1441,7 +1441,7 @@ int pmt_launch_reads_tc(const Plan& P, const float* weights, const PmtBatch* bat
   } else if (pmt_plan_tiles(batch, TILE, false, n_sm, tiles, nullptr, &n_claims, st)) {
     return 1;
   }
-  if (!reuse_images) pack_tc_kernel<<<T.n_steps, 256, 0, st>>>(P.d, T, weights, image);
+  if (!reuse_images) pack_tc_kernel<<<dim3(T.n_steps, 8), 256, 0, st>>>(P.d, T, weights, image);
   TcArgs A;
   A.wflat = weights; A.image = image; A.tiles = tiles; A.perm = perm; A.batch = *batch; A.out = *out;
   A.scratch = nullptr; A.tile_first = 0; A.tile_limit = 0x7fffffff;

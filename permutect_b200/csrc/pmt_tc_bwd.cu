@@ -676,7 +676,7 @@ __global__ void pack_tc_bwd_kernel(const __grid_constant__ PmtModelDesc D, const
   if (o.t_img_bytes == 0) return;
   const int Kp = o.N;                      // reduction length: output columns of the forward layer
   const int n_kb = (Kp + 31) / 32;
-  for (int idx = threadIdx.x; idx < n_kb * o.Nd * 32; idx += blockDim.x) {
+  for (int idx = blockIdx.y * blockDim.x + threadIdx.x; idx < n_kb * o.Nd * 32; idx += gridDim.y * blockDim.x) {
     const int kb = idx / (o.Nd * 32), rem = idx % (o.Nd * 32), n = rem / 32, kk = rem % 32;
     const int k = kb * 32 + kk;
     float v = 0.f;
@@ -909,7 +909,7 @@ int pmt_launch_reads_tc_backward(const Plan& P, const float* weights, const PmtB
   int n_claims = 0;
   if (pmt_plan_tiles(batch, BWD_MAXV, true, kMaxGrid, tiles, claims, &n_claims, st)) return 1;
   if (pmt_launch_pack_tc(P, T, weights, image_f, st)) return 1;
-  pack_tc_bwd_kernel<<<T.n_steps, 256, 0, st>>>(P.d, T, weights, image_t);
+  pack_tc_bwd_kernel<<<dim3(T.n_steps, 8), 256, 0, st>>>(P.d, T, weights, image_t);
 
   const long long rows = batch->n_rows > 0 ? batch->n_rows : 16LL * batch->n_variants;
   long long est_tiles = rows / 100 + n_claims;
