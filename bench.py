@@ -607,7 +607,12 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_cores = None
     if world > 1:
+        # one process per GPU: stay on the socket the GPU hangs off, so the pinned host batches of the e2e leg do not cross
+        # the inter-socket link (at N = 1 the process keeps every core: the CPU baseline runs in it)
+        from permutect_b200.training.distributed import bind_to_gpu_numa_node
+        numa_cores = bind_to_gpu_numa_node(local_rank)
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -772,6 +777,7 @@ def main():
         "clocks": clocks, "gpu_launches": fwd_launches * args.steps if fwd_launches is not None else None,
         "gpu_launches_per_step": fwd_launches, "gpu_launches_how": "library kernels of one step counted from a CUPTI trace outside the timed region",
         "e2e": {"value": e2e_value, "unit": "variants/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_seen[0],
+                "host_cores_bound": len(numa_cores) if numa_cores else None,
                 "call": "tools.filter_variants.generate_posterior_arrays over pinned host batches (prefetch_generator H2D on a side "
                         "stream, compute_batch_output, pmt_pack_posterior, posterior records D2H into pinned host arrays)"},
         "roofline": roofline,

@@ -110,3 +110,24 @@ def gather_variant_outputs(local: torch.Tensor, n_total: int, group=None) -> Opt
     chunks = [torch.empty_like(padded) for _ in sizes]
     dist.all_gather(chunks, padded, group=group)
     return torch.cat([c[:s] for c, s in zip(chunks, sizes)])
+
+
+def bind_to_gpu_numa_node(local_rank: int) -> Optional[List[int]]:
+    """Pins the calling process to the CPU cores NVML reports as local to GPU ``local_rank`` (one process per GPU: pinned
+    host buffers are then allocated on, and the H2D / D2H copies of the ingest pipeline stay on, the socket the GPU hangs
+    off instead of crossing the inter-socket link).  Returns the core list, or None when NVML / affinity is unavailable."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (n_cpu + 63) // 64)
+        cores = [64 * w + b for w, mask in enumerate(words) for b in range(64) if (int(mask) >> b) & 1 and 64 * w + b < n_cpu]
+        allowed = sorted(set(cores) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return None
