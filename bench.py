@@ -7,11 +7,12 @@ A step is one pass of the fused forward (compute_batch_output: every BatchOutput
 shard of synthetic WGS-shaped variants (10M variants sharded by variant
 over 8 GPUs -> 1.25M variants per GPU; weak scaling, per-GPU shard fixed).  `value` is measured with
 the shard resident in HBM; `e2e` goes through the public API with pinned HOST buffers, H2D of the
-compressed shard and D2H of the logits inside the timed region.  `train` (when the backward kernels
+compressed shard and D2H of the posterior records (int16 record + fp16-rounded logit + embedding, 180 B per variant)
+inside the timed region.  `train` (when the backward kernels
 are built) is one forward + losses + backward + clip + AdamW step per batch.
 
-`--impl reference` times the CPU restatement of the reference (oracle/, kind "port": the Python
-reference cannot travel to the GPU box) on the host cores, on a bounded sample of the same workload.
+`--impl reference` times the UNMODIFIED reference (oracle/_ref, kind "reference"; the oracle port only when the
+recipe oracle/build_ref.py has not been run) on the host cores, on a bounded sample of the same workload.
 """
 import argparse
 import json
@@ -674,23 +675,24 @@ def main():
     from permutect_b200.tools.filter_variants import generate_posterior_arrays
     d2h_seen = [0]
 
-    def e2e_pass():
+    def e2e_passes(k):
         # the call filter_variants makes (tools/filter_variants.py:generate_posterior_arrays): per batch the posterior records
-        # (int16 row + fp16-rounded logit + embedding, fp32) come back to host memory
+        # (int16 row + fp16-rounded logit + embedding, fp32) come back to host memory.  ONE call over a loader that delivers
+        # the shard k times, as the tool makes one call over its whole dataset: the pipeline's fill (first H2D) and drain
+        # (last D2H) are inside the timed region once, not once per step.
+        loader = (b for _ in range(k) for b in host_batches)
         n = 0
-        for int_rec, float_rec in generate_posterior_arrays(host_batches, model, dev):
+        for int_rec, float_rec in generate_posterior_arrays(loader, model, dev):
             n += int_rec.nbytes + float_rec.nbytes
-        d2h_seen[0] = n
+        d2h_seen[0] = n // k
 
     with torch.inference_mode():
-        for _ in range(2):
-            e2e_pass()
+        e2e_passes(2)
         barrier()
         sampler2 = ClockSampler(local_rank)
         sampler2.start()
         ev0.record()
-        for _ in range(args.steps):
-            e2e_pass()
+        e2e_passes(args.steps)
         ev1.record()
         barrier()
         e2e_ms = ev0.elapsed_time(ev1) / args.steps
@@ -778,7 +780,8 @@ def main():
         "gpu_launches_per_step": fwd_launches, "gpu_launches_how": "library kernels of one step counted from a CUPTI trace outside the timed region",
         "e2e": {"value": e2e_value, "unit": "variants/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_seen[0],
                 "host_cores_bound": len(numa_cores) if numa_cores else None,
-                "call": "tools.filter_variants.generate_posterior_arrays over pinned host batches (prefetch_generator H2D on a side "
+                "passes_per_call": args.steps,
+                "call": "one call of tools.filter_variants.generate_posterior_arrays over pinned host batches (prefetch_generator H2D on a side "
                         "stream, compute_batch_output, pmt_pack_posterior, posterior records D2H into pinned host arrays)"},
         "roofline": roofline,
     }

@@ -65,3 +65,15 @@ def test_gradient_allreduce_two_ranks_gloo():
     results = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), results), nprocs=world, join=True)
     assert dict(results) == {0: True, 1: True}
+
+
+def test_numa_binding_helper_is_harmless_without_a_gpu():
+    """bind_to_gpu_numa_node: the core list NVML reports for the GPU, or None (no NVML / no such GPU) -- never an exception,
+    and the process keeps a non-empty affinity mask."""
+    import os
+    from permutect_b200.training.distributed import bind_to_gpu_numa_node
+    before = os.sched_getaffinity(0)
+    cores = bind_to_gpu_numa_node(0)
+    assert cores is None or (len(cores) > 0 and set(cores) <= before)
+    assert len(os.sched_getaffinity(0)) > 0
+    os.sched_setaffinity(0, before)
