@@ -961,87 +961,101 @@ __global__ void plan_tiles_kernel(const long long* __restrict__ ref_off, const l
 __global__ void __launch_bounds__(128) plan_tiles_packed_kernel(const long long* __restrict__ ref_off, const long long* __restrict__ alt_off,
                                                                 int B, int claim_variants, int* __restrict__ tiles, int* __restrict__ perm) {
   __shared__ unsigned short s_order[4][PLAN_CLAIM], s_perm[4][PLAN_CLAIM];
-  __shared__ unsigned char s_r[4][PLAN_CLAIM], s_a[4][PLAN_CLAIM];
-  __shared__ int s_next[4][TILE + 1], s_end[4][TILE + 1];
-  __shared__ unsigned s_mask[4][5];
+  __shared__ unsigned short s_ra[4][PLAN_CLAIM];          // ref rows | alt rows << 8 of a claim's variant
+  __shared__ int s_bucket[4][TILE + 1];                   // per set size: position of its next unused entry in s_order << 16 | entries left
   __shared__ int s_tiles[4][2 * PLAN_CLAIM];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int claim = blockIdx.x * 4 + w;
   const long long c0 = (long long)claim * claim_variants;
   if (c0 >= B) return;
   const int n = (int)min((long long)claim_variants, (long long)B - c0);
-  for (int i = lane; i <= TILE; i += 32) { s_next[w][i] = 0; s_end[w][i] = 0; }
-  if (lane < 5) s_mask[w][lane] = 0u;
+  unsigned short* order = s_order[w];
+  unsigned short* ra = s_ra[w];
+  int* bucket = s_bucket[w];
+  int* fill = s_tiles[w];   // scratch of the counting sort (the tile list is written later)
+  for (int i = lane; i <= TILE; i += 32) { bucket[i] = 0; fill[i] = 0; }
   __syncwarp();
   // sizes; a set that does not fit a tile by itself is left out (size 255: the long-set path takes it)
-  for (int i0 = 0; i0 < n; i0 += 32) {
-    const int i = i0 + lane;
+  int my_size[PLAN_CLAIM / 32];
+#pragma unroll
+  for (int k = 0; k < PLAN_CLAIM / 32; ++k) {
+    const int i = k * 32 + lane;
     int size = 255;
     if (i < n) {
       const long long nr = __ldg(ref_off + c0 + i + 1) - __ldg(ref_off + c0 + i), na = __ldg(alt_off + c0 + i + 1) - __ldg(alt_off + c0 + i);
-      if (((nr + 3) & ~3LL) + na <= TILE) { size = (int)(nr + na); s_r[w][i] = (unsigned char)nr; s_a[w][i] = (unsigned char)na; }
+      if (((nr + 3) & ~3LL) + na <= TILE) { size = (int)(nr + na); ra[i] = (unsigned short)(nr | (na << 8)); }
     }
-    if (size <= TILE) atomicAdd(&s_end[w][size], 1);
+    my_size[k] = size;
+    if (size <= TILE) atomicAdd(&bucket[size], 1);
   }
   __syncwarp();
-  if (lane == 0) {   // bucket ranges: [s_next, s_end)
-    int run = 0;
-    for (int sz = 0; sz <= TILE; ++sz) {
-      const int c = s_end[w][sz];
-      s_next[w][sz] = run; run += c; s_end[w][sz] = run;
-      if (c > 0) s_mask[w][sz >> 5] |= 1u << (sz & 31);
+  // bucket ranges (warp scan over the 129 sizes) and the masks of the non-empty sizes: lo = sizes 0..63, hi = 64..127
+  unsigned long long lo = 0, hi = 0;
+  int has128 = 0, total = 0;
+  {
+    int carry = 0;
+    for (int s0 = 0; s0 <= TILE; s0 += 32) {
+      const int sz = s0 + lane;
+      const int c = sz <= TILE ? bucket[sz] : 0;
+      int inc = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+      if (sz <= TILE) bucket[sz] = ((carry + inc - c) << 16) | c;
+      const unsigned nz = __ballot_sync(0xffffffffu, c > 0);
+      if (s0 == 0) lo |= nz; else if (s0 == 32) lo |= (unsigned long long)nz << 32; else if (s0 == 64) hi |= nz;
+      else if (s0 == 96) hi |= (unsigned long long)nz << 32; else has128 = nz & 1;
+      carry += __shfl_sync(0xffffffffu, inc, 31);
     }
+    total = carry;
   }
   __syncwarp();
   // scatter in batch order (the rank inside a bucket is the variant's rank among the variants of its size)
-  {
-    int* fill = s_tiles[w];   // running fill of every bucket (the tile list is written later)
-    for (int i = lane; i <= TILE; i += 32) fill[i] = 0;
+#pragma unroll
+  for (int k = 0; k < PLAN_CLAIM / 32; ++k) {
+    const int size = my_size[k];
+    const unsigned peers = __match_any_sync(0xffffffffu, size);
+    const int rank = __popc(peers & ((1u << lane) - 1u));
+    if (size <= TILE) order[(bucket[size] >> 16) + fill[size] + rank] = (unsigned short)(k * 32 + lane);
     __syncwarp();
-    for (int i0 = 0; i0 < n; i0 += 32) {
-      const int i = i0 + lane;
-      int size = 255;
-      if (i < n) {
-        const long long nr = __ldg(ref_off + c0 + i + 1) - __ldg(ref_off + c0 + i), na = __ldg(alt_off + c0 + i + 1) - __ldg(alt_off + c0 + i);
-        if (((nr + 3) & ~3LL) + na <= TILE) size = (int)(nr + na);
-      }
-      const unsigned peers = __match_any_sync(0xffffffffu, size);
-      const int rank = __popc(peers & ((1u << lane) - 1u));
-      if (size <= TILE) {
-        s_order[w][s_next[w][size] + fill[size] + rank] = (unsigned short)i;
-      }
-      __syncwarp();
-      if (size <= TILE && rank == 0) fill[size] += __popc(peers);
-      __syncwarp();
-    }
+    if (size <= TILE && rank == 0) fill[size] += __popc(peers);
+    __syncwarp();
   }
-  __syncwarp();
   int n_tiles = 0, placed = 0;
   if (lane == 0) {
-    int remaining = s_end[w][TILE];
+    int remaining = total;
     while (remaining > 0) {
       int nr = 0, na = 0, nv = 0;
       const int p0 = placed;
       int limit = TILE;
-      while (limit >= 0 && nv < TILE) {
+      while (nv < TILE) {
         // largest non-empty size <= min(limit, free rows)
         int cap = TILE - (nr + na);
         if (cap > limit) cap = limit;
+        if (cap < 0) break;
         int sz = -1;
-        for (int wd = cap >> 5; wd >= 0; --wd) {
-          unsigned m = s_mask[w][wd];
-          if (wd == (cap >> 5)) m &= 0xFFFFFFFFu >> (31 - (cap & 31));
-          if (m) { sz = 32 * wd + 31 - __clz(m); break; }
+        if (cap >= TILE && has128) sz = TILE;
+        else {
+          const int ch = min(cap, 127) - 64;
+          const unsigned long long h = ch >= 0 ? hi & (~0ull >> (63 - ch)) : 0ull;
+          if (h) sz = 127 - __clzll((long long)h);
+          else {
+            const unsigned long long l = lo & (~0ull >> (63 - min(cap, 63)));
+            if (l) sz = 63 - __clzll((long long)l);
+          }
         }
         if (sz < 0) break;
-        const int pos = s_next[w][sz];
-        const int id = s_order[w][pos];
-        const int r = s_r[w][id], a = s_a[w][id];
+        const int pc = bucket[sz];
+        const int id = order[pc >> 16];
+        const int rv = ra[id], r = rv & 255, a = rv >> 8;
         if (((nr + r + 3) & ~3) + na + a <= TILE) {
           s_perm[w][placed++] = (unsigned short)id;
           nr += r; na += a; ++nv; --remaining;
-          s_next[w][sz] = pos + 1;
-          if (pos + 1 == s_end[w][sz]) s_mask[w][sz >> 5] &= ~(1u << (sz & 31));
+          bucket[sz] = pc + 65535;          // position + 1, entries left - 1
+          if ((pc & 0xFFFF) == 1) {         // that was the last one of its size
+            if (sz == TILE) has128 = 0;
+            else if (sz >= 64) hi &= ~(1ull << (sz - 64));
+            else lo &= ~(1ull << sz);
+          }
           limit = TILE;
         } else {
           limit = sz - 1;   // the padding of the ref rows made it too long: try the next smaller size
