@@ -205,3 +205,28 @@ def test_long_sets_on_the_tensor_cores_are_bitwise_reproducible():
     _, b = _long_forward(raw, "tf32x3")
     for name in ("logits_b", "logits_bk", "features_be", "ref_features_be"):
         assert torch.equal(getattr(a, name), getattr(b, name)), name
+
+
+def test_packed_tile_planner_changes_nothing_but_the_tile_count(monkeypatch):
+    """Inference batches of >= 2 M reads are tiled by plan_tiles_packed_kernel (best fit through a permutation of the
+    variants) instead of in batch order.  There is no arithmetic across the read sets of a tile, so every output must be
+    BITWISE what the sequential planner gives (PMT_TC_PACKED=0), including variants longer than a tile left to the long-set
+    path and a last claim that is not full."""
+    import bench
+    from permutect_b200.data.batch import Batch
+    from permutect_b200.synthetic import make_wgs_arrays
+    dev = torch.device("cuda:0")
+    model = bench.make_model(dev)
+    L.set_precision("tf32x3")
+    ia, fa, reads = make_wgs_arrays(140_123, seed=77)
+    batch = Batch.from_arrays(ia, fa, reads).copy_to(dev)
+    assert batch.reads.shape[0] >= 2_000_000
+    with torch.inference_mode():
+        monkeypatch.setenv("PMT_TC_PACKED", "0")
+        want = model.compute_batch_output(batch)
+        want = {k: getattr(want, k).clone() for k in ("logits_b", "logits_bk", "features_be", "ref_features_be", "outlier_binary_logits")}
+        monkeypatch.delenv("PMT_TC_PACKED")
+        got = model.compute_batch_output(batch)
+    for k, w in want.items():
+        assert torch.equal(getattr(got, k), w), k
+    L.set_precision("fp32")
