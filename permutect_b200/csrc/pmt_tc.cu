@@ -1044,19 +1044,39 @@ __global__ void __launch_bounds__(128) plan_tiles_packed_kernel(const long long*
           }
         }
         if (sz < 0) break;
-        const int pc = bucket[sz];
-        const int id = order[pc >> 16];
-        const int rv = ra[id], r = rv & 255, a = rv >> 8;
-        if (((nr + r + 3) & ~3) + na + a <= TILE) {
-          s_perm[w][placed++] = (unsigned short)id;
-          nr += r; na += a; ++nv; --remaining;
-          bucket[sz] = pc + 65535;          // position + 1, entries left - 1
-          if ((pc & 0xFFFF) == 1) {         // that was the last one of its size
+        // Best fit keeps taking this size while it fits (no larger size can start to fit as the space shrinks), so up to
+        // GROUP of its entries are read at once -- independent loads instead of one dependent chain per set
+        constexpr int GROUP = 6;
+        const int pc = bucket[sz], pos = pc >> 16, cnt = pc & 0xFFFF;
+        int want = sz > 0 ? cap / sz : GROUP;
+        if (want > cnt) want = cnt;
+        if (want > TILE - nv) want = TILE - nv;
+        if (want > GROUP) want = GROUP;
+        int ids[GROUP], rvs[GROUP];
+#pragma unroll
+        for (int j = 0; j < GROUP; ++j) ids[j] = j < want ? order[pos + j] : 0;
+#pragma unroll
+        for (int j = 0; j < GROUP; ++j) rvs[j] = j < want ? ra[ids[j]] : 0;
+        int took = 0;
+#pragma unroll
+        for (int j = 0; j < GROUP; ++j) {
+          if (j < want && took == j) {
+            const int r = rvs[j] & 255, a = rvs[j] >> 8;
+            if (((nr + r + 3) & ~3) + na + a <= TILE) {
+              s_perm[w][placed + j] = (unsigned short)ids[j];
+              nr += r; na += a; took = j + 1;
+            }
+          }
+        }
+        if (took > 0) {
+          placed += took; nv += took; remaining -= took;
+          bucket[sz] = pc + took * 65535;   // position + took, entries left - took
+          if (cnt == took) {                // the size is used up
             if (sz == TILE) has128 = 0;
             else if (sz >= 64) hi &= ~(1ull << (sz - 64));
             else lo &= ~(1ull << sz);
           }
-          limit = TILE;
+          limit = took == want ? TILE : sz - 1;   // stopped early: the next one of this size did not fit (padding) -> smaller sizes
         } else {
           limit = sz - 1;   // the padding of the ref rows made it too long: try the next smaller size
         }
