@@ -275,3 +275,49 @@ def load_model(path, device: Optional[torch.device] = None):
     model.load_state_dict(saved[constants.STATE_DICT_NAME])
     model.to(model._dtype)
     return model, saved[constants.ARTIFACT_LOG_PRIORS_NAME], saved[constants.ARTIFACT_SPECTRA_STATE_DICT_NAME]
+
+
+class EmbeddingRecords:
+    """The collector ``record_embeddings`` fills: the attributes of the reference's ``EmbeddingMetrics``
+    (metrics/evaluation_metrics.py:282-289) without its TensorBoard / UMAP output, which is out of scope here.  Pass the
+    reference's class instead (``metrics_factory=EmbeddingMetrics``) to get its projector output."""
+
+    def __init__(self):
+        self.label_metadata, self.correct_metadata, self.type_metadata, self.truncated_count_metadata = [], [], [], []
+        self.features, self.ref_features = [], []
+
+    def output_to_summary_writer(self, summary_writer, prefix: str = "", **kwargs):
+        if summary_writer is not None and hasattr(summary_writer, "add_embedding") and self.features:
+            meta = list(zip(self.label_metadata, self.correct_metadata, self.type_metadata, self.truncated_count_metadata))
+            summary_writer.add_embedding(torch.vstack(self.features), metadata=meta,
+                                         metadata_header=["Labels", "Correctness", "Types", "Counts"], tag=prefix + "embedding")
+
+
+@torch.no_grad()
+def record_embeddings(model: ArtifactModel, loader, summary_writer=None, metrics_factory=EmbeddingRecords):
+    """artifact_model.py:372-408: after training, the per-variant embeddings (alt / ref set means of the final features,
+    and the haplotype-CNN embedding) with their label / type / alt-count metadata.  One fused forward per batch
+    (``calculate_features``); the metadata columns are read from the batch once instead of element by element.  Returns
+    the two collectors (the reference returns nothing and writes them to the summary writer; both happen here)."""
+    from permutect_b200.data.count_binning import alt_count_bin_index, alt_count_bin_name
+    from permutect_b200.data.prefetch_generator import prefetch_generator
+    from permutect_b200.utils.enums import Variation
+    embedding_metrics, ref_alt_seq_metrics = metrics_factory(), metrics_factory()
+    for batch in prefetch_generator(loader, model._device):
+        ref_bre, alt_bre, seq_be = model.calculate_features(batch, weight_range=model._params.reweighting_range)
+        alt_means_be, ref_means_be, seq_be = alt_bre.means_over_sets().cpu(), ref_bre.means_over_sets().cpu(), seq_be.cpu()
+        labels_b, labeled_b = batch.get_training_labels().tolist(), batch.get_is_labeled_mask().tolist()
+        labels = [("artifact" if lab > 0.5 else "non-artifact") if isl > 0.5 else "unlabeled" for lab, isl in zip(labels_b, labeled_b)]
+        types = [Variation(idx).name for idx in batch.get(Data.VARIANT_TYPE).tolist()]
+        counts = [alt_count_bin_name(alt_count_bin_index(ac)) for ac in batch.get(Data.ALT_COUNT).tolist()]
+        for metrics, embeddings, ref_features in ((embedding_metrics, alt_means_be, ref_means_be), (ref_alt_seq_metrics, seq_be, None)):
+            metrics.label_metadata.extend(labels)
+            metrics.correct_metadata.extend(["unknown"] * batch.size())
+            metrics.type_metadata.extend(types)
+            metrics.truncated_count_metadata.extend(counts)
+            metrics.features.append(embeddings)
+            if ref_features is not None:
+                metrics.ref_features.append(ref_features)
+    embedding_metrics.output_to_summary_writer(summary_writer)
+    ref_alt_seq_metrics.output_to_summary_writer(summary_writer, prefix="ref and alt allele context")
+    return embedding_metrics, ref_alt_seq_metrics

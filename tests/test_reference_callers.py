@@ -231,3 +231,49 @@ def test_reference_generate_posterior_data_on_the_drop_in():
     assert (got_int[:, :2] == 0).all()                                                            # counts zeroed
     logits = got_float[:, rd.Data.CACHED_ARTIFACT_LOGIT.idx]
     assert np.array_equal(logits, logits.astype(np.float16).astype(np.float32))                   # fp16-rounded (quirk Q6)
+
+
+@pytest.mark.gpu
+def test_record_embeddings_reference_loop_and_drop_in_agree():
+    """artifact_model.py:372-408: the REFERENCE's record_embeddings (its loop, its prefetch_generator, its EmbeddingMetrics
+    with the TensorBoard output stubbed) run on this package's model collects the same embeddings and metadata as this
+    package's record_embeddings; the embeddings are the set means compute_batch_output reports."""
+    rb, rd = _ref()
+    import permutect.architecture.artifact_model as ram
+    import permutect.metrics.evaluation_metrics as rem
+
+    import bench
+    from permutect_b200.architecture.artifact_model import record_embeddings
+    from permutect_b200.utils.enums import Epoch
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    model = bench.make_model(dev)
+    model.set_epoch_type(Epoch.VALID)
+    batches = _batches(3, 80, seed0=91)
+
+    collected = []
+
+    class _Metrics(rem.EmbeddingMetrics):
+        def output_to_summary_writer(self, summary_writer, prefix="", **kwargs):
+            collected.append(self)
+
+    class _Loader(list):
+        pass
+
+    orig = ram.EmbeddingMetrics
+    ram.EmbeddingMetrics = _Metrics
+    try:
+        ram.record_embeddings(model, _Loader(batches), summary_writer=None)
+    finally:
+        ram.EmbeddingMetrics = orig
+    mine = record_embeddings(model, batches, summary_writer=None)
+    assert len(collected) == 2
+    with torch.inference_mode():
+        want_alt = torch.vstack([model.compute_batch_output(b.copy_to(dev)).features_be.cpu() for b in batches])
+    for theirs, ours in zip(collected, mine):
+        for name in ("label_metadata", "correct_metadata", "type_metadata", "truncated_count_metadata"):
+            assert getattr(theirs, name) == getattr(ours, name), name
+        assert torch.equal(torch.vstack(theirs.features), torch.vstack(ours.features))
+        assert len(theirs.ref_features) == len(ours.ref_features)
+    assert torch.equal(torch.vstack(mine[0].features), want_alt)
+    assert len(mine[0].label_metadata) == 240 and set(mine[0].label_metadata) <= {"artifact", "non-artifact", "unlabeled"}
