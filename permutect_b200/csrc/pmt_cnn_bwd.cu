@@ -491,7 +491,7 @@ static bool build_bwd_plan(const pmt::Plan& P, const cnntc::Plan& T, BPlan* out)
   return false;
 }
 
-static const int kCnnBwdChunk = 16384;   // variants per recompute + backward pair: the saved activations stay L2-sized
+static const int kCnnBwdChunk = 65536;   // variants per recompute + backward pair: bounds the saved activations (5.3 KB per variant)
 
 bool pmt_cnn_bwd_mma_supported(const pmt::Plan& P) {
   cnntc::Plan T;

@@ -22,6 +22,7 @@
 //   reduced with warp shuffles into per-warp slots of the same private buffer.
 // TMEM per slot (256 columns): G = dL/d(residual stream) (64), D = data-gradient accumulator (64), dY operand (64),
 // dW accumulator (64).  Arithmetic: TF32 operands rounded to nearest, fp32 accumulation.
+#include <cstdlib>
 #include <cstring>
 
 #include "pmt_tc.cuh"
@@ -840,7 +841,10 @@ using namespace pmt::tc;
 size_t pmt_plan_claim_bytes(int n_variants, int n_sm);
 
 static const int kMaxGrid = 148;
-static const int kChunkTiles = 2048;   // tiles per recompute / backward pass: bounds the operand scratch
+// Tiles per recompute / backward pass: bounds the operand scratch (0.7 MB per tile: 5.9 GB).  The scratch is streamed through
+// HBM either way (it never was L2-sized), so fewer, longer passes only save launches -- the tile bound is an upper bound and most
+// passes beyond the first found nothing to do -- and the partly filled last round of every pass.
+static const int kChunkTiles = 8192;
 
 static long long tile_bound(const PmtBatch* batch, int n_claims) {
   const long long rows = batch->n_rows > 0 ? batch->n_rows : 16LL * batch->n_variants;
@@ -872,7 +876,9 @@ static BwdLayout bwd_layout(const TcPlan& T, const PmtBatch* batch, int n_sm) {
   if (cv > PLAN_CLAIM) cv = PLAN_CLAIM;
   L.n_claims = B > 0 ? (B + cv - 1) / cv : 0;
   const long long bound = batch ? tile_bound(batch, L.n_claims) : 1;
-  L.chunk_tiles = (int)(bound < kChunkTiles ? bound : kChunkTiles);
+  int chunk_cap = kChunkTiles;
+  if (const char* e = getenv("PMT_BWD_CHUNK_TILES")) { const int v = atoi(e); if (v >= 1) chunk_cap = v; }   // tests: several passes on a small batch
+  L.chunk_tiles = (int)(bound < chunk_cap ? bound : chunk_cap);
   L.n_chunks = (int)((bound + L.chunk_tiles - 1) / L.chunk_tiles);
   L.scratch = off; off += (size_t)L.chunk_tiles * T.tile_bytes;
   L.total = off + 1024;

@@ -71,9 +71,11 @@ def test_tensor_core_gradients_are_bitwise_reproducible():
         np.testing.assert_array_equal(a[k], b[k], err_msg=k)
 
 
-def test_large_batch_several_recompute_ranges_against_fp32_kernels():
+def test_large_batch_several_recompute_ranges_against_fp32_kernels(monkeypatch):
     """40 000 WGS-shaped variants: more tiles than one recompute range holds (the backward walks the tile list in bounded
-    ranges), every slot of every CTA busy; compared with the FP32 kernels, which the reference pins."""
+    ranges -- 8 192 tiles by default, cut to 1 024 here so that this batch takes six of them), every slot of every CTA busy;
+    compared with the FP32 kernels, which the reference pins."""
+    monkeypatch.setenv("PMT_BWD_CHUNK_TILES", "1024")
     import bench
     from permutect_b200.data.batch import Batch
     from permutect_b200.synthetic import make_wgs_arrays
