@@ -180,6 +180,11 @@ int pmt_backward(const PmtModelDesc* desc, const float* weights, const PmtBatch*
 #define PMT_PRECISION_TF32 2
 int pmt_set_precision(int mode);
 int pmt_get_precision(void);
+/* Which kernels the backward of this model runs in the CURRENT precision mode: *reads_tc = 1 when the read path's backward
+ * is the tcgen05 kernel (pmt_tc_bwd.cu), *cnn_tc = 1 when the haplotype CNN's is the tensor-core kernel (pmt_cnn_bwd.cu);
+ * 0 = the FP32 SIMT kernel (FP32 mode, or a shape outside the tensor-core kernel's envelope).  Returns non-zero on a bad
+ * descriptor. */
+int pmt_backward_kernels(const PmtModelDesc* desc, int32_t* reads_tc, int32_t* cnn_tc);
 
 /* Measurement hook (no reference counterpart): when both are non-NULL, the next pmt_forward /
  * pmt_backward calls of this process record these cudaEvent_t around their dominant kernel

@@ -1302,6 +1302,16 @@ size_t pmt_backward_workspace_bytes(const Plan& P, const PmtBatch* batch) {
   return bytes;
 }
 
+extern "C" int pmt_backward_kernels(const PmtModelDesc* desc, int32_t* reads_tc, int32_t* cnn_tc) {
+  Plan P;
+  if (pmt_build_plan(desc, &P)) return 1;
+  const bool tc_mode = pmt_precision_mode() != PMT_PRECISION_FP32;
+  const char* cnn_env = getenv("PMT_CNN_BWD_SIMT");
+  if (reads_tc) *reads_tc = tc_mode && pmt_tc_supported(P) ? 1 : 0;
+  if (cnn_tc) *cnn_tc = tc_mode && pmt_cnn_bwd_mma_supported(P) && !(cnn_env && atoi(cnn_env) == 1) ? 1 : 0;
+  return 0;
+}
+
 extern "C" int pmt_backward(const PmtModelDesc* desc, const float* weights, const PmtBatch* batch, const PmtOutGrads* grads,
                             float* d_weights, void* workspace, size_t workspace_bytes, void* stream) {
   Plan P;

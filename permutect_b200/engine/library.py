@@ -93,7 +93,7 @@ class PmtLossGrads(C.Structure):
 
 
 EXPORTED_SYMBOLS = ["pmt_posterior_fit_step", "pmt_posterior_fit_workspace_size", "pmt_orthogonal_forward", "pmt_orthogonal_backward", "pmt_posterior_param_count", "pmt_posterior_log_posteriors", "pmt_dataset_read_indices", "pmt_pack_posterior", "pmt_adamw_step", "pmt_adamw_workspace_size", "pmt_losses_forward", "pmt_losses_backward", "pmt_losses_workspace_size", "pmt_set_cnn_trace", "pmt_set_reads_trace", "pmt_set_backward_trace", "pmt_last_error", "pmt_abi_version", "pmt_workspace_size", "pmt_forward", "pmt_forward_prepared", "pmt_backward",
-                    "pmt_decode_reads", "pmt_set_profile_events", "pmt_downsample_counts", "pmt_downsample_fill", "pmt_set_precision", "pmt_get_precision", "pmt_constraints_forward", "pmt_constraints_backward"]
+                    "pmt_decode_reads", "pmt_set_profile_events", "pmt_downsample_counts", "pmt_downsample_fill", "pmt_set_precision", "pmt_get_precision", "pmt_constraints_forward", "pmt_constraints_backward", "pmt_backward_kernels"]
 
 class PmtPosteriorDesc(C.Structure):
     _fields_ = [("n_components", C.c_int32), ("hap_start", C.c_int32), ("hap_len", C.c_int32), ("no_germline_mode", C.c_int32),
@@ -154,6 +154,8 @@ def load():
     lib.pmt_set_precision.restype = C.c_int
     lib.pmt_set_precision.argtypes = [C.c_int]
     lib.pmt_get_precision.restype = C.c_int
+    lib.pmt_backward_kernels.restype = C.c_int
+    lib.pmt_backward_kernels.argtypes = [C.POINTER(PmtModelDesc), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     lib.pmt_set_profile_events.restype = C.c_int
     lib.pmt_set_profile_events.argtypes = [C.c_void_p, C.c_void_p]
     lib.pmt_dataset_read_indices.restype = C.c_int
@@ -221,3 +223,10 @@ def set_precision(mode: str) -> None:
 def get_precision() -> str:
     code = load().pmt_get_precision()
     return {v: k for k, v in PRECISION_MODES.items()}[code]
+
+
+def backward_kernels(desc) -> dict:
+    """Which backward kernels the current precision mode runs for this model (pmt_backward_kernels)."""
+    reads, cnn = C.c_int32(0), C.c_int32(0)
+    check(load().pmt_backward_kernels(C.byref(desc), C.byref(reads), C.byref(cnn)))
+    return {"reads_tc": bool(reads.value), "cnn_tc": bool(cnn.value)}

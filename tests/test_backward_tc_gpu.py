@@ -119,3 +119,50 @@ def test_mixed_long_and_tile_sized_sets():
            for n, p in model.named_parameters()}
     bad = _violations(got, {k: v.numpy() for k, v in want.items()})
     assert not bad, "gradient error too large:\n" + "\n".join(f"{e:.3e} {n}" for e, n in bad[:25])
+
+
+@pytest.mark.parametrize("layers", [
+    # 16 channels, kernel sizes 3 / 5 / 3 / 3, the flatten keeps two positions (the Linear is a convolution of length 2)
+    ['convolution/kernel_size=3/out_channels=16', 'selu', 'pool/kernel_size=2/stride=1',
+     'convolution/kernel_size=5/out_channels=16', 'selu', 'pool/kernel_size=1',
+     'convolution/kernel_size=3/out_channels=24', 'selu', 'pool/kernel_size=2',
+     'convolution/kernel_size=3/out_channels=8', 'selu', 'pool/kernel_size=2',
+     'flatten', 'linear/out_features=10'],
+    # no pooling after the first convolution, one pooled layer, a SELU-free last convolution
+    ['convolution/kernel_size=4/out_channels=32', 'selu',
+     'convolution/kernel_size=3/out_channels=32', 'selu', 'pool/kernel_size=2',
+     'convolution/kernel_size=2/out_channels=12',
+     'flatten', 'linear/out_features=10'],
+])
+def test_haplotype_cnn_backward_other_shapes_against_the_oracle(layers):
+    """cnn_backward_mma_kernel (pmt_cnn_bwd.cu) is driven by the layer program, not by the v0.4.0 shapes: other channel
+    counts, kernel sizes, pool placements and a flatten that keeps more than one position, against the oracle's autograd."""
+    import bench
+    from helpers import batch_from_raw, params_from_hp
+    from oracle import artifact_oracle as orc
+    from permutect_b200.architecture.artifact_model import ArtifactModel
+    from permutect_b200.synthetic import make_wgs_arrays
+    hp = dict(bench.V040, ref_seq_layer_strings=layers, source_adversarial_strength=0.0)
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    model = ArtifactModel(params_from_hp(hp), 61, 71, 42, device=dev)
+    gen = torch.Generator().manual_seed(5)
+    with torch.no_grad():
+        for _, p in model.named_parameters():
+            if p.dim() == 0:
+                p.copy_(0.05 + 0.1 * torch.rand((), generator=gen))
+    model.set_epoch_type(Epoch.TRAIN)
+    assert L.backward_kernels(model.descriptor()) == {"reads_tc": True, "cnn_tc": True}     # not the SIMT fall-back
+    ia, fa, reads = make_wgs_arrays(203, seed=31)
+    raw = bench.oracle_inputs(ia, fa, reads)
+    batch = batch_from_raw(raw, dev)
+    model.compute_batch_losses(model.compute_batch_output(batch), batch).total_loss.backward()
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    names = [n for n, _ in model.named_parameters()]
+    _, _, want = orc.loss_and_grads(sd, hp, raw, names)
+    got = {n: (p.grad.detach().cpu().numpy() if p.grad is not None else np.zeros(tuple(p.shape), np.float32))
+           for n, p in model.named_parameters()}
+    bad = _violations(got, {k: v.numpy() for k, v in want.items()})
+    assert not bad, "gradient error too large:\n" + "\n".join(f"{e:.3e} {n}" for e, n in bad[:25])
+    cnn = [n for n in names if n.startswith("haplotypes_cnn")]
+    assert cnn and all(np.abs(got[n]).max() > 0 for n in cnn)
