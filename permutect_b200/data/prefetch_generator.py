@@ -90,6 +90,7 @@ def _pipeline(dataloader: Iterable[Batch], device, depth: int, holder: "_Ring") 
                 dst.copy_(getattr(batch_cpu, name), non_blocking=True)
             done = torch.cuda.Event()
             done.record(copy_stream)
+        batch_cpu._h2d_done = done          # a host-side staging ring (reads_dataset.MemoryMappedBatches) reuses the buffers after this
         batch_gpu = copy.copy(batch_cpu)
         for name, dst in views.items():
             setattr(batch_gpu, name, dst)

@@ -17,19 +17,83 @@ from permutect_b200.data.batch import Batch, BatchIndexedTensor, BatchProperty
 from permutect_b200.data.datum import Data, Datum, HAPLOTYPES_START_IDX, INFO_START_IDX, num_read_features
 
 
+class _StagingSlot:
+    """Persistent pinned host buffers of one in-flight batch (int / float / reads), grown on demand."""
+
+    def __init__(self):
+        self.buffers = {}
+        self.last_batch = None      # the Batch last built over these buffers (its H2D event tells when they are free again)
+
+    def view(self, name: str, like: np.ndarray) -> np.ndarray:
+        buf = self.buffers.get(name)
+        nbytes = like.size * like.dtype.itemsize
+        if buf is None or buf.numel() < nbytes:
+            buf = self.buffers[name] = torch.empty(int(nbytes * 1.1) + 4096, dtype=torch.uint8, pin_memory=True)
+        return buf[:nbytes].numpy().view(like.dtype).reshape(like.shape)
+
+
+def _register_host_array(arr) -> bool:
+    """Page-locks the memory of a host array in place (cudaHostRegister) so that batches cut from it are DMA-able views: no
+    staging copy at all.  Works for arrays that live in anonymous memory (a dataset loaded into RAM); a file-backed map is
+    usually refused by the driver -- the caller then falls back to the staging ring.  The registration lasts as long as the
+    process (the arrays of a dataset are opened once)."""
+    if not isinstance(arr, np.ndarray) or not arr.flags["C_CONTIGUOUS"] or arr.nbytes == 0:
+        return False
+    try:
+        if torch.from_numpy(arr[:1]).is_pinned():
+            return True
+        rc = torch.cuda.cudart().cudaHostRegister(arr.ctypes.data, arr.nbytes, 0)
+        return int(rc) == 0 and torch.from_numpy(arr[:1]).is_pinned()
+    except Exception:
+        return False
+
+
+def _parallel_copy(pool, dst: np.ndarray, src: np.ndarray, n_parts: int):
+    """dst[:] = src in row ranges handed to the pool (numpy releases the GIL inside the copy loop, so the ranges are copied
+    by different cores: one core moves ~8 GB/s out of the page cache, an ingest pipeline needs a multiple of that)."""
+    n = len(src)
+    if n_parts <= 1 or n < 4096:
+        np.copyto(dst, src)
+        return []
+    step = (n + n_parts - 1) // n_parts
+    return [pool.submit(np.copyto, dst[a:a + step], src[a:a + step]) for a in range(0, n, step)]
+
+
 class MemoryMappedBatches:
     """Iterable of ``Batch`` over consecutive variants of (int_mmap [N, 16+2L] int16, float_mmap [N, 6+I] fp16,
     reads_mmap [R, row_bytes] uint8).  ``num_data`` / ``num_reads`` bound the valid prefix of the maps, as in the
     reference (the files may be larger than the data, memory_mapped_data.py:45-47).  ``start`` / ``stop`` select a variant
-    range (the contiguous shard of one rank or worker, reads_dataset.py:141-142)."""
+    range (the contiguous shard of one rank or worker, reads_dataset.py:141-142).
+
+    ``staging_threads > 0`` (with ``pin_memory``): a producer thread cuts the batches ``prefetch`` ahead of the consumer
+    and copies their three slices into a ring of persistent pinned buffers with that many copy threads -- what the
+    reference leaves to DataLoader worker processes (reads_dataset.py:223-232), without the per-Datum collate.  The ring
+    holds ``prefetch + 3`` batches: a batch's buffers are refilled once that many further batches have been cut AND the
+    host-to-device copy ``prefetch_generator`` made of it has finished (its event is waited for); a consumer that does not go
+    through ``prefetch_generator`` must be done with a batch before it has taken ``prefetch + 2`` more.
+
+    ``pin_memory="register"``: the three arrays are page-locked IN PLACE once (cudaHostRegister) and every batch is a
+    zero-copy view of them -- the host side of the ingest pipeline is then three slices per batch.  For arrays the driver
+    refuses to register (file-backed maps) this falls back to the staging ring (``staging_threads`` or 4 copy threads)."""
 
     def __init__(self, int_mmap, float_mmap, reads_mmap, batch_size: int, num_data: Optional[int] = None,
-                 start: int = 0, stop: Optional[int] = None, pin_memory: bool = True):
+                 start: int = 0, stop: Optional[int] = None, pin_memory: bool = True, staging_threads: int = 0, prefetch: int = 2):
         self.int_mmap, self.float_mmap, self.reads_mmap = int_mmap, float_mmap, reads_mmap
         self.num_data = len(int_mmap) if num_data is None else num_data
         self.batch_size = int(batch_size)
         self.start, self.stop = start, self.num_data if stop is None else min(stop, self.num_data)
-        self.pin_memory = pin_memory
+        self.staging_threads, self.prefetch = int(staging_threads), max(1, int(prefetch))
+        self._slots = None
+        self.registered = False
+        if pin_memory == "register":
+            arrays = [np.asarray(a) if not isinstance(a, np.memmap) else a for a in (int_mmap, float_mmap, reads_mmap)]
+            self.registered = all(_register_host_array(a) for a in arrays)
+            if self.registered:
+                self.int_mmap, self.float_mmap, self.reads_mmap = arrays
+            else:
+                self.staging_threads = self.staging_threads or 4
+            pin_memory = True
+        self.pin_memory = bool(pin_memory)
         counts = np.asarray(int_mmap[: self.num_data, : Data.ALT_COUNT.idx + 1]).astype(np.int64)
         # read_end_indices (memory_mapped_data.py:53-58) as one cumulative sum; [v] = first row of variant v
         self.read_start_indices = np.concatenate(([0], np.cumsum(counts[:, Data.REF_COUNT.idx] + counts[:, Data.ALT_COUNT.idx])))
@@ -37,13 +101,73 @@ class MemoryMappedBatches:
     def __len__(self) -> int:
         return (self.stop - self.start + self.batch_size - 1) // self.batch_size
 
-    def __iter__(self) -> Iterator[Batch]:
+    def _slices(self):
         for v0 in range(self.start, self.stop, self.batch_size):
             v1 = min(v0 + self.batch_size, self.stop)
             r0, r1 = int(self.read_start_indices[v0]), int(self.read_start_indices[v1])
-            batch = Batch.from_dataset_slice(np.asarray(self.int_mmap[v0:v1]), np.asarray(self.float_mmap[v0:v1]),
-                                             np.asarray(self.reads_mmap[r0:r1]))
+            yield self.int_mmap[v0:v1], self.float_mmap[v0:v1], self.reads_mmap[r0:r1]
+
+    def __iter__(self) -> Iterator[Batch]:
+        if self.registered:
+            for ints, floats, reads in self._slices():
+                yield Batch.from_dataset_slice(ints, floats, reads)      # views of page-locked memory
+            return
+        if self.pin_memory and self.staging_threads > 0:
+            yield from self._staged()
+            return
+        for ints, floats, reads in self._slices():
+            batch = Batch.from_dataset_slice(np.asarray(ints), np.asarray(floats), np.asarray(reads))
             yield batch.pin_memory() if self.pin_memory else batch
+
+    def _staged(self) -> Iterator[Batch]:
+        import queue
+        import threading
+        from concurrent.futures import ThreadPoolExecutor
+        if self._slots is None:
+            self._slots = [_StagingSlot() for _ in range(self.prefetch + 3)]
+        slots, out = self._slots, queue.Queue(maxsize=self.prefetch)
+        stop_flag = threading.Event()
+
+        def produce():
+            try:
+                with ThreadPoolExecutor(self.staging_threads) as pool:
+                    for i, (ints, floats, reads) in enumerate(self._slices()):
+                        if stop_flag.is_set():
+                            return
+                        slot = slots[i % len(slots)]
+                        done = getattr(slot.last_batch, "_h2d_done", None) if slot.last_batch is not None else None
+                        if done is not None:
+                            done.synchronize()          # the copy out of these buffers has left the host
+                        views = [slot.view(name, np.asarray(src)) for name, src in (("int", ints), ("float", floats), ("reads", reads))]
+                        jobs = []
+                        for dst, src in zip(views, (ints, floats, reads)):
+                            jobs += _parallel_copy(pool, dst, np.asarray(src), self.staging_threads)
+                        for j in jobs:
+                            j.result()
+                        batch = Batch.from_dataset_slice(*views)
+                        slot.last_batch = batch
+                        out.put(batch)
+                out.put(None)
+            except BaseException as e:      # hand the failure to the consumer instead of dying silently
+                out.put(e)
+
+        worker = threading.Thread(target=produce, name="pmt-staging", daemon=True)
+        worker.start()
+        try:
+            while True:
+                item = out.get()
+                if item is None:
+                    return
+                if isinstance(item, BaseException):
+                    raise item
+                yield item
+        finally:
+            stop_flag.set()
+            while worker.is_alive():        # unblock a producer waiting on the full queue
+                try:
+                    out.get_nowait()
+                except queue.Empty:
+                    worker.join(timeout=0.05)
 
 
 # ---- fold helpers (reads_dataset.py:26-40) ---------------------------------------------------------------------------
