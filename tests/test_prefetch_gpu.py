@@ -77,6 +77,7 @@ def test_ring_is_shared_between_passes_and_survives_early_exit_and_nesting():
     assert all(torch.equal(a, w) for a, w in zip(got, want))
 
 
+@GPU
 def test_staged_dataset_batches_equal_the_plain_slices_and_feed_the_model():
     """MemoryMappedBatches(staging_threads > 0): a producer thread stages every batch into a ring of pinned buffers with
     copy threads.  Consumed through prefetch_generator (which leaves the H2D event the ring waits for before it refills a
@@ -117,6 +118,7 @@ def test_staged_dataset_batches_equal_the_plain_slices_and_feed_the_model():
         L.set_precision("fp32")
 
 
+@GPU
 def test_dataset_arrays_registered_in_place_give_zero_copy_pinned_batches():
     """MemoryMappedBatches(pin_memory="register"): the arrays are page-locked in place, batches are views of them (no copy),
     DMA-able, and equal to the plain loader's."""
