@@ -32,20 +32,33 @@ class _StagingSlot:
         return buf[:nbytes].numpy().view(like.dtype).reshape(like.shape)
 
 
-def _register_host_array(arr) -> bool:
+def _register_host_array(arr):
     """Page-locks the memory of a host array in place (cudaHostRegister) so that batches cut from it are DMA-able views: no
     staging copy at all.  Works for arrays that live in anonymous memory (a dataset loaded into RAM); a file-backed map is
-    usually refused by the driver -- the caller then falls back to the staging ring.  The registration lasts as long as the
-    process (the arrays of a dataset are opened once)."""
+    usually refused by the driver -- the caller then falls back to the staging ring.  Returns None on failure, else the
+    pointer to hand to ``_unregister_host_arrays`` (0 when the memory was pinned already and is not ours to release).  The
+    registration MUST end before the memory is freed: a freed range that still counts as page-locked makes later host
+    tensors at the same addresses look pinned, and their non-blocking copies race with the host."""
     if not isinstance(arr, np.ndarray) or not arr.flags["C_CONTIGUOUS"] or arr.nbytes == 0:
-        return False
+        return None
     try:
         if torch.from_numpy(arr[:1]).is_pinned():
-            return True
+            return 0
         rc = torch.cuda.cudart().cudaHostRegister(arr.ctypes.data, arr.nbytes, 0)
-        return int(rc) == 0 and torch.from_numpy(arr[:1]).is_pinned()
+        if int(rc) == 0 and torch.from_numpy(arr[:1]).is_pinned():
+            return int(arr.ctypes.data)
+        return None
     except Exception:
-        return False
+        return None
+
+
+def _unregister_host_arrays(pointers):
+    for ptr in pointers:
+        if ptr:
+            try:
+                torch.cuda.cudart().cudaHostUnregister(ptr)
+            except Exception:
+                pass
 
 
 def _parallel_copy(pool, dst: np.ndarray, src: np.ndarray, n_parts: int):
@@ -87,10 +100,19 @@ class MemoryMappedBatches:
         self.registered = False
         if pin_memory == "register":
             arrays = [np.asarray(a) if not isinstance(a, np.memmap) else a for a in (int_mmap, float_mmap, reads_mmap)]
-            self.registered = all(_register_host_array(a) for a in arrays)
+            handles = []
+            for arr in arrays:
+                h = _register_host_array(arr)
+                if h is None:
+                    break
+                handles.append(h)
+            self.registered = len(handles) == len(arrays)
             if self.registered:
-                self.int_mmap, self.float_mmap, self.reads_mmap = arrays
+                import weakref
+                self.int_mmap, self.float_mmap, self.reads_mmap = arrays       # the loader keeps the page-locked arrays alive ...
+                self._unregister = weakref.finalize(self, _unregister_host_arrays, handles)   # ... and unlocks them when it goes
             else:
+                _unregister_host_arrays(handles)
                 self.staging_threads = self.staging_threads or 4
             pin_memory = True
         self.pin_memory = bool(pin_memory)

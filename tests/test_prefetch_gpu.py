@@ -145,3 +145,9 @@ def test_dataset_arrays_registered_in_place_give_zero_copy_pinned_batches():
     assert got[1].int_tensor.data_ptr() == ia[1200:].ctypes.data          # a view of the dataset's own memory
     dev = torch.device("cuda:0")
     assert torch.equal(got[2].copy_to(dev).reads.cpu(), plain[2].reads)
+    # the page lock ends with the loader (a freed range that still counted as pinned would poison later host tensors)
+    torch.cuda.synchronize()
+    del got, loader
+    import gc
+    gc.collect()
+    assert not torch.from_numpy(ia[:1]).is_pinned() and not torch.from_numpy(reads_ds[:1]).is_pinned()
