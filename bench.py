@@ -708,9 +708,10 @@ def main():
         staging_threads = max(2, min(8, (os.cpu_count() or 8) // (2 * max(1, world))))
         maps_loader = MemoryMappedBatches(ia, fa, reads_dataset_order, batch_size=(args.variants + nb - 1) // nb, pin_memory=True,
                                           staging_threads=staging_threads, prefetch=2)
-        # and with the dataset's arrays page-locked in place once (they live in RAM here, as after MemoryMappedData's load):
-        # a batch is then three zero-copy slices
-        reg_loader = MemoryMappedBatches(np.ascontiguousarray(ia), np.ascontiguousarray(fa), np.ascontiguousarray(reads_dataset_order),
+        # and with the dataset loaded into page-locked memory once (load_into_pinned_memory: the load every run starts with, into
+        # cudaHostAlloc memory instead of pageable memory): a batch is then three zero-copy slices
+        from permutect_b200.data.reads_dataset import load_into_pinned_memory
+        reg_loader = MemoryMappedBatches(load_into_pinned_memory(ia), load_into_pinned_memory(fa), load_into_pinned_memory(reads_dataset_order),
                                          batch_size=(args.variants + nb - 1) // nb, pin_memory="register", prefetch=2)
 
         def maps_passes(k, loader):
@@ -828,7 +829,7 @@ def main():
                 "host_cores_bound": len(numa_cores) if numa_cores else None,
                 "passes_per_call": args.steps,
                 "call": "one call of tools.filter_variants.generate_posterior_arrays over data.reads_dataset.MemoryMappedBatches("
-                        + ("pin_memory='register': the dataset's arrays page-locked in place once, every batch three zero-copy slices"
+                        + ("the dataset's arrays loaded into page-locked memory once, every batch three zero-copy slices"
                            if reg_loader.registered else f"staging_threads={staging_threads}: batches staged into a pinned ring by copy threads")
                         + "), reads in dataset order (gather indices written on the device); prefetch_generator H2D on a side stream, "
                           "compute_batch_output, pmt_pack_posterior, posterior records D2H into pinned host arrays",

@@ -151,3 +151,16 @@ def test_dataset_arrays_registered_in_place_give_zero_copy_pinned_batches():
     import gc
     gc.collect()
     assert not torch.from_numpy(ia[:1]).is_pinned() and not torch.from_numpy(reads_ds[:1]).is_pinned()
+
+
+@GPU
+def test_dataset_loaded_into_pinned_memory_gives_pinned_views():
+    import numpy as np
+    from permutect_b200.data.reads_dataset import MemoryMappedBatches, load_into_pinned_memory
+    ia, fa, reads = make_wgs_arrays(800, seed=29)
+    pinned = load_into_pinned_memory(ia)
+    assert pinned.dtype == ia.dtype and np.array_equal(pinned, ia) and torch.from_numpy(pinned[100:200]).is_pinned()
+    n = ia[:, 0].astype(np.int64) + ia[:, 1].astype(np.int64)
+    loader = MemoryMappedBatches(pinned, load_into_pinned_memory(fa), load_into_pinned_memory(reads[: int(n.sum())]), 300,
+                                 pin_memory="register")
+    assert loader.registered and all(b.int_tensor.is_pinned() and b.reads.is_pinned() for b in loader)
