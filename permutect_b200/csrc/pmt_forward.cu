@@ -243,6 +243,84 @@ info_mlp_rows_kernel(const __grid_constant__ PmtModelDesc D, const float* __rest
   }
 }
 
+// Small batches: the thread-per-variant kernel above is a chain of ~7 600 dependent multiply-adds per variant (30 us for the 64
+// variants of the reference's default batch, a quarter of the whole inference call).  Here a WARP owns a variant and a lane
+// owns one output of every layer: the chain is in_dim FMAs long per layer, inputs travel by shuffle.  Same order of
+// summation (bias first, inputs in ascending order), so the results are bitwise those of the other kernel.
+constexpr int INFO_WARPS = 8;
+__global__ void __launch_bounds__(32 * INFO_WARPS)
+info_mlp_warp_kernel(const __grid_constant__ PmtModelDesc D, const float* __restrict__ wflat, const void* __restrict__ info, int info_kind,
+                     long long info_stride, int n_variants, float* __restrict__ info_seq) {
+  constexpr int W = 32;
+  extern __shared__ __align__(16) float smem[];
+  const int I = D.n_info_features, n_ops = D.n_info_ops;
+  float* wt = smem;   // per op [in_dim + 1][W]: transposed weights, then the bias row
+  {
+    // zero (the padding outputs), then the weights read in the order they lie in memory (coalesced) and transposed on the
+    // way into shared memory: at this batch size the staging is a good part of the kernel
+    int total = 0;
+    for (int i = 0; i < n_ops; ++i) total += (D.info_ops[i].in_dim + 1) * W;
+    for (int idx = threadIdx.x; idx < total; idx += 32 * INFO_WARPS) wt[idx] = 0.f;
+    __syncthreads();
+    int base = 0;
+    for (int i = 0; i < n_ops; ++i) {
+      const PmtLinearOp& op = D.info_ops[i];
+      const int nk = op.out_dim * op.in_dim;
+      for (int idx = threadIdx.x; idx < nk + op.out_dim; idx += 32 * INFO_WARPS) {
+        if (idx < nk) {
+          const int n = idx / op.in_dim, k = idx - n * op.in_dim;
+          wt[base + k * W + n] = __ldg(wflat + op.w_off + idx);
+        } else {
+          wt[base + op.in_dim * W + (idx - nk)] = __ldg(wflat + op.b_off + idx - nk);
+        }
+      }
+      base += (op.in_dim + 1) * W;
+    }
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int out_w = D.d_info + D.d_seq;
+  for (int v = blockIdx.x * INFO_WARPS + warp; v < n_variants; v += gridDim.x * INFO_WARPS) {
+    // the variant's features, lane l holding features l, l + 32, ...
+    float xin[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int f = q * 32 + lane;
+      float x = 0.f;
+      if (f < I) {
+        const long long o = (long long)v * info_stride + f;
+        x = info_kind == PMT_F16 ? __half2float(__ldg(reinterpret_cast<const __half*>(info) + o)) : __ldg(reinterpret_cast<const float*>(info) + o);
+      }
+      xin[q] = x;
+    }
+    float cur = 0.f, res = 0.f;
+    int base = 0;
+    for (int i = 0; i < n_ops; ++i) {
+      const PmtLinearOp op = D.info_ops[i];
+      const float* w = wt + base + lane;
+      float y = w[op.in_dim * W];   // bias
+      if (i == 0) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (q * 32 < op.in_dim) {
+            const int kn = min(32, op.in_dim - q * 32);
+            for (int k = 0; k < kn; ++k) y = fmaf(__shfl_sync(0xffffffffu, xin[q], k), w[(q * 32 + k) * W], y);
+          }
+        }
+      } else {
+        float src = cur;
+        if (op.flags & PMT_OP_SKIP_BEGIN) { res = cur; src = selu(cur); }
+        for (int k = 0; k < op.in_dim; ++k) y = fmaf(__shfl_sync(0xffffffffu, src, k), w[k * W], y);
+      }
+      if (op.flags & PMT_OP_SKIP_END) cur = fmaf(__ldg(wflat + op.alpha_off), y, res);
+      else if (op.flags & PMT_OP_POST_SELU) cur = lane < op.out_dim ? selu(y) : 0.f;
+      else cur = y;
+      base += (op.in_dim + 1) * W;
+    }
+    if (lane < D.d_info) info_seq[(long long)v * out_w + lane] = cur;
+  }
+}
+
 // The thread-per-variant kernel covers MLPs whose hidden vectors are at most 32 wide, with the input layer first and no
 // DenseSkipBlock opening on the raw input; anything else takes the tile-GEMM kernel above.
 static int info_rows_w4(const PmtModelDesc& d) {
@@ -744,7 +822,16 @@ int pmt_launch_variant_kernels(const Plan& P, const CnnGeom& G, const float* wei
                                cudaStream_t st) {
   const int B = batch->n_variants;
   const int w4 = info_rows_w4(P.d);
-  if (w4 > 0) {
+  if (w4 > 0 && B <= 4096) {   // small batch: latency, not throughput (info_mlp_warp_kernel)
+    size_t floats = 0;
+    for (int i = 0; i < P.d.n_info_ops; ++i) floats += (size_t)(P.d.info_ops[i].in_dim + 1) * 32;
+    const size_t smem = floats * sizeof(float) + 16;
+    PMT_CHECK(smem <= 200 * 1024, "info MLP does not fit in shared memory");
+    PMT_CUDA(cudaFuncSetAttribute(info_mlp_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int blocks = (B + INFO_WARPS - 1) / INFO_WARPS;
+    info_mlp_warp_kernel<<<blocks < 148 * 4 ? blocks : 148 * 4, 32 * INFO_WARPS, smem, st>>>(P.d, weights, batch->info, batch->info_kind,
+                                                                                               batch->info_stride, B, info_seq);
+  } else if (w4 > 0) {
     int rc = 1;
     switch (w4) {
       case 1: rc = launch_info_rows<1>(P.d, weights, batch, info_seq, st); break;
