@@ -143,10 +143,21 @@ typedef struct PmtOutGrads {
   const float* d_ref_means_be;/* [B][E] */
   const float* info_seq_be;   /* [B][d_info+d_seq] PmtOutputs.info_seq_be saved from the forward of the same batch and
                                  weights, or NULL: the per-variant embeddings are then recomputed */
+  const void* saved;          /* the buffer pmt_forward_train filled for the same batch and weights, or NULL: the backward
+                                 recomputes the forward (in bounded passes) itself */
 } PmtOutGrads;
 
 const char* pmt_last_error(void);
 int pmt_abi_version(void);
+
+/* Training without recompute.  pmt_forward_train is pmt_forward that additionally leaves, in `saved`, everything the
+ * tensor-core backward would otherwise recompute (the tile list, every layer's operand panels of every tile, the haplotype
+ * CNN's activations); pmt_backward takes the same buffer through PmtOutGrads.saved and skips its recompute passes.
+ * pmt_train_saved_bytes: bytes of `saved` for this batch, or 0 when the current precision mode / model shape has no such
+ * path or the buffer would pass 16 GB (0.7 MB per 128 reads) -- call pmt_forward and leave PmtOutGrads.saved NULL then. */
+size_t pmt_train_saved_bytes(const PmtModelDesc* desc, const PmtBatch* batch);
+int pmt_forward_train(const PmtModelDesc* desc, const float* weights, const PmtBatch* batch, const PmtOutputs* out,
+                      void* workspace, size_t workspace_bytes, void* saved, size_t saved_bytes, void* stream);
 
 /* Bytes of device workspace pmt_forward / pmt_backward need for this model and batch shape. */
 size_t pmt_workspace_size(const PmtModelDesc* desc, const PmtBatch* batch, int for_backward);

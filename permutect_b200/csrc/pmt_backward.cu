@@ -1353,6 +1353,17 @@ extern "C" int pmt_backward(const PmtModelDesc* desc, const float* weights, cons
   off += cnn_ws_bytes;
   PMT_CHECK(off <= workspace_bytes, "workspace layout overflow");
 
+  // what pmt_forward_train saved for this batch (PmtOutGrads.saved): [read path][haplotype CNN], as train_saved_split lays it out
+  const unsigned char* saved_tc = nullptr;
+  const float* saved_cnn = nullptr;
+  if (grads && grads->saved) {
+    PMT_CHECK(use_tc && cnn_mma && pmt_precision_mode() == PMT_PRECISION_TF32X3 && grads->info_seq_be,
+              "PmtOutGrads.saved needs the tf32x3 mode, the forward's info_seq_be, and the precision mode of the forward call");
+    const size_t tc = pmt_tc_train_saved_bytes(P, batch);
+    PMT_CHECK(tc > 0 && pmt_cnn_train_saved_bytes(P, batch) > 0, "PmtOutGrads.saved: no saved-forward path for this batch");
+    saved_tc = reinterpret_cast<const unsigned char*>(grads->saved);
+    saved_cnn = reinterpret_cast<const float*>(saved_tc + ((tc + 1023) & ~(size_t)1023));
+  }
   PMT_CUDA(cudaMemsetAsync(partials, 0, (size_t)kBwdGrid * desc->n_params * sizeof(float), st));
   // conv images: only the SIMT haplotype-CNN kernels read them (the recompute below when the forward's embeddings are not
   // passed in, and the SIMT backward)
@@ -1391,7 +1402,7 @@ extern "C" int pmt_backward(const PmtModelDesc* desc, const float* weights, cons
   int tc_grid = 0;
   if (use_tc) {
     if (pmt_launch_reads_tc_backward(P, weights, batch, info_seq, A.d_logits_bk, A.d_alt_means, A.d_ref_means, d_info_seq, tc_ws,
-                                     tc_ws_bytes, n_sm, &tc_grid, st))
+                                     tc_ws_bytes, n_sm, &tc_grid, st, saved_tc))
       return 1;
   } else {
     PMT_CUDA(cudaFuncSetAttribute(reads_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1415,7 +1426,8 @@ extern "C" int pmt_backward(const PmtModelDesc* desc, const float* weights, cons
                                                              (long long)scr_floats, partials, rows);
   }
   if (cnn_mma) {
-    if (pmt_launch_cnn_backward_mma(P, weights, batch, info_seq, d_info_seq, partials, kBwdGrid, cnn_ws, cnn_ws_bytes, n_sm, st)) return 1;
+    if (pmt_launch_cnn_backward_mma(P, weights, batch, info_seq, d_info_seq, partials, kBwdGrid, cnn_ws, cnn_ws_bytes, n_sm, st, saved_cnn))
+      return 1;
   } else if (pmt_launch_cnn_backward(P, G, weights, image, batch, d_info_seq, partials, kBwdGrid, st)) {
     return 1;
   }

@@ -508,8 +508,26 @@ size_t pmt_cnn_bwd_mma_workspace_bytes(const pmt::Plan& P, const PmtBatch* batch
   return pmt_cnn_tc_image_bytes(P) + 256 + (size_t)B.img_total * sizeof(float) + 256 + groups * B.group_floats * sizeof(float) + 1024;
 }
 
+// ---- training without recompute: the training forward runs the SAVE variant over the whole batch (pmt_forward_train) ----
+size_t pmt_cnn_train_saved_bytes(const pmt::Plan& P, const PmtBatch* batch) {
+  cnntc::Plan T;
+  BPlan B;
+  if (!batch || batch->n_variants <= 0 || !pmt_build_cnn_tc_plan(P, &T) || !build_bwd_plan(P, T, &B)) return 0;
+  const size_t groups = ((size_t)batch->n_variants + T.G - 1) / T.G;
+  return groups * B.group_floats * sizeof(float) + 256;
+}
+
+int pmt_cnn_forward_train(const pmt::Plan& P, const float* weights, const PmtBatch* batch, float* info_seq, unsigned char* image,
+                          float* save, int n_sm, cudaStream_t st) {
+  cnntc::Plan T;
+  PMT_CHECK(pmt_build_cnn_tc_plan(P, &T), "haplotype CNN outside the tensor-core envelope");
+  if (pmt_pack_cnn_tc_images(P, T, weights, image, st)) return 1;
+  return pmt_launch_cnn_tc_save(P, T, weights, batch, 0, batch->n_variants, info_seq, image, save, n_sm, st);
+}
+
 int pmt_launch_cnn_backward_mma(const pmt::Plan& P, const float* weights, const PmtBatch* batch, float* info_seq, const float* d_info_seq,
-                                float* partials, int n_partials, unsigned char* ws, size_t ws_bytes, int n_sm, cudaStream_t st) {
+                                float* partials, int n_partials, unsigned char* ws, size_t ws_bytes, int n_sm, cudaStream_t st,
+                                const float* saved) {
   cnntc::Plan T;
   BPlan B;
   PMT_CHECK(pmt_build_cnn_tc_plan(P, &T) && build_bwd_plan(P, T, &B), "haplotype CNN outside the tensor-core backward's envelope");
@@ -518,15 +536,17 @@ int pmt_launch_cnn_backward_mma(const pmt::Plan& P, const float* weights, const 
   unsigned char* fwd_image = p; p += (pmt_cnn_tc_image_bytes(P) + 255) & ~size_t(255);
   float* bwd_image = reinterpret_cast<float*>(p); p += ((size_t)B.img_total * sizeof(float) + 255) & ~size_t(255);
   float* save = reinterpret_cast<float*>(p);
-  // weight images: the forward's (split precision) and the data gradient's
-  if (pmt_pack_cnn_tc_images(P, T, weights, fwd_image, st)) return 1;
+  // weight images: the forward's (split precision; only for the recompute) and the data gradient's
+  if (!saved && pmt_pack_cnn_tc_images(P, T, weights, fwd_image, st)) return 1;
   pack_cnn_bwd_kernel<<<dim3(B.n_layers, 8), 256, 0, st>>>(B, weights, bwd_image);
   PMT_CUDA(cudaFuncSetAttribute(cnn_backward_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B.smem_bytes));
   const int out_w = P.d.d_info + P.d.d_seq;
   const size_t esz = batch->hap_kind == PMT_I64 ? 8 : 2;
-  for (int v_first = 0; v_first < batch->n_variants; v_first += kCnnBwdChunk) {
-    const int n = batch->n_variants - v_first < kCnnBwdChunk ? batch->n_variants - v_first : kCnnBwdChunk;
-    if (pmt_launch_cnn_tc_save(P, T, weights, batch, v_first, n, info_seq, fwd_image, save, n_sm, st)) return 1;
+  const int chunk = saved ? batch->n_variants : kCnnBwdChunk;   // saved by the training forward: the whole batch at once
+  for (int v_first = 0; v_first < batch->n_variants; v_first += chunk) {
+    const int n = batch->n_variants - v_first < chunk ? batch->n_variants - v_first : chunk;
+    if (saved) save = const_cast<float*>(saved);
+    else if (pmt_launch_cnn_tc_save(P, T, weights, batch, v_first, n, info_seq, fwd_image, save, n_sm, st)) return 1;
     const int n_groups = (n + B.VT - 1) / B.VT;
     int grid = n_groups < n_sm ? n_groups : n_sm;
     if (grid > n_partials) grid = n_partials;

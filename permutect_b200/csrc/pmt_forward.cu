@@ -819,7 +819,7 @@ int pmt_launch_prepare(const Plan& P, const CnnGeom& G, const float* weights, fl
 
 int pmt_launch_variant_kernels(const Plan& P, const CnnGeom& G, const float* weights, const float* image,
                                const PmtBatch* batch, float* info_seq, int mode, unsigned char* cnn_tc_image, bool reuse_images,
-                               cudaStream_t st) {
+                               cudaStream_t st, bool skip_cnn) {
   const int B = batch->n_variants;
   const int w4 = info_rows_w4(P.d);
   if (w4 > 0 && B <= 4096) {   // small batch: latency, not throughput (info_mlp_warp_kernel)
@@ -851,6 +851,7 @@ int pmt_launch_variant_kernels(const Plan& P, const CnnGeom& G, const float* wei
     info_mlp_kernel<<<(B + TILE - 1) / TILE, NTHREADS, smem, st>>>(P, weights, image, batch->info, batch->info_kind,
                                                                    batch->info_stride, B, info_seq);
   }
+  if (skip_cnn) return 0;   // the caller runs the haplotype CNN itself (training forward: its SAVE variant)
   if (mode != PMT_PRECISION_FP32 && cnn_tc_image && pmt_cnn_tc_supported(P)) {
     // tensor-core haplotype CNN (pmt_cnn_tc.cu); shapes outside its envelope run the FP32 SIMT kernel below
     int dev = 0, n_sm = 148;
@@ -879,8 +880,28 @@ static int choose_claim(const PmtBatch* batch, int n_sm) {
   return claim;
 }
 
+static size_t train_saved_split(const Plan& P, const PmtBatch* batch, size_t* cnn_off) {
+  // [read path: tile list + operand panels][haplotype CNN activations]; 0 when there is no such path for this call
+  if (pmt_precision_mode() != PMT_PRECISION_TF32X3 || !batch || !pmt_tc_supported(P) || !pmt_cnn_tc_supported(P) ||
+      !pmt_cnn_bwd_mma_supported(P))
+    return 0;
+  const size_t tc = pmt_tc_train_saved_bytes(P, batch), cnn = pmt_cnn_train_saved_bytes(P, batch);
+  if (tc == 0 || cnn == 0) return 0;
+  const size_t off = (tc + 1023) & ~(size_t)1023;
+  if (cnn_off) *cnn_off = off;
+  return off + cnn + 1024;
+}
+
+extern "C" size_t pmt_train_saved_bytes(const PmtModelDesc* desc, const PmtBatch* batch) {
+  Plan P;
+  if (pmt_build_plan(desc, &P)) return 0;
+  const size_t bytes = train_saved_split(P, batch, nullptr);
+  return bytes <= ((size_t)16 << 30) ? bytes : 0;
+}
+
 static int forward_impl(const PmtModelDesc* desc, const float* weights, const PmtBatch* batch, const PmtOutputs* out,
-                        void* workspace, size_t workspace_bytes, void* stream, bool reuse_images) {
+                        void* workspace, size_t workspace_bytes, void* stream, bool reuse_images, unsigned char* saved = nullptr,
+                        size_t saved_bytes = 0) {
   Plan P;
   CnnGeom G;
   if (pmt_build_plan(desc, &P) || pmt_cnn_geometry(P, &G)) return 1;
@@ -908,11 +929,22 @@ static int forward_impl(const PmtModelDesc* desc, const float* weights, const Pm
   }
   unsigned char* tc_image = reinterpret_cast<unsigned char*>(ws + L.tc_image);
   unsigned char* cnn_tc_image = reinterpret_cast<unsigned char*>(ws + L.cnn_tc_image);
-  if (pmt_launch_variant_kernels(P, G, weights, image, batch, info_seq, mode, cnn_tc_image, reuse_images, st)) return 1;
-
   int dev = 0, n_sm = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  size_t saved_cnn_off = 0;
+  if (saved) {
+    const size_t need_saved = train_saved_split(P, batch, &saved_cnn_off);
+    PMT_CHECK(need_saved > 0 && saved_bytes >= need_saved, "pmt_forward_train: no saved-forward path for this call or buffer too small (%zu < %zu)",
+              saved_bytes, need_saved);
+    PMT_CHECK((reinterpret_cast<uintptr_t>(saved) & 255) == 0, "pmt_forward_train: the saved buffer must be 256-byte aligned");
+    // per-variant embeddings: the info MLP as always, the haplotype CNN in its SAVE variant (same results, activations kept)
+    if (pmt_launch_variant_kernels(P, G, weights, image, batch, info_seq, mode, nullptr, reuse_images, st, /*skip_cnn=*/true)) return 1;
+    if (pmt_cnn_forward_train(P, weights, batch, info_seq, cnn_tc_image, reinterpret_cast<float*>(saved + saved_cnn_off), n_sm, st)) return 1;
+  } else if (pmt_launch_variant_kernels(P, G, weights, image, batch, info_seq, mode, cnn_tc_image, reuse_images, st)) {
+    return 1;
+  }
+
   P.claim_variants = choose_claim(batch, n_sm);
   ReadKernelArgs A;
   A.wflat = weights; A.image = image; A.batch = *batch; A.out = *out; A.out.info_seq_be = info_seq; A.claim_counter = counter;
@@ -925,8 +957,11 @@ static int forward_impl(const PmtModelDesc* desc, const float* weights, const Pm
     PMT_CHECK(pmt_tc_supported(P), "this model shape is outside the tensor-core kernel's envelope; use PMT_PRECISION_FP32");
     PmtOutputs o2 = *out;
     o2.info_seq_be = info_seq;
-    if (pmt_launch_reads_tc(P, weights, batch, &o2, tc_image, reinterpret_cast<unsigned char*>(ws + L.tiles), reuse_images, n_sm, mode, st))
+    if (saved) {   // training forward: deterministic tile list + the SAVE variant of the read kernel, operands kept for the backward
+      if (pmt_tc_forward_train(P, weights, batch, &o2, tc_image, reinterpret_cast<unsigned char*>(ws + L.tiles), saved, n_sm, st)) return 1;
+    } else if (pmt_launch_reads_tc(P, weights, batch, &o2, tc_image, reinterpret_cast<unsigned char*>(ws + L.tiles), reuse_images, n_sm, mode, st)) {
       return 1;
+    }
   } else {
     pmt_profile_begin(st);
     reads_forward_kernel<<<grid, NTHREADS, smem, st>>>(P, A);
@@ -952,6 +987,12 @@ static int forward_impl(const PmtModelDesc* desc, const float* weights, const Pm
 extern "C" int pmt_forward(const PmtModelDesc* desc, const float* weights, const PmtBatch* batch, const PmtOutputs* out,
                            void* workspace, size_t workspace_bytes, void* stream) {
   return forward_impl(desc, weights, batch, out, workspace, workspace_bytes, stream, false);
+}
+
+extern "C" int pmt_forward_train(const PmtModelDesc* desc, const float* weights, const PmtBatch* batch, const PmtOutputs* out,
+                                 void* workspace, size_t workspace_bytes, void* saved, size_t saved_bytes, void* stream) {
+  PMT_CHECK(saved != nullptr, "pmt_forward_train: saved buffer missing (pmt_train_saved_bytes() == 0 means: call pmt_forward)");
+  return forward_impl(desc, weights, batch, out, workspace, workspace_bytes, stream, false, reinterpret_cast<unsigned char*>(saved), saved_bytes);
 }
 
 extern "C" int pmt_forward_prepared(const PmtModelDesc* desc, const float* weights, const PmtBatch* batch, const PmtOutputs* out,

@@ -35,7 +35,7 @@ int pmt_launch_prepare(const pmt::Plan& P, const pmt::CnnGeom& G, const float* w
                        bool need_gemm = true, bool need_conv = true);
 int pmt_launch_variant_kernels(const pmt::Plan& P, const pmt::CnnGeom& G, const float* weights, const float* image,
                                const PmtBatch* batch, float* info_seq, int mode, unsigned char* cnn_tc_image, bool reuse_images,
-                               cudaStream_t st);
+                               cudaStream_t st, bool skip_cnn = false);
 size_t pmt_backward_workspace_bytes(const pmt::Plan& P, const PmtBatch* batch);
 void pmt_profile_begin(cudaStream_t st);
 void pmt_profile_end(cudaStream_t st);
@@ -55,7 +55,16 @@ int pmt_launch_reads_tc(const pmt::Plan& P, const float* weights, const PmtBatch
 size_t pmt_tc_bwd_workspace_bytes(const pmt::Plan& P, const PmtBatch* batch);
 int pmt_launch_reads_tc_backward(const pmt::Plan& P, const float* weights, const PmtBatch* batch, const float* info_seq,
                                  const float* d_logits_bk, const float* d_alt_means, const float* d_ref_means, float* d_info_seq,
-                                 unsigned char* ws, size_t ws_bytes, int n_sm, int* grid_out, cudaStream_t st);
+                                 unsigned char* ws, size_t ws_bytes, int n_sm, int* grid_out, cudaStream_t st,
+                                 const unsigned char* saved = nullptr);
+// training without recompute (pmt_tc_bwd.cu, pmt_cnn_bwd.cu): the training forward saves what the backward would recompute
+size_t pmt_tc_train_saved_bytes(const pmt::Plan& P, const PmtBatch* batch);
+int pmt_tc_forward_train(const pmt::Plan& P, const float* weights, const PmtBatch* batch, const PmtOutputs* out, unsigned char* image_buf,
+                         unsigned char* claim_buf, unsigned char* saved, int n_sm, cudaStream_t st);
+size_t pmt_plan_claim_bytes(int n_variants, int n_sm);
+size_t pmt_cnn_train_saved_bytes(const pmt::Plan& P, const PmtBatch* batch);
+int pmt_cnn_forward_train(const pmt::Plan& P, const float* weights, const PmtBatch* batch, float* info_seq, unsigned char* image,
+                          float* save, int n_sm, cudaStream_t st);
 int pmt_finish_reads_tc_backward(const pmt::Plan& P, const float* weights, const PmtBatch* batch, float* d_weights, unsigned char* ws,
                                  int grid, cudaStream_t st);
 bool pmt_cnn_tc_supported(const pmt::Plan& P);
@@ -66,4 +75,5 @@ int pmt_launch_cnn_tc(const pmt::Plan& P, const float* weights, const PmtBatch* 
 bool pmt_cnn_bwd_mma_supported(const pmt::Plan& P);
 size_t pmt_cnn_bwd_mma_workspace_bytes(const pmt::Plan& P, const PmtBatch* batch);
 int pmt_launch_cnn_backward_mma(const pmt::Plan& P, const float* weights, const PmtBatch* batch, float* info_seq, const float* d_info_seq,
-                                float* partials, int n_partials, unsigned char* ws, size_t ws_bytes, int n_sm, cudaStream_t st);
+                                float* partials, int n_partials, unsigned char* ws, size_t ws_bytes, int n_sm, cudaStream_t st,
+                                const float* saved = nullptr);

@@ -327,7 +327,8 @@ void pmt_tc_plan(const pmt::Plan& P, pmt::tc::TcPlan* out);
 size_t pmt_tc_bwd_workspace_bytes(const pmt::Plan& P, const PmtBatch* batch);
 int pmt_launch_reads_tc_backward(const pmt::Plan& P, const float* weights, const PmtBatch* batch, const float* info_seq,
                                  const float* d_logits_bk, const float* d_alt_means, const float* d_ref_means, float* d_info_seq,
-                                 unsigned char* ws, size_t ws_bytes, int n_sm, int* grid_out, cudaStream_t st);
+                                 unsigned char* ws, size_t ws_bytes, int n_sm, int* grid_out, cudaStream_t st,
+                                 const unsigned char* saved);   // default argument: pmt_host.h
 int pmt_finish_reads_tc_backward(const pmt::Plan& P, const float* weights, const PmtBatch* batch, float* d_weights, unsigned char* ws,
                                  int grid, cudaStream_t st);
 int pmt_launch_pack_tc(const pmt::Plan& P, const pmt::tc::TcPlan& T, const float* weights, unsigned char* image, cudaStream_t st);

@@ -850,6 +850,12 @@ static long long tile_bound(const PmtBatch* batch, int n_claims) {
   const long long rows = batch->n_rows > 0 ? batch->n_rows : 16LL * batch->n_variants;
   // a tile is closed when the next set does not fit or it holds BWD_MAXV sets; the last tile of a claim may be short
   long long bound = 2 * rows / TILE + batch->n_variants / BWD_MAXV + n_claims + 8;
+  if (batch->max_rows_per_variant > 0) {
+    // with the longest set known: a tile closed because the next set did not fit holds more than TILE - 3 - longest rows
+    const long long longest = batch->max_rows_per_variant < TILE - 4 ? batch->max_rows_per_variant : TILE - 4;
+    const long long tight = rows / (TILE - 3 - longest) + batch->n_variants / BWD_MAXV + n_claims + 8;
+    if (tight < bound) bound = tight;
+  }
   if (bound > batch->n_variants) bound = batch->n_variants;
   return bound < 1 ? 1 : bound;
 }
@@ -885,6 +891,63 @@ static BwdLayout bwd_layout(const TcPlan& T, const PmtBatch* batch, int n_sm) {
   return L;
 }
 
+// ---- training without recompute: what the training forward leaves for the backward (pmt_forward_train) ----
+// [256-byte header][tile list][operand scratch of EVERY tile of the (deterministic) list].  The tile count is only known
+// on the device, so the scratch is sized for the bound; over the budget the caller keeps the recompute.
+static const size_t kTrainSavedBudget = (size_t)16 << 30;   // measured: 9 GB (65 536 variants) wins 14 %, 27 GB (200 000) loses to the recompute
+static const unsigned kTrainSavedMagic = 0x544d5031u;
+struct TrainSavedLayout { size_t tiles, scratch, total; long long bound; };
+static TrainSavedLayout train_saved_layout(const TcPlan& T, const PmtBatch* batch) {
+  TrainSavedLayout S;
+  const BwdLayout L = bwd_layout(T, batch, kMaxGrid);
+  S.bound = tile_bound(batch, L.n_claims);
+  S.tiles = 256;
+  size_t off = S.tiles + (((size_t)(2 + 2 * (size_t)batch->n_variants) * sizeof(int) + 511) & ~(size_t)255);
+  off = (off + 1023) & ~(size_t)1023;
+  S.scratch = off;
+  S.total = off + (size_t)S.bound * T.tile_bytes + 1024;
+  return S;
+}
+size_t pmt_tc_train_saved_bytes(const Plan& P, const PmtBatch* batch) {
+  if (!batch || batch->n_variants <= 0 || !pmt_tc_supported(P)) return 0;
+  TcPlan T;
+  pmt_tc_plan(P, &T);
+  const TrainSavedLayout S = train_saved_layout(T, batch);
+  return S.total <= kTrainSavedBudget ? S.total : 0;
+}
+
+// The training forward of the tile-sized sets: deterministic tile list, then the SAVE variant of the read kernel over ALL
+// tiles with the outputs switched on.  `image_buf`: pmt_tc_image_bytes(P) bytes (forward weight images, packed here);
+// `claim_buf`: pmt_plan_claim_bytes(B, 148) + 256 bytes of scratch for the planner.
+int pmt_tc_forward_train(const Plan& P, const float* weights, const PmtBatch* batch, const PmtOutputs* out, unsigned char* image_buf,
+                         unsigned char* claim_buf, unsigned char* saved, int n_sm, cudaStream_t st) {
+  TcPlan T;
+  pmt_tc_plan(P, &T);
+  if (n_sm > kMaxGrid) n_sm = kMaxGrid;
+  const TrainSavedLayout S = train_saved_layout(T, batch);
+  unsigned char* image = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(image_buf) + 1023) & ~uintptr_t(1023));
+  int* tiles = reinterpret_cast<int*>(saved + S.tiles);
+  int* claims = reinterpret_cast<int*>((reinterpret_cast<uintptr_t>(claim_buf) + 255) & ~uintptr_t(255));
+  int n_claims = 0;
+  if (pmt_plan_tiles(batch, BWD_MAXV, true, kMaxGrid, tiles, claims, &n_claims, st)) return 1;
+  if (pmt_launch_pack_tc(P, T, weights, image, st)) return 1;
+  const unsigned header[4] = {kTrainSavedMagic, (unsigned)batch->n_variants, (unsigned)S.bound, 0u};
+  PMT_CUDA(cudaMemcpyAsync(saved, header, sizeof(header), cudaMemcpyHostToDevice, st));
+  const long long rows = batch->n_rows > 0 ? batch->n_rows : 16LL * batch->n_variants;
+  long long est_tiles = rows / 100 + n_claims;
+  if (est_tiles > batch->n_variants) est_tiles = batch->n_variants;
+  int grid = est_tiles < n_sm ? (int)est_tiles : n_sm;
+  if (grid < 1) grid = 1;
+  TcArgs F;
+  memset(&F, 0, sizeof(F));
+  F.wflat = weights; F.image = image; F.tiles = tiles; F.perm = nullptr; F.batch = *batch; F.out = *out;
+  F.scratch = saved + S.scratch; F.sched = 0; F.tile_first = 0; F.tile_limit = 0x7fffffff;
+  pmt_profile_begin(st);
+  const int rc = pmt_launch_reads_tc_save(P, T, F, grid, st);
+  pmt_profile_end(st);
+  return rc;
+}
+
 size_t pmt_tc_bwd_workspace_bytes(const Plan& P, const PmtBatch* batch) {
   TcPlan T;
   pmt_tc_plan(P, &T);
@@ -898,7 +961,7 @@ void pmt_set_backward_tc_trace(long long* device_buffer) { g_bwd_tc_trace = devi
 // in the private buffers of the workspace; pmt_finish_reads_tc_backward adds them to d_weights.
 int pmt_launch_reads_tc_backward(const Plan& P, const float* weights, const PmtBatch* batch, const float* info_seq,
                                  const float* d_logits_bk, const float* d_alt_means, const float* d_ref_means, float* d_info_seq,
-                                 unsigned char* ws, size_t ws_bytes, int n_sm, int* grid_out, cudaStream_t st) {
+                                 unsigned char* ws, size_t ws_bytes, int n_sm, int* grid_out, cudaStream_t st, const unsigned char* saved) {
   TcPlan T;
   pmt_tc_plan(P, &T);
   if (n_sm > kMaxGrid) n_sm = kMaxGrid;
@@ -913,8 +976,17 @@ int pmt_launch_reads_tc_backward(const Plan& P, const float* weights, const PmtB
   unsigned char* scratch = base + L.scratch;
 
   int n_claims = 0;
-  if (pmt_plan_tiles(batch, BWD_MAXV, true, kMaxGrid, tiles, claims, &n_claims, st)) return 1;
-  if (pmt_launch_pack_tc(P, T, weights, image_f, st)) return 1;
+  TrainSavedLayout SV;
+  memset(&SV, 0, sizeof(SV));
+  if (saved) {   // the training forward left the tile list and every tile's operands (pmt_tc_forward_train): no recompute
+    SV = train_saved_layout(T, batch);
+    tiles = const_cast<int*>(reinterpret_cast<const int*>(saved + SV.tiles));
+    scratch = const_cast<unsigned char*>(saved + SV.scratch);
+    n_claims = L.n_claims;
+  } else {
+    if (pmt_plan_tiles(batch, BWD_MAXV, true, kMaxGrid, tiles, claims, &n_claims, st)) return 1;
+    if (pmt_launch_pack_tc(P, T, weights, image_f, st)) return 1;
+  }
   pack_tc_bwd_kernel<<<dim3(T.n_steps, 8), 256, 0, st>>>(P.d, T, weights, image_t);
 
   const long long rows = batch->n_rows > 0 ? batch->n_rows : 16LL * batch->n_variants;
@@ -946,7 +1018,8 @@ int pmt_launch_reads_tc_backward(const Plan& P, const float* weights, const PmtB
   for (int c = 0; c < L.n_chunks; ++c) {
     F.tile_first = Bk.tile_first = c * L.chunk_tiles;
     F.tile_limit = Bk.tile_limit = (c + 1) * L.chunk_tiles;
-    if (pmt_launch_reads_tc_save(P, T, F, grid, st)) return 1;
+    if (saved) Bk.scratch = scratch + (size_t)Bk.tile_first * T.tile_bytes;   // the kernel indexes a pass's scratch from its first tile
+    else if (pmt_launch_reads_tc_save(P, T, F, grid, st)) return 1;
     if (g_bwd_tc_trace) reads_backward_tc_kernel<true><<<grid, THREADS, smem, st>>>(P.d, T, Bk, n_stages, stage_bytes, g_bwd_tc_trace);
     else reads_backward_tc_kernel<false><<<grid, THREADS, smem, st>>>(P.d, T, Bk, n_stages, stage_bytes, nullptr);
   }

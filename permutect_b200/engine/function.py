@@ -4,6 +4,7 @@ PyTorch is plumbing here: it owns the buffers, the stream and the autograd tape 
 parameter-constraint Jacobians; every per-read / per-variant FLOP is executed by the library.
 """
 import ctypes as C
+import os
 from typing import Dict, Optional
 
 import torch
@@ -58,13 +59,17 @@ def _require_cuda(t: torch.Tensor):
 
 
 def forward_call(desc: L.PmtModelDesc, flat: torch.Tensor, batch, want_final: bool = False,
-                 n_rows: Optional[int] = None, weights_key=None) -> Dict[str, torch.Tensor]:
+                 n_rows: Optional[int] = None, weights_key=None, for_training: bool = False) -> Dict[str, torch.Tensor]:
     """pmt_forward: one fused pass over a batch.  Returns logits_bk, logits_b, outlier_logits, alt/ref means,
     info_seq (and per-read final features when asked).
 
     ``weights_key``: an object that is identical (``is``) from call to call exactly as long as the contents of ``flat``
     are unchanged (the model passes the version tuple of its cached inference weights).  Consecutive calls with the
-    same key, workspace and precision mode go through pmt_forward_prepared, which reuses the packed weight images."""
+    same key, workspace and precision mode go through pmt_forward_prepared, which reuses the packed weight images.
+
+    ``for_training``: when the library has a saved-forward path for this call (tf32x3 mode, shapes inside the tensor-core
+    envelopes, buffer within its budget) the pass goes through pmt_forward_train and ``out["saved"]`` holds what the
+    backward would otherwise recompute; hand it to ``backward_call``.  PERMUTECT_B200_TRAIN_SAVED=0 keeps the recompute."""
     lib = L.load()
     _require_cuda(flat)
     dev = flat.device
@@ -91,6 +96,15 @@ def forward_call(desc: L.PmtModelDesc, flat: torch.Tensor, batch, want_final: bo
         a is b if i == 1 else a == b for i, (a, b) in enumerate(zip(_PREPARED[dev], state)))
     call = lib.pmt_forward_prepared if prepared else lib.pmt_forward
     _PREPARED[dev] = None
+    saved_bytes = 0
+    if for_training and os.environ.get("PERMUTECT_B200_TRAIN_SAVED", "1") != "0":
+        saved_bytes = int(lib.pmt_train_saved_bytes(C.byref(desc), C.byref(pb)))
+    if saved_bytes > 0:
+        out["saved"] = torch.empty(saved_bytes + 256, dtype=torch.uint8, device=dev)
+        base = (out["saved"].data_ptr() + 255) & ~255
+        L.check(lib.pmt_forward_train(C.byref(desc), flat.data_ptr(), C.byref(pb), C.byref(po), ws.data_ptr(), ws.numel(),
+                                      base, saved_bytes, torch.cuda.current_stream(dev).cuda_stream))
+        return out
     L.check(call(C.byref(desc), flat.data_ptr(), C.byref(pb), C.byref(po), ws.data_ptr(), ws.numel(),
                  torch.cuda.current_stream(dev).cuda_stream))
     if weights_key is not None:
@@ -100,7 +114,7 @@ def forward_call(desc: L.PmtModelDesc, flat: torch.Tensor, batch, want_final: bo
 
 def backward_call(desc: L.PmtModelDesc, flat: torch.Tensor, batch, d_logits_bk: Optional[torch.Tensor],
                   d_alt_means: Optional[torch.Tensor], d_ref_means: Optional[torch.Tensor],
-                  info_seq: Optional[torch.Tensor] = None) -> torch.Tensor:
+                  info_seq: Optional[torch.Tensor] = None, saved: Optional[torch.Tensor] = None) -> torch.Tensor:
     """pmt_backward: gradient of the fused pass w.r.t. the flat materialised weights."""
     lib = L.load()
     _require_cuda(flat)
@@ -108,7 +122,8 @@ def backward_call(desc: L.PmtModelDesc, flat: torch.Tensor, batch, d_logits_bk: 
     pb = batch.pmt_batch()
     ptr = lambda t: None if t is None else t.contiguous().data_ptr()
     keep = [None if t is None else t.contiguous() for t in (d_logits_bk, d_alt_means, d_ref_means)]
-    pg = L.PmtOutGrads(*[None if t is None else t.data_ptr() for t in keep], None if info_seq is None else info_seq.data_ptr())
+    pg = L.PmtOutGrads(*[None if t is None else t.data_ptr() for t in keep], None if info_seq is None else info_seq.data_ptr(),
+                       None if saved is None else (saved.data_ptr() + 255) & ~255)
     d_flat = torch.empty_like(flat)
     need = lib.pmt_workspace_size(C.byref(desc), C.byref(pb), 1)
     if need == 0:
@@ -125,10 +140,12 @@ class FusedArtifactFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, flat, desc, batch):
-        out = forward_call(desc, flat, batch)
+        out = forward_call(desc, flat, batch, for_training=True)
         ctx.desc, ctx.batch = desc, batch
         ctx.save_for_backward(flat, out["logits_bk"], out["logits_b"])
         ctx.info_seq = out["info_seq"]
+        ctx.saved = out.get("saved")            # operand panels / CNN activations of the forward (None: the backward recomputes)
+        ctx.saved_mode = L.get_precision()
         return out["logits_bk"], out["alt_means"], out["ref_means"], out["logits_b"], out["outlier_logits"]
 
     @staticmethod
@@ -147,7 +164,9 @@ class FusedArtifactFunction(torch.autograd.Function):
             g[:, 1] += g_out
             g[:, 0] -= g_out * sm[:, 0]
             g[:, 2:] -= g_out[:, None] * sm[:, 1:]
-        d_flat = backward_call(ctx.desc, flat, ctx.batch, g, g_alt, g_ref, ctx.info_seq)
+        saved = ctx.saved if (ctx.saved is not None and L.get_precision() == ctx.saved_mode) else None
+        d_flat = backward_call(ctx.desc, flat, ctx.batch, g, g_alt, g_ref, ctx.info_seq, saved)
+        ctx.saved = None                        # a second backward through the same node recomputes
         return d_flat, None, None
 
 

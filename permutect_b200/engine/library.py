@@ -64,7 +64,7 @@ class PmtOutputs(C.Structure):
 
 
 class PmtOutGrads(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("d_logits_bk", "d_alt_means_be", "d_ref_means_be", "info_seq_be")]
+    _fields_ = [(n, C.c_void_p) for n in ("d_logits_bk", "d_alt_means_be", "d_ref_means_be", "info_seq_be", "saved")]
 
 
 MAX_HEAD_DIM = 32
@@ -93,7 +93,7 @@ class PmtLossGrads(C.Structure):
 
 
 EXPORTED_SYMBOLS = ["pmt_posterior_fit_step", "pmt_posterior_fit_workspace_size", "pmt_orthogonal_forward", "pmt_orthogonal_backward", "pmt_posterior_param_count", "pmt_posterior_log_posteriors", "pmt_dataset_read_indices", "pmt_pack_posterior", "pmt_adamw_step", "pmt_adamw_workspace_size", "pmt_losses_forward", "pmt_losses_backward", "pmt_losses_workspace_size", "pmt_set_cnn_trace", "pmt_set_reads_trace", "pmt_set_backward_trace", "pmt_last_error", "pmt_abi_version", "pmt_workspace_size", "pmt_forward", "pmt_forward_prepared", "pmt_backward",
-                    "pmt_decode_reads", "pmt_set_profile_events", "pmt_downsample_counts", "pmt_downsample_fill", "pmt_set_precision", "pmt_get_precision", "pmt_constraints_forward", "pmt_constraints_backward", "pmt_backward_kernels"]
+                    "pmt_decode_reads", "pmt_set_profile_events", "pmt_downsample_counts", "pmt_downsample_fill", "pmt_set_precision", "pmt_get_precision", "pmt_constraints_forward", "pmt_constraints_backward", "pmt_backward_kernels", "pmt_train_saved_bytes", "pmt_forward_train"]
 
 class PmtPosteriorDesc(C.Structure):
     _fields_ = [("n_components", C.c_int32), ("hap_start", C.c_int32), ("hap_len", C.c_int32), ("no_germline_mode", C.c_int32),
@@ -140,6 +140,11 @@ def load():
                                 C.c_void_p, C.c_size_t, C.c_void_p]
     lib.pmt_forward_prepared.restype = C.c_int
     lib.pmt_forward_prepared.argtypes = lib.pmt_forward.argtypes
+    lib.pmt_train_saved_bytes.restype = C.c_size_t
+    lib.pmt_train_saved_bytes.argtypes = [C.POINTER(PmtModelDesc), C.POINTER(PmtBatch)]
+    lib.pmt_forward_train.restype = C.c_int
+    lib.pmt_forward_train.argtypes = [C.POINTER(PmtModelDesc), C.c_void_p, C.POINTER(PmtBatch), C.POINTER(PmtOutputs),
+                                      C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.pmt_backward.restype = C.c_int
     lib.pmt_backward.argtypes = [C.POINTER(PmtModelDesc), C.c_void_p, C.POINTER(PmtBatch), C.POINTER(PmtOutGrads),
                                  C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]

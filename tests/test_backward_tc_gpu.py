@@ -166,3 +166,39 @@ def test_haplotype_cnn_backward_other_shapes_against_the_oracle(layers):
     assert not bad, "gradient error too large:\n" + "\n".join(f"{e:.3e} {n}" for e, n in bad[:25])
     cnn = [n for n in names if n.startswith("haplotypes_cnn")]
     assert cnn and all(np.abs(got[n]).max() > 0 for n in cnn)
+
+
+def test_saved_forward_and_recompute_give_the_same_outputs_and_gradients(monkeypatch):
+    """pmt_forward_train (the training forward keeps the tile list, every tile's operand panels and the CNN's activations;
+    pmt_backward skips its recompute passes) against the recompute path (PERMUTECT_B200_TRAIN_SAVED=0): same kernels over
+    the same deterministic tile list, so outputs and every gradient are BITWISE equal."""
+    import bench
+    from permutect_b200.data.batch import Batch, DownsampledBatch
+    from permutect_b200.synthetic import make_wgs_arrays
+    dev = torch.device("cuda:0")
+    model = bench.make_model(dev)
+    model.set_epoch_type(Epoch.TRAIN)
+    parent = Batch.from_arrays(*make_wgs_arrays(3000, seed=41)).copy_to(dev)
+    frac = torch.full((3000,), 0.7, device=dev)
+    batch = DownsampledBatch(parent, frac, frac, seed=9)
+    desc = model.descriptor()
+    assert L.load().pmt_train_saved_bytes(__import__("ctypes").byref(desc), __import__("ctypes").byref(batch.pmt_batch())) > 0
+
+    def run():
+        for p in model.parameters():
+            p.grad = None
+        out = model.compute_batch_output(batch)
+        model.compute_batch_losses(out, batch).total_loss.backward()
+        return (out.logits_b.detach().clone(), out.features_be.detach().clone(),
+                {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None})
+
+    logits_s, feat_s, grads_s = run()
+    monkeypatch.setenv("PERMUTECT_B200_TRAIN_SAVED", "0")
+    logits_r, feat_r, grads_r = run()
+    assert torch.equal(logits_s, logits_r) and torch.equal(feat_s, feat_r)
+    assert grads_s.keys() == grads_r.keys()
+    for k in grads_s:
+        assert torch.equal(grads_s[k], grads_r[k]), k
+    # the FP32 mode has no saved-forward path: the library says so and the call falls back
+    L.set_precision("fp32")
+    assert L.load().pmt_train_saved_bytes(__import__("ctypes").byref(desc), __import__("ctypes").byref(batch.pmt_batch())) == 0

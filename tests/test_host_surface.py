@@ -152,7 +152,7 @@ def test_ctypes_structs_match_header_sizes():
     assert ctypes.sizeof(L.PmtLinearOp) == 24 and ctypes.sizeof(L.PmtCnnOp) == 40 and ctypes.sizeof(L.PmtBlockOffsets) == 76
     assert ctypes.sizeof(L.PmtModelDesc) == 17 * 4 + 3 * 16 * 24 + 16 * 40 + 12 * 76 + 10 * 4
     assert ctypes.sizeof(L.PmtBatch) == 16 + 3 * 8 + 4 * 8 + 8 + 8 + 8 + 8
-    assert ctypes.sizeof(L.PmtOutputs) == 7 * 8 and ctypes.sizeof(L.PmtOutGrads) == 4 * 8
+    assert ctypes.sizeof(L.PmtOutputs) == 7 * 8 and ctypes.sizeof(L.PmtOutGrads) == 5 * 8
 
 
 def test_ctypes_structs_match_the_compiled_header(tmp_path):
