@@ -364,8 +364,9 @@ def run_training(args, model, ia, fa, reads, dev, world, barrier):
             "backward": ("read path: tcgen05 (recompute + TF32 data / weight gradient MMAs, pmt_tc_bwd.cu); haplotype CNN: tcgen05 "
                          "recompute with saved activations + warp-level TF32 MMAs (pmt_cnn_bwd.cu)" if pmt_lib.get_precision() != "fp32"
                          else "FP32 SIMT"),
-            "step": "device DownsampledBatch + compute_batch_output + compute_batch_losses (fused loss head) + backward + "
-                    "flat grad all-reduce + clip(1.0) + AdamW (FlatAdamW)"}
+            "step": "device DownsampledBatch + compute_batch_output (pmt_forward_train: the forward keeps the operand panels, no "
+                    "recompute in the backward) + compute_batch_losses (fused loss head) + backward + flat grad all-reduce + "
+                    "clip(1.0) + AdamW (FlatAdamW)"}
 
 
 def run_config3_single_gpu(args, model, ia, fa, reads, dev, total_variants=10_000_000, steps=3):
