@@ -140,7 +140,8 @@ class FusedArtifactFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, flat, desc, batch):
-        out = forward_call(desc, flat, batch, for_training=True)
+        # keep the forward's operands only when a backward can follow (not under no_grad, not for frozen weights)
+        out = forward_call(desc, flat, batch, for_training=bool(ctx.needs_input_grad[0]))
         ctx.desc, ctx.batch = desc, batch
         ctx.save_for_backward(flat, out["logits_bk"], out["logits_b"])
         ctx.info_seq = out["info_seq"]
