@@ -22,6 +22,7 @@
 //   reduced with warp shuffles into per-warp slots of the same private buffer.
 // TMEM per slot (256 columns): G = dL/d(residual stream) (64), D = data-gradient accumulator (64), dY operand (64),
 // dW accumulator (64).  Arithmetic: TF32 operands rounded to nearest, fp32 accumulation.
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -916,6 +917,15 @@ size_t pmt_tc_train_saved_bytes(const Plan& P, const PmtBatch* batch) {
   return S.total <= kTrainSavedBudget ? S.total : 0;
 }
 
+// The operand scratch is sized from an upper bound of the tile count (tile_bound): should the planner ever produce more
+// tiles than that, fail loudly instead of writing past the buffer.
+__global__ void check_tile_bound_kernel(const int* __restrict__ tiles, int bound) {
+  if (tiles[0] > bound) {
+    printf("permutect_b200: %d tiles planned, bound %d (pmt_tc_bwd.cu: tile_bound)\n", tiles[0], bound);
+    __trap();
+  }
+}
+
 // The training forward of the tile-sized sets: deterministic tile list, then the SAVE variant of the read kernel over ALL
 // tiles with the outputs switched on.  `image_buf`: pmt_tc_image_bytes(P) bytes (forward weight images, packed here);
 // `claim_buf`: pmt_plan_claim_bytes(B, 148) + 256 bytes of scratch for the planner.
@@ -930,6 +940,7 @@ int pmt_tc_forward_train(const Plan& P, const float* weights, const PmtBatch* ba
   int* claims = reinterpret_cast<int*>((reinterpret_cast<uintptr_t>(claim_buf) + 255) & ~uintptr_t(255));
   int n_claims = 0;
   if (pmt_plan_tiles(batch, BWD_MAXV, true, kMaxGrid, tiles, claims, &n_claims, st)) return 1;
+  check_tile_bound_kernel<<<1, 1, 0, st>>>(tiles, (int)S.bound);
   if (pmt_launch_pack_tc(P, T, weights, image, st)) return 1;
   const unsigned header[4] = {kTrainSavedMagic, (unsigned)batch->n_variants, (unsigned)S.bound, 0u};
   PMT_CUDA(cudaMemcpyAsync(saved, header, sizeof(header), cudaMemcpyHostToDevice, st));
@@ -941,7 +952,7 @@ int pmt_tc_forward_train(const Plan& P, const float* weights, const PmtBatch* ba
   TcArgs F;
   memset(&F, 0, sizeof(F));
   F.wflat = weights; F.image = image; F.tiles = tiles; F.perm = nullptr; F.batch = *batch; F.out = *out;
-  F.scratch = saved + S.scratch; F.sched = 0; F.tile_first = 0; F.tile_limit = 0x7fffffff;
+  F.scratch = saved + S.scratch; F.sched = 0; F.tile_first = 0; F.tile_limit = (int)S.bound;
   pmt_profile_begin(st);
   const int rc = pmt_launch_reads_tc_save(P, T, F, grid, st);
   pmt_profile_end(st);
