@@ -94,3 +94,34 @@ def test_downsampling_a_dataset_order_batch_matches_downsampling_the_collated_ba
         assert torch.equal(da.ref_counts, db.ref_counts) and torch.equal(da.alt_counts, db.alt_counts)
         n = int(da.ref_counts.sum() + da.alt_counts.sum())
         assert da.get_reads_re().shape[0] == n and torch.equal(da.get_reads_re(), db.get_reads_re())
+
+
+def test_parallel_copy_and_plain_slices_of_the_dataset_loader():
+    """Host logic of the ingest path without a GPU: the row-range copy the staging threads run is exact for every split, and
+    the unpinned loader yields the maps' own slices in dataset order (variant count, row count, contents)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from permutect_b200.data.reads_dataset import MemoryMappedBatches, _parallel_copy
+    from permutect_b200.synthetic import make_wgs_arrays
+    rng = np.random.default_rng(3)
+    src = rng.integers(0, 255, (10_001, 12), dtype=np.uint8)
+    with ThreadPoolExecutor(4) as pool:
+        for parts in (1, 3, 4, 7):
+            dst = np.zeros_like(src)
+            for job in _parallel_copy(pool, dst, src, parts):
+                job.result()
+            assert np.array_equal(dst, src), parts
+    ia, fa, reads = make_wgs_arrays(1000, seed=8)
+    n = ia[:, 0].astype(np.int64) + ia[:, 1].astype(np.int64)
+    rows = np.arange(int(n.sum()), dtype=np.int64)           # stand-in for dataset-order rows: only the slicing is under test
+    reads_ds = reads[rows]
+    loader = MemoryMappedBatches(ia, fa, reads_ds, 300, pin_memory=False)
+    assert len(loader) == 4
+    seen_v = seen_r = 0
+    for b in loader:
+        nv = b.size()
+        assert np.array_equal(b.int_tensor.numpy(), ia[seen_v:seen_v + nv])
+        nr = int(n[seen_v:seen_v + nv].sum())
+        assert b.reads.shape[0] == nr and np.array_equal(b.reads.numpy(), reads_ds[seen_r:seen_r + nr])
+        seen_v += nv
+        seen_r += nr
+    assert seen_v == 1000 and seen_r == int(n.sum())
